@@ -1,0 +1,261 @@
+/* semireward_b200 — C ABI of the B200-native SemiReward train-step hot path.
+ *
+ * One shared library (libsrw_b200.so, built by __graft_entry__.build()) loaded by the Python plugin through ctypes.
+ * The reference (Westlake-AI/SemiReward) is pure Python/PyTorch and has no FFI of its own ("no native
+ * code"), so every entry point below replaces a *PyTorch library call site* of the reference; each declaration cites
+ * the reference file:line whose arithmetic it takes over.  Conventions:
+ *   - extern "C", plain pointers and sizes, no torch types;
+ *   - device pointers are BORROWED from the caller (PyTorch tensors); nothing is allocated inside except through the
+ *     caller-provided workspaces;
+ *   - every call is asynchronous on the cudaStream_t passed as void* (0 = legacy default stream), no hidden syncs;
+ *   - returns 0 on success, a negative SRW_ERR_* code otherwise; srw_last_error() gives the message; never throws;
+ *   - one process per GPU, single caller thread per device.
+ *
+ * "planes" = split-bf16 operand format: an fp32 matrix X[rows, ld] stored as two bf16 planes (hi, lo),
+ * hi = bf16(X), lo = bf16(X - hi), lo plane `plane_stride` elements after the hi plane (see csrc/srw_common.cuh).
+ */
+#ifndef SRW_H_
+#define SRW_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRW_OK 0
+#define SRW_ERR_CUDA (-1)
+#define SRW_ERR_ARG (-2)
+#define SRW_ERR_UNSUPPORTED (-3)
+#define SRW_ERR_DRIVER (-4)
+
+/* ---- library ---------------------------------------------------------------------------------------------- */
+int srw_version(void);                 /* ABI version, bumped on any struct change */
+const char* srw_last_error(void);      /* message of the last failing call on this thread */
+int srw_device_check(int* sm_major, int* sm_minor, int* sm_count); /* fails unless the current device is sm_100 */
+int64_t srw_kernel_launches(void);     /* number of kernels this library has launched so far (bench.py gpu_launches) */
+
+/* ---- split-plane conversion -------------------------------------------------------------------------------- */
+/* planes[r, c] = split(x[r, c] * (row_scale ? row_scale[r / rows_per_scale] : 1)).  Used for weights once per optimizer
+ * step and for gradient tensors entering a GEMM.  transposed != 0 additionally writes planes_t[c, r] (ld = rows). */
+typedef struct {
+  const float* x; int64_t ldx;
+  int rows, cols;
+  const float* row_scale; int rows_per_scale;
+  void* planes; int64_t ldp; int64_t plane_stride;
+  void* planes_t; int64_t ldpt; int64_t plane_stride_t;
+} srw_split_args;
+int srw_split_planes(const srw_split_args* a, void* stream);
+
+/* ---- linear layers: torch.nn.functional.linear and its two backward GEMMs ----------------------------------- */
+/* D[M,N] = A[M,K] * B[N,K]^T on tcgen05 tensor cores (bf16x3, fp32 accumulate in TMEM), operands staged by TMA.
+ * Replaces F.linear in vit.py:93 (qkv), :105 (proj), :70/:73 (fc1/fc2) and autograd's dgrad / wgrad for them
+ * (param_update.py:33 loss.backward()).
+ *   a_mn_major = 0: A is stored [M, lda] (K contiguous);  1: A is stored [K, lda] (M contiguous)  (wgrad: dOut^T)
+ *   b_mn_major = 0: B is stored [N, ldb] (K contiguous);  1: B is stored [K, ldb] (N contiguous)  (wgrad: activations)
+ */
+enum srw_epilogue {
+  SRW_EPI_F32 = 0,          /* out_f32 = acc (+ bias) */
+  SRW_EPI_PLANES = 1,       /* out_planes = split(acc + bias) */
+  SRW_EPI_GELU = 2,         /* out_f32 = z = acc + bias ; out_planes = split(gelu(z))   (vit.py:70-71) */
+  SRW_EPI_RESID = 3,        /* out_f32 = resid + row_scale[row / rows_per_scale] * (acc + bias)  (vit.py:164-165 + DropPath) */
+  SRW_EPI_DGELU = 4,        /* out_planes = split(acc * gelu'(aux))  (backward of vit.py:71) */
+  SRW_EPI_SPLITK = 5        /* workspace[split, M, N] = partial acc (reduced by srw_splitk_reduce) */
+};
+enum srw_gemm_impl { SRW_GEMM_TCGEN05 = 0, SRW_GEMM_SIMT = 1 };
+
+typedef struct {
+  int M, N, K;
+  const void* a; int64_t lda; int64_t a_plane_stride; int a_mn_major;
+  const void* b; int64_t ldb; int64_t b_plane_stride; int b_mn_major;
+  int epilogue;
+  const float* bias;                          /* [N] or NULL */
+  const float* resid; int64_t ldr;            /* SRW_EPI_RESID */
+  const float* row_scale; int rows_per_scale; /* SRW_EPI_RESID; NULL = 1.0 */
+  const float* aux; int64_t ldaux;            /* SRW_EPI_DGELU: pre-activation z */
+  float* out_f32; int64_t ldo;
+  void* out_planes; int64_t ldp; int64_t out_plane_stride;
+  int split_k; float* workspace;              /* SRW_EPI_SPLITK: split_k >= 1 slices of K, workspace [split_k, M, N] */
+  int impl;                                   /* srw_gemm_impl; SIMT is the on-device verification twin */
+} srw_gemm_args;
+int srw_gemm(const srw_gemm_args* a, void* stream);
+
+/* out[M,N] (+)= sum_s workspace[s,M,N]; optionally also out_planes = split(result) */
+typedef struct {
+  const float* workspace; int split_k; int M, N;
+  float* out; int64_t ldo; int accumulate;
+} srw_splitk_reduce_args;
+int srw_splitk_reduce(const srw_splitk_reduce_args* a, void* stream);
+
+/* out[c] (+)= sum_r x[r, c]  (bias gradients).  Input either fp32 (x) or planes. */
+typedef struct {
+  const float* x; int64_t ldx;
+  const void* planes; int64_t ldp; int64_t plane_stride;
+  const float* row_scale; int rows_per_scale;
+  int rows, cols;
+  float* out; int accumulate;
+  float* workspace;  /* >= 256 * cols floats */
+} srw_colsum_args;
+int srw_colsum(const srw_colsum_args* a, void* stream);
+
+/* ---- LayerNorm (vit.py:164-165, 282: nn.LayerNorm eps 1e-6) -------------------------------------------------- */
+typedef struct {
+  const float* x; int64_t ldx; int rows, cols; float eps;
+  const float* gamma; const float* beta;
+  float* mean; float* rstd;                  /* [rows], saved for backward */
+  void* y_planes; int64_t ldp; int64_t plane_stride;   /* may be NULL */
+  float* y_f32; int64_t ldy;                 /* may be NULL */
+} srw_layernorm_fwd_args;
+int srw_layernorm_fwd(const srw_layernorm_fwd_args* a, void* stream);
+
+typedef struct {
+  const float* dy; int64_t lddy;             /* upstream grad of the LN output */
+  const float* x; int64_t ldx; int rows, cols;
+  const float* gamma; const float* mean; const float* rstd;
+  float* dx; int64_t lddx; int accumulate_dx;  /* dx (+)= LN backward */
+  float* dgamma; float* dbeta; int accumulate_dparams;
+  float* workspace;                          /* >= 2 * 256 * cols floats */
+} srw_layernorm_bwd_args;
+int srw_layernorm_bwd(const srw_layernorm_bwd_args* a, void* stream);
+
+/* ---- attention (vit.py:100-104: softmax(q k^T * scale) v, per image and head) --------------------------------- */
+/* qkv planes are token-major [B*N, 3*D] exactly as the qkv Linear produces them (vit.py:93-98 does the head split
+ * with reshape/permute; here the kernel indexes heads in place).  o planes [B*N, D].  lse [B, H, N]. */
+typedef struct {
+  int B, N, H, head_dim; float scale;
+  const void* qkv; int64_t ld_qkv; int64_t qkv_plane_stride;
+  void* o; int64_t ld_o; int64_t o_plane_stride;
+  float* lse;
+} srw_attn_fwd_args;
+int srw_attn_fwd(const srw_attn_fwd_args* a, void* stream);
+
+typedef struct {
+  int B, N, H, head_dim; float scale;
+  const void* qkv; int64_t ld_qkv; int64_t qkv_plane_stride;
+  const void* o; int64_t ld_o; int64_t o_plane_stride;
+  const void* d_o; int64_t ld_do; int64_t do_plane_stride;
+  const float* lse;
+  float* delta;                               /* scratch [B, H, N] */
+  void* dqkv; int64_t ld_dqkv; int64_t dqkv_plane_stride;
+} srw_attn_bwd_args;
+int srw_attn_bwd(const srw_attn_bwd_args* a, void* stream);
+
+/* ---- ViT engine: the whole backbone forward / backward as one native call ------------------------------------ */
+/* Mirrors VisionTransformer.forward (vit.py:277-306).  Parameters stay PyTorch-owned fp32 tensors in nn.Linear layout;
+ * `params` / `grads` are arrays of device pointers in state_dict order (cls_token, pos_embed, patch_embed.proj.weight,
+ * patch_embed.proj.bias, then per block norm1.w, norm1.b, qkv.w, qkv.b, proj.w, proj.b, norm2.w, norm2.b, fc1.w,
+ * fc1.b, fc2.w, fc2.b, then norm.w, norm.b, head.w, head.b  = 4 + 12*depth + 4 pointers). */
+typedef struct {
+  int img_size, patch_size, in_chans, embed_dim, depth, num_heads, hidden_dim, num_classes;
+  float ln_eps;
+} srw_vit_config;
+
+int64_t srw_vit_weight_planes_bytes(const srw_vit_config* c);           /* split (+transposed) weight cache */
+int64_t srw_vit_workspace_bytes(const srw_vit_config* c, int batch, int grad_batch);
+
+/* Refresh the split-plane weight cache from the fp32 parameters (call after every optimizer step). */
+int srw_vit_prepare_weights(const srw_vit_config* c, const float* const* params, void* weight_planes, void* stream);
+
+typedef struct {
+  const srw_vit_config* cfg;
+  const float* const* params;
+  const void* weight_planes;
+  const float* x; int batch;                  /* [batch, C, H, W] fp32 NCHW */
+  int grad_batch;                             /* the first grad_batch images will be back-propagated (activations kept) */
+  const float* drop_scale;                    /* [depth, 2, batch] DropPath multipliers mask/keep, or NULL */
+  float* logits; float* feat;                 /* [batch, num_classes], [batch, embed_dim] */
+  void* workspace; int64_t workspace_bytes;
+  int gemm_impl;
+} srw_vit_fwd_args;
+int srw_vit_forward(const srw_vit_fwd_args* a, void* stream);
+
+typedef struct {
+  const srw_vit_config* cfg;
+  const float* const* params;
+  const void* weight_planes;
+  const float* x; int batch; int grad_batch;
+  const float* drop_scale;
+  const float* dlogits; const float* dfeat;   /* [grad_batch, C] and [grad_batch, D] (dfeat may be NULL) */
+  float* const* grads;                        /* same order as params; gradients are ACCUMULATED (+=) */
+  void* workspace; int64_t workspace_bytes;
+  int gemm_impl;
+} srw_vit_bwd_args;
+int srw_vit_backward(const srw_vit_bwd_args* a, void* stream);
+
+/* ---- fused SSL epilogue (the a6-a12 rows of SURVEY.md §8a) ---------------------------------------------------- */
+/* Rewarder.forward (semireward.py:52-72): reward[b] in (0,1), one CTA, softmax over the 2B rows done on chip.
+ * rp = 17 device pointers in Rewarder.state_dict order. */
+typedef struct {
+  int B, feature_dim, label_rows;
+  const float* const* rp;
+  const float* feats; int64_t ld_feats;
+  const int64_t* labels;
+  float* reward;                               /* [B] */
+  float* workspace;                            /* >= srw_rewarder_workspace_floats(B) */
+} srw_rewarder_fwd_args;
+int64_t srw_rewarder_workspace_floats(int B, int feature_dim);
+int srw_rewarder_fwd(const srw_rewarder_fwd_args* a, void* stream);
+
+/* Generator.forward (semireward.py:21-24) followed by .long() (srflexmatch.py:157-158): integer fake labels. */
+typedef struct {
+  int B, feature_dim;
+  const float* const* gp;                      /* 8 pointers, Generator.state_dict order */
+  const float* feats; int64_t ld_feats;
+  int64_t* labels;                             /* [B] */
+  float* workspace;                            /* >= B * 448 floats */
+} srw_generator_fwd_args;
+int srw_generator_fwd(const srw_generator_fwd_args* a, void* stream);
+
+/* Rewarder training step (srflexmatch.py:173-208): reward = R(feats, gen_label); target = (gen==true ? 1 : .5)
+ * (== cosine_similarity_n of the two one-hots, semireward.py:130-139); grads of MSE(reward,1) + MSE(reward,target);
+ * one torch.optim.Adam step (lr, betas .9/.999, eps 1e-8) on the 17 Rewarder tensors.  m/v = Adam moments, same order. */
+typedef struct {
+  int B, feature_dim, label_rows, num_classes;
+  float* const* rp; float* const* m; float* const* v;
+  const float* feats; int64_t ld_feats;
+  const int64_t* gen_labels; const int64_t* true_labels;
+  float lr; int step;                          /* step = t (1-based) for bias correction */
+  float* losses;                               /* [2] generator_loss, rewarder_loss */
+  float* workspace;                            /* >= srw_rewarder_train_workspace_floats(...) */
+} srw_rewarder_train_args;
+int64_t srw_rewarder_train_workspace_floats(int B, int feature_dim, int label_rows);
+int srw_rewarder_train(const srw_rewarder_train_args* a, void* stream);
+
+/* FlexMatch step epilogue: everything between the backbone outputs and dlogits in SRFlexMatch.train_step
+ * (srflexmatch.py:132-152, 210; srflexmatch/utils.py:23-63; hooks/pseudo_label.py:40; consistency.py:13-45;
+ * cross_entropy.py:11-31).  One CTA.  Device-resident hook state replaces the host Counter (utils.py:25-29):
+ * hist[c+1] = #entries of selected_label equal to c is maintained incrementally. */
+typedef struct {
+  int B_lb, B_ulb, num_classes, ulb_dest_len;
+  const float* logits_lb; const float* logits_w; const float* logits_s; int64_t ld_logits;
+  const int64_t* y_lb; const int64_t* idx_ulb;
+  float p_cutoff; int thresh_warmup; float lambda_u;
+  int64_t* selected_label;  /* [ulb_dest_len] hook state, -1 = unused */
+  int32_t* hist;            /* [num_classes + 1] hook state: hist[0] counts the -1 bucket */
+  float* classwise_acc;     /* [num_classes] hook state */
+  const float* reward;      /* [B_ulb] or NULL (stage 1); when given mask2 = reward >= mean(reward) */
+  int mask_only;            /* 1: only run the hook (mask, pseudo, state update), no losses (data_generator replays) */
+  const float* mask_in;     /* optional: use this mask instead of running the hook (stage-2 final pass) */
+  float* probs_w;           /* [B_ulb, C] out */
+  int64_t* pseudo;          /* [B_ulb] out */
+  float* mask; float* mask2;/* [B_ulb] out */
+  float* losses;            /* [4] sup, unsup, total, util_ratio */
+  float* dlogits_lb; float* dlogits_s; int64_t ld_dlogits; /* d total / d logits, may be NULL */
+} srw_flexmatch_epilogue_args;
+int srw_flexmatch_epilogue(const srw_flexmatch_epilogue_args* a, void* stream);
+
+/* ---- optimizer: torch.optim.AdamW over the reference's layer-decay groups (build.py:193-224) ------------------- */
+typedef struct {
+  int num_tensors;
+  float* const* params; const float* const* grads; float* const* exp_avg; float* const* exp_avg_sq;
+  const int64_t* numel; const float* lr; const float* weight_decay;  /* per tensor (lr already includes schedule) */
+  float beta1, beta2, eps; int step; int zero_grads;
+  void* device_table;       /* >= srw_adamw_table_bytes(num_tensors), device memory for the pointer table */
+} srw_adamw_args;
+int64_t srw_adamw_table_bytes(int num_tensors);
+int srw_adamw_step(const srw_adamw_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRW_H_ */

@@ -1,0 +1,187 @@
+"""ctypes binding of libsrw_b200.so (include/srw.h).  The library is the product: if it cannot be loaded this module
+raises — there is no CPU or PyTorch fallback anywhere in semireward_b200."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsrw_b200.so")
+
+c_f32p = C.c_void_p
+i64 = C.c_int64
+i32 = C.c_int
+f32 = C.c_float
+vp = C.c_void_p
+
+# enums (include/srw.h)
+EPI_F32, EPI_PLANES, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_SPLITK = range(6)
+GEMM_TCGEN05, GEMM_SIMT = 0, 1
+
+
+class SplitArgs(C.Structure):
+    _fields_ = [("x", vp), ("ldx", i64), ("rows", i32), ("cols", i32), ("row_scale", vp), ("rows_per_scale", i32),
+                ("planes", vp), ("ldp", i64), ("plane_stride", i64), ("planes_t", vp), ("ldpt", i64), ("plane_stride_t", i64)]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("M", i32), ("N", i32), ("K", i32),
+                ("a", vp), ("lda", i64), ("a_plane_stride", i64), ("a_mn_major", i32),
+                ("b", vp), ("ldb", i64), ("b_plane_stride", i64), ("b_mn_major", i32),
+                ("epilogue", i32), ("bias", vp), ("resid", vp), ("ldr", i64), ("row_scale", vp), ("rows_per_scale", i32),
+                ("aux", vp), ("ldaux", i64), ("out_f32", vp), ("ldo", i64), ("out_planes", vp), ("ldp", i64),
+                ("out_plane_stride", i64), ("split_k", i32), ("workspace", vp), ("impl", i32)]
+
+
+class SplitKReduceArgs(C.Structure):
+    _fields_ = [("workspace", vp), ("split_k", i32), ("M", i32), ("N", i32), ("out", vp), ("ldo", i64), ("accumulate", i32)]
+
+
+class ColsumArgs(C.Structure):
+    _fields_ = [("x", vp), ("ldx", i64), ("planes", vp), ("ldp", i64), ("plane_stride", i64), ("row_scale", vp),
+                ("rows_per_scale", i32), ("rows", i32), ("cols", i32), ("out", vp), ("accumulate", i32), ("workspace", vp)]
+
+
+class LayerNormFwdArgs(C.Structure):
+    _fields_ = [("x", vp), ("ldx", i64), ("rows", i32), ("cols", i32), ("eps", f32), ("gamma", vp), ("beta", vp),
+                ("mean", vp), ("rstd", vp), ("y_planes", vp), ("ldp", i64), ("plane_stride", i64), ("y_f32", vp), ("ldy", i64)]
+
+
+class LayerNormBwdArgs(C.Structure):
+    _fields_ = [("dy", vp), ("lddy", i64), ("x", vp), ("ldx", i64), ("rows", i32), ("cols", i32), ("gamma", vp), ("mean", vp),
+                ("rstd", vp), ("dx", vp), ("lddx", i64), ("accumulate_dx", i32), ("dgamma", vp), ("dbeta", vp),
+                ("accumulate_dparams", i32), ("workspace", vp)]
+
+
+class AttnFwdArgs(C.Structure):
+    _fields_ = [("B", i32), ("N", i32), ("H", i32), ("head_dim", i32), ("scale", f32), ("qkv", vp), ("ld_qkv", i64),
+                ("qkv_plane_stride", i64), ("o", vp), ("ld_o", i64), ("o_plane_stride", i64), ("lse", vp)]
+
+
+class AttnBwdArgs(C.Structure):
+    _fields_ = [("B", i32), ("N", i32), ("H", i32), ("head_dim", i32), ("scale", f32), ("qkv", vp), ("ld_qkv", i64),
+                ("qkv_plane_stride", i64), ("o", vp), ("ld_o", i64), ("o_plane_stride", i64), ("d_o", vp), ("ld_do", i64),
+                ("do_plane_stride", i64), ("lse", vp), ("delta", vp), ("dqkv", vp), ("ld_dqkv", i64), ("dqkv_plane_stride", i64)]
+
+
+class VitConfig(C.Structure):
+    _fields_ = [("img_size", i32), ("patch_size", i32), ("in_chans", i32), ("embed_dim", i32), ("depth", i32),
+                ("num_heads", i32), ("hidden_dim", i32), ("num_classes", i32), ("ln_eps", f32)]
+
+
+class VitFwdArgs(C.Structure):
+    _fields_ = [("cfg", C.POINTER(VitConfig)), ("params", C.POINTER(vp)), ("weight_planes", vp), ("x", vp), ("batch", i32),
+                ("grad_batch", i32), ("drop_scale", vp), ("logits", vp), ("feat", vp), ("workspace", vp),
+                ("workspace_bytes", i64), ("gemm_impl", i32)]
+
+
+class VitBwdArgs(C.Structure):
+    _fields_ = [("cfg", C.POINTER(VitConfig)), ("params", C.POINTER(vp)), ("weight_planes", vp), ("x", vp), ("batch", i32),
+                ("grad_batch", i32), ("drop_scale", vp), ("dlogits", vp), ("dfeat", vp), ("grads", C.POINTER(vp)),
+                ("workspace", vp), ("workspace_bytes", i64), ("gemm_impl", i32)]
+
+
+class RewarderFwdArgs(C.Structure):
+    _fields_ = [("B", i32), ("feature_dim", i32), ("label_rows", i32), ("rp", C.POINTER(vp)), ("feats", vp), ("ld_feats", i64),
+                ("labels", vp), ("reward", vp), ("workspace", vp)]
+
+
+class GeneratorFwdArgs(C.Structure):
+    _fields_ = [("B", i32), ("feature_dim", i32), ("gp", C.POINTER(vp)), ("feats", vp), ("ld_feats", i64), ("labels", vp),
+                ("workspace", vp)]
+
+
+class RewarderTrainArgs(C.Structure):
+    _fields_ = [("B", i32), ("feature_dim", i32), ("label_rows", i32), ("num_classes", i32), ("rp", C.POINTER(vp)),
+                ("m", C.POINTER(vp)), ("v", C.POINTER(vp)), ("feats", vp), ("ld_feats", i64), ("gen_labels", vp),
+                ("true_labels", vp), ("lr", f32), ("step", i32), ("losses", vp), ("workspace", vp)]
+
+
+class FlexMatchEpilogueArgs(C.Structure):
+    _fields_ = [("B_lb", i32), ("B_ulb", i32), ("num_classes", i32), ("ulb_dest_len", i32), ("logits_lb", vp), ("logits_w", vp),
+                ("logits_s", vp), ("ld_logits", i64), ("y_lb", vp), ("idx_ulb", vp), ("p_cutoff", f32), ("thresh_warmup", i32),
+                ("lambda_u", f32), ("selected_label", vp), ("hist", vp), ("classwise_acc", vp), ("reward", vp),
+                ("mask_only", i32), ("mask_in", vp), ("probs_w", vp), ("pseudo", vp), ("mask", vp), ("mask2", vp),
+                ("losses", vp), ("dlogits_lb", vp), ("dlogits_s", vp), ("ld_dlogits", i64)]
+
+
+class AdamWArgs(C.Structure):
+    _fields_ = [("num_tensors", i32), ("params", C.POINTER(vp)), ("grads", C.POINTER(vp)), ("exp_avg", C.POINTER(vp)),
+                ("exp_avg_sq", C.POINTER(vp)), ("numel", C.POINTER(i64)), ("lr", C.POINTER(f32)), ("weight_decay", C.POINTER(f32)),
+                ("beta1", f32), ("beta2", f32), ("eps", f32), ("step", i32), ("zero_grads", i32), ("device_table", vp)]
+
+
+# every symbol include/srw.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("srw_version", i32, []),
+    ("srw_last_error", C.c_char_p, []),
+    ("srw_device_check", i32, [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+    ("srw_kernel_launches", i64, []),
+    ("srw_split_planes", i32, [C.POINTER(SplitArgs), vp]),
+    ("srw_gemm", i32, [C.POINTER(GemmArgs), vp]),
+    ("srw_splitk_reduce", i32, [C.POINTER(SplitKReduceArgs), vp]),
+    ("srw_colsum", i32, [C.POINTER(ColsumArgs), vp]),
+    ("srw_layernorm_fwd", i32, [C.POINTER(LayerNormFwdArgs), vp]),
+    ("srw_layernorm_bwd", i32, [C.POINTER(LayerNormBwdArgs), vp]),
+    ("srw_attn_fwd", i32, [C.POINTER(AttnFwdArgs), vp]),
+    ("srw_attn_bwd", i32, [C.POINTER(AttnBwdArgs), vp]),
+    ("srw_vit_weight_planes_bytes", i64, [C.POINTER(VitConfig)]),
+    ("srw_vit_workspace_bytes", i64, [C.POINTER(VitConfig), i32, i32]),
+    ("srw_vit_prepare_weights", i32, [C.POINTER(VitConfig), C.POINTER(vp), vp, vp]),
+    ("srw_vit_forward", i32, [C.POINTER(VitFwdArgs), vp]),
+    ("srw_vit_backward", i32, [C.POINTER(VitBwdArgs), vp]),
+    ("srw_rewarder_workspace_floats", i64, [i32, i32]),
+    ("srw_rewarder_fwd", i32, [C.POINTER(RewarderFwdArgs), vp]),
+    ("srw_generator_fwd", i32, [C.POINTER(GeneratorFwdArgs), vp]),
+    ("srw_rewarder_train_workspace_floats", i64, [i32, i32, i32]),
+    ("srw_rewarder_train", i32, [C.POINTER(RewarderTrainArgs), vp]),
+    ("srw_flexmatch_epilogue", i32, [C.POINTER(FlexMatchEpilogueArgs), vp]),
+    ("srw_adamw_table_bytes", i64, [i32]),
+    ("srw_adamw_step", i32, [C.POINTER(AdamWArgs), vp]),
+]
+
+_lib = None
+
+
+class SrwError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """dlopen the library (building is __graft_entry__.build()'s job; a missing .so is a hard error)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise SrwError(f"{LIB_PATH} not found: run `python -m semireward_b200.build` (or __graft_entry__.build()). "
+                       "semireward_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError if the header and the library drift apart
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().srw_last_error()
+        raise SrwError(f"{what} failed with code {rc}: {msg.decode() if msg else ''}")
+
+
+def ptr(t) -> int:
+    """device pointer of a torch tensor (or None)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr_array(tensors):
+    arr = (vp * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr

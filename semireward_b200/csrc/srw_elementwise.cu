@@ -1,0 +1,308 @@
+// srw_elementwise — HBM-bound kernels around the GEMMs: split-plane conversion, split-K reduce, column sums (bias
+// gradients), LayerNorm forward/backward (vit.py:164-165,282), patch embedding (vit.py:39-44, 279-280) and the
+// final-norm + head (vit.py:282, 298, 304) with their backward.  All fp32 math, coalesced row-major accesses,
+// deterministic two-stage reductions (no float atomics).
+#include <atomic>
+
+#include "../../include/srw.h"
+#include "srw_common.cuh"
+
+namespace srw {
+extern std::atomic<int64_t> g_launches;
+
+// ------------------------------------------------------------------------------------------------
+// split planes (+ optional transposed copy)
+// ------------------------------------------------------------------------------------------------
+__global__ void split_planes_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols,
+                                    const float* __restrict__ row_scale, int rows_per_scale,
+                                    __nv_bfloat16* __restrict__ planes, int64_t ldp, int64_t ps,
+                                    __nv_bfloat16* __restrict__ planes_t, int64_t ldpt, int64_t pst) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = x[(int64_t)r * ldx + c];
+      if (row_scale) v *= row_scale[r / rows_per_scale];
+      if (planes) {
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        planes[(int64_t)r * ldp + c] = h;
+        planes[(int64_t)r * ldp + c + ps] = l;
+      }
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  if (planes_t == nullptr) return;
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;  // output row = c, output col = r
+    if (c < cols && r < rows) {
+      __nv_bfloat16 h, l;
+      split_bf16(tile[threadIdx.x][i], h, l);
+      planes_t[(int64_t)c * ldpt + r] = h;
+      planes_t[(int64_t)c * ldpt + r + pst] = l;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// split-K reduce
+// ------------------------------------------------------------------------------------------------
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int split, int M, int N, float* __restrict__ out, int64_t ldo,
+                                     int accumulate) {
+  const int64_t total4 = (int64_t)M * N / 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i * 4;
+    const int m = (int)(e / N), n = (int)(e % N);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < split; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(ws + (int64_t)s * M * N + e);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float4* dst = reinterpret_cast<float4*>(out + (int64_t)m * ldo + n);
+    if (accumulate) {
+      const float4 o = *dst;
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    *dst = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums: out[c] (+)= sum_r scale(r) * x[r,c]
+// ------------------------------------------------------------------------------------------------
+__global__ void colsum_stage1_kernel(const float* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ planes,
+                                     int64_t ldp, int64_t ps, const float* __restrict__ row_scale, int rows_per_scale, int rows,
+                                     int cols, float* __restrict__ partial) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (c < cols) {
+    for (int r = blockIdx.y * 8 + ty; r < rows; r += 8 * gridDim.y) {
+      float v = x ? x[(int64_t)r * ldx + c] : plane_value(planes, ps, (int64_t)r * ldp + c);
+      if (row_scale) v *= row_scale[r / rows_per_scale];
+      acc += v;
+    }
+  }
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][tx];
+    partial[(int64_t)blockIdx.y * cols + c] = s;
+  }
+}
+__global__ void colsum_stage2_kernel(const float* __restrict__ partial, int nparts, int cols, float* __restrict__ out, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += partial[(int64_t)p * cols + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward: one warp per row
+// ------------------------------------------------------------------------------------------------
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, float eps,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ mean_out,
+                                     float* __restrict__ rstd_out, __nv_bfloat16* __restrict__ yp, int64_t ldp, int64_t ps,
+                                     float* __restrict__ yf, int64_t ldy) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + (int64_t)row * ldx;
+  float s = 0.f;
+  for (int c = lane * 4; c < cols; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = warp_sum(s) / (float)cols;
+  float q = 0.f;
+  for (int c = lane * 4; c < cols; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    const float a = v.x - mean, b = v.y - mean, cc = v.z - mean, d = v.w - mean;
+    q += (a * a + b * b) + (cc * cc + d * d);
+  }
+  const float var = warp_sum(q) / (float)cols;
+  const float rstd = rsqrtf(var + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  for (int c = lane * 4; c < cols; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 b = *reinterpret_cast<const float4*>(beta + c);
+    float4 y;
+    y.x = (v.x - mean) * rstd * g.x + b.x;
+    y.y = (v.y - mean) * rstd * g.y + b.y;
+    y.z = (v.z - mean) * rstd * g.z + b.z;
+    y.w = (v.w - mean) * rstd * g.w + b.w;
+    if (yf) *reinterpret_cast<float4*>(yf + (int64_t)row * ldy + c) = y;
+    if (yp) {
+      uint32_t h0, l0, h1, l1;
+      split2(y.x, y.y, h0, l0);
+      split2(y.z, y.w, h1, l1);
+      __nv_bfloat16* hp = yp + (int64_t)row * ldp + c;
+      *reinterpret_cast<uint2*>(hp) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(hp + ps) = make_uint2(l0, l1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  Block = 8 warps, each warp walks rows (stride 8*gridDim.x); per-lane column partials of
+// dgamma/dbeta stay in registers (J = cols/32 columns per lane, column = lane + 32*j -> coalesced), reduced across
+// the block through shared memory into partial[blockIdx.x][2][cols]; a second kernel folds the partials.
+// ------------------------------------------------------------------------------------------------
+template <int J>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ x,
+                                                            int64_t ldx, int rows, const float* __restrict__ gamma,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            float* __restrict__ dx, int64_t lddx, int accumulate_dx,
+                                                            float* __restrict__ partial) {
+  constexpr int COLS = J * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float pg[J], pb[J], gm[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) { pg[j] = 0.f; pb[j] = 0.f; gm[j] = gamma[lane + 32 * j]; }
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += 8 * gridDim.x) {
+    const float mu = mean[row], rs = rstd[row];
+    const float* dyr = dy + (int64_t)row * lddy;
+    const float* xr = x + (int64_t)row * ldx;
+    float g[J], xh[J];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const float d = dyr[lane + 32 * j];
+      xh[j] = (xr[lane + 32 * j] - mu) * rs;
+      g[j] = d * gm[j];
+      s1 += g[j];
+      s2 += g[j] * xh[j];
+      pg[j] += d * xh[j];
+      pb[j] += d;
+    }
+    s1 = warp_sum(s1) * (1.0f / COLS);
+    s2 = warp_sum(s2) * (1.0f / COLS);
+    float* dxr = dx + (int64_t)row * lddx;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const float v = rs * (g[j] - s1 - xh[j] * s2);
+      dxr[lane + 32 * j] = accumulate_dx ? dxr[lane + 32 * j] + v : v;
+    }
+  }
+  __shared__ float red[8][COLS];
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < J; ++j) red[warp][lane + 32 * j] = pass == 0 ? pg[j] : pb[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < COLS; c += 256) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][c];
+      partial[((int64_t)blockIdx.x * 2 + pass) * COLS + c] = s;
+    }
+  }
+}
+
+__global__ void layernorm_bwd_params_kernel(const float* __restrict__ partial, int nparts, int cols, float* __restrict__ dgamma,
+                                            float* __restrict__ dbeta, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float sg = 0.f, sb = 0.f;
+  for (int p = 0; p < nparts; ++p) {
+    sg += partial[((int64_t)p * 2 + 0) * cols + c];
+    sb += partial[((int64_t)p * 2 + 1) * cols + c];
+  }
+  dgamma[c] = accumulate ? dgamma[c] + sg : sg;
+  dbeta[c] = accumulate ? dbeta[c] + sb : sb;
+}
+
+}  // namespace srw
+
+using namespace srw;
+
+extern "C" int srw_split_planes(const srw_split_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SRW_REQUIRE(a && a->x && a->rows > 0 && a->cols > 0 && (a->planes || a->planes_t), "srw_split_planes: bad args");
+  dim3 grid(cdiv(a->cols, 32), cdiv(a->rows, 32)), block(32, 8);
+  split_planes_kernel<<<grid, block, 0, stream>>>(a->x, a->ldx, a->rows, a->cols, a->row_scale, a->rows_per_scale > 0 ? a->rows_per_scale : 1,
+                                                 reinterpret_cast<__nv_bfloat16*>(a->planes), a->ldp, a->plane_stride,
+                                                 reinterpret_cast<__nv_bfloat16*>(a->planes_t), a->ldpt, a->plane_stride_t);
+  g_launches++;
+  SRW_LAUNCH_CHECK();
+  return SRW_OK;
+}
+
+extern "C" int srw_splitk_reduce(const srw_splitk_reduce_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SRW_REQUIRE(a && a->workspace && a->out && a->split_k >= 1 && a->N % 4 == 0 && a->ldo % 4 == 0, "srw_splitk_reduce: bad args");
+  const int64_t total4 = (int64_t)a->M * a->N / 4;
+  const int blocks = (int)std::min<int64_t>(cdiv64(total4, 256), 148 * 8);
+  splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(a->workspace, a->split_k, a->M, a->N, a->out, a->ldo, a->accumulate);
+  g_launches++;
+  SRW_LAUNCH_CHECK();
+  return SRW_OK;
+}
+
+extern "C" int srw_colsum(const srw_colsum_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SRW_REQUIRE(a && (a->x || a->planes) && a->out && a->workspace && a->rows > 0 && a->cols > 0, "srw_colsum: bad args");
+  const int nparts = std::min(256, cdiv(a->rows, 8));
+  dim3 grid(cdiv(a->cols, 32), nparts);
+  colsum_stage1_kernel<<<grid, 256, 0, stream>>>(a->x, a->ldx, reinterpret_cast<const __nv_bfloat16*>(a->planes), a->ldp, a->plane_stride,
+                                                a->row_scale, a->rows_per_scale > 0 ? a->rows_per_scale : 1, a->rows, a->cols, a->workspace);
+  g_launches++;
+  SRW_LAUNCH_CHECK();
+  colsum_stage2_kernel<<<cdiv(a->cols, 128), 128, 0, stream>>>(a->workspace, nparts, a->cols, a->out, a->accumulate);
+  g_launches++;
+  SRW_LAUNCH_CHECK();
+  return SRW_OK;
+}
+
+extern "C" int srw_layernorm_fwd(const srw_layernorm_fwd_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SRW_REQUIRE(a && a->x && a->gamma && a->beta && a->rows > 0 && a->cols > 0 && a->cols % 4 == 0 && a->ldx % 4 == 0,
+              "srw_layernorm_fwd: bad args (cols %% 4 == 0 required)");
+  SRW_REQUIRE(!a->y_planes || a->ldp % 4 == 0, "srw_layernorm_fwd: ldp %% 4");
+  SRW_REQUIRE(!a->y_f32 || a->ldy % 4 == 0, "srw_layernorm_fwd: ldy %% 4");
+  layernorm_fwd_kernel<<<cdiv(a->rows, 8), 256, 0, stream>>>(a->x, a->ldx, a->rows, a->cols, a->eps, a->gamma, a->beta, a->mean, a->rstd,
+                                                            reinterpret_cast<__nv_bfloat16*>(a->y_planes), a->ldp, a->plane_stride,
+                                                            a->y_f32, a->ldy);
+  g_launches++;
+  SRW_LAUNCH_CHECK();
+  return SRW_OK;
+}
+
+extern "C" int srw_layernorm_bwd(const srw_layernorm_bwd_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SRW_REQUIRE(a && a->dy && a->x && a->gamma && a->mean && a->rstd && a->dx && a->workspace && a->rows > 0, "srw_layernorm_bwd: bad args");
+  SRW_REQUIRE(a->cols % 32 == 0 && a->cols <= 1024, "srw_layernorm_bwd: cols must be a multiple of 32 and <= 1024 (cols=%d)", a->cols);
+  const int nblocks = std::min(256, cdiv(a->rows, 8));
+#define SRW_LN_BWD(J)                                                                                                             \
+  case J:                                                                                                                         \
+    layernorm_bwd_kernel<J><<<nblocks, 256, 0, stream>>>(a->dy, a->lddy, a->x, a->ldx, a->rows, a->gamma, a->mean, a->rstd, a->dx, \
+                                                         a->lddx, a->accumulate_dx, a->workspace);                                \
+    break;
+  switch (a->cols / 32) {
+    SRW_LN_BWD(2) SRW_LN_BWD(4) SRW_LN_BWD(6) SRW_LN_BWD(8) SRW_LN_BWD(12) SRW_LN_BWD(16) SRW_LN_BWD(24) SRW_LN_BWD(32)
+    default:
+      set_last_error("srw_layernorm_bwd: unsupported cols=%d", a->cols);
+      return SRW_ERR_UNSUPPORTED;
+  }
+#undef SRW_LN_BWD
+  g_launches++;
+  SRW_LAUNCH_CHECK();
+  if (a->dgamma && a->dbeta) {
+    layernorm_bwd_params_kernel<<<cdiv(a->cols, 128), 128, 0, stream>>>(a->workspace, nblocks, a->cols, a->dgamma, a->dbeta, a->accumulate_dparams);
+    g_launches++;
+    SRW_LAUNCH_CHECK();
+  }
+  return SRW_OK;
+}

@@ -1,0 +1,435 @@
+// srw_gemm — D[M,N] = A[M,K] * B[N,K]^T for the reference's nn.Linear call sites (vit.py:93,105,70,73) and their
+// dgrad / wgrad, on sm_100a tensor cores:
+//   TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared memory -> tcgen05.mma kind::f16 (bf16 x bf16, fp32 accumulate in
+//   TMEM) -> tcgen05.ld -> fused epilogue -> global.
+// Operands are "split planes" (srw_common.cuh): per 64-wide K block the kernel stages A_hi, A_lo, B_hi, B_lo once and
+// issues three MMAs (hi*hi, hi*lo, lo*hi) into the same accumulator.
+//
+// Roles (one 128x128 output tile per CTA, 256 threads):
+//   warp 0  : TMA producer (one elected lane)          warp 2 : TMEM allocator / deallocator
+//   warp 1  : MMA issuer  (one elected lane)           warps 4-7 : epilogue (thread == accumulator row == TMEM lane)
+// A SIMT kernel over the same operands and the same epilogue code is kept as the on-device verification twin
+// (srw_gemm_args.impl = SRW_GEMM_SIMT); it is a debugging aid, never the default path.
+#include <cuda.h>
+
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/srw.h"
+#include "srw_common.cuh"
+
+namespace srw {
+
+extern std::atomic<int64_t> g_launches;
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int PLANE_TILE_BYTES = 128 * BK * 2;         // 16 KiB: one 128 x 64 bf16 tile
+constexpr int STAGE_BYTES = 4 * PLANE_TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
+constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 128;
+
+struct EpiParams {
+  int M, N;
+  int epilogue;
+  const float* bias;
+  const float* resid; int64_t ldr;
+  const float* row_scale; int rows_per_scale;
+  const float* aux; int64_t ldaux;
+  float* out_f32; int64_t ldo;
+  __nv_bfloat16* out_planes; int64_t ldp; int64_t out_plane_stride;
+  float* workspace;  // split-K partials [split, M, N]
+};
+
+// Apply the fused epilogue to NV consecutive accumulator columns of one row.  NV is 32 (tcgen05 path: one tcgen05.ld
+// chunk) or 4 (SIMT twin); col0 % NV == 0, N % 4 == 0 (checked on the host).
+template <int NV>
+__device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int col0, float (&v)[NV], int split) {
+  if (row >= p.M) return;
+  const int epi = p.epilogue;
+  if (epi == SRW_EPI_SPLITK) {
+    float* dst = p.workspace + ((int64_t)split * p.M + row) * p.N + col0;
+#pragma unroll
+    for (int j = 0; j < NV; j += 4)
+      if (col0 + j < p.N) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    return;
+  }
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < NV; j += 4)
+      if (col0 + j < p.N) {
+        const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + j);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+  }
+  if (epi == SRW_EPI_RESID) {
+    const float s = p.row_scale ? p.row_scale[row / p.rows_per_scale] : 1.0f;
+    const float* r = p.resid + (int64_t)row * p.ldr + col0;
+    float* dst = p.out_f32 + (int64_t)row * p.ldo + col0;
+#pragma unroll
+    for (int j = 0; j < NV; j += 4)
+      if (col0 + j < p.N) {
+        const float4 rr = *reinterpret_cast<const float4*>(r + j);
+        *reinterpret_cast<float4*>(dst + j) =
+            make_float4(rr.x + s * v[j], rr.y + s * v[j + 1], rr.z + s * v[j + 2], rr.w + s * v[j + 3]);
+      }
+    return;
+  }
+  if (epi == SRW_EPI_F32 || epi == SRW_EPI_GELU) {
+    float* dst = p.out_f32 + (int64_t)row * p.ldo + col0;
+#pragma unroll
+    for (int j = 0; j < NV; j += 4)
+      if (col0 + j < p.N) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    if (epi == SRW_EPI_F32) return;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = gelu_f(v[j]);
+  }
+  if (epi == SRW_EPI_DGELU) {
+    const float* z = p.aux + (int64_t)row * p.ldaux + col0;
+#pragma unroll
+    for (int j = 0; j < NV; j += 4)
+      if (col0 + j < p.N) {
+        const float4 zz = *reinterpret_cast<const float4*>(z + j);
+        v[j] *= gelu_grad_f(zz.x); v[j + 1] *= gelu_grad_f(zz.y); v[j + 2] *= gelu_grad_f(zz.z); v[j + 3] *= gelu_grad_f(zz.w);
+      }
+  }
+  // planes out (SRW_EPI_PLANES, SRW_EPI_GELU, SRW_EPI_DGELU)
+  __nv_bfloat16* hi = p.out_planes + (int64_t)row * p.ldp + col0;
+  __nv_bfloat16* lo = hi + p.out_plane_stride;
+#pragma unroll
+  for (int j = 0; j < NV; j += 4)
+    if (col0 + j < p.N) {
+      uint32_t h0, l0, h1, l1;
+      split2(v[j], v[j + 1], h0, l0);
+      split2(v[j + 2], v[j + 3], h1, l1);
+      *reinterpret_cast<uint2*>(hi + j) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(lo + j) = make_uint2(l0, l1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 kernel
+// ------------------------------------------------------------------------------------------------
+struct TcParams {
+  int K;            // reduction length
+  int kb_per_split; // k blocks (of 64) handled by one grid.z slice
+  int a_mn, b_mn;   // operand majors
+};
+
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                           const TcParams tp, const EpiParams ep) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  const int split = blockIdx.z;
+  const int num_kb_total = (tp.K + BK - 1) / BK;
+  const int kb_begin = split * tp.kb_per_split;
+  const int kb_end = min(num_kb_total, kb_begin + tp.kb_per_split);
+  const int num_kb = max(0, kb_end - kb_begin);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        const int k0 = (kb_begin + i) * BK;
+        if (!tp.a_mn) {
+          tma_load_3d(st, &tmap_a, &full_bar[s], k0, m0, 0);                       // [2][128][64]
+        } else {
+          tma_load_3d(st, &tmap_a, &full_bar[s], m0, k0, 0);                       // [2][64 k][64 mn] chunk 0
+          tma_load_3d(st + PLANE_TILE_BYTES, &tmap_a, &full_bar[s], m0 + 64, k0, 0);  // chunk 1
+        }
+        uint8_t* sb = st + 2 * PLANE_TILE_BYTES;
+        if (!tp.b_mn) {
+          tma_load_3d(sb, &tmap_b, &full_bar[s], k0, n0, 0);
+        } else {
+          tma_load_3d(sb, &tmap_b, &full_bar[s], n0, k0, 0);
+          tma_load_3d(sb + PLANE_TILE_BYTES, &tmap_b, &full_bar[s], n0 + 64, k0, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(BN, tp.a_mn, tp.b_mn);
+      // per-operand descriptor geometry
+      const uint32_t a_lo_off = tp.a_mn ? (PLANE_TILE_BYTES / 2) : PLANE_TILE_BYTES;  // lo plane offset inside the operand
+      const uint32_t b_lo_off = tp.b_mn ? (PLANE_TILE_BYTES / 2) : PLANE_TILE_BYTES;
+      const uint32_t a_lbo = tp.a_mn ? PLANE_TILE_BYTES : 16, b_lbo = tp.b_mn ? PLANE_TILE_BYTES : 16;
+      const uint32_t a_kstep = tp.a_mn ? 2048 : 32, b_kstep = tp.b_mn ? 2048 : 32;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_base = a_base + 2 * PLANE_TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          const uint64_t a_hi = umma_smem_desc(a_base + kk * a_kstep, a_lbo, 1024);
+          const uint64_t a_lo = umma_smem_desc(a_base + a_lo_off + kk * a_kstep, a_lbo, 1024);
+          const uint64_t b_hi = umma_smem_desc(b_base + kk * b_kstep, b_lbo, 1024);
+          const uint64_t b_lo = umma_smem_desc(b_base + b_lo_off + kk * b_kstep, b_lbo, 1024);
+          umma_bf16(tmem_base, a_lo, b_hi, idesc, (i > 0 || kk > 0) ? 1u : 0u);  // small terms first
+          umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
+          umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(accum_bar);  // accumulator complete
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int q = warp - 4;  // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    if (num_kb > 0) {
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      if (num_kb > 0) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+      }
+      if (n0 + c * 32 < ep.N) epilogue_store<32>(ep, row, n0 + c * 32, v, split);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT verification twin: same operands (hi+lo reconstructed to fp32), fp32 FMA, same epilogue code.
+// 64x64 tile, 256 threads, 4x4 outputs per thread.
+// ------------------------------------------------------------------------------------------------
+struct SimtParams {
+  int K, kb_per_split;
+  const __nv_bfloat16* a; int64_t lda, a_ps; int a_mn;
+  const __nv_bfloat16* b; int64_t ldb, b_ps; int b_mn;
+};
+
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams sp, const EpiParams ep) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int split = blockIdx.z;
+  const int k_begin = split * sp.kb_per_split * BK;
+  const int k_end = min(sp.K, k_begin + sp.kb_per_split * BK);
+  float acc[4][4] = {};
+  for (int k0 = k_begin; k0 < k_end; k0 += 16) {
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      int mm, kk;
+      if (!sp.a_mn) { kk = e % 16; mm = e / 16; } else { mm = e % 64; kk = e / 64; }
+      const int m = m0 + mm, k = k0 + kk;
+      float va = 0.f;
+      if (m < ep.M && k < k_end) {
+        const int64_t idx = sp.a_mn ? ((int64_t)k * sp.lda + m) : ((int64_t)m * sp.lda + k);
+        va = plane_value(sp.a, sp.a_ps, idx);
+      }
+      As[kk][mm] = va;
+      int nn, kb;
+      if (!sp.b_mn) { kb = e % 16; nn = e / 16; } else { nn = e % 64; kb = e / 64; }
+      const int n = n0 + nn, k2 = k0 + kb;
+      float vb = 0.f;
+      if (n < ep.N && k2 < k_end) {
+        const int64_t idx = sp.b_mn ? ((int64_t)k2 * sp.ldb + n) : ((int64_t)n * sp.ldb + k2);
+        vb = plane_value(sp.b, sp.b_ps, idx);
+      }
+      Bs[kb][nn] = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int col0 = n0 + tx * 4;
+    if (col0 < ep.N) epilogue_store<4>(ep, m0 + ty * 4 + i, col0, acc[i], split);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// 3-D bf16 tensor map over split planes: dims (inner, outer, plane).  box = (64, box_outer, 2), SWIZZLE_128B.
+int make_plane_tmap(CUtensorMap* out, const void* base, int64_t inner, int64_t outer, int64_t ld, int64_t plane_stride,
+                    int box_outer) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_last_error("cuTensorMapEncodeTiled not available from the driver");
+    return SRW_ERR_DRIVER;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 8) || (plane_stride % 8)) {
+    set_last_error("TMA operand must be 16-byte aligned with ld and plane stride multiples of 8 elements (ld=%lld ps=%lld)",
+                   (long long)ld, (long long)plane_stride);
+    return SRW_ERR_ARG;
+  }
+  cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)outer, 2};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_stride * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_outer, 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed: %d (inner=%lld outer=%lld ld=%lld ps=%lld)", (int)r, (long long)inner,
+                   (long long)outer, (long long)ld, (long long)plane_stride);
+    return SRW_ERR_DRIVER;
+  }
+  return SRW_OK;
+}
+
+static int fill_epi(const srw_gemm_args* a, EpiParams& ep) {
+  ep.M = a->M; ep.N = a->N; ep.epilogue = a->epilogue;
+  ep.bias = a->bias;
+  ep.resid = a->resid; ep.ldr = a->ldr;
+  ep.row_scale = a->row_scale; ep.rows_per_scale = a->rows_per_scale > 0 ? a->rows_per_scale : 1;
+  ep.aux = a->aux; ep.ldaux = a->ldaux;
+  ep.out_f32 = a->out_f32; ep.ldo = a->ldo;
+  ep.out_planes = reinterpret_cast<__nv_bfloat16*>(a->out_planes); ep.ldp = a->ldp; ep.out_plane_stride = a->out_plane_stride;
+  ep.workspace = a->workspace;
+  SRW_REQUIRE(a->N % 4 == 0, "srw_gemm: N must be a multiple of 4 (N=%d)", a->N);
+  switch (a->epilogue) {
+    case SRW_EPI_F32: SRW_REQUIRE(a->out_f32 && a->ldo % 4 == 0, "srw_gemm: EPI_F32 needs out_f32, ldo%%4==0"); break;
+    case SRW_EPI_PLANES: SRW_REQUIRE(a->out_planes && a->ldp % 4 == 0, "srw_gemm: EPI_PLANES needs out_planes"); break;
+    case SRW_EPI_GELU:
+      SRW_REQUIRE(a->out_planes && a->out_f32 && a->ldp % 4 == 0 && a->ldo % 4 == 0, "srw_gemm: EPI_GELU needs out_f32 and out_planes");
+      break;
+    case SRW_EPI_RESID: SRW_REQUIRE(a->out_f32 && a->resid && a->ldo % 4 == 0 && a->ldr % 4 == 0, "srw_gemm: EPI_RESID needs out_f32 and resid"); break;
+    case SRW_EPI_DGELU: SRW_REQUIRE(a->out_planes && a->aux && a->ldp % 4 == 0 && a->ldaux % 4 == 0, "srw_gemm: EPI_DGELU needs out_planes and aux"); break;
+    case SRW_EPI_SPLITK: SRW_REQUIRE(a->workspace && a->split_k >= 1, "srw_gemm: EPI_SPLITK needs workspace and split_k>=1"); break;
+    default: set_last_error("srw_gemm: unknown epilogue %d", a->epilogue); return SRW_ERR_ARG;
+  }
+  return SRW_OK;
+}
+
+}  // namespace srw
+
+using namespace srw;
+
+extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SRW_REQUIRE(a && a->M > 0 && a->N > 0 && a->K > 0, "srw_gemm: bad shape");
+  SRW_REQUIRE(a->a && a->b, "srw_gemm: null operand");
+  EpiParams ep;
+  int rc = fill_epi(a, ep);
+  if (rc) return rc;
+  const int num_kb = cdiv(a->K, BK);
+  int split = (a->epilogue == SRW_EPI_SPLITK) ? a->split_k : 1;
+  if (split > num_kb) split = num_kb;
+  const int kb_per_split = cdiv(num_kb, split);
+  // note: with split < requested, the untouched workspace slices are still written (as zeros) because grid.z = split_k
+  const int grid_z = (a->epilogue == SRW_EPI_SPLITK) ? a->split_k : 1;
+
+  if (a->impl == SRW_GEMM_SIMT) {
+    SimtParams sp;
+    sp.K = a->K; sp.kb_per_split = kb_per_split;
+    sp.a = reinterpret_cast<const __nv_bfloat16*>(a->a); sp.lda = a->lda; sp.a_ps = a->a_plane_stride; sp.a_mn = a->a_mn_major;
+    sp.b = reinterpret_cast<const __nv_bfloat16*>(a->b); sp.ldb = a->ldb; sp.b_ps = a->b_plane_stride; sp.b_mn = a->b_mn_major;
+    dim3 grid(cdiv(a->N, 64), cdiv(a->M, 64), grid_z);
+    gemm_simt_kernel<<<grid, 256, 0, stream>>>(sp, ep);
+    g_launches++;
+    SRW_LAUNCH_CHECK();
+    return SRW_OK;
+  }
+  SRW_REQUIRE(a->impl == SRW_GEMM_TCGEN05, "srw_gemm: unknown impl %d", a->impl);
+
+  CUtensorMap ta, tb;
+  if (!a->a_mn_major) rc = make_plane_tmap(&ta, a->a, a->K, a->M, a->lda, a->a_plane_stride, 128);
+  else rc = make_plane_tmap(&ta, a->a, a->M, a->K, a->lda, a->a_plane_stride, 64);
+  if (rc) return rc;
+  if (!a->b_mn_major) rc = make_plane_tmap(&tb, a->b, a->K, a->N, a->ldb, a->b_plane_stride, 128);
+  else rc = make_plane_tmap(&tb, a->b, a->N, a->K, a->ldb, a->b_plane_stride, 64);
+  if (rc) return rc;
+
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_bf16x3_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+  });
+  SRW_CUDA(attr_err);
+
+  TcParams tp;
+  tp.K = a->K; tp.kb_per_split = kb_per_split; tp.a_mn = a->a_mn_major ? 1 : 0; tp.b_mn = a->b_mn_major ? 1 : 0;
+  dim3 grid(cdiv(a->N, BN), cdiv(a->M, BM), grid_z);
+  gemm_bf16x3_tcgen05_kernel<<<grid, 256, GEMM_SMEM_BYTES, stream>>>(ta, tb, tp, ep);
+  g_launches++;
+  SRW_LAUNCH_CHECK();
+  return SRW_OK;
+}
