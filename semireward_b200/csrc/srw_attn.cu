@@ -1,0 +1,605 @@
+// srw_attn — softmax(q k^T * scale) v per (image, head) and its backward, replacing the reference's naive
+// `attn = (q @ k.transpose(-2,-1)) * scale; attn.softmax(-1); attn @ v` (vit.py:100-104, which materialises
+// [B,H,N,N] fp32 scores in HBM) and autograd's backward of it.  Nothing N x N ever leaves the SM here.
+//
+// Operands are split-bf16 planes (srw_common.cuh); every product runs as hi*hi + hi*lo + lo*hi on tcgen05 tensor cores
+// with fp32 accumulation in TMEM.  head_dim is 64 (ViT-S/B, BERT-base and HuBERT-base all use 64).
+//
+// Forward (one CTA per (128-query tile, head, image); N <= 272 keys so a whole score row lives in TMEM):
+//   TMA: Q tile, all K, all V -> smem.   MMA: S[128, NP] = Q K^T into TMEM.   4 softmax warps (thread == query row):
+//   row max, p = exp2((s - max) * scale*log2e), split p into bf16 hi/lo and write 64-key chunks of P into swizzled
+//   smem; the MMA warp consumes each chunk as soon as it lands: O += P_chunk V_chunk.  O / rowsum -> global planes.
+// Backward = two kernels sharing one skeleton (attn_bwd_kernel<MODE>): a 128-row tile R against 64-wide column
+//   chunks C_j:   T1_j = R1 C1_j^T, T2_j = R2 C2_j^T (TMEM) -> threads form X_j (and Y_j) -> Acc += X_j C1_j (Y_j C2_j).
+//   MODE_DQ : R = query tile (Q, dO), C = key chunks (K, V):  X = dS           -> dQ = sum_j dS_j K_j
+//   MODE_DKV: R = key tile (K, V),  C = query chunks (Q, dO): X = dS^T, Y = P^T -> dK = sum_j dS^T_j Q_j, dV = sum_j P^T_j dO_j
+//   (dS = P o (dP - delta) * scale, P = exp(S*scale - lse), delta = rowsum(dO o O)).  No atomics: deterministic.
+#include <cuda.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/srw.h"
+#include "srw_common.cuh"
+
+namespace srw {
+extern std::atomic<int64_t> g_launches;
+
+constexpr int HD = 64;                    // head dim
+constexpr int ROW_TILE_BYTES = 128 * 128; // 128 rows x 64 bf16 (one plane)
+constexpr float LOG2E = 1.4426950408889634f;
+
+// byte offset of the 16-byte group `g` (0..7) of row `r` inside a K-major SWIZZLE_128B tile (128 B rows, 8-row atoms)
+__device__ __forceinline__ uint32_t sw128_off(int r, int g) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((g ^ (r & 7)) << 4));
+}
+
+// write 32 consecutive fp32 values of row r (columns [c0, c0+32) of a 64-wide chunk) as split planes into a swizzled tile
+__device__ __forceinline__ void store_row32_planes(uint8_t* hi_tile, uint8_t* lo_tile, int r, int c0, const float (&v)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split2(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1], h[j], l[j]);
+    const uint32_t off = sw128_off(r, (c0 >> 3) + g);
+    *reinterpret_cast<uint4*>(hi_tile + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo_tile + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+struct AttnFwdParams {
+  int B, N, H, NP;        // NP = N rounded up to 16 (<= 272)
+  float scale;            // head_dim^-0.5
+  __nv_bfloat16* o; int64_t ld_o, o_ps;
+  float* lse;             // [B, H, N] natural-log units: scale*max + log(sum)
+};
+
+__global__ void __launch_bounds__(160, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int NP = p.NP;
+  const uint32_t kv_plane = (uint32_t)NP * 128;           // bytes of one K (or V) plane
+  const uint32_t off_k = 2 * ROW_TILE_BYTES;              // after Q hi, Q lo
+  const uint32_t off_v = max(off_k + 2 * kv_plane, 4u * ROW_TILE_BYTES);  // P buffers alias [0, 64 KiB)
+  const uint32_t off_bar = off_v + 2 * kv_plane;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bar);
+  uint64_t* bar_qk = bars + 0; uint64_t* bar_v = bars + 1; uint64_t* bar_s = bars + 2; uint64_t* bar_o = bars + 3;
+  uint64_t* bar_p = bars + 4;      // [2]
+  uint64_t* bar_pfree = bars + 6;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int D = p.H * HD;
+  const int row0 = b * p.N;           // first token row of this image in the [B*N, 3D] qkv matrix
+  const int nchunks = (NP + 63) / 64;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_kv);
+    mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    mbar_init(&bar_p[0], 128); mbar_init(&bar_p[1], 128);
+    mbar_init(&bar_pfree[0], 1); mbar_init(&bar_pfree[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t TM_S = tmem, TM_O = tmem + 384, TM_OX = tmem + 448;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---- loads ----
+      const int half = NP / 2;
+      mbar_arrive_expect_tx(bar_qk, 2 * ROW_TILE_BYTES + 2 * kv_plane);
+      tma_load_3d(smem, &tmap_q, bar_qk, h * HD, row0 + qt * 128, 0);
+      tma_load_3d(smem + ROW_TILE_BYTES, &tmap_q, bar_qk, h * HD, row0 + qt * 128, 1);
+      for (int pl = 0; pl < 2; ++pl)
+        for (int hf = 0; hf < 2; ++hf)
+          tma_load_3d(smem + off_k + pl * kv_plane + hf * half * 128, &tmap_kv, bar_qk, D + h * HD, row0 + hf * half, pl);
+      mbar_arrive_expect_tx(bar_v, 2 * kv_plane);
+      for (int pl = 0; pl < 2; ++pl)
+        for (int hf = 0; hf < 2; ++hf)
+          tma_load_3d(smem + off_v + pl * kv_plane + hf * half * 128, &tmap_kv, bar_v, 2 * D + h * HD, row0 + hf * half, pl);
+      // ---- S = Q K^T ----
+      mbar_wait(bar_qk, 0);
+      tc_fence_after();
+      const uint32_t q_hi = smem_u32(smem), q_lo = q_hi + ROW_TILE_BYTES;
+      const uint32_t k_hi = smem_u32(smem + off_k), k_lo = k_hi + kv_plane;
+      const int n1 = NP <= 256 ? NP : 256, n2 = NP - n1;
+      for (int part = 0; part < 2; ++part) {
+        const int n = part == 0 ? n1 : n2;
+        if (n == 0) break;
+        const uint32_t idesc = umma_idesc_bf16(n, 0, 0);
+        const uint32_t boff = part * 256 * 128, tcol = part * 256;
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint64_t aq_hi = umma_smem_desc(q_hi + kk * 32, 16, 1024), aq_lo = umma_smem_desc(q_lo + kk * 32, 16, 1024);
+          const uint64_t bk_hi = umma_smem_desc(k_hi + boff + kk * 32, 16, 1024), bk_lo = umma_smem_desc(k_lo + boff + kk * 32, 16, 1024);
+          umma_bf16(TM_S + tcol, aq_lo, bk_hi, idesc, kk > 0 ? 1u : 0u);
+          umma_bf16(TM_S + tcol, aq_hi, bk_lo, idesc, 1u);
+          umma_bf16(TM_S + tcol, aq_hi, bk_hi, idesc, 1u);
+        }
+      }
+      umma_commit(bar_s);
+      // ---- O += P_c V_c ----
+      mbar_wait(bar_v, 0);
+      const uint32_t v_hi = smem_u32(smem + off_v), v_lo = v_hi + kv_plane;
+      const uint32_t idesc_pv = umma_idesc_bf16(HD, 0, 1);
+      for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        mbar_wait(&bar_p[buf], (c >> 1) & 1);
+        tc_fence_after();
+        const uint32_t p_hi = smem_u32(smem + buf * 2 * ROW_TILE_BYTES), p_lo = p_hi + ROW_TILE_BYTES;
+        const int ksteps = min(4, (NP - c * 64) / 16);
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint32_t voff = (uint32_t)(c * 64 + kk * 16) * 128;
+          const uint64_t ap_hi = umma_smem_desc(p_hi + kk * 32, 16, 1024), ap_lo = umma_smem_desc(p_lo + kk * 32, 16, 1024);
+          const uint64_t bv_hi = umma_smem_desc(v_hi + voff, 1024, 1024), bv_lo = umma_smem_desc(v_lo + voff, 1024, 1024);
+          const uint32_t acc = (c > 0 || kk > 0) ? 1u : 0u;
+          umma_bf16(TM_OX, ap_lo, bv_hi, idesc_pv, acc);
+          umma_bf16(TM_OX, ap_hi, bv_lo, idesc_pv, 1u);
+          umma_bf16(TM_O, ap_hi, bv_hi, idesc_pv, acc);
+        }
+        umma_commit(&bar_pfree[buf]);
+      }
+      umma_commit(bar_o);
+    }
+  } else {
+    // ---- softmax warps: thread == query row ----
+    const int r = threadIdx.x;                       // 0..127, TMEM lane
+    const int qr = qt * 128 + r;                     // query index inside the image
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const float c2 = p.scale * LOG2E;
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    float m = -INFINITY;
+    for (int c0 = 0; c0 < NP; c0 += 32) {
+      if (NP - c0 >= 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(TM_S + lane_addr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < p.N) m = fmaxf(m, __uint_as_float(v[j]));
+      } else {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(TM_S + lane_addr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c0 + j < p.N) m = fmaxf(m, __uint_as_float(v[j]));
+      }
+    }
+    const float mc = m * c2;
+    float sum = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      float pv[2][32];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int c0 = c * 64 + hf * 32;
+        if (c0 + 32 <= NP) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(TM_S + lane_addr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float e = (c0 + j < p.N) ? exp2f(fmaf(__uint_as_float(v[j]), c2, -mc)) : 0.f;
+            pv[hf][j] = e;
+            sum += e;
+          }
+        } else if (c0 + 16 <= NP) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(TM_S + lane_addr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float e = (c0 + j < p.N) ? exp2f(fmaf(__uint_as_float(v[j]), c2, -mc)) : 0.f;
+            pv[hf][j] = e;
+            sum += e;
+          }
+#pragma unroll
+          for (int j = 16; j < 32; ++j) pv[hf][j] = 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pv[hf][j] = 0.f;
+        }
+      }
+      if (c >= 2) mbar_wait(&bar_pfree[buf], ((c >> 1) - 1) & 1);
+      uint8_t* hi_tile = smem + buf * 2 * ROW_TILE_BYTES;
+      uint8_t* lo_tile = hi_tile + ROW_TILE_BYTES;
+      store_row32_planes(hi_tile, lo_tile, r, 0, pv[0]);
+      store_row32_planes(hi_tile, lo_tile, r, 32, pv[1]);
+      fence_proxy_async();
+      mbar_arrive(&bar_p[buf]);
+    }
+    // ---- epilogue ----
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const float inv = 1.0f / sum;
+    if (qr < p.N) {
+      if (p.lse) p.lse[((int64_t)b * p.H + h) * p.N + qr] = m * p.scale + logf(sum);
+    }
+    __nv_bfloat16* orow = p.o + (int64_t)(row0 + qr) * p.ld_o + h * HD;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      uint32_t a[32], x[32];
+      tmem_ld_32x32b_x32(TM_O + lane_addr + hf * 32, a);
+      tmem_ld_32x32b_x32(TM_OX + lane_addr + hf * 32, x);
+      tmem_ld_wait();
+      if (qr < p.N) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t hh[4], ll[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int e = g * 8 + 2 * j;
+            const float v0 = (__uint_as_float(a[e]) + __uint_as_float(x[e])) * inv;
+            const float v1 = (__uint_as_float(a[e + 1]) + __uint_as_float(x[e + 1])) * inv;
+            split2(v0, v1, hh[j], ll[j]);
+          }
+          *reinterpret_cast<uint4*>(orow + hf * 32 + g * 8) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+          *reinterpret_cast<uint4*>(orow + p.o_ps + hf * 32 + g * 8) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+enum { MODE_DQ = 0, MODE_DKV = 1 };
+
+struct AttnBwdParams {
+  int B, N, H, NP;
+  float scale;
+  const __nv_bfloat16* o; int64_t ld_o, o_ps;       // forward output planes   (MODE_DQ: delta)
+  const __nv_bfloat16* d_o; int64_t ld_do, do_ps;   // upstream gradient planes (MODE_DQ: delta)
+  const float* lse;                                  // [B,H,N]
+  float* delta;                                      // [B,H,N]  written by MODE_DQ, read by MODE_DKV
+  __nv_bfloat16* dqkv; int64_t ld_dqkv, dqkv_ps;
+};
+
+constexpr int BWD_OFF_R1 = 0, BWD_OFF_R2 = 2 * ROW_TILE_BYTES, BWD_OFF_C = 4 * ROW_TILE_BYTES;
+constexpr int BWD_CSTAGE = 2 * ROW_TILE_BYTES;  // C1 (hi 8K, lo 8K) + C2 (hi 8K, lo 8K)
+constexpr int BWD_OFF_X = BWD_OFF_C + 2 * BWD_CSTAGE;
+constexpr int BWD_OFF_Y = BWD_OFF_X + 2 * ROW_TILE_BYTES;
+constexpr int BWD_OFF_VEC = BWD_OFF_Y + 2 * ROW_TILE_BYTES;       // 2 x 320 floats (lse*log2e, delta per column)
+constexpr int BWD_OFF_BAR = BWD_OFF_VEC + 2 * 320 * 4;
+constexpr int BWD_SMEM = BWD_OFF_BAR + 256 + 1024;
+
+template <int MODE>
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_constant__ CUtensorMap tm_do_r,
+                const __grid_constant__ CUtensorMap tm_qkv_c, const __grid_constant__ CUtensorMap tm_do_c, const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BWD_OFF_BAR);
+  uint64_t* bar_r = bars + 0;
+  uint64_t* bar_cfull = bars + 1;   // [2]
+  uint64_t* bar_cfree = bars + 3;   // [2]
+  uint64_t* bar_t = bars + 5;       // [2]
+  uint64_t* bar_x = bars + 7;
+  uint64_t* bar_xfree = bars + 8;
+  uint64_t* bar_acc = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* vec_lse = reinterpret_cast<float*>(smem + BWD_OFF_VEC);
+  float* vec_delta = vec_lse + 320;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int D = p.H * HD;
+  const int row0 = b * p.N;
+  const int nchunks = (p.NP + 63) / 64;
+  const int64_t stat0 = ((int64_t)b * p.H + h) * p.N;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv_r); tma_prefetch_desc(&tm_do_r); tma_prefetch_desc(&tm_qkv_c); tma_prefetch_desc(&tm_do_c);
+    mbar_init(bar_r, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_cfull[s], 1); mbar_init(&bar_cfree[s], 1); mbar_init(&bar_t[s], 1); }
+    mbar_init(bar_x, 128); mbar_init(bar_xfree, 1); mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (MODE == MODE_DKV) {
+    // per-column (query) statistics
+    for (int i = threadIdx.x; i < p.NP; i += blockDim.x) {
+      vec_lse[i] = i < p.N ? p.lse[stat0 + i] * LOG2E : 0.f;
+      vec_delta[i] = i < p.N ? p.delta[stat0 + i] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM columns: T1[s] = s*128, T2[s] = s*128 + 64; AccX main 256, cross 320; AccY main 384, cross 448
+  const int r1_col = (MODE == MODE_DQ ? 0 : D) + h * HD;       // R1: Q (DQ) / K (DKV)
+  const int r2_col = (MODE == MODE_DQ ? 0 : 2 * D) + h * HD;   // R2: dO (DQ, own matrix) / V (DKV)
+  const int c1_col = (MODE == MODE_DQ ? D : 0) + h * HD;       // C1: K (DQ) / Q (DKV)
+  const int c2_col = (MODE == MODE_DQ ? 2 * D : 0) + h * HD;   // C2: V (DQ) / dO (DKV, own matrix)
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      mbar_arrive_expect_tx(bar_r, 4 * ROW_TILE_BYTES);
+      tma_load_3d(smem + BWD_OFF_R1, &tm_qkv_r, bar_r, r1_col, row0 + rt * 128, 0);  // box planes = 2: hi, lo
+      if (MODE == MODE_DQ) tma_load_3d(smem + BWD_OFF_R2, &tm_do_r, bar_r, h * HD, row0 + rt * 128, 0);
+      else tma_load_3d(smem + BWD_OFF_R2, &tm_qkv_r, bar_r, r2_col, row0 + rt * 128, 0);
+      for (int j = 0; j < nchunks; ++j) {
+        const int s = j & 1;
+        mbar_wait(&bar_cfree[s], ((j >> 1) & 1) ^ 1);
+        uint8_t* st = smem + BWD_OFF_C + s * BWD_CSTAGE;
+        mbar_arrive_expect_tx(&bar_cfull[s], BWD_CSTAGE);
+        tma_load_3d(st, &tm_qkv_c, &bar_cfull[s], c1_col, row0 + j * 64, 0);
+        if (MODE == MODE_DQ) tma_load_3d(st + ROW_TILE_BYTES, &tm_qkv_c, &bar_cfull[s], c2_col, row0 + j * 64, 0);
+        else tma_load_3d(st + ROW_TILE_BYTES, &tm_do_c, &bar_cfull[s], h * HD, row0 + j * 64, 0);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc_t = umma_idesc_bf16(64, 0, 0);     // T = R C^T   (both K-major, K = head dim)
+      const uint32_t idesc_a = umma_idesc_bf16(64, 0, 1);     // Acc = X C   (X K-major, C MN-major, K = chunk columns)
+      const uint32_t r1 = smem_u32(smem + BWD_OFF_R1), r2 = smem_u32(smem + BWD_OFF_R2);
+      const uint32_t xb = smem_u32(smem + BWD_OFF_X), yb = smem_u32(smem + BWD_OFF_Y);
+      mbar_wait(bar_r, 0);
+      auto issue_t = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(&bar_cfull[s], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t c1 = smem_u32(smem + BWD_OFF_C + s * BWD_CSTAGE), c2 = c1 + ROW_TILE_BYTES;
+        const uint32_t t1 = tmem + s * 128, t2 = t1 + 64;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t ko = kk * 32;
+          const uint64_t a1h = umma_smem_desc(r1 + ko, 16, 1024), a1l = umma_smem_desc(r1 + ROW_TILE_BYTES + ko, 16, 1024);
+          const uint64_t b1h = umma_smem_desc(c1 + ko, 16, 1024), b1l = umma_smem_desc(c1 + ROW_TILE_BYTES / 2 + ko, 16, 1024);
+          umma_bf16(t1, a1l, b1h, idesc_t, kk > 0 ? 1u : 0u);
+          umma_bf16(t1, a1h, b1l, idesc_t, 1u);
+          umma_bf16(t1, a1h, b1h, idesc_t, 1u);
+          const uint64_t a2h = umma_smem_desc(r2 + ko, 16, 1024), a2l = umma_smem_desc(r2 + ROW_TILE_BYTES + ko, 16, 1024);
+          const uint64_t b2h = umma_smem_desc(c2 + ko, 16, 1024), b2l = umma_smem_desc(c2 + ROW_TILE_BYTES / 2 + ko, 16, 1024);
+          umma_bf16(t2, a2l, b2h, idesc_t, kk > 0 ? 1u : 0u);
+          umma_bf16(t2, a2h, b2l, idesc_t, 1u);
+          umma_bf16(t2, a2h, b2h, idesc_t, 1u);
+        }
+        umma_commit(&bar_t[s]);
+      };
+      issue_t(0);
+      for (int j = 0; j < nchunks; ++j) {
+        const int s = j & 1;
+        if (j + 1 < nchunks) issue_t(j + 1);
+        mbar_wait(bar_x, j & 1);
+        tc_fence_after();
+        const uint32_t c1 = smem_u32(smem + BWD_OFF_C + s * BWD_CSTAGE), c2 = c1 + ROW_TILE_BYTES;
+        const int ksteps = min(4, (p.NP - j * 64) / 16);
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint32_t acc = (j > 0 || kk > 0) ? 1u : 0u;
+          const uint32_t ko = kk * 32, bo = kk * 2048;
+          const uint64_t xh = umma_smem_desc(xb + ko, 16, 1024), xl = umma_smem_desc(xb + ROW_TILE_BYTES + ko, 16, 1024);
+          const uint64_t b1h = umma_smem_desc(c1 + bo, 1024, 1024), b1l = umma_smem_desc(c1 + ROW_TILE_BYTES / 2 + bo, 1024, 1024);
+          umma_bf16(tmem + 320, xl, b1h, idesc_a, acc);
+          umma_bf16(tmem + 320, xh, b1l, idesc_a, 1u);
+          umma_bf16(tmem + 256, xh, b1h, idesc_a, acc);
+          if (MODE == MODE_DKV) {
+            const uint64_t yh = umma_smem_desc(yb + ko, 16, 1024), yl = umma_smem_desc(yb + ROW_TILE_BYTES + ko, 16, 1024);
+            const uint64_t b2h = umma_smem_desc(c2 + bo, 1024, 1024), b2l = umma_smem_desc(c2 + ROW_TILE_BYTES / 2 + bo, 1024, 1024);
+            umma_bf16(tmem + 448, yl, b2h, idesc_a, acc);
+            umma_bf16(tmem + 448, yh, b2l, idesc_a, 1u);
+            umma_bf16(tmem + 384, yh, b2h, idesc_a, acc);
+          }
+        }
+        umma_commit(bar_xfree);
+        umma_commit(&bar_cfree[s]);
+      }
+      umma_commit(bar_acc);
+    }
+  } else {
+    // ===== element-wise warps: thread == tile row =====
+    const int r = threadIdx.x;
+    const int rr = rt * 128 + r;            // row index inside the image (query for DQ, key for DKV)
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const float c2s = p.scale * LOG2E;
+    float row_lse = 0.f, row_delta = 0.f;
+    if (MODE == MODE_DQ) {
+      if (rr < p.N) {
+        row_lse = p.lse[stat0 + rr] * LOG2E;
+        // delta = sum_d dO * O over this head's 64 columns (fp32 values reconstructed from the planes)
+        const __nv_bfloat16* orow = p.o + (int64_t)(row0 + rr) * p.ld_o + h * HD;
+        const __nv_bfloat16* drow = p.d_o + (int64_t)(row0 + rr) * p.ld_do + h * HD;
+        float acc = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint4 oh = *reinterpret_cast<const uint4*>(orow + g * 8), ol = *reinterpret_cast<const uint4*>(orow + p.o_ps + g * 8);
+          const uint4 dh = *reinterpret_cast<const uint4*>(drow + g * 8), dl = *reinterpret_cast<const uint4*>(drow + p.do_ps + g * 8);
+          const uint32_t ohh[4] = {oh.x, oh.y, oh.z, oh.w}, oll[4] = {ol.x, ol.y, ol.z, ol.w};
+          const uint32_t dhh[4] = {dh.x, dh.y, dh.z, dh.w}, dll[4] = {dl.x, dl.y, dl.z, dl.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc = fmaf(bf16_lo_f(ohh[j]) + bf16_lo_f(oll[j]), bf16_lo_f(dhh[j]) + bf16_lo_f(dll[j]), acc);
+            acc = fmaf(bf16_hi_f(ohh[j]) + bf16_hi_f(oll[j]), bf16_hi_f(dhh[j]) + bf16_hi_f(dll[j]), acc);
+          }
+        }
+        row_delta = acc;
+        p.delta[stat0 + rr] = acc;
+      }
+    }
+    for (int j = 0; j < nchunks; ++j) {
+      const int s = j & 1;
+      mbar_wait(&bar_t[s], (j >> 1) & 1);
+      tc_fence_after();
+      if (j >= 1) mbar_wait(bar_xfree, (j - 1) & 1);
+      uint8_t* x_hi = smem + BWD_OFF_X; uint8_t* x_lo = x_hi + ROW_TILE_BYTES;
+      uint8_t* y_hi = smem + BWD_OFF_Y; uint8_t* y_lo = y_hi + ROW_TILE_BYTES;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t t1[32], t2[32];
+        tmem_ld_32x32b_x32(tmem + lane_addr + s * 128 + hf * 32, t1);
+        tmem_ld_32x32b_x32(tmem + lane_addr + s * 128 + 64 + hf * 32, t2);
+        tmem_ld_wait();
+        float xs[32], ys[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int col = j * 64 + hf * 32 + e;     // key index (DQ) / query index (DKV)
+          float pe, ds;
+          if (MODE == MODE_DQ) {
+            pe = (col < p.N) ? exp2f(fmaf(__uint_as_float(t1[e]), c2s, -row_lse)) : 0.f;
+            ds = pe * (__uint_as_float(t2[e]) - row_delta) * p.scale;
+          } else {
+            pe = (col < p.N) ? exp2f(fmaf(__uint_as_float(t1[e]), c2s, -vec_lse[col])) : 0.f;
+            ds = pe * (__uint_as_float(t2[e]) - vec_delta[col]) * p.scale;
+          }
+          xs[e] = ds;
+          ys[e] = pe;
+        }
+        store_row32_planes(x_hi, x_lo, r, hf * 32, xs);
+        if (MODE == MODE_DKV) store_row32_planes(y_hi, y_lo, r, hf * 32, ys);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(bar_x);
+    }
+    // ---- write the accumulators ----
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int nout = MODE == MODE_DQ ? 1 : 2;
+    for (int w = 0; w < nout; ++w) {
+      // DQ: dQ -> columns [0, D);  DKV: dK -> [D, 2D), dV -> [2D, 3D)
+      const int col0 = (MODE == MODE_DQ ? 0 : (w == 0 ? D : 2 * D)) + h * HD;
+      __nv_bfloat16* orow = p.dqkv + (int64_t)(row0 + rr) * p.ld_dqkv + col0;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t a[32], x[32];
+        tmem_ld_32x32b_x32(tmem + lane_addr + 256 + w * 128 + hf * 32, a);
+        tmem_ld_32x32b_x32(tmem + lane_addr + 320 + w * 128 + hf * 32, x);
+        tmem_ld_wait();
+        if (rr < p.N) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t hh[4], ll[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int e = g * 8 + 2 * q;
+              split2(__uint_as_float(a[e]) + __uint_as_float(x[e]), __uint_as_float(a[e + 1]) + __uint_as_float(x[e + 1]), hh[q], ll[q]);
+            }
+            *reinterpret_cast<uint4*>(orow + hf * 32 + g * 8) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<uint4*>(orow + p.dqkv_ps + hf * 32 + g * 8) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+static int check_attn_shape(int B, int N, int H, int head_dim, const char* who) {
+  SRW_REQUIRE(B > 0 && N > 0 && H > 0, "%s: bad shape", who);
+  if (head_dim != HD) {
+    set_last_error("%s: head_dim must be 64 (got %d)", who, head_dim);
+    return SRW_ERR_UNSUPPORTED;
+  }
+  if (N > 272 || N < 16) {
+    set_last_error("%s: 16 <= tokens per image <= 272 supported by the single-pass kernels (got %d)", who, N);
+    return SRW_ERR_UNSUPPORTED;
+  }
+  return SRW_OK;
+}
+
+}  // namespace srw
+
+using namespace srw;
+
+extern "C" int srw_attn_fwd(const srw_attn_fwd_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SRW_REQUIRE(a && a->qkv && a->o, "srw_attn_fwd: null pointer");
+  int rc = check_attn_shape(a->B, a->N, a->H, a->head_dim, "srw_attn_fwd");
+  if (rc) return rc;
+  const int NP = (a->N + 15) / 16 * 16;
+  const int64_t T = (int64_t)a->B * a->N;
+  CUtensorMap tq, tkv;
+  rc = make_plane_tmap(&tq, a->qkv, 3 * a->H * HD, T, a->ld_qkv, a->qkv_plane_stride, 128, 1);
+  if (rc) return rc;
+  rc = make_plane_tmap(&tkv, a->qkv, 3 * a->H * HD, T, a->ld_qkv, a->qkv_plane_stride, NP / 2, 1);
+  if (rc) return rc;
+  SRW_REQUIRE(a->ld_o % 8 == 0 && a->o_plane_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(a->o) & 15) == 0, "srw_attn_fwd: o planes must be 16-byte aligned");
+  const uint32_t kv_plane = (uint32_t)NP * 128;
+  const uint32_t off_v = std::max<uint32_t>(2 * ROW_TILE_BYTES + 2 * kv_plane, 4u * ROW_TILE_BYTES);
+  const int smem_bytes = (int)(off_v + 2 * kv_plane + 256 + 1024);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  SRW_CUDA(attr_err);
+  AttnFwdParams p;
+  p.B = a->B; p.N = a->N; p.H = a->H; p.NP = NP; p.scale = a->scale;
+  p.o = reinterpret_cast<__nv_bfloat16*>(a->o); p.ld_o = a->ld_o; p.o_ps = a->o_plane_stride; p.lse = a->lse;
+  dim3 grid(cdiv(a->N, 128), a->H, a->B);
+  attn_fwd_kernel<<<grid, 160, smem_bytes, stream>>>(tq, tkv, p);
+  g_launches++;
+  SRW_LAUNCH_CHECK();
+  return SRW_OK;
+}
+
+extern "C" int srw_attn_bwd(const srw_attn_bwd_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SRW_REQUIRE(a && a->qkv && a->o && a->d_o && a->lse && a->delta && a->dqkv, "srw_attn_bwd: null pointer");
+  int rc = check_attn_shape(a->B, a->N, a->H, a->head_dim, "srw_attn_bwd");
+  if (rc) return rc;
+  const int NP = (a->N + 15) / 16 * 16;
+  const int64_t T = (int64_t)a->B * a->N;
+  const int D = a->H * HD;
+  CUtensorMap qkv_r, do_r, qkv_c, do_c;
+  if ((rc = make_plane_tmap(&qkv_r, a->qkv, 3 * D, T, a->ld_qkv, a->qkv_plane_stride, 128, 2))) return rc;
+  if ((rc = make_plane_tmap(&do_r, a->d_o, D, T, a->ld_do, a->do_plane_stride, 128, 2))) return rc;
+  if ((rc = make_plane_tmap(&qkv_c, a->qkv, 3 * D, T, a->ld_qkv, a->qkv_plane_stride, 64, 2))) return rc;
+  if ((rc = make_plane_tmap(&do_c, a->d_o, D, T, a->ld_do, a->do_plane_stride, 64, 2))) return rc;
+  SRW_REQUIRE(a->ld_o % 8 == 0 && a->o_plane_stride % 8 == 0 && a->ld_dqkv % 8 == 0 && a->dqkv_plane_stride % 8 == 0 &&
+                  (reinterpret_cast<uintptr_t>(a->o) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->dqkv) & 15) == 0,
+              "srw_attn_bwd: planes must be 16-byte aligned");
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(attn_bwd_kernel<MODE_DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(attn_bwd_kernel<MODE_DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+  });
+  SRW_CUDA(attr_err);
+  AttnBwdParams p;
+  p.B = a->B; p.N = a->N; p.H = a->H; p.NP = NP; p.scale = a->scale;
+  p.o = reinterpret_cast<const __nv_bfloat16*>(a->o); p.ld_o = a->ld_o; p.o_ps = a->o_plane_stride;
+  p.d_o = reinterpret_cast<const __nv_bfloat16*>(a->d_o); p.ld_do = a->ld_do; p.do_ps = a->do_plane_stride;
+  p.lse = a->lse; p.delta = a->delta;
+  p.dqkv = reinterpret_cast<__nv_bfloat16*>(a->dqkv); p.ld_dqkv = a->ld_dqkv; p.dqkv_ps = a->dqkv_plane_stride;
+  dim3 grid(cdiv(a->N, 128), a->H, a->B);
+  attn_bwd_kernel<MODE_DQ><<<grid, 192, BWD_SMEM, stream>>>(qkv_r, do_r, qkv_c, do_c, p);
+  g_launches++;
+  SRW_LAUNCH_CHECK();
+  attn_bwd_kernel<MODE_DKV><<<grid, 192, BWD_SMEM, stream>>>(qkv_r, do_r, qkv_c, do_c, p);
+  g_launches++;
+  SRW_LAUNCH_CHECK();
+  return SRW_OK;
+}

@@ -27,7 +27,7 @@ constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
 constexpr int PLANE_TILE_BYTES = 128 * BK * 2;         // 16 KiB: one 128 x 64 bf16 tile
 constexpr int STAGE_BYTES = 4 * PLANE_TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
 constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int TMEM_COLS = 128;
+constexpr int TMEM_COLS = 256;  // [0,128): hi*hi accumulator, [128,256): cross-term (hi*lo + lo*hi) accumulator
 
 struct EpiParams {
   int M, N;
@@ -205,9 +205,12 @@ gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
           const uint64_t a_lo = umma_smem_desc(a_base + a_lo_off + kk * a_kstep, a_lbo, 1024);
           const uint64_t b_hi = umma_smem_desc(b_base + kk * b_kstep, b_lbo, 1024);
           const uint64_t b_lo = umma_smem_desc(b_base + b_lo_off + kk * b_kstep, b_lbo, 1024);
-          umma_bf16(tmem_base, a_lo, b_hi, idesc, (i > 0 || kk > 0) ? 1u : 0u);  // small terms first
-          umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
-          umma_bf16(tmem_base, a_hi, b_hi, idesc, 1u);
+          // the 2^-9-sized cross terms get their own accumulator: the tensor core's fp32 accumulate truncates, and
+          // adding them into the large hi*hi sum would lose them (and triple the number of biased roundings there)
+          const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
+          umma_bf16(tmem_base + BN, a_lo, b_hi, idesc, acc);
+          umma_bf16(tmem_base + BN, a_hi, b_lo, idesc, 1u);
+          umma_bf16(tmem_base, a_hi, b_hi, idesc, acc);
         }
         umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
       }
@@ -225,11 +228,12 @@ gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
     for (int c = 0; c < BN / 32; ++c) {
       float v[32];
       if (num_kb > 0) {
-        uint32_t r[32];
+        uint32_t r[32], x[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c * 32), x);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(x[j]);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.0f;
@@ -327,9 +331,9 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// 3-D bf16 tensor map over split planes: dims (inner, outer, plane).  box = (64, box_outer, 2), SWIZZLE_128B.
+// 3-D bf16 tensor map over split planes: dims (inner, outer, plane).  box = (64, box_outer, box_planes), SWIZZLE_128B.
 int make_plane_tmap(CUtensorMap* out, const void* base, int64_t inner, int64_t outer, int64_t ld, int64_t plane_stride,
-                    int box_outer) {
+                    int box_outer, int box_planes) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) {
     set_last_error("cuTensorMapEncodeTiled not available from the driver");
@@ -342,14 +346,14 @@ int make_plane_tmap(CUtensorMap* out, const void* base, int64_t inner, int64_t o
   }
   cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)outer, 2};
   cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_stride * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)box_outer, 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_outer, (cuuint32_t)box_planes};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_last_error("cuTensorMapEncodeTiled failed: %d (inner=%lld outer=%lld ld=%lld ps=%lld)", (int)r, (long long)inner,
-                   (long long)outer, (long long)ld, (long long)plane_stride);
+    set_last_error("cuTensorMapEncodeTiled failed: %d (inner=%lld outer=%lld ld=%lld ps=%lld box=%d)", (int)r, (long long)inner,
+                   (long long)outer, (long long)ld, (long long)plane_stride, box_outer);
     return SRW_ERR_DRIVER;
   }
   return SRW_OK;
@@ -411,11 +415,11 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
   SRW_REQUIRE(a->impl == SRW_GEMM_TCGEN05, "srw_gemm: unknown impl %d", a->impl);
 
   CUtensorMap ta, tb;
-  if (!a->a_mn_major) rc = make_plane_tmap(&ta, a->a, a->K, a->M, a->lda, a->a_plane_stride, 128);
-  else rc = make_plane_tmap(&ta, a->a, a->M, a->K, a->lda, a->a_plane_stride, 64);
+  if (!a->a_mn_major) rc = make_plane_tmap(&ta, a->a, a->K, a->M, a->lda, a->a_plane_stride, 128, 2);
+  else rc = make_plane_tmap(&ta, a->a, a->M, a->K, a->lda, a->a_plane_stride, 64, 2);
   if (rc) return rc;
-  if (!a->b_mn_major) rc = make_plane_tmap(&tb, a->b, a->K, a->N, a->ldb, a->b_plane_stride, 128);
-  else rc = make_plane_tmap(&tb, a->b, a->N, a->K, a->ldb, a->b_plane_stride, 64);
+  if (!a->b_mn_major) rc = make_plane_tmap(&tb, a->b, a->K, a->N, a->ldb, a->b_plane_stride, 128, 2);
+  else rc = make_plane_tmap(&tb, a->b, a->N, a->K, a->ldb, a->b_plane_stride, 64, 2);
   if (rc) return rc;
 
   static std::once_flag attr_once;
