@@ -176,7 +176,8 @@ typedef struct {
   const float* x; int batch; int grad_batch;
   const float* drop_scale;
   const float* dlogits; const float* dfeat;   /* [grad_batch, C] and [grad_batch, D] (dfeat may be NULL) */
-  float* const* grads;                        /* same order as params; gradients are ACCUMULATED (+=) */
+  float* const* grads;                        /* same order as params */
+  int accumulate_grads;                       /* 0: grads are overwritten, 1: grads += */
   void* workspace; int64_t workspace_bytes;
   int gemm_impl;
 } srw_vit_bwd_args;

@@ -9,16 +9,11 @@
     return SRW_ERR_UNSUPPORTED;                                     \
   }
 
-SRW_STUB(srw_vit_prepare_weights, const srw_vit_config*, const float* const*, void*, void*)
-SRW_STUB(srw_vit_forward, const srw_vit_fwd_args*, void*)
-SRW_STUB(srw_vit_backward, const srw_vit_bwd_args*, void*)
 SRW_STUB(srw_rewarder_fwd, const srw_rewarder_fwd_args*, void*)
 SRW_STUB(srw_generator_fwd, const srw_generator_fwd_args*, void*)
 SRW_STUB(srw_rewarder_train, const srw_rewarder_train_args*, void*)
 SRW_STUB(srw_flexmatch_epilogue, const srw_flexmatch_epilogue_args*, void*)
 SRW_STUB(srw_adamw_step, const srw_adamw_args*, void*)
-extern "C" int64_t srw_vit_weight_planes_bytes(const srw_vit_config*) { return -1; }
-extern "C" int64_t srw_vit_workspace_bytes(const srw_vit_config*, int, int) { return -1; }
 extern "C" int64_t srw_rewarder_workspace_floats(int, int) { return -1; }
 extern "C" int64_t srw_rewarder_train_workspace_floats(int, int, int) { return -1; }
 extern "C" int64_t srw_adamw_table_bytes(int) { return -1; }

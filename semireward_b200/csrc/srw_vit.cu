@@ -1,0 +1,626 @@
+// srw_vit — the ViT backbone forward and backward as two native calls (reference: VisionTransformer.forward/extract,
+// Block.forward, Attention.forward, Mlp.forward, PatchEmbed.forward  —  semilearn/nets/vit/vit.py:277-306, 163-166,
+// 91-107, 69-75, 39-44; backward = what loss.backward() does for them in param_update.py:33).
+//
+// The engine strings together the kernels of this library on ONE stream, with all activations in a caller-provided
+// workspace laid out by Layout below.  Parameters stay PyTorch-owned fp32 tensors (nn.Linear [out,in] layout); a cache
+// of their split-bf16 planes (srw_vit_prepare_weights) feeds the tensor-core GEMMs; no transposed copies are needed
+// because the GEMM takes MN-major operands.
+//
+//   forward, per block:   LN1 -> planes | qkv GEMM -> planes | attention | proj GEMM + residual | LN2 -> planes |
+//                         fc1 GEMM + GELU (z fp32 kept, gelu(z) planes) | fc2 GEMM + residual
+//   backward, per block:  mirrored; dgrad GEMMs read the same weight planes MN-major, wgrad GEMMs are split-K over the
+//                         token dimension into a workspace and folded by srw_splitk_reduce; bias grads = column sums.
+// Only the first `grad_batch` images are back-propagated (the weak-augmentation rows of the SSL batch only feed
+// detached consumers: srflexmatch.py:135,165).
+#include <cuda.h>
+
+#include <atomic>
+#include <vector>
+
+#include "../../include/srw.h"
+#include "srw_common.cuh"
+
+namespace srw {
+extern std::atomic<int64_t> g_launches;
+
+// ------------------------------------------------------------------------------------------------
+// small kernels: patchify, token assembly, head, embedding gradients
+// ------------------------------------------------------------------------------------------------
+// patches[(b*P + p), k] = x[b, c, py*ps + i, px*ps + j],  k = (c*ps + i)*ps + j  (Conv2d weight order), zero padded to Kpad
+__global__ void patchify_kernel(const float* __restrict__ x, int B, int C, int HW, int ps, int Kpad, __nv_bfloat16* __restrict__ planes,
+                                int64_t plane_stride) {
+  const int gw = HW / ps, P = gw * gw, K = C * ps * ps;
+  const int64_t total = (int64_t)B * P * Kpad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kpad);
+    const int64_t row = i / Kpad;
+    float v = 0.f;
+    if (k < K) {
+      const int p = (int)(row % P), b = (int)(row / P);
+      const int c = k / (ps * ps), ij = k % (ps * ps), ii = ij / ps, jj = ij % ps;
+      const int py = p / gw, px = p % gw;
+      v = x[(((int64_t)b * C + c) * HW + py * ps + ii) * HW + px * ps + jj];
+    }
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    planes[i] = h;
+    planes[i + plane_stride] = l;
+  }
+}
+
+// t[b, 0, :] = cls + pos[0];  t[b, 1+p, :] = tmp[b*P + p, :] + pos[1+p]      (vit.py:279-280)
+__global__ void assemble_tokens_kernel(const float* __restrict__ tmp, const float* __restrict__ cls, const float* __restrict__ pos,
+                                       int B, int N, int D, float* __restrict__ t) {
+  const int64_t total4 = (int64_t)B * N * D / 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i * 4;
+    const int d = (int)(e % D);
+    const int64_t tok = e / D;
+    const int n = (int)(tok % N), b = (int)(tok / N);
+    const float4 pp = *reinterpret_cast<const float4*>(pos + (int64_t)n * D + d);
+    float4 v;
+    if (n == 0) v = *reinterpret_cast<const float4*>(cls + d);
+    else v = *reinterpret_cast<const float4*>(tmp + ((int64_t)b * (N - 1) + n - 1) * D + d);
+    *reinterpret_cast<float4*>(t + e) = make_float4(v.x + pp.x, v.y + pp.y, v.z + pp.z, v.w + pp.w);
+  }
+}
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w];
+  return s;
+}
+
+// final LayerNorm of the CLS row + classifier head (vit.py:282, 298, 304).  One CTA (256 threads) per image.
+__global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ t, int N, int D, int C, float eps,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ Wh, const float* __restrict__ bh,
+                                                       float* __restrict__ feat, float* __restrict__ logits, float* __restrict__ xhat,
+                                                       float* __restrict__ rstd_out) {
+  extern __shared__ float sm[];
+  float* y = sm;         // [D]
+  float* red = sm + D;   // [8]
+  const int b = blockIdx.x;
+  const float* row = t + (int64_t)b * N * D;
+  float s = 0.f;
+  for (int d = threadIdx.x; d < D; d += 256) s += row[d];
+  const float mean = block_sum_256(s, red) / (float)D;
+  float q = 0.f;
+  for (int d = threadIdx.x; d < D; d += 256) { const float a = row[d] - mean; q += a * a; }
+  const float var = block_sum_256(q, red) / (float)D;
+  const float rstd = rsqrtf(var + eps);
+  for (int d = threadIdx.x; d < D; d += 256) {
+    const float xh = (row[d] - mean) * rstd;
+    const float v = xh * gamma[d] + beta[d];
+    y[d] = v;
+    feat[(int64_t)b * D + d] = v;
+    if (xhat) xhat[(int64_t)b * D + d] = xh;
+  }
+  if (threadIdx.x == 0 && rstd_out) rstd_out[b] = rstd;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = warp; c < C; c += 8) {
+    const float* w = Wh + (int64_t)c * D;
+    float acc = 0.f;
+    for (int d = lane; d < D; d += 32) acc = fmaf(y[d], w[d], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) logits[(int64_t)b * C + c] = acc + bh[c];
+  }
+}
+
+// per image: dfeat = dlogits Wh (+ dfeat_in);  LayerNorm backward of the CLS row -> dt[b*N + 0, :]
+__global__ void __launch_bounds__(256) head_bwd_rows_kernel(const float* __restrict__ dlogits, const float* __restrict__ dfeat_in, int N, int D,
+                                                            int C, const float* __restrict__ gamma, const float* __restrict__ Wh,
+                                                            const float* __restrict__ xhat, const float* __restrict__ rstd,
+                                                            float* __restrict__ dfeat_out, float* __restrict__ dt) {
+  extern __shared__ float sm[];
+  float* dl = sm;        // [C]
+  float* red = sm + C;   // [8]
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += 256) dl[c] = dlogits[(int64_t)b * C + c];
+  __syncthreads();
+  float s1 = 0.f, s2 = 0.f;
+  // D <= 1024 -> at most 4 columns per thread
+  float g[4], xh[4];
+  int nd = 0;
+  for (int d = threadIdx.x; d < D; d += 256, ++nd) {
+    float acc = dfeat_in ? dfeat_in[(int64_t)b * D + d] : 0.f;
+    for (int c = 0; c < C; ++c) acc = fmaf(dl[c], Wh[(int64_t)c * D + d], acc);
+    dfeat_out[(int64_t)b * D + d] = acc;
+    xh[nd] = xhat[(int64_t)b * D + d];
+    g[nd] = acc * gamma[d];
+    s1 += g[nd];
+    s2 += g[nd] * xh[nd];
+  }
+  s1 = block_sum_256(s1, red) / (float)D;
+  s2 = block_sum_256(s2, red) / (float)D;
+  const float rs = rstd[b];
+  nd = 0;
+  for (int d = threadIdx.x; d < D; d += 256, ++nd) dt[(int64_t)b * N * D + d] = rs * (g[nd] - s1 - xh[nd] * s2);
+}
+
+// parameter gradients of the head: dWh[c,d] = sum_b dlogits[b,c] feat[b,d]; dbh[c]; dgamma[d] = sum_b dfeat[b,d] xhat[b,d]; dbeta[d]
+__global__ void head_bwd_params_kernel(const float* __restrict__ dlogits, const float* __restrict__ feat, const float* __restrict__ dfeat,
+                                       const float* __restrict__ xhat, int Bg, int D, int C, float* __restrict__ dWh,
+                                       float* __restrict__ dbh, float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nW = (int64_t)C * D;
+  if (i < nW) {
+    const int c = (int)(i / D), d = (int)(i % D);
+    float acc = 0.f;
+    for (int b = 0; b < Bg; ++b) acc = fmaf(dlogits[(int64_t)b * C + c], feat[(int64_t)b * D + d], acc);
+    dWh[i] = accumulate ? dWh[i] + acc : acc;
+  } else if (i < nW + C) {
+    const int c = (int)(i - nW);
+    float acc = 0.f;
+    for (int b = 0; b < Bg; ++b) acc += dlogits[(int64_t)b * C + c];
+    dbh[c] = accumulate ? dbh[c] + acc : acc;
+  } else if (i < nW + C + D) {
+    const int d = (int)(i - nW - C);
+    float ag = 0.f, ab = 0.f;
+    for (int b = 0; b < Bg; ++b) {
+      const float df = dfeat[(int64_t)b * D + d];
+      ag = fmaf(df, xhat[(int64_t)b * D + d], ag);
+      ab += df;
+    }
+    dgamma[d] = accumulate ? dgamma[d] + ag : ag;
+    dbeta[d] = accumulate ? dbeta[d] + ab : ab;
+  }
+}
+
+// dpos[n,d] = sum_b dt[b,n,d];  dcls[d] = sum_b dt[b,0,d]
+__global__ void embed_grad_kernel(const float* __restrict__ dt, int Bg, int N, int D, float* __restrict__ dpos, float* __restrict__ dcls,
+                                  int accumulate) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)N * D) return;
+  float acc = 0.f;
+  for (int b = 0; b < Bg; ++b) acc += dt[(int64_t)b * N * D + i];
+  dpos[i] = accumulate ? dpos[i] + acc : acc;
+  if (i < D) dcls[i] = accumulate ? dcls[i] + acc : acc;
+}
+
+// dtmp planes[(b*P + p), d] = split(dt[(b*N + 1 + p), d])
+__global__ void gather_patch_grad_kernel(const float* __restrict__ dt, int Bg, int N, int D, __nv_bfloat16* __restrict__ planes,
+                                         int64_t plane_stride) {
+  const int P = N - 1;
+  const int64_t total2 = (int64_t)Bg * P * D / 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total2; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i * 2;
+    const int d = (int)(e % D);
+    const int64_t row = e / D;
+    const int p = (int)(row % P), b = (int)(row / P);
+    const float2 v = *reinterpret_cast<const float2*>(dt + ((int64_t)b * N + 1 + p) * D + d);
+    uint32_t h, l;
+    split2(v.x, v.y, h, l);
+    *reinterpret_cast<uint32_t*>(planes + e) = h;
+    *reinterpret_cast<uint32_t*>(planes + e + plane_stride) = l;
+  }
+}
+
+// out[r, 0:cols) (+)= src[r, 0:cols) with different leading dimensions
+__global__ void copy_cols_kernel(const float* __restrict__ src, int64_t lds, int rows, int cols, float* __restrict__ dst, int64_t ldd,
+                                 int accumulate) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  const float v = src[(int64_t)r * lds + c];
+  float* d = dst + (int64_t)r * ldd + c;
+  *d = accumulate ? *d + v : v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace layout
+// ------------------------------------------------------------------------------------------------
+struct Dims {
+  int B, Bg, N, P, D, H, Hd, L, C, K, Kpad, hidden;
+  int64_t T, Tg;
+};
+
+static int make_dims(const srw_vit_config* c, int batch, int grad_batch, Dims& d) {
+  SRW_REQUIRE(c && batch > 0 && grad_batch >= 0 && grad_batch <= batch, "srw_vit: bad batch (%d, grad %d)", batch, grad_batch);
+  SRW_REQUIRE(c->patch_size > 0 && c->img_size % c->patch_size == 0, "srw_vit: img_size %% patch_size != 0");
+  SRW_REQUIRE(c->embed_dim % 64 == 0 && c->embed_dim <= 1024 && c->num_heads * 64 == c->embed_dim,
+              "srw_vit: embed_dim must be num_heads*64 and <= 1024 (got %d, %d heads)", c->embed_dim, c->num_heads);
+  SRW_REQUIRE(c->hidden_dim % 64 == 0 && c->depth > 0 && c->num_classes > 0, "srw_vit: bad hidden_dim/depth/num_classes");
+  const int gw = c->img_size / c->patch_size;
+  d.B = batch; d.Bg = grad_batch; d.P = gw * gw; d.N = d.P + 1; d.D = c->embed_dim; d.H = c->num_heads; d.Hd = 64;
+  d.L = c->depth; d.C = c->num_classes; d.K = c->in_chans * c->patch_size * c->patch_size; d.Kpad = (d.K + 63) / 64 * 64;
+  d.hidden = c->hidden_dim;
+  d.T = (int64_t)batch * d.N; d.Tg = (int64_t)grad_batch * d.N;
+  SRW_REQUIRE(d.K % 4 == 0, "srw_vit: in_chans*patch_size^2 must be a multiple of 4");
+  return SRW_OK;
+}
+
+struct Carver {
+  int64_t off = 0;
+  int64_t take(int64_t bytes) {
+    const int64_t o = off;
+    off += (bytes + 1023) / 1024 * 1024;
+    return o;
+  }
+};
+
+struct BlockBufs {
+  int64_t mean1, rstd1, mean2, rstd2, y1, qkv, o, lse, t_mid, y2, z, h;
+};
+
+struct Layout {
+  // forward (kept for backward)
+  int64_t patches, tmp_embed;
+  std::vector<int64_t> t;          // [L+1] fp32 [T, D]
+  std::vector<BlockBufs> blk;      // [L]
+  int64_t cls_xhat, cls_rstd, feat;
+  // backward scratch
+  int64_t dt, g, dz, dy, d_o, dqkv, delta, dfeat, dtmp, dwpe, splitk, colsum_ws, ln_ws;
+  int64_t splitk_floats;
+  int64_t total;
+};
+
+static int64_t splitk_for(int M, int N, int64_t K, int* split_out) {
+  // enough K slices to put >= ~2 CTAs on each of the 148 SMs, but at least 4 k-blocks (256 rows) per slice
+  const int tiles = cdiv(M, 128) * cdiv(N, 128);
+  int split = std::max(1, 296 / tiles);
+  const int kb = (int)cdiv64(K, 64);
+  split = std::min(split, std::max(1, kb / 4));
+  if (split_out) *split_out = split;
+  return (int64_t)split * M * N;
+}
+
+static Layout make_layout(const Dims& d) {
+  Layout L;
+  Carver c;
+  const int64_t T = d.T, D = d.D, F = d.hidden;
+  L.patches = c.take((int64_t)d.B * d.P * d.Kpad * 4);
+  L.tmp_embed = c.take((int64_t)d.B * d.P * D * 4);
+  L.t.resize(d.L + 1);
+  L.blk.resize(d.L);
+  for (int l = 0; l <= d.L; ++l) L.t[l] = c.take(T * D * 4);
+  for (int l = 0; l < d.L; ++l) {
+    BlockBufs& b = L.blk[l];
+    b.mean1 = c.take(T * 4); b.rstd1 = c.take(T * 4); b.mean2 = c.take(T * 4); b.rstd2 = c.take(T * 4);
+    b.y1 = c.take(T * D * 4); b.qkv = c.take(T * 3 * D * 4); b.o = c.take(T * D * 4);
+    b.lse = c.take((int64_t)d.B * d.H * d.N * 4);
+    b.t_mid = c.take(T * D * 4); b.y2 = c.take(T * D * 4); b.z = c.take(T * F * 4); b.h = c.take(T * F * 4);
+  }
+  L.cls_xhat = c.take((int64_t)d.B * D * 4);
+  L.cls_rstd = c.take((int64_t)d.B * 4);
+  L.feat = c.take((int64_t)d.B * D * 4);
+  const int64_t Tg = std::max<int64_t>(d.Tg, 1);
+  L.dt = c.take(Tg * D * 4); L.g = c.take(Tg * D * 4); L.dz = c.take(Tg * F * 4); L.dy = c.take(Tg * D * 4);
+  L.d_o = c.take(Tg * D * 4); L.dqkv = c.take(Tg * 3 * D * 4);
+  L.delta = c.take((int64_t)std::max(d.Bg, 1) * d.H * d.N * 4);
+  L.dfeat = c.take((int64_t)std::max(d.Bg, 1) * D * 4);
+  L.dtmp = c.take((int64_t)std::max(d.Bg, 1) * d.P * D * 4);
+  L.dwpe = c.take((int64_t)D * d.Kpad * 4);
+  int64_t sk = 0;
+  sk = std::max(sk, splitk_for(d.D, d.hidden, Tg, nullptr));
+  sk = std::max(sk, splitk_for(d.hidden, d.D, Tg, nullptr));
+  sk = std::max(sk, splitk_for(d.D, d.D, Tg, nullptr));
+  sk = std::max(sk, splitk_for(3 * d.D, d.D, Tg, nullptr));
+  sk = std::max(sk, splitk_for(d.D, d.Kpad, (int64_t)std::max(d.Bg, 1) * d.P, nullptr));
+  L.splitk_floats = sk;
+  L.splitk = c.take(sk * 4);
+  L.colsum_ws = c.take((int64_t)256 * std::max(3 * d.D, d.hidden) * 4);
+  L.ln_ws = c.take((int64_t)2 * 256 * D * 4);
+  L.total = c.off;
+  return L;
+}
+
+// parameter index helpers (state_dict order, see include/srw.h)
+enum { P_CLS = 0, P_POS = 1, P_PE_W = 2, P_PE_B = 3 };
+enum { B_N1W = 0, B_N1B, B_QKVW, B_QKVB, B_PROJW, B_PROJB, B_N2W, B_N2B, B_FC1W, B_FC1B, B_FC2W, B_FC2B };
+static inline int pblk(int l, int which) { return 4 + 12 * l + which; }
+static inline int ptail(int L, int which) { return 4 + 12 * L + which; }  // 0 norm.w, 1 norm.b, 2 head.w, 3 head.b
+
+// weight planes cache: per block qkv [3D,D], proj [D,D], fc1 [F,D], fc2 [D,F]; then patch-embed [D,Kpad]
+struct WOff { int64_t qkv, proj, fc1, fc2; };
+static int64_t weight_layout(const Dims& d, std::vector<WOff>& w, int64_t& pe) {
+  Carver c;
+  w.resize(d.L);
+  for (int l = 0; l < d.L; ++l) {
+    w[l].qkv = c.take((int64_t)3 * d.D * d.D * 4);
+    w[l].proj = c.take((int64_t)d.D * d.D * 4);
+    w[l].fc1 = c.take((int64_t)d.hidden * d.D * 4);
+    w[l].fc2 = c.take((int64_t)d.D * d.hidden * 4);
+  }
+  pe = c.take((int64_t)d.D * d.Kpad * 4);
+  return c.off;
+}
+
+static int split_to(const float* x, int64_t ldx, int rows, int cols, void* planes, int64_t ldp, const float* row_scale, int rows_per_scale,
+                    cudaStream_t s) {
+  srw_split_args a = {};
+  a.x = x; a.ldx = ldx; a.rows = rows; a.cols = cols; a.row_scale = row_scale; a.rows_per_scale = rows_per_scale;
+  a.planes = planes; a.ldp = ldp; a.plane_stride = (int64_t)rows * ldp;
+  return srw_split_planes(&a, s);
+}
+
+struct Gemm {
+  srw_gemm_args g = {};
+  Gemm(int M, int N, int K, int impl) { g.M = M; g.N = N; g.K = K; g.impl = impl; g.split_k = 1; }
+  // operand stored [rows, ld] as planes with `rows_total` rows per plane
+  Gemm& A(const void* p, int64_t ld, int64_t rows_total, int mn) { g.a = p; g.lda = ld; g.a_plane_stride = rows_total * ld; g.a_mn_major = mn; return *this; }
+  Gemm& Bm(const void* p, int64_t ld, int64_t rows_total, int mn) { g.b = p; g.ldb = ld; g.b_plane_stride = rows_total * ld; g.b_mn_major = mn; return *this; }
+  int run(cudaStream_t s) { return srw_gemm(&g, s); }
+};
+
+#define SRW_TRY(expr)        \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc) return _rc;     \
+  } while (0)
+
+static int wgrad(int M, int N, int64_t K, const void* a_planes, int64_t lda, int64_t a_rows, const void* b_planes, int64_t ldb, int64_t b_rows,
+                 float* ws, float* out, int64_t ldo, int accumulate, int impl, cudaStream_t s) {
+  // out[M,N] (+)= A^T B with A stored [K, M] and B stored [K, N] (token-major activations / gradients)
+  int split = 1;
+  splitk_for(M, N, K, &split);
+  Gemm g(M, N, (int)K, impl);
+  g.A(a_planes, lda, a_rows, 1).Bm(b_planes, ldb, b_rows, 1);
+  g.g.epilogue = SRW_EPI_SPLITK; g.g.split_k = split; g.g.workspace = ws;
+  SRW_TRY(g.run(s));
+  srw_splitk_reduce_args r = {};
+  r.workspace = ws; r.split_k = split; r.M = M; r.N = N; r.out = out; r.ldo = ldo; r.accumulate = accumulate;
+  return srw_splitk_reduce(&r, s);
+}
+
+static int colsum_planes(const void* planes, int64_t ld, int64_t rows_total, int rows, int cols, float* out, int accumulate, float* ws,
+                         cudaStream_t s) {
+  srw_colsum_args a = {};
+  a.planes = planes; a.ldp = ld; a.plane_stride = rows_total * ld; a.rows = rows; a.cols = cols; a.out = out; a.accumulate = accumulate;
+  a.workspace = ws;
+  return srw_colsum(&a, s);
+}
+
+}  // namespace srw
+
+using namespace srw;
+
+extern "C" int64_t srw_vit_weight_planes_bytes(const srw_vit_config* c) {
+  Dims d;
+  if (make_dims(c, 1, 0, d)) return -1;
+  std::vector<WOff> w;
+  int64_t pe;
+  return weight_layout(d, w, pe);
+}
+
+extern "C" int64_t srw_vit_workspace_bytes(const srw_vit_config* c, int batch, int grad_batch) {
+  Dims d;
+  if (make_dims(c, batch, grad_batch, d)) return -1;
+  return make_layout(d).total;
+}
+
+extern "C" int srw_vit_prepare_weights(const srw_vit_config* c, const float* const* params, void* weight_planes, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  Dims d;
+  SRW_TRY(make_dims(c, 1, 0, d));
+  SRW_REQUIRE(params && weight_planes, "srw_vit_prepare_weights: null pointer");
+  std::vector<WOff> w;
+  int64_t pe;
+  weight_layout(d, w, pe);
+  uint8_t* base = reinterpret_cast<uint8_t*>(weight_planes);
+  for (int l = 0; l < d.L; ++l) {
+    SRW_TRY(split_to(params[pblk(l, B_QKVW)], d.D, 3 * d.D, d.D, base + w[l].qkv, d.D, nullptr, 1, s));
+    SRW_TRY(split_to(params[pblk(l, B_PROJW)], d.D, d.D, d.D, base + w[l].proj, d.D, nullptr, 1, s));
+    SRW_TRY(split_to(params[pblk(l, B_FC1W)], d.D, d.hidden, d.D, base + w[l].fc1, d.D, nullptr, 1, s));
+    SRW_TRY(split_to(params[pblk(l, B_FC2W)], d.hidden, d.D, d.hidden, base + w[l].fc2, d.hidden, nullptr, 1, s));
+  }
+  // patch-embed weight [D, K] -> planes [D, Kpad], zero padded
+  SRW_CUDA(cudaMemsetAsync(base + pe, 0, (size_t)d.D * d.Kpad * 4, s));
+  SRW_TRY(split_to(params[P_PE_W], d.K, d.D, d.K, base + pe, d.Kpad, nullptr, 1, s));
+  return SRW_OK;
+}
+
+extern "C" int srw_vit_forward(const srw_vit_fwd_args* a, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  SRW_REQUIRE(a && a->cfg && a->params && a->weight_planes && a->x && a->logits && a->feat && a->workspace, "srw_vit_forward: null pointer");
+  Dims d;
+  SRW_TRY(make_dims(a->cfg, a->batch, a->grad_batch, d));
+  const Layout L = make_layout(d);
+  SRW_REQUIRE(a->workspace_bytes >= L.total, "srw_vit_forward: workspace too small (%lld < %lld)", (long long)a->workspace_bytes, (long long)L.total);
+  SRW_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 1023) == 0, "srw_vit_forward: workspace must be 1024-byte aligned");
+  std::vector<WOff> w;
+  int64_t pe;
+  weight_layout(d, w, pe);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
+  const uint8_t* wp = reinterpret_cast<const uint8_t*>(a->weight_planes);
+  const float* const* P = a->params;
+  auto F32 = [&](int64_t off) { return reinterpret_cast<float*>(ws + off); };
+  const int T = (int)d.T, D = d.D, Fh = d.hidden, impl = a->gemm_impl;
+  const float eps = a->cfg->ln_eps;
+
+  // ---- patch embedding ----
+  {
+    const int64_t total = (int64_t)d.B * d.P * d.Kpad;
+    patchify_kernel<<<(int)std::min<int64_t>(cdiv64(total, 256), 148 * 16), 256, 0, s>>>(
+        a->x, d.B, a->cfg->in_chans, a->cfg->img_size, a->cfg->patch_size, d.Kpad, reinterpret_cast<__nv_bfloat16*>(ws + L.patches), total);
+    g_launches++;
+    SRW_LAUNCH_CHECK();
+    Gemm g(d.B * d.P, D, d.Kpad, impl);
+    g.A(ws + L.patches, d.Kpad, (int64_t)d.B * d.P, 0).Bm(wp + pe, d.Kpad, D, 0);
+    g.g.epilogue = SRW_EPI_F32; g.g.bias = P[P_PE_B]; g.g.out_f32 = F32(L.tmp_embed); g.g.ldo = D;
+    SRW_TRY(g.run(s));
+    const int64_t total4 = (int64_t)T * D / 4;
+    assemble_tokens_kernel<<<(int)std::min<int64_t>(cdiv64(total4, 256), 148 * 16), 256, 0, s>>>(F32(L.tmp_embed), P[P_CLS], P[P_POS], d.B, d.N, D,
+                                                                                                F32(L.t[0]));
+    g_launches++;
+    SRW_LAUNCH_CHECK();
+  }
+  // ---- blocks ----
+  for (int l = 0; l < d.L; ++l) {
+    const BlockBufs& b = L.blk[l];
+    const float* ds_attn = a->drop_scale ? a->drop_scale + ((int64_t)l * 2 + 0) * d.B : nullptr;
+    const float* ds_mlp = a->drop_scale ? a->drop_scale + ((int64_t)l * 2 + 1) * d.B : nullptr;
+    srw_layernorm_fwd_args ln = {};
+    ln.x = F32(L.t[l]); ln.ldx = D; ln.rows = T; ln.cols = D; ln.eps = eps; ln.gamma = P[pblk(l, B_N1W)]; ln.beta = P[pblk(l, B_N1B)];
+    ln.mean = F32(b.mean1); ln.rstd = F32(b.rstd1); ln.y_planes = ws + b.y1; ln.ldp = D; ln.plane_stride = (int64_t)T * D;
+    SRW_TRY(srw_layernorm_fwd(&ln, s));
+    {
+      Gemm g(T, 3 * D, D, impl);
+      g.A(ws + b.y1, D, T, 0).Bm(wp + w[l].qkv, D, 3 * D, 0);
+      g.g.epilogue = SRW_EPI_PLANES; g.g.bias = P[pblk(l, B_QKVB)]; g.g.out_planes = ws + b.qkv; g.g.ldp = 3 * D; g.g.out_plane_stride = (int64_t)T * 3 * D;
+      SRW_TRY(g.run(s));
+    }
+    {
+      srw_attn_fwd_args at = {};
+      at.B = d.B; at.N = d.N; at.H = d.H; at.head_dim = 64; at.scale = 0.125f;
+      at.qkv = ws + b.qkv; at.ld_qkv = 3 * D; at.qkv_plane_stride = (int64_t)T * 3 * D;
+      at.o = ws + b.o; at.ld_o = D; at.o_plane_stride = (int64_t)T * D; at.lse = F32(b.lse);
+      SRW_TRY(srw_attn_fwd(&at, s));
+    }
+    {
+      Gemm g(T, D, D, impl);
+      g.A(ws + b.o, D, T, 0).Bm(wp + w[l].proj, D, D, 0);
+      g.g.epilogue = SRW_EPI_RESID; g.g.bias = P[pblk(l, B_PROJB)]; g.g.resid = F32(L.t[l]); g.g.ldr = D; g.g.row_scale = ds_attn;
+      g.g.rows_per_scale = d.N; g.g.out_f32 = F32(b.t_mid); g.g.ldo = D;
+      SRW_TRY(g.run(s));
+    }
+    ln.x = F32(b.t_mid); ln.gamma = P[pblk(l, B_N2W)]; ln.beta = P[pblk(l, B_N2B)]; ln.mean = F32(b.mean2); ln.rstd = F32(b.rstd2);
+    ln.y_planes = ws + b.y2;
+    SRW_TRY(srw_layernorm_fwd(&ln, s));
+    {
+      Gemm g(T, Fh, D, impl);
+      g.A(ws + b.y2, D, T, 0).Bm(wp + w[l].fc1, D, Fh, 0);
+      g.g.epilogue = SRW_EPI_GELU; g.g.bias = P[pblk(l, B_FC1B)]; g.g.out_f32 = F32(b.z); g.g.ldo = Fh; g.g.out_planes = ws + b.h; g.g.ldp = Fh;
+      g.g.out_plane_stride = (int64_t)T * Fh;
+      SRW_TRY(g.run(s));
+    }
+    {
+      Gemm g(T, D, Fh, impl);
+      g.A(ws + b.h, Fh, T, 0).Bm(wp + w[l].fc2, Fh, D, 0);
+      g.g.epilogue = SRW_EPI_RESID; g.g.bias = P[pblk(l, B_FC2B)]; g.g.resid = F32(b.t_mid); g.g.ldr = D; g.g.row_scale = ds_mlp;
+      g.g.rows_per_scale = d.N; g.g.out_f32 = F32(L.t[l + 1]); g.g.ldo = D;
+      SRW_TRY(g.run(s));
+    }
+  }
+  // ---- final norm (CLS rows) + head ----
+  head_fwd_kernel<<<d.B, 256, (D + 8) * sizeof(float), s>>>(F32(L.t[d.L]), d.N, D, d.C, eps, P[ptail(d.L, 0)], P[ptail(d.L, 1)], P[ptail(d.L, 2)],
+                                                            P[ptail(d.L, 3)], a->feat, a->logits, F32(L.cls_xhat), F32(L.cls_rstd));
+  g_launches++;
+  SRW_LAUNCH_CHECK();
+  SRW_CUDA(cudaMemcpyAsync(F32(L.feat), a->feat, (size_t)d.B * D * 4, cudaMemcpyDeviceToDevice, s));
+  return SRW_OK;
+}
+
+extern "C" int srw_vit_backward(const srw_vit_bwd_args* a, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  SRW_REQUIRE(a && a->cfg && a->params && a->weight_planes && a->dlogits && a->grads && a->workspace, "srw_vit_backward: null pointer");
+  Dims d;
+  SRW_TRY(make_dims(a->cfg, a->batch, a->grad_batch, d));
+  SRW_REQUIRE(d.Bg > 0, "srw_vit_backward: grad_batch must be > 0");
+  const Layout L = make_layout(d);
+  SRW_REQUIRE(a->workspace_bytes >= L.total, "srw_vit_backward: workspace too small");
+  std::vector<WOff> w;
+  int64_t pe;
+  weight_layout(d, w, pe);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
+  const uint8_t* wp = reinterpret_cast<const uint8_t*>(a->weight_planes);
+  const float* const* P = a->params;
+  float* const* G = a->grads;
+  auto F32 = [&](int64_t off) { return reinterpret_cast<float*>(ws + off); };
+  const int T = (int)d.T, Tg = (int)d.Tg, D = d.D, Fh = d.hidden, impl = a->gemm_impl, acc = a->accumulate_grads ? 1 : 0;
+  float* sk = F32(L.splitk);
+  float* cws = F32(L.colsum_ws);
+  float* dt = F32(L.dt);
+
+  // ---- head + final norm ----
+  SRW_CUDA(cudaMemsetAsync(dt, 0, (size_t)Tg * D * 4, s));
+  head_bwd_rows_kernel<<<d.Bg, 256, (d.C + 8) * sizeof(float), s>>>(a->dlogits, a->dfeat, d.N, D, d.C, P[ptail(d.L, 0)], P[ptail(d.L, 2)],
+                                                                    F32(L.cls_xhat), F32(L.cls_rstd), F32(L.dfeat), dt);
+  g_launches++;
+  SRW_LAUNCH_CHECK();
+  {
+    const int64_t n = (int64_t)d.C * D + d.C + D;
+    head_bwd_params_kernel<<<(int)cdiv64(n, 256), 256, 0, s>>>(a->dlogits, F32(L.feat), F32(L.dfeat), F32(L.cls_xhat), d.Bg, D, d.C,
+                                                               G[ptail(d.L, 2)], G[ptail(d.L, 3)], G[ptail(d.L, 0)], G[ptail(d.L, 1)], acc);
+    g_launches++;
+    SRW_LAUNCH_CHECK();
+  }
+  // ---- blocks ----
+  for (int l = d.L - 1; l >= 0; --l) {
+    const BlockBufs& b = L.blk[l];
+    const float* ds_attn = a->drop_scale ? a->drop_scale + ((int64_t)l * 2 + 0) * d.B : nullptr;
+    const float* ds_mlp = a->drop_scale ? a->drop_scale + ((int64_t)l * 2 + 1) * d.B : nullptr;
+    // MLP branch:  t_out = t_mid + s * (gelu(LN2(t_mid) W1^T + b1) W2^T + b2)
+    SRW_TRY(split_to(dt, D, Tg, D, ws + L.g, D, ds_mlp, d.N, s));
+    SRW_TRY(colsum_planes(ws + L.g, D, Tg, Tg, D, G[pblk(l, B_FC2B)], acc, cws, s));
+    SRW_TRY(wgrad(D, Fh, Tg, ws + L.g, D, Tg, ws + b.h, Fh, T, sk, G[pblk(l, B_FC2W)], Fh, acc, impl, s));
+    {
+      Gemm g(Tg, Fh, D, impl);  // dz = (g W2) * gelu'(z)
+      g.A(ws + L.g, D, Tg, 0).Bm(wp + w[l].fc2, Fh, D, 1);
+      g.g.epilogue = SRW_EPI_DGELU; g.g.aux = F32(b.z); g.g.ldaux = Fh; g.g.out_planes = ws + L.dz; g.g.ldp = Fh; g.g.out_plane_stride = (int64_t)Tg * Fh;
+      SRW_TRY(g.run(s));
+    }
+    SRW_TRY(colsum_planes(ws + L.dz, Fh, Tg, Tg, Fh, G[pblk(l, B_FC1B)], acc, cws, s));
+    SRW_TRY(wgrad(Fh, D, Tg, ws + L.dz, Fh, Tg, ws + b.y2, D, T, sk, G[pblk(l, B_FC1W)], D, acc, impl, s));
+    {
+      Gemm g(Tg, D, Fh, impl);  // dy2 = dz W1
+      g.A(ws + L.dz, Fh, Tg, 0).Bm(wp + w[l].fc1, D, Fh, 1);
+      g.g.epilogue = SRW_EPI_F32; g.g.out_f32 = F32(L.dy); g.g.ldo = D;
+      SRW_TRY(g.run(s));
+    }
+    srw_layernorm_bwd_args lb = {};
+    lb.dy = F32(L.dy); lb.lddy = D; lb.x = F32(b.t_mid); lb.ldx = D; lb.rows = Tg; lb.cols = D; lb.gamma = P[pblk(l, B_N2W)];
+    lb.mean = F32(b.mean2); lb.rstd = F32(b.rstd2); lb.dx = dt; lb.lddx = D; lb.accumulate_dx = 1;
+    lb.dgamma = G[pblk(l, B_N2W)]; lb.dbeta = G[pblk(l, B_N2B)]; lb.accumulate_dparams = acc; lb.workspace = F32(L.ln_ws);
+    SRW_TRY(srw_layernorm_bwd(&lb, s));
+    // attention branch:  t_mid = t_in + s * (attn(LN1(t_in)) Wp^T + bp)
+    SRW_TRY(split_to(dt, D, Tg, D, ws + L.g, D, ds_attn, d.N, s));
+    SRW_TRY(colsum_planes(ws + L.g, D, Tg, Tg, D, G[pblk(l, B_PROJB)], acc, cws, s));
+    SRW_TRY(wgrad(D, D, Tg, ws + L.g, D, Tg, ws + b.o, D, T, sk, G[pblk(l, B_PROJW)], D, acc, impl, s));
+    {
+      Gemm g(Tg, D, D, impl);  // d_o = g Wp
+      g.A(ws + L.g, D, Tg, 0).Bm(wp + w[l].proj, D, D, 1);
+      g.g.epilogue = SRW_EPI_PLANES; g.g.out_planes = ws + L.d_o; g.g.ldp = D; g.g.out_plane_stride = (int64_t)Tg * D;
+      SRW_TRY(g.run(s));
+    }
+    {
+      srw_attn_bwd_args at = {};
+      at.B = d.Bg; at.N = d.N; at.H = d.H; at.head_dim = 64; at.scale = 0.125f;
+      at.qkv = ws + b.qkv; at.ld_qkv = 3 * D; at.qkv_plane_stride = (int64_t)T * 3 * D;
+      at.o = ws + b.o; at.ld_o = D; at.o_plane_stride = (int64_t)T * D;
+      at.d_o = ws + L.d_o; at.ld_do = D; at.do_plane_stride = (int64_t)Tg * D;
+      at.lse = F32(b.lse); at.delta = F32(L.delta);
+      at.dqkv = ws + L.dqkv; at.ld_dqkv = 3 * D; at.dqkv_plane_stride = (int64_t)Tg * 3 * D;
+      SRW_TRY(srw_attn_bwd(&at, s));
+    }
+    SRW_TRY(colsum_planes(ws + L.dqkv, 3 * D, Tg, Tg, 3 * D, G[pblk(l, B_QKVB)], acc, cws, s));
+    SRW_TRY(wgrad(3 * D, D, Tg, ws + L.dqkv, 3 * D, Tg, ws + b.y1, D, T, sk, G[pblk(l, B_QKVW)], D, acc, impl, s));
+    {
+      Gemm g(Tg, D, 3 * D, impl);  // dy1 = dqkv Wqkv
+      g.A(ws + L.dqkv, 3 * D, Tg, 0).Bm(wp + w[l].qkv, D, 3 * D, 1);
+      g.g.epilogue = SRW_EPI_F32; g.g.out_f32 = F32(L.dy); g.g.ldo = D;
+      SRW_TRY(g.run(s));
+    }
+    lb.x = F32(L.t[l]); lb.gamma = P[pblk(l, B_N1W)]; lb.mean = F32(b.mean1); lb.rstd = F32(b.rstd1);
+    lb.dgamma = G[pblk(l, B_N1W)]; lb.dbeta = G[pblk(l, B_N1B)];
+    SRW_TRY(srw_layernorm_bwd(&lb, s));
+  }
+  // ---- embedding ----
+  {
+    const int64_t n = (int64_t)d.N * D;
+    embed_grad_kernel<<<(int)cdiv64(n, 256), 256, 0, s>>>(dt, d.Bg, d.N, D, G[P_POS], G[P_CLS], acc);
+    g_launches++;
+    SRW_LAUNCH_CHECK();
+    const int64_t rows = (int64_t)d.Bg * d.P;
+    const int64_t total2 = rows * D / 2;
+    gather_patch_grad_kernel<<<(int)std::min<int64_t>(cdiv64(total2, 256), 148 * 16), 256, 0, s>>>(dt, d.Bg, d.N, D, reinterpret_cast<__nv_bfloat16*>(ws + L.dtmp),
+                                                                                                 rows * D);
+    g_launches++;
+    SRW_LAUNCH_CHECK();
+    SRW_TRY(colsum_planes(ws + L.dtmp, D, rows, (int)rows, D, G[P_PE_B], acc, cws, s));
+    SRW_TRY(wgrad(D, d.Kpad, rows, ws + L.dtmp, D, rows, ws + L.patches, d.Kpad, (int64_t)d.B * d.P, sk, F32(L.dwpe), d.Kpad, 0, impl, s));
+    const int64_t nw = (int64_t)D * d.K;
+    copy_cols_kernel<<<(int)cdiv64(nw, 256), 256, 0, s>>>(F32(L.dwpe), d.Kpad, D, d.K, G[P_PE_W], d.K, acc);
+    g_launches++;
+    SRW_LAUNCH_CHECK();
+  }
+  return SRW_OK;
+}

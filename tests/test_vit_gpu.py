@@ -1,0 +1,76 @@
+"""-m gpu: the native ViT engine (srw_vit_forward/backward through the nn.Module boundary) against the oracle's
+vit_forward + torch autograd on CPU fp32, same deterministic weights and images.
+Tolerances (BASELINE.json north_star): logits/feat within 1e-3 abs; gradients within 1e-3 relative to the tensor's
+largest entry."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(depth, num_classes=100, head_gain=4.0, seed=0):
+    from oracle import ssl_oracle as O
+    from semireward_b200 import detgen
+    from semireward_b200.nets import vit_small_patch2_32
+    vc = O.ViTConfig(depth=depth, num_classes=num_classes)
+    p = {n: torch.from_numpy(detgen.fill_param(n, s, seed)) for n, s in vc.param_shapes()}
+    p["head.weight"] = p["head.weight"] * head_gain
+    model = vit_small_patch2_32(num_classes=num_classes, depth=depth, drop_path_rate=0.0)
+    model.load_state_dict(p)
+    model = model.cuda().train()
+    return O, vc, p, model
+
+
+@pytest.mark.parametrize("depth,use_drop", [(2, False), (2, True), (12, False)])
+def test_vit_forward_backward_vs_oracle(depth, use_drop):
+    from semireward_b200 import detgen
+    O, vc, p, model = _setup(depth)
+    batch = detgen.ssl_batch(8, 1, 100, 50000, seed=1, step=0)
+    # engine order: rows that carry gradient first (labelled, strong), weak rows last
+    x = torch.from_numpy(np.concatenate([batch["x_lb"], batch["x_ulb_s"], batch["x_ulb_w"]]))
+    B, Bg = x.shape[0], 16
+    drop = None
+    if use_drop:
+        g = torch.Generator().manual_seed(5)
+        drop = (torch.bernoulli(torch.full((depth, 2, B), 0.7), generator=g) / 0.7)
+    out = model(x.cuda(), grad_batch=Bg, drop_scale=drop.cuda() if drop is not None else None)
+    logits, feat = out["logits"], out["feat"]
+    # oracle
+    po = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    lo, fo = O.vit_forward(po, x, vc, drop)
+    err_l = (logits.cpu() - lo.detach()).abs().max().item()
+    err_f = (feat.cpu() - fo.detach()).abs().max().item()
+    print(f"depth {depth} drop {use_drop}: logits err {err_l:.3e} (max |logit| {lo.abs().max().item():.2f}), feat err {err_f:.3e}")
+    assert err_l < 1e-3 and err_f < 1e-3
+    # backward: random cotangents on the gradient-carrying rows only
+    g = torch.Generator().manual_seed(7)
+    cl = torch.randn(B, vc.num_classes, generator=g)
+    cf = torch.randn(B, vc.embed_dim, generator=g) * 0.1
+    cl[Bg:] = 0
+    cf[Bg:] = 0
+    loss = (logits * cl.cuda()).sum() + (feat * cf.cuda()).sum()
+    loss.backward()
+    ((lo * cl).sum() + (fo * cf).sum()).backward()
+    worst = 0.0
+    for name, prm in model.named_parameters():
+        ref = po[name].grad
+        got = prm.grad.cpu()
+        scale = ref.abs().max().item()
+        err = (got - ref).abs().max().item()
+        rel = err / max(scale, 1e-12)
+        worst = max(worst, rel)
+        assert rel < 1e-3, f"{name}: grad err {err:.3e} vs max |grad| {scale:.3e}"
+    print(f"worst relative gradient error {worst:.3e}")
+
+
+def test_vit_simt_twin_matches_tcgen05():
+    """The SIMT verification GEMM (fp32 FMA over the same planes) and the tcgen05 path agree to fp32-accumulate level."""
+    from semireward_b200 import _lib as L, detgen
+    O, vc, p, model = _setup(2)
+    x = torch.from_numpy(detgen.normal("x", (4, 3, 32, 32), 3)).cuda()
+    with torch.no_grad():
+        a = model(x)["logits"]
+        model.gemm_impl = L.GEMM_SIMT
+        b = model(x)["logits"]
+    assert (a - b).abs().max().item() < 1e-3
