@@ -153,6 +153,11 @@ typedef struct {
 int64_t srw_vit_weight_planes_bytes(const srw_vit_config* c);           /* split (+transposed) weight cache */
 int64_t srw_vit_workspace_bytes(const srw_vit_config* c, int batch, int grad_batch);
 
+/* Where parameter `param_index` (state_dict order) lives inside the weight-plane cache: byte offset of its hi plane,
+ * logical columns, leading dimension and plane stride (elements).  Returns SRW_ERR_ARG for parameters that have no
+ * planes (biases, norms, cls/pos, head).  Lets the fused optimizer rewrite the cache in place. */
+int srw_vit_weight_plane_slot(const srw_vit_config* c, int param_index, int64_t* byte_offset, int* cols, int* ldp, int64_t* plane_stride);
+
 /* Refresh the split-plane weight cache from the fp32 parameters (call after every optimizer step). */
 int srw_vit_prepare_weights(const srw_vit_config* c, const float* const* params, void* weight_planes, void* stream);
 
@@ -194,7 +199,7 @@ typedef struct {
   float* reward;                               /* [B] */
   float* workspace;                            /* >= srw_rewarder_workspace_floats(B) */
 } srw_rewarder_fwd_args;
-int64_t srw_rewarder_workspace_floats(int B, int feature_dim);
+int64_t srw_rewarder_workspace_floats(int B, int feature_dim);  /* also covers srw_rewarder_train */
 int srw_rewarder_fwd(const srw_rewarder_fwd_args* a, void* stream);
 
 /* Generator.forward (semireward.py:21-24) followed by .long() (srflexmatch.py:157-158): integer fake labels. */
@@ -212,48 +217,77 @@ int srw_generator_fwd(const srw_generator_fwd_args* a, void* stream);
  * one torch.optim.Adam step (lr, betas .9/.999, eps 1e-8) on the 17 Rewarder tensors.  m/v = Adam moments, same order. */
 typedef struct {
   int B, feature_dim, label_rows, num_classes;
-  float* const* rp; float* const* m; float* const* v;
+  float* const* rp; float* const* g; float* const* m; float* const* v;   /* params, grad scratch, Adam moments */
   const float* feats; int64_t ld_feats;
   const int64_t* gen_labels; const int64_t* true_labels;
   float lr; int step;                          /* step = t (1-based) for bias correction */
   float* losses;                               /* [2] generator_loss, rewarder_loss */
-  float* workspace;                            /* >= srw_rewarder_train_workspace_floats(...) */
+  float* workspace;                            /* >= srw_rewarder_workspace_floats(B, feature_dim) */
 } srw_rewarder_train_args;
-int64_t srw_rewarder_train_workspace_floats(int B, int feature_dim, int label_rows);
 int srw_rewarder_train(const srw_rewarder_train_args* a, void* stream);
 
-/* FlexMatch step epilogue: everything between the backbone outputs and dlogits in SRFlexMatch.train_step
- * (srflexmatch.py:132-152, 210; srflexmatch/utils.py:23-63; hooks/pseudo_label.py:40; consistency.py:13-45;
- * cross_entropy.py:11-31).  One CTA.  Device-resident hook state replaces the host Counter (utils.py:25-29):
- * hist[c+1] = #entries of selected_label equal to c is maintained incrementally. */
+/* FlexMatchThresholdingHook.masking + update (srflexmatch/utils.py:23-63) fused with compute_prob (algorithmbase.py:332-333)
+ * and PseudoLabelingHook.gen_ulb_targets hard labels (hooks/pseudo_label.py:40).  One CTA.  The host Counter over all
+ * ulb_dest_len entries (utils.py:25-29) is replaced by a device-resident histogram kept incrementally:
+ * hist[c+1] = #entries of selected_label equal to c, hist[0] = #entries still -1. */
 typedef struct {
-  int B_lb, B_ulb, num_classes, ulb_dest_len;
-  const float* logits_lb; const float* logits_w; const float* logits_s; int64_t ld_logits;
-  const int64_t* y_lb; const int64_t* idx_ulb;
-  float p_cutoff; int thresh_warmup; float lambda_u;
-  int64_t* selected_label;  /* [ulb_dest_len] hook state, -1 = unused */
-  int32_t* hist;            /* [num_classes + 1] hook state: hist[0] counts the -1 bucket */
+  int B, num_classes, ulb_dest_len;
+  const float* logits_w; int64_t ld_logits;
+  const int64_t* idx_ulb;
+  float p_cutoff; int thresh_warmup;
+  int64_t* selected_label;  /* [ulb_dest_len] hook state */
+  int32_t* hist;            /* [num_classes + 1] hook state */
   float* classwise_acc;     /* [num_classes] hook state */
-  const float* reward;      /* [B_ulb] or NULL (stage 1); when given mask2 = reward >= mean(reward) */
-  int mask_only;            /* 1: only run the hook (mask, pseudo, state update), no losses (data_generator replays) */
-  const float* mask_in;     /* optional: use this mask instead of running the hook (stage-2 final pass) */
-  float* probs_w;           /* [B_ulb, C] out */
-  int64_t* pseudo;          /* [B_ulb] out */
-  float* mask; float* mask2;/* [B_ulb] out */
-  float* losses;            /* [4] sup, unsup, total, util_ratio */
-  float* dlogits_lb; float* dlogits_s; int64_t ld_dlogits; /* d total / d logits, may be NULL */
-} srw_flexmatch_epilogue_args;
-int srw_flexmatch_epilogue(const srw_flexmatch_epilogue_args* a, void* stream);
+  float* probs_w;           /* [B, C] out, row stride num_classes (may be NULL) */
+  int64_t* pseudo;          /* [B] out: argmax of probs_w */
+  float* mask;              /* [B] out */
+  float* max_probs;         /* [B] out (may be NULL) */
+} srw_flexmatch_mask_args;
+int srw_flexmatch_mask(const srw_flexmatch_mask_args* a, void* stream);
 
-/* ---- optimizer: torch.optim.AdamW over the reference's layer-decay groups (build.py:193-224) ------------------- */
+/* Losses of the SSL step and their gradient w.r.t. the logits (srflexmatch.py:132,100-102,152,210; cross_entropy.py:11-31;
+ * consistency.py:13-45):  sup = mean CE(logits_lb, y_lb);  mask2 = reward >= mean(reward) (when reward != NULL);
+ * unsup = mean_B(CE(logits_s, pseudo) * mask * mask2);  total = sup + lambda_u * unsup;  util = mean(mask).  One CTA. */
 typedef struct {
-  int num_tensors;
-  float* const* params; const float* const* grads; float* const* exp_avg; float* const* exp_avg_sq;
-  const int64_t* numel; const float* lr; const float* weight_decay;  /* per tensor (lr already includes schedule) */
-  float beta1, beta2, eps; int step; int zero_grads;
-  void* device_table;       /* >= srw_adamw_table_bytes(num_tensors), device memory for the pointer table */
+  int B_lb, B_ulb, num_classes;
+  const float* logits_lb; const float* logits_s; int64_t ld_logits;
+  const int64_t* y_lb; const int64_t* pseudo;
+  const float* mask;        /* [B_ulb] per-sample weight (0/1 for FlexMatch/FreeMatch, soft for SoftMatch) */
+  const float* reward;      /* [B_ulb] or NULL */
+  float lambda_u;
+  float* mask2;             /* [B_ulb] out (ones when reward == NULL; may be NULL) */
+  float* losses;            /* [4] out: sup, unsup, total, util_ratio */
+  float* dlogits_lb; float* dlogits_s; int64_t ld_dlogits;   /* d total / d logits (may be NULL) */
+} srw_ssl_loss_args;
+int srw_ssl_loss(const srw_ssl_loss_args* a, void* stream);
+
+/* ---- optimizer: torch.optim.AdamW / Adam over many tensors in one launch --------------------------------------------- */
+/* Replaces optimizer.step() of param_update.py:36 for the AdamW built by get_optimizer with the reference's layer-decay
+ * param groups (build.py:193-224, nets/utils.py:143-204), and model.zero_grad() is unnecessary because the backward
+ * overwrites gradients.  Same arithmetic as torch's single-tensor Adam: p *= 1 - lr*wd (decoupled) ; m.lerp_(g, 1-b1) ;
+ * v = v*b2 + (1-b2) g g ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).  Optionally rewrites the split-bf16 planes of the
+ * updated parameter in the same pass (the ViT engine's weight cache), saving srw_vit_prepare_weights.
+ * The table (one row per tensor) lives in DEVICE memory; the caller fills it with a plain copy of this struct array. */
+#define SRW_ADAMW_BLOCK_ELEMS 4096
+typedef struct {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+  void* planes;             /* NULL, or planes of this parameter: element i -> planes[(i / cols) * ldp + i % cols] */
+  int64_t numel;
+  int64_t plane_stride;
+  int32_t cols, ldp;
+  double lr;                /* param-group base lr (layer-decay scale included), before the schedule factor */
+  double weight_decay;
+  int64_t first_block;      /* exclusive prefix sum of ceil(numel / SRW_ADAMW_BLOCK_ELEMS) */
+} srw_adamw_row;
+
+typedef struct {
+  int num_tensors; int64_t total_blocks;
+  const srw_adamw_row* table;   /* device pointer */
+  double lr_factor;             /* schedule multiplier of this step (LambdaLR) */
+  double beta1, beta2, eps;
+  int step;                     /* 1-based */
+  int decoupled;                /* 1 = AdamW, 0 = Adam with L2 (grad += wd * p) */
 } srw_adamw_args;
-int64_t srw_adamw_table_bytes(int num_tensors);
 int srw_adamw_step(const srw_adamw_args* a, void* stream);
 
 #ifdef __cplusplus

@@ -510,7 +510,8 @@ class SSLOracle:
         lr_wd = {k: (self.cfg.sr_lr, 0.0) for k in names}
         self.gopt.step(self.gp, {}, {k: (self.cfg.sr_lr, 0.0) for k in self.gp})  # all grads None -> no-op
         self.ropt.step(self.rp, grads, lr_wd)
-        rec.update(sr_gen_label=gen.squeeze(1), sr_reward=reward.detach(), sr_target=target,
+        rec.update(sr_grads={k: (None if v is None else v.detach().clone()) for k, v in grads.items()},
+                   sr_gen_label=gen.squeeze(1), sr_reward=reward.detach(), sr_target=target,
                    sr_gen_loss=gen_loss.detach(), sr_rew_loss=rew_loss.detach())
 
     # -- public ---------------------------------------------------------------------------------

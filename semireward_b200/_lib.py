@@ -93,23 +93,36 @@ class GeneratorFwdArgs(C.Structure):
 
 class RewarderTrainArgs(C.Structure):
     _fields_ = [("B", i32), ("feature_dim", i32), ("label_rows", i32), ("num_classes", i32), ("rp", C.POINTER(vp)),
-                ("m", C.POINTER(vp)), ("v", C.POINTER(vp)), ("feats", vp), ("ld_feats", i64), ("gen_labels", vp),
-                ("true_labels", vp), ("lr", f32), ("step", i32), ("losses", vp), ("workspace", vp)]
+                ("g", C.POINTER(vp)), ("m", C.POINTER(vp)), ("v", C.POINTER(vp)), ("feats", vp), ("ld_feats", i64),
+                ("gen_labels", vp), ("true_labels", vp), ("lr", f32), ("step", i32), ("losses", vp), ("workspace", vp)]
 
 
-class FlexMatchEpilogueArgs(C.Structure):
-    _fields_ = [("B_lb", i32), ("B_ulb", i32), ("num_classes", i32), ("ulb_dest_len", i32), ("logits_lb", vp), ("logits_w", vp),
-                ("logits_s", vp), ("ld_logits", i64), ("y_lb", vp), ("idx_ulb", vp), ("p_cutoff", f32), ("thresh_warmup", i32),
-                ("lambda_u", f32), ("selected_label", vp), ("hist", vp), ("classwise_acc", vp), ("reward", vp),
-                ("mask_only", i32), ("mask_in", vp), ("probs_w", vp), ("pseudo", vp), ("mask", vp), ("mask2", vp),
-                ("losses", vp), ("dlogits_lb", vp), ("dlogits_s", vp), ("ld_dlogits", i64)]
+class FlexMatchMaskArgs(C.Structure):
+    _fields_ = [("B", i32), ("num_classes", i32), ("ulb_dest_len", i32), ("logits_w", vp), ("ld_logits", i64), ("idx_ulb", vp),
+                ("p_cutoff", f32), ("thresh_warmup", i32), ("selected_label", vp), ("hist", vp), ("classwise_acc", vp),
+                ("probs_w", vp), ("pseudo", vp), ("mask", vp), ("max_probs", vp)]
+
+
+class SslLossArgs(C.Structure):
+    _fields_ = [("B_lb", i32), ("B_ulb", i32), ("num_classes", i32), ("logits_lb", vp), ("logits_s", vp), ("ld_logits", i64),
+                ("y_lb", vp), ("pseudo", vp), ("mask", vp), ("reward", vp), ("lambda_u", f32), ("mask2", vp), ("losses", vp),
+                ("dlogits_lb", vp), ("dlogits_s", vp), ("ld_dlogits", i64)]
+
+
+f64 = C.c_double
+
+
+class AdamWRow(C.Structure):
+    _fields_ = [("param", vp), ("grad", vp), ("exp_avg", vp), ("exp_avg_sq", vp), ("planes", vp), ("numel", i64),
+                ("plane_stride", i64), ("cols", i32), ("ldp", i32), ("lr", f64), ("weight_decay", f64), ("first_block", i64)]
 
 
 class AdamWArgs(C.Structure):
-    _fields_ = [("num_tensors", i32), ("params", C.POINTER(vp)), ("grads", C.POINTER(vp)), ("exp_avg", C.POINTER(vp)),
-                ("exp_avg_sq", C.POINTER(vp)), ("numel", C.POINTER(i64)), ("lr", C.POINTER(f32)), ("weight_decay", C.POINTER(f32)),
-                ("beta1", f32), ("beta2", f32), ("eps", f32), ("step", i32), ("zero_grads", i32), ("device_table", vp)]
+    _fields_ = [("num_tensors", i32), ("total_blocks", i64), ("table", vp), ("lr_factor", f64), ("beta1", f64), ("beta2", f64),
+                ("eps", f64), ("step", i32), ("decoupled", i32)]
 
+
+ADAMW_BLOCK_ELEMS = 4096
 
 # every symbol include/srw.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -127,16 +140,16 @@ SYMBOLS = [
     ("srw_attn_bwd", i32, [C.POINTER(AttnBwdArgs), vp]),
     ("srw_vit_weight_planes_bytes", i64, [C.POINTER(VitConfig)]),
     ("srw_vit_workspace_bytes", i64, [C.POINTER(VitConfig), i32, i32]),
+    ("srw_vit_weight_plane_slot", i32, [C.POINTER(VitConfig), i32, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]),
     ("srw_vit_prepare_weights", i32, [C.POINTER(VitConfig), C.POINTER(vp), vp, vp]),
     ("srw_vit_forward", i32, [C.POINTER(VitFwdArgs), vp]),
     ("srw_vit_backward", i32, [C.POINTER(VitBwdArgs), vp]),
     ("srw_rewarder_workspace_floats", i64, [i32, i32]),
     ("srw_rewarder_fwd", i32, [C.POINTER(RewarderFwdArgs), vp]),
     ("srw_generator_fwd", i32, [C.POINTER(GeneratorFwdArgs), vp]),
-    ("srw_rewarder_train_workspace_floats", i64, [i32, i32, i32]),
     ("srw_rewarder_train", i32, [C.POINTER(RewarderTrainArgs), vp]),
-    ("srw_flexmatch_epilogue", i32, [C.POINTER(FlexMatchEpilogueArgs), vp]),
-    ("srw_adamw_table_bytes", i64, [i32]),
+    ("srw_flexmatch_mask", i32, [C.POINTER(FlexMatchMaskArgs), vp]),
+    ("srw_ssl_loss", i32, [C.POINTER(SslLossArgs), vp]),
     ("srw_adamw_step", i32, [C.POINTER(AdamWArgs), vp]),
 ]
 

@@ -1,0 +1,11 @@
+"""Algorithm lookup with the reference's surface (semilearn/algorithms/__init__.py:8-18)."""
+from ..core.registry import ALGORITHMS
+from . import srflexmatch  # noqa: F401  (registers 'srflexmatch')
+
+name2alg = ALGORITHMS
+
+
+def get_algorithm(args, net_builder, tb_log, logger):
+    if args.algorithm in ALGORITHMS:
+        return ALGORITHMS[args.algorithm](args=args, net_builder=net_builder, tb_log=tb_log, logger=logger)
+    raise KeyError(f"Unknown algorithm: {str(args.algorithm)}")

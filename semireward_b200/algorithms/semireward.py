@@ -1,0 +1,125 @@
+"""SemiReward modules behind the reference's class names (semilearn/algorithms/semireward/semireward.py):
+Rewarder (:27-72), Generator (:6-24), cosine_similarity_n (:130-139), label_dim (:147-148).
+
+The nn.Modules are parameter holders with the reference's state_dict keys and default initialisation; forward() and the
+online training step run as single fused kernels (srw_rewarder_fwd / srw_generator_fwd / srw_rewarder_train)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+
+
+def label_dim(x, default_dim=100):
+    return int(max(default_dim, x))
+
+
+def cosine_similarity_n(x1, x2):
+    """(cos + 1) / 2 of two one-hot label matrices -> {1.0, 0.5}.  Kept for API parity; the fused training kernel
+    evaluates the same target in closed form (equal ? 1 : 0.5)."""
+    cos = torch.cosine_similarity(x1, x2, dim=-1, eps=1e-8)
+    return ((cos + 1) / 2).view(x1.size(0), 1)
+
+
+def _ws(B, dev, feature_dim):
+    n = L.load().srw_rewarder_workspace_floats(B, feature_dim)
+    return torch.empty(max(n, B * 449 + 16), dtype=torch.float32, device=dev)
+
+
+class Generator(nn.Module):
+    def __init__(self, feature_dim=384):
+        super().__init__()
+        self.feature_dim = feature_dim
+        self.fc_layers = nn.Sequential(nn.Linear(feature_dim, 256), nn.ReLU(), nn.Linear(256, 128), nn.ReLU(),
+                                       nn.Linear(128, 64), nn.ReLU(), nn.Linear(64, 1))
+
+    def _params(self):
+        return [t for i in (0, 2, 4, 6) for t in (self.fc_layers[i].weight, self.fc_layers[i].bias)]
+
+    @torch.no_grad()
+    def generate_labels(self, feats):
+        """relu(fc_layers(x)).long() as one kernel -> int64 [B] (srflexmatch.py:157-158).  `.long()` cuts the graph in
+        the reference too: the Generator never receives a gradient."""
+        feats = feats.detach()
+        if feats.stride(-1) != 1:
+            feats = feats.contiguous()
+        B = feats.shape[0]
+        labels = torch.empty(B, dtype=torch.long, device=feats.device)
+        ws = _ws(B, feats.device, self.feature_dim)
+        a = L.GeneratorFwdArgs(B=B, feature_dim=self.feature_dim, gp=L.ptr_array(self._params()), feats=feats.data_ptr(),
+                               ld_feats=feats.stride(0), labels=labels.data_ptr(), workspace=ws.data_ptr())
+        L.check(L.load().srw_generator_fwd(C.byref(a), L.stream_ptr()), "srw_generator_fwd")
+        return labels
+
+    def forward(self, x):
+        raise NotImplementedError("use generate_labels(): the float output is only ever consumed through .long()")
+
+
+class Rewarder(nn.Module):
+    def __init__(self, label_dim, label_embedding_dim, feature_dim=384):
+        super().__init__()
+        if label_embedding_dim != 128:
+            raise NotImplementedError("label_embedding_dim is 128 in every SemiReward algorithm (srflexmatch.py:49)")
+        self.label_rows, self.feature_dim = int(label_dim), int(feature_dim)
+        self.feature_fc = nn.Linear(feature_dim, 128)
+        self.feature_norm = nn.LayerNorm(128)
+        self.label_embedding = nn.Embedding(label_dim, label_embedding_dim)
+        self.label_norm = nn.LayerNorm(label_embedding_dim)
+        self.cross_attention_fc = nn.Linear(128, 1)
+        self.mlp_fc1 = nn.Linear(128, 256)
+        self.mlp_fc2 = nn.Linear(256, 128)
+        self.ffn_fc1 = nn.Linear(128, 64)
+        self.ffn_fc2 = nn.Linear(64, 1)
+        self._adam = None
+
+    def _params(self):
+        return [self.feature_fc.weight, self.feature_fc.bias, self.feature_norm.weight, self.feature_norm.bias,
+                self.label_embedding.weight, self.label_norm.weight, self.label_norm.bias, self.cross_attention_fc.weight,
+                self.cross_attention_fc.bias, self.mlp_fc1.weight, self.mlp_fc1.bias, self.mlp_fc2.weight, self.mlp_fc2.bias,
+                self.ffn_fc1.weight, self.ffn_fc1.bias, self.ffn_fc2.weight, self.ffn_fc2.bias]
+
+    @torch.no_grad()
+    def forward(self, features, label_indices):
+        """reward [B,1] in (0,1).  Inference only: every consumer in the SR algorithms either detaches the inputs or
+        thresholds the output (srflexmatch.py:99-101,165-169); the training path is train_step() below."""
+        feats = features.detach()
+        if feats.stride(-1) != 1:
+            feats = feats.contiguous()
+        B = feats.shape[0]
+        labels = label_indices.to(torch.long).contiguous()
+        reward = torch.empty(B, 1, dtype=torch.float32, device=feats.device)
+        ws = _ws(B, feats.device, self.feature_dim)
+        a = L.RewarderFwdArgs(B=B, feature_dim=self.feature_dim, label_rows=self.label_rows, rp=L.ptr_array(self._params()),
+                              feats=feats.data_ptr(), ld_feats=feats.stride(0), labels=labels.data_ptr(), reward=reward.data_ptr(),
+                              workspace=ws.data_ptr())
+        L.check(L.load().srw_rewarder_fwd(C.byref(a), L.stream_ptr()), "srw_rewarder_fwd")
+        return reward
+
+    @torch.no_grad()
+    def train_step(self, features, gen_labels, true_labels, lr, num_classes):
+        """One online update (srflexmatch.py:173-208): reward = R(features, gen_labels); generator_loss = MSE(reward, 1);
+        rewarder_loss = MSE(reward, cos-target(gen, true)); both backward passes and one torch.optim.Adam step, fused.
+        Returns a [2] device tensor (generator_loss, rewarder_loss)."""
+        ps = self._params()
+        dev = ps[0].device
+        if self._adam is None or self._adam["m"][0].device != dev:
+            self._adam = dict(m=[torch.zeros_like(p) for p in ps], v=[torch.zeros_like(p) for p in ps],
+                              g=[torch.empty_like(p) for p in ps], step=0)
+        st = self._adam
+        st["step"] += 1
+        feats = features.detach()
+        if feats.stride(-1) != 1:
+            feats = feats.contiguous()
+        B = feats.shape[0]
+        losses = torch.empty(2, dtype=torch.float32, device=dev)
+        ws = _ws(B, dev, self.feature_dim)
+        gl, tl = gen_labels.to(torch.long).contiguous(), true_labels.to(torch.long).contiguous()
+        a = L.RewarderTrainArgs(B=B, feature_dim=self.feature_dim, label_rows=self.label_rows, num_classes=int(num_classes),
+                                rp=L.ptr_array(ps), g=L.ptr_array(st["g"]), m=L.ptr_array(st["m"]), v=L.ptr_array(st["v"]),
+                                feats=feats.data_ptr(), ld_feats=feats.stride(0), gen_labels=gl.data_ptr(), true_labels=tl.data_ptr(),
+                                lr=float(lr), step=st["step"], losses=losses.data_ptr(), workspace=ws.data_ptr())
+        L.check(L.load().srw_rewarder_train(C.byref(a), L.stream_ptr()), "srw_rewarder_train")
+        return losses

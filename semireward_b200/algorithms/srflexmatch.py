@@ -1,0 +1,179 @@
+"""SRFlexMatch — FlexMatch + SemiReward train step on the B200-native kernels, registered under the reference's name.
+
+Follows semilearn/algorithms/srflexmatch/srflexmatch.py: ctor :44-58, set_hooks :66-70, data_generator :72-104,
+train_step :107-217, get_save_dict/load_model :219-231, get_argument :233-246.
+
+What runs where (all device work is in libsrw_b200.so; this file only sequences calls):
+  backbone fwd/bwd ........ srw_vit_forward / srw_vit_backward  (one autograd.Function; weak rows carry no gradient)
+  probs/pseudo/mask/hook .. srw_flexmatch_mask   (1 launch instead of ~10 + a 400 KB D2H Counter round trip)
+  reward / mask2 .......... srw_rewarder_fwd + srw_ssl_loss
+  sup/unsup/total + dlogits srw_ssl_loss          (loss tensor is returned with a grad_fn so ParamUpdateHook's
+                                                   loss.backward() works unchanged)
+  SR online update ........ srw_generator_fwd + srw_rewarder_train (fwd + 2 MSE + bwd + Adam in one launch)
+  4x .item() .............. one 16-byte D2H copy of the loss vector
+The engine wants the gradient-carrying rows first, so the concatenation order is (x_lb, x_ulb_s, x_ulb_w) instead of
+the reference's (x_lb, x_ulb_w, x_ulb_s); per-row results are identical because LayerNorm nets do not couple rows."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .. import _lib as L
+from ..core.algorithmbase import AlgorithmBase
+from ..core.hooks import FlexMatchThresholdingHook, PseudoLabelingHook
+from ..core.registry import ALGORITHMS
+from .semireward import Generator, Rewarder, label_dim
+from .utils import SSL_Argument, str2bool
+
+
+class _SSLLoss(torch.autograd.Function):
+    """total_loss with a grad_fn: forward evaluates srw_ssl_loss (which also writes d total / d logits), backward hands
+    those gradients to the two logit tensors (they may come from two different backbone passes in stage 2)."""
+
+    @staticmethod
+    def forward(ctx, logits_lb, logits_s, y_lb, pseudo, mask, reward, lambda_u, out):
+        B_lb, Cn = logits_lb.shape
+        B_u = logits_s.shape[0]
+        dev = logits_lb.device
+        dl_lb = torch.empty(B_lb, Cn, dtype=torch.float32, device=dev)
+        dl_s = torch.empty(B_u, Cn, dtype=torch.float32, device=dev)
+        losses = torch.empty(4, dtype=torch.float32, device=dev)
+        mask2 = torch.empty(B_u, dtype=torch.float32, device=dev)
+        assert logits_lb.stride(1) == 1 and logits_s.stride(1) == 1 and logits_lb.stride(0) == logits_s.stride(0)
+        a = L.SslLossArgs(B_lb=B_lb, B_ulb=B_u, num_classes=Cn, logits_lb=logits_lb.data_ptr(), logits_s=logits_s.data_ptr(),
+                          ld_logits=logits_lb.stride(0), y_lb=y_lb.data_ptr(), pseudo=pseudo.data_ptr(), mask=mask.data_ptr(),
+                          reward=L.ptr(reward), lambda_u=float(lambda_u), mask2=mask2.data_ptr(), losses=losses.data_ptr(),
+                          dlogits_lb=dl_lb.data_ptr(), dlogits_s=dl_s.data_ptr(), ld_dlogits=Cn)
+        L.check(L.load().srw_ssl_loss(C.byref(a), L.stream_ptr()), "srw_ssl_loss")
+        ctx.dl_lb, ctx.dl_s = dl_lb, dl_s
+        out["losses"], out["mask2"] = losses, mask2
+        return losses[2].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.dl_lb * g, ctx.dl_s * g, None, None, None, None, None, None
+
+
+@ALGORITHMS.register("srflexmatch")
+class SRFlexMatch(AlgorithmBase):
+    def __init__(self, args, net_builder, tb_log=None, logger=None):
+        super().__init__(args, net_builder, tb_log, logger)
+        self.init(T=args.T, p_cutoff=args.p_cutoff, hard_label=args.hard_label, thresh_warmup=args.thresh_warmup)
+        self.N_k = args.N_k
+        if args.sr_ema != 0:
+            raise NotImplementedError("sr_ema: every shipped SemiReward config sets sr_ema: False (EMARewarder is unused, SURVEY.md §8a a6)")
+        self.rewarder = Rewarder(label_dim(self.num_classes), 128, args.feature_dim)
+        self.generator = Generator(args.feature_dim)
+        self.start_timing = args.start_timing
+        self.sr_lr = args.sr_lr
+        self.max_reward = -float("inf")
+        # with DropPath/dropout off every sampling pass of data_generator sees identical logits: run the backbone once
+        # and replay only the hook-state updates (bit-equivalent in that mode only — SURVEY.md §8a a2)
+        self.replay_deterministic_passes = True
+
+    def init(self, T, p_cutoff, hard_label=True, thresh_warmup=True):
+        self.T, self.p_cutoff, self.use_hard_label, self.thresh_warmup = T, p_cutoff, hard_label, thresh_warmup
+
+    def set_hooks(self):
+        self.register_hook(PseudoLabelingHook(), "PseudoLabelingHook")
+        self.register_hook(FlexMatchThresholdingHook(ulb_dest_len=self.args.ulb_dest_len, num_classes=self.num_classes,
+                                                     thresh_warmup=self.args.thresh_warmup, device=f"cuda:{self.gpu}"), "MaskingHook")
+        super().set_hooks()
+
+    # -- pieces -----------------------------------------------------------------------------------
+    def _backbone(self, x_lb, x_ulb_w, x_ulb_s, need_grad=True):
+        """-> logits/feats of (lb, weak, strong).  Gradient rows (lb, strong) go first inside the engine."""
+        if not self.use_cat:
+            raise NotImplementedError("use_cat: False (BERT/HuBERT configs) is a 'next' row (SURVEY.md §8f)")
+        nl, nu = x_lb.shape[0], x_ulb_s.shape[0]
+        inputs = torch.cat((x_lb, x_ulb_s, x_ulb_w))
+        if need_grad:
+            out = self.model(inputs, grad_batch=nl + nu)
+        else:
+            with torch.no_grad():
+                out = self.model(inputs)
+        lg, ft = out["logits"], out["feat"]
+        return (lg[:nl], lg[nl + nu:], lg[nl:nl + nu]), (ft[:nl], ft[nl + nu:], ft[nl:nl + nu])
+
+    def _stochastic_backbone(self):
+        m = self.model.module if hasattr(self.model, "module") else self.model
+        return m.training and max(getattr(m, "drop_path_rates", [0.0])) > 0.0
+
+    def _mask_and_pseudo(self, logits_w, idx_ulb):
+        mask = self.call_hook("masking", "MaskingHook", logits_x_ulb=logits_w, idx_ulb=idx_ulb, softmax_x_ulb=True)
+        pseudo = self.call_hook("gen_ulb_targets", "PseudoLabelingHook", logits=self._last_probs, use_hard_label=self.use_hard_label,
+                                T=self.T, softmax=False)
+        return mask, pseudo
+
+    def data_generator(self, x_lb, y_lb, idx_ulb, x_ulb_w, x_ulb_s, rewarder, gpu, first_pass=None):
+        """K = sr_decay() sampling passes; the last pass's (logits_s, pseudo, mask, reward) define the loss
+        (srflexmatch.py:72-104).  Returns those tensors; the loss itself is formed by _SSLLoss."""
+        K = self.sr_decay()
+        stochastic = self._stochastic_backbone() or not self.replay_deterministic_passes
+        last = None
+        for k in range(K):
+            if stochastic:
+                is_last = k == K - 1
+                (l_lb, l_w, l_s), (_, f_w, _) = self._backbone(x_lb, x_ulb_w, x_ulb_s, need_grad=is_last)
+            else:
+                (l_lb, l_w, l_s), (_, f_w, _) = first_pass
+            mask, pseudo = self._mask_and_pseudo(l_w, idx_ulb)
+            if stochastic or k == K - 1:   # the reward of pass k only feeds pass k's loss, and only the last loss survives
+                last = (l_s, pseudo, mask, rewarder(f_w, pseudo))
+        return last
+
+    # -- the step ---------------------------------------------------------------------------------
+    def train_step(self, x_lb, y_lb, idx_ulb, x_ulb_w, x_ulb_s):
+        (logits_lb, logits_w, logits_s), (feats_lb, feats_w, feats_s) = self._backbone(x_lb, x_ulb_w, x_ulb_s)
+        feat_dict = {"x_lb": feats_lb, "x_ulb_w": feats_w, "x_ulb_s": feats_s}
+        y_lb = y_lb.to(torch.long)
+        mask, pseudo_label = self._mask_and_pseudo(logits_w, idx_ulb)
+        side = {}
+        if self.it > self.start_timing:
+            l_s, pseudo_dg, mask_dg, reward_dg = self.data_generator(
+                x_lb, y_lb, idx_ulb, x_ulb_w, x_ulb_s, self.rewarder, self.gpu,
+                first_pass=((logits_lb, logits_w, logits_s), (feats_lb, feats_w, feats_s)))
+            total_loss = _SSLLoss.apply(logits_lb, l_s, y_lb, pseudo_dg, mask_dg, reward_dg.view(-1), self.lambda_u, side)
+        else:
+            total_loss = _SSLLoss.apply(logits_lb, logits_s, y_lb, pseudo_label, mask, None, self.lambda_u, side)
+        if self.it > 0:
+            if self.it >= self.start_timing:
+                # mean reward bookkeeping of srflexmatch.py:165-172 (the "filtered" tensors are always the current batch)
+                if self.it % self.N_k == 0 and self.it > self.start_timing:
+                    self.max_reward = -float("inf")
+                    gen = self.generator.generate_labels(feats_w)
+                    self.rewarder.train_step(feats_w, gen, pseudo_label, self.sr_lr, self.num_classes)
+            else:
+                gen = self.generator.generate_labels(feats_lb)
+                self.rewarder.train_step(feats_lb, gen, y_lb, self.sr_lr, self.num_classes)
+        sup, unsup, total, util = side["losses"].tolist()   # one 16-byte D2H instead of four .item() syncs
+        if self.it <= self.start_timing:
+            util = float(util)
+        else:
+            util = float(mask.mean().item())  # the reference logs pass-0's mask (srflexmatch.py:216)
+        out_dict = self.process_out_dict(loss=total_loss, feat=feat_dict)
+        log_dict = self.process_log_dict(sup_loss=sup, unsup_loss=unsup, total_loss=total, util_ratio=util)
+        self._last_mask, self._last_mask2, self._last_pseudo_label = mask, side["mask2"], pseudo_label
+        return out_dict, log_dict
+
+    def get_save_dict(self):
+        d = super().get_save_dict()
+        d["classwise_acc"] = self.hooks_dict["MaskingHook"].classwise_acc.cpu()
+        d["selected_label"] = self.hooks_dict["MaskingHook"].selected_label.cpu()
+        return d
+
+    def load_model(self, load_path):
+        ck = super().load_model(load_path)
+        h = self.hooks_dict["MaskingHook"]
+        h.classwise_acc = ck["classwise_acc"].cuda(self.gpu)
+        h.selected_label = ck["selected_label"].cuda(self.gpu)
+        h._rebuild_hist()
+        return ck
+
+    @staticmethod
+    def get_argument():
+        return [SSL_Argument("--hard_label", str2bool, True), SSL_Argument("--T", float, 0.5), SSL_Argument("--p_cutoff", float, 0.95),
+                SSL_Argument("--thresh_warmup", str2bool, True), SSL_Argument("--start_timing", int, 20000),
+                SSL_Argument("--feature_dim", int, 384), SSL_Argument("--sr_lr", float, 0.0005), SSL_Argument("--N_k", int, 10),
+                SSL_Argument("--sr_ema", str2bool, True), SSL_Argument("--sr_ema_m", float, 0.999)]

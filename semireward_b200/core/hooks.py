@@ -1,0 +1,115 @@
+"""Hooks on the hot path, with the reference's names and call protocol (semilearn/core/hooks/hook.py:6-42):
+`algorithm.call_hook(fn_name, hook_name, **kw)`.
+
+  ParamUpdateHook            <- semilearn/core/hooks/param_update.py:21-45
+  PseudoLabelingHook         <- semilearn/algorithms/hooks/pseudo_label.py:16-52
+  FlexMatchThresholdingHook  <- semilearn/algorithms/srflexmatch/utils.py:11-63  (state lives on the device; the
+                                softmax/argmax/mask/scatter/histogram run as ONE kernel, srw_flexmatch_mask)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .. import _lib as L
+
+
+class Hook:
+    stages = ("before_run", "before_train_epoch", "before_train_step", "after_train_step", "after_train_epoch", "after_run")
+
+    def before_train_epoch(self, algorithm): pass
+    def after_train_epoch(self, algorithm): pass
+    def before_train_step(self, algorithm): pass
+    def after_train_step(self, algorithm): pass
+    def before_run(self, algorithm): pass
+    def after_run(self, algorithm): pass
+
+
+class ParamUpdateHook(Hook):
+    """backward + (clip) + optimizer.step + scheduler.step + zero_grad; CUDA-event run_time like the reference."""
+
+    def before_train_step(self, algorithm):
+        if hasattr(algorithm, "start_run"):
+            torch.cuda.synchronize()
+            algorithm.start_run.record()
+
+    def after_train_step(self, algorithm):
+        loss = algorithm.out_dict["loss"]
+        if algorithm.use_amp:
+            raise NotImplementedError("amp: every SemiReward config runs fp32 (amp: False); the native path is fp32-accurate")
+        loss.backward()
+        if algorithm.clip_grad > 0:
+            torch.nn.utils.clip_grad_norm_(algorithm.model.parameters(), algorithm.clip_grad)
+        algorithm.optimizer.step()
+        if algorithm.scheduler is not None:
+            algorithm.scheduler.step()
+        algorithm.model.zero_grad()
+        if hasattr(algorithm, "end_run"):
+            algorithm.end_run.record()
+            torch.cuda.synchronize()
+            algorithm.log_dict["train/run_time"] = algorithm.start_run.elapsed_time(algorithm.end_run) / 1000.0
+
+
+class PseudoLabelingHook(Hook):
+    """gen_ulb_targets: hard labels = argmax; soft labels = softmax(logits / T).  On the fused path the hard labels come
+    out of srw_flexmatch_mask (`algorithm._last_pseudo`) so no extra kernel runs; the generic branch stays available."""
+
+    @torch.no_grad()
+    def gen_ulb_targets(self, algorithm, logits, use_hard_label=True, T=1.0, softmax=True, label_smoothing=0.0):
+        if use_hard_label:
+            cached = getattr(algorithm, "_last_pseudo", None)
+            if cached is not None and cached[0].data_ptr() == logits.data_ptr():
+                return cached[1]
+            raise RuntimeError("hard pseudo-labels are produced by the fused masking kernel; call the MaskingHook first")
+        raise NotImplementedError("soft pseudo-labels (hard_label: False) are not used by any SemiReward config")
+
+
+class FlexMatchThresholdingHook(Hook):
+    """Device-resident FlexMatch state: selected_label int64[ulb_dest_len] (-1 = never selected), classwise_acc fp32[C],
+    plus hist int32[C+1] replacing the reference's host Counter (utils.py:25-29)."""
+
+    def __init__(self, ulb_dest_len, num_classes, thresh_warmup=True, device="cuda"):
+        self.ulb_dest_len, self.num_classes, self.thresh_warmup = int(ulb_dest_len), int(num_classes), bool(thresh_warmup)
+        self.device = torch.device(device)
+        self.selected_label = torch.full((self.ulb_dest_len,), -1, dtype=torch.long, device=self.device)
+        self.classwise_acc = torch.zeros(self.num_classes, dtype=torch.float32, device=self.device)
+        self._hist = None
+        self._rebuild_hist()
+
+    def _rebuild_hist(self):
+        """Recount after selected_label was replaced from outside (checkpoint load)."""
+        h = torch.bincount(self.selected_label + 1, minlength=self.num_classes + 1).to(torch.int32)
+        self._hist = h.contiguous()
+        self._hist_src = self.selected_label.data_ptr()
+
+    @torch.no_grad()
+    def masking(self, algorithm, logits_x_ulb, idx_ulb, softmax_x_ulb=True, raw_logits=None, *args, **kwargs):
+        """logits_x_ulb: raw logits (softmax_x_ulb=True) — on the fused path the algorithm passes the raw weak logits and
+        receives (mask, probs, pseudo) computed in one launch."""
+        if not softmax_x_ulb:
+            raise RuntimeError("fused FlexMatch hook takes raw logits (softmax is fused into the kernel)")
+        if self.selected_label.device != logits_x_ulb.device:
+            self.selected_label = self.selected_label.to(logits_x_ulb.device)
+            self.classwise_acc = self.classwise_acc.to(logits_x_ulb.device)
+            self._rebuild_hist()
+        if self._hist_src != self.selected_label.data_ptr():
+            self._rebuild_hist()
+        lw = logits_x_ulb.detach()
+        if lw.stride(-1) != 1:
+            lw = lw.contiguous()
+        B, Cn = lw.shape
+        dev = lw.device
+        probs = torch.empty(B, Cn, dtype=torch.float32, device=dev)
+        pseudo = torch.empty(B, dtype=torch.long, device=dev)
+        mask = torch.empty(B, dtype=torch.float32, device=dev)
+        idx = idx_ulb.to(device=dev, dtype=torch.long).contiguous()
+        a = L.FlexMatchMaskArgs(B=B, num_classes=Cn, ulb_dest_len=self.ulb_dest_len, logits_w=lw.data_ptr(), ld_logits=lw.stride(0),
+                                idx_ulb=idx.data_ptr(), p_cutoff=float(algorithm.p_cutoff), thresh_warmup=int(self.thresh_warmup),
+                                selected_label=self.selected_label.data_ptr(), hist=self._hist.data_ptr(),
+                                classwise_acc=self.classwise_acc.data_ptr(), probs_w=probs.data_ptr(), pseudo=pseudo.data_ptr(),
+                                mask=mask.data_ptr(), max_probs=None)
+        L.check(L.load().srw_flexmatch_mask(C.byref(a), L.stream_ptr()), "srw_flexmatch_mask")
+        algorithm._last_pseudo = (probs, pseudo)
+        algorithm._last_probs = probs
+        return mask

@@ -391,6 +391,35 @@ extern "C" int64_t srw_vit_weight_planes_bytes(const srw_vit_config* c) {
   return weight_layout(d, w, pe);
 }
 
+extern "C" int srw_vit_weight_plane_slot(const srw_vit_config* c, int param_index, int64_t* byte_offset, int* cols, int* ldp,
+                                         int64_t* plane_stride) {
+  Dims d;
+  SRW_TRY(make_dims(c, 1, 0, d));
+  SRW_REQUIRE(byte_offset && cols && ldp && plane_stride, "srw_vit_weight_plane_slot: null pointer");
+  std::vector<WOff> w;
+  int64_t pe;
+  weight_layout(d, w, pe);
+  if (param_index == P_PE_W) {
+    *byte_offset = pe; *cols = d.K; *ldp = d.Kpad; *plane_stride = (int64_t)d.D * d.Kpad;
+    return SRW_OK;
+  }
+  const int rel = param_index - 4;
+  if (rel >= 0 && rel < 12 * d.L) {
+    const int l = rel / 12, which = rel % 12;
+    int64_t off = -1, rows = 0, cc = 0;
+    if (which == B_QKVW) { off = w[l].qkv; rows = 3 * d.D; cc = d.D; }
+    else if (which == B_PROJW) { off = w[l].proj; rows = d.D; cc = d.D; }
+    else if (which == B_FC1W) { off = w[l].fc1; rows = d.hidden; cc = d.D; }
+    else if (which == B_FC2W) { off = w[l].fc2; rows = d.D; cc = d.hidden; }
+    if (off >= 0) {
+      *byte_offset = off; *cols = (int)cc; *ldp = (int)cc; *plane_stride = rows * cc;
+      return SRW_OK;
+    }
+  }
+  set_last_error("srw_vit_weight_plane_slot: parameter %d has no planes", param_index);
+  return SRW_ERR_ARG;
+}
+
 extern "C" int64_t srw_vit_workspace_bytes(const srw_vit_config* c, int batch, int grad_batch) {
   Dims d;
   if (make_dims(c, batch, grad_batch, d)) return -1;
