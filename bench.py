@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py — SSL train-step samples/sec (ViT-S CIFAR-100, FlexMatch+SemiReward) on N B200s, next to the CPU reference.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--batch-size B] [--stage 1|2]
+
+One "step" = SRFlexMatch.train_step + ParamUpdateHook.after_train_step (backward + AdamW + scheduler) on one batch of
+BASELINE.json configs[1] (config/SemiReward/usb_cv/flexmatch/flexmatch_cifar100_200_0.yaml: vit_small_patch2_32,
+batch_size 8, uratio 1 -> 24 samples per step and rank, AdamW lr 5e-4 layer_decay 0.5, DropPath 0.2, fp32), stage 1
+(0 < it < start_timing: one backbone pass, Rewarder trained on the labelled batch every step) — SURVEY.md §8d.
+Synthetic N(0,1) images, random-init weights.  samples/s = world_size * 24 * K / max-over-ranks device time.
+
+Prints ONE JSON line (rank 0).  `value` = inputs already resident in HBM; `e2e` = the same steps driven through the
+public API from pinned host tensors (H2D of the batch and D2H of the loss vector inside the timed region).
+`--impl reference` times the CPU restatement of the reference's own train_step (oracle/, pinned bit-exactly against the
+live reference in the build container; the reference itself is not installable on the GPU box) on the host cores."""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+YAML_CFG = dict(  # flexmatch_cifar100_200_0.yaml:10-54 (+ code defaults)
+    algorithm="srflexmatch", net="vit_small_patch2_32", optim="AdamW", lr=5e-4, layer_decay=0.5, weight_decay=5e-4,
+    num_train_iter=204800, num_warmup_iter=5120, start_timing=20000, N_k=10, batch_size=8, uratio=1, num_classes=100,
+    ulb_dest_len=50000, feature_dim=384, sr_lr=5e-4, sr_ema=False, use_cat=True, amp=False, ema_m=0.0, img_size=32,
+    p_cutoff=0.95, thresh_warmup=True, ulb_loss_ratio=1.0, clip_grad=0)
+F_FWD_GF = 12.134          # GFLOP per sample forward
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch-size", type=int, default=8, help="per-GPU labelled batch (config-faithful: 8)")
+    ap.add_argument("--stage", type=int, default=1, choices=[1, 2])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(self.rows))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1383.8), d.get("bf16_tflops", 1635.7), d.get("hbm_gbs", 6483.3), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(cfg, steps, warmup, stage):
+    """Stage-1 (or stage-2) steps of the oracle = CPU restatement of the reference's train_step + ParamUpdateHook, fp32,
+    all host threads; identical synthetic tensors and deterministic weights.  Returns (samples/s, seconds/step, cores)."""
+    import torch
+    from oracle import ssl_oracle as O
+    from semireward_b200 import detgen
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    vc = O.ViTConfig(depth=12, num_classes=cfg["num_classes"], drop_path_rate=0.2)
+    sc = O.StepConfig(algorithm="srflexmatch", num_classes=cfg["num_classes"], ulb_dest_len=cfg["ulb_dest_len"], p_cutoff=cfg["p_cutoff"],
+                      thresh_warmup=cfg["thresh_warmup"], start_timing=cfg["start_timing"], N_k=cfg["N_k"], num_train_iter=cfg["num_train_iter"],
+                      num_warmup_iter=cfg["num_warmup_iter"], lr=cfg["lr"], weight_decay=cfg["weight_decay"], layer_decay=cfg["layer_decay"],
+                      sr_lr=cfg["sr_lr"], feature_dim=cfg["feature_dim"])
+    orc = O.build_det_oracle(vc, sc, seed=0)
+    orc.drop_gen = torch.Generator().manual_seed(0)
+    it0 = 1 if stage == 1 else cfg["start_timing"] + 1 + 8 * cfg["num_train_iter"]  # K = 8 in stage 2
+    times = []
+    for i in range(warmup + steps):
+        b = O.to_torch_batch(detgen.ssl_batch(cfg["batch_size"], cfg["uratio"], cfg["num_classes"], cfg["ulb_dest_len"], seed=1, step=i))
+        t0 = time.perf_counter()
+        orc.train_step(b, it0 + i)
+        orc.param_update()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    per_step = sum(times) / len(times)
+    samples = cfg["batch_size"] * (1 + 2 * cfg["uratio"])
+    return samples / per_step, per_step, cores
+
+
+def main_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = dict(YAML_CFG, batch_size=a.batch_size)
+    steps, warmup = max(1, min(a.steps, 8)), max(0, min(a.warmup, 2))   # bounded sample: ~1-2 s per CPU step
+    sps, per_step, cores = cpu_reference_run(cfg, steps, warmup, a.stage)
+    line = dict(impl="reference", metric="SSL train-step samples/sec (ViT-S CIFAR-100)", value=sps, unit="samples/s", n_gpus=a.gpus,
+                steps=steps, warmup=warmup, ms_per_step=per_step * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(workload=f"srflexmatch vit_small_patch2_32 cifar100 batch_size {a.batch_size} uratio 1 stage {a.stage} (BASELINE configs[1])",
+                            samples_per_step=cfg["batch_size"] * 3),
+                cpu_baseline=dict(value=sps, unit="samples/s", cores=cores, kind="port",
+                                  sample=f"{steps} stage-{a.stage} steps of the oracle restatement (bit-exact vs the live reference), {warmup} warm-up"),
+                e2e=dict(value=sps, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------
+def main_native(a):
+    import torch
+    import torch.distributed as dist
+    import semireward_b200 as S
+    from semireward_b200 import _lib as L, detgen
+    from semireward_b200.parallel import send_model_cuda
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = L.load()
+    L.check(lib.srw_device_check(None, None, None), "srw_device_check")
+
+    cfg = dict(YAML_CFG, batch_size=a.batch_size, gpu=local, distributed=world > 1, world_size=world, rank=rank)
+    args = S.get_config(cfg)
+    torch.manual_seed(0)
+    alg = S.get_algorithm(args, S.get_net_builder(args.net, False), None, None)
+    alg.model = send_model_cuda(args, alg.model)
+    alg.model.train()
+    alg.start_run, alg.end_run = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    it0 = 1 if a.stage == 1 else args.start_timing + 1 + 8 * args.num_train_iter
+    B, U = args.batch_size, args.batch_size * args.uratio
+    samples_per_step = B + 2 * U
+
+    def host_batch(i):
+        b = detgen.ssl_batch(B, args.uratio, args.num_classes, args.ulb_dest_len, seed=1 + rank, step=i)
+        return {k: torch.from_numpy(v).pin_memory() for k, v in b.items()}
+
+    n_batches = 4
+    hbatches = [host_batch(i) for i in range(n_batches)]
+    dbatches = [{k: v.cuda(non_blocking=True) for k, v in hb.items()} for hb in hbatches]
+    h2d = sum(v.numel() * v.element_size() for v in hbatches[0].values())
+
+    def step_device(i):
+        alg.it = it0 + i
+        alg.out_dict, alg.log_dict = alg.train_step(**dbatches[i % n_batches])
+        alg.call_hook("after_train_step")
+
+    def step_e2e(i):
+        alg.it = it0 + i
+        alg.out_dict, alg.log_dict = alg.train_step(**alg.process_batch(**hbatches[i % n_batches]))
+        alg.call_hook("after_train_step")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, offset):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            fn(offset + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    # the ParamUpdateHook's own event timing syncs every step; the bench brackets the whole region instead
+    del alg.start_run, alg.end_run
+    W, K = max(3, a.warmup), a.steps
+    for i in range(W):
+        step_device(i)
+    launches0 = lib.srw_kernel_launches()
+    with ClockSampler(local) as clk:
+        ms = timed(step_device, K, W)
+    launches = lib.srw_kernel_launches() - launches0
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, K, W + K)
+    value = world * samples_per_step * K / (ms / 1e3)
+    e2e = world * samples_per_step * K / (ms_e2e / 1e3)
+
+    roof = attn = None
+    if not a.no_roofline and rank == 0:
+        lib.srw_profile_enable(1)
+        st = (L.ProfileStats * L.PROF_NUM)()
+        nprof = min(K, 5)
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); t0.record()
+        for i in range(nprof):
+            step_device(W + 2 * K + i)
+        t1.record(); torch.cuda.synchronize()
+        step_ms_prof = t0.elapsed_time(t1) / nprof
+        L.check(lib.srw_profile_collect(st), "srw_profile_collect")
+        lib.srw_profile_enable(0)
+        sust, burst, hbm, how = peaks()
+        g = st[L.PROF_GEMM]
+        ach = g.flops / (g.total_ms * 1e-3) / 1e12 if g.total_ms > 0 else 0.0
+        roof = dict(bound="tensor", kernel="gemm_bf16x3_tcgen05_kernel", achieved=ach, peak=sust, unit="TFLOP/s", frac=ach / sust,
+                    traffic=None, peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})", launches_per_step=g.launches / nprof,
+                    avg_launch_us=1e3 * g.total_ms / max(g.launches, 1), share_of_step=g.total_ms / nprof / step_ms_prof,
+                    note="achieved = algorithmic 2MNK per launch / CUDA-event launch time; the kernel issues 3 bf16 MMAs per algorithmic "
+                         "product (hi*hi, hi*lo, lo*hi) for fp32-level accuracy, so the tensor pipe does 3x these FLOPs")
+        af, ab = st[L.PROF_ATTN_FWD], st[L.PROF_ATTN_BWD]
+        attn = dict(fwd=dict(achieved=af.flops / (af.total_ms * 1e-3) / 1e12 if af.total_ms > 0 else 0.0, unit="TFLOP/s",
+                             avg_launch_us=1e3 * af.total_ms / max(af.launches, 1), share_of_step=af.total_ms / nprof / step_ms_prof),
+                    bwd=dict(achieved=ab.flops / (ab.total_ms * 1e-3) / 1e12 if ab.total_ms > 0 else 0.0, unit="TFLOP/s",
+                             avg_launch_us=1e3 * ab.total_ms / max(ab.launches, 1), share_of_step=ab.total_ms / nprof / step_ms_prof),
+                    peak=sust)
+        ad = st[L.PROF_ADAMW]
+        if ad.total_ms > 0:
+            attn["adamw"] = dict(achieved_gbs=ad.bytes / (ad.total_ms * 1e-3) / 1e9, peak_gbs=hbm, avg_launch_us=1e3 * ad.total_ms / max(ad.launches, 1))
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        sps, per_step, cores = cpu_reference_run(dict(YAML_CFG, batch_size=a.batch_size), 6, 1, a.stage)
+        cpu = dict(value=sps, unit="samples/s", cores=cores, kind="port",
+                   sample=f"6 stage-{a.stage} steps (+1 warm-up) of the oracle restatement of the reference train_step+ParamUpdateHook, "
+                          f"{per_step:.2f} s/step, torch CPU fp32, {cores} threads")
+    if rank == 0:
+        line = dict(metric="SSL train-step samples/sec (ViT-S CIFAR-100)", value=value, unit="samples/s", n_gpus=world, steps=K, warmup=W,
+                    ms_per_step=ms / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=f"srflexmatch vit_small_patch2_32 cifar100 batch_size {B} uratio {args.uratio} stage {a.stage} (BASELINE configs[1])",
+                                samples_per_step_per_gpu=samples_per_step, parallelism=f"dp{world}", drop_path=0.2,
+                                arithmetic="fp32 semantics: bf16x3 split-precision tcgen05 MMA, fp32 accumulate",
+                                l2="step working set (~1.8 GB of activations at batch 8) >> 126 MB L2; 4 rotating input batches",
+                                algorithmic_gflop_per_step_per_gpu=7 * B * F_FWD_GF),
+                    clocks=clk.summary(), gpu_launches=int(launches),
+                    e2e=dict(value=e2e, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=16, ms_per_step=ms_e2e / K))
+        if roof is not None:
+            line["roofline"] = roof
+            line["attention"] = attn
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args_ = parse()
+    if args_.impl == "reference":
+        main_reference(args_)
+    else:
+        main_native(args_)

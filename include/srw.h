@@ -35,6 +35,14 @@ const char* srw_last_error(void);      /* message of the last failing call on th
 int srw_device_check(int* sm_major, int* sm_minor, int* sm_count); /* fails unless the current device is sm_100 */
 int64_t srw_kernel_launches(void);     /* number of kernels this library has launched so far (bench.py gpu_launches) */
 
+/* Per-kernel-class device timing for bench.py's roofline block: when enabled, every launch of the classes below is
+ * bracketed by CUDA events on its own stream; srw_profile_collect synchronises, sums and resets.  Off by default
+ * (the bench's headline timing runs with it off). */
+enum srw_profile_class { SRW_PROF_GEMM = 0, SRW_PROF_ATTN_FWD = 1, SRW_PROF_ATTN_BWD = 2, SRW_PROF_ADAMW = 3, SRW_PROF_NUM = 4 };
+typedef struct { int64_t launches; double total_ms; double flops; double bytes; } srw_profile_stats;
+int srw_profile_enable(int on);
+int srw_profile_collect(srw_profile_stats* out /* [SRW_PROF_NUM] */);
+
 /* ---- split-plane conversion -------------------------------------------------------------------------------- */
 /* planes[r, c] = split(x[r, c] * (row_scale ? row_scale[r / rows_per_scale] : 1)).  Used for weights once per optimizer
  * step and for gradient tensors entering a GEMM.  transposed != 0 additionally writes planes_t[c, r] (ld = rows). */
@@ -221,6 +229,8 @@ typedef struct {
   const float* feats; int64_t ld_feats;
   const int64_t* gen_labels; const int64_t* true_labels;
   float lr; int step;                          /* step = t (1-based) for bias correction */
+  int phase;                                   /* 0: forward+backward+Adam fused; 1: forward+backward only (g written);
+                                                  2: Adam only from g (lets the caller all-reduce g between 1 and 2: DDP, C3) */
   float* losses;                               /* [2] generator_loss, rewarder_loss */
   float* workspace;                            /* >= srw_rewarder_workspace_floats(B, feature_dim) */
 } srw_rewarder_train_args;

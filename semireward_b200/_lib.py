@@ -94,7 +94,7 @@ class GeneratorFwdArgs(C.Structure):
 class RewarderTrainArgs(C.Structure):
     _fields_ = [("B", i32), ("feature_dim", i32), ("label_rows", i32), ("num_classes", i32), ("rp", C.POINTER(vp)),
                 ("g", C.POINTER(vp)), ("m", C.POINTER(vp)), ("v", C.POINTER(vp)), ("feats", vp), ("ld_feats", i64),
-                ("gen_labels", vp), ("true_labels", vp), ("lr", f32), ("step", i32), ("losses", vp), ("workspace", vp)]
+                ("gen_labels", vp), ("true_labels", vp), ("lr", f32), ("step", i32), ("phase", i32), ("losses", vp), ("workspace", vp)]
 
 
 class FlexMatchMaskArgs(C.Structure):
@@ -123,6 +123,12 @@ class AdamWArgs(C.Structure):
 
 
 ADAMW_BLOCK_ELEMS = 4096
+PROF_GEMM, PROF_ATTN_FWD, PROF_ATTN_BWD, PROF_ADAMW, PROF_NUM = 0, 1, 2, 3, 4
+
+
+class ProfileStats(C.Structure):
+    _fields_ = [("launches", i64), ("total_ms", f64), ("flops", f64), ("bytes", f64)]
+
 
 # every symbol include/srw.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -130,6 +136,8 @@ SYMBOLS = [
     ("srw_last_error", C.c_char_p, []),
     ("srw_device_check", i32, [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
     ("srw_kernel_launches", i64, []),
+    ("srw_profile_enable", i32, [i32]),
+    ("srw_profile_collect", i32, [vp]),
     ("srw_split_planes", i32, [C.POINTER(SplitArgs), vp]),
     ("srw_gemm", i32, [C.POINTER(GemmArgs), vp]),
     ("srw_splitk_reduce", i32, [C.POINTER(SplitKReduceArgs), vp]),

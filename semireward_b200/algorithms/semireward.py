@@ -106,8 +106,12 @@ class Rewarder(nn.Module):
         ps = self._params()
         dev = ps[0].device
         if self._adam is None or self._adam["m"][0].device != dev:
-            self._adam = dict(m=[torch.zeros_like(p) for p in ps], v=[torch.zeros_like(p) for p in ps],
-                              g=[torch.empty_like(p) for p in ps], step=0)
+            gflat = torch.empty(sum(p.numel() for p in ps), dtype=torch.float32, device=dev)
+            gs, off = [], 0
+            for p in ps:
+                gs.append(gflat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            self._adam = dict(m=[torch.zeros_like(p) for p in ps], v=[torch.zeros_like(p) for p in ps], g=gs, gflat=gflat, step=0)
         st = self._adam
         st["step"] += 1
         feats = features.detach()
@@ -120,6 +124,17 @@ class Rewarder(nn.Module):
         a = L.RewarderTrainArgs(B=B, feature_dim=self.feature_dim, label_rows=self.label_rows, num_classes=int(num_classes),
                                 rp=L.ptr_array(ps), g=L.ptr_array(st["g"]), m=L.ptr_array(st["m"]), v=L.ptr_array(st["v"]),
                                 feats=feats.data_ptr(), ld_feats=feats.stride(0), gen_labels=gl.data_ptr(), true_labels=tl.data_ptr(),
-                                lr=float(lr), step=st["step"], losses=losses.data_ptr(), workspace=ws.data_ptr())
-        L.check(L.load().srw_rewarder_train(C.byref(a), L.stream_ptr()), "srw_rewarder_train")
+                                lr=float(lr), step=st["step"], phase=0, losses=losses.data_ptr(), workspace=ws.data_ptr())
+        group = getattr(self, "_dp_group", None)
+        if group is None:
+            L.check(L.load().srw_rewarder_train(C.byref(a), L.stream_ptr()), "srw_rewarder_train")
+        else:
+            # data-parallel (reference: Rewarder wrapped in DDP, srflexmatch.py:49-51): gradients are averaged over the
+            # ranks between the backward and the Adam step
+            from ..parallel import allreduce_mean_
+            a.phase = 1
+            L.check(L.load().srw_rewarder_train(C.byref(a), L.stream_ptr()), "srw_rewarder_train")
+            allreduce_mean_(st["gflat"], group)
+            a.phase = 2
+            L.check(L.load().srw_rewarder_train(C.byref(a), L.stream_ptr()), "srw_rewarder_train")
         return losses

@@ -65,6 +65,14 @@ class SRFlexMatch(AlgorithmBase):
             raise NotImplementedError("sr_ema: every shipped SemiReward config sets sr_ema: False (EMARewarder is unused, SURVEY.md §8a a6)")
         self.rewarder = Rewarder(label_dim(self.num_classes), 128, args.feature_dim)
         self.generator = Generator(args.feature_dim)
+        if torch.cuda.is_available():   # reference: send_model_cuda(args, Rewarder(...)) in the ctor (srflexmatch.py:49-51)
+            self.rewarder, self.generator = self.rewarder.cuda(self.gpu), self.generator.cuda(self.gpu)
+            if self.distributed:
+                import torch.distributed as dist
+                with torch.no_grad():
+                    for p in list(self.rewarder.parameters()) + list(self.generator.parameters()):
+                        dist.broadcast(p.data, src=0)
+                self.rewarder._dp_group = dist.group.WORLD
         self.start_timing = args.start_timing
         self.sr_lr = args.sr_lr
         self.max_reward = -float("inf")

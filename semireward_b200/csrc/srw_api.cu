@@ -2,6 +2,8 @@
 #include <stdarg.h>
 
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "../../include/srw.h"
 #include "srw_common.cuh"
@@ -23,7 +25,53 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return SRW_ERR_CUDA;
 }
 
+// ---- profiling -------------------------------------------------------------------------------------------------
+struct ProfRec { int cls; cudaEvent_t e0, e1; double flops, bytes; };
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+bool g_prof_on = false;
+
+void* prof_begin(int cls, double flops, double bytes, cudaStream_t s) {
+  if (!g_prof_on) return nullptr;
+  ProfRec* r = new ProfRec{cls, nullptr, nullptr, flops, bytes};
+  cudaEventCreate(&r->e0);
+  cudaEventCreate(&r->e1);
+  cudaEventRecord(r->e0, s);
+  return r;
+}
+void prof_end(void* h, cudaStream_t s) {
+  if (!h) return;
+  ProfRec* r = reinterpret_cast<ProfRec*>(h);
+  cudaEventRecord(r->e1, s);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(*r);
+  delete r;
+}
+
 }  // namespace srw
+
+extern "C" int srw_profile_enable(int on) {
+  srw::g_prof_on = on != 0;
+  return SRW_OK;
+}
+
+extern "C" int srw_profile_collect(srw_profile_stats* out) {
+  SRW_REQUIRE(out, "srw_profile_collect: null pointer");
+  SRW_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < SRW_PROF_NUM; ++i) out[i] = srw_profile_stats{0, 0.0, 0.0, 0.0};
+  std::lock_guard<std::mutex> lk(srw::g_prof_mu);
+  for (auto& r : srw::g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+    if (r.cls >= 0 && r.cls < SRW_PROF_NUM) {
+      out[r.cls].launches += 1; out[r.cls].total_ms += ms; out[r.cls].flops += r.flops; out[r.cls].bytes += r.bytes;
+    }
+  }
+  srw::g_prof.clear();
+  return SRW_OK;
+}
 
 extern "C" int srw_version(void) { return 1; }
 

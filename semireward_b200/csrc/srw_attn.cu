@@ -558,7 +558,10 @@ extern "C" int srw_attn_fwd(const srw_attn_fwd_args* a, void* stream_) {
   p.B = a->B; p.N = a->N; p.H = a->H; p.NP = NP; p.scale = a->scale;
   p.o = reinterpret_cast<__nv_bfloat16*>(a->o); p.ld_o = a->ld_o; p.o_ps = a->o_plane_stride; p.lse = a->lse;
   dim3 grid(cdiv(a->N, 128), a->H, a->B);
+  const double pair_flops = 2.0 * a->B * a->H * (double)a->N * a->N * HD;   // one N x N x 64 product per (image, head)
+  void* prof = prof_begin(SRW_PROF_ATTN_FWD, 2.0 * pair_flops, 4.0 * 4.0 * a->B * a->N * a->H * HD, stream);
   attn_fwd_kernel<<<grid, 160, smem_bytes, stream>>>(tq, tkv, p);
+  prof_end(prof, stream);
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;
@@ -595,10 +598,14 @@ extern "C" int srw_attn_bwd(const srw_attn_bwd_args* a, void* stream_) {
   p.lse = a->lse; p.delta = a->delta;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(a->dqkv); p.ld_dqkv = a->ld_dqkv; p.dqkv_ps = a->dqkv_plane_stride;
   dim3 grid(cdiv(a->N, 128), a->H, a->B);
+  // algorithmic backward = 4 products (dP, dV, dQ, dK); the S recomputations are overhead, not counted
+  const double pair_flops = 2.0 * a->B * a->H * (double)a->N * a->N * HD;
+  void* prof = prof_begin(SRW_PROF_ATTN_BWD, 4.0 * pair_flops, 4.0 * 9.0 * a->B * a->N * a->H * HD, stream);
   attn_bwd_kernel<MODE_DQ><<<grid, 192, BWD_SMEM, stream>>>(qkv_r, do_r, qkv_c, do_c, p);
   g_launches++;
   SRW_LAUNCH_CHECK();
   attn_bwd_kernel<MODE_DKV><<<grid, 192, BWD_SMEM, stream>>>(qkv_r, do_r, qkv_c, do_c, p);
+  prof_end(prof, stream);
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;

@@ -44,6 +44,10 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     }                                          \
   } while (0)
 
+// bench-only device timing of a kernel class (srw_profile_enable); no-ops when disabled
+void* prof_begin(int cls, double flops, double bytes, cudaStream_t s);
+void prof_end(void* handle, cudaStream_t s);
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -432,7 +432,9 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
   TcParams tp;
   tp.K = a->K; tp.kb_per_split = kb_per_split; tp.a_mn = a->a_mn_major ? 1 : 0; tp.b_mn = a->b_mn_major ? 1 : 0;
   dim3 grid(cdiv(a->N, BN), cdiv(a->M, BM), grid_z);
+  void* prof = prof_begin(SRW_PROF_GEMM, 2.0 * a->M * a->N * a->K, 4.0 * ((double)a->M * a->K + (double)a->N * a->K + (double)a->M * a->N), stream);
   gemm_bf16x3_tcgen05_kernel<<<grid, 256, GEMM_SMEM_BYTES, stream>>>(ta, tb, tp, ep);
+  prof_end(prof, stream);
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;

@@ -106,7 +106,9 @@ extern "C" int srw_adamw_step(const srw_adamw_args* a, void* stream_) {
   sc.bc1 = 1.0 - pow(a->beta1, (double)a->step);
   sc.bc2_sqrt = sqrt(1.0 - pow(a->beta2, (double)a->step));
   sc.decoupled = a->decoupled; sc.num_tensors = a->num_tensors;
+  void* prof = prof_begin(SRW_PROF_ADAMW, 0.0, 32.0 * (double)a->total_blocks * SRW_ADAMW_BLOCK_ELEMS, stream);
   adamw_kernel<<<(unsigned)a->total_blocks, 256, 0, stream>>>(a->table, sc);
+  prof_end(prof, stream);
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;

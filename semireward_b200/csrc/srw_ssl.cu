@@ -388,9 +388,10 @@ struct AdamScalars { float lr; double bc1, bc2_sqrt; };
 
 __global__ void __launch_bounds__(SSL_THREADS) rewarder_train_kernel(RewPtrs P, RewPtrs G, RewPtrs M, RewPtrs V, RewSizes N, const float* feats,
                                                                     int64_t ld_feats, const int64_t* gen_labels, const int64_t* true_labels,
-                                                                    int B, int D, int label_rows, AdamScalars ad, float* losses, float* ws) {
+                                                                    int B, int D, int label_rows, AdamScalars ad, int phase, float* losses, float* ws) {
   __shared__ float red[32];
   const RewWs s = rew_carve(ws, B);
+  if (phase != 2) {
   rewarder_forward_cta(P, s, feats, ld_feats, gen_labels, B, D, label_rows, red);
   float* f = s.X;
   (void)f;
@@ -476,6 +477,8 @@ __global__ void __launch_bounds__(SSL_THREADS) rewarder_train_kernel(RewPtrs P, 
       G.p[R_EMB][l * 128 + c] += s.demb[b * 128 + c];
     }
   __syncthreads();
+  }  // phase != 2
+  if (phase == 1) return;
   // torch.optim.Adam (single-tensor math): m.lerp_(g, 1-b1); v = v*b2 + (1-b2) g g; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
   const float step_size = (float)((double)ad.lr / ad.bc1);
   const float bc2s = (float)ad.bc2_sqrt;
@@ -566,7 +569,7 @@ extern "C" int srw_rewarder_train(const srw_rewarder_train_args* a, void* stream
   ad.bc1 = 1.0 - pow(0.9, (double)a->step);
   ad.bc2_sqrt = sqrt(1.0 - pow(0.999, (double)a->step));
   rewarder_train_kernel<<<1, SSL_THREADS, 0, stream>>>(P, G, M, V, N, a->feats, a->ld_feats, a->gen_labels, a->true_labels, a->B, a->feature_dim,
-                                                      a->label_rows, ad, a->losses, a->workspace);
+                                                      a->label_rows, ad, a->phase, a->losses, a->workspace);
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;

@@ -103,6 +103,10 @@ class _VitFunction(torch.autograd.Function):
                          workspace_bytes=ctx.wbytes, gemm_impl=model.gemm_impl)
         L.check(lib.srw_vit_backward(C.byref(a), L.stream_ptr()), "srw_vit_backward")
         ctx.ws = None
+        group = getattr(model, "_dp_group", None)
+        if group is not None:   # data parallel: one all-reduce(avg) of the whole flat gradient (C1 in SURVEY.md §2.1)
+            from ..parallel import allreduce_mean_
+            allreduce_mean_(flat, group)
         return (None, None, None, None) + tuple(grads)
 
 
