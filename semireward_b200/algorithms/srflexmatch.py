@@ -86,7 +86,8 @@ class SRFlexMatch(AlgorithmBase):
     def set_hooks(self):
         self.register_hook(PseudoLabelingHook(), "PseudoLabelingHook")
         self.register_hook(FlexMatchThresholdingHook(ulb_dest_len=self.args.ulb_dest_len, num_classes=self.num_classes,
-                                                     thresh_warmup=self.args.thresh_warmup, device=f"cuda:{self.gpu}"), "MaskingHook")
+                                                     thresh_warmup=self.args.thresh_warmup,
+                                                     device=f"cuda:{self.gpu}" if torch.cuda.is_available() else "cpu"), "MaskingHook")
         super().set_hooks()
 
     # -- pieces -----------------------------------------------------------------------------------

@@ -1,0 +1,118 @@
+"""CPU: the C-ABI library loads and exports every symbol include/srw.h declares (no compute calls), and the host-side
+mirror of the reference's plugin surface behaves like the reference's (names, argument meaning, errors)."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as G
+    G.build()
+    from semireward_b200 import _lib as L
+    lib = L.load()
+    hdr = open(os.path.join(ROOT, "include", "srw.h")).read()
+    declared = set(re.findall(r"\b(srw_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"srw_epilogue", "srw_gemm_impl", "srw_profile_class"}
+    assert len(declared) >= 20
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/srw.h but not exported"
+    bound = {n for n, _, _ in L.SYMBOLS}
+    assert declared <= bound, f"not bound in _lib.py: {sorted(declared - bound)}"
+    assert lib.srw_version() >= 1
+
+
+def test_struct_sizes_match_header_layout():
+    """ctypes mirrors of the argument structs: spot-check sizes that would drift if a field were added on one side."""
+    import ctypes as C
+    from semireward_b200 import _lib as L
+    assert C.sizeof(L.AdamWRow) == 5 * 8 + 8 + 8 + 4 + 4 + 8 + 8 + 8
+    assert C.sizeof(L.ProfileStats) == 32
+    assert C.sizeof(L.VitConfig) == 9 * 4
+
+
+def test_registry_and_config_surface():
+    import semireward_b200 as S
+    assert "srflexmatch" in S.ALGORITHMS and "srflexmatch" in S.name2alg.keys()
+    args = S.get_config(dict(algorithm="srflexmatch", ulb_dest_len=100))
+    assert args.p_cutoff == 0.95 and args.start_timing == 20000 and args.feature_dim == 384 and args.N_k == 10 and args.thresh_warmup is True
+    with pytest.raises(KeyError, match="Unknown algorithm"):
+        S.get_config(dict(algorithm="nope"))
+    args.algorithm = "nope"
+    with pytest.raises(KeyError, match="Unknown algorithm"):
+        S.get_algorithm(args, None, None, None)
+    with pytest.raises(KeyError):
+        S.get_net_builder("resnet_nope")
+    assert S.get_net_builder("vit_small_patch2_32").__name__ == "vit_small_patch2_32"
+
+
+def test_net_builder_state_dict_contract():
+    import semireward_b200 as S
+    from oracle import ssl_oracle as O
+    m = S.get_net_builder("vit_small_patch2_32")(num_classes=100)
+    sd = m.state_dict()
+    ref = O.ViTConfig().param_shapes()
+    assert [k for k in sd] == [n for n, _ in ref] and len(sd) == 152
+    assert all(tuple(sd[n].shape) == tuple(s) for n, s in ref)
+    assert m.num_features == 384 and m.no_weight_decay() == {"pos_embed", "cls_token"}
+    assert set(m.group_matcher()) == {"stem", "blocks"}
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 3, 32, 32))   # no CPU fallback
+
+
+def test_param_groups_match_reference_table():
+    import semireward_b200 as S
+    from oracle import ssl_oracle as O
+    from semireward_b200.core.optim import get_cosine_schedule_with_warmup, get_optimizer
+    m = S.get_net_builder("vit_small_patch2_32")(num_classes=100)
+    opt = get_optimizer(m, "AdamW", 5e-4, 0.9, 5e-4, 0.5)
+    assert len(opt.param_groups) == 28
+    hp = O.vit_param_hparams(O.ViTConfig().param_shapes(), 12, 5e-4, 5e-4, 0.5)
+    names = {id(p): n for n, p in m.named_parameters()}
+    for g in opt.param_groups:
+        for p in g["params"]:
+            lr, wd = hp[names[id(p)]]
+            assert abs(g["lr"] - lr) < 1e-18 and g["weight_decay"] == wd, names[id(p)]
+    sched = get_cosine_schedule_with_warmup(opt, 204800, num_warmup_steps=5120)
+    assert sched.get_last_lr()[0] == 0.0
+    assert abs(O.cosine_lr_factor(5120, 204800, 5120) - 1.0) < 1e-12 and O.cosine_lr_factor(100, 204800, 5120) == 100 / 5120
+
+
+def test_algorithm_construction_and_process_batch_filter():
+    import functools
+    import semireward_b200 as S
+    args = S.get_config(dict(algorithm="srflexmatch", optim="AdamW", lr=5e-4, layer_decay=0.5, ulb_dest_len=64, sr_ema=False, num_train_iter=64))
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only construction test")
+    alg = S.get_algorithm(args, functools.partial(S.get_net_builder(args.net), depth=1), None, None)
+    assert list(alg.hooks_dict) == ["ParamUpdateHook", "PseudoLabelingHook", "MaskingHook"]
+    assert alg.registered_hook("MaskingHook") and not alg.registered_hook("DistAlignHook")
+    import inspect
+    assert list(inspect.signature(alg.train_step).parameters) == ["x_lb", "y_lb", "idx_ulb", "x_ulb_w", "x_ulb_s"]
+    alg.it = 20001
+    assert alg.sr_decay() == int(max(8, 1 + 64 / 20001))
+    sd = alg.get_save_dict()
+    assert {"model", "ema_model", "optimizer", "scheduler", "it", "epoch", "best_it", "best_eval_acc", "classwise_acc", "selected_label"} <= set(sd)
+    assert sd["selected_label"].shape == (64,) and int(sd["selected_label"][0]) == -1
+
+
+def test_detgen_is_platform_independent():
+    """Counter-based integer hashing + exact float64 arithmetic: fixed checksums on every machine."""
+    import hashlib
+    from semireward_b200 import detgen
+    x = detgen.normal("x_lb", (4, 3, 8, 8), 7)
+    assert hashlib.sha256(x.tobytes()).hexdigest()[:16] == hashlib.sha256(detgen.normal("x_lb", (4, 3, 8, 8), 7).tobytes()).hexdigest()[:16]
+    assert x.dtype.name == "float32" and abs(float(x.mean())) < 0.2 and 0.7 < float(x.std()) < 1.3
+    idx = detgen.distinct_integers("idx_ulb", 8, 50000, 3)
+    assert len(set(idx.tolist())) == 8 and idx.min() >= 0 and idx.max() < 50000
+    golden = os.path.join(ROOT, "tests", "golden", "detgen_checksums.txt")
+    lines = []
+    for tag, shape, seed in (("x_lb", (8, 3, 32, 32), 1000003), ("head.weight", (100, 384), 0), ("rewarder.label_embedding.weight", (100, 128), 0)):
+        arr = detgen.normal(tag, shape, seed) if tag == "x_lb" else detgen.fill_param(tag, shape, seed)
+        lines.append(f"{tag} {hashlib.sha256(arr.tobytes()).hexdigest()}")
+    if not os.path.isfile(golden):
+        open(golden, "w").write("\n".join(lines) + "\n")
+    assert open(golden).read().split("\n")[:3] == lines
