@@ -52,6 +52,8 @@ typedef struct {
   const float* row_scale; int rows_per_scale;
   void* planes; int64_t ldp; int64_t plane_stride;
   void* planes_t; int64_t ldpt; int64_t plane_stride_t;
+  float* colsum_out; int colsum_accumulate;   /* optional: out[c] (+)= sum_r scaled x[r, c] in the same pass (bias gradient) */
+  float* colsum_workspace;                    /* >= 64 * cols floats when colsum_out != NULL */
 } srw_split_args;
 int srw_split_planes(const srw_split_args* a, void* stream);
 

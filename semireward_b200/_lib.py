@@ -21,7 +21,8 @@ GEMM_TCGEN05, GEMM_SIMT = 0, 1
 
 class SplitArgs(C.Structure):
     _fields_ = [("x", vp), ("ldx", i64), ("rows", i32), ("cols", i32), ("row_scale", vp), ("rows_per_scale", i32),
-                ("planes", vp), ("ldp", i64), ("plane_stride", i64), ("planes_t", vp), ("ldpt", i64), ("plane_stride_t", i64)]
+                ("planes", vp), ("ldp", i64), ("plane_stride", i64), ("planes_t", vp), ("ldpt", i64), ("plane_stride_t", i64),
+                ("colsum_out", vp), ("colsum_accumulate", i32), ("colsum_workspace", vp)]
 
 
 class GemmArgs(C.Structure):

@@ -79,6 +79,11 @@ class SRFlexMatch(AlgorithmBase):
         # with DropPath/dropout off every sampling pass of data_generator sees identical logits: run the backbone once
         # and replay only the hook-state updates (bit-equivalent in that mode only — SURVEY.md §8a a2)
         self.replay_deterministic_passes = True
+        # The SR online update (Generator forward + fused Rewarder train kernel) only consumes detached features and does
+        # not feed this step's loss, so it runs on a side stream concurrently with the backbone backward (two single-CTA
+        # kernels next to 147 busy SMs).  The next step's first use of the Rewarder waits for it.
+        self._sr_stream = None
+        self._sr_done = None
 
     def init(self, T, p_cutoff, hard_label=True, thresh_warmup=True):
         self.T, self.p_cutoff, self.use_hard_label, self.thresh_warmup = T, p_cutoff, hard_label, thresh_warmup
@@ -133,7 +138,26 @@ class SRFlexMatch(AlgorithmBase):
         return last
 
     # -- the step ---------------------------------------------------------------------------------
+    def _sr_update_async(self, feats, true_labels):
+        main = torch.cuda.current_stream()
+        if self._sr_stream is None:
+            self._sr_stream = torch.cuda.Stream()
+        side = self._sr_stream
+        side.wait_stream(main)                       # feats / labels are produced on the main stream
+        with torch.cuda.stream(side):
+            gen = self.generator.generate_labels(feats)
+            self.rewarder.train_step(feats, gen, true_labels, self.sr_lr, self.num_classes)
+            for t in (feats, true_labels):
+                t.record_stream(side)
+        self._sr_done = side.record_event()
+
+    def _sr_wait(self):
+        if self._sr_done is not None:
+            torch.cuda.current_stream().wait_event(self._sr_done)
+            self._sr_done = None
+
     def train_step(self, x_lb, y_lb, idx_ulb, x_ulb_w, x_ulb_s):
+        self._sr_wait()   # last step's Rewarder update must be complete before the Rewarder is read or updated again
         (logits_lb, logits_w, logits_s), (feats_lb, feats_w, feats_s) = self._backbone(x_lb, x_ulb_w, x_ulb_s)
         feat_dict = {"x_lb": feats_lb, "x_ulb_w": feats_w, "x_ulb_s": feats_s}
         y_lb = y_lb.to(torch.long)
@@ -151,11 +175,9 @@ class SRFlexMatch(AlgorithmBase):
                 # mean reward bookkeeping of srflexmatch.py:165-172 (the "filtered" tensors are always the current batch)
                 if self.it % self.N_k == 0 and self.it > self.start_timing:
                     self.max_reward = -float("inf")
-                    gen = self.generator.generate_labels(feats_w)
-                    self.rewarder.train_step(feats_w, gen, pseudo_label, self.sr_lr, self.num_classes)
+                    self._sr_update_async(feats_w.detach(), pseudo_label)
             else:
-                gen = self.generator.generate_labels(feats_lb)
-                self.rewarder.train_step(feats_lb, gen, y_lb, self.sr_lr, self.num_classes)
+                self._sr_update_async(feats_lb.detach(), y_lb)
         sup, unsup, total, util = side["losses"].tolist()   # one 16-byte D2H instead of four .item() syncs
         if self.it <= self.start_timing:
             util = float(util)

@@ -34,16 +34,31 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int g) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((g ^ (r & 7)) << 4));
 }
 
-// write 32 consecutive fp32 values of row r (columns [c0, c0+32) of a 64-wide chunk) as split planes into a swizzled tile
-__device__ __forceinline__ void store_row32_planes(uint8_t* hi_tile, uint8_t* lo_tile, int r, int c0, const float (&v)[32]) {
+// write 16 consecutive fp32 values of row r (columns [c0, c0+16) of a 64-wide chunk, c0 % 16 == 0) as split planes
+__device__ __forceinline__ void store_row16_planes(uint8_t* hi_tile, uint8_t* lo_tile, int r, int c0, const float (&v)[16]) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < 2; ++g) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) split2(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1], h[j], l[j]);
     const uint32_t off = sw128_off(r, (c0 >> 3) + g);
     *reinterpret_cast<uint4*>(hi_tile + off) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(lo_tile + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// sync the 512 element-wise threads only (named barrier 1); the TMA / MMA warps never take part
+__device__ __forceinline__ void ew_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+// write 16 fp32 accumulator columns of one row as split planes to global (32 B hi + 32 B lo)
+__device__ __forceinline__ void store_out16(__nv_bfloat16* hi_ptr, int64_t plane_stride, const float (&v)[16]) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    uint32_t hh[4], ll[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split2(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1], hh[j], ll[j]);
+    *reinterpret_cast<uint4*>(hi_ptr + g * 8) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    *reinterpret_cast<uint4*>(hi_ptr + plane_stride + g * 8) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
   }
 }
 
@@ -57,7 +72,9 @@ struct AttnFwdParams {
   float* lse;             // [B, H, N] natural-log units: scale*max + log(sum)
 };
 
-__global__ void __launch_bounds__(160, 1)
+constexpr int FWD_THREADS = 512 + 32;   // 16 softmax warps (4 per TMEM lane quarter, 16 columns each) + 1 TMA/MMA warp
+
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -71,6 +88,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* bar_p = bars + 4;      // [2]
   uint64_t* bar_pfree = bars + 6;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* xch = reinterpret_cast<float*>(smem + off_bar + 128);   // [4][128] partial row max / row sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -78,11 +96,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int row0 = b * p.N;           // first token row of this image in the [B*N, 3D] qkv matrix
   const int nchunks = (NP + 63) / 64;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_kv);
     mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
-    mbar_init(&bar_p[0], 128); mbar_init(&bar_p[1], 128);
+    mbar_init(&bar_p[0], 16); mbar_init(&bar_p[1], 16);
     mbar_init(&bar_pfree[0], 1); mbar_init(&bar_pfree[1], 1);
     fence_barrier_init();
   }
@@ -96,7 +114,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t tmem = *tmem_slot;
   const uint32_t TM_S = tmem, TM_O = tmem + 384, TM_OX = tmem + 448;
 
-  if (warp == 4) {
+  if (warp == 16) {
     if (lane == 0) {
       // ---- loads ----
       const int half = NP / 2;
@@ -155,103 +173,72 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       umma_commit(bar_o);
     }
   } else {
-    // ---- softmax warps: thread == query row ----
-    const int r = threadIdx.x;                       // 0..127, TMEM lane
+    // ---- softmax warps: 4 warps per TMEM lane quarter; thread == (query row, 16-column interleave `part`) ----
+    const int q = warp & 3, part = warp >> 2;
+    const int r = q * 32 + lane;                     // 0..127, TMEM lane
     const int qr = qt * 128 + r;                     // query index inside the image
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float c2 = p.scale * LOG2E;
+    const int nsub = NP / 16;                        // 16-column sub-chunks; this thread owns sub-chunks part, part+4, ...
     mbar_wait(bar_s, 0);
     tc_fence_after();
     float m = -INFINITY;
-    for (int c0 = 0; c0 < NP; c0 += 32) {
-      if (NP - c0 >= 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(TM_S + lane_addr + c0, v);
-        tmem_ld_wait();
+    for (int sc = part; sc < nsub; sc += 4) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(TM_S + lane_addr + sc * 16, v);
+      tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < p.N) m = fmaxf(m, __uint_as_float(v[j]));
-      } else {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(TM_S + lane_addr + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c0 + j < p.N) m = fmaxf(m, __uint_as_float(v[j]));
-      }
+      for (int j = 0; j < 16; ++j)
+        if (sc * 16 + j < p.N) m = fmaxf(m, __uint_as_float(v[j]));
     }
+    xch[part * 128 + r] = m;
+    ew_sync();
+    m = fmaxf(fmaxf(xch[r], xch[128 + r]), fmaxf(xch[256 + r], xch[384 + r]));
+    ew_sync();                                       // xch is reused for the row sums below
     const float mc = m * c2;
     float sum = 0.f;
     for (int c = 0; c < nchunks; ++c) {
       const int buf = c & 1;
-      float pv[2][32];
+      const int sc = c * 4 + part;
+      float pv[16];
+      const bool have = sc < nsub;
+      if (have) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(TM_S + lane_addr + sc * 16, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        const int c0 = c * 64 + hf * 32;
-        if (c0 + 32 <= NP) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(TM_S + lane_addr + c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float e = (c0 + j < p.N) ? exp2f(fmaf(__uint_as_float(v[j]), c2, -mc)) : 0.f;
-            pv[hf][j] = e;
-            sum += e;
-          }
-        } else if (c0 + 16 <= NP) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(TM_S + lane_addr + c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float e = (c0 + j < p.N) ? exp2f(fmaf(__uint_as_float(v[j]), c2, -mc)) : 0.f;
-            pv[hf][j] = e;
-            sum += e;
-          }
-#pragma unroll
-          for (int j = 16; j < 32; ++j) pv[hf][j] = 0.f;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) pv[hf][j] = 0.f;
+        for (int j = 0; j < 16; ++j) {
+          const float e = (sc * 16 + j < p.N) ? exp2f(fmaf(__uint_as_float(v[j]), c2, -mc)) : 0.f;
+          pv[j] = e;
+          sum += e;
         }
       }
       if (c >= 2) mbar_wait(&bar_pfree[buf], ((c >> 1) - 1) & 1);
-      uint8_t* hi_tile = smem + buf * 2 * ROW_TILE_BYTES;
-      uint8_t* lo_tile = hi_tile + ROW_TILE_BYTES;
-      store_row32_planes(hi_tile, lo_tile, r, 0, pv[0]);
-      store_row32_planes(hi_tile, lo_tile, r, 32, pv[1]);
+      if (have) {
+        uint8_t* hi_tile = smem + buf * 2 * ROW_TILE_BYTES;
+        store_row16_planes(hi_tile, hi_tile + ROW_TILE_BYTES, r, part * 16, pv);
+      }
       fence_proxy_async();
-      mbar_arrive(&bar_p[buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p[buf]);
     }
-    // ---- epilogue ----
+    xch[part * 128 + r] = sum;
+    ew_sync();
+    sum = (xch[r] + xch[128 + r]) + (xch[256 + r] + xch[384 + r]);
+    // ---- epilogue: this thread writes output columns [16*part, 16*part+16) of its row ----
     mbar_wait(bar_o, 0);
     tc_fence_after();
     const float inv = 1.0f / sum;
+    if (part == 0 && qr < p.N && p.lse) p.lse[((int64_t)b * p.H + h) * p.N + qr] = m * p.scale + logf(sum);
+    uint32_t a[16], x[16];
+    tmem_ld_32x32b_x16(TM_O + lane_addr + part * 16, a);
+    tmem_ld_32x32b_x16(TM_OX + lane_addr + part * 16, x);
+    tmem_ld_wait();
     if (qr < p.N) {
-      if (p.lse) p.lse[((int64_t)b * p.H + h) * p.N + qr] = m * p.scale + logf(sum);
-    }
-    __nv_bfloat16* orow = p.o + (int64_t)(row0 + qr) * p.ld_o + h * HD;
+      float o16[16];
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      uint32_t a[32], x[32];
-      tmem_ld_32x32b_x32(TM_O + lane_addr + hf * 32, a);
-      tmem_ld_32x32b_x32(TM_OX + lane_addr + hf * 32, x);
-      tmem_ld_wait();
-      if (qr < p.N) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t hh[4], ll[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int e = g * 8 + 2 * j;
-            const float v0 = (__uint_as_float(a[e]) + __uint_as_float(x[e])) * inv;
-            const float v1 = (__uint_as_float(a[e + 1]) + __uint_as_float(x[e + 1])) * inv;
-            split2(v0, v1, hh[j], ll[j]);
-          }
-          *reinterpret_cast<uint4*>(orow + hf * 32 + g * 8) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-          *reinterpret_cast<uint4*>(orow + p.o_ps + hf * 32 + g * 8) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-        }
-      }
+      for (int j = 0; j < 16; ++j) o16[j] = (__uint_as_float(a[j]) + __uint_as_float(x[j])) * inv;
+      store_out16(p.o + (int64_t)(row0 + qr) * p.ld_o + h * HD + part * 16, p.o_ps, o16);
     }
   }
   tc_fence_before();
@@ -277,16 +264,17 @@ struct AttnBwdParams {
   __nv_bfloat16* dqkv; int64_t ld_dqkv, dqkv_ps;
 };
 
+constexpr int BWD_THREADS = 512 + 64;   // 16 element-wise warps + TMA warp + MMA warp
 constexpr int BWD_OFF_R1 = 0, BWD_OFF_R2 = 2 * ROW_TILE_BYTES, BWD_OFF_C = 4 * ROW_TILE_BYTES;
 constexpr int BWD_CSTAGE = 2 * ROW_TILE_BYTES;  // C1 (hi 8K, lo 8K) + C2 (hi 8K, lo 8K)
 constexpr int BWD_OFF_X = BWD_OFF_C + 2 * BWD_CSTAGE;
 constexpr int BWD_OFF_Y = BWD_OFF_X + 2 * ROW_TILE_BYTES;
-constexpr int BWD_OFF_VEC = BWD_OFF_Y + 2 * ROW_TILE_BYTES;       // 2 x 320 floats (lse*log2e, delta per column)
-constexpr int BWD_OFF_BAR = BWD_OFF_VEC + 2 * 320 * 4;
+constexpr int BWD_OFF_VEC = BWD_OFF_Y + 2 * ROW_TILE_BYTES;       // 2 x 320 floats (lse*log2e, delta per column) + [4][128] exchange
+constexpr int BWD_OFF_BAR = BWD_OFF_VEC + 2 * 320 * 4 + 4 * 128 * 4;
 constexpr int BWD_SMEM = BWD_OFF_BAR + 256 + 1024;
 
 template <int MODE>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_constant__ CUtensorMap tm_do_r,
                 const __grid_constant__ CUtensorMap tm_qkv_c, const __grid_constant__ CUtensorMap tm_do_c, const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -302,6 +290,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
   float* vec_lse = reinterpret_cast<float*>(smem + BWD_OFF_VEC);
   float* vec_delta = vec_lse + 320;
+  float* xch = vec_delta + 320;     // [4][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -310,11 +299,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
   const int nchunks = (p.NP + 63) / 64;
   const int64_t stat0 = ((int64_t)b * p.H + h) * p.N;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tm_qkv_r); tma_prefetch_desc(&tm_do_r); tma_prefetch_desc(&tm_qkv_c); tma_prefetch_desc(&tm_do_c);
     mbar_init(bar_r, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&bar_cfull[s], 1); mbar_init(&bar_cfree[s], 1); mbar_init(&bar_t[s], 1); }
-    mbar_init(bar_x, 128); mbar_init(bar_xfree, 1); mbar_init(bar_acc, 1);
+    mbar_init(bar_x, 16); mbar_init(bar_xfree, 1); mbar_init(bar_acc, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -338,7 +327,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
   const int c1_col = (MODE == MODE_DQ ? D : 0) + h * HD;       // C1: K (DQ) / Q (DKV)
   const int c2_col = (MODE == MODE_DQ ? 2 * D : 0) + h * HD;   // C2: V (DQ) / dO (DKV, own matrix)
 
-  if (warp == 4) {
+  if (warp == 16) {
     if (lane == 0) {
       // ===== TMA producer =====
       mbar_arrive_expect_tx(bar_r, 4 * ROW_TILE_BYTES);
@@ -355,7 +344,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
         else tma_load_3d(st + ROW_TILE_BYTES, &tm_do_c, &bar_cfull[s], h * HD, row0 + j * 64, 0);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 17) {
     if (lane == 0) {
       // ===== MMA issuer =====
       const uint32_t idesc_t = umma_idesc_bf16(64, 0, 0);     // T = R C^T   (both K-major, K = head dim)
@@ -415,21 +404,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       umma_commit(bar_acc);
     }
   } else {
-    // ===== element-wise warps: thread == tile row =====
-    const int r = threadIdx.x;
+    // ===== element-wise warps: 4 per TMEM lane quarter; thread == (tile row, 16-column slice `part` of each 64-column chunk) =====
+    const int q = warp & 3, part = warp >> 2;
+    const int r = q * 32 + lane;
     const int rr = rt * 128 + r;            // row index inside the image (query for DQ, key for DKV)
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float c2s = p.scale * LOG2E;
     float row_lse = 0.f, row_delta = 0.f;
     if (MODE == MODE_DQ) {
+      // delta = sum_d dO * O over this head's 64 columns; each of the row's 4 threads sums 16 of them
+      float acc = 0.f;
       if (rr < p.N) {
         row_lse = p.lse[stat0 + rr] * LOG2E;
-        // delta = sum_d dO * O over this head's 64 columns (fp32 values reconstructed from the planes)
-        const __nv_bfloat16* orow = p.o + (int64_t)(row0 + rr) * p.ld_o + h * HD;
-        const __nv_bfloat16* drow = p.d_o + (int64_t)(row0 + rr) * p.ld_do + h * HD;
-        float acc = 0.f;
+        const __nv_bfloat16* orow = p.o + (int64_t)(row0 + rr) * p.ld_o + h * HD + part * 16;
+        const __nv_bfloat16* drow = p.d_o + (int64_t)(row0 + rr) * p.ld_do + h * HD + part * 16;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
+        for (int g = 0; g < 2; ++g) {
           const uint4 oh = *reinterpret_cast<const uint4*>(orow + g * 8), ol = *reinterpret_cast<const uint4*>(orow + p.o_ps + g * 8);
           const uint4 dh = *reinterpret_cast<const uint4*>(drow + g * 8), dl = *reinterpret_cast<const uint4*>(drow + p.do_ps + g * 8);
           const uint32_t ohh[4] = {oh.x, oh.y, oh.z, oh.w}, oll[4] = {ol.x, ol.y, ol.z, ol.w};
@@ -440,72 +430,61 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
             acc = fmaf(bf16_hi_f(ohh[j]) + bf16_hi_f(oll[j]), bf16_hi_f(dhh[j]) + bf16_hi_f(dll[j]), acc);
           }
         }
-        row_delta = acc;
-        p.delta[stat0 + rr] = acc;
       }
+      xch[part * 128 + r] = acc;
+      ew_sync();
+      row_delta = (xch[r] + xch[128 + r]) + (xch[256 + r] + xch[384 + r]);
+      if (part == 0 && rr < p.N) p.delta[stat0 + rr] = row_delta;
     }
+    uint8_t* x_hi = smem + BWD_OFF_X; uint8_t* x_lo = x_hi + ROW_TILE_BYTES;
+    uint8_t* y_hi = smem + BWD_OFF_Y; uint8_t* y_lo = y_hi + ROW_TILE_BYTES;
     for (int j = 0; j < nchunks; ++j) {
       const int s = j & 1;
       mbar_wait(&bar_t[s], (j >> 1) & 1);
       tc_fence_after();
-      if (j >= 1) mbar_wait(bar_xfree, (j - 1) & 1);
-      uint8_t* x_hi = smem + BWD_OFF_X; uint8_t* x_lo = x_hi + ROW_TILE_BYTES;
-      uint8_t* y_hi = smem + BWD_OFF_Y; uint8_t* y_lo = y_hi + ROW_TILE_BYTES;
+      uint32_t t1[16], t2[16];
+      tmem_ld_32x32b_x16(tmem + lane_addr + s * 128 + part * 16, t1);
+      tmem_ld_32x32b_x16(tmem + lane_addr + s * 128 + 64 + part * 16, t2);
+      tmem_ld_wait();
+      float xs[16], ys[16];
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t t1[32], t2[32];
-        tmem_ld_32x32b_x32(tmem + lane_addr + s * 128 + hf * 32, t1);
-        tmem_ld_32x32b_x32(tmem + lane_addr + s * 128 + 64 + hf * 32, t2);
-        tmem_ld_wait();
-        float xs[32], ys[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int col = j * 64 + hf * 32 + e;     // key index (DQ) / query index (DKV)
-          float pe, ds;
-          if (MODE == MODE_DQ) {
-            pe = (col < p.N) ? exp2f(fmaf(__uint_as_float(t1[e]), c2s, -row_lse)) : 0.f;
-            ds = pe * (__uint_as_float(t2[e]) - row_delta) * p.scale;
-          } else {
-            pe = (col < p.N) ? exp2f(fmaf(__uint_as_float(t1[e]), c2s, -vec_lse[col])) : 0.f;
-            ds = pe * (__uint_as_float(t2[e]) - vec_delta[col]) * p.scale;
-          }
-          xs[e] = ds;
-          ys[e] = pe;
+      for (int e = 0; e < 16; ++e) {
+        const int col = j * 64 + part * 16 + e;     // key index (DQ) / query index (DKV)
+        float pe, ds;
+        if (MODE == MODE_DQ) {
+          pe = (col < p.N) ? exp2f(fmaf(__uint_as_float(t1[e]), c2s, -row_lse)) : 0.f;
+          ds = pe * (__uint_as_float(t2[e]) - row_delta) * p.scale;
+        } else {
+          pe = (col < p.N) ? exp2f(fmaf(__uint_as_float(t1[e]), c2s, -vec_lse[col])) : 0.f;
+          ds = pe * (__uint_as_float(t2[e]) - vec_delta[col]) * p.scale;
         }
-        store_row32_planes(x_hi, x_lo, r, hf * 32, xs);
-        if (MODE == MODE_DKV) store_row32_planes(y_hi, y_lo, r, hf * 32, ys);
+        xs[e] = ds;
+        ys[e] = pe;
       }
+      if (j >= 1) mbar_wait(bar_xfree, (j - 1) & 1);
+      store_row16_planes(x_hi, x_lo, r, part * 16, xs);
+      if (MODE == MODE_DKV) store_row16_planes(y_hi, y_lo, r, part * 16, ys);
       tc_fence_before();
       fence_proxy_async();
-      mbar_arrive(bar_x);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_x);
     }
-    // ---- write the accumulators ----
+    // ---- write the accumulators: this thread owns head-dim columns [16*part, 16*part+16) of its row ----
     mbar_wait(bar_acc, 0);
     tc_fence_after();
     const int nout = MODE == MODE_DQ ? 1 : 2;
     for (int w = 0; w < nout; ++w) {
       // DQ: dQ -> columns [0, D);  DKV: dK -> [D, 2D), dV -> [2D, 3D)
-      const int col0 = (MODE == MODE_DQ ? 0 : (w == 0 ? D : 2 * D)) + h * HD;
-      __nv_bfloat16* orow = p.dqkv + (int64_t)(row0 + rr) * p.ld_dqkv + col0;
+      const int col0 = (MODE == MODE_DQ ? 0 : (w == 0 ? D : 2 * D)) + h * HD + part * 16;
+      uint32_t a[16], x[16];
+      tmem_ld_32x32b_x16(tmem + lane_addr + 256 + w * 128 + part * 16, a);
+      tmem_ld_32x32b_x16(tmem + lane_addr + 320 + w * 128 + part * 16, x);
+      tmem_ld_wait();
+      if (rr < p.N) {
+        float o16[16];
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t a[32], x[32];
-        tmem_ld_32x32b_x32(tmem + lane_addr + 256 + w * 128 + hf * 32, a);
-        tmem_ld_32x32b_x32(tmem + lane_addr + 320 + w * 128 + hf * 32, x);
-        tmem_ld_wait();
-        if (rr < p.N) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint32_t hh[4], ll[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int e = g * 8 + 2 * q;
-              split2(__uint_as_float(a[e]) + __uint_as_float(x[e]), __uint_as_float(a[e + 1]) + __uint_as_float(x[e + 1]), hh[q], ll[q]);
-            }
-            *reinterpret_cast<uint4*>(orow + hf * 32 + g * 8) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-            *reinterpret_cast<uint4*>(orow + p.dqkv_ps + hf * 32 + g * 8) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-          }
-        }
+        for (int e = 0; e < 16; ++e) o16[e] = __uint_as_float(a[e]) + __uint_as_float(x[e]);
+        store_out16(p.dqkv + (int64_t)(row0 + rr) * p.ld_dqkv + col0, p.dqkv_ps, o16);
       }
     }
   }
@@ -549,7 +528,7 @@ extern "C" int srw_attn_fwd(const srw_attn_fwd_args* a, void* stream_) {
   SRW_REQUIRE(a->ld_o % 8 == 0 && a->o_plane_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(a->o) & 15) == 0, "srw_attn_fwd: o planes must be 16-byte aligned");
   const uint32_t kv_plane = (uint32_t)NP * 128;
   const uint32_t off_v = std::max<uint32_t>(2 * ROW_TILE_BYTES + 2 * kv_plane, 4u * ROW_TILE_BYTES);
-  const int smem_bytes = (int)(off_v + 2 * kv_plane + 256 + 1024);
+  const int smem_bytes = (int)(off_v + 2 * kv_plane + 128 + 4 * 128 * 4 + 1024);
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
@@ -560,7 +539,7 @@ extern "C" int srw_attn_fwd(const srw_attn_fwd_args* a, void* stream_) {
   dim3 grid(cdiv(a->N, 128), a->H, a->B);
   const double pair_flops = 2.0 * a->B * a->H * (double)a->N * a->N * HD;   // one N x N x 64 product per (image, head)
   void* prof = prof_begin(SRW_PROF_ATTN_FWD, 2.0 * pair_flops, 4.0 * 4.0 * a->B * a->N * a->H * HD, stream);
-  attn_fwd_kernel<<<grid, 160, smem_bytes, stream>>>(tq, tkv, p);
+  attn_fwd_kernel<<<grid, FWD_THREADS, smem_bytes, stream>>>(tq, tkv, p);
   prof_end(prof, stream);
   g_launches++;
   SRW_LAUNCH_CHECK();
@@ -601,10 +580,10 @@ extern "C" int srw_attn_bwd(const srw_attn_bwd_args* a, void* stream_) {
   // algorithmic backward = 4 products (dP, dV, dQ, dK); the S recomputations are overhead, not counted
   const double pair_flops = 2.0 * a->B * a->H * (double)a->N * a->N * HD;
   void* prof = prof_begin(SRW_PROF_ATTN_BWD, 4.0 * pair_flops, 4.0 * 9.0 * a->B * a->N * a->H * HD, stream);
-  attn_bwd_kernel<MODE_DQ><<<grid, 192, BWD_SMEM, stream>>>(qkv_r, do_r, qkv_c, do_c, p);
+  attn_bwd_kernel<MODE_DQ><<<grid, BWD_THREADS, BWD_SMEM, stream>>>(qkv_r, do_r, qkv_c, do_c, p);
   g_launches++;
   SRW_LAUNCH_CHECK();
-  attn_bwd_kernel<MODE_DKV><<<grid, 192, BWD_SMEM, stream>>>(qkv_r, do_r, qkv_c, do_c, p);
+  attn_bwd_kernel<MODE_DKV><<<grid, BWD_THREADS, BWD_SMEM, stream>>>(qkv_r, do_r, qkv_c, do_c, p);
   prof_end(prof, stream);
   g_launches++;
   SRW_LAUNCH_CHECK();

@@ -47,6 +47,81 @@ __global__ void split_planes_kernel(const float* __restrict__ x, int64_t ldx, in
   }
 }
 
+// Fast path (no transposed copy): planes = split(scale(r) * x), optionally with per-block column partial sums
+// (the bias gradient of the layer whose output gradient this is).  128 columns per block-column (float4 per lane),
+// 8 warps stride the rows of the block's row range.
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols,
+                                                         const float* __restrict__ row_scale, int rows_per_scale,
+                                                         __nv_bfloat16* __restrict__ planes, int64_t ldp, int64_t ps,
+                                                         float* __restrict__ partial /* [gridDim.y, cols] or NULL */) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + lane * 4;
+  const int rows_per_block = (rows + gridDim.y - 1) / gridDim.y;
+  const int r_begin = blockIdx.y * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < cols) {
+    for (int r = r_begin + warp; r < r_end; r += 8) {
+      float4 v = *reinterpret_cast<const float4*>(x + (int64_t)r * ldx + c);
+      if (row_scale) {
+        const float sc = row_scale[r / rows_per_scale];
+        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+      }
+      uint32_t h0, l0, h1, l1;
+      split2(v.x, v.y, h0, l0);
+      split2(v.z, v.w, h1, l1);
+      __nv_bfloat16* hp = planes + (int64_t)r * ldp + c;
+      *reinterpret_cast<uint2*>(hp) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(hp + ps) = make_uint2(l0, l1);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  if (partial == nullptr) return;
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && c < cols) {
+    float4 s = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { s.x += red[w][lane].x; s.y += red[w][lane].y; s.z += red[w][lane].z; s.w += red[w][lane].w; }
+    *reinterpret_cast<float4*>(partial + (int64_t)blockIdx.y * cols + c) = s;
+  }
+}
+
+// column partial sums of split planes: 8 bf16 (one uint4 per plane) per lane, 256 columns per block-column
+__global__ void __launch_bounds__(256) colsum_planes_kernel(const __nv_bfloat16* __restrict__ planes, int64_t ldp, int64_t ps, int rows, int cols,
+                                                            float* __restrict__ partial /* [gridDim.y, cols] */) {
+  __shared__ float red[8][32][9];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + lane * 8;
+  const int rows_per_block = (rows + gridDim.y - 1) / gridDim.y;
+  const int r_begin = blockIdx.y * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < cols) {
+    for (int r = r_begin + warp; r < r_end; r += 8) {
+      const uint4 h = *reinterpret_cast<const uint4*>(planes + (int64_t)r * ldp + c);
+      const uint4 l = *reinterpret_cast<const uint4*>(planes + (int64_t)r * ldp + c + ps);
+      const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] += bf16_lo_f(hh[j]) + bf16_lo_f(ll[j]);
+        acc[2 * j + 1] += bf16_hi_f(hh[j]) + bf16_hi_f(ll[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp][lane][j] = acc[j];
+  __syncthreads();
+  if (warp == 0 && c < cols) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][lane][j];
+      partial[(int64_t)blockIdx.y * cols + c + j] = s;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // split-K reduce
 // ------------------------------------------------------------------------------------------------
@@ -96,6 +171,28 @@ __global__ void colsum_stage1_kernel(const float* __restrict__ x, int64_t ldx, c
     partial[(int64_t)blockIdx.y * cols + c] = s;
   }
 }
+// out_y[c] (+)= sum_p partial[p * stride_p + y * stride_y + c]  for y = blockIdx.y; 8 warps split the partials, then a
+// shared-memory fold in fixed order (deterministic).  Used by colsum (y = 0) and LayerNorm dgamma / dbeta (y = 0, 1).
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int nparts, int64_t stride_p, int64_t stride_y,
+                                                              int cols, float* __restrict__ out0, float* __restrict__ out1, int accumulate) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const float* src = partial + blockIdx.y * stride_y;
+  float acc = 0.f;
+  if (c < cols)
+    for (int p = ty; p < nparts; p += 8) acc += src[(int64_t)p * stride_p + c];
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][tx];
+    float* out = blockIdx.y == 0 ? out0 : out1;
+    out[c] = accumulate ? out[c] + s : s;
+  }
+}
+
 __global__ void colsum_stage2_kernel(const float* __restrict__ partial, int nparts, int cols, float* __restrict__ out, int accumulate) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
@@ -142,6 +239,59 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, int64_t ldx, i
     y.y = (v.y - mean) * rstd * g.y + b.y;
     y.z = (v.z - mean) * rstd * g.z + b.z;
     y.w = (v.w - mean) * rstd * g.w + b.w;
+    if (yf) *reinterpret_cast<float4*>(yf + (int64_t)row * ldy + c) = y;
+    if (yp) {
+      uint32_t h0, l0, h1, l1;
+      split2(y.x, y.y, h0, l0);
+      split2(y.z, y.w, h1, l1);
+      __nv_bfloat16* hp = yp + (int64_t)row * ldp + c;
+      *reinterpret_cast<uint2*>(hp) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(hp + ps) = make_uint2(l0, l1);
+    }
+  }
+}
+
+// Register-resident variant for cols == J * 128: the row is read from HBM exactly once.
+template <int J>
+__global__ void __launch_bounds__(256) layernorm_fwd_reg_kernel(const float* __restrict__ x, int64_t ldx, int rows, float eps,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                                __nv_bfloat16* __restrict__ yp, int64_t ldp, int64_t ps, float* __restrict__ yf,
+                                                                int64_t ldy) {
+  constexpr int COLS = J * 128;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + (int64_t)row * ldx;
+  float4 v[J];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    v[j] = *reinterpret_cast<const float4*>(xr + j * 128 + lane * 4);
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / COLS);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+    q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / COLS) + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int c = j * 128 + lane * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 b = *reinterpret_cast<const float4*>(beta + c);
+    float4 y;
+    y.x = v[j].x * rstd * g.x + b.x;
+    y.y = v[j].y * rstd * g.y + b.y;
+    y.z = v[j].z * rstd * g.z + b.z;
+    y.w = v[j].w * rstd * g.w + b.w;
     if (yf) *reinterpret_cast<float4*>(yf + (int64_t)row * ldy + c) = y;
     if (yp) {
       uint32_t h0, l0, h1, l1;
@@ -231,6 +381,26 @@ using namespace srw;
 extern "C" int srw_split_planes(const srw_split_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SRW_REQUIRE(a && a->x && a->rows > 0 && a->cols > 0 && (a->planes || a->planes_t), "srw_split_planes: bad args");
+  const bool fast = a->planes && !a->planes_t && a->cols % 4 == 0 && a->ldx % 4 == 0 && a->ldp % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->planes) & 7) == 0 && a->plane_stride % 4 == 0;
+  if (fast) {
+    const int nparts = a->colsum_out ? std::min(64, cdiv(a->rows, 32)) : std::min(std::max(1, 592 / cdiv(a->cols, 128)), cdiv(a->rows, 8));
+    SRW_REQUIRE(!a->colsum_out || a->colsum_workspace, "srw_split_planes: colsum_out needs colsum_workspace (>= 64 * cols floats)");
+    split_rows_kernel<<<dim3(cdiv(a->cols, 128), nparts), 256, 0, stream>>>(a->x, a->ldx, a->rows, a->cols, a->row_scale,
+                                                                          a->rows_per_scale > 0 ? a->rows_per_scale : 1,
+                                                                          reinterpret_cast<__nv_bfloat16*>(a->planes), a->ldp, a->plane_stride,
+                                                                          a->colsum_out ? a->colsum_workspace : nullptr);
+    g_launches++;
+    SRW_LAUNCH_CHECK();
+    if (a->colsum_out) {
+      reduce_partials_kernel<<<dim3(cdiv(a->cols, 32), 1), 256, 0, stream>>>(a->colsum_workspace, nparts, a->cols, 0, a->cols, a->colsum_out, nullptr,
+                                                                               a->colsum_accumulate);
+      g_launches++;
+      SRW_LAUNCH_CHECK();
+    }
+    return SRW_OK;
+  }
+  SRW_REQUIRE(!a->colsum_out, "srw_split_planes: fused column sums need the aligned non-transposed path");
   dim3 grid(cdiv(a->cols, 32), cdiv(a->rows, 32)), block(32, 8);
   split_planes_kernel<<<grid, block, 0, stream>>>(a->x, a->ldx, a->rows, a->cols, a->row_scale, a->rows_per_scale > 0 ? a->rows_per_scale : 1,
                                                  reinterpret_cast<__nv_bfloat16*>(a->planes), a->ldp, a->plane_stride,
@@ -254,13 +424,23 @@ extern "C" int srw_splitk_reduce(const srw_splitk_reduce_args* a, void* stream_)
 extern "C" int srw_colsum(const srw_colsum_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SRW_REQUIRE(a && (a->x || a->planes) && a->out && a->workspace && a->rows > 0 && a->cols > 0, "srw_colsum: bad args");
-  const int nparts = std::min(256, cdiv(a->rows, 8));
+  const int nparts = std::min(64, cdiv(a->rows, 32));
+  if (a->planes && !a->row_scale && a->cols % 8 == 0 && a->ldp % 8 == 0 && a->plane_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(a->planes) & 15) == 0) {
+    colsum_planes_kernel<<<dim3(cdiv(a->cols, 256), nparts), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->planes), a->ldp, a->plane_stride,
+                                                                              a->rows, a->cols, a->workspace);
+    g_launches++;
+    SRW_LAUNCH_CHECK();
+    reduce_partials_kernel<<<dim3(cdiv(a->cols, 32), 1), 256, 0, stream>>>(a->workspace, nparts, a->cols, 0, a->cols, a->out, nullptr, a->accumulate);
+    g_launches++;
+    SRW_LAUNCH_CHECK();
+    return SRW_OK;
+  }
   dim3 grid(cdiv(a->cols, 32), nparts);
   colsum_stage1_kernel<<<grid, 256, 0, stream>>>(a->x, a->ldx, reinterpret_cast<const __nv_bfloat16*>(a->planes), a->ldp, a->plane_stride,
                                                 a->row_scale, a->rows_per_scale > 0 ? a->rows_per_scale : 1, a->rows, a->cols, a->workspace);
   g_launches++;
   SRW_LAUNCH_CHECK();
-  colsum_stage2_kernel<<<cdiv(a->cols, 128), 128, 0, stream>>>(a->workspace, nparts, a->cols, a->out, a->accumulate);
+  reduce_partials_kernel<<<dim3(cdiv(a->cols, 32), 1), 256, 0, stream>>>(a->workspace, nparts, a->cols, 0, a->cols, a->out, nullptr, a->accumulate);
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;
@@ -272,9 +452,18 @@ extern "C" int srw_layernorm_fwd(const srw_layernorm_fwd_args* a, void* stream_)
               "srw_layernorm_fwd: bad args (cols %% 4 == 0 required)");
   SRW_REQUIRE(!a->y_planes || a->ldp % 4 == 0, "srw_layernorm_fwd: ldp %% 4");
   SRW_REQUIRE(!a->y_f32 || a->ldy % 4 == 0, "srw_layernorm_fwd: ldy %% 4");
-  layernorm_fwd_kernel<<<cdiv(a->rows, 8), 256, 0, stream>>>(a->x, a->ldx, a->rows, a->cols, a->eps, a->gamma, a->beta, a->mean, a->rstd,
-                                                            reinterpret_cast<__nv_bfloat16*>(a->y_planes), a->ldp, a->plane_stride,
-                                                            a->y_f32, a->ldy);
+#define SRW_LN_FWD(J)                                                                                                                   \
+  layernorm_fwd_reg_kernel<J><<<cdiv(a->rows, 8), 256, 0, stream>>>(a->x, a->ldx, a->rows, a->eps, a->gamma, a->beta, a->mean, a->rstd,       \
+                                                                   reinterpret_cast<__nv_bfloat16*>(a->y_planes), a->ldp, a->plane_stride, \
+                                                                   a->y_f32, a->ldy)
+  if (a->cols == 384) SRW_LN_FWD(3);
+  else if (a->cols == 768) SRW_LN_FWD(6);
+  else if (a->cols == 1024) SRW_LN_FWD(8);
+  else
+    layernorm_fwd_kernel<<<cdiv(a->rows, 8), 256, 0, stream>>>(a->x, a->ldx, a->rows, a->cols, a->eps, a->gamma, a->beta, a->mean, a->rstd,
+                                                              reinterpret_cast<__nv_bfloat16*>(a->y_planes), a->ldp, a->plane_stride,
+                                                              a->y_f32, a->ldy);
+#undef SRW_LN_FWD
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;
@@ -300,7 +489,8 @@ extern "C" int srw_layernorm_bwd(const srw_layernorm_bwd_args* a, void* stream_)
   g_launches++;
   SRW_LAUNCH_CHECK();
   if (a->dgamma && a->dbeta) {
-    layernorm_bwd_params_kernel<<<cdiv(a->cols, 128), 128, 0, stream>>>(a->workspace, nblocks, a->cols, a->dgamma, a->dbeta, a->accumulate_dparams);
+    reduce_partials_kernel<<<dim3(cdiv(a->cols, 32), 2), 256, 0, stream>>>(a->workspace, nblocks, 2 * (int64_t)a->cols, a->cols, a->cols, a->dgamma,
+                                                                             a->dbeta, a->accumulate_dparams);
     g_launches++;
     SRW_LAUNCH_CHECK();
   }

@@ -5,9 +5,15 @@
 // Operands are "split planes" (srw_common.cuh): per 64-wide K block the kernel stages A_hi, A_lo, B_hi, B_lo once and
 // issues three MMAs (hi*hi, hi*lo, lo*hi) into the same accumulator.
 //
-// Roles (one 128x128 output tile per CTA, 256 threads):
+// Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x + i*gridDim.x (n fastest, so the CTAs
+// running together share A row-blocks and the whole weight matrix through L2).  Tile = 128 x BN, BN in {192, 128, 64}
+// (192 divides every ViT width: 384/1152/1536, 768/2304/3072).  256 threads:
 //   warp 0  : TMA producer (one elected lane)          warp 2 : TMEM allocator / deallocator
-//   warp 1  : MMA issuer  (one elected lane)           warps 4-7 : epilogue (thread == accumulator row == TMEM lane)
+//   warp 1  : MMA issuer  (one elected lane)           warps 4-15: epilogue (12 warps: the fused epilogues — erf GELU, hi/lo
+//                                                       split, residual — are instruction-bound, not memory-bound)
+// The fp32 accumulator is double-buffered in TMEM (2 x 256 columns), so the epilogue of tile i (TMEM -> registers ->
+// fused op -> global) overlaps the MMAs of tile i+1.  One accumulator per tile; the host keeps K per CTA <= 2048 (split-K
+// beyond) because the tensor core's fp32 accumulate truncates and long single-accumulator sums lose the cross terms.
 // A SIMT kernel over the same operands and the same epilogue code is kept as the on-device verification twin
 // (srw_gemm_args.impl = SRW_GEMM_SIMT); it is a debugging aid, never the default path.
 #include <cuda.h>
@@ -23,11 +29,20 @@ namespace srw {
 
 extern std::atomic<int64_t> g_launches;
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int BM = 128, BK = 64;
 constexpr int PLANE_TILE_BYTES = 128 * BK * 2;         // 16 KiB: one 128 x 64 bf16 tile
-constexpr int STAGE_BYTES = 4 * PLANE_TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
-constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int TMEM_COLS = 256;  // [0,128): hi*hi accumulator, [128,256): cross-term (hi*lo + lo*hi) accumulator
+constexpr int A_STAGE_BYTES = 2 * PLANE_TILE_BYTES;    // A_hi, A_lo
+constexpr int TMEM_COLS = 512;                         // two accumulator buffers of 256 columns
+constexpr int MAX_K_PER_CTA = 2048;
+__host__ __device__ constexpr int gemm_stage_bytes(int bn) { return A_STAGE_BYTES + bn * BK * 2 * 2; }
+__host__ __device__ constexpr int gemm_stages(int bn) { return bn == 64 ? 3 : 2; }
+constexpr int EPI_STAGE_LD = 36;                         // floats per staged row (32 + 4 pad: 16 B aligned, conflict-free)
+constexpr int EPI_WARPS = 12;                            // 3 warps per TMEM lane quarter, interleaved over 32-column chunks
+constexpr int GEMM_THREADS = 128 + 32 * EPI_WARPS;
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * EPI_STAGE_LD * 4;  // one 32 x 32 fp32 transpose buffer per epilogue warp
+__host__ __device__ constexpr int gemm_smem_bytes(int bn) {
+  return gemm_stages(bn) * gemm_stage_bytes(bn) + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
+}
 
 struct EpiParams {
   int M, N;
@@ -112,30 +127,33 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
 // ------------------------------------------------------------------------------------------------
 struct TcParams {
   int K;            // reduction length
-  int kb_per_split; // k blocks (of 64) handled by one grid.z slice
+  int kb_per_split; // k blocks (of 64) handled by one split
   int a_mn, b_mn;   // operand majors
+  int m_tiles, n_tiles, splits;
 };
 
-__global__ void __launch_bounds__(256, 1)
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                            const TcParams tp, const EpiParams ep) {
+  constexpr int STAGES = gemm_stages(BN);
+  constexpr int STAGE_BYTES = gemm_stage_bytes(BN);
+  constexpr int B_PLANE_BYTES = BN * BK * 2;            // one K-major B plane
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* acc_full = empty_bar + STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM;
-  const int n0 = blockIdx.x * BN;
-  const int split = blockIdx.z;
   const int num_kb_total = (tp.K + BK - 1) / BK;
-  const int kb_begin = split * tp.kb_per_split;
-  const int kb_end = min(num_kb_total, kb_begin + tp.kb_per_split);
-  const int num_kb = max(0, kb_end - kb_begin);
+  const int tiles_mn = tp.m_tiles * tp.n_tiles;
+  const int total_tiles = tiles_mn * tp.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -146,7 +164,10 @@ gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], EPI_WARPS);   // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -161,25 +182,32 @@ gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
   if (warp == 0) {
     // ===== TMA producer =====
     if (elect_one()) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* st = smem + s * STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-        const int k0 = (kb_begin + i) * BK;
-        if (!tp.a_mn) {
-          tma_load_3d(st, &tmap_a, &full_bar[s], k0, m0, 0);                       // [2][128][64]
-        } else {
-          tma_load_3d(st, &tmap_a, &full_bar[s], m0, k0, 0);                       // [2][64 k][64 mn] chunk 0
-          tma_load_3d(st + PLANE_TILE_BYTES, &tmap_a, &full_bar[s], m0 + 64, k0, 0);  // chunk 1
-        }
-        uint8_t* sb = st + 2 * PLANE_TILE_BYTES;
-        if (!tp.b_mn) {
-          tma_load_3d(sb, &tmap_b, &full_bar[s], k0, n0, 0);
-        } else {
-          tma_load_3d(sb, &tmap_b, &full_bar[s], n0, k0, 0);
-          tma_load_3d(sb + PLANE_TILE_BYTES, &tmap_b, &full_bar[s], n0 + 64, k0, 0);
+      uint32_t it = 0;   // running k-block counter across tiles -> stage / phase
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int split = t / tiles_mn, rem = t % tiles_mn;
+        const int m0 = (rem / tp.n_tiles) * BM, n0 = (rem % tp.n_tiles) * BN;
+        const int kb_begin = split * tp.kb_per_split;
+        const int kb_end = min(num_kb_total, kb_begin + tp.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = smem + s * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (!tp.a_mn) {
+            tma_load_3d(st, &tmap_a, &full_bar[s], k0, m0, 0);                       // [2][128][64]
+          } else {
+            tma_load_3d(st, &tmap_a, &full_bar[s], m0, k0, 0);                       // [2][64 k][64 mn] chunk 0
+            tma_load_3d(st + PLANE_TILE_BYTES, &tmap_a, &full_bar[s], m0 + 64, k0, 0);  // chunk 1
+          }
+          uint8_t* sb = st + A_STAGE_BYTES;
+          if (!tp.b_mn) {
+            tma_load_3d(sb, &tmap_b, &full_bar[s], k0, n0, 0);                       // [2][BN][64]
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_3d(sb + c * PLANE_TILE_BYTES, &tmap_b, &full_bar[s], n0 + c * 64, k0, 0);
+          }
         }
       }
     }
@@ -189,56 +217,85 @@ gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
       const uint32_t idesc = umma_idesc_bf16(BN, tp.a_mn, tp.b_mn);
       // per-operand descriptor geometry
       const uint32_t a_lo_off = tp.a_mn ? (PLANE_TILE_BYTES / 2) : PLANE_TILE_BYTES;  // lo plane offset inside the operand
-      const uint32_t b_lo_off = tp.b_mn ? (PLANE_TILE_BYTES / 2) : PLANE_TILE_BYTES;
+      const uint32_t b_lo_off = tp.b_mn ? (PLANE_TILE_BYTES / 2) : B_PLANE_BYTES;
       const uint32_t a_lbo = tp.a_mn ? PLANE_TILE_BYTES : 16, b_lbo = tp.b_mn ? PLANE_TILE_BYTES : 16;
       const uint32_t a_kstep = tp.a_mn ? 2048 : 32, b_kstep = tp.b_mn ? 2048 : 32;
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, tile_iter = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
+        const int split = t / tiles_mn;
+        const int kb_begin = split * tp.kb_per_split;
+        const int kb_end = min(num_kb_total, kb_begin + tp.kb_per_split);
+        const uint32_t as = tile_iter & 1;
+        mbar_wait(&acc_empty[as], ((tile_iter >> 1) & 1) ^ 1);   // epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t b_base = a_base + 2 * PLANE_TILE_BYTES;
+        const uint32_t acc_addr = tmem_base + as * 256;
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b_base = a_base + A_STAGE_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          const uint64_t a_hi = umma_smem_desc(a_base + kk * a_kstep, a_lbo, 1024);
-          const uint64_t a_lo = umma_smem_desc(a_base + a_lo_off + kk * a_kstep, a_lbo, 1024);
-          const uint64_t b_hi = umma_smem_desc(b_base + kk * b_kstep, b_lbo, 1024);
-          const uint64_t b_lo = umma_smem_desc(b_base + b_lo_off + kk * b_kstep, b_lbo, 1024);
-          // the 2^-9-sized cross terms get their own accumulator: the tensor core's fp32 accumulate truncates, and
-          // adding them into the large hi*hi sum would lose them (and triple the number of biased roundings there)
-          const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
-          umma_bf16(tmem_base + BN, a_lo, b_hi, idesc, acc);
-          umma_bf16(tmem_base + BN, a_hi, b_lo, idesc, 1u);
-          umma_bf16(tmem_base, a_hi, b_hi, idesc, acc);
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t a_hi = umma_smem_desc(a_base + kk * a_kstep, a_lbo, 1024);
+            const uint64_t a_lo = umma_smem_desc(a_base + a_lo_off + kk * a_kstep, a_lbo, 1024);
+            const uint64_t b_hi = umma_smem_desc(b_base + kk * b_kstep, b_lbo, 1024);
+            const uint64_t b_lo = umma_smem_desc(b_base + b_lo_off + kk * b_kstep, b_lbo, 1024);
+            umma_bf16(acc_addr, a_lo, b_hi, idesc, (kb > kb_begin || kk > 0) ? 1u : 0u);  // small terms first
+            umma_bf16(acc_addr, a_hi, b_lo, idesc, 1u);
+            umma_bf16(acc_addr, a_hi, b_hi, idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+        umma_commit(&acc_full[as]);    // accumulator of this tile complete
       }
-      umma_commit(accum_bar);  // accumulator complete
     }
   } else if (warp >= 4) {
     // ===== epilogue =====
-    const int q = warp - 4;  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    if (num_kb > 0) {
-      mbar_wait(accum_bar, 0);
+    const int q = warp & 3;           // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
+    const int part = (warp - 4) >> 2;  // which of the EPI_WARPS/4 column interleaves
+    uint32_t tile_iter = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
+      const int split = t / tiles_mn, rem = t % tiles_mn;
+      const int m0 = (rem / tp.n_tiles) * BM, n0 = (rem % tp.n_tiles) * BN;
+      const int kb_begin = split * tp.kb_per_split;
+      const bool has_k = kb_begin < num_kb_total;
+      const uint32_t as = tile_iter & 1;
+      mbar_wait(&acc_full[as], (tile_iter >> 1) & 1);
       tc_fence_after();
-    }
+      // TMEM gives each lane one accumulator ROW; global memory wants lanes along the COLUMNS.  Every 32 x 32 chunk is
+      // transposed through a padded per-warp smem buffer so that 8 lanes cover one 128 B row segment (4 rows per access):
+      // all bias / residual / aux reads and all stores are fully coalesced.
+      float* st = epi_stage + (warp - 4) * (32 * EPI_STAGE_LD);
+      const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      float v[32];
-      if (num_kb > 0) {
-        uint32_t r[32], x[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c * 32), x);
-        tmem_ld_wait();
+      for (int c = part; c < BN / 32; c += EPI_WARPS / 4) {
+        if (n0 + c * 32 >= ep.N) break;
+        if (has_k) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + (uint32_t)(c * 32), r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(x[j]);
-      } else {
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(st + lane * EPI_STAGE_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(st + lane * EPI_STAGE_LD + j) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + sub_r;
+          const float4 x = *reinterpret_cast<const float4*>(st + rr * EPI_STAGE_LD + sub_c);
+          float v[4] = {x.x, x.y, x.z, x.w};
+          epilogue_store<4>(ep, m0 + q * 32 + rr, n0 + c * 32 + sub_c, v, split);
+        }
+        __syncwarp();
       }
-      if (n0 + c * 32 < ep.N) epilogue_store<32>(ep, row, n0 + c * 32, v, split);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
     }
   }
   tc_fence_before();
@@ -359,6 +416,24 @@ int make_plane_tmap(CUtensorMap* out, const void* base, int64_t inner, int64_t o
   return SRW_OK;
 }
 
+// Tile width: the candidate with the fewest (waves x tile cost) over the 148 SMs; ties go to the wider tile (less L2
+// traffic per FLOP).  192 divides the ViT widths exactly, 128 / 64 give more tiles for small problems.
+int gemm_pick_bn(int M, int N, int splits) {
+  const int cands[3] = {192, 128, 64};
+  int best = 128;
+  double best_cost = 1e30;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (bn == 192 && N % 192 != 0) continue;
+    if (bn == 128 && N <= 64) continue;
+    const int64_t tiles = (int64_t)cdiv(M, BM) * cdiv(N, bn) * std::max(1, splits);
+    const double waves = (double)((tiles + 147) / 148);
+    const double cost = waves * (bn + 40);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
 static int fill_epi(const srw_gemm_args* a, EpiParams& ep) {
   ep.M = a->M; ep.N = a->N; ep.epilogue = a->epilogue;
   ep.bias = a->bias;
@@ -414,26 +489,38 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
   }
   SRW_REQUIRE(a->impl == SRW_GEMM_TCGEN05, "srw_gemm: unknown impl %d", a->impl);
 
+  SRW_REQUIRE(kb_per_split * BK <= MAX_K_PER_CTA, "srw_gemm: K per CTA is %d > %d: use SRW_EPI_SPLITK with more splits (single fp32 accumulator)",
+              kb_per_split * BK, MAX_K_PER_CTA);
+  const int bn = srw::gemm_pick_bn(a->M, a->N, grid_z);
   CUtensorMap ta, tb;
   if (!a->a_mn_major) rc = make_plane_tmap(&ta, a->a, a->K, a->M, a->lda, a->a_plane_stride, 128, 2);
   else rc = make_plane_tmap(&ta, a->a, a->M, a->K, a->lda, a->a_plane_stride, 64, 2);
   if (rc) return rc;
-  if (!a->b_mn_major) rc = make_plane_tmap(&tb, a->b, a->K, a->N, a->ldb, a->b_plane_stride, 128, 2);
+  if (!a->b_mn_major) rc = make_plane_tmap(&tb, a->b, a->K, a->N, a->ldb, a->b_plane_stride, bn, 2);
   else rc = make_plane_tmap(&tb, a->b, a->N, a->K, a->ldb, a->b_plane_stride, 64, 2);
   if (rc) return rc;
 
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
+  static int num_sms = 148;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_bf16x3_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(gemm_bf16x3_tcgen05_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(192));
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(gemm_bf16x3_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128));
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(gemm_bf16x3_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(64));
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) num_sms = n;
   });
   SRW_CUDA(attr_err);
 
   TcParams tp;
   tp.K = a->K; tp.kb_per_split = kb_per_split; tp.a_mn = a->a_mn_major ? 1 : 0; tp.b_mn = a->b_mn_major ? 1 : 0;
-  dim3 grid(cdiv(a->N, BN), cdiv(a->M, BM), grid_z);
+  tp.m_tiles = cdiv(a->M, BM); tp.n_tiles = cdiv(a->N, bn); tp.splits = grid_z;
+  const int total_tiles = tp.m_tiles * tp.n_tiles * tp.splits;
+  const int grid = std::min(total_tiles, num_sms);
   void* prof = prof_begin(SRW_PROF_GEMM, 2.0 * a->M * a->N * a->K, 4.0 * ((double)a->M * a->K + (double)a->N * a->K + (double)a->M * a->N), stream);
-  gemm_bf16x3_tcgen05_kernel<<<grid, 256, GEMM_SMEM_BYTES, stream>>>(ta, tb, tp, ep);
+  if (bn == 192) gemm_bf16x3_tcgen05_kernel<192><<<grid, GEMM_THREADS, gemm_smem_bytes(192), stream>>>(ta, tb, tp, ep);
+  else if (bn == 128) gemm_bf16x3_tcgen05_kernel<128><<<grid, GEMM_THREADS, gemm_smem_bytes(128), stream>>>(ta, tb, tp, ep);
+  else gemm_bf16x3_tcgen05_kernel<64><<<grid, GEMM_THREADS, gemm_smem_bytes(64), stream>>>(ta, tb, tp, ep);
   prof_end(prof, stream);
   g_launches++;
   SRW_LAUNCH_CHECK();

@@ -129,15 +129,21 @@ __global__ void __launch_bounds__(SSL_THREADS) ssl_loss_kernel(const srw_ssl_los
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int C = a.num_classes;
   const int rows = a.B_lb + a.B_ulb;
-  // mask2 = reward >= mean(reward)   (srflexmatch.py:100-101); sequential sum = fixed order
-  if (threadIdx.x == 0) {
-    float mean = 0.f;
-    if (a.reward) {
-      float s = 0.f;
-      for (int b = 0; b < a.B_ulb; ++b) s += a.reward[b];
-      mean = s / (float)a.B_ulb;
+  // mask2 = reward >= mean(reward)   (srflexmatch.py:100-101).  The sum is a fixed-order pairwise tree: samples that share
+  // a pseudo-label have bit-identical rewards (the Rewarder sees features only through the batch context), and a batch
+  // of identical rewards must compare equal to its own mean, which a pairwise sum guarantees for power-of-two batches
+  // (a running sum r+r+r... rounds at 3r) and which is what torch's vectorised reduction does as well.
+  if (a.reward) {
+    float* tree = s_ce;   // scratch: the CE values are written later
+    for (int b = threadIdx.x; b < a.B_ulb; b += blockDim.x) tree[b] = a.reward[b];
+    __syncthreads();
+    for (int stride = 1; stride < a.B_ulb; stride <<= 1) {
+      for (int i = threadIdx.x * 2 * stride; i + stride < a.B_ulb; i += blockDim.x * 2 * stride) tree[i] += tree[i + stride];
+      __syncthreads();
     }
-    s_scalar[0] = mean;
+    if (threadIdx.x == 0) s_scalar[0] = tree[0] / (float)a.B_ulb;
+  } else if (threadIdx.x == 0) {
+    s_scalar[0] = 0.f;
   }
   __syncthreads();
   for (int b = threadIdx.x; b < a.B_ulb; b += blockDim.x) {

@@ -264,13 +264,21 @@ struct Layout {
 };
 
 static int64_t splitk_for(int M, int N, int64_t K, int* split_out) {
-  // enough K slices to put >= ~2 CTAs on each of the 148 SMs, but at least 4 k-blocks (256 rows) per slice
-  const int tiles = cdiv(M, 128) * cdiv(N, 128);
-  int split = std::max(1, 296 / tiles);
+  // K slices so that (tiles x slices) fills the 148 SMs about twice, with at least 4 k-blocks (256 rows) per slice and
+  // at most 2048 rows per slice (single fp32 accumulator per tile, see srw_gemm.cu)
   const int kb = (int)cdiv64(K, 64);
-  split = std::min(split, std::max(1, kb / 4));
-  if (split_out) *split_out = split;
-  return (int64_t)split * M * N;
+  int best = 1;
+  double best_cost = 1e30;
+  const int max_split = std::max(1, kb / 4), min_split = (int)cdiv64(K, 2048);
+  for (int split = min_split; split <= std::max(min_split, std::min(max_split, 64)); ++split) {
+    const int bn = gemm_pick_bn(M, N, split);
+    const int64_t tiles = (int64_t)cdiv(M, 128) * cdiv(N, bn) * split;
+    const double waves = (double)((tiles + 147) / 148);
+    const double cost = waves * (cdiv(kb, split) * (bn + 40) + 0.5 * bn) + 0.02 * split;   // mainloop + epilogue + reduce traffic
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = split; }
+  }
+  if (split_out) *split_out = best;
+  return (int64_t)best * M * N;
 }
 
 static Layout make_layout(const Dims& d) {
@@ -335,10 +343,11 @@ static int64_t weight_layout(const Dims& d, std::vector<WOff>& w, int64_t& pe) {
 }
 
 static int split_to(const float* x, int64_t ldx, int rows, int cols, void* planes, int64_t ldp, const float* row_scale, int rows_per_scale,
-                    cudaStream_t s) {
+                    cudaStream_t s, float* colsum_out = nullptr, int colsum_accumulate = 0, float* colsum_ws = nullptr) {
   srw_split_args a = {};
   a.x = x; a.ldx = ldx; a.rows = rows; a.cols = cols; a.row_scale = row_scale; a.rows_per_scale = rows_per_scale;
   a.planes = planes; a.ldp = ldp; a.plane_stride = (int64_t)rows * ldp;
+  a.colsum_out = colsum_out; a.colsum_accumulate = colsum_accumulate; a.colsum_workspace = colsum_ws;
   return srw_split_planes(&a, s);
 }
 
@@ -578,8 +587,7 @@ extern "C" int srw_vit_backward(const srw_vit_bwd_args* a, void* stream_) {
     const float* ds_attn = a->drop_scale ? a->drop_scale + ((int64_t)l * 2 + 0) * d.B : nullptr;
     const float* ds_mlp = a->drop_scale ? a->drop_scale + ((int64_t)l * 2 + 1) * d.B : nullptr;
     // MLP branch:  t_out = t_mid + s * (gelu(LN2(t_mid) W1^T + b1) W2^T + b2)
-    SRW_TRY(split_to(dt, D, Tg, D, ws + L.g, D, ds_mlp, d.N, s));
-    SRW_TRY(colsum_planes(ws + L.g, D, Tg, Tg, D, G[pblk(l, B_FC2B)], acc, cws, s));
+    SRW_TRY(split_to(dt, D, Tg, D, ws + L.g, D, ds_mlp, d.N, s, G[pblk(l, B_FC2B)], acc, cws));   // + fc2 bias gradient
     SRW_TRY(wgrad(D, Fh, Tg, ws + L.g, D, Tg, ws + b.h, Fh, T, sk, G[pblk(l, B_FC2W)], Fh, acc, impl, s));
     {
       Gemm g(Tg, Fh, D, impl);  // dz = (g W2) * gelu'(z)
@@ -601,8 +609,7 @@ extern "C" int srw_vit_backward(const srw_vit_bwd_args* a, void* stream_) {
     lb.dgamma = G[pblk(l, B_N2W)]; lb.dbeta = G[pblk(l, B_N2B)]; lb.accumulate_dparams = acc; lb.workspace = F32(L.ln_ws);
     SRW_TRY(srw_layernorm_bwd(&lb, s));
     // attention branch:  t_mid = t_in + s * (attn(LN1(t_in)) Wp^T + bp)
-    SRW_TRY(split_to(dt, D, Tg, D, ws + L.g, D, ds_attn, d.N, s));
-    SRW_TRY(colsum_planes(ws + L.g, D, Tg, Tg, D, G[pblk(l, B_PROJB)], acc, cws, s));
+    SRW_TRY(split_to(dt, D, Tg, D, ws + L.g, D, ds_attn, d.N, s, G[pblk(l, B_PROJB)], acc, cws));  // + proj bias gradient
     SRW_TRY(wgrad(D, D, Tg, ws + L.g, D, Tg, ws + b.o, D, T, sk, G[pblk(l, B_PROJW)], D, acc, impl, s));
     {
       Gemm g(Tg, D, D, impl);  // d_o = g Wp

@@ -32,7 +32,7 @@ def test_split_planes_roundtrip(ops):
 
 @pytest.mark.parametrize("impl", [1, 0])  # SIMT twin first, then tcgen05
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (6168, 1152, 384), (257, 100, 1536), (384, 384, 6168)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (6168, 1152, 384), (257, 100, 1536), (384, 384, 6168), (1000, 64, 200), (300, 1536, 384)])
 def test_gemm_f32(ops, impl, a_mn, b_mn, M, N, K):
     from semireward_b200 import _lib as L
     A = _rand(M, K, seed=2)
@@ -44,7 +44,15 @@ def test_gemm_f32(ops, impl, a_mn, b_mn, M, N, K):
     pa = ops.split_planes(A.t().contiguous()) if a_mn else ops.split_planes(A)
     pb = ops.split_planes(B.t().contiguous()) if b_mn else ops.split_planes(B)
     bias = _rand(N, seed=4)
-    out, _ = ops.gemm(pa, pb, M, N, K, a_mn=a_mn, b_mn=b_mn, epilogue=L.EPI_F32, bias=bias, impl=impl)
+    if K > 2048 and impl == 0:
+        # one fp32 TMEM accumulator per tile: long reductions go through split-K (as the engine's wgrad GEMMs do)
+        with pytest.raises(L.SrwError, match="K per CTA"):
+            ops.gemm(pa, pb, M, N, K, a_mn=a_mn, b_mn=b_mn, epilogue=L.EPI_F32, bias=bias, impl=impl)
+        ws = ops.gemm(pa, pb, M, N, K, a_mn=a_mn, b_mn=b_mn, epilogue=L.EPI_SPLITK, split_k=8, impl=impl)
+        out = bias.repeat(M, 1).contiguous()
+        ops.splitk_reduce(ws, out, accumulate=True)
+    else:
+        out, _ = ops.gemm(pa, pb, M, N, K, a_mn=a_mn, b_mn=b_mn, epilogue=L.EPI_F32, bias=bias, impl=impl)
     torch.cuda.synchronize()
     ref = (A.double() @ B.double().t() + bias.double())
     err = (out.double() - ref).abs().max().item()
