@@ -72,7 +72,7 @@ enum srw_epilogue {
   SRW_EPI_DGELU = 4,        /* out_planes = split(acc * gelu'(aux))  (backward of vit.py:71) */
   SRW_EPI_SPLITK = 5        /* workspace[split, M, N] = partial acc (reduced by srw_splitk_reduce) */
 };
-enum srw_gemm_impl { SRW_GEMM_TCGEN05 = 0, SRW_GEMM_SIMT = 1 };
+enum srw_gemm_impl { SRW_GEMM_TCGEN05 = 0 /* 2-CTA pairs where they fit, else 1-CTA */, SRW_GEMM_SIMT = 1, SRW_GEMM_TCGEN05_1CTA = 2 };
 
 typedef struct {
   int M, N, K;

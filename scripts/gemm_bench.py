@@ -29,11 +29,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--only", default=None)
+    ap.add_argument("--epi", type=int, default=None, help="override the epilogue (0 F32, 1 PLANES, 2 GELU, 3 RESID, 4 DGELU)")
+    ap.add_argument("--impl", type=int, default=0)
     a = ap.parse_args()
     torch.manual_seed(0)
     for name, (M, N, K, amn, bmn, epi, split) in SHAPES.items():
         if a.only and a.only != name:
             continue
+        if a.epi is not None and epi != L.EPI_SPLITK:
+            epi = a.epi
         nbuf = 4
         As = [O.split_planes(torch.randn((K, M) if amn else (M, K), device="cuda")) for _ in range(nbuf)]
         Bs = [O.split_planes(torch.randn((K, N) if bmn else (N, K), device="cuda") * 0.05) for _ in range(nbuf)]
@@ -46,7 +50,7 @@ def main():
 
         def run(i):
             O.gemm(As[i % nbuf], Bs[i % nbuf], M, N, K, a_mn=bool(amn), b_mn=bool(bmn), epilogue=epi, bias=None if epi in (L.EPI_SPLITK, L.EPI_DGELU) else bias,
-                   resid=resid, aux=aux, out_f32=outf, out_planes=outp, split_k=split, workspace=ws)
+                   resid=resid, aux=aux, out_f32=outf, out_planes=outp, split_k=split, workspace=ws, impl=a.impl)
         for i in range(3):
             run(i)
         torch.cuda.synchronize()

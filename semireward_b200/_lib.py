@@ -16,7 +16,7 @@ vp = C.c_void_p
 
 # enums (include/srw.h)
 EPI_F32, EPI_PLANES, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_SPLITK = range(6)
-GEMM_TCGEN05, GEMM_SIMT = 0, 1
+GEMM_TCGEN05, GEMM_SIMT, GEMM_TCGEN05_1CTA = 0, 1, 2
 
 
 class SplitArgs(C.Structure):

@@ -63,13 +63,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
-// split two floats -> packed hi pair, packed lo pair (element 0 in the low half)
+// split two floats -> packed hi pair, packed lo pair (element 0 in the low half).  Two packed conversions
+// (cvt.rn.bf16x2.f32), two bit ops and two subtractions: 3 instructions per element.
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 h0, l0, h1, l1;
-  split_bf16(x0, h0, l0);
-  split_bf16(x1, h1, l1);
-  hi = pack_bf16x2(h0, h1);
-  lo = pack_bf16x2(l0, l1);
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float r0 = x0 - __uint_as_float(hi << 16);
+  const float r1 = x1 - __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 __device__ __forceinline__ float bf16_lo_f(uint32_t packed) { return __uint_as_float(packed << 16); }
@@ -79,12 +81,29 @@ __device__ __forceinline__ float plane_value(const __nv_bfloat16* __restrict__ p
   return __bfloat162float(planes[idx]) + __bfloat162float(planes[idx + plane_stride]);
 }
 
-// exact-erf GELU and its derivative (nn.GELU default; reference vit.py:223)
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf-GELU (nn.GELU default; reference vit.py:223) and its derivative.  erf is evaluated branch-free with Abramowitz-Stegun
+// 7.1.26 (|error| < 5e-7 in fp32, about twice the fp32 rounding of gelu itself and far below the 1e-3 parity gate): the
+// fused GEMM epilogues are instruction-bound, and libdevice erff costs ~3x as many instructions.  exp(-x^2/2) is shared by
+// the erf tail and the Gaussian density of the derivative.
+__device__ __forceinline__ void gelu_parts(float x, float& erf_z, float& gauss) {
+  const float az = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, az, 1.0f));
+  gauss = __expf(-az * az);                               // exp(-x^2 / 2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  erf_z = copysignf(fmaf(-poly * t, gauss, 1.0f), x);     // erf(x / sqrt 2)
+}
+__device__ __forceinline__ float gelu_f(float x) {
+  float e, g;
+  gelu_parts(x, e, g);
+  return 0.5f * x * (1.0f + e);
+}
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float e, g;
+  gelu_parts(x, e, g);
+  return fmaf(x * 0.39894228040143267794f, g, 0.5f * (1.0f + e));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -236,6 +255,7 @@ int make_plane_tmap(::CUtensorMap_st* out, const void* base, int64_t inner, int6
                     int box_outer, int box_planes);
 
 int gemm_pick_bn(int M, int N, int splits);
+int gemm2_pick_bn(int M, int N, int splits, bool b_mn);
 
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |

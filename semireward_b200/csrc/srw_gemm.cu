@@ -125,6 +125,118 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 kernel
 // ------------------------------------------------------------------------------------------------
+// Epilogue of one tile for one warp.  TMEM gives each lane one accumulator ROW; global memory wants lanes along the
+// COLUMNS.  Every 32 x 32 chunk is transposed through a padded per-warp smem buffer so that 8 lanes cover one 128 B row
+// segment (4 rows per access): all bias / residual / aux reads and all stores are fully coalesced.
+//
+// Interior tiles take drain_full<>: the epilogue kind is a template parameter and there is no bounds logic, so the eight
+// row-group iterations of a chunk are straight-line code; the residual / aux operands of all eight are requested BEFORE
+// the TMEM load and the transpose, which hides their L2 latency (the epilogues are latency- and issue-bound, not
+// bandwidth-bound: 12 warps, 3 per scheduler).
+template <int BN, int EPI>
+__device__ __forceinline__ void drain_full(const EpiParams& ep, uint32_t acc_addr, float* st, int q, int part, int lane, int m0, int n0, int split) {
+  const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+  const int row_first = m0 + q * 32 + sub_r;       // this lane's rows: row_first + 4 i
+  float scale[8];
+  if (EPI == SRW_EPI_RESID) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) scale[i] = ep.row_scale ? ep.row_scale[(row_first + 4 * i) / ep.rows_per_scale] : 1.0f;
+  }
+#pragma unroll 1
+  for (int c = part; c < BN / 32; c += EPI_WARPS / 4) {
+    const int col = n0 + c * 32 + sub_c;
+    float4 pre[8];
+    if (EPI == SRW_EPI_RESID) {
+      const float* r = ep.resid + (int64_t)row_first * ep.ldr + col;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pre[i] = *reinterpret_cast<const float4*>(r + (int64_t)(4 * i) * ep.ldr);
+    } else if (EPI == SRW_EPI_DGELU) {
+      const float* z = ep.aux + (int64_t)row_first * ep.ldaux + col;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pre[i] = *reinterpret_cast<const float4*>(z + (int64_t)(4 * i) * ep.ldaux);
+    }
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (EPI != SRW_EPI_SPLITK && ep.bias != nullptr) b4 = *reinterpret_cast<const float4*>(ep.bias + col);
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(acc_addr + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(st + lane * EPI_STAGE_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row_first + 4 * i;
+      float4 x = *reinterpret_cast<const float4*>(st + (4 * i + sub_r) * EPI_STAGE_LD + sub_c);
+      x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+      if (EPI == SRW_EPI_SPLITK) {
+        *reinterpret_cast<float4*>(ep.workspace + ((int64_t)split * ep.M + row) * ep.N + col) = x;
+        continue;
+      }
+      if (EPI == SRW_EPI_RESID) {
+        const float sc = scale[i];
+        *reinterpret_cast<float4*>(ep.out_f32 + (int64_t)row * ep.ldo + col) =
+            make_float4(fmaf(sc, x.x, pre[i].x), fmaf(sc, x.y, pre[i].y), fmaf(sc, x.z, pre[i].z), fmaf(sc, x.w, pre[i].w));
+        continue;
+      }
+      if (EPI == SRW_EPI_F32 || EPI == SRW_EPI_GELU) {
+        *reinterpret_cast<float4*>(ep.out_f32 + (int64_t)row * ep.ldo + col) = x;
+        if (EPI == SRW_EPI_F32) continue;
+        x.x = gelu_f(x.x); x.y = gelu_f(x.y); x.z = gelu_f(x.z); x.w = gelu_f(x.w);
+      }
+      if (EPI == SRW_EPI_DGELU) {
+        x.x *= gelu_grad_f(pre[i].x); x.y *= gelu_grad_f(pre[i].y); x.z *= gelu_grad_f(pre[i].z); x.w *= gelu_grad_f(pre[i].w);
+      }
+      uint32_t h0, l0, h1, l1;
+      split2(x.x, x.y, h0, l0);
+      split2(x.z, x.w, h1, l1);
+      __nv_bfloat16* hp = ep.out_planes + (int64_t)row * ep.ldp + col;
+      *reinterpret_cast<uint2*>(hp) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(hp + ep.out_plane_stride) = make_uint2(l0, l1);
+    }
+    __syncwarp();
+  }
+}
+
+template <int BN>
+__device__ __forceinline__ void drain_accumulator(const EpiParams& ep, uint32_t acc_addr, float* st, int q, int part, int lane, int m0, int n0,
+                                                  int split, bool has_k) {
+  if (has_k && m0 + BM <= ep.M && n0 + BN <= ep.N) {
+    switch (ep.epilogue) {
+      case SRW_EPI_F32: drain_full<BN, SRW_EPI_F32>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
+      case SRW_EPI_PLANES: drain_full<BN, SRW_EPI_PLANES>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
+      case SRW_EPI_GELU: drain_full<BN, SRW_EPI_GELU>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
+      case SRW_EPI_RESID: drain_full<BN, SRW_EPI_RESID>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
+      case SRW_EPI_DGELU: drain_full<BN, SRW_EPI_DGELU>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
+      default: drain_full<BN, SRW_EPI_SPLITK>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
+    }
+  }
+  // edge tiles (partial in M or N) and empty K ranges: generic bounds-checked path
+  const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+#pragma unroll 1
+  for (int c = part; c < BN / 32; c += EPI_WARPS / 4) {
+    if (n0 + c * 32 >= ep.N) break;
+    if (has_k) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(acc_addr + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(st + lane * EPI_STAGE_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(st + lane * EPI_STAGE_LD + j) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+      const int rr = i * 4 + sub_r;
+      const float4 x = *reinterpret_cast<const float4*>(st + rr * EPI_STAGE_LD + sub_c);
+      float v[4] = {x.x, x.y, x.z, x.w};
+      epilogue_store<4>(ep, m0 + q * 32 + rr, n0 + c * 32 + sub_c, v, split);
+    }
+    __syncwarp();
+  }
+}
+
 struct TcParams {
   int K;            // reduction length
   int kb_per_split; // k blocks (of 64) handled by one split
@@ -264,35 +376,7 @@ gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
       const uint32_t as = tile_iter & 1;
       mbar_wait(&acc_full[as], (tile_iter >> 1) & 1);
       tc_fence_after();
-      // TMEM gives each lane one accumulator ROW; global memory wants lanes along the COLUMNS.  Every 32 x 32 chunk is
-      // transposed through a padded per-warp smem buffer so that 8 lanes cover one 128 B row segment (4 rows per access):
-      // all bias / residual / aux reads and all stores are fully coalesced.
-      float* st = epi_stage + (warp - 4) * (32 * EPI_STAGE_LD);
-      const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
-#pragma unroll 1
-      for (int c = part; c < BN / 32; c += EPI_WARPS / 4) {
-        if (n0 + c * 32 >= ep.N) break;
-        if (has_k) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + (uint32_t)(c * 32), r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<uint4*>(st + lane * EPI_STAGE_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(st + lane * EPI_STAGE_LD + j) = make_uint4(0u, 0u, 0u, 0u);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + sub_r;
-          const float4 x = *reinterpret_cast<const float4*>(st + rr * EPI_STAGE_LD + sub_c);
-          float v[4] = {x.x, x.y, x.z, x.w};
-          epilogue_store<4>(ep, m0 + q * 32 + rr, n0 + c * 32 + sub_c, v, split);
-        }
-        __syncwarp();
-      }
+      drain_accumulator<BN>(ep, tmem_base + as * 256, epi_stage + (warp - 4) * (32 * EPI_STAGE_LD), q, part, lane, m0, n0, split, has_k);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
@@ -303,6 +387,215 @@ gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2-CTA kernel: a CTA pair (cluster of 2 on one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows of N); the pair's MMA reads both halves, so
+// B crosses L2 -> SM once per pair instead of once per CTA, and a stage shrinks from 32+BN/4 KB... to 32 KB + BN*128 B,
+// which buys a third pipeline stage.  Roles per CTA as above; only the leader CTA (rank 0) issues MMAs, its commits
+// arrive (multicast) on both CTAs' barriers; both CTAs' TMA loads complete on the LEADER's full barrier.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int gemm2_stage_bytes(int bn) { return A_STAGE_BYTES + (bn / 2) * BK * 2 * 2; }
+__host__ __device__ constexpr int gemm2_stages(int bn) { return bn == 256 ? 2 : 3; }
+__host__ __device__ constexpr int gemm2_smem_bytes(int bn) { return gemm2_stages(bn) * gemm2_stage_bytes(bn) + 1024 + 256 + EPI_STAGE_BYTES; }
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are credited to the mbarrier at `bar_cluster_addr` (the leader CTA's barrier)
+__device__ __forceinline__ void tma_load_3d_2cta(void* smem_dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this smem offset in BOTH CTAs of the pair once all prior MMAs of this thread are complete
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_m256(int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcParams tp,
+                            const EpiParams ep) {
+  constexpr int STAGES = gemm2_stages(BN);
+  constexpr int STAGE_BYTES = gemm2_stage_bytes(BN);
+  constexpr int BH = BN / 2;                            // rows of B staged by each CTA
+  constexpr int B_PLANE_BYTES = BH * BK * 2;            // one K-major plane of the half tile
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_full = empty_bar + STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]  (waited on by the leader only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_kb_total = (tp.K + BK - 1) / BK;
+  const int tiles_mn = tp.m_tiles * tp.n_tiles;       // m_tiles counts 256-row pair tiles here
+  const int total_tiles = tiles_mn * tp.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 2 * EPI_WARPS);   // the epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int t = pair; t < total_tiles; t += num_pairs) {
+        const int split = t / tiles_mn, rem = t % tiles_mn;
+        const int m0 = (rem / tp.n_tiles) * 256 + (int)rank * BM, n0 = (rem % tp.n_tiles) * BN + (int)rank * BH;
+        const int kb_begin = split * tp.kb_per_split;
+        const int kb_end = min(num_kb_total, kb_begin + tp.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = smem + s * STAGE_BYTES;
+          const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[s]), 0);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);   // this CTA's bytes + the peer's
+          const int k0 = kb * BK;
+          if (!tp.a_mn) {
+            tma_load_3d_2cta(st, &tmap_a, leader_full, k0, m0, 0);
+          } else {
+            tma_load_3d_2cta(st, &tmap_a, leader_full, m0, k0, 0);
+            tma_load_3d_2cta(st + PLANE_TILE_BYTES, &tmap_a, leader_full, m0 + 64, k0, 0);
+          }
+          uint8_t* sb = st + A_STAGE_BYTES;
+          if (!tp.b_mn) {
+            tma_load_3d_2cta(sb, &tmap_b, leader_full, k0, n0, 0);                    // [2][BH][64]
+          } else {
+#pragma unroll
+            for (int c = 0; c < BH / 64; ++c) tma_load_3d_2cta(sb + c * PLANE_TILE_BYTES, &tmap_b, leader_full, n0 + c * 64, k0, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16_m256(BN, tp.a_mn, tp.b_mn);
+      const uint32_t a_lo_off = tp.a_mn ? (PLANE_TILE_BYTES / 2) : PLANE_TILE_BYTES;
+      const uint32_t b_lo_off = tp.b_mn ? (PLANE_TILE_BYTES / 2) : B_PLANE_BYTES;
+      const uint32_t a_lbo = tp.a_mn ? PLANE_TILE_BYTES : 16, b_lbo = tp.b_mn ? PLANE_TILE_BYTES : 16;
+      const uint32_t a_kstep = tp.a_mn ? 2048 : 32, b_kstep = tp.b_mn ? 2048 : 32;
+      uint32_t it = 0, tile_iter = 0;
+      for (int t = pair; t < total_tiles; t += num_pairs, ++tile_iter) {
+        const int split = t / tiles_mn;
+        const int kb_begin = split * tp.kb_per_split;
+        const int kb_end = min(num_kb_total, kb_begin + tp.kb_per_split);
+        const uint32_t as = tile_iter & 1;
+        mbar_wait(&acc_empty[as], ((tile_iter >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc_addr = tmem_base + as * 256;
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b_base = a_base + A_STAGE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t a_hi = umma_smem_desc(a_base + kk * a_kstep, a_lbo, 1024);
+            const uint64_t a_lo = umma_smem_desc(a_base + a_lo_off + kk * a_kstep, a_lbo, 1024);
+            const uint64_t b_hi = umma_smem_desc(b_base + kk * b_kstep, b_lbo, 1024);
+            const uint64_t b_lo = umma_smem_desc(b_base + b_lo_off + kk * b_kstep, b_lbo, 1024);
+            umma_bf16_2cta(acc_addr, a_lo, b_hi, idesc, (kb > kb_begin || kk > 0) ? 1u : 0u);
+            umma_bf16_2cta(acc_addr, a_hi, b_lo, idesc, 1u);
+            umma_bf16_2cta(acc_addr, a_hi, b_hi, idesc, 1u);
+          }
+          umma_commit_2cta(&empty_bar[s]);   // both CTAs' producers may refill this stage
+        }
+        umma_commit_2cta(&acc_full[as]);     // both CTAs' epilogues may drain this accumulator
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs, each drains its own 128 accumulator rows) =====
+    const int q = warp & 3;
+    const int part = (warp - 4) >> 2;
+    uint32_t tile_iter = 0;
+    for (int t = pair; t < total_tiles; t += num_pairs, ++tile_iter) {
+      const int split = t / tiles_mn, rem = t % tiles_mn;
+      const int m0 = (rem / tp.n_tiles) * 256 + (int)rank * BM, n0 = (rem % tp.n_tiles) * BN;
+      const int kb_begin = split * tp.kb_per_split;
+      const bool has_k = kb_begin < num_kb_total;
+      const uint32_t as = tile_iter & 1;
+      mbar_wait(&acc_full[as], (tile_iter >> 1) & 1);
+      tc_fence_after();
+      drain_accumulator<BN>(ep, tmem_base + as * 256, epi_stage + (warp - 4) * (32 * EPI_STAGE_LD), q, part, lane, m0, n0, split, has_k);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[as]), 0));
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, TMEM_COLS);
   }
 }
 
@@ -434,6 +727,30 @@ int gemm_pick_bn(int M, int N, int splits) {
   return best;
 }
 
+// Pair-tile width for the 2-CTA kernel (0 = use the 1-CTA kernel): 256 x BN tiles, BN/2 rows of B per CTA, which must be
+// a multiple of 64 for MN-major B.  Small problems (fewer pair tiles than half the SMs' worth) stay on the 1-CTA kernel.
+int gemm2_pick_bn(int M, int N, int splits, bool b_mn) {
+  const int cands[3] = {256, 192, 128};
+  int best = 0;
+  double best_cost = 1e30;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (bn == 192 && (b_mn || N % 192 != 0)) continue;
+    if (bn == 256 && N % 256 != 0 && N < 1024) continue;
+    if (N < bn) continue;
+    const int64_t tiles = (int64_t)cdiv(M, 256) * cdiv(N, bn) * std::max(1, splits);
+    const double waves = (double)((tiles + 73) / 74);
+    const double cost = waves * (bn + 40);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  // compare with the 1-CTA kernel's wave cost (per-SM work): prefer 2-CTA unless it quantises clearly worse
+  const int bn1 = gemm_pick_bn(M, N, splits);
+  const int64_t tiles1 = (int64_t)cdiv(M, BM) * cdiv(N, bn1) * std::max(1, splits);
+  const double cost1 = (double)((tiles1 + 147) / 148) * (bn1 + 40);
+  if (best == 0 || best_cost > 1.15 * cost1) return 0;
+  return best;
+}
+
 static int fill_epi(const srw_gemm_args* a, EpiParams& ep) {
   ep.M = a->M; ep.N = a->N; ep.epilogue = a->epilogue;
   ep.bias = a->bias;
@@ -487,10 +804,65 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
     SRW_LAUNCH_CHECK();
     return SRW_OK;
   }
-  SRW_REQUIRE(a->impl == SRW_GEMM_TCGEN05, "srw_gemm: unknown impl %d", a->impl);
-
+  SRW_REQUIRE(a->impl == SRW_GEMM_TCGEN05 || a->impl == SRW_GEMM_TCGEN05_1CTA, "srw_gemm: unknown impl %d", a->impl);
   SRW_REQUIRE(kb_per_split * BK <= MAX_K_PER_CTA, "srw_gemm: K per CTA is %d > %d: use SRW_EPI_SPLITK with more splits (single fp32 accumulator)",
               kb_per_split * BK, MAX_K_PER_CTA);
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  static int num_sms = 148;
+  std::call_once(attr_once, [] {
+    auto set = [&](const void* fn, int bytes) {
+      if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    };
+    set((const void*)gemm_bf16x3_tcgen05_kernel<192>, gemm_smem_bytes(192));
+    set((const void*)gemm_bf16x3_tcgen05_kernel<128>, gemm_smem_bytes(128));
+    set((const void*)gemm_bf16x3_tcgen05_kernel<64>, gemm_smem_bytes(64));
+    set((const void*)gemm2_bf16x3_tcgen05_kernel<256>, gemm2_smem_bytes(256));
+    set((const void*)gemm2_bf16x3_tcgen05_kernel<192>, gemm2_smem_bytes(192));
+    set((const void*)gemm2_bf16x3_tcgen05_kernel<128>, gemm2_smem_bytes(128));
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) num_sms = n;
+  });
+  SRW_CUDA(attr_err);
+
+  TcParams tp;
+  tp.K = a->K; tp.kb_per_split = kb_per_split; tp.a_mn = a->a_mn_major ? 1 : 0; tp.b_mn = a->b_mn_major ? 1 : 0;
+  tp.splits = grid_z;
+  const double flops = 2.0 * a->M * a->N * a->K, bytes = 4.0 * ((double)a->M * a->K + (double)a->N * a->K + (double)a->M * a->N);
+
+  // ---- 2-CTA path: pair tiles of 256 x BN ----
+  const int bn2 = srw::gemm2_pick_bn(a->M, a->N, grid_z, a->b_mn_major != 0);
+  if (a->impl == SRW_GEMM_TCGEN05 && bn2 > 0) {
+    CUtensorMap ta, tb;
+    if (!a->a_mn_major) rc = make_plane_tmap(&ta, a->a, a->K, a->M, a->lda, a->a_plane_stride, 128, 2);
+    else rc = make_plane_tmap(&ta, a->a, a->M, a->K, a->lda, a->a_plane_stride, 64, 2);
+    if (rc) return rc;
+    if (!a->b_mn_major) rc = make_plane_tmap(&tb, a->b, a->K, a->N, a->ldb, a->b_plane_stride, bn2 / 2, 2);
+    else rc = make_plane_tmap(&tb, a->b, a->N, a->K, a->ldb, a->b_plane_stride, 64, 2);
+    if (rc) return rc;
+    tp.m_tiles = cdiv(a->M, 256); tp.n_tiles = cdiv(a->N, bn2);
+    const int total_tiles = tp.m_tiles * tp.n_tiles * tp.splits;
+    const int pairs = std::min(total_tiles, num_sms / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GEMM_THREADS); cfg.stream = stream;
+    cfg.dynamicSmemBytes = gemm2_smem_bytes(bn2);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    void* prof = prof_begin(SRW_PROF_GEMM, flops, bytes, stream);
+    cudaError_t le;
+    if (bn2 == 256) le = cudaLaunchKernelEx(&cfg, gemm2_bf16x3_tcgen05_kernel<256>, ta, tb, tp, ep);
+    else if (bn2 == 192) le = cudaLaunchKernelEx(&cfg, gemm2_bf16x3_tcgen05_kernel<192>, ta, tb, tp, ep);
+    else le = cudaLaunchKernelEx(&cfg, gemm2_bf16x3_tcgen05_kernel<128>, ta, tb, tp, ep);
+    prof_end(prof, stream);
+    g_launches++;
+    SRW_CUDA(le);
+    SRW_LAUNCH_CHECK();
+    return SRW_OK;
+  }
+
+  // ---- 1-CTA path ----
   const int bn = srw::gemm_pick_bn(a->M, a->N, grid_z);
   CUtensorMap ta, tb;
   if (!a->a_mn_major) rc = make_plane_tmap(&ta, a->a, a->K, a->M, a->lda, a->a_plane_stride, 128, 2);
@@ -499,25 +871,10 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
   if (!a->b_mn_major) rc = make_plane_tmap(&tb, a->b, a->K, a->N, a->ldb, a->b_plane_stride, bn, 2);
   else rc = make_plane_tmap(&tb, a->b, a->N, a->K, a->ldb, a->b_plane_stride, 64, 2);
   if (rc) return rc;
-
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  static int num_sms = 148;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_bf16x3_tcgen05_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(192));
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(gemm_bf16x3_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128));
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(gemm_bf16x3_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(64));
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) num_sms = n;
-  });
-  SRW_CUDA(attr_err);
-
-  TcParams tp;
-  tp.K = a->K; tp.kb_per_split = kb_per_split; tp.a_mn = a->a_mn_major ? 1 : 0; tp.b_mn = a->b_mn_major ? 1 : 0;
-  tp.m_tiles = cdiv(a->M, BM); tp.n_tiles = cdiv(a->N, bn); tp.splits = grid_z;
+  tp.m_tiles = cdiv(a->M, BM); tp.n_tiles = cdiv(a->N, bn);
   const int total_tiles = tp.m_tiles * tp.n_tiles * tp.splits;
   const int grid = std::min(total_tiles, num_sms);
-  void* prof = prof_begin(SRW_PROF_GEMM, 2.0 * a->M * a->N * a->K, 4.0 * ((double)a->M * a->K + (double)a->N * a->K + (double)a->M * a->N), stream);
+  void* prof = prof_begin(SRW_PROF_GEMM, flops, bytes, stream);
   if (bn == 192) gemm_bf16x3_tcgen05_kernel<192><<<grid, GEMM_THREADS, gemm_smem_bytes(192), stream>>>(ta, tb, tp, ep);
   else if (bn == 128) gemm_bf16x3_tcgen05_kernel<128><<<grid, GEMM_THREADS, gemm_smem_bytes(128), stream>>>(ta, tb, tp, ep);
   else gemm_bf16x3_tcgen05_kernel<64><<<grid, GEMM_THREADS, gemm_smem_bytes(64), stream>>>(ta, tb, tp, ep);

@@ -30,7 +30,7 @@ def test_split_planes_roundtrip(ops):
     assert torch.equal(pt.to_f32(), p.to_f32().t())
 
 
-@pytest.mark.parametrize("impl", [1, 0])  # SIMT twin first, then tcgen05
+@pytest.mark.parametrize("impl", [1, 2, 0])  # SIMT twin, 1-CTA tcgen05, default (2-CTA pairs where they fit)
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (6168, 1152, 384), (257, 100, 1536), (384, 384, 6168), (1000, 64, 200), (300, 1536, 384)])
 def test_gemm_f32(ops, impl, a_mn, b_mn, M, N, K):
@@ -44,7 +44,7 @@ def test_gemm_f32(ops, impl, a_mn, b_mn, M, N, K):
     pa = ops.split_planes(A.t().contiguous()) if a_mn else ops.split_planes(A)
     pb = ops.split_planes(B.t().contiguous()) if b_mn else ops.split_planes(B)
     bias = _rand(N, seed=4)
-    if K > 2048 and impl == 0:
+    if K > 2048 and impl != 1:
         # one fp32 TMEM accumulator per tile: long reductions go through split-K (as the engine's wgrad GEMMs do)
         with pytest.raises(L.SrwError, match="K per CTA"):
             ops.gemm(pa, pb, M, N, K, a_mn=a_mn, b_mn=b_mn, epilogue=L.EPI_F32, bias=bias, impl=impl)
