@@ -198,6 +198,22 @@ typedef struct {
 } srw_vit_bwd_args;
 int srw_vit_backward(const srw_vit_bwd_args* a, void* stream);
 
+/* srw_vit_forward / srw_vit_backward capture their launches into a CUDA graph the second time they see an identical
+ * argument set (same pointers and sizes) and replay it afterwards: a training loop that keeps its buffers stable pays
+ * one graph launch instead of ~90 / ~340 kernel launches of host time per call.  on = 0 disables replay and drops the
+ * cached graphs (also: environment SRW_GRAPHS=0).  Replay is bypassed while srw_profile_enable(1) is active. */
+int srw_set_graph_mode(int on);
+
+/* The engine's kernels are launched with programmatic dependent launch (each kernel's launch latency and prologue overlap
+ * its predecessor's tail; griddepcontrol.wait orders the memory accesses).  on = 0 launches them plainly (also SRW_PDL=0).
+ * Changing the mode does not affect CUDA graphs that were already captured. */
+int srw_set_pdl_mode(int on);
+
+/* x[i] *= *scale for i < n, where scale is a DEVICE scalar; returns without touching memory when *scale == 1.  Used to
+ * apply autograd's upstream gradient of the loss (normally exactly 1, param_update.py:33) to gradients that were
+ * computed ahead of loss.backward(). */
+int srw_scale_inplace(float* x, int64_t n, const float* scale, void* stream);
+
 /* ---- fused SSL epilogue (the a6-a12 rows of SURVEY.md §8a) ---------------------------------------------------- */
 /* Rewarder.forward (semireward.py:52-72): reward[b] in (0,1), one CTA, softmax over the 2B rows done on chip.
  * rp = 17 device pointers in Rewarder.state_dict order. */
@@ -268,10 +284,59 @@ typedef struct {
   const float* reward;      /* [B_ulb] or NULL */
   float lambda_u;
   float* mask2;             /* [B_ulb] out (ones when reward == NULL; may be NULL) */
-  float* losses;            /* [4] out: sup, unsup, total, util_ratio */
+  float* losses;            /* [>= 4] out: sup, unsup, total, util_ratio ([4] = FreeMatch entropy term, written by srw_freematch_entropy) */
   float* dlogits_lb; float* dlogits_s; int64_t ld_dlogits;   /* d total / d logits (may be NULL) */
 } srw_ssl_loss_args;
 int srw_ssl_loss(const srw_ssl_loss_args* a, void* stream);
+
+/* FreeMatchThresholdingHook.masking + update (semilearn/algorithms/freematch/utils.py:23-66) fused with compute_prob
+ * (algorithmbase.py:332-333) and PseudoLabelingHook.gen_ulb_targets hard labels (hooks/pseudo_label.py:40).  One CTA.
+ * State (device): time_p [1], p_model [C], label_hist [C]; every EMA in the reference's fp32 evaluation order.
+ * pseudo_from_probs: 0 = argmax of the logits (train_step, srfreematch.py:146-150), 1 = argmax of the probabilities
+ * (data_generator, :93-97).  world_size 1 view: the reference all-gathers the probabilities over ranks first (C4). */
+typedef struct {
+  int B, num_classes;
+  const float* logits_w; int64_t ld_logits;
+  double momentum; int use_quantile; int clip_thresh;
+  float* time_p; float* p_model; float* label_hist;
+  float* probs_w;           /* [B, C] out: softmax(logits_w), row stride C */
+  int64_t* pseudo; int pseudo_from_probs;
+  float* mask;              /* [B] out */
+  float* max_probs;         /* [B] out (may be NULL) */
+} srw_freematch_mask_args;
+int srw_freematch_mask(const srw_freematch_mask_args* a, void* stream);
+
+/* entropy_loss of SRFreeMatch (srfreematch.py:12-44) over the rows with mask != 0, and `total += lambda_e * ent`
+ * (srfreematch.py:214-219): losses[4] = ent, losses[2] += lambda_e * ent; dlogits_s (+)= lambda_e * d ent / d logits_s.
+ * ent = 0 and no gradient when no row is selected. */
+typedef struct {
+  int B, num_classes;
+  const float* mask; const float* logits_s; int64_t ld_logits;
+  const float* p_model; const float* label_hist;
+  float lambda_e;
+  float* losses;            /* [5]: see srw_ssl_loss for [0..3] */
+  float* dlogits_s; int64_t ld_dlogits; int accumulate;   /* may be NULL; accumulate = 0 overwrites (zeros for unselected rows) */
+} srw_freematch_entropy_args;
+int srw_freematch_entropy(const srw_freematch_entropy_args* a, void* stream);
+
+/* SoftMatch: softmax, optional DistAlignEMAHook.dist_align (hooks/dist_align.py:25-55, uniform target), then
+ * SoftMatchWeightingHook.update + masking with per_class = False (srsoftmatch/utils.py:31-77): EMA of the mean and the
+ * unbiased variance of the (aligned) max probabilities, weight = exp(-clamp(max_p - mu, max=0)^2 / (2 var / n_sigma^2)).
+ * The reference's two .item() host syncs per call are gone; the EMA keeps its mixed fp32 / double arithmetic.  One CTA. */
+typedef struct {
+  int B, num_classes;
+  const float* logits_w; int64_t ld_logits;
+  double momentum; int n_sigma;
+  int dist_align;                      /* 1: train_step (srsoftmatch.py:134-141); 0: data_generator passes (:84-90) */
+  float* da_p_model; const float* da_p_target; int32_t* da_initialized;   /* DistAlign state ([C], [C], [1]); p_model is set on first use */
+  float* prob_max_mu_t; float* prob_max_var_t;                             /* [1], [1] state */
+  float* probs_w;                      /* [B, C] out: softmax(logits_w) (un-aligned) */
+  float* probs_aligned;                /* [B, C] out (may be NULL) */
+  int64_t* pseudo; int pseudo_from_probs;
+  float* mask;                         /* [B] out: the soft weights */
+  float* max_probs;                    /* [B] out (may be NULL): the max of the probabilities the weights were formed from */
+} srw_softmatch_mask_args;
+int srw_softmatch_mask(const srw_softmatch_mask_args* a, void* stream);
 
 /* ---- optimizer: torch.optim.AdamW / Adam over many tensors in one launch --------------------------------------------- */
 /* Replaces optimizer.step() of param_update.py:36 for the AdamW built by get_optimizer with the reference's layer-decay

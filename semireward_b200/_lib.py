@@ -113,6 +113,24 @@ class SslLossArgs(C.Structure):
 f64 = C.c_double
 
 
+class FreeMatchMaskArgs(C.Structure):
+    _fields_ = [("B", i32), ("num_classes", i32), ("logits_w", vp), ("ld_logits", i64), ("momentum", C.c_double), ("use_quantile", i32),
+                ("clip_thresh", i32), ("time_p", vp), ("p_model", vp), ("label_hist", vp), ("probs_w", vp), ("pseudo", vp),
+                ("pseudo_from_probs", i32), ("mask", vp), ("max_probs", vp)]
+
+
+class FreeMatchEntropyArgs(C.Structure):
+    _fields_ = [("B", i32), ("num_classes", i32), ("mask", vp), ("logits_s", vp), ("ld_logits", i64), ("p_model", vp),
+                ("label_hist", vp), ("lambda_e", f32), ("losses", vp), ("dlogits_s", vp), ("ld_dlogits", i64), ("accumulate", i32)]
+
+
+class SoftMatchMaskArgs(C.Structure):
+    _fields_ = [("B", i32), ("num_classes", i32), ("logits_w", vp), ("ld_logits", i64), ("momentum", C.c_double), ("n_sigma", i32),
+                ("dist_align", i32), ("da_p_model", vp), ("da_p_target", vp), ("da_initialized", vp), ("prob_max_mu_t", vp),
+                ("prob_max_var_t", vp), ("probs_w", vp), ("probs_aligned", vp), ("pseudo", vp), ("pseudo_from_probs", i32),
+                ("mask", vp), ("max_probs", vp)]
+
+
 class AdamWRow(C.Structure):
     _fields_ = [("param", vp), ("grad", vp), ("exp_avg", vp), ("exp_avg_sq", vp), ("planes", vp), ("numel", i64),
                 ("plane_stride", i64), ("cols", i32), ("ldp", i32), ("lr", f64), ("weight_decay", f64), ("first_block", i64)]
@@ -153,12 +171,18 @@ SYMBOLS = [
     ("srw_vit_prepare_weights", i32, [C.POINTER(VitConfig), C.POINTER(vp), vp, vp]),
     ("srw_vit_forward", i32, [C.POINTER(VitFwdArgs), vp]),
     ("srw_vit_backward", i32, [C.POINTER(VitBwdArgs), vp]),
+    ("srw_set_graph_mode", i32, [i32]),
+    ("srw_set_pdl_mode", i32, [i32]),
+    ("srw_scale_inplace", i32, [vp, i64, vp, vp]),
     ("srw_rewarder_workspace_floats", i64, [i32, i32]),
     ("srw_rewarder_fwd", i32, [C.POINTER(RewarderFwdArgs), vp]),
     ("srw_generator_fwd", i32, [C.POINTER(GeneratorFwdArgs), vp]),
     ("srw_rewarder_train", i32, [C.POINTER(RewarderTrainArgs), vp]),
     ("srw_flexmatch_mask", i32, [C.POINTER(FlexMatchMaskArgs), vp]),
     ("srw_ssl_loss", i32, [C.POINTER(SslLossArgs), vp]),
+    ("srw_freematch_mask", i32, [C.POINTER(FreeMatchMaskArgs), vp]),
+    ("srw_freematch_entropy", i32, [C.POINTER(FreeMatchEntropyArgs), vp]),
+    ("srw_softmatch_mask", i32, [C.POINTER(SoftMatchMaskArgs), vp]),
     ("srw_adamw_step", i32, [C.POINTER(AdamWArgs), vp]),
 ]
 

@@ -1,6 +1,6 @@
 """Algorithm lookup with the reference's surface (semilearn/algorithms/__init__.py:8-18)."""
 from ..core.registry import ALGORITHMS
-from . import srflexmatch  # noqa: F401  (registers 'srflexmatch')
+from . import srflexmatch, srfreematch, srsoftmatch  # noqa: F401  (register 'srflexmatch', 'srfreematch', 'srsoftmatch')
 
 name2alg = ALGORITHMS
 

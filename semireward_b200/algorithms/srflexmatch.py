@@ -55,11 +55,53 @@ class _SSLLoss(torch.autograd.Function):
         return ctx.dl_lb * g, ctx.dl_s * g, None, None, None, None, None, None
 
 
+def _ssl_loss_native(logits_lb, logits_s, y_lb, pseudo, mask, reward, lambda_u, dl_lb, dl_s):
+    """srw_ssl_loss -> (losses[4] = sup, unsup, total, util ; mask2).  d total / d logits goes into dl_lb / dl_s (row stride C)."""
+    B_lb, Cn = logits_lb.shape
+    B_u = logits_s.shape[0]
+    dev = logits_lb.device
+    losses = torch.empty(5, dtype=torch.float32, device=dev)   # [4]: extra term of the algorithm (FreeMatch entropy)
+    mask2 = torch.empty(B_u, dtype=torch.float32, device=dev)
+    assert logits_lb.stride(1) == 1 and logits_s.stride(1) == 1 and logits_lb.stride(0) == logits_s.stride(0)
+    a = L.SslLossArgs(B_lb=B_lb, B_ulb=B_u, num_classes=Cn, logits_lb=logits_lb.data_ptr(), logits_s=logits_s.data_ptr(),
+                      ld_logits=logits_lb.stride(0), y_lb=y_lb.data_ptr(), pseudo=pseudo.data_ptr(), mask=mask.data_ptr(),
+                      reward=L.ptr(reward), lambda_u=float(lambda_u), mask2=mask2.data_ptr(), losses=losses.data_ptr(),
+                      dlogits_lb=dl_lb.data_ptr(), dlogits_s=dl_s.data_ptr(), ld_dlogits=Cn)
+    L.check(L.load().srw_ssl_loss(C.byref(a), L.stream_ptr()), "srw_ssl_loss")
+    return losses, mask2
+
+
+class _PrecomputedGrads(torch.autograd.Function):
+    """The loss tensor handed to ParamUpdateHook when the backbone backward was already launched inside train_step
+    (eager backward).  loss.backward() applies the upstream gradient (exactly 1 for a plain `loss.backward()`;
+    srw_scale_inplace is a no-op then) and hands the finished gradients to the parameters: `p.grad = view of the flat
+    gradient buffer` (or `p.grad += view` when a gradient is already there).  The hand-over is done here instead of through
+    152 AccumulateGrad nodes, which would copy every gradient (85.7 MB per step) because the views are long-lived."""
+
+    @staticmethod
+    def forward(ctx, loss_value, net, anchor):
+        ctx.net = net
+        return loss_value.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        net = ctx.net
+        flat, views = net._flat_grads, net._grad_views
+        g = g.to(torch.float32).contiguous()
+        L.check(L.load().srw_scale_inplace(flat.data_ptr(), flat.numel(), g.data_ptr(), L.stream_ptr()), "srw_scale_inplace")
+        for p, v in zip(net._ordered_params(), views):
+            if p.grad is None:
+                p.grad = v
+            else:
+                p.grad.add_(v)
+        return None, None, None
+
+
 @ALGORITHMS.register("srflexmatch")
 class SRFlexMatch(AlgorithmBase):
     def __init__(self, args, net_builder, tb_log=None, logger=None):
         super().__init__(args, net_builder, tb_log, logger)
-        self.init(T=args.T, p_cutoff=args.p_cutoff, hard_label=args.hard_label, thresh_warmup=args.thresh_warmup)
+        self._init_algorithm(args)
         self.N_k = args.N_k
         if args.sr_ema != 0:
             raise NotImplementedError("sr_ema: every shipped SemiReward config sets sr_ema: False (EMARewarder is unused, SURVEY.md §8a a6)")
@@ -84,6 +126,14 @@ class SRFlexMatch(AlgorithmBase):
         # kernels next to 147 busy SMs).  The next step's first use of the Rewarder waits for it.
         self._sr_stream = None
         self._sr_done = None
+        # Eager backward: train_step launches the backbone backward itself as soon as d loss / d logits exists (it is a
+        # by-product of the loss kernel), BEFORE the host reads the loss values back for log_dict.  The device therefore
+        # never waits for the host between forward and backward; ParamUpdateHook's loss.backward() just collects the
+        # gradients.  Set to False to go through autograd (_VitFunction / _SSLLoss) instead.
+        self.eager_backward = True
+
+    def _init_algorithm(self, args):
+        self.init(T=args.T, p_cutoff=args.p_cutoff, hard_label=args.hard_label, thresh_warmup=args.thresh_warmup)
 
     def init(self, T, p_cutoff, hard_label=True, thresh_warmup=True):
         self.T, self.p_cutoff, self.use_hard_label, self.thresh_warmup = T, p_cutoff, hard_label, thresh_warmup
@@ -114,7 +164,9 @@ class SRFlexMatch(AlgorithmBase):
         m = self.model.module if hasattr(self.model, "module") else self.model
         return m.training and max(getattr(m, "drop_path_rates", [0.0])) > 0.0
 
-    def _mask_and_pseudo(self, logits_w, idx_ulb):
+    def _mask_and_pseudo(self, logits_w, idx_ulb, first_pass=True):
+        """(mask, hard pseudo-labels) of the weak logits and the MaskingHook state update, one launch.  first_pass: the
+        call in train_step itself (True) or one of data_generator's sampling passes (False) — the same thing for FlexMatch."""
         mask = self.call_hook("masking", "MaskingHook", logits_x_ulb=logits_w, idx_ulb=idx_ulb, softmax_x_ulb=True)
         pseudo = self.call_hook("gen_ulb_targets", "PseudoLabelingHook", logits=self._last_probs, use_hard_label=self.use_hard_label,
                                 T=self.T, softmax=False)
@@ -156,7 +208,106 @@ class SRFlexMatch(AlgorithmBase):
             torch.cuda.current_stream().wait_event(self._sr_done)
             self._sr_done = None
 
+    def _net(self):
+        return self.model.module if hasattr(self.model, "module") else self.model
+
+    def _host_scalars(self, n):
+        """Two alternating pinned staging buffers for the per-step D2H read of the loss vector."""
+        bufs = getattr(self, "_host_bufs", None)
+        if bufs is None or bufs[0].numel() != n:
+            bufs = self._host_bufs = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._host_flip = 0
+        self._host_flip ^= 1
+        return bufs[self._host_flip]
+
+    def _backbone_native(self, x_lb, x_ulb_w, x_ulb_s, need_grad=True):
+        """Autograd-free pass on the net's persistent buffers -> (logits, feats, handle), split as (lb, weak, strong)."""
+        if not self.use_cat:
+            raise NotImplementedError("use_cat: False (BERT/HuBERT configs) is a 'next' row (SURVEY.md §8f)")
+        net = self._net()
+        nl, nu = x_lb.shape[0], x_ulb_s.shape[0]
+        xb = net.input_buffer((nl + 2 * nu,) + tuple(x_lb.shape[1:]), x_lb.device)
+        torch.cat((x_lb, x_ulb_s, x_ulb_w), out=xb)
+        lg, ft, handle = net.forward_native(xb, grad_batch=(nl + nu) if need_grad else 0)
+        return (lg[:nl], lg[nl + nu:], lg[nl:nl + nu]), (ft[:nl], ft[nl + nu:], ft[nl:nl + nu]), handle
+
+    def _train_step_eager(self, x_lb, y_lb, idx_ulb, x_ulb_w, x_ulb_s):
+        """Same step as train_step's autograd route (srflexmatch.py:107-217), with the backward launched in here."""
+        self._sr_wait()
+        net = self._net()
+        dev = x_lb.device
+        nl, nu = x_lb.shape[0], x_ulb_s.shape[0]
+        (logits_lb, logits_w, logits_s), (feats_lb, feats_w, feats_s), h0 = self._backbone_native(x_lb, x_ulb_w, x_ulb_s)
+        feat_dict = {"x_lb": feats_lb, "x_ulb_w": feats_w, "x_ulb_s": feats_s}
+        y_lb = y_lb.to(torch.long)
+        mask, pseudo_label = self._mask_and_pseudo(logits_w, idx_ulb, first_pass=True)
+        dl = net.dlogits_buffer(nl + nu, dev)
+        dl_lb, dl_s = dl[:nl], dl[nl:]
+        h_last = None
+        if self.it > self.start_timing:
+            K = self.sr_decay()
+            stochastic = self._stochastic_backbone() or not self.replay_deterministic_passes
+            l_s = logits_s
+            for k in range(K):
+                if stochastic:   # the reference re-runs the backbone every pass; only the last pass's graph survives
+                    (_, l_w, l_s), (_, f_w, _), h = self._backbone_native(x_lb, x_ulb_w, x_ulb_s, need_grad=(k == K - 1))
+                    h_last = h if k == K - 1 else None
+                else:
+                    l_w, f_w = logits_w, feats_w
+                mask_dg, pseudo_dg = self._mask_and_pseudo(l_w, idx_ulb, first_pass=False)
+                if stochastic or k == K - 1:
+                    reward_dg = self.rewarder(f_w, pseudo_dg)
+            losses, mask2 = _ssl_loss_native(logits_lb, l_s, y_lb, pseudo_dg, mask_dg, reward_dg.view(-1), self.lambda_u, dl_lb, dl_s)
+        else:
+            losses, mask2 = _ssl_loss_native(logits_lb, logits_s, y_lb, pseudo_label, mask, None, self.lambda_u, dl_lb, dl_s)
+        # gradient buffers of the pass(es) that carry gradient; algorithm-specific extra terms (FreeMatch's entropy loss on
+        # pass 0's strong logits) are added to losses[2] and to the pass-0 gradient here
+        if h_last is None:
+            self._extra_loss(losses, mask, logits_s, dl_s)
+            dl0 = dl1 = None
+        else:   # two graphs carry gradient (srflexmatch.py:132 sup through pass 0, :102 unsup through the last pass)
+            dl0 = torch.zeros_like(dl)
+            dl0[:nl].copy_(dl_lb)
+            dl1 = dl.clone()
+            dl1[:nl].zero_()
+            self._extra_loss(losses, mask, logits_s, dl0[nl:])
+        # The loss values (and pass-0's mask for util_ratio) start their way to the host NOW, ahead of the backward in
+        # stream order, into pinned memory; the host waits for that copy only after everything else is queued.
+        host = self._host_scalars(5 + nu)
+        host[:5].copy_(losses, non_blocking=True)
+        host[5:].copy_(mask, non_blocking=True)
+        copied = torch.cuda.Event()
+        copied.record()
+        # SR online update first (side stream, forks from here), then the backbone backward on the main stream
+        if self.it > 0:
+            if self.it >= self.start_timing:
+                if self.it % self.N_k == 0 and self.it > self.start_timing:
+                    self.max_reward = -float("inf")
+                    self._sr_update_async(feats_w, pseudo_label)
+            else:
+                self._sr_update_async(feats_lb, y_lb)
+        if h_last is None:
+            net.backward_native(h0, dl)
+        else:
+            net.backward_native(h0, dl0)
+            net.backward_native(h_last, dl1, accumulate=True)
+        net.allreduce_grads_()
+        total_loss = _PrecomputedGrads.apply(losses[2], net, net.cls_token)   # one parameter anchors the node in the graph
+        copied.synchronize()                        # the device is busy with the backward while the host reads these
+        sup, unsup, total, util = host[:4].tolist()
+        if self.it > self.start_timing:
+            util = float(host[5:].mean())           # the reference logs pass-0's mask (srflexmatch.py:216)
+        out_dict = self.process_out_dict(loss=total_loss, feat=feat_dict)
+        log_dict = self.process_log_dict(sup_loss=sup, unsup_loss=unsup, total_loss=total, util_ratio=float(util))
+        self._last_mask, self._last_mask2, self._last_pseudo_label = mask, mask2, pseudo_label
+        return out_dict, log_dict
+
+    def _extra_loss(self, losses, mask, logits_s, dl_s):
+        """Hook for algorithm-specific loss terms on pass 0's strong logits: add to losses[2] and accumulate into dl_s."""
+
     def train_step(self, x_lb, y_lb, idx_ulb, x_ulb_w, x_ulb_s):
+        if self.eager_backward and torch.is_grad_enabled() and hasattr(self._net(), "forward_native"):
+            return self._train_step_eager(x_lb, y_lb, idx_ulb, x_ulb_w, x_ulb_s)
         self._sr_wait()   # last step's Rewarder update must be complete before the Rewarder is read or updated again
         (logits_lb, logits_w, logits_s), (feats_lb, feats_w, feats_s) = self._backbone(x_lb, x_ulb_w, x_ulb_s)
         feat_dict = {"x_lb": feats_lb, "x_ulb_w": feats_w, "x_ulb_s": feats_s}

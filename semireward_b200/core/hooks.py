@@ -113,3 +113,116 @@ class FlexMatchThresholdingHook(Hook):
         algorithm._last_pseudo = (probs, pseudo)
         algorithm._last_probs = probs
         return mask
+
+
+def _contig_logits(logits_x_ulb):
+    lw = logits_x_ulb.detach()
+    return lw if lw.stride(-1) == 1 else lw.contiguous()
+
+
+class FreeMatchThresholdingHook(Hook):
+    """Device-resident FreeMatch self-adaptive threshold state (semilearn/algorithms/freematch/utils.py:10-66): time_p,
+    p_model[C], label_hist[C].  masking() = softmax + update() + mask + hard pseudo-labels in ONE launch
+    (srw_freematch_mask); the attributes keep the reference's names, so get_save_dict / load_model work unchanged."""
+
+    def __init__(self, num_classes, momentum=0.999, device="cuda"):
+        self.num_classes, self.m = int(num_classes), float(momentum)
+        dev = torch.device(device)
+        self.p_model = torch.ones(self.num_classes, dtype=torch.float32, device=dev) / self.num_classes
+        self.label_hist = torch.ones(self.num_classes, dtype=torch.float32, device=dev) / self.num_classes
+        self.time_p = self.p_model.mean().reshape(1)
+
+    @torch.no_grad()
+    def masking(self, algorithm, logits_x_ulb, softmax_x_ulb=True, pseudo_from_probs=False, *args, **kwargs):
+        if not softmax_x_ulb:
+            raise RuntimeError("fused FreeMatch hook takes raw logits (softmax is fused into the kernel)")
+        if getattr(algorithm, "distributed", False) and getattr(algorithm, "world_size", 1) > 1:
+            raise NotImplementedError("srfreematch under data parallelism needs the all-gathered probabilities for update() "
+                                      "(C4 in SURVEY.md §2.1): not built yet")
+        lw = _contig_logits(logits_x_ulb)
+        dev = lw.device
+        for n in ("p_model", "label_hist", "time_p"):
+            t = getattr(self, n)
+            if t.device != dev or not t.is_contiguous() or t.dtype != torch.float32:
+                setattr(self, n, t.to(device=dev, dtype=torch.float32).contiguous())
+        self.time_p = self.time_p.reshape(1)
+        B, Cn = lw.shape
+        probs = torch.empty(B, Cn, dtype=torch.float32, device=dev)
+        pseudo = torch.empty(B, dtype=torch.long, device=dev)
+        mask = torch.empty(B, dtype=torch.float32, device=dev)
+        a = L.FreeMatchMaskArgs(B=B, num_classes=Cn, logits_w=lw.data_ptr(), ld_logits=lw.stride(0), momentum=self.m,
+                                use_quantile=int(bool(algorithm.use_quantile)), clip_thresh=int(bool(algorithm.clip_thresh)),
+                                time_p=self.time_p.data_ptr(), p_model=self.p_model.data_ptr(), label_hist=self.label_hist.data_ptr(),
+                                probs_w=probs.data_ptr(), pseudo=pseudo.data_ptr(), pseudo_from_probs=int(bool(pseudo_from_probs)),
+                                mask=mask.data_ptr(), max_probs=None)
+        L.check(L.load().srw_freematch_mask(C.byref(a), L.stream_ptr()), "srw_freematch_mask")
+        algorithm.p_model, algorithm.label_hist, algorithm.time_p = self.p_model, self.label_hist, self.time_p   # utils.py:41-43
+        algorithm._last_pseudo = (probs, pseudo)
+        algorithm._last_probs = probs
+        return mask
+
+
+class DistAlignEMAHook(Hook):
+    """State holder of DistAlignEMAHook with a uniform target (semilearn/algorithms/hooks/dist_align.py:10-72); the
+    alignment itself runs inside srw_softmatch_mask."""
+
+    def __init__(self, num_classes, momentum=0.999, p_target_type="uniform", p_target=None, device="cuda"):
+        if p_target_type != "uniform":
+            raise NotImplementedError("DistAlign p_target_type 'model'/'gt': every SemiReward SoftMatch config uses dist_uniform: True")
+        self.num_classes, self.m = int(num_classes), float(momentum)
+        dev = torch.device(device)
+        self.p_target = torch.ones(self.num_classes, dtype=torch.float32, device=dev) / self.num_classes
+        self._p_model = torch.zeros(self.num_classes, dtype=torch.float32, device=dev)
+        self._initialized = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    @property
+    def p_model(self):   # None until the first dist_align, like the reference (dist_align.py:22)
+        return self._p_model
+
+    @p_model.setter
+    def p_model(self, value):   # load_model restores it (srsoftmatch.py:236)
+        self._p_model = value.to(device=self._p_model.device, dtype=torch.float32).contiguous()
+        self._initialized.fill_(1)
+
+
+class SoftMatchWeightingHook(Hook):
+    """Device-resident SoftMatch truncated-Gaussian weighting state (semilearn/algorithms/srsoftmatch/utils.py:12-77):
+    prob_max_mu_t, prob_max_var_t.  masking() = softmax (+ DistAlign) + update() + weights + hard pseudo-labels in ONE
+    launch (srw_softmatch_mask), without the reference's two .item() syncs."""
+
+    def __init__(self, num_classes, n_sigma=2, momentum=0.999, per_class=False, device="cuda"):
+        if per_class:
+            raise NotImplementedError("SoftMatch per_class: True is not used by any SemiReward config")
+        self.num_classes, self.n_sigma, self.m = int(num_classes), int(n_sigma), float(momentum)
+        dev = torch.device(device)
+        self.prob_max_mu_t = torch.full((1,), 1.0 / self.num_classes, dtype=torch.float32, device=dev)
+        self.prob_max_var_t = torch.ones(1, dtype=torch.float32, device=dev)
+
+    @torch.no_grad()
+    def masking(self, algorithm, logits_x_ulb, softmax_x_ulb=True, dist_align=False, pseudo_from_probs=False, *args, **kwargs):
+        if not softmax_x_ulb:
+            raise RuntimeError("fused SoftMatch hook takes raw logits (softmax and DistAlign are fused into the kernel)")
+        if getattr(algorithm, "distributed", False) and getattr(algorithm, "world_size", 1) > 1:
+            raise NotImplementedError("srsoftmatch under data parallelism needs the all-gathered probabilities "
+                                      "(C4 in SURVEY.md §2.1): not built yet")
+        lw = _contig_logits(logits_x_ulb)
+        dev = lw.device
+        for n in ("prob_max_mu_t", "prob_max_var_t"):
+            t = getattr(self, n)
+            if t.device != dev or t.dim() != 1 or t.dtype != torch.float32:
+                setattr(self, n, t.to(device=dev, dtype=torch.float32).reshape(1).contiguous())
+        da = algorithm.hooks_dict["DistAlignHook"] if dist_align else None
+        B, Cn = lw.shape
+        probs = torch.empty(B, Cn, dtype=torch.float32, device=dev)
+        pseudo = torch.empty(B, dtype=torch.long, device=dev)
+        mask = torch.empty(B, dtype=torch.float32, device=dev)
+        a = L.SoftMatchMaskArgs(B=B, num_classes=Cn, logits_w=lw.data_ptr(), ld_logits=lw.stride(0), momentum=self.m, n_sigma=self.n_sigma,
+                                dist_align=int(da is not None), da_p_model=L.ptr(da._p_model) if da else None,
+                                da_p_target=L.ptr(da.p_target) if da else None, da_initialized=L.ptr(da._initialized) if da else None,
+                                prob_max_mu_t=self.prob_max_mu_t.data_ptr(), prob_max_var_t=self.prob_max_var_t.data_ptr(),
+                                probs_w=probs.data_ptr(), probs_aligned=None, pseudo=pseudo.data_ptr(),
+                                pseudo_from_probs=int(bool(pseudo_from_probs)), mask=mask.data_ptr(), max_probs=None)
+        L.check(L.load().srw_softmatch_mask(C.byref(a), L.stream_ptr()), "srw_softmatch_mask")
+        algorithm._last_pseudo = (probs, pseudo)
+        algorithm._last_probs = probs
+        return mask

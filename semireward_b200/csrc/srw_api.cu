@@ -1,5 +1,6 @@
 // srw_api — library-level C ABI: version, error string, device check, launch counter.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -48,7 +49,21 @@ void prof_end(void* h, cudaStream_t s) {
   delete r;
 }
 
+static int g_pdl_mode = -1;   // -1: read SRW_PDL on first use
+bool pdl_enabled() {
+  if (g_pdl_mode < 0) {
+    const char* e = getenv("SRW_PDL");
+    g_pdl_mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl_mode != 0;
+}
+
 }  // namespace srw
+
+extern "C" int srw_set_pdl_mode(int on) {
+  srw::g_pdl_mode = on ? 1 : 0;
+  return SRW_OK;
+}
 
 extern "C" int srw_profile_enable(int on) {
   srw::g_prof_on = on != 0;

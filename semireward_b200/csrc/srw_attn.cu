@@ -90,6 +90,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   float* xch = reinterpret_cast<float*>(smem + off_bar + 128);   // [4][128] partial row max / row sum exchange
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int D = p.H * HD;
@@ -113,6 +114,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t TM_S = tmem, TM_O = tmem + 384, TM_OX = tmem + 448;
+  pdl_wait();   // CTA-local setup above; q/k/v come from the previous kernel
 
   if (warp == 16) {
     if (lane == 0) {
@@ -292,6 +294,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
   float* vec_delta = vec_lse + 320;
   float* xch = vec_delta + 320;     // [4][128]
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int D = p.H * HD;
@@ -310,6 +313,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  pdl_wait();   // barrier init / TMEM allocation above are CTA-local; everything below reads the previous kernels' outputs
   if (MODE == MODE_DKV) {
     // per-column (query) statistics
     for (int i = threadIdx.x; i < p.NP; i += blockDim.x) {
@@ -539,7 +543,7 @@ extern "C" int srw_attn_fwd(const srw_attn_fwd_args* a, void* stream_) {
   dim3 grid(cdiv(a->N, 128), a->H, a->B);
   const double pair_flops = 2.0 * a->B * a->H * (double)a->N * a->N * HD;   // one N x N x 64 product per (image, head)
   void* prof = prof_begin(SRW_PROF_ATTN_FWD, 2.0 * pair_flops, 4.0 * 4.0 * a->B * a->N * a->H * HD, stream);
-  attn_fwd_kernel<<<grid, FWD_THREADS, smem_bytes, stream>>>(tq, tkv, p);
+  SRW_CUDA(launch_pdl(attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), smem_bytes, stream, tq, tkv, p));
   prof_end(prof, stream);
   g_launches++;
   SRW_LAUNCH_CHECK();
@@ -580,10 +584,10 @@ extern "C" int srw_attn_bwd(const srw_attn_bwd_args* a, void* stream_) {
   // algorithmic backward = 4 products (dP, dV, dQ, dK); the S recomputations are overhead, not counted
   const double pair_flops = 2.0 * a->B * a->H * (double)a->N * a->N * HD;
   void* prof = prof_begin(SRW_PROF_ATTN_BWD, 4.0 * pair_flops, 4.0 * 9.0 * a->B * a->N * a->H * HD, stream);
-  attn_bwd_kernel<MODE_DQ><<<grid, BWD_THREADS, BWD_SMEM, stream>>>(qkv_r, do_r, qkv_c, do_c, p);
+  SRW_CUDA(launch_pdl(attn_bwd_kernel<MODE_DQ>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p));
   g_launches++;
   SRW_LAUNCH_CHECK();
-  attn_bwd_kernel<MODE_DKV><<<grid, BWD_THREADS, BWD_SMEM, stream>>>(qkv_r, do_r, qkv_c, do_c, p);
+  SRW_CUDA(launch_pdl(attn_bwd_kernel<MODE_DKV>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p));
   prof_end(prof, stream);
   g_launches++;
   SRW_LAUNCH_CHECK();

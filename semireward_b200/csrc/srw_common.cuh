@@ -48,6 +48,20 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 void* prof_begin(int cls, double flops, double bytes, cudaStream_t s);
 void prof_end(void* handle, cudaStream_t s);
 
+// Host side of PDL: launch `kernel` allowing it to overlap the tail of its stream predecessor (srw_set_pdl_mode / SRW_PDL=0
+// turn the attribute off; the kernels' pdl_wait() is then a no-op).  Only for kernels that call pdl_wait().
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -171,6 +185,15 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, ui
       "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+
+// Programmatic dependent launch (PDL).  Kernels of the ViT engine are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: pdl_trigger() at the top lets the NEXT kernel of the stream be
+// scheduled as soon as every CTA of this one has started, so its launch latency and prologue (barrier init, TMEM
+// allocation, descriptor prefetch) hide under this kernel's tail; pdl_wait() blocks until the PREVIOUS kernel has
+// completed and its writes are visible, and must precede the first global-memory access.  Both are no-ops for launches
+// without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
                                                          const float* __restrict__ row_scale, int rows_per_scale,
                                                          __nv_bfloat16* __restrict__ planes, int64_t ldp, int64_t ps,
                                                          float* __restrict__ partial /* [gridDim.y, cols] or NULL */) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float4 red[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 128 + lane * 4;
@@ -90,6 +92,8 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
 // column partial sums of split planes: 8 bf16 (one uint4 per plane) per lane, 256 columns per block-column
 __global__ void __launch_bounds__(256) colsum_planes_kernel(const __nv_bfloat16* __restrict__ planes, int64_t ldp, int64_t ps, int rows, int cols,
                                                             float* __restrict__ partial /* [gridDim.y, cols] */) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][32][9];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 256 + lane * 8;
@@ -127,6 +131,8 @@ __global__ void __launch_bounds__(256) colsum_planes_kernel(const __nv_bfloat16*
 // ------------------------------------------------------------------------------------------------
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int split, int M, int N, float* __restrict__ out, int64_t ldo,
                                      int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t total4 = (int64_t)M * N / 4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e = i * 4;
@@ -175,6 +181,8 @@ __global__ void colsum_stage1_kernel(const float* __restrict__ x, int64_t ldx, c
 // shared-memory fold in fixed order (deterministic).  Used by colsum (y = 0) and LayerNorm dgamma / dbeta (y = 0, 1).
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int nparts, int64_t stride_p, int64_t stride_y,
                                                               int cols, float* __restrict__ out0, float* __restrict__ out1, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -258,6 +266,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_reg_kernel(const float* __r
                                                                 float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                                 __nv_bfloat16* __restrict__ yp, int64_t ldp, int64_t ps, float* __restrict__ yf,
                                                                 int64_t ldy) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int COLS = J * 128;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -315,6 +325,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             float* __restrict__ dx, int64_t lddx, int accumulate_dx,
                                                             float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int COLS = J * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float pg[J], pb[J], gm[J];
@@ -374,6 +386,19 @@ __global__ void layernorm_bwd_params_kernel(const float* __restrict__ partial, i
   dbeta[c] = accumulate ? dbeta[c] + sb : sb;
 }
 
+
+// x[i] *= *scale unless *scale == 1 (then no memory is touched)
+__global__ void scale_inplace_kernel(float* __restrict__ x, int64_t n, const float* __restrict__ scale) {
+  const float sc = *scale;
+  if (sc == 1.0f) return;
+  const int64_t n4 = n / 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(x)[i];
+    v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+    reinterpret_cast<float4*>(x)[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n - n4 * 4)) x[n4 * 4 + threadIdx.x] *= sc;
+}
 }  // namespace srw
 
 using namespace srw;
@@ -386,15 +411,15 @@ extern "C" int srw_split_planes(const srw_split_args* a, void* stream_) {
   if (fast) {
     const int nparts = a->colsum_out ? std::min(64, cdiv(a->rows, 32)) : std::min(std::max(1, 592 / cdiv(a->cols, 128)), cdiv(a->rows, 8));
     SRW_REQUIRE(!a->colsum_out || a->colsum_workspace, "srw_split_planes: colsum_out needs colsum_workspace (>= 64 * cols floats)");
-    split_rows_kernel<<<dim3(cdiv(a->cols, 128), nparts), 256, 0, stream>>>(a->x, a->ldx, a->rows, a->cols, a->row_scale,
+    SRW_CUDA(launch_pdl(split_rows_kernel, dim3(dim3(cdiv(a->cols, 128), nparts)), dim3(256), 0, stream, a->x, a->ldx, a->rows, a->cols, a->row_scale,
                                                                           a->rows_per_scale > 0 ? a->rows_per_scale : 1,
                                                                           reinterpret_cast<__nv_bfloat16*>(a->planes), a->ldp, a->plane_stride,
-                                                                          a->colsum_out ? a->colsum_workspace : nullptr);
+                                                                          a->colsum_out ? a->colsum_workspace : nullptr));
     g_launches++;
     SRW_LAUNCH_CHECK();
     if (a->colsum_out) {
-      reduce_partials_kernel<<<dim3(cdiv(a->cols, 32), 1), 256, 0, stream>>>(a->colsum_workspace, nparts, a->cols, 0, a->cols, a->colsum_out, nullptr,
-                                                                               a->colsum_accumulate);
+      SRW_CUDA(launch_pdl(reduce_partials_kernel, dim3(dim3(cdiv(a->cols, 32), 1)), dim3(256), 0, stream, a->colsum_workspace, nparts, a->cols, 0, a->cols, a->colsum_out, nullptr,
+                                                                               a->colsum_accumulate));
       g_launches++;
       SRW_LAUNCH_CHECK();
     }
@@ -415,7 +440,7 @@ extern "C" int srw_splitk_reduce(const srw_splitk_reduce_args* a, void* stream_)
   SRW_REQUIRE(a && a->workspace && a->out && a->split_k >= 1 && a->N % 4 == 0 && a->ldo % 4 == 0, "srw_splitk_reduce: bad args");
   const int64_t total4 = (int64_t)a->M * a->N / 4;
   const int blocks = (int)std::min<int64_t>(cdiv64(total4, 256), 148 * 8);
-  splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(a->workspace, a->split_k, a->M, a->N, a->out, a->ldo, a->accumulate);
+  SRW_CUDA(launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, stream, a->workspace, a->split_k, a->M, a->N, a->out, a->ldo, a->accumulate));
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;
@@ -426,11 +451,11 @@ extern "C" int srw_colsum(const srw_colsum_args* a, void* stream_) {
   SRW_REQUIRE(a && (a->x || a->planes) && a->out && a->workspace && a->rows > 0 && a->cols > 0, "srw_colsum: bad args");
   const int nparts = std::min(64, cdiv(a->rows, 32));
   if (a->planes && !a->row_scale && a->cols % 8 == 0 && a->ldp % 8 == 0 && a->plane_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(a->planes) & 15) == 0) {
-    colsum_planes_kernel<<<dim3(cdiv(a->cols, 256), nparts), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->planes), a->ldp, a->plane_stride,
-                                                                              a->rows, a->cols, a->workspace);
+    SRW_CUDA(launch_pdl(colsum_planes_kernel, dim3(dim3(cdiv(a->cols, 256), nparts)), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(a->planes), a->ldp, a->plane_stride,
+                                                                              a->rows, a->cols, a->workspace));
     g_launches++;
     SRW_LAUNCH_CHECK();
-    reduce_partials_kernel<<<dim3(cdiv(a->cols, 32), 1), 256, 0, stream>>>(a->workspace, nparts, a->cols, 0, a->cols, a->out, nullptr, a->accumulate);
+    SRW_CUDA(launch_pdl(reduce_partials_kernel, dim3(dim3(cdiv(a->cols, 32), 1)), dim3(256), 0, stream, a->workspace, nparts, a->cols, 0, a->cols, a->out, nullptr, a->accumulate));
     g_launches++;
     SRW_LAUNCH_CHECK();
     return SRW_OK;
@@ -440,7 +465,7 @@ extern "C" int srw_colsum(const srw_colsum_args* a, void* stream_) {
                                                 a->row_scale, a->rows_per_scale > 0 ? a->rows_per_scale : 1, a->rows, a->cols, a->workspace);
   g_launches++;
   SRW_LAUNCH_CHECK();
-  reduce_partials_kernel<<<dim3(cdiv(a->cols, 32), 1), 256, 0, stream>>>(a->workspace, nparts, a->cols, 0, a->cols, a->out, nullptr, a->accumulate);
+  SRW_CUDA(launch_pdl(reduce_partials_kernel, dim3(dim3(cdiv(a->cols, 32), 1)), dim3(256), 0, stream, a->workspace, nparts, a->cols, 0, a->cols, a->out, nullptr, a->accumulate));
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;
@@ -453,9 +478,9 @@ extern "C" int srw_layernorm_fwd(const srw_layernorm_fwd_args* a, void* stream_)
   SRW_REQUIRE(!a->y_planes || a->ldp % 4 == 0, "srw_layernorm_fwd: ldp %% 4");
   SRW_REQUIRE(!a->y_f32 || a->ldy % 4 == 0, "srw_layernorm_fwd: ldy %% 4");
 #define SRW_LN_FWD(J)                                                                                                                   \
-  layernorm_fwd_reg_kernel<J><<<cdiv(a->rows, 8), 256, 0, stream>>>(a->x, a->ldx, a->rows, a->eps, a->gamma, a->beta, a->mean, a->rstd,       \
+  SRW_CUDA(launch_pdl(layernorm_fwd_reg_kernel<J>, dim3(cdiv(a->rows, 8)), dim3(256), 0, stream, a->x, a->ldx, a->rows, a->eps, a->gamma, a->beta, a->mean, a->rstd,       \
                                                                    reinterpret_cast<__nv_bfloat16*>(a->y_planes), a->ldp, a->plane_stride, \
-                                                                   a->y_f32, a->ldy)
+                                                                   a->y_f32, a->ldy))
   if (a->cols == 384) SRW_LN_FWD(3);
   else if (a->cols == 768) SRW_LN_FWD(6);
   else if (a->cols == 1024) SRW_LN_FWD(8);
@@ -476,8 +501,8 @@ extern "C" int srw_layernorm_bwd(const srw_layernorm_bwd_args* a, void* stream_)
   const int nblocks = std::min(256, cdiv(a->rows, 8));
 #define SRW_LN_BWD(J)                                                                                                             \
   case J:                                                                                                                         \
-    layernorm_bwd_kernel<J><<<nblocks, 256, 0, stream>>>(a->dy, a->lddy, a->x, a->ldx, a->rows, a->gamma, a->mean, a->rstd, a->dx, \
-                                                         a->lddx, a->accumulate_dx, a->workspace);                                \
+    SRW_CUDA(launch_pdl(layernorm_bwd_kernel<J>, dim3(nblocks), dim3(256), 0, stream, a->dy, a->lddy, a->x, a->ldx, a->rows, a->gamma, a->mean, a->rstd, a->dx, \
+                                                         a->lddx, a->accumulate_dx, a->workspace));                                \
     break;
   switch (a->cols / 32) {
     SRW_LN_BWD(2) SRW_LN_BWD(4) SRW_LN_BWD(6) SRW_LN_BWD(8) SRW_LN_BWD(12) SRW_LN_BWD(16) SRW_LN_BWD(24) SRW_LN_BWD(32)
@@ -489,10 +514,19 @@ extern "C" int srw_layernorm_bwd(const srw_layernorm_bwd_args* a, void* stream_)
   g_launches++;
   SRW_LAUNCH_CHECK();
   if (a->dgamma && a->dbeta) {
-    reduce_partials_kernel<<<dim3(cdiv(a->cols, 32), 2), 256, 0, stream>>>(a->workspace, nblocks, 2 * (int64_t)a->cols, a->cols, a->cols, a->dgamma,
-                                                                             a->dbeta, a->accumulate_dparams);
+    SRW_CUDA(launch_pdl(reduce_partials_kernel, dim3(dim3(cdiv(a->cols, 32), 2)), dim3(256), 0, stream, a->workspace, nblocks, 2 * (int64_t)a->cols, a->cols, a->cols, a->dgamma,
+                                                                             a->dbeta, a->accumulate_dparams));
     g_launches++;
     SRW_LAUNCH_CHECK();
   }
+  return SRW_OK;
+}
+
+extern "C" int srw_scale_inplace(float* x, int64_t n, const float* scale, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SRW_REQUIRE(x && scale && n > 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "srw_scale_inplace: bad args (x must be 16-byte aligned)");
+  scale_inplace_kernel<<<148 * 8, 256, 0, stream>>>(x, n, scale);
+  g_launches++;
+  SRW_LAUNCH_CHECK();
   return SRW_OK;
 }

@@ -261,6 +261,7 @@ gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb_total = (tp.K + BK - 1) / BK;
@@ -290,6 +291,7 @@ gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above is CTA-local; operands / epilogue inputs come from the previous kernel
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -468,6 +470,7 @@ gemm2_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -499,6 +502,7 @@ gemm2_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs) =====
@@ -846,10 +850,12 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GEMM_THREADS); cfg.stream = stream;
     cfg.dynamicSmemBytes = gemm2_smem_bytes(bn2);
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 2;
     void* prof = prof_begin(SRW_PROF_GEMM, flops, bytes, stream);
     cudaError_t le;
     if (bn2 == 256) le = cudaLaunchKernelEx(&cfg, gemm2_bf16x3_tcgen05_kernel<256>, ta, tb, tp, ep);
@@ -875,11 +881,13 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
   const int total_tiles = tp.m_tiles * tp.n_tiles * tp.splits;
   const int grid = std::min(total_tiles, num_sms);
   void* prof = prof_begin(SRW_PROF_GEMM, flops, bytes, stream);
-  if (bn == 192) gemm_bf16x3_tcgen05_kernel<192><<<grid, GEMM_THREADS, gemm_smem_bytes(192), stream>>>(ta, tb, tp, ep);
-  else if (bn == 128) gemm_bf16x3_tcgen05_kernel<128><<<grid, GEMM_THREADS, gemm_smem_bytes(128), stream>>>(ta, tb, tp, ep);
-  else gemm_bf16x3_tcgen05_kernel<64><<<grid, GEMM_THREADS, gemm_smem_bytes(64), stream>>>(ta, tb, tp, ep);
+  cudaError_t le;
+  if (bn == 192) le = launch_pdl(gemm_bf16x3_tcgen05_kernel<192>, dim3(grid), dim3(GEMM_THREADS), gemm_smem_bytes(192), stream, ta, tb, tp, ep);
+  else if (bn == 128) le = launch_pdl(gemm_bf16x3_tcgen05_kernel<128>, dim3(grid), dim3(GEMM_THREADS), gemm_smem_bytes(128), stream, ta, tb, tp, ep);
+  else le = launch_pdl(gemm_bf16x3_tcgen05_kernel<64>, dim3(grid), dim3(GEMM_THREADS), gemm_smem_bytes(64), stream, ta, tb, tp, ep);
   prof_end(prof, stream);
   g_launches++;
+  SRW_CUDA(le);
   SRW_LAUNCH_CHECK();
   return SRW_OK;
 }

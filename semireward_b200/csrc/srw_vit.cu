@@ -15,7 +15,10 @@
 // detached consumers: srflexmatch.py:135,165).
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "../../include/srw.h"
@@ -456,8 +459,7 @@ extern "C" int srw_vit_prepare_weights(const srw_vit_config* c, const float* con
   return SRW_OK;
 }
 
-extern "C" int srw_vit_forward(const srw_vit_fwd_args* a, void* stream_) {
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+static int vit_forward_body(const srw_vit_fwd_args* a, cudaStream_t s) {
   SRW_REQUIRE(a && a->cfg && a->params && a->weight_planes && a->x && a->logits && a->feat && a->workspace, "srw_vit_forward: null pointer");
   Dims d;
   SRW_TRY(make_dims(a->cfg, a->batch, a->grad_batch, d));
@@ -547,8 +549,7 @@ extern "C" int srw_vit_forward(const srw_vit_fwd_args* a, void* stream_) {
   return SRW_OK;
 }
 
-extern "C" int srw_vit_backward(const srw_vit_bwd_args* a, void* stream_) {
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+static int vit_backward_body(const srw_vit_bwd_args* a, cudaStream_t s) {
   SRW_REQUIRE(a && a->cfg && a->params && a->weight_planes && a->dlogits && a->grads && a->workspace, "srw_vit_backward: null pointer");
   Dims d;
   SRW_TRY(make_dims(a->cfg, a->batch, a->grad_batch, d));
@@ -659,4 +660,140 @@ extern "C" int srw_vit_backward(const srw_vit_bwd_args* a, void* stream_) {
     SRW_LAUNCH_CHECK();
   }
   return SRW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-graph replay.  A training loop calls srw_vit_forward / srw_vit_backward with the SAME arguments every step
+// (same workspace, parameter, gradient and I/O pointers): the ~90 / ~340 launches of a call are then captured once into
+// a CUDA graph and replayed, which removes the per-launch host cost (tensor-map encoding included) from the step.
+// Policy: the first call with a given argument set runs eagerly, the second one is captured, later ones replay.  Any
+// change of any pointer or size is simply a different key.  Disabled while per-kernel profiling is on, when the caller's
+// stream is already being captured, and by srw_set_graph_mode(0) / SRW_GRAPHS=0.
+// ------------------------------------------------------------------------------------------------
+namespace srw {
+extern bool g_prof_on;
+static int g_graph_mode = -1;   // -1: read SRW_GRAPHS on first use
+
+struct GraphEntry {
+  std::vector<uint8_t> key;
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0;
+  uint64_t last_use = 0;
+  int seen = 0;
+};
+static std::vector<GraphEntry> g_graphs;
+static uint64_t g_graph_tick = 0;
+static std::mutex g_graph_mu;
+constexpr size_t MAX_GRAPHS = 24;
+
+struct KeyBuilder {
+  std::vector<uint8_t> k;
+  template <typename T> void add(const T& v) {
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(&v);
+    k.insert(k.end(), b, b + sizeof(T));
+  }
+};
+
+static bool graphs_enabled(cudaStream_t s) {
+  if (g_graph_mode < 0) {
+    const char* e = getenv("SRW_GRAPHS");
+    g_graph_mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!g_graph_mode || g_prof_on) return false;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return false;
+  return true;
+}
+
+template <typename Body>
+static int run_graphed(std::vector<uint8_t>&& key, cudaStream_t s, Body body) {
+  std::lock_guard<std::mutex> lk(g_graph_mu);
+  GraphEntry* e = nullptr;
+  for (auto& g : g_graphs)
+    if (g.key == key) { e = &g; break; }
+  if (!e) {
+    if (g_graphs.size() >= MAX_GRAPHS) {   // evict the least recently used entry
+      size_t victim = 0;
+      for (size_t i = 1; i < g_graphs.size(); ++i)
+        if (g_graphs[i].last_use < g_graphs[victim].last_use) victim = i;
+      if (g_graphs[victim].exec) cudaGraphExecDestroy(g_graphs[victim].exec);
+      g_graphs.erase(g_graphs.begin() + victim);
+    }
+    g_graphs.emplace_back();
+    e = &g_graphs.back();
+    e->key = std::move(key);
+  }
+  e->last_use = ++g_graph_tick;
+  if (e->exec) {
+    SRW_CUDA(cudaGraphLaunch(e->exec, s));
+    g_launches += e->launches;
+    return SRW_OK;
+  }
+  if (e->seen++ == 0) return body(s);      // first sighting: eager (also warms the one-time attribute setup)
+  // capture on a private stream: PyTorch's default stream is the legacy stream, which cannot be captured; the graph is
+  // stream-agnostic and is launched on the caller's stream
+  static cudaStream_t cap = nullptr;
+  if (!cap) SRW_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+  const int64_t before = g_launches.load();
+  SRW_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+  const int rc = body(cap);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+  if (rc != SRW_OK || ce != cudaSuccess || graph == nullptr) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    e->seen = -1000000;                     // never try to capture this key again
+    if (rc != SRW_OK) return rc;
+    return body(s);
+  }
+  e->launches = g_launches.load() - before;
+  const cudaError_t ie = cudaGraphInstantiate(&e->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) {
+    e->exec = nullptr;
+    e->seen = -1000000;
+    cudaGetLastError();
+    g_launches -= e->launches;
+    return body(s);
+  }
+  SRW_CUDA(cudaGraphLaunch(e->exec, s));
+  return SRW_OK;
+}
+
+static int vit_num_params(const srw_vit_config* c) { return 4 + 12 * c->depth + 4; }
+}  // namespace srw
+
+extern "C" int srw_set_graph_mode(int on) {
+  std::lock_guard<std::mutex> lk(g_graph_mu);
+  g_graph_mode = on ? 1 : 0;
+  if (!on) {
+    for (auto& g : g_graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    g_graphs.clear();
+  }
+  return SRW_OK;
+}
+
+extern "C" int srw_vit_forward(const srw_vit_fwd_args* a, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  SRW_REQUIRE(a && a->cfg && a->params, "srw_vit_forward: null pointer");
+  if (!graphs_enabled(s) || a->cfg->depth <= 0 || a->cfg->depth > 4096) return vit_forward_body(a, s);
+  KeyBuilder kb;
+  kb.add((int)1); kb.add(*a->cfg); kb.add(s);
+  for (int i = 0; i < vit_num_params(a->cfg); ++i) kb.add(a->params[i]);
+  kb.add(a->weight_planes); kb.add(a->x); kb.add(a->batch); kb.add(a->grad_batch); kb.add(a->drop_scale); kb.add(a->logits); kb.add(a->feat);
+  kb.add(a->workspace); kb.add(a->workspace_bytes); kb.add(a->gemm_impl);
+  return run_graphed(std::move(kb.k), s, [a](cudaStream_t st) { return vit_forward_body(a, st); });
+}
+
+extern "C" int srw_vit_backward(const srw_vit_bwd_args* a, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  SRW_REQUIRE(a && a->cfg && a->params && a->grads, "srw_vit_backward: null pointer");
+  if (!graphs_enabled(s) || a->cfg->depth <= 0 || a->cfg->depth > 4096) return vit_backward_body(a, s);
+  KeyBuilder kb;
+  kb.add((int)2); kb.add(*a->cfg); kb.add(s);
+  for (int i = 0; i < vit_num_params(a->cfg); ++i) { kb.add(a->params[i]); kb.add(a->grads[i]); }
+  kb.add(a->weight_planes); kb.add(a->x); kb.add(a->batch); kb.add(a->grad_batch); kb.add(a->drop_scale); kb.add(a->dlogits); kb.add(a->dfeat);
+  kb.add(a->accumulate_grads); kb.add(a->workspace); kb.add(a->workspace_bytes); kb.add(a->gemm_impl);
+  return run_graphed(std::move(kb.k), s, [a](cudaStream_t st) { return vit_backward_body(a, st); });
 }

@@ -68,7 +68,7 @@ class _VitFunction(torch.autograd.Function):
         wbytes = lib.srw_vit_workspace_bytes(C.byref(cfg), B, grad_batch)
         if wbytes < 0:
             L.check(-2, "srw_vit_workspace_bytes")
-        ws = torch.empty(wbytes, dtype=torch.uint8, device=x.device)
+        ws = model._acquire_ws(wbytes, x.device)
         logits = torch.empty(B, cfg.num_classes, dtype=torch.float32, device=x.device)
         feat = torch.empty(B, cfg.embed_dim, dtype=torch.float32, device=x.device)
         pa = L.ptr_array(params)
@@ -80,6 +80,8 @@ class _VitFunction(torch.autograd.Function):
             ctx.model, ctx.ws, ctx.wbytes, ctx.x, ctx.drop_scale = model, ws, wbytes, x, drop_scale
             ctx.B, ctx.grad_batch = B, grad_batch
             ctx.params = params
+        else:
+            model._release_ws(ws)   # stream-ordered: the next user of this workspace runs after this forward
         ctx.mark_non_differentiable()
         return logits, feat
 
@@ -102,6 +104,7 @@ class _VitFunction(torch.autograd.Function):
                          dfeat=L.ptr(df), grads=L.ptr_array(grads), accumulate_grads=0, workspace=ctx.ws.data_ptr(),
                          workspace_bytes=ctx.wbytes, gemm_impl=model.gemm_impl)
         L.check(lib.srw_vit_backward(C.byref(a), L.stream_ptr()), "srw_vit_backward")
+        model._release_ws(ctx.ws)
         ctx.ws = None
         group = getattr(model, "_dp_group", None)
         if group is not None:   # data parallel: one all-reduce(avg) of the whole flat gradient (C1 in SURVEY.md §2.1)
@@ -138,6 +141,8 @@ class VisionTransformer(nn.Module):
                                 num_heads=num_heads, hidden_dim=int(embed_dim * mlp_ratio), num_classes=num_classes, ln_eps=1e-6)
         self._planes = None
         self._planes_key = None
+        self._keep_cache, self._ws_pool, self._bufs = {}, {}, {}
+        self._pa = self._pa_key = self._flat_grads = self._grad_views = self._ga = None
 
     # -- native plumbing ------------------------------------------------------------------------
     def _ordered_params(self):
@@ -179,13 +184,118 @@ class VisionTransformer(nn.Module):
         else:
             self._planes_key = None
 
-    def _draw_drop_scale(self, batch, device):
+    def _draw_drop_scale(self, batch, device, out=None):
         """[depth, 2, batch] DropPath multipliers mask/keep (timm semantics: per sample Bernoulli(keep)/keep)."""
         if not self.training or max(self.drop_path_rates) == 0.0:
             return None
-        keep = 1.0 - torch.tensor(self.drop_path_rates, dtype=torch.float32, device=device).view(-1, 1, 1)
-        keep = keep.expand(-1, 2, batch)
-        return (torch.bernoulli(keep) / keep).contiguous()
+        key = (batch, str(device))
+        keep = self._keep_cache.get(key)
+        if keep is None:
+            keep = 1.0 - torch.tensor(self.drop_path_rates, dtype=torch.float32, device=device).view(-1, 1, 1)
+            keep = self._keep_cache[key] = keep.expand(-1, 2, batch).contiguous()
+        if out is None:
+            out = torch.empty_like(keep)
+        torch.bernoulli(keep, out=out)
+        return out.div_(keep)
+
+    # -- workspace pool / persistent buffers: stable device pointers let the engine replay CUDA graphs (include/srw.h) ----
+    def _acquire_ws(self, wbytes, device):
+        pool = self._ws_pool.setdefault((wbytes, str(device)), [])
+        return pool.pop() if pool else torch.empty(wbytes, dtype=torch.uint8, device=device)
+
+    def _release_ws(self, ws):
+        if ws is not None:
+            self._ws_pool.setdefault((ws.numel(), str(ws.device)), []).append(ws)
+
+    def _buf(self, name, shape, device, dtype=torch.float32):
+        key = (name, tuple(shape), str(device), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = self._bufs[key] = torch.empty(shape, dtype=dtype, device=device)
+        return t
+
+    def input_buffer(self, shape, device):
+        """Persistent staging buffer for the batch: `torch.cat(parts, out=net.input_buffer(...))` then forward_native()."""
+        return self._buf("x", shape, device)
+
+    def _native_params(self):
+        ps = self._ordered_params()
+        key = tuple(p.data_ptr() for p in ps)
+        if self._pa_key != key:
+            self._pa, self._pa_key = L.ptr_array(ps), key
+        return ps, self._pa
+
+    @torch.no_grad()
+    def forward_native(self, x, grad_batch=0, drop_scale=None):
+        """One autograd-free forward through srw_vit_forward on persistent buffers -> (logits, feat, handle).  `handle`
+        keeps the activations of the first `grad_batch` rows for backward_native(); release it with release_pass() when
+        no backward will follow.  logits / feat are fresh tensors."""
+        if not x.is_cuda:
+            raise RuntimeError("semireward_b200 ViT runs on CUDA (sm_100a) only; there is no CPU path")
+        lib, cfg, dev, B = L.load(), self._cfg, x.device, x.shape[0]
+        xb = self.input_buffer(x.shape, dev)
+        if x.data_ptr() != xb.data_ptr():
+            xb.copy_(x)
+        params, pa = self._native_params()
+        wbytes = lib.srw_vit_workspace_bytes(C.byref(cfg), B, grad_batch)
+        if wbytes < 0:
+            L.check(-2, "srw_vit_workspace_bytes")
+        ws = self._acquire_ws(wbytes, dev)
+        ds = drop_scale
+        if ds is None and self.training and max(self.drop_path_rates) > 0.0:
+            # one persistent buffer per workspace: a pass kept alive for backward keeps its own DropPath draw
+            ds = self._draw_drop_scale(B, dev, out=self._buf(("drop", ws.data_ptr()), (cfg.depth, 2, B), dev))
+        lo, fe = self._buf("logits", (B, cfg.num_classes), dev), self._buf("feat", (B, cfg.embed_dim), dev)
+        a = L.VitFwdArgs(cfg=C.pointer(cfg), params=pa, weight_planes=self._weight_planes().data_ptr(), x=xb.data_ptr(), batch=B,
+                         grad_batch=grad_batch, drop_scale=L.ptr(ds), logits=lo.data_ptr(), feat=fe.data_ptr(),
+                         workspace=ws.data_ptr(), workspace_bytes=wbytes, gemm_impl=self.gemm_impl)
+        L.check(lib.srw_vit_forward(C.byref(a), L.stream_ptr()), "srw_vit_forward")
+        handle = dict(ws=ws, wbytes=wbytes, x=xb, drop_scale=ds, B=B, grad_batch=grad_batch)
+        if grad_batch == 0:
+            self.release_pass(handle)
+        return lo.clone(), fe.clone(), handle
+
+    def release_pass(self, handle):
+        self._release_ws(handle.pop("ws", None))
+
+    def dlogits_buffer(self, grad_batch, device):
+        return self._buf("dlogits", (grad_batch, self._cfg.num_classes), device)
+
+    @torch.no_grad()
+    def backward_native(self, handle, dlogits, dfeat=None, accumulate=False):
+        """srw_vit_backward for a pass of forward_native(): parameter gradients (state_dict order) into the persistent flat
+        buffer -> (flat, views).  Data parallel: the flat buffer is all-reduced (mean) here unless more passes accumulate."""
+        lib, cfg = L.load(), self._cfg
+        Bg, dev = handle["grad_batch"], dlogits.device
+        params, pa = self._native_params()
+        if self._flat_grads is None or self._flat_grads.device != dev:
+            numels = [p.numel() for p in params]
+            self._flat_grads = torch.empty(sum(numels), dtype=torch.float32, device=dev)
+            self._grad_views, off = [], 0
+            for p, n in zip(params, numels):
+                self._grad_views.append(self._flat_grads[off:off + n].view_as(p))
+                off += n
+            self._ga = L.ptr_array(self._grad_views)
+        dl = self.dlogits_buffer(Bg, dev)
+        if dlogits.data_ptr() != dl.data_ptr():
+            dl.copy_(dlogits)
+        df = None
+        if dfeat is not None:
+            df = self._buf("dfeat", (Bg, cfg.embed_dim), dev)
+            df.copy_(dfeat)
+        a = L.VitBwdArgs(cfg=C.pointer(cfg), params=pa, weight_planes=self._weight_planes().data_ptr(), x=handle["x"].data_ptr(),
+                         batch=handle["B"], grad_batch=Bg, drop_scale=L.ptr(handle["drop_scale"]), dlogits=dl.data_ptr(), dfeat=L.ptr(df),
+                         grads=self._ga, accumulate_grads=int(bool(accumulate)), workspace=handle["ws"].data_ptr(),
+                         workspace_bytes=handle["wbytes"], gemm_impl=self.gemm_impl)
+        L.check(lib.srw_vit_backward(C.byref(a), L.stream_ptr()), "srw_vit_backward")
+        self.release_pass(handle)
+        return self._flat_grads, self._grad_views
+
+    def allreduce_grads_(self):
+        group = getattr(self, "_dp_group", None)
+        if group is not None and self._flat_grads is not None:   # data parallel: C1 in SURVEY.md §2.1
+            from ..parallel import allreduce_mean_
+            allreduce_mean_(self._flat_grads, group)
 
     def _run(self, x, grad_batch=None, drop_scale=None):
         if not x.is_cuda:

@@ -22,7 +22,9 @@ def build_oracle(cfg: dict, depth: int, seed: int = 0, head_gain: float = 4.0):
     sc = O.StepConfig(algorithm=cfg["algorithm"], num_classes=cfg["num_classes"], ulb_dest_len=cfg["ulb_dest_len"],
                       p_cutoff=cfg["p_cutoff"], thresh_warmup=cfg["thresh_warmup"], start_timing=cfg["start_timing"], N_k=cfg["N_k"],
                       num_train_iter=cfg["num_train_iter"], num_warmup_iter=cfg["num_warmup_iter"], lr=cfg["lr"],
-                      weight_decay=cfg["weight_decay"], layer_decay=cfg["layer_decay"], sr_lr=cfg["sr_lr"], feature_dim=cfg["feature_dim"])
+                      weight_decay=cfg["weight_decay"], layer_decay=cfg["layer_decay"], sr_lr=cfg["sr_lr"], feature_dim=cfg["feature_dim"],
+                      ema_p=cfg.get("ema_p", 0.999), use_quantile=cfg.get("use_quantile", True), clip_thresh=cfg.get("clip_thresh", False),
+                      n_sigma=cfg.get("n_sigma", 2), lambda_e=cfg.get("ent_loss_ratio", 0.001))
     return O.build_det_oracle(vc, sc, seed=seed, head_gain=head_gain)
 
 

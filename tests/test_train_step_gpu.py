@@ -36,16 +36,18 @@ def _resync(alg, orc):
             p.copy_(orc.rp[n].detach())
 
 
-@pytest.mark.parametrize("depth,steps,over,resync", [
-    (2, 8, {}, True),
-    (2, 6, dict(thresh_warmup=False, p_cutoff=0.6), True),
-    (12, 5, {}, True),
-    (2, 8, {}, False),
+@pytest.mark.parametrize("depth,steps,over,resync,eager", [
+    (2, 8, {}, True, True),
+    (2, 6, dict(thresh_warmup=False, p_cutoff=0.6), True, True),
+    (12, 5, {}, True, True),
+    (2, 8, {}, False, True),
+    (2, 8, {}, True, False),    # the autograd route (_VitFunction / _SSLLoss) instead of the eager backward
 ])
-def test_srflexmatch_steps_vs_oracle(depth, steps, over, resync):
+def test_srflexmatch_steps_vs_oracle(depth, steps, over, resync, eager):
     cfg = small_cfg(**over)
     orc = build_oracle(cfg, depth)
     alg = build_native(cfg, depth)
+    alg.eager_backward = eager
     hook = alg.hooks_dict["MaskingHook"]
     tap = _grad_tap(alg)
     seen_mask_values = set()
@@ -58,8 +60,10 @@ def test_srflexmatch_steps_vs_oracle(depth, steps, over, resync):
         alg.call_hook("after_train_step")
         torch.cuda.synchronize()
         ld = alg.log_dict
-        tol = 1e-3 if resync else 5e-3
         for k_native, k_or in (("train/sup_loss", "sup_loss"), ("train/unsup_loss", "unsup_loss"), ("train/total_loss", "total_loss")):
+            # gate: 1e-3 abs from identical state; the free-running trajectory (no resync) separates chaotically through Adam
+            # (see _resync), so it is only held to 5e-3 relative (losses are ~1..16 here, head_gain 4)
+            tol = 1e-3 if resync else 5e-3 * max(1.0, abs(float(rec[k_or])))
             assert abs(ld[k_native] - float(rec[k_or])) < tol, f"it {it} {k_or}: {ld[k_native]} vs {float(rec[k_or])}"
         assert abs(ld["train/util_ratio"] - float(rec["util_ratio"])) < 1e-6
         # bit-exact integer / mask state
@@ -98,3 +102,90 @@ def test_srflexmatch_steps_vs_oracle(depth, steps, over, resync):
             assert worst_r < 2e-5, f"it {it}: rewarder parameters drifted {worst_r}"
             _resync(alg, orc)
     print("mask values seen:", sorted(seen_mask_values))
+
+
+def test_stochastic_stage2_eager_matches_autograd_route():
+    """DropPath on: stage 2 re-runs the backbone K times (fresh DropPath draws per pass, like the reference) and two
+    graphs carry gradient (pass 0 -> sup loss, last pass -> unsup loss).  The eager backward and the autograd route must
+    give the same losses, masks and gradients from the same RNG state."""
+    import functools
+    import semireward_b200 as S
+    from semireward_b200 import detgen
+    cfg = small_cfg(num_train_iter=8, start_timing=1)   # it=3: K = max(8, 1 + 8/3) = 8
+    results = []
+    for eager in (True, False):
+        args = S.get_config(cfg)
+        builder = functools.partial(S.get_net_builder(args.net, False), depth=2, drop_path_rate=0.3)
+        alg = S.get_algorithm(args, builder, None, None)
+        with torch.no_grad():
+            for prefix, mod in (("", alg.model), ("rewarder.", alg.rewarder), ("generator.", alg.generator)):
+                for n, p in mod.named_parameters():
+                    p.copy_(torch.from_numpy(detgen.fill_param(prefix + n, p.shape, 0)))
+        alg.model = alg.model.cuda(args.gpu).train()
+        alg.rewarder, alg.generator = alg.rewarder.cuda(args.gpu), alg.generator.cuda(args.gpu)
+        alg.eager_backward = eager
+        tap = _grad_tap(alg)
+        torch.manual_seed(123)
+        rec = []
+        for it in (2, 3, 4):
+            alg.it = it
+            alg.out_dict, alg.log_dict = alg.train_step(**alg.process_batch(**batch_tensors(cfg, it)))
+            alg.call_hook("after_train_step")
+            torch.cuda.synchronize()
+            rec.append((dict(alg.log_dict), alg._last_mask.clone(), alg._last_mask2.clone(), {n: g.clone() for n, g in tap.items()}))
+        results.append(rec)
+    for (ld_a, m_a, m2_a, g_a), (ld_b, m_b, m2_b, g_b) in zip(*results):
+        for k in ("train/sup_loss", "train/unsup_loss", "train/total_loss", "train/util_ratio"):
+            assert abs(ld_a[k] - ld_b[k]) < 1e-6, (k, ld_a[k], ld_b[k])
+        assert torch.equal(m_a, m_b) and torch.equal(m2_a, m2_b)
+        for n in g_a:
+            sc = g_b[n].abs().max().item()
+            assert (g_a[n] - g_b[n]).abs().max().item() <= 1e-5 * max(sc, 1e-20), n
+
+
+@pytest.mark.parametrize("algorithm,over", [
+    ("srfreematch", dict(use_quantile=True, clip_thresh=False, ent_loss_ratio=0.05)),
+    ("srfreematch", dict(use_quantile=False, clip_thresh=True, ent_loss_ratio=0.05)),
+    ("srsoftmatch", dict(n_sigma=2)),
+])
+def test_srfreematch_srsoftmatch_steps_vs_oracle(algorithm, over):
+    """SRFreeMatch / SRSoftMatch native steps (stage 1, the gap step, stage 2 with and without an SR update) against the
+    oracle from identical state: hard pseudo-labels and 0/1 masks bit-exact, SoftMatch's soft weights and every EMA state
+    within 1e-6, losses within 1e-3, gradients within 1e-3 relative."""
+    cfg = small_cfg(algorithm=algorithm, ema_p=0.9, **over)   # momentum 0.9: the state moves visibly within 8 steps
+    orc = build_oracle(cfg, 2)
+    alg = build_native(cfg, 2)
+    tap = _grad_tap(alg)
+    hook = alg.hooks_dict["MaskingHook"]
+    for it in range(8):
+        batch = batch_tensors(cfg, it)
+        rec = orc.train_step(dict(batch), it)
+        ref_grads = orc.param_update()
+        alg.it = it
+        alg.out_dict, alg.log_dict = alg.train_step(**alg.process_batch(**batch))
+        alg.call_hook("after_train_step")
+        torch.cuda.synchronize()
+        ld = alg.log_dict
+        for k_native, k_or in (("train/sup_loss", "sup_loss"), ("train/unsup_loss", "unsup_loss"), ("train/total_loss", "total_loss")):
+            assert abs(ld[k_native] - float(rec[k_or])) < 1e-3, f"it {it} {k_or}: {ld[k_native]} vs {float(rec[k_or])}"
+        assert abs(ld["train/util_ratio"] - float(rec["util_ratio"])) < 1e-5
+        assert torch.equal(alg._last_pseudo_label.cpu(), rec["pseudo"]), f"it {it}: pseudo labels differ"
+        if algorithm == "srfreematch":
+            assert torch.equal(alg._last_mask.cpu(), rec["mask"]), f"it {it}: mask differs"
+            assert (hook.p_model.cpu() - orc.hook.p_model).abs().max().item() < 1e-6
+            assert (hook.label_hist.cpu() - orc.hook.label_hist).abs().max().item() < 1e-6
+            assert abs(hook.time_p.item() - float(orc.hook.time_p)) < 1e-6
+        else:
+            assert (alg._last_mask.cpu() - rec["mask"]).abs().max().item() < 1e-5, f"it {it}: weights differ"
+            assert abs(hook.prob_max_mu_t.item() - float(orc.hook.prob_max_mu_t)) < 1e-6
+            assert abs(hook.prob_max_var_t.item() - float(orc.hook.prob_max_var_t)) < 1e-6
+            assert (alg.hooks_dict["DistAlignHook"].p_model.cpu() - orc.da.p_model).abs().max().item() < 1e-6
+        if "dg_mask2" in rec:
+            assert torch.equal(alg._last_mask2.cpu(), rec["dg_mask2"]), f"it {it}: mask2 differs"
+        worst_g = 0.0
+        for n, p in alg.model.named_parameters():
+            gr = ref_grads[n]
+            worst_g = max(worst_g, (tap[n].cpu() - gr).abs().max().item() / max(gr.abs().max().item(), 1e-20))
+        print(f"{algorithm} it {it}: total {ld['train/total_loss']:.5f} (oracle {float(rec['total_loss']):.5f}) util {ld['train/util_ratio']:.3f} grad rel err {worst_g:.2e}")
+        assert worst_g < 1e-3, f"it {it}: gradient error {worst_g}"
+        _resync(alg, orc)

@@ -74,3 +74,47 @@ def test_vit_simt_twin_matches_tcgen05():
         model.gemm_impl = L.GEMM_SIMT
         b = model(x)["logits"]
     assert (a - b).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("use_drop", [False, True])
+def test_native_pass_graph_replay_matches_autograd_path(use_drop):
+    """forward_native/backward_native (persistent buffers -> CUDA-graph replay from the 3rd identical call on) give
+    bit-identical logits and gradients to the autograd route, call after call, and follow changing inputs."""
+    from semireward_b200 import _lib as L, detgen
+    O, vc, p, model = _setup(2)
+    lib = L.load()
+    B, Bg = 12, 8
+    for rep in range(5):   # rep 0 eager, rep 1 captures, rep >= 2 replays
+        x = torch.from_numpy(detgen.normal("x", (B, 3, 32, 32), 10 + rep)).cuda()
+        drop = None
+        if use_drop:
+            g = torch.Generator().manual_seed(rep)
+            drop = (torch.bernoulli(torch.full((2, 2, B), 0.7), generator=g) / 0.7).cuda()
+        cl = torch.from_numpy(detgen.normal("cl", (Bg, 100), 20 + rep)).cuda()
+        model.zero_grad()
+        out = model(x, grad_batch=Bg, drop_scale=drop)
+        (out["logits"][:Bg] * cl).sum().backward()
+        ref_grads = [q.grad.clone() for q in model._ordered_params()]
+        ds = None
+        if drop is not None:
+            ds = model._buf("test_drop", drop.shape, drop.device)
+            ds.copy_(drop)
+        n0 = lib.srw_kernel_launches()
+        lg, ft, h = model.forward_native(x, grad_batch=Bg, drop_scale=ds)
+        flat, views = model.backward_native(h, cl)
+        assert lib.srw_kernel_launches() - n0 > 50   # replays are counted like launches
+        torch.cuda.synchronize()
+        assert torch.equal(lg, out["logits"].detach()) and torch.equal(ft, out["feat"].detach()), f"rep {rep}"
+        for a, b in zip(views, ref_grads):
+            assert torch.equal(a, b), f"rep {rep}: gradient differs between graph replay and eager launches"
+
+
+def test_scale_inplace():
+    from semireward_b200 import _lib as L
+    x = torch.arange(1003, dtype=torch.float32, device="cuda")
+    one, half = torch.ones((), device="cuda"), torch.full((), 0.5, device="cuda")
+    lib = L.load()
+    L.check(lib.srw_scale_inplace(x.data_ptr(), x.numel(), one.data_ptr(), L.stream_ptr()))
+    assert torch.equal(x, torch.arange(1003, dtype=torch.float32, device="cuda"))
+    L.check(lib.srw_scale_inplace(x.data_ptr(), x.numel(), half.data_ptr(), L.stream_ptr()))
+    assert torch.equal(x, torch.arange(1003, dtype=torch.float32, device="cuda") * 0.5)
