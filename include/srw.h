@@ -124,7 +124,13 @@ typedef struct {
   const float* gamma; const float* mean; const float* rstd;
   float* dx; int64_t lddx; int accumulate_dx;  /* dx (+)= LN backward */
   float* dgamma; float* dbeta; int accumulate_dparams;
-  float* workspace;                          /* >= 2 * 256 * cols floats */
+  float* workspace;                          /* >= 3 * 256 * cols floats */
+  /* optional fused hand-over to the next backward GEMM: dx_planes = split(row_scale[row / rows_per_scale] * dx_new)
+   * (dx_new = the value written to dx) and colsum_out[c] (+)= its column sums (the bias gradient of the layer whose
+   * output gradient dx is).  Saves the separate srw_split_planes pass over dx. */
+  void* dx_planes; int64_t ldp; int64_t plane_stride;
+  const float* row_scale; int rows_per_scale;
+  float* colsum_out; int colsum_accumulate;
 } srw_layernorm_bwd_args;
 int srw_layernorm_bwd(const srw_layernorm_bwd_args* a, void* stream);
 

@@ -51,7 +51,8 @@ class LayerNormFwdArgs(C.Structure):
 class LayerNormBwdArgs(C.Structure):
     _fields_ = [("dy", vp), ("lddy", i64), ("x", vp), ("ldx", i64), ("rows", i32), ("cols", i32), ("gamma", vp), ("mean", vp),
                 ("rstd", vp), ("dx", vp), ("lddx", i64), ("accumulate_dx", i32), ("dgamma", vp), ("dbeta", vp),
-                ("accumulate_dparams", i32), ("workspace", vp)]
+                ("accumulate_dparams", i32), ("workspace", vp), ("dx_planes", vp), ("ldp", i64), ("plane_stride", i64),
+                ("row_scale", vp), ("rows_per_scale", i32), ("colsum_out", vp), ("colsum_accumulate", i32)]
 
 
 class AttnFwdArgs(C.Structure):

@@ -99,25 +99,39 @@ __device__ __forceinline__ float plane_value(const __nv_bfloat16* __restrict__ p
 // 7.1.26 (|error| < 5e-7 in fp32, about twice the fp32 rounding of gelu itself and far below the 1e-3 parity gate): the
 // fused GEMM epilogues are instruction-bound, and libdevice erff costs ~3x as many instructions.  exp(-x^2/2) is shared by
 // the erf tail and the Gaussian density of the derivative.
-__device__ __forceinline__ void gelu_parts(float x, float& erf_z, float& gauss) {
-  const float az = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, az, 1.0f));
-  gauss = __expf(-az * az);                               // exp(-x^2 / 2)
+// The fused GEMM epilogues are instruction-issue bound (ncu source view: ~40 SASS instructions per element before this
+// form), so the special functions are the raw MUFU approximations (rcp.approx / ex2.approx, <= 2 ulp, no IEEE slow-path
+// branches or denormal fix-ups) and every constant is folded: 4 FMUL + 7 FFMA + 2 MUFU per gelu().
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// erf_abs = erf(|x| / sqrt 2) in [0, 1), gauss = exp(-x^2 / 2)
+__device__ __forceinline__ void gelu_parts(float x, float& erf_abs, float& gauss) {
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f));
+  gauss = ex2_approx((x * x) * (-0.5f * 1.4426950408889634f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  erf_z = copysignf(fmaf(-poly * t, gauss, 1.0f), x);     // erf(x / sqrt 2)
+  erf_abs = fmaf(-(poly * t), gauss, 1.0f);
 }
 __device__ __forceinline__ float gelu_f(float x) {
   float e, g;
   gelu_parts(x, e, g);
-  return 0.5f * x * (1.0f + e);
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), e, hx);                            // 0.5 x (1 + sign(x) erf(|x|/sqrt 2))
 }
 __device__ __forceinline__ float gelu_grad_f(float x) {
   float e, g;
   gelu_parts(x, e, g);
-  return fmaf(x * 0.39894228040143267794f, g, 0.5f * (1.0f + e));
+  return fmaf(x * 0.39894228040143267794f, g, fmaf(0.5f, copysignf(e, x), 0.5f));
 }
 
 // ------------------------------------------------------------------------------------------------

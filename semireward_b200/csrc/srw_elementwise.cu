@@ -180,7 +180,8 @@ __global__ void colsum_stage1_kernel(const float* __restrict__ x, int64_t ldx, c
 // out_y[c] (+)= sum_p partial[p * stride_p + y * stride_y + c]  for y = blockIdx.y; 8 warps split the partials, then a
 // shared-memory fold in fixed order (deterministic).  Used by colsum (y = 0) and LayerNorm dgamma / dbeta (y = 0, 1).
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int nparts, int64_t stride_p, int64_t stride_y,
-                                                              int cols, float* __restrict__ out0, float* __restrict__ out1, int accumulate) {
+                                                              int cols, float* __restrict__ out0, float* __restrict__ out1, int accumulate,
+                                                              float* __restrict__ out2 = nullptr, int accumulate2 = 0) {
   pdl_trigger();
   pdl_wait();
   __shared__ float red[8][33];
@@ -196,8 +197,9 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += red[i][tx];
-    float* out = blockIdx.y == 0 ? out0 : out1;
-    out[c] = accumulate ? out[c] + s : s;
+    float* out = blockIdx.y == 0 ? out0 : (blockIdx.y == 1 ? out1 : out2);
+    const int acc_flag = blockIdx.y == 2 ? accumulate2 : accumulate;
+    out[c] = acc_flag ? out[c] + s : s;
   }
 }
 
@@ -324,14 +326,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             int64_t ldx, int rows, const float* __restrict__ gamma,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             float* __restrict__ dx, int64_t lddx, int accumulate_dx,
-                                                            float* __restrict__ partial) {
+                                                            float* __restrict__ partial, __nv_bfloat16* __restrict__ dxp, int64_t ldp, int64_t ps,
+                                                            const float* __restrict__ row_scale, int rows_per_scale) {
   pdl_trigger();
   pdl_wait();
   constexpr int COLS = J * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float pg[J], pb[J], gm[J];
+  float pg[J], pb[J], gm[J], pc[J];
 #pragma unroll
-  for (int j = 0; j < J; ++j) { pg[j] = 0.f; pb[j] = 0.f; gm[j] = gamma[lane + 32 * j]; }
+  for (int j = 0; j < J; ++j) { pg[j] = 0.f; pb[j] = 0.f; pc[j] = 0.f; gm[j] = gamma[lane + 32 * j]; }
   for (int row = blockIdx.x * 8 + warp; row < rows; row += 8 * gridDim.x) {
     const float mu = mean[row], rs = rstd[row];
     const float* dyr = dy + (int64_t)row * lddy;
@@ -351,24 +354,34 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     s1 = warp_sum(s1) * (1.0f / COLS);
     s2 = warp_sum(s2) * (1.0f / COLS);
     float* dxr = dx + (int64_t)row * lddx;
+    const float sc = (dxp && row_scale) ? row_scale[row / rows_per_scale] : 1.0f;
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      const float v = rs * (g[j] - s1 - xh[j] * s2);
-      dxr[lane + 32 * j] = accumulate_dx ? dxr[lane + 32 * j] + v : v;
+      float v = rs * (g[j] - s1 - xh[j] * s2);
+      if (accumulate_dx) v += dxr[lane + 32 * j];
+      dxr[lane + 32 * j] = v;
+      if (dxp) {   // the next GEMM's operand: planes of scale(row) * dx, and its column sums (that layer's bias gradient)
+        const float u = v * sc;
+        __nv_bfloat16 h, l;
+        split_bf16(u, h, l);
+        dxp[(int64_t)row * ldp + lane + 32 * j] = h;
+        dxp[(int64_t)row * ldp + lane + 32 * j + ps] = l;
+        pc[j] += u;
+      }
     }
   }
   __shared__ float red[8][COLS];
-#pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
+  const int npass = dxp ? 3 : 2;
+  for (int pass = 0; pass < npass; ++pass) {
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < J; ++j) red[warp][lane + 32 * j] = pass == 0 ? pg[j] : pb[j];
+    for (int j = 0; j < J; ++j) red[warp][lane + 32 * j] = pass == 0 ? pg[j] : (pass == 1 ? pb[j] : pc[j]);
     __syncthreads();
     for (int c = threadIdx.x; c < COLS; c += 256) {
       float s = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) s += red[w][c];
-      partial[((int64_t)blockIdx.x * 2 + pass) * COLS + c] = s;
+      partial[((int64_t)blockIdx.x * 3 + pass) * COLS + c] = s;
     }
   }
 }
@@ -419,7 +432,7 @@ extern "C" int srw_split_planes(const srw_split_args* a, void* stream_) {
     SRW_LAUNCH_CHECK();
     if (a->colsum_out) {
       SRW_CUDA(launch_pdl(reduce_partials_kernel, dim3(dim3(cdiv(a->cols, 32), 1)), dim3(256), 0, stream, a->colsum_workspace, nparts, a->cols, 0, a->cols, a->colsum_out, nullptr,
-                                                                               a->colsum_accumulate));
+                                                                               a->colsum_accumulate, nullptr, 0));
       g_launches++;
       SRW_LAUNCH_CHECK();
     }
@@ -455,7 +468,7 @@ extern "C" int srw_colsum(const srw_colsum_args* a, void* stream_) {
                                                                               a->rows, a->cols, a->workspace));
     g_launches++;
     SRW_LAUNCH_CHECK();
-    SRW_CUDA(launch_pdl(reduce_partials_kernel, dim3(dim3(cdiv(a->cols, 32), 1)), dim3(256), 0, stream, a->workspace, nparts, a->cols, 0, a->cols, a->out, nullptr, a->accumulate));
+    SRW_CUDA(launch_pdl(reduce_partials_kernel, dim3(dim3(cdiv(a->cols, 32), 1)), dim3(256), 0, stream, a->workspace, nparts, a->cols, 0, a->cols, a->out, nullptr, a->accumulate, nullptr, 0));
     g_launches++;
     SRW_LAUNCH_CHECK();
     return SRW_OK;
@@ -465,7 +478,7 @@ extern "C" int srw_colsum(const srw_colsum_args* a, void* stream_) {
                                                 a->row_scale, a->rows_per_scale > 0 ? a->rows_per_scale : 1, a->rows, a->cols, a->workspace);
   g_launches++;
   SRW_LAUNCH_CHECK();
-  SRW_CUDA(launch_pdl(reduce_partials_kernel, dim3(dim3(cdiv(a->cols, 32), 1)), dim3(256), 0, stream, a->workspace, nparts, a->cols, 0, a->cols, a->out, nullptr, a->accumulate));
+  SRW_CUDA(launch_pdl(reduce_partials_kernel, dim3(dim3(cdiv(a->cols, 32), 1)), dim3(256), 0, stream, a->workspace, nparts, a->cols, 0, a->cols, a->out, nullptr, a->accumulate, nullptr, 0));
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;
@@ -497,12 +510,14 @@ extern "C" int srw_layernorm_fwd(const srw_layernorm_fwd_args* a, void* stream_)
 extern "C" int srw_layernorm_bwd(const srw_layernorm_bwd_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SRW_REQUIRE(a && a->dy && a->x && a->gamma && a->mean && a->rstd && a->dx && a->workspace && a->rows > 0, "srw_layernorm_bwd: bad args");
+  SRW_REQUIRE(!a->dx_planes || (a->ldp > 0 && a->plane_stride > 0), "srw_layernorm_bwd: dx_planes needs ldp / plane_stride");
   SRW_REQUIRE(a->cols % 32 == 0 && a->cols <= 1024, "srw_layernorm_bwd: cols must be a multiple of 32 and <= 1024 (cols=%d)", a->cols);
   const int nblocks = std::min(256, cdiv(a->rows, 8));
 #define SRW_LN_BWD(J)                                                                                                             \
   case J:                                                                                                                         \
     SRW_CUDA(launch_pdl(layernorm_bwd_kernel<J>, dim3(nblocks), dim3(256), 0, stream, a->dy, a->lddy, a->x, a->ldx, a->rows, a->gamma, a->mean, a->rstd, a->dx, \
-                                                         a->lddx, a->accumulate_dx, a->workspace));                                \
+                                                         a->lddx, a->accumulate_dx, a->workspace, reinterpret_cast<__nv_bfloat16*>(a->dx_planes), a->ldp,   \
+                                                         a->plane_stride, a->row_scale, a->rows_per_scale > 0 ? a->rows_per_scale : 1));                                \
     break;
   switch (a->cols / 32) {
     SRW_LN_BWD(2) SRW_LN_BWD(4) SRW_LN_BWD(6) SRW_LN_BWD(8) SRW_LN_BWD(12) SRW_LN_BWD(16) SRW_LN_BWD(24) SRW_LN_BWD(32)
@@ -514,8 +529,9 @@ extern "C" int srw_layernorm_bwd(const srw_layernorm_bwd_args* a, void* stream_)
   g_launches++;
   SRW_LAUNCH_CHECK();
   if (a->dgamma && a->dbeta) {
-    SRW_CUDA(launch_pdl(reduce_partials_kernel, dim3(dim3(cdiv(a->cols, 32), 2)), dim3(256), 0, stream, a->workspace, nblocks, 2 * (int64_t)a->cols, a->cols, a->cols, a->dgamma,
-                                                                             a->dbeta, a->accumulate_dparams));
+    SRW_REQUIRE(!a->colsum_out || a->dx_planes, "srw_layernorm_bwd: colsum_out needs dx_planes");
+    SRW_CUDA(launch_pdl(reduce_partials_kernel, dim3(cdiv(a->cols, 32), (a->dx_planes && a->colsum_out) ? 3 : 2), dim3(256), 0, stream, a->workspace, nblocks,
+                        3 * (int64_t)a->cols, a->cols, a->cols, a->dgamma, a->dbeta, a->accumulate_dparams, a->colsum_out, a->colsum_accumulate));
     g_launches++;
     SRW_LAUNCH_CHECK();
   }

@@ -44,6 +44,8 @@ __host__ __device__ constexpr int gemm_smem_bytes(int bn) {
   return gemm_stages(bn) * gemm_stage_bytes(bn) + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 }
 
+unsigned long long* g_gemm_trace = nullptr;
+
 struct EpiParams {
   int M, N;
   int epilogue;
@@ -237,7 +239,10 @@ __device__ __forceinline__ void drain_accumulator(const EpiParams& ep, uint32_t 
   }
 }
 
+// Debug timeline (srw_gemm_set_trace): per CTA 16 clock64() stamps — 0 entry, 1 setup done, 2 first TMA issued, 3 first stage
+// landed, 4+2i accumulator of the CTA's i-th tile complete, 5+2i its epilogue done, 15 exit.  NULL in production.
 struct TcParams {
+  unsigned long long* trace;
   int K;            // reduction length
   int kb_per_split; // k blocks (of 64) handled by one split
   int a_mn, b_mn;   // operand majors
@@ -262,6 +267,8 @@ gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
   float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
 
   pdl_trigger();
+  unsigned long long* tr = tp.trace ? tp.trace + (size_t)blockIdx.x * 16 : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb_total = (tp.K + BK - 1) / BK;
@@ -292,6 +299,7 @@ gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above is CTA-local; operands / epilogue inputs come from the previous kernel
+  if (tr && threadIdx.x == 0) tr[1] = clock64();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -308,6 +316,7 @@ gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = smem + s * STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          if (tr && it == 0) tr[2] = clock64();
           const int k0 = kb * BK;
           if (!tp.a_mn) {
             tma_load_3d(st, &tmap_a, &full_bar[s], k0, m0, 0);                       // [2][128][64]
@@ -348,6 +357,7 @@ gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (tr && it == 0) tr[3] = clock64();
           const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t b_base = a_base + A_STAGE_BYTES;
 #pragma unroll
@@ -378,14 +388,17 @@ gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
       const uint32_t as = tile_iter & 1;
       mbar_wait(&acc_full[as], (tile_iter >> 1) & 1);
       tc_fence_after();
+      if (tr && warp == 4 && lane == 0 && tile_iter < 5) tr[4 + 2 * tile_iter] = clock64();
       drain_accumulator<BN>(ep, tmem_base + as * 256, epi_stage + (warp - 4) * (32 * EPI_STAGE_LD), q, part, lane, m0, n0, split, has_k);
       tc_fence_before();
       __syncwarp();
+      if (tr && warp == 4 && lane == 0 && tile_iter < 5) tr[5 + 2 * tile_iter] = clock64();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (tr && threadIdx.x == 0) tr[15] = clock64();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -830,6 +843,7 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
   SRW_CUDA(attr_err);
 
   TcParams tp;
+  tp.trace = g_gemm_trace;
   tp.K = a->K; tp.kb_per_split = kb_per_split; tp.a_mn = a->a_mn_major ? 1 : 0; tp.b_mn = a->b_mn_major ? 1 : 0;
   tp.splits = grid_z;
   const double flops = 2.0 * a->M * a->N * a->K, bytes = 4.0 * ((double)a->M * a->K + (double)a->N * a->K + (double)a->M * a->N);
@@ -889,5 +903,11 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
   g_launches++;
   SRW_CUDA(le);
   SRW_LAUNCH_CHECK();
+  return SRW_OK;
+}
+
+// debug: per-CTA clock64 timeline of the 1-CTA kernel into buf[grid][16] (NULL turns it off).  Not part of include/srw.h.
+extern "C" int srw_gemm_set_trace(unsigned long long* buf) {
+  srw::g_gemm_trace = buf;
   return SRW_OK;
 }

@@ -319,7 +319,7 @@ static Layout make_layout(const Dims& d) {
   L.splitk_floats = sk;
   L.splitk = c.take(sk * 4);
   L.colsum_ws = c.take((int64_t)256 * std::max(3 * d.D, d.hidden) * 4);
-  L.ln_ws = c.take((int64_t)2 * 256 * D * 4);
+  L.ln_ws = c.take((int64_t)3 * 256 * D * 4);
   L.total = c.off;
   return L;
 }
@@ -588,7 +588,9 @@ static int vit_backward_body(const srw_vit_bwd_args* a, cudaStream_t s) {
     const float* ds_attn = a->drop_scale ? a->drop_scale + ((int64_t)l * 2 + 0) * d.B : nullptr;
     const float* ds_mlp = a->drop_scale ? a->drop_scale + ((int64_t)l * 2 + 1) * d.B : nullptr;
     // MLP branch:  t_out = t_mid + s * (gelu(LN2(t_mid) W1^T + b1) W2^T + b2)
-    SRW_TRY(split_to(dt, D, Tg, D, ws + L.g, D, ds_mlp, d.N, s, G[pblk(l, B_FC2B)], acc, cws));   // + fc2 bias gradient
+    // g = planes of ds_mlp * dt (+ fc2 bias gradient = its column sums): produced by the previous block's LN1 backward
+    // (fused hand-over), except for the first block processed, whose dt comes from the head
+    if (l == d.L - 1) SRW_TRY(split_to(dt, D, Tg, D, ws + L.g, D, ds_mlp, d.N, s, G[pblk(l, B_FC2B)], acc, cws));
     SRW_TRY(wgrad(D, Fh, Tg, ws + L.g, D, Tg, ws + b.h, Fh, T, sk, G[pblk(l, B_FC2W)], Fh, acc, impl, s));
     {
       Gemm g(Tg, Fh, D, impl);  // dz = (g W2) * gelu'(z)
@@ -608,9 +610,11 @@ static int vit_backward_body(const srw_vit_bwd_args* a, cudaStream_t s) {
     lb.dy = F32(L.dy); lb.lddy = D; lb.x = F32(b.t_mid); lb.ldx = D; lb.rows = Tg; lb.cols = D; lb.gamma = P[pblk(l, B_N2W)];
     lb.mean = F32(b.mean2); lb.rstd = F32(b.rstd2); lb.dx = dt; lb.lddx = D; lb.accumulate_dx = 1;
     lb.dgamma = G[pblk(l, B_N2W)]; lb.dbeta = G[pblk(l, B_N2B)]; lb.accumulate_dparams = acc; lb.workspace = F32(L.ln_ws);
+    // attention branch:  t_mid = t_in + s * (attn(LN1(t_in)) Wp^T + bp): the LN2 backward also emits g = planes of
+    // ds_attn * dt and the proj bias gradient
+    lb.dx_planes = ws + L.g; lb.ldp = D; lb.plane_stride = (int64_t)Tg * D; lb.row_scale = ds_attn; lb.rows_per_scale = d.N;
+    lb.colsum_out = G[pblk(l, B_PROJB)]; lb.colsum_accumulate = acc;
     SRW_TRY(srw_layernorm_bwd(&lb, s));
-    // attention branch:  t_mid = t_in + s * (attn(LN1(t_in)) Wp^T + bp)
-    SRW_TRY(split_to(dt, D, Tg, D, ws + L.g, D, ds_attn, d.N, s, G[pblk(l, B_PROJB)], acc, cws));  // + proj bias gradient
     SRW_TRY(wgrad(D, D, Tg, ws + L.g, D, Tg, ws + b.o, D, T, sk, G[pblk(l, B_PROJW)], D, acc, impl, s));
     {
       Gemm g(Tg, D, D, impl);  // d_o = g Wp
@@ -638,6 +642,12 @@ static int vit_backward_body(const srw_vit_bwd_args* a, cudaStream_t s) {
     }
     lb.x = F32(L.t[l]); lb.gamma = P[pblk(l, B_N1W)]; lb.mean = F32(b.mean1); lb.rstd = F32(b.rstd1);
     lb.dgamma = G[pblk(l, B_N1W)]; lb.dbeta = G[pblk(l, B_N1B)];
+    if (l > 0) {   // hand-over to block l-1's MLP branch: planes of its ds_mlp * dt and its fc2 bias gradient
+      lb.row_scale = a->drop_scale ? a->drop_scale + ((int64_t)(l - 1) * 2 + 1) * d.B : nullptr;
+      lb.colsum_out = G[pblk(l - 1, B_FC2B)];
+    } else {
+      lb.dx_planes = nullptr; lb.colsum_out = nullptr; lb.row_scale = nullptr;
+    }
     SRW_TRY(srw_layernorm_bwd(&lb, s));
   }
   // ---- embedding ----

@@ -127,7 +127,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx=None, accumulate_dx=False, dgamma
     if dgamma is None:
         dgamma = torch.empty(cols, dtype=torch.float32, device=x.device)
         dbeta = torch.empty_like(dgamma)
-    ws = torch.empty(2 * 256 * cols, dtype=torch.float32, device=x.device)
+    ws = torch.empty(3 * 256 * cols, dtype=torch.float32, device=x.device)
     a = L.LayerNormBwdArgs(dy=dy.data_ptr(), lddy=dy.stride(0), x=x.data_ptr(), ldx=x.stride(0), rows=rows, cols=cols,
                            gamma=gamma.data_ptr(), mean=mean.data_ptr(), rstd=rstd.data_ptr(), dx=dx.data_ptr(), lddx=dx.stride(0),
                            accumulate_dx=int(accumulate_dx), dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(),

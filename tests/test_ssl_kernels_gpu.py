@@ -113,3 +113,99 @@ def test_flexmatch_mask_and_loss_kernels():
     assert torch.equal(side["mask2"].cpu(), m2)
     assert (gl.grad.cpu() - llb.grad).abs().max().item() < 1e-6
     assert (gs.grad.cpu() - ls.grad).abs().max().item() < 1e-6
+
+
+class _Alg:   # the attributes the hooks read from the algorithm
+    distributed, world_size = False, 1
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+        self.hooks_dict = {}
+
+
+@pytest.mark.parametrize("B,C,use_quantile,clip", [(8, 100, True, False), (8, 100, False, True), (37, 10, True, True), (128, 1000, True, False)])
+def test_freematch_mask_kernel_vs_oracle_state_machine(B, C, use_quantile, clip):
+    """srw_freematch_mask against FreeMatchState (freematch/utils.py:23-66) on IDENTICAL logits over several calls: masks
+    and pseudo-labels bit-exact, time_p / p_model / label_hist to fp32 rounding (the sums run in a different order)."""
+    from oracle import ssl_oracle as O
+    from semireward_b200 import detgen
+    from semireward_b200.core.hooks import FreeMatchThresholdingHook
+    st = O.FreeMatchState(C, 0.9)
+    hook = FreeMatchThresholdingHook(C, 0.9, device="cuda")
+    alg = _Alg(use_quantile=use_quantile, clip_thresh=clip)
+    for call in range(6):
+        logits = torch.from_numpy(detgen.normal("fm_logits", (B, C), 40 + call)) * (1.0 + call)
+        from_probs = call % 2 == 1
+        probs = torch.softmax(logits, dim=-1)
+        ref_mask = st.masking(probs, use_quantile, clip)
+        ref_pseudo = probs.argmax(dim=-1) if from_probs else logits.argmax(dim=-1)
+        mask = hook.masking(alg, logits.cuda(), softmax_x_ulb=True, pseudo_from_probs=from_probs)
+        torch.cuda.synchronize()
+        assert torch.equal(alg._last_pseudo[1].cpu(), ref_pseudo), f"call {call}"
+        assert (alg._last_probs.cpu() - probs).abs().max().item() < 1e-6
+        assert abs(hook.time_p.item() - float(st.time_p)) < 2e-7, (call, hook.time_p.item(), float(st.time_p))
+        assert (hook.p_model.cpu() - st.p_model).abs().max().item() < 2e-7
+        assert (hook.label_hist.cpu() - st.label_hist).abs().max().item() < 2e-7
+        assert torch.equal(mask.cpu(), ref_mask), f"call {call}: mask differs"
+
+
+@pytest.mark.parametrize("B,C", [(8, 100), (37, 10), (128, 1000)])
+def test_softmatch_mask_kernel_vs_oracle_state_machine(B, C):
+    """srw_softmatch_mask against DistAlignState + SoftMatchState on identical logits: aligned (train_step) and
+    un-aligned (data_generator) calls interleaved; weights and state to 1e-6."""
+    from oracle import ssl_oracle as O
+    from semireward_b200 import detgen
+    from semireward_b200.core.hooks import DistAlignEMAHook, SoftMatchWeightingHook
+    st, da = O.SoftMatchState(C, 2, 0.9), O.DistAlignState(C, 0.9)
+    hook, dah = SoftMatchWeightingHook(C, 2, 0.9, device="cuda"), DistAlignEMAHook(C, 0.9, device="cuda")
+    alg = _Alg()
+    alg.hooks_dict["DistAlignHook"] = dah
+    for call in range(6):
+        logits = torch.from_numpy(detgen.normal("sm_logits", (B, C), 60 + call)) * (1.0 + 0.5 * call)
+        align = call % 3 != 2
+        probs = torch.softmax(logits, dim=-1)
+        ref_w = st.masking(da.dist_align(probs) if align else probs)
+        w = hook.masking(alg, logits.cuda(), softmax_x_ulb=True, dist_align=align, pseudo_from_probs=not align)
+        torch.cuda.synchronize()
+        assert torch.equal(alg._last_pseudo[1].cpu(), probs.argmax(-1) if not align else logits.argmax(-1))
+        assert abs(hook.prob_max_mu_t.item() - float(st.prob_max_mu_t)) < 1e-6
+        assert abs(hook.prob_max_var_t.item() - float(st.prob_max_var_t)) < 1e-6
+        assert (dah.p_model.cpu() - da.p_model).abs().max().item() < 1e-6
+        assert (w.cpu() - ref_w).abs().max().item() < 2e-6, f"call {call}"
+
+
+@pytest.mark.parametrize("B,C,nsel", [(8, 100, 5), (8, 100, 0), (37, 10, 37), (128, 1000, 64)])
+def test_freematch_entropy_kernel_vs_autograd(B, C, nsel):
+    """srw_freematch_entropy: value and gradient w.r.t. the strong logits against torch autograd of the oracle's
+    freematch_entropy_loss (srfreematch.py:16-44); accumulates on top of an existing gradient / total loss."""
+    import ctypes as Ct
+    from oracle import ssl_oracle as O
+    from semireward_b200 import _lib as L, detgen
+    logits = (torch.from_numpy(detgen.normal("ent_logits", (B, C), 70)) * 2.0).requires_grad_(True)
+    mask = torch.zeros(B)
+    mask[torch.from_numpy(detgen.integers("ent_sel", (B,), 0, 1 << 30, 71)).argsort()[:nsel]] = 1.0
+    p_model = torch.softmax(torch.from_numpy(detgen.normal("ent_pm", (C,), 72)), 0)
+    label_hist = torch.softmax(torch.from_numpy(detgen.normal("ent_lh", (C,), 73)), 0)
+    if C >= 10:
+        label_hist[3] = 0.0   # exercises replace_inf_to_zero
+    lam = 0.05
+    base = torch.from_numpy(detgen.normal("ent_base", (B, C), 74)) * 0.01
+    losses = torch.tensor([0.5, 0.25, 0.75, 1.0, -1.0], device="cuda")
+    dl = base.clone().cuda()
+    lg = logits.detach().cuda()
+    a = L.FreeMatchEntropyArgs(B=B, num_classes=C, mask=mask.cuda().data_ptr(), logits_s=lg.data_ptr(), ld_logits=C,
+                               p_model=p_model.cuda().data_ptr(), label_hist=label_hist.cuda().data_ptr(), lambda_e=lam,
+                               losses=losses.data_ptr(), dlogits_s=dl.data_ptr(), ld_dlogits=C, accumulate=1)
+    mk, pm, lh = mask.cuda(), p_model.cuda(), label_hist.cuda()
+    a.mask, a.p_model, a.label_hist = mk.data_ptr(), pm.data_ptr(), lh.data_ptr()
+    L.check(L.load().srw_freematch_entropy(Ct.byref(a), L.stream_ptr()), "srw_freematch_entropy")
+    torch.cuda.synchronize()
+    if nsel == 0:
+        assert losses[4].item() == 0.0 and abs(losses[2].item() - 0.75) < 1e-7 and torch.equal(dl.cpu(), base)
+        return
+    ref = O.freematch_entropy_loss(mask, logits, p_model, label_hist)
+    (g_ref,) = torch.autograd.grad(lam * ref, logits)
+    assert abs(losses[4].item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item())), (losses[4].item(), ref.item())
+    assert abs(losses[2].item() - (0.75 + lam * ref.item())) < 1e-5
+    err = (dl.cpu() - base - g_ref).abs().max().item()
+    assert err < 1e-5 * max(g_ref.abs().max().item(), 1e-3), (err, g_ref.abs().max().item())
