@@ -38,8 +38,8 @@ F_FWD_GF = 12.134          # GFLOP per sample forward
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch-size", type=int, default=8, help="per-GPU labelled batch (config-faithful: 8)")
     ap.add_argument("--stage", type=int, default=1, choices=[1, 2])
@@ -133,7 +133,7 @@ def main_reference(a):
     if rank != 0:
         return
     cfg = dict(YAML_CFG, batch_size=a.batch_size)
-    steps, warmup = max(1, min(a.steps, 8)), max(0, min(a.warmup, 2))   # bounded sample: ~1-2 s per CPU step
+    steps, warmup = max(1, min(a.steps, 8)), max(0, min(a.warmup, 2))   # bounded sample: ~1 s per CPU step, at most 8 + 2 steps
     sps, per_step, cores = cpu_reference_run(cfg, steps, warmup, a.stage)
     line = dict(impl="reference", metric="SSL train-step samples/sec (ViT-S CIFAR-100)", value=sps, unit="samples/s", n_gpus=a.gpus,
                 steps=steps, warmup=warmup, ms_per_step=per_step * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -246,8 +246,13 @@ def main_native(a):
         sust, burst, hbm, how = peaks()
         g = st[L.PROF_GEMM]
         ach = g.flops / (g.total_ms * 1e-3) / 1e12 if g.total_ms > 0 else 0.0
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+        if os.path.isfile(tp):   # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch from the committed `ncu --set full` capture
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj.get("gemm_mean_traffic_bytes"), tj.get("source")
         roof = dict(bound="tensor", kernel="gemm_bf16x3_tcgen05_kernel", achieved=ach, peak=sust, unit="TFLOP/s", frac=ach / sust,
-                    traffic=None, peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})", launches_per_step=g.launches / nprof,
+                    traffic=traffic, traffic_source=traffic_src, algorithmic_bytes_per_launch=g.bytes / max(g.launches, 1), peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})", launches_per_step=g.launches / nprof,
                     avg_launch_us=1e3 * g.total_ms / max(g.launches, 1), share_of_step=g.total_ms / nprof / step_ms_prof,
                     note="achieved = algorithmic 2MNK per launch / CUDA-event launch time; the kernel issues 3 bf16 MMAs per algorithmic "
                          "product (hi*hi, hi*lo, lo*hi) for fp32-level accuracy, so the tensor pipe does 3x these FLOPs")
@@ -274,9 +279,11 @@ def main_native(a):
                                 samples_per_step_per_gpu=samples_per_step, parallelism=f"dp{world}", drop_path=0.2,
                                 arithmetic="fp32 semantics: bf16x3 split-precision tcgen05 MMA, fp32 accumulate",
                                 l2="step working set (~1.8 GB of activations at batch 8) >> 126 MB L2; 4 rotating input batches",
+                                launch="CUDA-graph replay of the backbone forward/backward (SRW_GRAPHS) + programmatic dependent launch (SRW_PDL); "
+                                       "backward launched inside train_step ahead of the loss read-back",
                                 algorithmic_gflop_per_step_per_gpu=7 * B * F_FWD_GF),
                     clocks=clk.summary(), gpu_launches=int(launches),
-                    e2e=dict(value=e2e, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=16, ms_per_step=ms_e2e / K))
+                    e2e=dict(value=e2e, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4 * (5 + U), ms_per_step=ms_e2e / K))
         if roof is not None:
             line["roofline"] = roof
             line["attention"] = attn
@@ -288,6 +295,9 @@ def main_native(a):
 
 
 if __name__ == "__main__":
+    import faulthandler
+    # a hung collective or kernel must end as a traceback + non-zero exit, not as a silent stall of the whole run
+    faulthandler.dump_traceback_later(int(os.environ.get("SRW_BENCH_WATCHDOG", "900")), exit=True)
     args_ = parse()
     if args_.impl == "reference":
         main_reference(args_)

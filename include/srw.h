@@ -299,7 +299,7 @@ int srw_ssl_loss(const srw_ssl_loss_args* a, void* stream);
  * (algorithmbase.py:332-333) and PseudoLabelingHook.gen_ulb_targets hard labels (hooks/pseudo_label.py:40).  One CTA.
  * State (device): time_p [1], p_model [C], label_hist [C]; every EMA in the reference's fp32 evaluation order.
  * pseudo_from_probs: 0 = argmax of the logits (train_step, srfreematch.py:146-150), 1 = argmax of the probabilities
- * (data_generator, :93-97).  world_size 1 view: the reference all-gathers the probabilities over ranks first (C4). */
+ * (data_generator, :93-97). */
 typedef struct {
   int B, num_classes;
   const float* logits_w; int64_t ld_logits;
@@ -309,6 +309,10 @@ typedef struct {
   int64_t* pseudo; int pseudo_from_probs;
   float* mask;              /* [B] out */
   float* max_probs;         /* [B] out (may be NULL) */
+  /* data parallel (C4, freematch/utils.py:25-26): update() sees the probabilities of ALL ranks, masking() the local ones.
+   * phase 0 = everything in one launch (world size 1, probs_all = NULL); phase 1 = softmax + pseudo-labels only; then the
+   * caller all-gathers probs_w into probs_all [B_all, C]; phase 2 = update() from probs_all + mask of the local rows. */
+  int phase; const float* probs_all; int B_all;
 } srw_freematch_mask_args;
 int srw_freematch_mask(const srw_freematch_mask_args* a, void* stream);
 

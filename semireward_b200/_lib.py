@@ -117,7 +117,7 @@ f64 = C.c_double
 class FreeMatchMaskArgs(C.Structure):
     _fields_ = [("B", i32), ("num_classes", i32), ("logits_w", vp), ("ld_logits", i64), ("momentum", C.c_double), ("use_quantile", i32),
                 ("clip_thresh", i32), ("time_p", vp), ("p_model", vp), ("label_hist", vp), ("probs_w", vp), ("pseudo", vp),
-                ("pseudo_from_probs", i32), ("mask", vp), ("max_probs", vp)]
+                ("pseudo_from_probs", i32), ("mask", vp), ("max_probs", vp), ("phase", i32), ("probs_all", vp), ("B_all", i32)]
 
 
 class FreeMatchEntropyArgs(C.Structure):

@@ -132,13 +132,16 @@ class FreeMatchThresholdingHook(Hook):
         self.label_hist = torch.ones(self.num_classes, dtype=torch.float32, device=dev) / self.num_classes
         self.time_p = self.p_model.mean().reshape(1)
 
+    @staticmethod
+    def _distributed(algorithm):
+        return bool(getattr(algorithm, "distributed", False)) and getattr(algorithm, "world_size", 1) > 1
+
     @torch.no_grad()
-    def masking(self, algorithm, logits_x_ulb, softmax_x_ulb=True, pseudo_from_probs=False, *args, **kwargs):
+    def masking(self, algorithm, logits_x_ulb, softmax_x_ulb=True, pseudo_from_probs=False, probs_all=None, *args, **kwargs):
+        """probs_all (testing hook): phase-2 input as if gathered from all ranks; the local probabilities must be its rows
+        [rank * B, (rank + 1) * B)."""
         if not softmax_x_ulb:
             raise RuntimeError("fused FreeMatch hook takes raw logits (softmax is fused into the kernel)")
-        if getattr(algorithm, "distributed", False) and getattr(algorithm, "world_size", 1) > 1:
-            raise NotImplementedError("srfreematch under data parallelism needs the all-gathered probabilities for update() "
-                                      "(C4 in SURVEY.md §2.1): not built yet")
         lw = _contig_logits(logits_x_ulb)
         dev = lw.device
         for n in ("p_model", "label_hist", "time_p"):
@@ -154,7 +157,17 @@ class FreeMatchThresholdingHook(Hook):
                                 use_quantile=int(bool(algorithm.use_quantile)), clip_thresh=int(bool(algorithm.clip_thresh)),
                                 time_p=self.time_p.data_ptr(), p_model=self.p_model.data_ptr(), label_hist=self.label_hist.data_ptr(),
                                 probs_w=probs.data_ptr(), pseudo=pseudo.data_ptr(), pseudo_from_probs=int(bool(pseudo_from_probs)),
-                                mask=mask.data_ptr(), max_probs=None)
+                                mask=mask.data_ptr(), max_probs=None, phase=0, probs_all=None, B_all=0)
+        if probs_all is not None or self._distributed(algorithm):
+            # data parallel: update() sees every rank's probabilities (concat_all_gather, utils.py:25-26; rank-major rows as in
+            # semilearn/algorithms/utils/ops.py:34-45): softmax launch, all_gather, then the update + mask launch
+            a.phase = 1
+            L.check(L.load().srw_freematch_mask(C.byref(a), L.stream_ptr()), "srw_freematch_mask")
+            if probs_all is None:
+                import torch.distributed as dist
+                probs_all = torch.empty(dist.get_world_size() * B, Cn, dtype=torch.float32, device=dev)
+                dist.all_gather_into_tensor(probs_all, probs)
+            a.phase, a.probs_all, a.B_all = 2, probs_all.data_ptr(), probs_all.shape[0]
         L.check(L.load().srw_freematch_mask(C.byref(a), L.stream_ptr()), "srw_freematch_mask")
         algorithm.p_model, algorithm.label_hist, algorithm.time_p = self.p_model, self.label_hist, self.time_p   # utils.py:41-43
         algorithm._last_pseudo = (probs, pseudo)

@@ -74,35 +74,45 @@ struct AttnFwdParams {
 
 constexpr int FWD_THREADS = 512 + 32;   // 16 softmax warps (4 per TMEM lane quarter, 16 columns each) + 1 TMA/MMA warp
 
+// One CTA per (head, image).  K and V of the head are staged ONCE and stay in shared memory while the CTA walks the
+// ceil(N / 128) query tiles: per tile  TMA Q -> S = Q K^T (TMEM) -> softmax warps -> P chunks -> O += P V -> store.
+// The next tile's Q load overlaps this tile's epilogue, its S MMAs start as soon as the softmax warps have drained S.
+// Shared memory: [A: Q tile, re-used as P buffer 1 once S is done | B: P buffer 0 | K hi,lo | V hi,lo | barriers | exchange].
+// Rows beyond N (the third tile of N = 257 holds ONE valid row) skip all softmax work: MMA rows are independent, so their
+// stale P rows only produce discarded O rows.
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  pdl_trigger();
   const int NP = p.NP;
   const uint32_t kv_plane = (uint32_t)NP * 128;           // bytes of one K (or V) plane
-  const uint32_t off_k = 2 * ROW_TILE_BYTES;              // after Q hi, Q lo
-  const uint32_t off_v = max(off_k + 2 * kv_plane, 4u * ROW_TILE_BYTES);  // P buffers alias [0, 64 KiB)
+  const uint32_t off_k = 4 * ROW_TILE_BYTES;              // after region A (Q / P1) and region B (P0), 32 KiB each
+  const uint32_t off_v = off_k + 2 * kv_plane;
   const uint32_t off_bar = off_v + 2 * kv_plane;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bar);
-  uint64_t* bar_qk = bars + 0; uint64_t* bar_v = bars + 1; uint64_t* bar_s = bars + 2; uint64_t* bar_o = bars + 3;
+  uint64_t* bar_kv = bars + 0; uint64_t* bar_q = bars + 1; uint64_t* bar_s = bars + 2; uint64_t* bar_o = bars + 3;
   uint64_t* bar_p = bars + 4;      // [2]
   uint64_t* bar_pfree = bars + 6;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_sfree = bars + 8;  // softmax warps have read S for the last time (count 16)
+  uint64_t* bar_ofree = bars + 9;  // softmax warps have read O (count 16)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
   float* xch = reinterpret_cast<float*>(smem + off_bar + 128);   // [4][128] partial row max / row sum exchange
 
-  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int h = blockIdx.x, b = blockIdx.y;
   const int D = p.H * HD;
   const int row0 = b * p.N;           // first token row of this image in the [B*N, 3D] qkv matrix
   const int nchunks = (NP + 63) / 64;
+  const int ntiles = (p.N + 127) / 128;
 
   if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_kv);
-    mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
     mbar_init(&bar_p[0], 16); mbar_init(&bar_p[1], 16);
     mbar_init(&bar_pfree[0], 1); mbar_init(&bar_pfree[1], 1);
+    mbar_init(bar_sfree, 16); mbar_init(bar_ofree, 16);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -118,129 +128,160 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   if (warp == 16) {
     if (lane == 0) {
-      // ---- loads ----
+      // ---- K, V once; Q of tile 0 ----
       const int half = NP / 2;
-      mbar_arrive_expect_tx(bar_qk, 2 * ROW_TILE_BYTES + 2 * kv_plane);
-      tma_load_3d(smem, &tmap_q, bar_qk, h * HD, row0 + qt * 128, 0);
-      tma_load_3d(smem + ROW_TILE_BYTES, &tmap_q, bar_qk, h * HD, row0 + qt * 128, 1);
+      mbar_arrive_expect_tx(bar_kv, 4 * kv_plane);
       for (int pl = 0; pl < 2; ++pl)
-        for (int hf = 0; hf < 2; ++hf)
-          tma_load_3d(smem + off_k + pl * kv_plane + hf * half * 128, &tmap_kv, bar_qk, D + h * HD, row0 + hf * half, pl);
-      mbar_arrive_expect_tx(bar_v, 2 * kv_plane);
-      for (int pl = 0; pl < 2; ++pl)
-        for (int hf = 0; hf < 2; ++hf)
-          tma_load_3d(smem + off_v + pl * kv_plane + hf * half * 128, &tmap_kv, bar_v, 2 * D + h * HD, row0 + hf * half, pl);
-      // ---- S = Q K^T ----
-      mbar_wait(bar_qk, 0);
-      tc_fence_after();
+        for (int hf = 0; hf < 2; ++hf) {
+          tma_load_3d(smem + off_k + pl * kv_plane + hf * half * 128, &tmap_kv, bar_kv, D + h * HD, row0 + hf * half, pl);
+          tma_load_3d(smem + off_v + pl * kv_plane + hf * half * 128, &tmap_kv, bar_kv, 2 * D + h * HD, row0 + hf * half, pl);
+        }
+      mbar_arrive_expect_tx(bar_q, 2 * ROW_TILE_BYTES);
+      tma_load_3d(smem, &tmap_q, bar_q, h * HD, row0, 0);
+      tma_load_3d(smem + ROW_TILE_BYTES, &tmap_q, bar_q, h * HD, row0, 1);
+      mbar_wait(bar_kv, 0);
       const uint32_t q_hi = smem_u32(smem), q_lo = q_hi + ROW_TILE_BYTES;
       const uint32_t k_hi = smem_u32(smem + off_k), k_lo = k_hi + kv_plane;
-      const int n1 = NP <= 256 ? NP : 256, n2 = NP - n1;
-      for (int part = 0; part < 2; ++part) {
-        const int n = part == 0 ? n1 : n2;
-        if (n == 0) break;
-        const uint32_t idesc = umma_idesc_bf16(n, 0, 0);
-        const uint32_t boff = part * 256 * 128, tcol = part * 256;
-#pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint64_t aq_hi = umma_smem_desc(q_hi + kk * 32, 16, 1024), aq_lo = umma_smem_desc(q_lo + kk * 32, 16, 1024);
-          const uint64_t bk_hi = umma_smem_desc(k_hi + boff + kk * 32, 16, 1024), bk_lo = umma_smem_desc(k_lo + boff + kk * 32, 16, 1024);
-          umma_bf16(TM_S + tcol, aq_lo, bk_hi, idesc, kk > 0 ? 1u : 0u);
-          umma_bf16(TM_S + tcol, aq_hi, bk_lo, idesc, 1u);
-          umma_bf16(TM_S + tcol, aq_hi, bk_hi, idesc, 1u);
-        }
-      }
-      umma_commit(bar_s);
-      // ---- O += P_c V_c ----
-      mbar_wait(bar_v, 0);
       const uint32_t v_hi = smem_u32(smem + off_v), v_lo = v_hi + kv_plane;
       const uint32_t idesc_pv = umma_idesc_bf16(HD, 0, 1);
-      for (int c = 0; c < nchunks; ++c) {
-        const int buf = c & 1;
-        mbar_wait(&bar_p[buf], (c >> 1) & 1);
+      const int n1 = NP <= 256 ? NP : 256, n2 = NP - n1;
+      uint32_t g = 0;   // running P-chunk counter across tiles -> buffer / phase
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(bar_q, t & 1);
+        if (t > 0) mbar_wait(bar_sfree, (t - 1) & 1);      // the softmax warps have drained S of tile t-1
         tc_fence_after();
-        const uint32_t p_hi = smem_u32(smem + buf * 2 * ROW_TILE_BYTES), p_lo = p_hi + ROW_TILE_BYTES;
-        const int ksteps = min(4, (NP - c * 64) / 16);
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint32_t voff = (uint32_t)(c * 64 + kk * 16) * 128;
-          const uint64_t ap_hi = umma_smem_desc(p_hi + kk * 32, 16, 1024), ap_lo = umma_smem_desc(p_lo + kk * 32, 16, 1024);
-          const uint64_t bv_hi = umma_smem_desc(v_hi + voff, 1024, 1024), bv_lo = umma_smem_desc(v_lo + voff, 1024, 1024);
-          const uint32_t acc = (c > 0 || kk > 0) ? 1u : 0u;
-          umma_bf16(TM_OX, ap_lo, bv_hi, idesc_pv, acc);
-          umma_bf16(TM_OX, ap_hi, bv_lo, idesc_pv, 1u);
-          umma_bf16(TM_O, ap_hi, bv_hi, idesc_pv, acc);
+        // ---- S = Q K^T ----
+        for (int part = 0; part < 2; ++part) {
+          const int n = part == 0 ? n1 : n2;
+          if (n == 0) break;
+          const uint32_t idesc = umma_idesc_bf16(n, 0, 0);
+          const uint32_t boff = part * 256 * 128, tcol = part * 256;
+#pragma unroll
+          for (int kk = 0; kk < HD / 16; ++kk) {
+            const uint64_t aq_hi = umma_smem_desc(q_hi + kk * 32, 16, 1024), aq_lo = umma_smem_desc(q_lo + kk * 32, 16, 1024);
+            const uint64_t bk_hi = umma_smem_desc(k_hi + boff + kk * 32, 16, 1024), bk_lo = umma_smem_desc(k_lo + boff + kk * 32, 16, 1024);
+            umma_bf16(TM_S + tcol, aq_lo, bk_hi, idesc, kk > 0 ? 1u : 0u);
+            umma_bf16(TM_S + tcol, aq_hi, bk_lo, idesc, 1u);
+            umma_bf16(TM_S + tcol, aq_hi, bk_hi, idesc, 1u);
+          }
         }
-        umma_commit(&bar_pfree[buf]);
+        umma_commit(bar_s);
+        if (t > 0) mbar_wait(bar_ofree, (t - 1) & 1);      // the epilogue of tile t-1 has read O
+        tc_fence_after();
+        // ---- O += P_c V_c ----
+        for (int c = 0; c < nchunks; ++c, ++g) {
+          const int buf = g & 1;
+          mbar_wait(&bar_p[buf], (g >> 1) & 1);
+          tc_fence_after();
+          const uint32_t p_hi = smem_u32(smem + (buf ^ 1) * 2 * ROW_TILE_BYTES), p_lo = p_hi + ROW_TILE_BYTES;   // buffer 0 = region B, 1 = region A
+          const int ksteps = min(4, (NP - c * 64) / 16);
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const uint32_t voff = (uint32_t)(c * 64 + kk * 16) * 128;
+            const uint64_t ap_hi = umma_smem_desc(p_hi + kk * 32, 16, 1024), ap_lo = umma_smem_desc(p_lo + kk * 32, 16, 1024);
+            const uint64_t bv_hi = umma_smem_desc(v_hi + voff, 1024, 1024), bv_lo = umma_smem_desc(v_lo + voff, 1024, 1024);
+            const uint32_t acc = (c > 0 || kk > 0) ? 1u : 0u;
+            umma_bf16(TM_OX, ap_lo, bv_hi, idesc_pv, acc);
+            umma_bf16(TM_OX, ap_hi, bv_lo, idesc_pv, 1u);
+            umma_bf16(TM_O, ap_hi, bv_hi, idesc_pv, acc);
+          }
+          umma_commit(&bar_pfree[buf]);
+        }
+        umma_commit(bar_o);
+        if (t + 1 < ntiles) {
+          // region A held P buffer 1 of this tile: reload it with the next Q tile once every MMA that read it is complete
+          mbar_wait(bar_o, t & 1);
+          mbar_arrive_expect_tx(bar_q, 2 * ROW_TILE_BYTES);
+          tma_load_3d(smem, &tmap_q, bar_q, h * HD, row0 + (t + 1) * 128, 0);
+          tma_load_3d(smem + ROW_TILE_BYTES, &tmap_q, bar_q, h * HD, row0 + (t + 1) * 128, 1);
+        }
       }
-      umma_commit(bar_o);
     }
   } else {
     // ---- softmax warps: 4 warps per TMEM lane quarter; thread == (query row, 16-column interleave `part`) ----
     const int q = warp & 3, part = warp >> 2;
     const int r = q * 32 + lane;                     // 0..127, TMEM lane
-    const int qr = qt * 128 + r;                     // query index inside the image
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float c2 = p.scale * LOG2E;
     const int nsub = NP / 16;                        // 16-column sub-chunks; this thread owns sub-chunks part, part+4, ...
-    mbar_wait(bar_s, 0);
-    tc_fence_after();
-    float m = -INFINITY;
-    for (int sc = part; sc < nsub; sc += 4) {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(TM_S + lane_addr + sc * 16, v);
-      tmem_ld_wait();
+    // P buffer 0 is region B (offset 32 KiB), buffer 1 is region A (offset 0): buffer index -> byte offset
+    uint32_t g = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      const int qr = t * 128 + r;                    // query index inside the image
+      const bool valid = qr < p.N;
+      const bool warp_valid = (t * 128 + q * 32) < p.N;   // any valid row in this warp (uniform per warp)
+      mbar_wait(bar_s, t & 1);
+      tc_fence_after();
+      float m = -INFINITY;
+      if (warp_valid) {
+        for (int sc = part; sc < nsub; sc += 4) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(TM_S + lane_addr + sc * 16, v);
+          tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (sc * 16 + j < p.N) m = fmaxf(m, __uint_as_float(v[j]));
-    }
-    xch[part * 128 + r] = m;
-    ew_sync();
-    m = fmaxf(fmaxf(xch[r], xch[128 + r]), fmaxf(xch[256 + r], xch[384 + r]));
-    ew_sync();                                       // xch is reused for the row sums below
-    const float mc = m * c2;
-    float sum = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-      const int buf = c & 1;
-      const int sc = c * 4 + part;
-      float pv[16];
-      const bool have = sc < nsub;
-      if (have) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(TM_S + lane_addr + sc * 16, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float e = (sc * 16 + j < p.N) ? exp2f(fmaf(__uint_as_float(v[j]), c2, -mc)) : 0.f;
-          pv[j] = e;
-          sum += e;
+          for (int j = 0; j < 16; ++j)
+            if (sc * 16 + j < p.N) m = fmaxf(m, __uint_as_float(v[j]));
         }
       }
-      if (c >= 2) mbar_wait(&bar_pfree[buf], ((c >> 1) - 1) & 1);
-      if (have) {
-        uint8_t* hi_tile = smem + buf * 2 * ROW_TILE_BYTES;
-        store_row16_planes(hi_tile, hi_tile + ROW_TILE_BYTES, r, part * 16, pv);
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_p[buf]);
-    }
-    xch[part * 128 + r] = sum;
-    ew_sync();
-    sum = (xch[r] + xch[128 + r]) + (xch[256 + r] + xch[384 + r]);
-    // ---- epilogue: this thread writes output columns [16*part, 16*part+16) of its row ----
-    mbar_wait(bar_o, 0);
-    tc_fence_after();
-    const float inv = 1.0f / sum;
-    if (part == 0 && qr < p.N && p.lse) p.lse[((int64_t)b * p.H + h) * p.N + qr] = m * p.scale + logf(sum);
-    uint32_t a[16], x[16];
-    tmem_ld_32x32b_x16(TM_O + lane_addr + part * 16, a);
-    tmem_ld_32x32b_x16(TM_OX + lane_addr + part * 16, x);
-    tmem_ld_wait();
-    if (qr < p.N) {
-      float o16[16];
+      xch[part * 128 + r] = m;
+      ew_sync();
+      m = fmaxf(fmaxf(xch[r], xch[128 + r]), fmaxf(xch[256 + r], xch[384 + r]));
+      ew_sync();                                     // xch is reused for the row sums below
+      const float mc = m * c2;
+      float sum = 0.f;
+      for (int c = 0; c < nchunks; ++c, ++g) {
+        const int buf = g & 1;
+        const int sc = c * 4 + part;
+        float pv[16];
+        const bool have = sc < nsub && warp_valid;
+        if (have) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(TM_S + lane_addr + sc * 16, v);
+          tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) o16[j] = (__uint_as_float(a[j]) + __uint_as_float(x[j])) * inv;
-      store_out16(p.o + (int64_t)(row0 + qr) * p.ld_o + h * HD + part * 16, p.o_ps, o16);
+          for (int j = 0; j < 16; ++j) {
+            const float e = (valid && sc * 16 + j < p.N) ? exp2f(fmaf(__uint_as_float(v[j]), c2, -mc)) : 0.f;
+            pv[j] = e;
+            sum += e;
+          }
+        }
+        if (c == nchunks - 1) {                      // last read of S by this warp: the next tile's S MMAs may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_sfree);
+        }
+        if (g >= 2) mbar_wait(&bar_pfree[buf], ((g >> 1) - 1) & 1);
+        if (have) {
+          uint8_t* hi_tile = smem + (buf ^ 1) * 2 * ROW_TILE_BYTES;   // buffer 0 -> region B (32 KiB), buffer 1 -> region A (0)
+          store_row16_planes(hi_tile, hi_tile + ROW_TILE_BYTES, r, part * 16, pv);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_p[buf]);
+      }
+      xch[part * 128 + r] = sum;
+      ew_sync();
+      sum = (xch[r] + xch[128 + r]) + (xch[256 + r] + xch[384 + r]);
+      // ---- epilogue: this thread writes output columns [16*part, 16*part+16) of its row ----
+      mbar_wait(bar_o, t & 1);
+      tc_fence_after();
+      uint32_t a[16], x[16];
+      if (warp_valid) {
+        tmem_ld_32x32b_x16(TM_O + lane_addr + part * 16, a);
+        tmem_ld_32x32b_x16(TM_OX + lane_addr + part * 16, x);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_ofree);
+      if (valid) {
+        const float inv = 1.0f / sum;
+        if (part == 0 && p.lse) p.lse[((int64_t)b * p.H + h) * p.N + qr] = m * p.scale + logf(sum);
+        float o16[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o16[j] = (__uint_as_float(a[j]) + __uint_as_float(x[j])) * inv;
+        store_out16(p.o + (int64_t)(row0 + qr) * p.ld_o + h * HD + part * 16, p.o_ps, o16);
+      }
+      ew_sync();                                     // xch (row sums) is rewritten by the next tile's row max
     }
   }
   tc_fence_before();
@@ -531,8 +572,7 @@ extern "C" int srw_attn_fwd(const srw_attn_fwd_args* a, void* stream_) {
   if (rc) return rc;
   SRW_REQUIRE(a->ld_o % 8 == 0 && a->o_plane_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(a->o) & 15) == 0, "srw_attn_fwd: o planes must be 16-byte aligned");
   const uint32_t kv_plane = (uint32_t)NP * 128;
-  const uint32_t off_v = std::max<uint32_t>(2 * ROW_TILE_BYTES + 2 * kv_plane, 4u * ROW_TILE_BYTES);
-  const int smem_bytes = (int)(off_v + 2 * kv_plane + 128 + 4 * 128 * 4 + 1024);
+  const int smem_bytes = (int)(4 * ROW_TILE_BYTES + 4 * kv_plane + 128 + 4 * 128 * 4 + 1024);   // regions A, B | K | V | barriers | exchange | align
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
@@ -540,7 +580,7 @@ extern "C" int srw_attn_fwd(const srw_attn_fwd_args* a, void* stream_) {
   AttnFwdParams p;
   p.B = a->B; p.N = a->N; p.H = a->H; p.NP = NP; p.scale = a->scale;
   p.o = reinterpret_cast<__nv_bfloat16*>(a->o); p.ld_o = a->ld_o; p.o_ps = a->o_plane_stride; p.lse = a->lse;
-  dim3 grid(cdiv(a->N, 128), a->H, a->B);
+  dim3 grid(a->H, a->B);
   const double pair_flops = 2.0 * a->B * a->H * (double)a->N * a->N * HD;   // one N x N x 64 product per (image, head)
   void* prof = prof_begin(SRW_PROF_ATTN_FWD, 2.0 * pair_flops, 4.0 * 4.0 * a->B * a->N * a->H * HD, stream);
   SRW_CUDA(launch_pdl(attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), smem_bytes, stream, tq, tkv, p));

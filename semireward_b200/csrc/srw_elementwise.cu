@@ -386,6 +386,84 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   }
 }
 
+// Vectorised variant for cols = 128 * J4 (384, 768, 1024): lane owns 4 consecutive columns per 128-column group, so dy / x /
+// dx move as float4 and the optional plane hand-over as 8-byte hi / lo stores.  Same arithmetic and reduction order per column.
+template <int J4>
+__global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ x,
+                                                                int64_t ldx, int rows, const float* __restrict__ gamma,
+                                                                const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                float* __restrict__ dx, int64_t lddx, int accumulate_dx,
+                                                                float* __restrict__ partial, __nv_bfloat16* __restrict__ dxp, int64_t ldp,
+                                                                int64_t ps, const float* __restrict__ row_scale, int rows_per_scale) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int COLS = J4 * 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 pg[J4], pb[J4], pc[J4], gm[J4];
+#pragma unroll
+  for (int j = 0; j < J4; ++j) {
+    pg[j] = pb[j] = pc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gm[j] = *reinterpret_cast<const float4*>(gamma + j * 128 + lane * 4);
+  }
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += 8 * gridDim.x) {
+    const float mu = mean[row], rs = rstd[row];
+    const float* dyr = dy + (int64_t)row * lddy;
+    const float* xr = x + (int64_t)row * ldx;
+    float4 g[J4], xh[J4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < J4; ++j) {
+      const float4 d = *reinterpret_cast<const float4*>(dyr + j * 128 + lane * 4);
+      const float4 xv = *reinterpret_cast<const float4*>(xr + j * 128 + lane * 4);
+      xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      g[j] = make_float4(d.x * gm[j].x, d.y * gm[j].y, d.z * gm[j].z, d.w * gm[j].w);
+      s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+      s2 += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
+      pg[j].x += d.x * xh[j].x; pg[j].y += d.y * xh[j].y; pg[j].z += d.z * xh[j].z; pg[j].w += d.w * xh[j].w;
+      pb[j].x += d.x; pb[j].y += d.y; pb[j].z += d.z; pb[j].w += d.w;
+    }
+    s1 = warp_sum(s1) * (1.0f / COLS);
+    s2 = warp_sum(s2) * (1.0f / COLS);
+    float* dxr = dx + (int64_t)row * lddx;
+    const float sc = (dxp && row_scale) ? row_scale[row / rows_per_scale] : 1.0f;
+#pragma unroll
+    for (int j = 0; j < J4; ++j) {
+      float4 v = make_float4(rs * (g[j].x - s1 - xh[j].x * s2), rs * (g[j].y - s1 - xh[j].y * s2), rs * (g[j].z - s1 - xh[j].z * s2),
+                             rs * (g[j].w - s1 - xh[j].w * s2));
+      float4* dst = reinterpret_cast<float4*>(dxr + j * 128 + lane * 4);
+      if (accumulate_dx) {
+        const float4 o = *dst;
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      }
+      *dst = v;
+      if (dxp) {   // the next GEMM's operand: planes of scale(row) * dx, and its column sums (that layer's bias gradient)
+        const float4 u = make_float4(v.x * sc, v.y * sc, v.z * sc, v.w * sc);
+        uint32_t h0, l0, h1, l1;
+        split2(u.x, u.y, h0, l0);
+        split2(u.z, u.w, h1, l1);
+        __nv_bfloat16* hp = dxp + (int64_t)row * ldp + j * 128 + lane * 4;
+        *reinterpret_cast<uint2*>(hp) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(hp + ps) = make_uint2(l0, l1);
+        pc[j].x += u.x; pc[j].y += u.y; pc[j].z += u.z; pc[j].w += u.w;
+      }
+    }
+  }
+  __shared__ float4 red[8][COLS / 4];
+  const int npass = dxp ? 3 : 2;
+  for (int pass = 0; pass < npass; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < J4; ++j) red[warp][j * 32 + lane] = pass == 0 ? pg[j] : (pass == 1 ? pb[j] : pc[j]);
+    __syncthreads();
+    for (int c4 = threadIdx.x; c4 < COLS / 4; c4 += 256) {
+      float4 sacc = red[0][c4];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) { sacc.x += red[w][c4].x; sacc.y += red[w][c4].y; sacc.z += red[w][c4].z; sacc.w += red[w][c4].w; }
+      *reinterpret_cast<float4*>(partial + ((int64_t)blockIdx.x * 3 + pass) * COLS + c4 * 4) = sacc;
+    }
+  }
+}
+
 __global__ void layernorm_bwd_params_kernel(const float* __restrict__ partial, int nparts, int cols, float* __restrict__ dgamma,
                                             float* __restrict__ dbeta, int accumulate) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -519,6 +597,17 @@ extern "C" int srw_layernorm_bwd(const srw_layernorm_bwd_args* a, void* stream_)
                                                          a->lddx, a->accumulate_dx, a->workspace, reinterpret_cast<__nv_bfloat16*>(a->dx_planes), a->ldp,   \
                                                          a->plane_stride, a->row_scale, a->rows_per_scale > 0 ? a->rows_per_scale : 1));                                \
     break;
+#define SRW_LN_BWD_VEC(J4)                                                                                                          \
+  SRW_CUDA(launch_pdl(layernorm_bwd_vec_kernel<J4>, dim3(nblocks), dim3(256), 0, stream, a->dy, a->lddy, a->x, a->ldx, a->rows, a->gamma,   \
+                      a->mean, a->rstd, a->dx, a->lddx, a->accumulate_dx, a->workspace, reinterpret_cast<__nv_bfloat16*>(a->dx_planes), a->ldp, \
+                      a->plane_stride, a->row_scale, a->rows_per_scale > 0 ? a->rows_per_scale : 1))
+  const bool vec_ok = a->lddy % 4 == 0 && a->ldx % 4 == 0 && a->lddx % 4 == 0 && (!a->dx_planes || (a->ldp % 4 == 0 && a->plane_stride % 4 == 0)) &&
+                      ((reinterpret_cast<uintptr_t>(a->dy) | reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->dx) |
+                        reinterpret_cast<uintptr_t>(a->gamma)) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->dx_planes) & 7) == 0;
+  if (vec_ok && a->cols == 384) { SRW_LN_BWD_VEC(3); }
+  else if (vec_ok && a->cols == 768) { SRW_LN_BWD_VEC(6); }
+  else if (vec_ok && a->cols == 1024) { SRW_LN_BWD_VEC(8); }
+  else
   switch (a->cols / 32) {
     SRW_LN_BWD(2) SRW_LN_BWD(4) SRW_LN_BWD(6) SRW_LN_BWD(8) SRW_LN_BWD(12) SRW_LN_BWD(16) SRW_LN_BWD(24) SRW_LN_BWD(32)
     default:
@@ -526,6 +615,7 @@ extern "C" int srw_layernorm_bwd(const srw_layernorm_bwd_args* a, void* stream_)
       return SRW_ERR_UNSUPPORTED;
   }
 #undef SRW_LN_BWD
+#undef SRW_LN_BWD_VEC
   g_launches++;
   SRW_LAUNCH_CHECK();
   if (a->dgamma && a->dbeta) {

@@ -78,34 +78,72 @@ __device__ __forceinline__ void warp_softmax_row(const float* row, int C, int la
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SSL2_THREADS) freematch_mask_kernel(const srw_freematch_mask_args a, float m_f, float om_f) {
   extern __shared__ int s_hist[];                   // [C]
-  __shared__ float s_maxp[SSL2_MAX_ROWS];
+  __shared__ float s_maxp[SSL2_MAX_ROWS];           // local rows
   __shared__ int s_maxi[SSL2_MAX_ROWS];
+  __shared__ float s_allp[SSL2_MAX_ROWS];           // rows update() sees (== local rows unless probs_all is given)
+  __shared__ int s_alli[SSL2_MAX_ROWS];
   __shared__ float red[32];
   __shared__ float s_q[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int C = a.num_classes, B = a.B;
   for (int c = threadIdx.x; c < C; c += blockDim.x) s_hist[c] = 0;
-  for (int b = warp; b < B; b += nw) {
-    float bp; int ap, al;
-    warp_softmax_row(a.logits_w + (int64_t)b * a.ld_logits, C, lane, a.probs_w ? a.probs_w + (int64_t)b * C : nullptr, bp, ap, al);
-    if (lane == 0) {
-      s_maxp[b] = bp; s_maxi[b] = ap;
-      a.pseudo[b] = a.pseudo_from_probs ? ap : al;
-      if (a.max_probs) a.max_probs[b] = bp;
+  if (a.phase != 2) {   // softmax of the local rows
+    for (int b = warp; b < B; b += nw) {
+      float bp; int ap, al;
+      warp_softmax_row(a.logits_w + (int64_t)b * a.ld_logits, C, lane, a.probs_w + (int64_t)b * C, bp, ap, al);
+      if (lane == 0) {
+        s_maxp[b] = bp; s_maxi[b] = ap;
+        a.pseudo[b] = a.pseudo_from_probs ? ap : al;
+        if (a.max_probs) a.max_probs[b] = bp;
+      }
     }
+    if (a.phase == 1) return;
+  } else {              // phase 2: probs_w was written by phase 1; only max / argmax are needed again
+    for (int b = warp; b < B; b += nw) {
+      const float* pr = a.probs_w + (int64_t)b * C;
+      float bp = -1.f; int bi = 0x7fffffff;
+      for (int c = lane; c < C; c += 32) if (pr[c] > bp) { bp = pr[c]; bi = c; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, bp, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > bp || (ob == bp && oi < bi)) { bp = ob; bi = oi; }
+      }
+      if (lane == 0) { s_maxp[b] = bp; s_maxi[b] = bi; }
+    }
+  }
+  // rows seen by update(): all ranks' probabilities when given (concat_all_gather, freematch/utils.py:25-26), else the local ones
+  const float* up = a.probs_all ? a.probs_all : a.probs_w;
+  const int BU = a.probs_all ? a.B_all : B;
+  __syncthreads();
+  if (a.probs_all) {
+    for (int b = warp; b < BU; b += nw) {
+      const float* pr = up + (int64_t)b * C;
+      float bp = -1.f; int bi = 0x7fffffff;
+      for (int c = lane; c < C; c += 32) if (pr[c] > bp) { bp = pr[c]; bi = c; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, bp, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > bp || (ob == bp && oi < bi)) { bp = ob; bi = oi; }
+      }
+      if (lane == 0) { s_allp[b] = bp; s_alli[b] = bi; }
+    }
+  } else {
+    for (int b = threadIdx.x; b < B; b += blockDim.x) { s_allp[b] = s_maxp[b]; s_alli[b] = s_maxi[b]; }
   }
   __syncthreads();
   // ---- update(): time_p ----
   float stat;
   if (a.use_quantile) {
     // torch.quantile(x, 0.8): rank = 0.8f * (n - 1) in fp32, linear interpolation between the two neighbouring order statistics
-    const float rank = __fmul_rn(0.8f, (float)(B - 1));
+    const float rank = __fmul_rn(0.8f, (float)(BU - 1));
     const int lo = (int)floorf(rank), hi = (int)ceilf(rank);
-    for (int i = threadIdx.x; i < B; i += blockDim.x) {
-      const float v = s_maxp[i];
+    for (int i = threadIdx.x; i < BU; i += blockDim.x) {
+      const float v = s_allp[i];
       int r = 0;
-      for (int j = 0; j < B; ++j) {
-        const float u = s_maxp[j];
+      for (int j = 0; j < BU; ++j) {
+        const float u = s_allp[j];
         r += (u < v || (u == v && j < i)) ? 1 : 0;
       }
       if (r == lo) s_q[0] = v;
@@ -118,8 +156,8 @@ __global__ void __launch_bounds__(SSL2_THREADS) freematch_mask_kernel(const srw_
   } else {
     float s = 0.f;
     if (threadIdx.x == 0) {
-      for (int i = 0; i < B; ++i) s += s_maxp[i];
-      s_q[0] = s / (float)B;
+      for (int i = 0; i < BU; ++i) s += s_allp[i];
+      s_q[0] = s / (float)BU;
     }
     __syncthreads();
     stat = s_q[0];
@@ -127,25 +165,26 @@ __global__ void __launch_bounds__(SSL2_THREADS) freematch_mask_kernel(const srw_
   float time_p = __fadd_rn(__fmul_rn(*a.time_p, m_f), __fmul_rn(om_f, stat));
   if (a.clip_thresh) time_p = fminf(fmaxf(time_p, 0.0f), 0.95f);
   // ---- p_model, label_hist ----
-  for (int b = threadIdx.x; b < B; b += blockDim.x) atomicAdd(&s_hist[s_maxi[b]], 1);
+  for (int b = threadIdx.x; b < BU; b += blockDim.x) atomicAdd(&s_hist[s_alli[b]], 1);
   __syncthreads();
   float pmax = -INFINITY;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s += a.probs_w[(int64_t)b * C + c];
-    const float mean = s / (float)B;
+    for (int b = 0; b < BU; ++b) s += up[(int64_t)b * C + c];
+    const float mean = s / (float)BU;
     const float pm = __fadd_rn(__fmul_rn(a.p_model[c], m_f), __fmul_rn(om_f, mean));
     a.p_model[c] = pm;
     pmax = fmaxf(pmax, pm);
-    a.label_hist[c] = __fadd_rn(__fmul_rn(a.label_hist[c], m_f), __fmul_rn(om_f, (float)s_hist[c] / (float)B));
+    a.label_hist[c] = __fadd_rn(__fmul_rn(a.label_hist[c], m_f), __fmul_rn(om_f, (float)s_hist[c] / (float)BU));
   }
   pmax = blk_max(pmax, red);
   __syncthreads();   // p_model writes of this CTA are visible to all its threads
-  // ---- masking(): max_p >= time_p * p_model[idx] / max(p_model) ----
+  // ---- masking(): max_p >= time_p * p_model[idx] / max(p_model), local rows ----
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     const float mod = a.p_model[s_maxi[b]] / pmax;
     a.mask[b] = s_maxp[b] >= __fmul_rn(time_p, mod) ? 1.0f : 0.0f;
   }
+  __syncthreads();
   if (threadIdx.x == 0) *a.time_p = time_p;
 }
 
@@ -339,6 +378,7 @@ extern "C" int srw_freematch_mask(const srw_freematch_mask_args* a, void* stream
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SRW_REQUIRE(a && a->logits_w && a->time_p && a->p_model && a->label_hist && a->probs_w && a->pseudo && a->mask, "srw_freematch_mask: null pointer");
   SRW_REQUIRE(a->B > 0 && a->B <= SSL2_MAX_ROWS && a->num_classes > 0 && a->num_classes <= 8192, "srw_freematch_mask: 0 < B <= %d, C <= 8192 required", SSL2_MAX_ROWS);
+  SRW_REQUIRE(a->phase >= 0 && a->phase <= 2 && (!a->probs_all || (a->B_all >= a->B && a->B_all <= SSL2_MAX_ROWS)), "srw_freematch_mask: bad phase / B_all");
   const float m_f = (float)a->momentum, om_f = (float)(1.0 - a->momentum);
   freematch_mask_kernel<<<1, SSL2_THREADS, a->num_classes * sizeof(int), stream>>>(*a, m_f, om_f);
   g_launches++;

@@ -209,3 +209,30 @@ def test_freematch_entropy_kernel_vs_autograd(B, C, nsel):
     assert abs(losses[2].item() - (0.75 + lam * ref.item())) < 1e-5
     err = (dl.cpu() - base - g_ref).abs().max().item()
     assert err < 1e-5 * max(g_ref.abs().max().item(), 1e-3), (err, g_ref.abs().max().item())
+
+
+def test_freematch_mask_data_parallel_view():
+    """C4 (freematch/utils.py:25-26): under data parallelism update() integrates the probabilities of ALL ranks and
+    masking() thresholds the local rows.  Emulated in one process: the hook of 'rank 1' gets the rank-major gathered
+    probabilities through its testing hook and must reproduce the reference state machine fed the same way."""
+    from oracle import ssl_oracle as O
+    from semireward_b200 import detgen
+    from semireward_b200.core.hooks import FreeMatchThresholdingHook
+    B, C, W, rank = 8, 100, 2, 1
+    st = O.FreeMatchState(C, 0.9)
+    hook = FreeMatchThresholdingHook(C, 0.9, device="cuda")
+    alg = _Alg(use_quantile=True, clip_thresh=False)
+    for call in range(4):
+        logits_all = torch.from_numpy(detgen.normal("fm_dp_logits", (W * B, C), 90 + call)) * (1.5 + call)
+        probs_all = torch.softmax(logits_all, dim=-1)
+        local = slice(rank * B, (rank + 1) * B)
+        # reference: update() on the gathered probabilities, mask on the local ones (masking() after update(), utils.py:60-65)
+        st.update(probs_all, True, False)
+        mp, mi = probs_all[local].max(dim=-1)
+        ref_mask = mp.ge(st.time_p * (st.p_model / st.p_model.max())[mi]).float()
+        mask = hook.masking(alg, logits_all[local].cuda(), softmax_x_ulb=True, probs_all=probs_all.cuda())
+        torch.cuda.synchronize()
+        assert abs(hook.time_p.item() - float(st.time_p)) < 2e-7
+        assert (hook.p_model.cpu() - st.p_model).abs().max().item() < 2e-7
+        assert (hook.label_hist.cpu() - st.label_hist).abs().max().item() < 2e-7
+        assert torch.equal(mask.cpu(), ref_mask), f"call {call}"
