@@ -231,7 +231,7 @@ def main_native(a):
     e2e = world * samples_per_step * K / (ms_e2e / 1e3)
 
     roof = attn = None
-    if not a.no_roofline and rank == 0:
+    if not a.no_roofline:   # every rank runs the profiled steps (they contain the gradient all-reduce); rank 0 reports
         lib.srw_profile_enable(1)
         st = (L.ProfileStats * L.PROF_NUM)()
         nprof = min(K, 5)
