@@ -131,6 +131,13 @@ class SRFlexMatch(AlgorithmBase):
         # never waits for the host between forward and backward; ParamUpdateHook's loss.backward() just collects the
         # gradients.  Set to False to go through autograd (_VitFunction / _SSLLoss) instead.
         self.eager_backward = True
+        # Stage 2 with DropPath on: the reference runs 1 + K full backbone passes per step (srflexmatch.py:72-104), but the
+        # passes do not depend on each other (only the hook state, which consumes their weak logits in order, does), and of
+        # passes 1..K-1 only the weak rows are ever used, of pass K only weak + strong.  batch_stochastic_passes runs all rows
+        # that are used (nl + 2 nu + (K + 1) nu instead of (K + 1)(nl + 2 nu)) as ONE forward with per-row DropPath draws and
+        # ONE backward over the rows that carry gradient.  Row-for-row identical to the sequential passes given the same
+        # DropPath multipliers (tested); False runs the passes one after the other.
+        self.batch_stochastic_passes = True
 
     def _init_algorithm(self, args):
         self.init(T=args.T, p_cutoff=args.p_cutoff, hard_label=args.hard_label, thresh_warmup=args.thresh_warmup)
@@ -220,24 +227,86 @@ class SRFlexMatch(AlgorithmBase):
         self._host_flip ^= 1
         return bufs[self._host_flip]
 
-    def _backbone_native(self, x_lb, x_ulb_w, x_ulb_s, need_grad=True):
-        """Autograd-free pass on the net's persistent buffers -> (logits, feats, handle), split as (lb, weak, strong)."""
+    def _backbone_native(self, x_lb, x_ulb_w, x_ulb_s, need_grad=True, drop_scale=None):
+        """Autograd-free pass on the net's persistent buffers -> (logits, feats, handle), split as (lb, weak, strong).
+        drop_scale: DropPath multipliers [depth, 2, nl + 2 nu] in engine row order (lb, strong, weak), or None to draw."""
         if not self.use_cat:
             raise NotImplementedError("use_cat: False (BERT/HuBERT configs) is a 'next' row (SURVEY.md §8f)")
         net = self._net()
         nl, nu = x_lb.shape[0], x_ulb_s.shape[0]
         xb = net.input_buffer((nl + 2 * nu,) + tuple(x_lb.shape[1:]), x_lb.device)
         torch.cat((x_lb, x_ulb_s, x_ulb_w), out=xb)
-        lg, ft, handle = net.forward_native(xb, grad_batch=(nl + nu) if need_grad else 0)
+        lg, ft, handle = net.forward_native(xb, grad_batch=(nl + nu) if need_grad else 0, drop_scale=drop_scale)
         return (lg[:nl], lg[nl + nu:], lg[nl:nl + nu]), (ft[:nl], ft[nl + nu:], ft[nl:nl + nu]), handle
+
+    def _has_extra_loss(self):
+        return type(self)._extra_loss is not SRFlexMatch._extra_loss
+
+    def _train_step_stage2_batched(self, x_lb, y_lb, idx_ulb, x_ulb_w, x_ulb_s):
+        """Stage 2 with a stochastic backbone: every row the step uses, in one forward and one backward (see
+        batch_stochastic_passes in the ctor).  Engine rows: [lb (pass 0) | strong (pass K) | strong (pass 0) | weak (pass 0..K)];
+        the first two groups (three when the algorithm adds a loss term on pass 0's strong logits) carry gradient."""
+        self._sr_wait()
+        net, dev = self._net(), x_lb.device
+        nl, nu, K = x_lb.shape[0], x_ulb_s.shape[0], self.sr_decay()
+        per = nl + 2 * nu
+        # DropPath multipliers for every (pass, row) the reference would draw, passes in order, rows in engine order (lb, s, w)
+        full = net._draw_drop_scale((K + 1) * per, dev).view(-1, 2, K + 1, per)
+        cols = [full[:, :, 0, :nl], full[:, :, K, nl:nl + nu], full[:, :, 0, nl:nl + nu]] + [full[:, :, k, nl + nu:] for k in range(K + 1)]
+        ds = torch.cat(cols, dim=2)
+        rows = nl + 2 * nu + (K + 1) * nu
+        xb = net.input_buffer((rows,) + tuple(x_lb.shape[1:]), dev)
+        torch.cat([x_lb, x_ulb_s, x_ulb_s] + [x_ulb_w] * (K + 1), out=xb)
+        extra = self._has_extra_loss()
+        gb = nl + (2 * nu if extra else nu)
+        lg, ft, h = net.forward_native(xb, grad_batch=gb, drop_scale=ds)
+        w0 = nl + 2 * nu
+        logits_lb, l_sK, logits_s0 = lg[:nl], lg[nl:nl + nu], lg[nl + nu:w0]
+        l_w = [lg[w0 + k * nu:w0 + (k + 1) * nu] for k in range(K + 1)]
+        f_w = [ft[w0 + k * nu:w0 + (k + 1) * nu] for k in range(K + 1)]
+        feat_dict = {"x_lb": ft[:nl], "x_ulb_w": f_w[0], "x_ulb_s": ft[nl + nu:w0]}
+        y_lb = y_lb.to(torch.long)
+        mask, pseudo_label = self._mask_and_pseudo(l_w[0], idx_ulb, first_pass=True)
+        for k in range(1, K + 1):
+            mask_dg, pseudo_dg = self._mask_and_pseudo(l_w[k], idx_ulb, first_pass=False)
+        reward_dg = self.rewarder(f_w[K], pseudo_dg)
+        dl = net.dlogits_buffer(gb, dev)
+        losses, mask2 = _ssl_loss_native(logits_lb, l_sK, y_lb, pseudo_dg, mask_dg, reward_dg.view(-1), self.lambda_u, dl[:nl], dl[nl:nl + nu])
+        if extra:
+            dl[nl + nu:].zero_()
+            self._extra_loss(losses, mask, logits_s0, dl[nl + nu:])
+        host = self._host_scalars(5 + nu)
+        host[:5].copy_(losses, non_blocking=True)
+        host[5:].copy_(mask, non_blocking=True)
+        copied = torch.cuda.Event()
+        copied.record()
+        if self.it % self.N_k == 0:
+            self.max_reward = -float("inf")
+            self._sr_update_async(f_w[0], pseudo_label)
+        net.backward_native(h, dl)
+        net.allreduce_grads_()
+        total_loss = _PrecomputedGrads.apply(losses[2], net, net.cls_token)
+        copied.synchronize()
+        sup, unsup, total, _ = host[:4].tolist()
+        out_dict = self.process_out_dict(loss=total_loss, feat=feat_dict)
+        log_dict = self.process_log_dict(sup_loss=sup, unsup_loss=unsup, total_loss=total, util_ratio=float(host[5:].mean()))
+        self._last_mask, self._last_mask2, self._last_pseudo_label = mask, mask2, pseudo_label
+        return out_dict, log_dict
 
     def _train_step_eager(self, x_lb, y_lb, idx_ulb, x_ulb_w, x_ulb_s):
         """Same step as train_step's autograd route (srflexmatch.py:107-217), with the backward launched in here."""
+        stochastic2 = self.it > self.start_timing and (self._stochastic_backbone() or not self.replay_deterministic_passes)
+        if stochastic2 and self.batch_stochastic_passes:
+            return self._train_step_stage2_batched(x_lb, y_lb, idx_ulb, x_ulb_w, x_ulb_s)
         self._sr_wait()
         net = self._net()
         dev = x_lb.device
         nl, nu = x_lb.shape[0], x_ulb_s.shape[0]
-        (logits_lb, logits_w, logits_s), (feats_lb, feats_w, feats_s), h0 = self._backbone_native(x_lb, x_ulb_w, x_ulb_s)
+        full = None
+        if stochastic2 and self._stochastic_backbone():   # same draw layout as the batched route: [depth, 2, pass, (lb, s, w) rows]
+            full = net._draw_drop_scale((self.sr_decay() + 1) * (nl + 2 * nu), dev).view(-1, 2, self.sr_decay() + 1, nl + 2 * nu)
+        (logits_lb, logits_w, logits_s), (feats_lb, feats_w, feats_s), h0 = self._backbone_native(
+            x_lb, x_ulb_w, x_ulb_s, drop_scale=None if full is None else full[:, :, 0].contiguous())
         feat_dict = {"x_lb": feats_lb, "x_ulb_w": feats_w, "x_ulb_s": feats_s}
         y_lb = y_lb.to(torch.long)
         mask, pseudo_label = self._mask_and_pseudo(logits_w, idx_ulb, first_pass=True)
@@ -250,7 +319,8 @@ class SRFlexMatch(AlgorithmBase):
             l_s = logits_s
             for k in range(K):
                 if stochastic:   # the reference re-runs the backbone every pass; only the last pass's graph survives
-                    (_, l_w, l_s), (_, f_w, _), h = self._backbone_native(x_lb, x_ulb_w, x_ulb_s, need_grad=(k == K - 1))
+                    (_, l_w, l_s), (_, f_w, _), h = self._backbone_native(
+                        x_lb, x_ulb_w, x_ulb_s, need_grad=(k == K - 1), drop_scale=None if full is None else full[:, :, k + 1].contiguous())
                     h_last = h if k == K - 1 else None
                 else:
                     l_w, f_w = logits_w, feats_w

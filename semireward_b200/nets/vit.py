@@ -242,9 +242,15 @@ class VisionTransformer(nn.Module):
             L.check(-2, "srw_vit_workspace_bytes")
         ws = self._acquire_ws(wbytes, dev)
         ds = drop_scale
-        if ds is None and self.training and max(self.drop_path_rates) > 0.0:
-            # one persistent buffer per workspace: a pass kept alive for backward keeps its own DropPath draw
-            ds = self._draw_drop_scale(B, dev, out=self._buf(("drop", ws.data_ptr()), (cfg.depth, 2, B), dev))
+        if self.training and max(self.drop_path_rates) > 0.0:
+            # one persistent buffer per workspace: a pass kept alive for backward keeps its own DropPath draw; explicit
+            # multipliers are copied into it so the engine sees a stable pointer (graph replay)
+            buf = self._buf(("drop", ws.data_ptr()), (cfg.depth, 2, B), dev)
+            if ds is None:
+                ds = self._draw_drop_scale(B, dev, out=buf)
+            elif ds.data_ptr() != buf.data_ptr():
+                buf.copy_(ds)
+                ds = buf
         lo, fe = self._buf("logits", (B, cfg.num_classes), dev), self._buf("feat", (B, cfg.embed_dim), dev)
         a = L.VitFwdArgs(cfg=C.pointer(cfg), params=pa, weight_planes=self._weight_planes().data_ptr(), x=xb.data_ptr(), batch=B,
                          grad_batch=grad_batch, drop_scale=L.ptr(ds), logits=lo.data_ptr(), feat=fe.data_ptr(),

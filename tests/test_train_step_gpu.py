@@ -115,16 +115,18 @@ def test_srflexmatch_steps_vs_oracle(depth, steps, over, resync, eager):
     print("mask values seen:", sorted(seen_mask_values))
 
 
-def test_stochastic_stage2_eager_matches_autograd_route():
-    """DropPath on: stage 2 re-runs the backbone K times (fresh DropPath draws per pass, like the reference) and two
-    graphs carry gradient (pass 0 -> sup loss, last pass -> unsup loss).  The eager backward and the autograd route must
-    give the same losses, masks and gradients from the same RNG state."""
+@pytest.mark.parametrize("algorithm", ["srflexmatch", "srfreematch"])
+def test_stochastic_stage2_batched_matches_sequential_passes(algorithm):
+    """DropPath on: stage 2 needs 1 + K backbone passes per step with fresh DropPath draws (like the reference), and two
+    graphs carry gradient (pass 0 -> sup loss [+ FreeMatch entropy], last pass -> unsup loss).  The batched route (all used
+    rows in ONE forward + ONE backward) must reproduce the sequential passes from the same RNG state: identical masks and
+    pseudo-labels, losses to fp32 rounding, gradients to 1e-4 relative (the wgrad split-K partition differs)."""
     import functools
     import semireward_b200 as S
     from semireward_b200 import detgen
-    cfg = small_cfg(num_train_iter=8, start_timing=1)   # it=3: K = max(8, 1 + 8/3) = 8
+    cfg = small_cfg(algorithm=algorithm, num_train_iter=8, start_timing=1, ent_loss_ratio=0.05, use_quantile=True)   # it=3: K = 8
     results = []
-    for eager in (True, False):
+    for batched in (True, False):
         args = S.get_config(cfg)
         builder = functools.partial(S.get_net_builder(args.net, False), depth=2, drop_path_rate=0.3)
         alg = S.get_algorithm(args, builder, None, None)
@@ -134,7 +136,7 @@ def test_stochastic_stage2_eager_matches_autograd_route():
                     p.copy_(torch.from_numpy(detgen.fill_param(prefix + n, p.shape, 0)))
         alg.model = alg.model.cuda(args.gpu).train()
         alg.rewarder, alg.generator = alg.rewarder.cuda(args.gpu), alg.generator.cuda(args.gpu)
-        alg.eager_backward = eager
+        alg.batch_stochastic_passes = batched
         tap = _grad_tap(alg)
         torch.manual_seed(123)
         rec = []
@@ -143,15 +145,16 @@ def test_stochastic_stage2_eager_matches_autograd_route():
             alg.out_dict, alg.log_dict = alg.train_step(**alg.process_batch(**batch_tensors(cfg, it)))
             alg.call_hook("after_train_step")
             torch.cuda.synchronize()
-            rec.append((dict(alg.log_dict), alg._last_mask.clone(), alg._last_mask2.clone(), {n: g.clone() for n, g in tap.items()}))
+            rec.append((dict(alg.log_dict), alg._last_mask.clone(), alg._last_mask2.clone(), alg._last_pseudo_label.clone(),
+                        {n: g.clone() for n, g in tap.items()}))
         results.append(rec)
-    for (ld_a, m_a, m2_a, g_a), (ld_b, m_b, m2_b, g_b) in zip(*results):
+    for (ld_a, m_a, m2_a, p_a, g_a), (ld_b, m_b, m2_b, p_b, g_b) in zip(*results):
         for k in ("train/sup_loss", "train/unsup_loss", "train/total_loss", "train/util_ratio"):
-            assert abs(ld_a[k] - ld_b[k]) < 1e-6, (k, ld_a[k], ld_b[k])
-        assert torch.equal(m_a, m_b) and torch.equal(m2_a, m2_b)
+            assert abs(ld_a[k] - ld_b[k]) < 2e-5 * max(1.0, abs(ld_b[k])), (k, ld_a[k], ld_b[k])
+        assert torch.equal(m_a, m_b) and torch.equal(m2_a, m2_b) and torch.equal(p_a, p_b)
         for n in g_a:
             sc = g_b[n].abs().max().item()
-            assert (g_a[n] - g_b[n]).abs().max().item() <= 1e-5 * max(sc, 1e-20), n
+            assert (g_a[n] - g_b[n]).abs().max().item() <= 1e-4 * max(sc, 1e-20), n
 
 
 @pytest.mark.parametrize("algorithm,over", [
