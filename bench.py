@@ -188,12 +188,12 @@ def main_native(a):
     def step_device(i):
         alg.it = it0 + i
         alg.out_dict, alg.log_dict = alg.train_step(**dbatches[i % n_batches])
-        alg.call_hook("after_train_step")
+        alg.call_hook("after_train_step", "ParamUpdateHook")   # the metric excludes the EMA / logging hooks
 
     def step_e2e(i):
         alg.it = it0 + i
         alg.out_dict, alg.log_dict = alg.train_step(**alg.process_batch(**hbatches[i % n_batches]))
-        alg.call_hook("after_train_step")
+        alg.call_hook("after_train_step", "ParamUpdateHook")   # the metric excludes the EMA / logging hooks
 
     def barrier():
         if world > 1:

@@ -345,6 +345,12 @@ typedef struct {
   int64_t* pseudo; int pseudo_from_probs;
   float* mask;                         /* [B] out: the soft weights */
   float* max_probs;                    /* [B] out (may be NULL): the max of the probabilities the weights were formed from */
+  /* data parallel (C4: dist_align.py:40-42, srsoftmatch/utils.py:33-34): DistAlign averages every rank's probabilities,
+   * the weighting statistics run over every rank's (aligned) max probabilities.  phase 0 = one launch (world size 1);
+   * phase 1 = softmax + pseudo-labels (max_probs = un-aligned row max); all-gather probs_w -> probs_all [B_all, C];
+   * phase 2 (dist_align only) = DistAlign update + aligned row max -> max_probs; all-gather max_probs -> maxp_all [n_all];
+   * phase 3 = EMA of mean / variance over maxp_all + weights of the local rows (from max_probs). */
+  int phase; const float* probs_all; int B_all; const float* maxp_all; int n_all;
 } srw_softmatch_mask_args;
 int srw_softmatch_mask(const srw_softmatch_mask_args* a, void* stream);
 
@@ -376,6 +382,13 @@ typedef struct {
   int decoupled;                /* 1 = AdamW, 0 = Adam with L2 (grad += wd * p) */
 } srw_adamw_args;
 int srw_adamw_step(const srw_adamw_args* a, void* stream);
+
+/* ---- EMA of the parameters: EMAHook.after_train_step / EMA.update (core/hooks/ema.py:20-24, core/utils/misc.py:152-155) ---- */
+/* shadow = (1 - decay) * param + decay * shadow over many tensors in one launch (bit-exact with the reference's fp32 tensor
+ * expression).  The table lives in device memory; first_block as in srw_adamw_row.  HBM-bound: 12 B per parameter. */
+typedef struct { const float* param; float* shadow; int64_t numel; int64_t first_block; } srw_ema_row;
+typedef struct { int num_tensors; int64_t total_blocks; const srw_ema_row* table; double decay; } srw_ema_args;
+int srw_ema_step(const srw_ema_args* a, void* stream);
 
 #ifdef __cplusplus
 }

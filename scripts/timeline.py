@@ -40,7 +40,7 @@ def main():
     def step(i):
         alg.it = 1 + i
         alg.out_dict, alg.log_dict = alg.train_step(**batches[i % 4])
-        alg.call_hook("after_train_step")
+        alg.call_hook("after_train_step", "ParamUpdateHook")   # the metric excludes the EMA / logging hooks
 
     for i in range(5):
         step(i)

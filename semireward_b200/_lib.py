@@ -129,7 +129,7 @@ class SoftMatchMaskArgs(C.Structure):
     _fields_ = [("B", i32), ("num_classes", i32), ("logits_w", vp), ("ld_logits", i64), ("momentum", C.c_double), ("n_sigma", i32),
                 ("dist_align", i32), ("da_p_model", vp), ("da_p_target", vp), ("da_initialized", vp), ("prob_max_mu_t", vp),
                 ("prob_max_var_t", vp), ("probs_w", vp), ("probs_aligned", vp), ("pseudo", vp), ("pseudo_from_probs", i32),
-                ("mask", vp), ("max_probs", vp)]
+                ("mask", vp), ("max_probs", vp), ("phase", i32), ("probs_all", vp), ("B_all", i32), ("maxp_all", vp), ("n_all", i32)]
 
 
 class AdamWRow(C.Structure):
@@ -140,6 +140,14 @@ class AdamWRow(C.Structure):
 class AdamWArgs(C.Structure):
     _fields_ = [("num_tensors", i32), ("total_blocks", i64), ("table", vp), ("lr_factor", f64), ("beta1", f64), ("beta2", f64),
                 ("eps", f64), ("step", i32), ("decoupled", i32)]
+
+
+class EmaRow(C.Structure):
+    _fields_ = [("param", vp), ("shadow", vp), ("numel", i64), ("first_block", i64)]
+
+
+class EmaArgs(C.Structure):
+    _fields_ = [("num_tensors", i32), ("total_blocks", i64), ("table", vp), ("decay", f64)]
 
 
 ADAMW_BLOCK_ELEMS = 4096
@@ -185,6 +193,7 @@ SYMBOLS = [
     ("srw_freematch_entropy", i32, [C.POINTER(FreeMatchEntropyArgs), vp]),
     ("srw_softmatch_mask", i32, [C.POINTER(SoftMatchMaskArgs), vp]),
     ("srw_adamw_step", i32, [C.POINTER(AdamWArgs), vp]),
+    ("srw_ema_step", i32, [C.POINTER(EmaArgs), vp]),
 ]
 
 _lib = None

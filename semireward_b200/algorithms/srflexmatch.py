@@ -155,8 +155,10 @@ class SRFlexMatch(AlgorithmBase):
     # -- pieces -----------------------------------------------------------------------------------
     def _backbone(self, x_lb, x_ulb_w, x_ulb_s, need_grad=True):
         """-> logits/feats of (lb, weak, strong).  Gradient rows (lb, strong) go first inside the engine."""
-        if not self.use_cat:
-            raise NotImplementedError("use_cat: False (BERT/HuBERT configs) is a 'next' row (SURVEY.md §8f)")
+        # use_cat: False makes the reference call the model three times (lb, strong with grad; weak under no_grad,
+        # srflexmatch.py:119-130).  For a LayerNorm backbone rows do not interact, so the one batched call below computes the
+        # same numbers; the weak rows carry no gradient either way.  (The BERT / HuBERT wrappers that need use_cat: False for
+        # their dict / ragged inputs are not built: get_net_builder raises for them.)
         nl, nu = x_lb.shape[0], x_ulb_s.shape[0]
         inputs = torch.cat((x_lb, x_ulb_s, x_ulb_w))
         if need_grad:
@@ -230,8 +232,10 @@ class SRFlexMatch(AlgorithmBase):
     def _backbone_native(self, x_lb, x_ulb_w, x_ulb_s, need_grad=True, drop_scale=None):
         """Autograd-free pass on the net's persistent buffers -> (logits, feats, handle), split as (lb, weak, strong).
         drop_scale: DropPath multipliers [depth, 2, nl + 2 nu] in engine row order (lb, strong, weak), or None to draw."""
-        if not self.use_cat:
-            raise NotImplementedError("use_cat: False (BERT/HuBERT configs) is a 'next' row (SURVEY.md §8f)")
+        # use_cat: False makes the reference call the model three times (lb, strong with grad; weak under no_grad,
+        # srflexmatch.py:119-130).  For a LayerNorm backbone rows do not interact, so the one batched call below computes the
+        # same numbers; the weak rows carry no gradient either way.  (The BERT / HuBERT wrappers that need use_cat: False for
+        # their dict / ragged inputs are not built: get_net_builder raises for them.)
         net = self._net()
         nl, nu = x_lb.shape[0], x_ulb_s.shape[0]
         xb = net.input_buffer((nl + 2 * nu,) + tuple(x_lb.shape[1:]), x_lb.device)

@@ -14,7 +14,7 @@ from inspect import signature
 
 import torch
 
-from .hooks import Hook, ParamUpdateHook
+from .hooks import EMAHook, Hook, ParamUpdateHook
 from .optim import get_cosine_schedule_with_warmup, get_optimizer
 
 
@@ -78,6 +78,7 @@ class AlgorithmBase:
 
     def set_hooks(self):
         self.register_hook(ParamUpdateHook(), None, "HIGHEST")
+        self.register_hook(EMAHook(), None, "HIGH")   # algorithmbase.py:229-230: parameter update first, then the EMA
 
     # -- hook protocol ----------------------------------------------------------------------------
     _PRIORITY = dict(HIGHEST=0, VERY_HIGH=10, HIGH=30, ABOVE_NORMAL=40, NORMAL=50, BELOW_NORMAL=60, LOW=70, VERY_LOW=90, LOWEST=100)

@@ -51,6 +51,86 @@ class ParamUpdateHook(Hook):
             algorithm.log_dict["train/run_time"] = algorithm.start_run.elapsed_time(algorithm.end_run) / 1000.0
 
 
+class EMA:
+    """EMA of the model parameters with the reference's interface (semilearn/core/utils/misc.py:131-164: register / load /
+    update / apply_shadow / restore, `shadow` dict by parameter name).  The shadow tensors ARE the parameters of
+    `ema_model`, so after update() the EMA model is current without the reference's two load_state_dict passes per step
+    (core/hooks/ema.py:23-24); update() is one srw_ema_step launch over all tensors."""
+
+    def __init__(self, model, decay, ema_model=None):
+        self.model, self.decay, self.ema_model = model, float(decay), ema_model
+        self.shadow, self.backup, self._table = {}, {}, None
+
+    def _named(self):
+        m = self.model.module if hasattr(self.model, "module") else self.model
+        return list(m.named_parameters())
+
+    def register(self):
+        named = self._named()
+        if self.ema_model is not None:
+            em = dict(self.ema_model.named_parameters())
+            for n, p in named:
+                if em[n].device != p.device:
+                    em[n].data = em[n].data.to(p.device)
+                em[n].data.copy_(p.data)
+                self.shadow[n] = em[n].data
+        else:
+            for n, p in named:
+                self.shadow[n] = p.data.clone()
+        self._table = None
+
+    def load(self, ema_model):
+        for n, p in ema_model.named_parameters():
+            self.shadow[n].copy_(p.data.to(self.shadow[n].device))
+
+    def _build(self):
+        named = self._named()
+        rows = (L.EmaRow * len(named))()
+        blk = 0
+        for i, (n, p) in enumerate(named):
+            sh = self.shadow[n]
+            assert p.is_contiguous() and sh.is_contiguous() and p.dtype == torch.float32
+            rows[i].param, rows[i].shadow, rows[i].numel, rows[i].first_block = p.data_ptr(), sh.data_ptr(), p.numel(), blk
+            blk += (p.numel() + L.ADAMW_BLOCK_ELEMS - 1) // L.ADAMW_BLOCK_ELEMS
+        dev = named[0][1].device
+        host = torch.empty(C.sizeof(rows), dtype=torch.uint8)
+        C.memmove(host.data_ptr(), C.addressof(rows), C.sizeof(rows))
+        self._table = host.to(dev)
+        self._n, self._blocks = len(named), blk
+        self._key = tuple(p.data_ptr() for _, p in named)
+
+    @torch.no_grad()
+    def update(self):
+        if self._table is None or self._key != tuple(p.data_ptr() for _, p in self._named()):
+            self._build()
+        a = L.EmaArgs(num_tensors=self._n, total_blocks=self._blocks, table=self._table.data_ptr(), decay=self.decay)
+        L.check(L.load().srw_ema_step(C.byref(a), L.stream_ptr()), "srw_ema_step")
+
+    def apply_shadow(self):
+        for n, p in self._named():
+            self.backup[n] = p.data
+            p.data = self.shadow[n]
+
+    def restore(self):
+        for n, p in self._named():
+            p.data = self.backup[n]
+        self.backup = {}
+
+
+class EMAHook(Hook):
+    """semilearn/core/hooks/ema.py:8-24: creates algorithm.ema in before_run, updates it after every train step.  The
+    shadow lives in algorithm.ema_model's parameters (see EMA)."""
+
+    def before_run(self, algorithm):
+        algorithm.ema = EMA(algorithm.model, algorithm.ema_m, ema_model=algorithm.ema_model)
+        algorithm.ema.register()
+
+    def after_train_step(self, algorithm):
+        if getattr(algorithm, "ema", None) is None:
+            self.before_run(algorithm)
+        algorithm.ema.update()
+
+
 class PseudoLabelingHook(Hook):
     """gen_ulb_targets: hard labels = argmax; soft labels = softmax(logits / T).  On the fused path the hard labels come
     out of srw_flexmatch_mask (`algorithm._last_pseudo`) so no extra kernel runs; the generic branch stays available."""
@@ -212,12 +292,12 @@ class SoftMatchWeightingHook(Hook):
         self.prob_max_var_t = torch.ones(1, dtype=torch.float32, device=dev)
 
     @torch.no_grad()
-    def masking(self, algorithm, logits_x_ulb, softmax_x_ulb=True, dist_align=False, pseudo_from_probs=False, *args, **kwargs):
+    def masking(self, algorithm, logits_x_ulb, softmax_x_ulb=True, dist_align=False, pseudo_from_probs=False, gathered=None,
+                *args, **kwargs):
+        """gathered (testing hook): callable(kind, local_tensor) -> tensor standing in for the all_gather over ranks
+        (kind 'probs' -> [W*B, C], 'max_probs' -> [W*B])."""
         if not softmax_x_ulb:
             raise RuntimeError("fused SoftMatch hook takes raw logits (softmax and DistAlign are fused into the kernel)")
-        if getattr(algorithm, "distributed", False) and getattr(algorithm, "world_size", 1) > 1:
-            raise NotImplementedError("srsoftmatch under data parallelism needs the all-gathered probabilities "
-                                      "(C4 in SURVEY.md §2.1): not built yet")
         lw = _contig_logits(logits_x_ulb)
         dev = lw.device
         for n in ("prob_max_mu_t", "prob_max_var_t"):
@@ -234,8 +314,31 @@ class SoftMatchWeightingHook(Hook):
                                 da_p_target=L.ptr(da.p_target) if da else None, da_initialized=L.ptr(da._initialized) if da else None,
                                 prob_max_mu_t=self.prob_max_mu_t.data_ptr(), prob_max_var_t=self.prob_max_var_t.data_ptr(),
                                 probs_w=probs.data_ptr(), probs_aligned=None, pseudo=pseudo.data_ptr(),
-                                pseudo_from_probs=int(bool(pseudo_from_probs)), mask=mask.data_ptr(), max_probs=None)
-        L.check(L.load().srw_softmatch_mask(C.byref(a), L.stream_ptr()), "srw_softmatch_mask")
+                                pseudo_from_probs=int(bool(pseudo_from_probs)), mask=mask.data_ptr(), max_probs=None,
+                                phase=0, probs_all=None, B_all=0, maxp_all=None, n_all=0)
+        launch = lambda: L.check(L.load().srw_softmatch_mask(C.byref(a), L.stream_ptr()), "srw_softmatch_mask")  # noqa: E731
+        distributed = bool(getattr(algorithm, "distributed", False)) and getattr(algorithm, "world_size", 1) > 1
+        if gathered is not None or distributed:
+            # data parallel (C4): DistAlign and the weighting statistics see every rank's rows (concat_all_gather,
+            # dist_align.py:40-42, srsoftmatch/utils.py:33-34); masks are formed for the local rows
+            import torch.distributed as dist
+
+            def gather(kind, t):
+                if gathered is not None:
+                    return gathered(kind, t)
+                out = torch.empty((dist.get_world_size() * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+                dist.all_gather_into_tensor(out, t)
+                return out
+            maxp = torch.empty(B, dtype=torch.float32, device=dev)
+            a.max_probs, a.phase = maxp.data_ptr(), 1
+            launch()
+            if da is not None:
+                probs_all = gather("probs", probs)
+                a.phase, a.probs_all, a.B_all = 2, probs_all.data_ptr(), probs_all.shape[0]
+                launch()
+            maxp_all = gather("max_probs", maxp)
+            a.phase, a.maxp_all, a.n_all = 3, maxp_all.data_ptr(), maxp_all.shape[0]
+        launch()
         algorithm._last_pseudo = (probs, pseudo)
         algorithm._last_probs = probs
         return mask

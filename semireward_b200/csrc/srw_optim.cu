@@ -94,9 +94,43 @@ __global__ void __launch_bounds__(256) adamw_kernel(const srw_adamw_row* __restr
     }
   }
 }
+// EMA of the parameters (EMA.update, semilearn/core/utils/misc.py:152-155): shadow = (1 - d) * p + d * shadow, two rounded
+// products and one rounded sum like the reference's tensor expression (bit-exact).  Same chunk-per-CTA table walk as AdamW.
+__global__ void __launch_bounds__(256) ema_kernel(const srw_ema_row* __restrict__ table, int num_tensors, float d, float omd) {
+  int lo = 0, hi = num_tensors - 1;
+  const int64_t blk = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].first_block <= blk) lo = mid; else hi = mid - 1;
+  }
+  const srw_ema_row row = table[lo];
+  const int64_t base = (blk - row.first_block) * SRW_ADAMW_BLOCK_ELEMS;
+  const int64_t end = min(row.numel, base + SRW_ADAMW_BLOCK_ELEMS);
+  const bool vec = ((row.numel & 3) == 0) && ((reinterpret_cast<uintptr_t>(row.param) | reinterpret_cast<uintptr_t>(row.shadow)) & 15) == 0;
+  if (vec) {
+    for (int64_t i = base + threadIdx.x * 4; i < end; i += 256 * 4) {
+      const float4 p = *reinterpret_cast<const float4*>(row.param + i);
+      float4 s = *reinterpret_cast<float4*>(row.shadow + i);
+      s.x = __fadd_rn(__fmul_rn(omd, p.x), __fmul_rn(d, s.x)); s.y = __fadd_rn(__fmul_rn(omd, p.y), __fmul_rn(d, s.y));
+      s.z = __fadd_rn(__fmul_rn(omd, p.z), __fmul_rn(d, s.z)); s.w = __fadd_rn(__fmul_rn(omd, p.w), __fmul_rn(d, s.w));
+      *reinterpret_cast<float4*>(row.shadow + i) = s;
+    }
+  } else {
+    for (int64_t i = base + threadIdx.x; i < end; i += 256) row.shadow[i] = __fadd_rn(__fmul_rn(omd, row.param[i]), __fmul_rn(d, row.shadow[i]));
+  }
+}
 }  // namespace srw
 
 using namespace srw;
+
+extern "C" int srw_ema_step(const srw_ema_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SRW_REQUIRE(a && a->table && a->num_tensors > 0 && a->total_blocks > 0, "srw_ema_step: bad args");
+  ema_kernel<<<(unsigned)a->total_blocks, 256, 0, stream>>>(a->table, a->num_tensors, (float)a->decay, (float)(1.0 - a->decay));
+  g_launches++;
+  SRW_LAUNCH_CHECK();
+  return SRW_OK;
+}
 
 extern "C" int srw_adamw_step(const srw_adamw_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

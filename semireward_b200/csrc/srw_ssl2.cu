@@ -303,26 +303,32 @@ __global__ void __launch_bounds__(SSL2_THREADS) freematch_entropy_kernel(const s
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SSL2_THREADS) softmatch_mask_kernel(const srw_softmatch_mask_args a, float m_f, float om_f, double om_d) {
   __shared__ float s_maxp[SSL2_MAX_ROWS];
-  __shared__ float red[32];
   __shared__ float s_stat[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int C = a.num_classes, B = a.B;
-  for (int b = warp; b < B; b += nw) {
-    float bp; int ap, al;
-    warp_softmax_row(a.logits_w + (int64_t)b * a.ld_logits, C, lane, a.probs_w + (int64_t)b * C, bp, ap, al);
-    if (lane == 0) {
-      s_maxp[b] = bp;
-      a.pseudo[b] = a.pseudo_from_probs ? ap : al;
+  if (a.phase <= 1) {   // softmax of the local rows
+    for (int b = warp; b < B; b += nw) {
+      float bp; int ap, al;
+      warp_softmax_row(a.logits_w + (int64_t)b * a.ld_logits, C, lane, a.probs_w + (int64_t)b * C, bp, ap, al);
+      if (lane == 0) {
+        s_maxp[b] = bp;
+        a.pseudo[b] = a.pseudo_from_probs ? ap : al;
+        if (a.phase == 1 && a.max_probs) a.max_probs[b] = bp;
+      }
     }
+    if (a.phase == 1) return;
+    __syncthreads();
   }
-  __syncthreads();
-  if (a.dist_align) {
-    // DistAlignEMAHook.update_p: p_model = mean(probs) on the first call, EMA afterwards (dist_align.py:44-48)
+  if (a.dist_align && (a.phase == 0 || a.phase == 2)) {
+    // DistAlignEMAHook.update_p: p_model = mean(probs) on the first call, EMA afterwards (dist_align.py:44-48); under data
+    // parallelism the mean runs over every rank's probabilities (probs_all, dist_align.py:40-42)
+    const float* up = a.probs_all ? a.probs_all : a.probs_w;
+    const int BU = a.probs_all ? a.B_all : B;
     const int first = *a.da_initialized == 0;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       float s = 0.f;
-      for (int b = 0; b < B; ++b) s += a.probs_w[(int64_t)b * C + c];
-      const float mean = s / (float)B;
+      for (int b = 0; b < BU; ++b) s += up[(int64_t)b * C + c];
+      const float mean = s / (float)BU;
       a.da_p_model[c] = first ? mean : __fadd_rn(__fmul_rn(a.da_p_model[c], m_f), __fmul_rn(mean, om_f));
     }
     __syncthreads();
@@ -341,18 +347,28 @@ __global__ void __launch_bounds__(SSL2_THREADS) softmatch_mask_kernel(const srw_
       mx = warp_max(mx);
       if (a.probs_aligned)
         for (int c = lane; c < C; c += 32) a.probs_aligned[(int64_t)b * C + c] /= s;
-      if (lane == 0) s_maxp[b] = mx / s;
+      if (lane == 0) {
+        s_maxp[b] = mx / s;
+        if (a.phase == 2 && a.max_probs) a.max_probs[b] = mx / s;
+      }
     }
+    if (a.phase == 2) return;
     __syncthreads();
   }
-  // SoftMatchWeightingHook.update (per_class = False): EMA of mean / unbiased variance of max_probs
+  if (a.phase == 3)
+    for (int b = threadIdx.x; b < B; b += blockDim.x) s_maxp[b] = a.max_probs[b];
+  __syncthreads();
+  // SoftMatchWeightingHook.update (per_class = False): EMA of mean / unbiased variance of max_probs (of every rank's rows
+  // under data parallelism: maxp_all, srsoftmatch/utils.py:33-34)
   if (threadIdx.x == 0) {
+    const float* vals = a.maxp_all ? a.maxp_all : s_maxp;
+    const int n = a.maxp_all ? a.n_all : B;
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s += s_maxp[b];
-    const float mu = s / (float)B;
+    for (int b = 0; b < n; ++b) s += vals[b];
+    const float mu = s / (float)n;
     double q = 0.0;
-    for (int b = 0; b < B; ++b) { const double d = (double)s_maxp[b] - (double)mu; q += d * d; }
-    const float var = B > 1 ? (float)(q / (double)(B - 1)) : NAN;   // torch.var(unbiased=True) of one element is nan
+    for (int b = 0; b < n; ++b) { const double d = (double)vals[b] - (double)mu; q += d * d; }
+    const float var = n > 1 ? (float)(q / (double)(n - 1)) : NAN;   // torch.var(unbiased=True) of one element is nan
     // m * t + (1 - m) * x.item(): fp32 tensor product + python double product rounded to fp32 by the tensor add
     const float mu_t = __fadd_rn(__fmul_rn(m_f, *a.prob_max_mu_t), (float)(om_d * (double)mu));
     const float var_t = __fadd_rn(__fmul_rn(m_f, *a.prob_max_var_t), (float)(om_d * (double)var));
@@ -365,9 +381,8 @@ __global__ void __launch_bounds__(SSL2_THREADS) softmatch_mask_kernel(const srw_
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     const float d = fminf(__fsub_rn(s_maxp[b], mu_t), 0.0f);
     a.mask[b] = expf(-__fdiv_rn(__fmul_rn(d, d), denom));
-    if (a.max_probs) a.max_probs[b] = s_maxp[b];
+    if (a.max_probs && a.phase == 0) a.max_probs[b] = s_maxp[b];
   }
-  (void)red;
 }
 
 }  // namespace srw
@@ -407,6 +422,8 @@ extern "C" int srw_softmatch_mask(const srw_softmatch_mask_args* a, void* stream
   SRW_REQUIRE(a && a->logits_w && a->prob_max_mu_t && a->prob_max_var_t && a->probs_w && a->pseudo && a->mask, "srw_softmatch_mask: null pointer");
   SRW_REQUIRE(!a->dist_align || (a->da_p_model && a->da_p_target && a->da_initialized), "srw_softmatch_mask: dist_align needs its state");
   SRW_REQUIRE(a->B > 0 && a->B <= SSL2_MAX_ROWS && a->num_classes > 0 && a->n_sigma > 0, "srw_softmatch_mask: 0 < B <= %d required", SSL2_MAX_ROWS);
+  SRW_REQUIRE(a->phase >= 0 && a->phase <= 3 && (a->phase == 0 || a->max_probs), "srw_softmatch_mask: phases 1-3 need max_probs");
+  SRW_REQUIRE((!a->probs_all || a->B_all >= a->B) && (!a->maxp_all || a->n_all >= a->B), "srw_softmatch_mask: gathered inputs smaller than the local batch");
   const float m_f = (float)a->momentum, om_f = (float)(1.0 - a->momentum);
   softmatch_mask_kernel<<<1, SSL2_THREADS, 0, stream>>>(*a, m_f, om_f, 1.0 - a->momentum);
   g_launches++;

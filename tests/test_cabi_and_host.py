@@ -88,7 +88,7 @@ def test_algorithm_construction_and_process_batch_filter():
     if torch.cuda.is_available():
         pytest.skip("CPU-only construction test")
     alg = S.get_algorithm(args, functools.partial(S.get_net_builder(args.net), depth=1), None, None)
-    assert list(alg.hooks_dict) == ["ParamUpdateHook", "PseudoLabelingHook", "MaskingHook"]
+    assert list(alg.hooks_dict) == ["ParamUpdateHook", "EMAHook", "PseudoLabelingHook", "MaskingHook"]   # priority order (algorithmbase.py:226-240)
     assert alg.registered_hook("MaskingHook") and not alg.registered_hook("DistAlignHook")
     import inspect
     assert list(inspect.signature(alg.train_step).parameters) == ["x_lb", "y_lb", "idx_ulb", "x_ulb_w", "x_ulb_s"]

@@ -236,3 +236,70 @@ def test_freematch_mask_data_parallel_view():
         assert (hook.p_model.cpu() - st.p_model).abs().max().item() < 2e-7
         assert (hook.label_hist.cpu() - st.label_hist).abs().max().item() < 2e-7
         assert torch.equal(mask.cpu(), ref_mask), f"call {call}"
+
+
+def test_ema_hook_matches_reference_expression():
+    """EMAHook / EMA.update (core/hooks/ema.py:20-24, misc.py:152-155): shadow = (1 - d) * p + d * shadow over every
+    parameter in one launch, bit-exact with the tensor expression; the shadow is ema_model's parameters."""
+    from semireward_b200.core.hooks import EMA
+    from semireward_b200.nets import vit_small_patch2_32
+    torch.manual_seed(0)
+    model = vit_small_patch2_32(num_classes=100, depth=2).cuda()
+    ema_model = vit_small_patch2_32(num_classes=100, depth=2)
+    ema = EMA(model, 0.999, ema_model=ema_model)
+    ema.register()
+    ref = {n: p.detach().clone() for n, p in model.named_parameters()}
+    for step in range(3):
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(torch.randn_like(p) * 0.01)
+        ema.update()
+        for n, p in model.named_parameters():
+            ref[n] = (1.0 - 0.999) * p.data + 0.999 * ref[n]
+    torch.cuda.synchronize()
+    for n, p in ema_model.named_parameters():
+        assert p.is_cuda and torch.equal(p.data, ref[n]), n
+        assert ema.shadow[n].data_ptr() == p.data_ptr()
+    keep = {n: p.data for n, p in model.named_parameters()}
+    ema.apply_shadow()
+    assert all(p.data.data_ptr() == ema.shadow[n].data_ptr() for n, p in model.named_parameters())
+    ema.restore()
+    assert all(p.data.data_ptr() == keep[n].data_ptr() for n, p in model.named_parameters())
+
+
+def test_softmatch_mask_data_parallel_view():
+    """C4 for SoftMatch (dist_align.py:40-42, srsoftmatch/utils.py:33-34): DistAlign's EMA and the mean / variance EMA
+    integrate the rows of ALL ranks, the weights are formed for the local rows.  Emulated in one process for 'rank 1' of 2
+    through the hook's `gathered` testing hook, against the reference state machines fed the same way."""
+    from oracle import ssl_oracle as O
+    from semireward_b200 import detgen
+    from semireward_b200.core.hooks import DistAlignEMAHook, SoftMatchWeightingHook
+    B, C, W, rank = 8, 100, 2, 1
+    st, da = O.SoftMatchState(C, 2, 0.9), O.DistAlignState(C, 0.9)
+    hook, dah = SoftMatchWeightingHook(C, 2, 0.9, device="cuda"), DistAlignEMAHook(C, 0.9, device="cuda")
+    alg = _Alg()
+    alg.hooks_dict["DistAlignHook"] = dah
+    local = slice(rank * B, (rank + 1) * B)
+    for call in range(5):
+        logits_all = torch.from_numpy(detgen.normal("sm_dp_logits", (W * B, C), 110 + call)) * (1.0 + 0.5 * call)
+        probs_all = torch.softmax(logits_all, dim=-1)
+        align = call % 2 == 0
+        used_all = da.dist_align(probs_all) if align else probs_all      # every rank aligns with the same (gathered) p_model
+        maxp_all = used_all.max(dim=-1)[0]
+        # reference update() on the gathered rows, weights for the local rows (srsoftmatch/utils.py:31-77)
+        mu, var = torch.mean(maxp_all).item(), torch.var(maxp_all, unbiased=True).item()
+        st.prob_max_mu_t = st.m * st.prob_max_mu_t + (1 - st.m) * mu
+        st.prob_max_var_t = st.m * st.prob_max_var_t + (1 - st.m) * var
+        ref_w = torch.exp(-((torch.clamp(maxp_all[local] - st.prob_max_mu_t, max=0.0) ** 2) / (2 * st.prob_max_var_t / (st.n_sigma ** 2))))
+
+        def gathered(kind, t):
+            full = (probs_all if kind == "probs" else maxp_all).cuda().clone()
+            full[local] = t     # the local rows come from the kernel itself
+            return full
+        w = hook.masking(alg, logits_all[local].cuda(), softmax_x_ulb=True, dist_align=align, pseudo_from_probs=not align, gathered=gathered)
+        torch.cuda.synchronize()
+        assert abs(hook.prob_max_mu_t.item() - float(st.prob_max_mu_t)) < 1e-6
+        assert abs(hook.prob_max_var_t.item() - float(st.prob_max_var_t)) < 1e-6
+        if align:
+            assert (dah.p_model.cpu() - da.p_model).abs().max().item() < 1e-6
+        assert (w.cpu() - ref_w).abs().max().item() < 2e-6, f"call {call}"
