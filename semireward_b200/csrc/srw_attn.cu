@@ -65,11 +65,14 @@ __device__ __forceinline__ void store_out16(__nv_bfloat16* hi_ptr, int64_t plane
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+unsigned long long* g_attn_trace = nullptr;
+
 struct AttnFwdParams {
   int B, N, H, NP;        // NP = N rounded up to 16 (<= 272)
   float scale;            // head_dim^-0.5
   __nv_bfloat16* o; int64_t ld_o, o_ps;
   float* lse;             // [B, H, N] natural-log units: scale*max + log(sum)
+  unsigned long long* trace;   // debug (srw_attn_set_trace): per CTA 32 clock64 stamps, see scripts/attn_trace.py; NULL in production
 };
 
 constexpr int FWD_THREADS = 512 + 32;   // 16 softmax warps (4 per TMEM lane quarter, 16 columns each) + 1 TMA/MMA warp
@@ -105,6 +108,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int row0 = b * p.N;           // first token row of this image in the [B*N, 3D] qkv matrix
   const int nchunks = (NP + 63) / 64;
   const int ntiles = (p.N + 127) / 128;
+  unsigned long long* tr = p.trace ? p.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 32 : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
 
   if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -140,9 +145,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tma_load_3d(smem, &tmap_q, bar_q, h * HD, row0, 0);
       tma_load_3d(smem + ROW_TILE_BYTES, &tmap_q, bar_q, h * HD, row0, 1);
       mbar_wait(bar_kv, 0);
-      const uint32_t q_hi = smem_u32(smem), q_lo = q_hi + ROW_TILE_BYTES;
-      const uint32_t k_hi = smem_u32(smem + off_k), k_lo = k_hi + kv_plane;
-      const uint32_t v_hi = smem_u32(smem + off_v), v_lo = v_hi + kv_plane;
+      if (tr) tr[1] = clock64();                       // K, V landed
+      // The single issuing thread is the bottleneck of the small (N = 64) PV MMAs if it rebuilds four 64-bit descriptors per
+      // MMA triple: build each base descriptor once; a step along K (or to the next chunk) only adds (bytes >> 4) to the
+      // 14-bit start-address field (no carry: everything lives below 227 KB).
+      const uint64_t dq_hi = umma_smem_desc(smem_u32(smem), 16, 1024), dq_lo = umma_smem_desc(smem_u32(smem) + ROW_TILE_BYTES, 16, 1024);
+      const uint64_t dk_hi = umma_smem_desc(smem_u32(smem + off_k), 16, 1024), dk_lo = umma_smem_desc(smem_u32(smem + off_k) + kv_plane, 16, 1024);
+      const uint64_t dv_hi = umma_smem_desc(smem_u32(smem + off_v), 1024, 1024), dv_lo = umma_smem_desc(smem_u32(smem + off_v) + kv_plane, 1024, 1024);
+      // P buffer 0 = region B (offset 32 KiB), buffer 1 = region A (offset 0)
+      const uint64_t dp_hi0 = umma_smem_desc(smem_u32(smem) + 2 * ROW_TILE_BYTES, 16, 1024), dp_hi1 = umma_smem_desc(smem_u32(smem), 16, 1024);
+      const uint64_t dp_lo0 = umma_smem_desc(smem_u32(smem) + 3 * ROW_TILE_BYTES, 16, 1024), dp_lo1 = umma_smem_desc(smem_u32(smem) + ROW_TILE_BYTES, 16, 1024);
       const uint32_t idesc_pv = umma_idesc_bf16(HD, 0, 1);
       const int n1 = NP <= 256 ? NP : 256, n2 = NP - n1;
       uint32_t g = 0;   // running P-chunk counter across tiles -> buffer / phase
@@ -155,11 +167,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const int n = part == 0 ? n1 : n2;
           if (n == 0) break;
           const uint32_t idesc = umma_idesc_bf16(n, 0, 0);
-          const uint32_t boff = part * 256 * 128, tcol = part * 256;
+          const uint32_t boff = part * ((256 * 128) >> 4), tcol = part * 256;
 #pragma unroll
           for (int kk = 0; kk < HD / 16; ++kk) {
-            const uint64_t aq_hi = umma_smem_desc(q_hi + kk * 32, 16, 1024), aq_lo = umma_smem_desc(q_lo + kk * 32, 16, 1024);
-            const uint64_t bk_hi = umma_smem_desc(k_hi + boff + kk * 32, 16, 1024), bk_lo = umma_smem_desc(k_lo + boff + kk * 32, 16, 1024);
+            const uint64_t aq_hi = dq_hi + kk * 2, aq_lo = dq_lo + kk * 2;             // + 32 B per K step
+            const uint64_t bk_hi = dk_hi + boff + kk * 2, bk_lo = dk_lo + boff + kk * 2;
             umma_bf16(TM_S + tcol, aq_lo, bk_hi, idesc, kk > 0 ? 1u : 0u);
             umma_bf16(TM_S + tcol, aq_hi, bk_lo, idesc, 1u);
             umma_bf16(TM_S + tcol, aq_hi, bk_hi, idesc, 1u);
@@ -173,12 +185,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const int buf = g & 1;
           mbar_wait(&bar_p[buf], (g >> 1) & 1);
           tc_fence_after();
-          const uint32_t p_hi = smem_u32(smem + (buf ^ 1) * 2 * ROW_TILE_BYTES), p_lo = p_hi + ROW_TILE_BYTES;   // buffer 0 = region B, 1 = region A
           const int ksteps = min(4, (NP - c * 64) / 16);
+          const uint64_t pb_hi = buf ? dp_hi1 : dp_hi0, pb_lo = buf ? dp_lo1 : dp_lo0;
+#pragma unroll 4
           for (int kk = 0; kk < ksteps; ++kk) {
-            const uint32_t voff = (uint32_t)(c * 64 + kk * 16) * 128;
-            const uint64_t ap_hi = umma_smem_desc(p_hi + kk * 32, 16, 1024), ap_lo = umma_smem_desc(p_lo + kk * 32, 16, 1024);
-            const uint64_t bv_hi = umma_smem_desc(v_hi + voff, 1024, 1024), bv_lo = umma_smem_desc(v_lo + voff, 1024, 1024);
+            const uint32_t voff = (uint32_t)(c * 64 + kk * 16) * (128 >> 4);
+            const uint64_t ap_hi = pb_hi + kk * 2, ap_lo = pb_lo + kk * 2;
+            const uint64_t bv_hi = dv_hi + voff, bv_lo = dv_lo + voff;
             const uint32_t acc = (c > 0 || kk > 0) ? 1u : 0u;
             umma_bf16(TM_OX, ap_lo, bv_hi, idesc_pv, acc);
             umma_bf16(TM_OX, ap_hi, bv_lo, idesc_pv, 1u);
@@ -211,6 +224,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const bool warp_valid = (t * 128 + q * 32) < p.N;   // any valid row in this warp (uniform per warp)
       mbar_wait(bar_s, t & 1);
       tc_fence_after();
+      if (tr && threadIdx.x == 0 && t < 3) tr[2 + 8 * t] = clock64();      // S ready
       float m = -INFINITY;
       if (warp_valid) {
         for (int sc = part; sc < nsub; sc += 4) {
@@ -226,6 +240,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       ew_sync();
       m = fmaxf(fmaxf(xch[r], xch[128 + r]), fmaxf(xch[256 + r], xch[384 + r]));
       ew_sync();                                     // xch is reused for the row sums below
+      if (tr && threadIdx.x == 0 && t < 3) tr[3 + 8 * t] = clock64();      // row max known
       const float mc = m * c2;
       float sum = 0.f;
       for (int c = 0; c < nchunks; ++c, ++g) {
@@ -257,6 +272,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_p[buf]);
+        if (tr && threadIdx.x == 0 && t < 3 && (c == 0 || c == nchunks - 1)) tr[(c == 0 ? 4 : 5) + 8 * t] = clock64();   // first / last P chunk handed over
       }
       xch[part * 128 + r] = sum;
       ew_sync();
@@ -264,6 +280,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       // ---- epilogue: this thread writes output columns [16*part, 16*part+16) of its row ----
       mbar_wait(bar_o, t & 1);
       tc_fence_after();
+      if (tr && threadIdx.x == 0 && t < 3) tr[6 + 8 * t] = clock64();      // O complete
       uint32_t a[16], x[16];
       if (warp_valid) {
         tmem_ld_32x32b_x16(TM_O + lane_addr + part * 16, a);
@@ -282,6 +299,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         store_out16(p.o + (int64_t)(row0 + qr) * p.ld_o + h * HD + part * 16, p.o_ps, o16);
       }
       ew_sync();                                     // xch (row sums) is rewritten by the next tile's row max
+      if (tr && threadIdx.x == 0 && t < 3) tr[7 + 8 * t] = clock64();      // tile stored
     }
   }
   tc_fence_before();
@@ -394,28 +412,37 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       // ===== MMA issuer =====
       const uint32_t idesc_t = umma_idesc_bf16(64, 0, 0);     // T = R C^T   (both K-major, K = head dim)
       const uint32_t idesc_a = umma_idesc_bf16(64, 0, 1);     // Acc = X C   (X K-major, C MN-major, K = chunk columns)
+      // base descriptors once (the single issuing thread is on the critical path of these N = 64 MMAs); a K step adds
+      // (bytes >> 4) to the start-address field: 32 B -> 2 for K-major tiles, 2048 B -> 128 for MN-major tiles
       const uint32_t r1 = smem_u32(smem + BWD_OFF_R1), r2 = smem_u32(smem + BWD_OFF_R2);
       const uint32_t xb = smem_u32(smem + BWD_OFF_X), yb = smem_u32(smem + BWD_OFF_Y);
+      const uint64_t dr1h = umma_smem_desc(r1, 16, 1024), dr1l = umma_smem_desc(r1 + ROW_TILE_BYTES, 16, 1024);
+      const uint64_t dr2h = umma_smem_desc(r2, 16, 1024), dr2l = umma_smem_desc(r2 + ROW_TILE_BYTES, 16, 1024);
+      const uint64_t dxh = umma_smem_desc(xb, 16, 1024), dxl = umma_smem_desc(xb + ROW_TILE_BYTES, 16, 1024);
+      const uint64_t dyh = umma_smem_desc(yb, 16, 1024), dyl = umma_smem_desc(yb + ROW_TILE_BYTES, 16, 1024);
+      // C stage 0 views, K-major (T MMAs) and MN-major (Acc MMAs); stage 1 = + (BWD_CSTAGE >> 4) in the address field
+      const uint32_t c1s0 = smem_u32(smem + BWD_OFF_C), c2s0 = c1s0 + ROW_TILE_BYTES;
+      const uint64_t dc1h0 = umma_smem_desc(c1s0, 16, 1024), dc1l0 = umma_smem_desc(c1s0 + ROW_TILE_BYTES / 2, 16, 1024);
+      const uint64_t dc2h0 = umma_smem_desc(c2s0, 16, 1024), dc2l0 = umma_smem_desc(c2s0 + ROW_TILE_BYTES / 2, 16, 1024);
+      const uint64_t mc1h0 = umma_smem_desc(c1s0, 1024, 1024), mc1l0 = umma_smem_desc(c1s0 + ROW_TILE_BYTES / 2, 1024, 1024);
+      const uint64_t mc2h0 = umma_smem_desc(c2s0, 1024, 1024), mc2l0 = umma_smem_desc(c2s0 + ROW_TILE_BYTES / 2, 1024, 1024);
+      constexpr uint32_t STAGE_STEP = BWD_CSTAGE >> 4;
       mbar_wait(bar_r, 0);
       auto issue_t = [&](int j) {
         const int s = j & 1;
         mbar_wait(&bar_cfull[s], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t c1 = smem_u32(smem + BWD_OFF_C + s * BWD_CSTAGE), c2 = c1 + ROW_TILE_BYTES;
         const uint32_t t1 = tmem + s * 128, t2 = t1 + 64;
+        const uint32_t so = s * STAGE_STEP;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          const uint32_t ko = kk * 32;
-          const uint64_t a1h = umma_smem_desc(r1 + ko, 16, 1024), a1l = umma_smem_desc(r1 + ROW_TILE_BYTES + ko, 16, 1024);
-          const uint64_t b1h = umma_smem_desc(c1 + ko, 16, 1024), b1l = umma_smem_desc(c1 + ROW_TILE_BYTES / 2 + ko, 16, 1024);
-          umma_bf16(t1, a1l, b1h, idesc_t, kk > 0 ? 1u : 0u);
-          umma_bf16(t1, a1h, b1l, idesc_t, 1u);
-          umma_bf16(t1, a1h, b1h, idesc_t, 1u);
-          const uint64_t a2h = umma_smem_desc(r2 + ko, 16, 1024), a2l = umma_smem_desc(r2 + ROW_TILE_BYTES + ko, 16, 1024);
-          const uint64_t b2h = umma_smem_desc(c2 + ko, 16, 1024), b2l = umma_smem_desc(c2 + ROW_TILE_BYTES / 2 + ko, 16, 1024);
-          umma_bf16(t2, a2l, b2h, idesc_t, kk > 0 ? 1u : 0u);
-          umma_bf16(t2, a2h, b2l, idesc_t, 1u);
-          umma_bf16(t2, a2h, b2h, idesc_t, 1u);
+          const uint32_t ko = kk * 2;
+          umma_bf16(t1, dr1l + ko, dc1h0 + so + ko, idesc_t, kk > 0 ? 1u : 0u);
+          umma_bf16(t1, dr1h + ko, dc1l0 + so + ko, idesc_t, 1u);
+          umma_bf16(t1, dr1h + ko, dc1h0 + so + ko, idesc_t, 1u);
+          umma_bf16(t2, dr2l + ko, dc2h0 + so + ko, idesc_t, kk > 0 ? 1u : 0u);
+          umma_bf16(t2, dr2h + ko, dc2l0 + so + ko, idesc_t, 1u);
+          umma_bf16(t2, dr2h + ko, dc2h0 + so + ko, idesc_t, 1u);
         }
         umma_commit(&bar_t[s]);
       };
@@ -425,22 +452,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
         if (j + 1 < nchunks) issue_t(j + 1);
         mbar_wait(bar_x, j & 1);
         tc_fence_after();
-        const uint32_t c1 = smem_u32(smem + BWD_OFF_C + s * BWD_CSTAGE), c2 = c1 + ROW_TILE_BYTES;
         const int ksteps = min(4, (p.NP - j * 64) / 16);
+#pragma unroll 4
         for (int kk = 0; kk < ksteps; ++kk) {
           const uint32_t acc = (j > 0 || kk > 0) ? 1u : 0u;
-          const uint32_t ko = kk * 32, bo = kk * 2048;
-          const uint64_t xh = umma_smem_desc(xb + ko, 16, 1024), xl = umma_smem_desc(xb + ROW_TILE_BYTES + ko, 16, 1024);
-          const uint64_t b1h = umma_smem_desc(c1 + bo, 1024, 1024), b1l = umma_smem_desc(c1 + ROW_TILE_BYTES / 2 + bo, 1024, 1024);
-          umma_bf16(tmem + 320, xl, b1h, idesc_a, acc);
-          umma_bf16(tmem + 320, xh, b1l, idesc_a, 1u);
-          umma_bf16(tmem + 256, xh, b1h, idesc_a, acc);
+          const uint32_t ko = kk * 2, bo = kk * 128 + s * STAGE_STEP;
+          umma_bf16(tmem + 320, dxl + ko, mc1h0 + bo, idesc_a, acc);
+          umma_bf16(tmem + 320, dxh + ko, mc1l0 + bo, idesc_a, 1u);
+          umma_bf16(tmem + 256, dxh + ko, mc1h0 + bo, idesc_a, acc);
           if (MODE == MODE_DKV) {
-            const uint64_t yh = umma_smem_desc(yb + ko, 16, 1024), yl = umma_smem_desc(yb + ROW_TILE_BYTES + ko, 16, 1024);
-            const uint64_t b2h = umma_smem_desc(c2 + bo, 1024, 1024), b2l = umma_smem_desc(c2 + ROW_TILE_BYTES / 2 + bo, 1024, 1024);
-            umma_bf16(tmem + 448, yl, b2h, idesc_a, acc);
-            umma_bf16(tmem + 448, yh, b2l, idesc_a, 1u);
-            umma_bf16(tmem + 384, yh, b2h, idesc_a, acc);
+            umma_bf16(tmem + 448, dyl + ko, mc2h0 + bo, idesc_a, acc);
+            umma_bf16(tmem + 448, dyh + ko, mc2l0 + bo, idesc_a, 1u);
+            umma_bf16(tmem + 384, dyh + ko, mc2h0 + bo, idesc_a, acc);
           }
         }
         umma_commit(bar_xfree);
@@ -580,6 +603,7 @@ extern "C" int srw_attn_fwd(const srw_attn_fwd_args* a, void* stream_) {
   AttnFwdParams p;
   p.B = a->B; p.N = a->N; p.H = a->H; p.NP = NP; p.scale = a->scale;
   p.o = reinterpret_cast<__nv_bfloat16*>(a->o); p.ld_o = a->ld_o; p.o_ps = a->o_plane_stride; p.lse = a->lse;
+  p.trace = g_attn_trace;
   dim3 grid(a->H, a->B);
   const double pair_flops = 2.0 * a->B * a->H * (double)a->N * a->N * HD;   // one N x N x 64 product per (image, head)
   void* prof = prof_begin(SRW_PROF_ATTN_FWD, 2.0 * pair_flops, 4.0 * 4.0 * a->B * a->N * a->H * HD, stream);
@@ -631,5 +655,11 @@ extern "C" int srw_attn_bwd(const srw_attn_bwd_args* a, void* stream_) {
   prof_end(prof, stream);
   g_launches++;
   SRW_LAUNCH_CHECK();
+  return SRW_OK;
+}
+
+// debug: per-CTA clock64 timeline of attn_fwd_kernel into buf[B * H][32] (NULL turns it off).  Not part of include/srw.h.
+extern "C" int srw_attn_set_trace(unsigned long long* buf) {
+  srw::g_attn_trace = buf;
   return SRW_OK;
 }

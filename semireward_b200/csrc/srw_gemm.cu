@@ -342,7 +342,12 @@ gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
       const uint32_t a_lo_off = tp.a_mn ? (PLANE_TILE_BYTES / 2) : PLANE_TILE_BYTES;  // lo plane offset inside the operand
       const uint32_t b_lo_off = tp.b_mn ? (PLANE_TILE_BYTES / 2) : B_PLANE_BYTES;
       const uint32_t a_lbo = tp.a_mn ? PLANE_TILE_BYTES : 16, b_lbo = tp.b_mn ? PLANE_TILE_BYTES : 16;
-      const uint32_t a_kstep = tp.a_mn ? 2048 : 32, b_kstep = tp.b_mn ? 2048 : 32;
+      const uint32_t a_kstep = (tp.a_mn ? 2048 : 32) >> 4, b_kstep = (tp.b_mn ? 2048 : 32) >> 4;
+      // base descriptors of stage 0, built once: the issuing thread must not spend more cycles rebuilding descriptors
+      // than the MMAs take (BN = 128: 64 clk each); a stage / K step only adds (bytes >> 4) to the start-address field
+      const uint32_t s0 = smem_u32(smem);
+      const uint64_t dA_hi = umma_smem_desc(s0, a_lbo, 1024), dA_lo = umma_smem_desc(s0 + a_lo_off, a_lbo, 1024);
+      const uint64_t dB_hi = umma_smem_desc(s0 + A_STAGE_BYTES, b_lbo, 1024), dB_lo = umma_smem_desc(s0 + A_STAGE_BYTES + b_lo_off, b_lbo, 1024);
       uint32_t it = 0, tile_iter = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_iter) {
         const int split = t / tiles_mn;
@@ -358,14 +363,11 @@ gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           if (tr && it == 0) tr[3] = clock64();
-          const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
-          const uint32_t b_base = a_base + A_STAGE_BYTES;
+          const uint32_t so = s * (STAGE_BYTES >> 4);
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint64_t a_hi = umma_smem_desc(a_base + kk * a_kstep, a_lbo, 1024);
-            const uint64_t a_lo = umma_smem_desc(a_base + a_lo_off + kk * a_kstep, a_lbo, 1024);
-            const uint64_t b_hi = umma_smem_desc(b_base + kk * b_kstep, b_lbo, 1024);
-            const uint64_t b_lo = umma_smem_desc(b_base + b_lo_off + kk * b_kstep, b_lbo, 1024);
+            const uint64_t a_hi = dA_hi + so + kk * a_kstep, a_lo = dA_lo + so + kk * a_kstep;
+            const uint64_t b_hi = dB_hi + so + kk * b_kstep, b_lo = dB_lo + so + kk * b_kstep;
             umma_bf16(acc_addr, a_lo, b_hi, idesc, (kb > kb_begin || kk > 0) ? 1u : 0u);  // small terms first
             umma_bf16(acc_addr, a_hi, b_lo, idesc, 1u);
             umma_bf16(acc_addr, a_hi, b_hi, idesc, 1u);
@@ -557,7 +559,10 @@ gemm2_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
       const uint32_t a_lo_off = tp.a_mn ? (PLANE_TILE_BYTES / 2) : PLANE_TILE_BYTES;
       const uint32_t b_lo_off = tp.b_mn ? (PLANE_TILE_BYTES / 2) : B_PLANE_BYTES;
       const uint32_t a_lbo = tp.a_mn ? PLANE_TILE_BYTES : 16, b_lbo = tp.b_mn ? PLANE_TILE_BYTES : 16;
-      const uint32_t a_kstep = tp.a_mn ? 2048 : 32, b_kstep = tp.b_mn ? 2048 : 32;
+      const uint32_t a_kstep = (tp.a_mn ? 2048 : 32) >> 4, b_kstep = (tp.b_mn ? 2048 : 32) >> 4;
+      const uint32_t s0 = smem_u32(smem);   // stage-0 base descriptors built once (see the 1-CTA kernel)
+      const uint64_t dA_hi = umma_smem_desc(s0, a_lbo, 1024), dA_lo = umma_smem_desc(s0 + a_lo_off, a_lbo, 1024);
+      const uint64_t dB_hi = umma_smem_desc(s0 + A_STAGE_BYTES, b_lbo, 1024), dB_lo = umma_smem_desc(s0 + A_STAGE_BYTES + b_lo_off, b_lbo, 1024);
       uint32_t it = 0, tile_iter = 0;
       for (int t = pair; t < total_tiles; t += num_pairs, ++tile_iter) {
         const int split = t / tiles_mn;
@@ -572,14 +577,11 @@ gemm2_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
-          const uint32_t b_base = a_base + A_STAGE_BYTES;
+          const uint32_t so = s * (STAGE_BYTES >> 4);
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint64_t a_hi = umma_smem_desc(a_base + kk * a_kstep, a_lbo, 1024);
-            const uint64_t a_lo = umma_smem_desc(a_base + a_lo_off + kk * a_kstep, a_lbo, 1024);
-            const uint64_t b_hi = umma_smem_desc(b_base + kk * b_kstep, b_lbo, 1024);
-            const uint64_t b_lo = umma_smem_desc(b_base + b_lo_off + kk * b_kstep, b_lbo, 1024);
+            const uint64_t a_hi = dA_hi + so + kk * a_kstep, a_lo = dA_lo + so + kk * a_kstep;
+            const uint64_t b_hi = dB_hi + so + kk * b_kstep, b_lo = dB_lo + so + kk * b_kstep;
             umma_bf16_2cta(acc_addr, a_lo, b_hi, idesc, (kb > kb_begin || kk > 0) ? 1u : 0u);
             umma_bf16_2cta(acc_addr, a_hi, b_lo, idesc, 1u);
             umma_bf16_2cta(acc_addr, a_hi, b_hi, idesc, 1u);

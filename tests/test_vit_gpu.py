@@ -118,3 +118,37 @@ def test_scale_inplace():
     assert torch.equal(x, torch.arange(1003, dtype=torch.float32, device="cuda"))
     L.check(lib.srw_scale_inplace(x.data_ptr(), x.numel(), half.data_ptr(), L.stream_ptr()))
     assert torch.equal(x, torch.arange(1003, dtype=torch.float32, device="cuda") * 0.5)
+
+
+@pytest.mark.parametrize("builder,kw,vc_kw", [
+    ("vit_tiny_patch2_32", dict(), dict(img_size=32, patch_size=2, embed_dim=192, num_heads=3)),
+    ("vit_base_patch16_96", dict(), dict(img_size=96, patch_size=16, embed_dim=768, num_heads=12)),
+    ("vit_small_patch16_224", dict(), dict(img_size=224, patch_size=16, embed_dim=384, num_heads=6)),
+])
+def test_other_vit_builders_vs_oracle(builder, kw, vc_kw):
+    """The remaining ViT builders of semilearn/nets/vit/vit.py:323-408 through the same engine:
+    D = 192 / 768, N = 37 / 197 / 257 tokens, patch-embed K = 12 / 768."""
+    from oracle import ssl_oracle as O
+    from semireward_b200 import detgen, nets
+    depth, C = 2, 10
+    vc = O.ViTConfig(depth=depth, num_classes=C, **vc_kw)
+    p = {n: torch.from_numpy(detgen.fill_param(n, s, 0)) for n, s in vc.param_shapes()}
+    p["head.weight"] = p["head.weight"] * 4.0
+    model = getattr(nets, builder)(num_classes=C, depth=depth, drop_path_rate=0.0, **kw)
+    model.load_state_dict(p)
+    model = model.cuda().train()
+    B, Bg = 6, 4
+    x = torch.from_numpy(detgen.normal("x_builders", (B, 3, vc.img_size, vc.img_size), 5))
+    out = model(x.cuda(), grad_batch=Bg)
+    po = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    lo, fo = O.vit_forward(po, x, vc, None)
+    assert (out["logits"].cpu() - lo.detach()).abs().max().item() < 1e-3
+    assert (out["feat"].cpu() - fo.detach()).abs().max().item() < 1e-3
+    cl = torch.from_numpy(detgen.normal("cl_builders", (B, C), 6))
+    cl[Bg:] = 0
+    (out["logits"] * cl.cuda()).sum().backward()
+    (lo * cl).sum().backward()
+    for name, prm in model.named_parameters():
+        ref = po[name].grad
+        rel = (prm.grad.cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-12)
+        assert rel < 1e-3, f"{builder} {name}: relative gradient error {rel:.3e}"
