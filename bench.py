@@ -33,6 +33,11 @@ YAML_CFG = dict(  # flexmatch_cifar100_200_0.yaml:10-54 (+ code defaults, SURVEY
     ulb_dest_len=50000, feature_dim=384, sr_lr=5e-4, sr_ema=False, use_cat=True, amp=False, ema_m=0.0, img_size=32,
     p_cutoff=0.95, thresh_warmup=True, ulb_loss_ratio=1.0, clip_grad=0)
 F_FWD_GF = 12.134          # GFLOP per sample forward
+# BASELINE configs[2] (a parity-test case, not the headline): FreeMatch+SemiReward, vit_base_patch16_224, 1000 classes,
+# synthetic 224x224, global batch 1024 over 8 ranks = 128 per GPU (SURVEY.md §8d "Config 3"); `--config 3`, GPU arm only.
+YAML_CFG3 = dict(YAML_CFG, algorithm="srfreematch", net="vit_base_patch16_224", num_classes=1000, batch_size=128, img_size=224,
+                 feature_dim=768, use_quantile=True, clip_thresh=False, ema_p=0.999, ent_loss_ratio=0.0001, hard_label=True, T=0.5)
+F_FWD_GF3 = 35.128
 
 
 def parse():
@@ -43,6 +48,7 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch-size", type=int, default=8, help="per-GPU labelled batch (config-faithful: 8)")
     ap.add_argument("--stage", type=int, default=1, choices=[1, 2])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3], help="BASELINE.json configs index + 1: 2 = headline ViT-S CIFAR-100, 3 = ViT-B/16 224 FreeMatch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     return ap.parse_args()
@@ -165,7 +171,9 @@ def main_native(a):
     lib = L.load()
     L.check(lib.srw_device_check(None, None, None), "srw_device_check")
 
-    cfg = dict(YAML_CFG, batch_size=a.batch_size, gpu=local, distributed=world > 1, world_size=world, rank=rank)
+    base_cfg = YAML_CFG if a.config == 2 else YAML_CFG3
+    bs = a.batch_size if (a.batch_size != 8 or a.config == 2) else base_cfg["batch_size"]
+    cfg = dict(base_cfg, batch_size=bs, gpu=local, distributed=world > 1, world_size=world, rank=rank)
     args = S.get_config(cfg)
     torch.manual_seed(0)
     alg = S.get_algorithm(args, S.get_net_builder(args.net, False), None, None)
@@ -177,10 +185,10 @@ def main_native(a):
     samples_per_step = B + 2 * U
 
     def host_batch(i):
-        b = detgen.ssl_batch(B, args.uratio, args.num_classes, args.ulb_dest_len, seed=1 + rank, step=i)
+        b = detgen.ssl_batch(B, args.uratio, args.num_classes, args.ulb_dest_len, img_size=args.img_size, seed=1 + rank, step=i)
         return {k: torch.from_numpy(v).pin_memory() for k, v in b.items()}
 
-    n_batches = 4
+    n_batches = 4 if a.config == 2 else 2   # config 3: 231 MB per host batch
     hbatches = [host_batch(i) for i in range(n_batches)]
     dbatches = [{k: v.cuda(non_blocking=True) for k, v in hb.items()} for hb in hbatches]
     h2d = sum(v.numel() * v.element_size() for v in hbatches[0].values())
@@ -267,7 +275,7 @@ def main_native(a):
             attn["adamw"] = dict(achieved_gbs=ad.bytes / (ad.total_ms * 1e-3) / 1e9, peak_gbs=hbm, avg_launch_us=1e3 * ad.total_ms / max(ad.launches, 1))
 
     cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and a.config == 2:
         sps, per_step, cores = cpu_reference_run(dict(YAML_CFG, batch_size=a.batch_size), 6, 1, a.stage)
         cpu = dict(value=sps, unit="samples/s", cores=cores, kind="port",
                    sample=f"6 stage-{a.stage} steps (+1 warm-up) of the oracle restatement of the reference train_step+ParamUpdateHook, "
@@ -275,13 +283,15 @@ def main_native(a):
     if rank == 0:
         line = dict(metric="SSL train-step samples/sec (ViT-S CIFAR-100)", value=value, unit="samples/s", n_gpus=world, steps=K, warmup=W,
                     ms_per_step=ms / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=f"srflexmatch vit_small_patch2_32 cifar100 batch_size {B} uratio {args.uratio} stage {a.stage} (BASELINE configs[1])",
+                    config=dict(workload=(f"srflexmatch vit_small_patch2_32 cifar100 batch_size {B} uratio {args.uratio} stage {a.stage} (BASELINE configs[1])"
+                                          if a.config == 2 else
+                                          f"srfreematch vit_base_patch16_224 synthetic 224x224 1000 classes batch_size {B} per GPU stage {a.stage} (BASELINE configs[2])"),
                                 samples_per_step_per_gpu=samples_per_step, parallelism=f"dp{world}", drop_path=0.2,
                                 arithmetic="fp32 semantics: bf16x3 split-precision tcgen05 MMA, fp32 accumulate",
                                 l2="step working set (~1.8 GB of activations at batch 8) >> 126 MB L2; 4 rotating input batches",
                                 launch="CUDA-graph replay of the backbone forward/backward (SRW_GRAPHS) + programmatic dependent launch (SRW_PDL); "
                                        "backward launched inside train_step ahead of the loss read-back",
-                                algorithmic_gflop_per_step_per_gpu=7 * B * F_FWD_GF),
+                                algorithmic_gflop_per_step_per_gpu=7 * B * (F_FWD_GF if a.config == 2 else F_FWD_GF3)),
                     clocks=clk.summary(), gpu_launches=int(launches),
                     e2e=dict(value=e2e, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4 * (5 + U), ms_per_step=ms_e2e / K))
         if roof is not None:
