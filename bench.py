@@ -190,7 +190,9 @@ def main_native(a):
 
     n_batches = 4 if a.config == 2 else 2   # config 3: 231 MB per host batch
     hbatches = [host_batch(i) for i in range(n_batches)]
-    dbatches = [{k: v.cuda(non_blocking=True) for k, v in hb.items()} for hb in hbatches]
+    import inspect
+    step_keys = set(inspect.signature(alg.train_step).parameters)   # process_batch's filter (algorithmbase.py:287-296)
+    dbatches = [{k: v.cuda(non_blocking=True) for k, v in hb.items() if k in step_keys} for hb in hbatches]
     h2d = sum(v.numel() * v.element_size() for v in hbatches[0].values())
 
     def step_device(i):

@@ -34,3 +34,5 @@ print(f"attn_fwd B={B} N={N} H={H} (us since CTA entry, median over {B * H} CTAs
 names = ["S ready", "row max", "P chunk 0", "P last", "O done", "stored"]
 for tl in range((N + 127) // 128):
     print(f"  tile {tl}: " + " | ".join(f"{n} {med(2 + 8 * tl + i):6.2f}" for i, n in enumerate(names)))
+print("  tile 0 chunk loop: softmax sees buffer free (c=2) %.2f | hands chunk 2 over %.2f | MMA thread sees chunk 2 %.2f | chunk 2 issued+committed %.2f | "
+      "MMA thread sees chunk 3 %.2f | softmax sees chunk 2's buffer free (c=4) %.2f" % tuple(med(i) for i in (26, 27, 28, 29, 30, 31)))

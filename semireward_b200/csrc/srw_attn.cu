@@ -50,15 +50,26 @@ __device__ __forceinline__ void store_row16_planes(uint8_t* hi_tile, uint8_t* lo
 // sync the 512 element-wise threads only (named barrier 1); the TMA / MMA warps never take part
 __device__ __forceinline__ void ew_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-// write 16 fp32 accumulator columns of one row as split planes to global (32 B hi + 32 B lo)
+// write 16 fp32 accumulator columns of one row as split planes to global (32 B hi + 32 B lo).  Each lane owns its own row,
+// so a 128-bit store would fill only half a 32-byte sector: one 256-bit store per plane (sm_100 STG.256) when aligned.
 __device__ __forceinline__ void store_out16(__nv_bfloat16* hi_ptr, int64_t plane_stride, const float (&v)[16]) {
+  uint32_t hh[8], ll[8];
 #pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    uint32_t hh[4], ll[4];
+  for (int j = 0; j < 8; ++j) split2(v[2 * j], v[2 * j + 1], hh[j], ll[j]);
+  __nv_bfloat16* lo_ptr = hi_ptr + plane_stride;
+  if (((reinterpret_cast<uintptr_t>(hi_ptr) | reinterpret_cast<uintptr_t>(lo_ptr)) & 31) == 0) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(hi_ptr), "r"(hh[0]), "r"(hh[1]), "r"(hh[2]), "r"(hh[3]),
+                 "r"(hh[4]), "r"(hh[5]), "r"(hh[6]), "r"(hh[7])
+                 : "memory");
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(lo_ptr), "r"(ll[0]), "r"(ll[1]), "r"(ll[2]), "r"(ll[3]),
+                 "r"(ll[4]), "r"(ll[5]), "r"(ll[6]), "r"(ll[7])
+                 : "memory");
+  } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) split2(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1], hh[j], ll[j]);
-    *reinterpret_cast<uint4*>(hi_ptr + g * 8) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-    *reinterpret_cast<uint4*>(hi_ptr + plane_stride + g * 8) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+    for (int g = 0; g < 2; ++g) {
+      *reinterpret_cast<uint4*>(hi_ptr + g * 8) = make_uint4(hh[4 * g], hh[4 * g + 1], hh[4 * g + 2], hh[4 * g + 3]);
+      *reinterpret_cast<uint4*>(lo_ptr + g * 8) = make_uint4(ll[4 * g], ll[4 * g + 1], ll[4 * g + 2], ll[4 * g + 3]);
+    }
   }
 }
 
@@ -100,7 +111,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* bar_sfree = bars + 8;  // softmax warps have read S for the last time (count 16)
   uint64_t* bar_ofree = bars + 9;  // softmax warps have read O (count 16)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-  float* xch = reinterpret_cast<float*>(smem + off_bar + 128);   // [4][128] partial row max / row sum exchange
+  float* xch_base = reinterpret_cast<float*>(smem + off_bar + 128);   // [2][4][128] partial row max / row sum exchange, one set per tile parity
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -185,6 +196,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const int buf = g & 1;
           mbar_wait(&bar_p[buf], (g >> 1) & 1);
           tc_fence_after();
+          if (tr && t == 0 && (c == 2 || c == 3)) tr[c == 2 ? 28 : 30] = clock64();   // MMA thread: P chunk c visible
           const int ksteps = min(4, (NP - c * 64) / 16);
           const uint64_t pb_hi = buf ? dp_hi1 : dp_hi0, pb_lo = buf ? dp_lo1 : dp_lo0;
 #pragma unroll 4
@@ -198,6 +210,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             umma_bf16(TM_O, ap_hi, bv_hi, idesc_pv, acc);
           }
           umma_commit(&bar_pfree[buf]);
+          if (tr && t == 0 && c == 2) tr[29] = clock64();                                // MMA thread: chunk 2 issued + committed
         }
         umma_commit(bar_o);
         if (t + 1 < ntiles) {
@@ -220,6 +233,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     uint32_t g = 0;
     for (int t = 0; t < ntiles; ++t) {
       const int qr = t * 128 + r;                    // query index inside the image
+      float* xch = xch_base + (t & 1) * 512;         // alternating sets: no barrier needed between tiles
       const bool valid = qr < p.N;
       const bool warp_valid = (t * 128 + q * 32) < p.N;   // any valid row in this warp (uniform per warp)
       mbar_wait(bar_s, t & 1);
@@ -265,6 +279,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           if (lane == 0) mbar_arrive(bar_sfree);
         }
         if (g >= 2) mbar_wait(&bar_pfree[buf], ((g >> 1) - 1) & 1);
+        if (tr && threadIdx.x == 0 && t == 0 && (c == 2 || c == 4)) tr[c == 2 ? 26 : 31] = clock64();   // softmax: buffer free again
         if (have) {
           uint8_t* hi_tile = smem + (buf ^ 1) * 2 * ROW_TILE_BYTES;   // buffer 0 -> region B (32 KiB), buffer 1 -> region A (0)
           store_row16_planes(hi_tile, hi_tile + ROW_TILE_BYTES, r, part * 16, pv);
@@ -273,6 +288,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_p[buf]);
         if (tr && threadIdx.x == 0 && t < 3 && (c == 0 || c == nchunks - 1)) tr[(c == 0 ? 4 : 5) + 8 * t] = clock64();   // first / last P chunk handed over
+        if (tr && threadIdx.x == 0 && t == 0 && c == 2) tr[27] = clock64();                                                  // chunk 2 handed over
       }
       xch[part * 128 + r] = sum;
       ew_sync();
@@ -298,7 +314,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int j = 0; j < 16; ++j) o16[j] = (__uint_as_float(a[j]) + __uint_as_float(x[j])) * inv;
         store_out16(p.o + (int64_t)(row0 + qr) * p.ld_o + h * HD + part * 16, p.o_ps, o16);
       }
-      ew_sync();                                     // xch (row sums) is rewritten by the next tile's row max
       if (tr && threadIdx.x == 0 && t < 3) tr[7 + 8 * t] = clock64();      // tile stored
     }
   }
@@ -595,7 +610,7 @@ extern "C" int srw_attn_fwd(const srw_attn_fwd_args* a, void* stream_) {
   if (rc) return rc;
   SRW_REQUIRE(a->ld_o % 8 == 0 && a->o_plane_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(a->o) & 15) == 0, "srw_attn_fwd: o planes must be 16-byte aligned");
   const uint32_t kv_plane = (uint32_t)NP * 128;
-  const int smem_bytes = (int)(4 * ROW_TILE_BYTES + 4 * kv_plane + 128 + 4 * 128 * 4 + 1024);   // regions A, B | K | V | barriers | exchange | align
+  const int smem_bytes = (int)(4 * ROW_TILE_BYTES + 4 * kv_plane + 128 + 2 * 4 * 128 * 4 + 1024);   // regions A, B | K | V | barriers | 2 exchange sets | align
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
