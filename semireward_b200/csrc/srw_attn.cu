@@ -143,7 +143,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   pdl_wait();   // CTA-local setup above; q/k/v come from the previous kernel
 
   if (warp == 16) {
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: the compiler keeps descriptors / addresses in uniform registers (no per-MMA R2UR waterfall)
       // ---- K, V once; Q of tile 0 ----
       const int half = NP / 2;
       mbar_arrive_expect_tx(bar_kv, 4 * kv_plane);
@@ -406,7 +406,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
   const int c2_col = (MODE == MODE_DQ ? 2 * D : 0) + h * HD;   // C2: V (DQ) / dO (DKV, own matrix)
 
   if (warp == 16) {
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: the compiler keeps descriptors / addresses in uniform registers (no per-MMA R2UR waterfall)
       // ===== TMA producer =====
       mbar_arrive_expect_tx(bar_r, 4 * ROW_TILE_BYTES);
       tma_load_3d(smem + BWD_OFF_R1, &tm_qkv_r, bar_r, r1_col, row0 + rt * 128, 0);  // box planes = 2: hi, lo
@@ -423,7 +423,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       }
     }
   } else if (warp == 17) {
-    if (lane == 0) {
+    if (elect_one()) {   // one elected lane: the compiler keeps descriptors / addresses in uniform registers (no per-MMA R2UR waterfall)
       // ===== MMA issuer =====
       const uint32_t idesc_t = umma_idesc_bf16(64, 0, 0);     // T = R C^T   (both K-major, K = head dim)
       const uint32_t idesc_a = umma_idesc_bf16(64, 0, 1);     // Acc = X C   (X K-major, C MN-major, K = chunk columns)
