@@ -201,6 +201,11 @@ typedef struct {
   int accumulate_grads;                       /* 0: grads are overwritten, 1: grads += */
   void* workspace; int64_t workspace_bytes;
   int gemm_impl;
+  /* block range of this call: blocks block_hi down to block_lo (block_hi < 0 = the whole backward).  The head / final-norm
+   * stage runs iff block_hi is the last block, the embedding stage iff block_lo == 0.  Successive calls over descending
+   * ranges on the same workspace equal one full call; data parallelism uses it to all-reduce the gradients of the
+   * finished blocks (the tail of the flat gradient buffer) while the remaining blocks run (DDP bucket overlap). */
+  int block_lo, block_hi;
 } srw_vit_bwd_args;
 int srw_vit_backward(const srw_vit_bwd_args* a, void* stream);
 

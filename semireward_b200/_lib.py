@@ -80,7 +80,7 @@ class VitFwdArgs(C.Structure):
 class VitBwdArgs(C.Structure):
     _fields_ = [("cfg", C.POINTER(VitConfig)), ("params", C.POINTER(vp)), ("weight_planes", vp), ("x", vp), ("batch", i32),
                 ("grad_batch", i32), ("drop_scale", vp), ("dlogits", vp), ("dfeat", vp), ("grads", C.POINTER(vp)),
-                ("accumulate_grads", i32), ("workspace", vp), ("workspace_bytes", i64), ("gemm_impl", i32)]
+                ("accumulate_grads", i32), ("workspace", vp), ("workspace_bytes", i64), ("gemm_impl", i32), ("block_lo", i32), ("block_hi", i32)]
 
 
 class RewarderFwdArgs(C.Structure):

@@ -363,7 +363,7 @@ class SRFlexMatch(AlgorithmBase):
         if h_last is None:
             net.backward_native(h0, dl)
         else:
-            net.backward_native(h0, dl0)
+            net.backward_native(h0, dl0, final=False)
             net.backward_native(h_last, dl1, accumulate=True)
         net.allreduce_grads_()
         total_loss = _PrecomputedGrads.apply(losses[2], net, net.cls_token)   # one parameter anchors the node in the graph

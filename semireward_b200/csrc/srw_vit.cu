@@ -569,7 +569,14 @@ static int vit_backward_body(const srw_vit_bwd_args* a, cudaStream_t s) {
   float* cws = F32(L.colsum_ws);
   float* dt = F32(L.dt);
 
+  // optional block range (data parallel: the caller all-reduces the gradients of the blocks already finished while the
+  // rest of the backward runs): blocks block_hi .. block_lo, head stage iff block_hi is the last block, embedding stage iff
+  // block_lo == 0; the running token gradient dt and the handed-over planes stay in the workspace between the calls
+  const int blk_hi = (a->block_hi < 0 || a->block_hi >= d.L) ? d.L - 1 : a->block_hi;
+  const int blk_lo = (a->block_hi < 0 || a->block_lo < 0) ? 0 : a->block_lo;
+  SRW_REQUIRE(blk_lo <= blk_hi, "srw_vit_backward: empty block range [%d, %d]", blk_lo, blk_hi);
   // ---- head + final norm ----
+  if (blk_hi == d.L - 1) {
   SRW_CUDA(cudaMemsetAsync(dt, 0, (size_t)Tg * D * 4, s));
   head_bwd_rows_kernel<<<d.Bg, 256, (d.C + 8) * sizeof(float), s>>>(a->dlogits, a->dfeat, d.N, D, d.C, P[ptail(d.L, 0)], P[ptail(d.L, 2)],
                                                                     F32(L.cls_xhat), F32(L.cls_rstd), F32(L.dfeat), dt);
@@ -582,8 +589,9 @@ static int vit_backward_body(const srw_vit_bwd_args* a, cudaStream_t s) {
     g_launches++;
     SRW_LAUNCH_CHECK();
   }
+  }
   // ---- blocks ----
-  for (int l = d.L - 1; l >= 0; --l) {
+  for (int l = blk_hi; l >= blk_lo; --l) {
     const BlockBufs& b = L.blk[l];
     const float* ds_attn = a->drop_scale ? a->drop_scale + ((int64_t)l * 2 + 0) * d.B : nullptr;
     const float* ds_mlp = a->drop_scale ? a->drop_scale + ((int64_t)l * 2 + 1) * d.B : nullptr;
@@ -651,7 +659,7 @@ static int vit_backward_body(const srw_vit_bwd_args* a, cudaStream_t s) {
     SRW_TRY(srw_layernorm_bwd(&lb, s));
   }
   // ---- embedding ----
-  {
+  if (blk_lo == 0) {
     const int64_t n = (int64_t)d.N * D;
     embed_grad_kernel<<<(int)cdiv64(n, 256), 256, 0, s>>>(dt, d.Bg, d.N, D, G[P_POS], G[P_CLS], acc);
     g_launches++;
@@ -804,6 +812,6 @@ extern "C" int srw_vit_backward(const srw_vit_bwd_args* a, void* stream_) {
   kb.add((int)2); kb.add(*a->cfg); kb.add(s);
   for (int i = 0; i < vit_num_params(a->cfg); ++i) { kb.add(a->params[i]); kb.add(a->grads[i]); }
   kb.add(a->weight_planes); kb.add(a->x); kb.add(a->batch); kb.add(a->grad_batch); kb.add(a->drop_scale); kb.add(a->dlogits); kb.add(a->dfeat);
-  kb.add(a->accumulate_grads); kb.add(a->workspace); kb.add(a->workspace_bytes); kb.add(a->gemm_impl);
+  kb.add(a->accumulate_grads); kb.add(a->workspace); kb.add(a->workspace_bytes); kb.add(a->gemm_impl); kb.add(a->block_lo); kb.add(a->block_hi);
   return run_graphed(std::move(kb.k), s, [a](cudaStream_t st) { return vit_backward_body(a, st); });
 }

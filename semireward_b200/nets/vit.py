@@ -102,7 +102,7 @@ class _VitFunction(torch.autograd.Function):
         a = L.VitBwdArgs(cfg=C.pointer(cfg), params=L.ptr_array(params), weight_planes=model._weight_planes().data_ptr(),
                          x=ctx.x.data_ptr(), batch=ctx.B, grad_batch=Bg, drop_scale=L.ptr(ctx.drop_scale), dlogits=dl.data_ptr(),
                          dfeat=L.ptr(df), grads=L.ptr_array(grads), accumulate_grads=0, workspace=ctx.ws.data_ptr(),
-                         workspace_bytes=ctx.wbytes, gemm_impl=model.gemm_impl)
+                         workspace_bytes=ctx.wbytes, gemm_impl=model.gemm_impl, block_lo=-1, block_hi=-1)
         L.check(lib.srw_vit_backward(C.byref(a), L.stream_ptr()), "srw_vit_backward")
         model._release_ws(ctx.ws)
         ctx.ws = None
@@ -142,6 +142,8 @@ class VisionTransformer(nn.Module):
         self._planes = None
         self._planes_key = None
         self._keep_cache, self._ws_pool, self._bufs = {}, {}, {}
+        self.dp_overlap_split = depth // 2   # data parallel: all-reduce blocks >= split while blocks < split are back-propagated (0 = off)
+        self._pending_reduce = []
         self._pa = self._pa_key = self._flat_grads = self._grad_views = self._ga = None
 
     # -- native plumbing ------------------------------------------------------------------------
@@ -268,7 +270,7 @@ class VisionTransformer(nn.Module):
         return self._buf("dlogits", (grad_batch, self._cfg.num_classes), device)
 
     @torch.no_grad()
-    def backward_native(self, handle, dlogits, dfeat=None, accumulate=False):
+    def backward_native(self, handle, dlogits, dfeat=None, accumulate=False, final=True):
         """srw_vit_backward for a pass of forward_native(): parameter gradients (state_dict order) into the persistent flat
         buffer -> (flat, views).  Data parallel: the flat buffer is all-reduced (mean) here unless more passes accumulate."""
         lib, cfg = L.load(), self._cfg
@@ -292,16 +294,49 @@ class VisionTransformer(nn.Module):
         a = L.VitBwdArgs(cfg=C.pointer(cfg), params=pa, weight_planes=self._weight_planes().data_ptr(), x=handle["x"].data_ptr(),
                          batch=handle["B"], grad_batch=Bg, drop_scale=L.ptr(handle["drop_scale"]), dlogits=dl.data_ptr(), dfeat=L.ptr(df),
                          grads=self._ga, accumulate_grads=int(bool(accumulate)), workspace=handle["ws"].data_ptr(),
-                         workspace_bytes=handle["wbytes"], gemm_impl=self.gemm_impl)
-        L.check(lib.srw_vit_backward(C.byref(a), L.stream_ptr()), "srw_vit_backward")
+                         workspace_bytes=handle["wbytes"], gemm_impl=self.gemm_impl, block_lo=-1, block_hi=-1)
+        group = getattr(self, "_dp_group", None)
+        split = self.dp_overlap_split if (group is not None and final and self.dp_overlap_split > 0) else 0
+        self._pending_reduce = []
+        if split and 0 < split < cfg.depth:
+            # data parallel with overlap (DDP's bucketed all-reduce, core/utils/misc.py:42-64): the gradients of blocks
+            # split..depth-1, the final norm and the head are the TAIL of the flat buffer and are complete after the first
+            # half of the backward — their all-reduce runs on NCCL's stream while blocks split-1..0 are computed
+            import torch.distributed as dist
+            off = sum(p.numel() for p in params[:4 + 12 * split])
+            a.block_lo, a.block_hi = split, cfg.depth - 1
+            L.check(lib.srw_vit_backward(C.byref(a), L.stream_ptr()), "srw_vit_backward")
+            self._pending_reduce.append(self._allreduce_async(self._flat_grads[off:], group))
+            a.block_lo, a.block_hi = 0, split - 1
+            L.check(lib.srw_vit_backward(C.byref(a), L.stream_ptr()), "srw_vit_backward")
+            self._pending_reduce.append(self._allreduce_async(self._flat_grads[:off], group))
+        else:
+            L.check(lib.srw_vit_backward(C.byref(a), L.stream_ptr()), "srw_vit_backward")
         self.release_pass(handle)
         return self._flat_grads, self._grad_views
 
+    @staticmethod
+    def _allreduce_async(t, group):
+        import torch.distributed as dist
+        if dist.get_backend(group) == "nccl":
+            return (dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group, async_op=True), None)
+        return (dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True), (t, dist.get_world_size(group)))   # gloo: no AVG
+
     def allreduce_grads_(self):
+        """Average the flat gradient over the data-parallel group (C1 in SURVEY.md §2.1); completes the overlapped
+        all-reduces backward_native() already started, or runs one all-reduce of the whole buffer."""
         group = getattr(self, "_dp_group", None)
-        if group is not None and self._flat_grads is not None:   # data parallel: C1 in SURVEY.md §2.1
-            from ..parallel import allreduce_mean_
-            allreduce_mean_(self._flat_grads, group)
+        if group is None or self._flat_grads is None:
+            return
+        pending, self._pending_reduce = getattr(self, "_pending_reduce", []), []
+        if pending:
+            for work, post in pending:
+                work.wait()            # the current stream waits for NCCL's stream
+                if post is not None:
+                    post[0].div_(post[1])
+            return
+        from ..parallel import allreduce_mean_
+        allreduce_mean_(self._flat_grads, group)
 
     def _run(self, x, grad_batch=None, drop_scale=None):
         if not x.is_cuda:
