@@ -20,7 +20,7 @@ rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 flats = []
-for split in (0, 2, 0, 3):
+for split in (0, 2, 0, 4):
     cfg = dict(bench.YAML_CFG, gpu=local, distributed=True, world_size=world, rank=rank, num_train_iter=64, start_timing=1000)
     args = S.get_config(cfg)
     torch.manual_seed(0)
@@ -41,7 +41,7 @@ ok = all(torch.equal(flats[0], f) for f in flats[1:])
 gathered = [torch.empty_like(flats[0]) for _ in range(world)]
 dist.all_gather(gathered, flats[1])
 same_across_ranks = all(torch.equal(gathered[0], g) for g in gathered)
-print(f"rank {rank}: parameters after 3 steps identical for split 0 / 2 / 0 / 3: {ok}; identical across ranks: {same_across_ranks}", flush=True)
+print(f"rank {rank}: parameters after 3 steps identical for 1 / 2 / 1 / 4 block ranges: {ok}; identical across ranks: {same_across_ranks}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok and same_across_ranks else 1)

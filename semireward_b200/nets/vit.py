@@ -142,7 +142,7 @@ class VisionTransformer(nn.Module):
         self._planes = None
         self._planes_key = None
         self._keep_cache, self._ws_pool, self._bufs = {}, {}, {}
-        self.dp_overlap_split = depth // 2   # data parallel: all-reduce blocks >= split while blocks < split are back-propagated (0 = off)
+        self.dp_overlap_split = 4   # data parallel: number of block ranges of the backward whose gradients are all-reduced while the next range runs (<= 1: off)
         self._pending_reduce = []
         self._pa = self._pa_key = self._flat_grads = self._grad_views = self._ga = None
 
@@ -296,24 +296,31 @@ class VisionTransformer(nn.Module):
                          grads=self._ga, accumulate_grads=int(bool(accumulate)), workspace=handle["ws"].data_ptr(),
                          workspace_bytes=handle["wbytes"], gemm_impl=self.gemm_impl, block_lo=-1, block_hi=-1)
         group = getattr(self, "_dp_group", None)
-        split = self.dp_overlap_split if (group is not None and final and self.dp_overlap_split > 0) else 0
         self._pending_reduce = []
-        if split and 0 < split < cfg.depth:
-            # data parallel with overlap (DDP's bucketed all-reduce, core/utils/misc.py:42-64): the gradients of blocks
-            # split..depth-1, the final norm and the head are the TAIL of the flat buffer and are complete after the first
-            # half of the backward — their all-reduce runs on NCCL's stream while blocks split-1..0 are computed
-            import torch.distributed as dist
-            off = sum(p.numel() for p in params[:4 + 12 * split])
-            a.block_lo, a.block_hi = split, cfg.depth - 1
-            L.check(lib.srw_vit_backward(C.byref(a), L.stream_ptr()), "srw_vit_backward")
-            self._pending_reduce.append(self._allreduce_async(self._flat_grads[off:], group))
-            a.block_lo, a.block_hi = 0, split - 1
-            L.check(lib.srw_vit_backward(C.byref(a), L.stream_ptr()), "srw_vit_backward")
-            self._pending_reduce.append(self._allreduce_async(self._flat_grads[:off], group))
+        bounds = self._dp_bounds(cfg.depth) if (group is not None and final) else []
+        if bounds:
+            # data parallel with overlap (DDP's bucketed all-reduce, core/utils/misc.py:42-64): the backward runs as descending
+            # block ranges; the gradients of a finished range (and, for the first one, of the final norm and the head) are a
+            # contiguous piece of the flat buffer, all-reduced on NCCL's stream while the next range is computed
+            hi, end = cfg.depth - 1, self._flat_grads.numel()
+            for lo in bounds + [0]:
+                a.block_lo, a.block_hi = lo, hi
+                L.check(lib.srw_vit_backward(C.byref(a), L.stream_ptr()), "srw_vit_backward")
+                off = sum(p.numel() for p in params[:4 + 12 * lo]) if lo > 0 else 0
+                self._pending_reduce.append(self._allreduce_async(self._flat_grads[off:end], group))
+                hi, end = lo - 1, off
         else:
             L.check(lib.srw_vit_backward(C.byref(a), L.stream_ptr()), "srw_vit_backward")
         self.release_pass(handle)
         return self._flat_grads, self._grad_views
+
+    def _dp_bounds(self, depth):
+        """Descending lower block bounds of all but the last range: dp_overlap_split = k -> k ranges of ~depth/k blocks."""
+        k = int(self.dp_overlap_split)
+        if k <= 1 or depth < 2:
+            return []
+        k = min(k, depth)
+        return sorted({(depth * i) // k for i in range(1, k)} - {0}, reverse=True)
 
     @staticmethod
     def _allreduce_async(t, group):

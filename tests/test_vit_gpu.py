@@ -152,3 +152,33 @@ def test_other_vit_builders_vs_oracle(builder, kw, vc_kw):
         ref = po[name].grad
         rel = (prm.grad.cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-12)
         assert rel < 1e-3, f"{builder} {name}: relative gradient error {rel:.3e}"
+
+
+def test_split_backward_equals_full_backward():
+    """srw_vit_backward over two descending block ranges (the data-parallel overlap route) == one full call, bit for bit;
+    the all-reduce hand-off is stubbed so that this runs in one process."""
+    from semireward_b200 import detgen
+    O, vc, p, model = _setup(4)
+    B, Bg = 9, 6
+    x = torch.from_numpy(detgen.normal("x_split", (B, 3, 32, 32), 31)).cuda()
+    cl = torch.from_numpy(detgen.normal("cl_split", (Bg, 100), 32)).cuda()
+
+    class _Done:
+        def wait(self):
+            return True
+    calls = []
+    results = []
+    for split in (0, 2, 3, 4):   # number of block ranges (depth 4)
+        model.dp_overlap_split = split
+        model._dp_group = object() if split else None
+        model._allreduce_async = lambda t, g: (calls.append(t.numel()) or (_Done(), None))
+        for rep in range(3):   # eager, captured, replayed
+            lg, ft, h = model.forward_native(x, grad_batch=Bg)
+            flat, views = model.backward_native(h, cl)
+            if split:
+                model.allreduce_grads_()
+        torch.cuda.synchronize()
+        results.append(flat.clone())
+    model._dp_group = None
+    assert all(torch.equal(results[0], r) for r in results[1:])
+    assert len(calls) == 3 * (2 + 3 + 4) and sum(calls[:2]) == results[0].numel()
