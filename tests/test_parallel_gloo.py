@@ -23,7 +23,17 @@ def _worker(rank, world, port, q):
     st = O.FlexMatchState(16, 4)
     g = torch.Generator().manual_seed(rank)
     st.masking(torch.softmax(4 * torch.randn(4, 4, generator=g), -1), torch.arange(4) + 4 * rank, 0.5)
-    q.put((rank, ok_avg, shard, float(t.item()), st.selected_label.tolist()))
+    # overlapped route of the ViT module (nets/vit.py): pieces of the flat gradient are all-reduced asynchronously as the
+    # backward's block ranges finish, allreduce_grads_() completes them (gloo has no AVG: SUM, then divide)
+    from semireward_b200.nets import vit_small_patch2_32
+    net = vit_small_patch2_32(num_classes=10, depth=4)
+    net._dp_group = dist.group.WORLD
+    net._flat_grads = torch.full((100,), float(rank + 1))
+    net._pending_reduce = [net._allreduce_async(net._flat_grads[60:], net._dp_group), net._allreduce_async(net._flat_grads[:60], net._dp_group)]
+    net.allreduce_grads_()
+    ok_overlap = bool(torch.allclose(net._flat_grads, torch.full((100,), (1 + world) / 2 * 1.0))) and net._pending_reduce == []
+    bounds = [net._dp_bounds(12), net._dp_bounds(4), net._dp_bounds(2), net._dp_bounds(1)]
+    q.put((rank, ok_avg and ok_overlap, shard, float(t.item()), st.selected_label.tolist(), bounds))
     dist.destroy_process_group()
 
 
@@ -42,3 +52,4 @@ def test_two_rank_gradient_average_and_sharding():
     assert res[0][2] == [0, 2, 4, 6, 8] and res[1][2] == [1, 3, 5, 7, 9]
     assert res[0][3] == res[1][3] == 11.0
     assert res[0][4] != res[1][4]
+    assert res[0][5] == [[9, 6, 3], [3, 2, 1], [1], []]   # dp_overlap_split = 4 block ranges
