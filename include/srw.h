@@ -87,6 +87,8 @@ typedef struct {
   void* out_planes; int64_t ldp; int64_t out_plane_stride;
   int split_k; float* workspace;              /* SRW_EPI_SPLITK: split_k >= 1 slices of K, workspace [split_k, M, N] */
   int impl;                                   /* srw_gemm_impl; SIMT is the on-device verification twin */
+  int max_ctas;                               /* 0 = the whole GPU; > 0: persistent grid of at most this many CTAs (the GEMM
+                                                 shares the GPU with kernels on other streams, e.g. the four wgrads of a block) */
 } srw_gemm_args;
 int srw_gemm(const srw_gemm_args* a, void* stream);
 

@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
                 ("b", vp), ("ldb", i64), ("b_plane_stride", i64), ("b_mn_major", i32),
                 ("epilogue", i32), ("bias", vp), ("resid", vp), ("ldr", i64), ("row_scale", vp), ("rows_per_scale", i32),
                 ("aux", vp), ("ldaux", i64), ("out_f32", vp), ("ldo", i64), ("out_planes", vp), ("ldp", i64),
-                ("out_plane_stride", i64), ("split_k", i32), ("workspace", vp), ("impl", i32)]
+                ("out_plane_stride", i64), ("split_k", i32), ("workspace", vp), ("impl", i32), ("max_ctas", i32)]
 
 
 class SplitKReduceArgs(C.Structure):

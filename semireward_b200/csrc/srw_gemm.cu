@@ -730,7 +730,8 @@ int make_plane_tmap(CUtensorMap* out, const void* base, int64_t inner, int64_t o
 
 // Tile width: the candidate with the fewest (waves x tile cost) over the 148 SMs; ties go to the wider tile (less L2
 // traffic per FLOP).  192 divides the ViT widths exactly, 128 / 64 give more tiles for small problems.
-int gemm_pick_bn(int M, int N, int splits) {
+int gemm_pick_bn(int M, int N, int splits, int ctas) {
+  if (ctas <= 0) ctas = 148;
   const int cands[3] = {192, 128, 64};
   int best = 128;
   double best_cost = 1e30;
@@ -739,7 +740,7 @@ int gemm_pick_bn(int M, int N, int splits) {
     if (bn == 192 && N % 192 != 0) continue;
     if (bn == 128 && N <= 64) continue;
     const int64_t tiles = (int64_t)cdiv(M, BM) * cdiv(N, bn) * std::max(1, splits);
-    const double waves = (double)((tiles + 147) / 148);
+    const double waves = (double)((tiles + ctas - 1) / ctas);
     const double cost = waves * (bn + 40);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
   }
@@ -748,7 +749,9 @@ int gemm_pick_bn(int M, int N, int splits) {
 
 // Pair-tile width for the 2-CTA kernel (0 = use the 1-CTA kernel): 256 x BN tiles, BN/2 rows of B per CTA, which must be
 // a multiple of 64 for MN-major B.  Small problems (fewer pair tiles than half the SMs' worth) stay on the 1-CTA kernel.
-int gemm2_pick_bn(int M, int N, int splits, bool b_mn) {
+int gemm2_pick_bn(int M, int N, int splits, bool b_mn, int ctas) {
+  if (ctas <= 0) ctas = 148;
+  const int npairs = std::max(1, ctas / 2);
   const int cands[3] = {256, 192, 128};
   int best = 0;
   double best_cost = 1e30;
@@ -758,14 +761,14 @@ int gemm2_pick_bn(int M, int N, int splits, bool b_mn) {
     if (bn == 256 && N % 256 != 0 && N < 1024) continue;
     if (N < bn) continue;
     const int64_t tiles = (int64_t)cdiv(M, 256) * cdiv(N, bn) * std::max(1, splits);
-    const double waves = (double)((tiles + 73) / 74);
+    const double waves = (double)((tiles + npairs - 1) / npairs);
     const double cost = waves * (bn + 40);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
   }
   // compare with the 1-CTA kernel's wave cost (per-SM work): prefer 2-CTA unless it quantises clearly worse
-  const int bn1 = gemm_pick_bn(M, N, splits);
+  const int bn1 = gemm_pick_bn(M, N, splits, ctas);
   const int64_t tiles1 = (int64_t)cdiv(M, BM) * cdiv(N, bn1) * std::max(1, splits);
-  const double cost1 = (double)((tiles1 + 147) / 148) * (bn1 + 40);
+  const double cost1 = (double)((tiles1 + ctas - 1) / ctas) * (bn1 + 40);
   if (best == 0 || best_cost > 1.15 * cost1) return 0;
   return best;
 }
@@ -851,7 +854,9 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
   const double flops = 2.0 * a->M * a->N * a->K, bytes = 4.0 * ((double)a->M * a->K + (double)a->N * a->K + (double)a->M * a->N);
 
   // ---- 2-CTA path: pair tiles of 256 x BN ----
-  const int bn2 = srw::gemm2_pick_bn(a->M, a->N, grid_z, a->b_mn_major != 0);
+  // max_ctas > 0: this GEMM may only occupy that many SMs (it runs next to other kernels on other streams)
+  const int cta_cap = (a->max_ctas > 0 && a->max_ctas < num_sms) ? std::max(2, a->max_ctas) : num_sms;
+  const int bn2 = srw::gemm2_pick_bn(a->M, a->N, grid_z, a->b_mn_major != 0, cta_cap);
   if (a->impl == SRW_GEMM_TCGEN05 && bn2 > 0) {
     CUtensorMap ta, tb;
     if (!a->a_mn_major) rc = make_plane_tmap(&ta, a->a, a->K, a->M, a->lda, a->a_plane_stride, 128, 2);
@@ -862,7 +867,7 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
     if (rc) return rc;
     tp.m_tiles = cdiv(a->M, 256); tp.n_tiles = cdiv(a->N, bn2);
     const int total_tiles = tp.m_tiles * tp.n_tiles * tp.splits;
-    const int pairs = std::min(total_tiles, num_sms / 2);
+    const int pairs = std::min(total_tiles, cta_cap / 2);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GEMM_THREADS); cfg.stream = stream;
     cfg.dynamicSmemBytes = gemm2_smem_bytes(bn2);
@@ -885,7 +890,7 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
   }
 
   // ---- 1-CTA path ----
-  const int bn = srw::gemm_pick_bn(a->M, a->N, grid_z);
+  const int bn = srw::gemm_pick_bn(a->M, a->N, grid_z, cta_cap);
   CUtensorMap ta, tb;
   if (!a->a_mn_major) rc = make_plane_tmap(&ta, a->a, a->K, a->M, a->lda, a->a_plane_stride, 128, 2);
   else rc = make_plane_tmap(&ta, a->a, a->M, a->K, a->lda, a->a_plane_stride, 64, 2);
@@ -895,7 +900,7 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
   if (rc) return rc;
   tp.m_tiles = cdiv(a->M, BM); tp.n_tiles = cdiv(a->N, bn);
   const int total_tiles = tp.m_tiles * tp.n_tiles * tp.splits;
-  const int grid = std::min(total_tiles, num_sms);
+  const int grid = std::min(total_tiles, cta_cap);
   void* prof = prof_begin(SRW_PROF_GEMM, flops, bytes, stream);
   cudaError_t le;
   if (bn == 192) le = launch_pdl(gemm_bf16x3_tcgen05_kernel<192>, dim3(grid), dim3(GEMM_THREADS), gemm_smem_bytes(192), stream, ta, tb, tp, ep);

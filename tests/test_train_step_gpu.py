@@ -53,6 +53,7 @@ def _resync(alg, orc):
     (12, 5, {}, True, True),
     (2, 8, {}, False, True),
     (2, 8, {}, True, False),    # the autograd route (_VitFunction / _SSLLoss) instead of the eager backward
+    (2, 5, dict(batch_size=40, uratio=2, ulb_dest_len=512), True, True),   # 200 images per step (uratio 2): multi-wave GEMMs, ragged tiles
 ])
 def test_srflexmatch_steps_vs_oracle(depth, steps, over, resync, eager):
     cfg = small_cfg(**over)
