@@ -276,7 +276,8 @@ typedef struct {
   const float* logits_w; int64_t ld_logits;
   const int64_t* idx_ulb;
   float p_cutoff; int thresh_warmup;
-  int64_t* selected_label;  /* [ulb_dest_len] hook state */
+  int64_t* selected_label;  /* [ulb_dest_len] hook state; NULL = FixedThresholdingHook (hooks/masking.py:42-57): stateless
+                               mask = max_p >= p_cutoff, idx_ulb / hist / classwise_acc unused (SRFixMatch) */
   int32_t* hist;            /* [num_classes + 1] hook state */
   float* classwise_acc;     /* [num_classes] hook state */
   float* probs_w;           /* [B, C] out, row stride num_classes (may be NULL) */

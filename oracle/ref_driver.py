@@ -75,8 +75,8 @@ def load_reference():
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     import semilearn  # noqa: E402
-    for alg in ("srflexmatch", "srfreematch", "srsoftmatch"):
-        mod = sys.modules.get(f"semilearn.algorithms.{alg}.{alg}")
+    for modname in ("srflexmatch.srflexmatch", "srfreematch.srfreematch", "srsoftmatch.srsoftmatch", "srfixmatch.fixmatch"):
+        mod = sys.modules.get(f"semilearn.algorithms.{modname}")
         if mod is not None:
             mod.send_model_cuda = lambda args, m, clip_batch=True: m
     _loaded = True

@@ -14,7 +14,8 @@ What is restated (fp32, torch CPU, functional style — no nn.Module of the refe
   * pseudo-labels                   — algorithms/hooks/pseudo_label.py:16-52
   * ce / consistency loss           — core/criterions/cross_entropy.py:11-31, consistency.py:13-45
   * FreeMatch fairness entropy loss — algorithms/srfreematch/srfreematch.py:16-44
-  * train_step / data_generator     — srflexmatch.py:72-217, srfreematch.py:76-228, srsoftmatch.py:61-221
+  * train_step / data_generator     — srflexmatch.py:72-217, srfreematch.py:76-228, srsoftmatch.py:61-221,
+                                      srfixmatch/fixmatch.py:62-210 (= srflexmatch with the stateless FixedThresholdingHook)
   * sr_decay                        — core/algorithmbase.py:177-183
   * ParamUpdateHook                 — core/hooks/param_update.py:21-40 (backward, AdamW, LambdaLR, zero_grad)
   * AdamW groups + cosine schedule  — core/utils/build.py:193-251, nets/utils.py:143-204 (layer decay)
@@ -403,7 +404,7 @@ class AdamState:
 # ------------------------------------------------------------------------------------------------
 @dataclass
 class StepConfig:
-    algorithm: str = "srflexmatch"  # srflexmatch | srfreematch | srsoftmatch
+    algorithm: str = "srflexmatch"  # srflexmatch | srfreematch | srsoftmatch | srfixmatch
     num_classes: int = 100
     ulb_dest_len: int = 50000
     p_cutoff: float = 0.95
@@ -446,7 +447,9 @@ class SSLOracle:
         self.sched_step = 0  # number of scheduler.step() calls so far (LambdaLR.last_epoch)
         self.max_reward = -float("inf")
         C = cfg.num_classes
-        if cfg.algorithm == "srflexmatch":
+        if cfg.algorithm == "srfixmatch":
+            self.hook = None  # FixedThresholdingHook is stateless (hooks/masking.py:42-57)
+        elif cfg.algorithm == "srflexmatch":
             self.hook = FlexMatchState(cfg.ulb_dest_len, C, cfg.thresh_warmup)
         elif cfg.algorithm == "srfreematch":
             self.hook = FreeMatchState(C, cfg.ema_p)
@@ -470,6 +473,8 @@ class SSLOracle:
 
     def _mask_from_probs(self, probs_w: Tensor, idx_ulb: Optional[Tensor]) -> Tensor:
         c = self.cfg
+        if c.algorithm == "srfixmatch":  # FixedThresholdingHook.masking (hooks/masking.py:47-57; srfixmatch/fixmatch.py:132)
+            return probs_w.max(dim=-1)[0].ge(c.p_cutoff).to(probs_w.dtype)
         if c.algorithm == "srflexmatch":
             return self.hook.masking(probs_w, idx_ulb, c.p_cutoff)
         if c.algorithm == "srfreematch":
@@ -529,7 +534,7 @@ class SSLOracle:
             probs_for_mask = probs_w
         mask = self._mask_from_probs(probs_for_mask, idx_ulb)
         pseudo = lw.detach().argmax(dim=-1)  # argmax(probs) == argmax(logits) up to fp ties; reference uses probs for
-        if c.algorithm == "srflexmatch":     # FlexMatch (srflexmatch.py:142-146) and logits for the others
+        if c.algorithm in ("srflexmatch", "srfixmatch"):     # FlexMatch / FixMatch (srflexmatch.py:142-146, fixmatch.py:135-139) and logits for the others
             pseudo = probs_w.argmax(dim=-1)
         if it > c.start_timing:
             unsup_loss = self._data_generator(x_lb, idx_ulb, x_ulb_w, x_ulb_s, it, rec)

@@ -195,6 +195,29 @@ class FlexMatchThresholdingHook(Hook):
         return mask
 
 
+class FixedThresholdingHook(Hook):
+    """semilearn/algorithms/hooks/masking.py:42-57 (FixMatch / UDA / pseudo-label): mask = max_p >= p_cutoff, stateless.
+    Softmax + hard pseudo-labels + mask in one launch (srw_flexmatch_mask without FlexMatch state)."""
+
+    @torch.no_grad()
+    def masking(self, algorithm, logits_x_ulb, softmax_x_ulb=True, *args, **kwargs):
+        if not softmax_x_ulb:
+            raise RuntimeError("fused FixedThresholdingHook takes raw logits (softmax is fused into the kernel)")
+        lw = _contig_logits(logits_x_ulb)
+        B, Cn = lw.shape
+        dev = lw.device
+        probs = torch.empty(B, Cn, dtype=torch.float32, device=dev)
+        pseudo = torch.empty(B, dtype=torch.long, device=dev)
+        mask = torch.empty(B, dtype=torch.float32, device=dev)
+        a = L.FlexMatchMaskArgs(B=B, num_classes=Cn, ulb_dest_len=0, logits_w=lw.data_ptr(), ld_logits=lw.stride(0), idx_ulb=None,
+                                p_cutoff=float(algorithm.p_cutoff), thresh_warmup=0, selected_label=None, hist=None, classwise_acc=None,
+                                probs_w=probs.data_ptr(), pseudo=pseudo.data_ptr(), mask=mask.data_ptr(), max_probs=None)
+        L.check(L.load().srw_flexmatch_mask(C.byref(a), L.stream_ptr()), "srw_flexmatch_mask")
+        algorithm._last_pseudo = (probs, pseudo)
+        algorithm._last_probs = probs
+        return mask
+
+
 def _contig_logits(logits_x_ulb):
     lw = logits_x_ulb.detach()
     return lw if lw.stride(-1) == 1 else lw.contiguous()

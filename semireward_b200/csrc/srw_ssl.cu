@@ -80,6 +80,12 @@ __global__ void __launch_bounds__(SSL_THREADS) flexmatch_mask_kernel(const srw_f
       if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
     }
     if (lane == 0) {
+      if (a.selected_label == nullptr) {   // FixedThresholdingHook (hooks/masking.py:42-57): stateless max_p >= p_cutoff
+        a.mask[b] = best >= a.p_cutoff ? 1.0f : 0.0f;
+        a.pseudo[b] = best_i;
+        if (a.max_probs) a.max_probs[b] = best;
+        continue;
+      }
       const float acc = a.classwise_acc[best_i];
       const float thr = a.p_cutoff * (acc / (2.0f - acc));          // utils.py:52
       a.mask[b] = best >= thr ? 1.0f : 0.0f;
@@ -89,6 +95,7 @@ __global__ void __launch_bounds__(SSL_THREADS) flexmatch_mask_kernel(const srw_f
       s_idx[b] = best_i;
     }
   }
+  if (a.selected_label == nullptr) return;
   __syncthreads();
   if (threadIdx.x == 0) {
     // selected_label[idx_ulb[select]] = max_idx[select]  (utils.py:60-61), histogram kept in step
@@ -512,7 +519,8 @@ using namespace srw;
 
 extern "C" int srw_flexmatch_mask(const srw_flexmatch_mask_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  SRW_REQUIRE(a && a->logits_w && a->idx_ulb && a->selected_label && a->hist && a->classwise_acc && a->pseudo && a->mask, "srw_flexmatch_mask: null pointer");
+  SRW_REQUIRE(a && a->logits_w && a->pseudo && a->mask, "srw_flexmatch_mask: null pointer");
+  SRW_REQUIRE(a->selected_label == nullptr || (a->idx_ulb && a->hist && a->classwise_acc), "srw_flexmatch_mask: FlexMatch state incomplete");
   SRW_REQUIRE(a->B > 0 && a->B <= MAX_ROWS && a->num_classes > 0, "srw_flexmatch_mask: 0 < B <= %d required (B=%d)", MAX_ROWS, a->B);
   flexmatch_mask_kernel<<<1, SSL_THREADS, 0, stream>>>(*a);
   g_launches++;

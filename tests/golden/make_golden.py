@@ -56,7 +56,7 @@ def run_case(name, spec):
         elif cfg["algorithm"] == "srfreematch":
             out[f"it{it}_p_model"] = h.p_model.numpy().copy()
             out[f"it{it}_time_p"] = np.float32(h.time_p.item())
-        else:
+        elif cfg["algorithm"] == "srsoftmatch":
             out[f"it{it}_mu"] = np.float32(float(h.prob_max_mu_t))
             out[f"it{it}_var"] = np.float32(float(h.prob_max_var_t))
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)

@@ -35,7 +35,7 @@ def _oracle_trace(spec):
         elif cfg["algorithm"] == "srfreematch":
             out[f"it{it}_p_model"] = orc.hook.p_model.numpy().copy()
             out[f"it{it}_time_p"] = np.float32(float(orc.hook.time_p))
-        else:
+        elif cfg["algorithm"] == "srsoftmatch":
             out[f"it{it}_mu"] = np.float32(float(orc.hook.prob_max_mu_t))
             out[f"it{it}_var"] = np.float32(float(orc.hook.prob_max_var_t))
     return out
