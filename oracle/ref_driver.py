@@ -75,7 +75,7 @@ def load_reference():
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     import semilearn  # noqa: E402
-    for modname in ("srflexmatch.srflexmatch", "srfreematch.srfreematch", "srsoftmatch.srsoftmatch", "srfixmatch.fixmatch"):
+    for modname in ("srflexmatch.srflexmatch", "srfreematch.srfreematch", "srsoftmatch.srsoftmatch", "srfixmatch.fixmatch", "srpseudolabel.srpseudolabel"):
         mod = sys.modules.get(f"semilearn.algorithms.{modname}")
         if mod is not None:
             mod.send_model_cuda = lambda args, m, clip_batch=True: m

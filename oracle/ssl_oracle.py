@@ -15,7 +15,8 @@ What is restated (fp32, torch CPU, functional style — no nn.Module of the refe
   * ce / consistency loss           — core/criterions/cross_entropy.py:11-31, consistency.py:13-45
   * FreeMatch fairness entropy loss — algorithms/srfreematch/srfreematch.py:16-44
   * train_step / data_generator     — srflexmatch.py:72-217, srfreematch.py:76-228, srsoftmatch.py:61-221,
-                                      srfixmatch/fixmatch.py:62-210 (= srflexmatch with the stateless FixedThresholdingHook)
+                                      srfixmatch/fixmatch.py:62-210 (= srflexmatch with the stateless FixedThresholdingHook),
+                                      srpseudolabel/srpseudolabel.py:58-201
   * sr_decay                        — core/algorithmbase.py:177-183
   * ParamUpdateHook                 — core/hooks/param_update.py:21-40 (backward, AdamW, LambdaLR, zero_grad)
   * AdamW groups + cosine schedule  — core/utils/build.py:193-251, nets/utils.py:143-204 (layer decay)
@@ -404,7 +405,8 @@ class AdamState:
 # ------------------------------------------------------------------------------------------------
 @dataclass
 class StepConfig:
-    algorithm: str = "srflexmatch"  # srflexmatch | srfreematch | srsoftmatch | srfixmatch
+    algorithm: str = "srflexmatch"  # srflexmatch | srfreematch | srsoftmatch | srfixmatch | srpseudolabel
+    unsup_warm_up: float = 0.4  # srpseudolabel
     num_classes: int = 100
     ulb_dest_len: int = 50000
     p_cutoff: float = 0.95
@@ -447,7 +449,7 @@ class SSLOracle:
         self.sched_step = 0  # number of scheduler.step() calls so far (LambdaLR.last_epoch)
         self.max_reward = -float("inf")
         C = cfg.num_classes
-        if cfg.algorithm == "srfixmatch":
+        if cfg.algorithm in ("srfixmatch", "srpseudolabel"):
             self.hook = None  # FixedThresholdingHook is stateless (hooks/masking.py:42-57)
         elif cfg.algorithm == "srflexmatch":
             self.hook = FlexMatchState(cfg.ulb_dest_len, C, cfg.thresh_warmup)
@@ -519,9 +521,59 @@ class SSLOracle:
                    sr_gen_label=gen.squeeze(1), sr_reward=reward.detach(), sr_target=target,
                    sr_gen_loss=gen_loss.detach(), sr_rew_loss=rew_loss.detach())
 
+    def _train_step_pseudolabel(self, batch: Dict[str, Tensor], it: int) -> dict:
+        """SRPseudoLabel.train_step / data_generator (srpseudolabel/srpseudolabel.py:58-201, task_type 'cls'): one unlabelled
+        view whose own logits carry the gradient of the consistency loss; the model is called separately on x_lb and
+        x_ulb_w (identical to a concatenated call for a LayerNorm net)."""
+        c = self.cfg
+        x_lb, y_lb, x_u = batch["x_lb"], batch["y_lb"], batch["x_ulb_w"]
+        rec: dict = {}
+
+        def fwd(x):
+            masks = draw_drop_path_masks(self.vit_cfg, x.shape[0], self.drop_gen)
+            return vit_forward(self.p, x, self.vit_cfg, masks)
+        llb, flb = fwd(x_lb)
+        lu, fu = fwd(x_u)
+        sup_loss = ce_loss(llb, y_lb, "mean")
+        probs = torch.softmax(lu.detach(), dim=-1)                       # FixedThresholdingHook with softmax_x_ulb=True (:105)
+        mask = probs.max(dim=-1)[0].ge(c.p_cutoff).to(probs.dtype)
+        pseudo = lu.detach().argmax(dim=-1)                               # gen_ulb_targets(logits, use_hard_label=True) (:108-110)
+        if it > c.start_timing:
+            K = sr_decay(c.num_train_iter, it)
+            rec["K"] = K
+            for _ in range(K):                                            # data_generator (:58-88)
+                lk, fk = fwd(x_u)
+                pk = torch.softmax(lk.detach(), dim=-1)
+                mk = pk.max(dim=-1)[0].ge(c.p_cutoff).to(pk.dtype)
+                pseudo_k = lk.detach().argmax(dim=-1)
+                reward = rewarder_forward(self.rp, fk, pseudo_k)
+                mask2 = torch.where(reward >= reward.mean(), 1, 0).squeeze().float()
+                unsup_loss = consistency_loss(lk, pseudo_k, mk, mask2)
+                rec.update(dg_mask=mk, dg_mask2=mask2, dg_reward=reward.detach(), dg_pseudo=pseudo_k)
+        else:
+            unsup_loss = consistency_loss(lu, pseudo, mask)
+        if it > 0:
+            if it >= c.start_timing:
+                r = rewarder_forward(self.rp, fu.detach(), pseudo).mean()
+                self.max_reward = float(r) if float(r) > self.max_reward else self.max_reward
+                if it % c.N_k == 0 and it > c.start_timing:
+                    self.max_reward = -float("inf")
+                    self._sr_update(fu.detach(), pseudo, rec)
+            else:
+                self._sr_update(flb.detach(), y_lb, rec)
+        warm = float(np.clip(it / (c.unsup_warm_up * c.num_train_iter), a_min=0.0, a_max=1.0))   # :194
+        total = sup_loss + c.lambda_u * unsup_loss * warm
+        self.loss = total
+        rec.update(logits_lb=llb.detach(), logits_w=lu.detach(), feat_lb=flb.detach(), feat_w=fu.detach(), probs_w=probs, pseudo=pseudo,
+                   mask=mask, sup_loss=sup_loss.detach(), unsup_loss=unsup_loss.detach(), total_loss=total.detach(),
+                   util_ratio=mask.float().mean())
+        return rec
+
     # -- public ---------------------------------------------------------------------------------
     def train_step(self, batch: Dict[str, Tensor], it: int) -> dict:
         c = self.cfg
+        if c.algorithm == "srpseudolabel":
+            return self._train_step_pseudolabel(batch, it)
         x_lb, y_lb, x_ulb_w, x_ulb_s = batch["x_lb"], batch["y_lb"], batch["x_ulb_w"], batch["x_ulb_s"]
         idx_ulb = batch.get("idx_ulb")
         rec: dict = {}

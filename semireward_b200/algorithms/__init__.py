@@ -1,6 +1,6 @@
 """Algorithm lookup with the reference's surface (semilearn/algorithms/__init__.py:8-18)."""
 from ..core.registry import ALGORITHMS
-from . import srfixmatch, srflexmatch, srfreematch, srsoftmatch  # noqa: F401  (register the four algorithms under the reference's names)
+from . import srfixmatch, srflexmatch, srfreematch, srpseudolabel, srsoftmatch  # noqa: F401  (register the five SR algorithms under the reference's names)
 
 name2alg = ALGORITHMS
 

@@ -24,7 +24,7 @@ def build_oracle(cfg: dict, depth: int, seed: int = 0, head_gain: float = 4.0):
                       num_train_iter=cfg["num_train_iter"], num_warmup_iter=cfg["num_warmup_iter"], lr=cfg["lr"],
                       weight_decay=cfg["weight_decay"], layer_decay=cfg["layer_decay"], sr_lr=cfg["sr_lr"], feature_dim=cfg["feature_dim"],
                       ema_p=cfg.get("ema_p", 0.999), use_quantile=cfg.get("use_quantile", True), clip_thresh=cfg.get("clip_thresh", False),
-                      n_sigma=cfg.get("n_sigma", 2), lambda_e=cfg.get("ent_loss_ratio", 0.001))
+                      n_sigma=cfg.get("n_sigma", 2), lambda_e=cfg.get("ent_loss_ratio", 0.001), unsup_warm_up=cfg.get("unsup_warm_up", 0.4))
     return O.build_det_oracle(vc, sc, seed=seed, head_gain=head_gain)
 
 

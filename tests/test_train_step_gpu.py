@@ -163,13 +163,14 @@ def test_stochastic_stage2_batched_matches_sequential_passes(algorithm):
     ("srfreematch", dict(use_quantile=False, clip_thresh=True, ent_loss_ratio=0.05)),
     ("srsoftmatch", dict(n_sigma=2)),
     ("srfixmatch", dict(p_cutoff=0.5)),
+    ("srpseudolabel", dict(p_cutoff=0.5, unsup_warm_up=0.05)),
 ])
 def test_srfreematch_srsoftmatch_steps_vs_oracle(algorithm, over):
     """SRFreeMatch / SRSoftMatch native steps (stage 1, the gap step, stage 2 with and without an SR update) against the
     oracle from identical parameters: hard pseudo-labels and 0/1 masks bit-exact, SoftMatch's soft weights and the EMA state
     within 1e-4 (they integrate probabilities of logits that agree to ~4e-4), losses within 1e-3, gradients within 1e-3 relative."""
     cfg = small_cfg(algorithm=algorithm, ema_p=0.9, **over)   # momentum 0.9: the state moves visibly within 8 steps
-    hg = 2.0 if algorithm == "srfixmatch" else 4.0           # FixMatch: mixed masks at p_cutoff 0.5 (as in the golden case)
+    hg = 2.0 if algorithm in ("srfixmatch", "srpseudolabel") else 4.0   # mixed masks at p_cutoff 0.5 (as in the golden cases)
     orc = build_oracle(cfg, 2, head_gain=hg)
     alg = build_native(cfg, 2, head_gain=hg)
     tap = _grad_tap(alg)
@@ -190,7 +191,7 @@ def test_srfreematch_srsoftmatch_steps_vs_oracle(algorithm, over):
             assert abs(ld[k_native] - float(rec[k_or])) < 1e-3, f"it {it} {k_or}: {ld[k_native]} vs {float(rec[k_or])}"
         assert abs(ld["train/util_ratio"] - float(rec["util_ratio"])) < 1e-5
         assert torch.equal(alg._last_pseudo_label.cpu(), rec["pseudo"]), f"it {it}: pseudo labels differ"
-        if algorithm == "srfixmatch":
+        if algorithm in ("srfixmatch", "srpseudolabel"):
             assert torch.equal(alg._last_mask.cpu(), rec["mask"]), f"it {it}: mask differs"
         elif algorithm == "srfreematch":
             assert torch.equal(alg._last_mask.cpu(), rec["mask"]), f"it {it}: mask differs"
