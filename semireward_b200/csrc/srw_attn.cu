@@ -17,6 +17,7 @@
 #include <cuda.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 #include "../../include/srw.h"
@@ -77,6 +78,7 @@ __device__ __forceinline__ void store_out16(__nv_bfloat16* hi_ptr, int64_t plane
 // forward
 // ------------------------------------------------------------------------------------------------
 unsigned long long* g_attn_trace = nullptr;
+unsigned long long* g_attn_bwd_trace = nullptr;   // [2 kernels][B * H * row tiles][48]
 
 struct AttnFwdParams {
   int B, N, H, NP;        // NP = N rounded up to 16 (<= 272)
@@ -95,7 +97,7 @@ constexpr int FWD_THREADS = 512 + 32;   // 16 softmax warps (4 per TMEM lane qua
 // Rows beyond N (the third tile of N = 257 holds ONE valid row) skip all softmax work: MMA rows are independent, so their
 // stale P rows only produce discarded O rows.
 __global__ void __launch_bounds__(FWD_THREADS, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const AttnFwdParams p) {
+attn_fwd_smem_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   pdl_trigger();
@@ -326,6 +328,255 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
+// forward, P through tensor memory
+// ------------------------------------------------------------------------------------------------
+// Same decomposition as above (one CTA per (head, image), K/V staged once, loop over query tiles) but the probabilities
+// never touch shared memory: a softmax thread reads 16 fp32 scores of its row from TMEM, and writes the 16 probabilities
+// back IN PLACE as split bf16 — columns [16g, 16g+8) = packed hi pairs, [16g+8, 16g+16) = packed lo pairs of key group g —
+// and the PV product takes its A operand from TMEM (umma_bf16_ts).  Per key group that is two MMAs instead of three:
+//   [O | OX] += P_hi [V_hi | V_lo]   (one N = 128 MN-major operand: the lo plane is the second 64-wide chunk, LBO = plane)
+//        OX  += P_lo  V_hi
+// What this removes (scripts/attn_trace.py on the kernel above): the two 32 KB P buffers and their hand-back barrier —
+// a 1.8 us round trip per pair of 64-key chunks that made a tile cost 7.6 us whatever the softmax work — the
+// st.shared + fence.proxy.async of every P element, and a third of the PV instructions.  The freed shared memory double-
+// buffers Q, and the tensor pipe orders S(t+1) after PV(t) by itself (tcgen05.mma executes in issue order), so the next
+// tile's scores are computed while the softmax warps write the current tile's output.
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  pdl_trigger();
+  const int NP = p.NP;
+  const uint32_t kv_plane = (uint32_t)NP * 128;           // bytes of one K (or V) plane
+  const uint32_t off_k = 4 * ROW_TILE_BYTES;              // after the two Q buffers (hi, lo planes: 32 KiB each)
+  const uint32_t off_v = off_k + 2 * kv_plane;
+  const uint32_t off_bar = off_v + 2 * kv_plane;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bar);
+  uint64_t* bar_kv = bars + 0; uint64_t* bar_s = bars + 1; uint64_t* bar_o = bars + 2;
+  uint64_t* bar_ofree = bars + 3;  // softmax warps have read O (count 16)
+  uint64_t* bar_q = bars + 4;      // [2]
+  uint64_t* bar_p = bars + 6;      // [5] one per 64-key chunk (count 16), phase = tile parity
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  float* xch_base = reinterpret_cast<float*>(smem + off_bar + 128);   // [2][4][128] partial row max / row sum exchange, one set per tile parity
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int D = p.H * HD;
+  const int row0 = b * p.N;           // first token row of this image in the [B*N, 3D] qkv matrix
+  const int nchunks = (NP + 63) / 64;
+  const int ntiles = (p.N + 127) / 128;
+  unsigned long long* tr = p.trace ? p.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 32 : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
+
+  if (warp == 16 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_kv);
+    mbar_init(bar_kv, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_init(bar_ofree, 16);
+    mbar_init(&bar_q[0], 1); mbar_init(&bar_q[1], 1);
+    for (int c = 0; c < 5; ++c) mbar_init(&bar_p[c], 16);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t TM_S = tmem, TM_O = tmem + 384, TM_OX = tmem + 448;   // [O | OX] must be adjacent: one N = 128 MMA writes both
+  pdl_wait();   // CTA-local setup above; q/k/v come from the previous kernel
+
+  if (warp == 16) {
+    if (elect_one()) {   // one elected lane: the compiler keeps descriptors / addresses in uniform registers (no per-MMA R2UR waterfall)
+      // ---- K, V once; Q of tiles 0 and 1 ----
+      const int half = NP / 2;
+      mbar_arrive_expect_tx(bar_kv, 4 * kv_plane);
+      for (int pl = 0; pl < 2; ++pl)
+        for (int hf = 0; hf < 2; ++hf) {
+          tma_load_3d(smem + off_k + pl * kv_plane + hf * half * 128, &tmap_kv, bar_kv, D + h * HD, row0 + hf * half, pl);
+          tma_load_3d(smem + off_v + pl * kv_plane + hf * half * 128, &tmap_kv, bar_kv, 2 * D + h * HD, row0 + hf * half, pl);
+        }
+      for (int t = 0; t < 2 && t < ntiles; ++t) {
+        mbar_arrive_expect_tx(&bar_q[t], 2 * ROW_TILE_BYTES);
+        tma_load_3d(smem + t * 2 * ROW_TILE_BYTES, &tmap_q, &bar_q[t], h * HD, row0 + t * 128, 0);
+        tma_load_3d(smem + t * 2 * ROW_TILE_BYTES + ROW_TILE_BYTES, &tmap_q, &bar_q[t], h * HD, row0 + t * 128, 1);
+      }
+      mbar_wait(bar_kv, 0);
+      if (tr) tr[1] = clock64();                       // K, V landed
+      const uint64_t dq_hi = umma_smem_desc(smem_u32(smem), 16, 1024), dq_lo = umma_smem_desc(smem_u32(smem) + ROW_TILE_BYTES, 16, 1024);
+      const uint64_t dk_hi = umma_smem_desc(smem_u32(smem + off_k), 16, 1024), dk_lo = umma_smem_desc(smem_u32(smem + off_k) + kv_plane, 16, 1024);
+      const uint64_t dv_both = umma_smem_desc(smem_u32(smem + off_v), kv_plane, 1024);   // chunk 0 = V_hi, chunk 1 (LBO further) = V_lo
+      const uint64_t dv_hi = umma_smem_desc(smem_u32(smem + off_v), 1024, 1024);
+      constexpr uint32_t idesc_pv2 = umma_idesc_bf16(2 * HD, 0, 1), idesc_pv1 = umma_idesc_bf16(HD, 0, 1);
+      // scores in two MMAs per K step: keys [0, n1) and [n1, NP); 272 = 144 + 128 keeps both shapes large (an N = 16 MMA costs
+      // a third of an N = 256 one for a sixteenth of the work)
+      const int n1 = NP <= 256 ? NP : NP - 128, n2 = NP - n1;
+      const uint32_t idesc_s1 = umma_idesc_bf16(n1, 0, 0), idesc_s2 = umma_idesc_bf16(n2 > 0 ? n2 : 16, 0, 0);
+      const uint32_t boff2 = (uint32_t)(n1 * 128) >> 4;
+      for (int t = 0; t < ntiles; ++t) {
+        const uint32_t qo = (uint32_t)(t & 1) * ((2 * ROW_TILE_BYTES) >> 4);
+        mbar_wait(&bar_q[t & 1], (t >> 1) & 1);
+        tc_fence_after();
+        // ---- S = Q K^T (the tensor pipe runs these after the PV MMAs of tile t-1, which read P from the same columns) ----
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint64_t aq_hi = dq_hi + qo + kk * 2, aq_lo = dq_lo + qo + kk * 2;       // + 32 B per K step
+          umma_bf16(TM_S, aq_lo, dk_hi + kk * 2, idesc_s1, kk > 0 ? 1u : 0u);
+          umma_bf16(TM_S, aq_hi, dk_lo + kk * 2, idesc_s1, 1u);
+          umma_bf16(TM_S, aq_hi, dk_hi + kk * 2, idesc_s1, 1u);
+        }
+        if (n2 > 0) {
+#pragma unroll
+          for (int kk = 0; kk < HD / 16; ++kk) {
+            const uint64_t aq_hi = dq_hi + qo + kk * 2, aq_lo = dq_lo + qo + kk * 2;
+            umma_bf16(TM_S + n1, aq_lo, dk_hi + boff2 + kk * 2, idesc_s2, kk > 0 ? 1u : 0u);
+            umma_bf16(TM_S + n1, aq_hi, dk_lo + boff2 + kk * 2, idesc_s2, 1u);
+            umma_bf16(TM_S + n1, aq_hi, dk_hi + boff2 + kk * 2, idesc_s2, 1u);
+          }
+        }
+        umma_commit(bar_s);
+        if (t + 2 < ntiles) {
+          // this Q buffer is free once the S MMAs above are complete: fetch the tile after next into it
+          mbar_wait(bar_s, t & 1);
+          mbar_arrive_expect_tx(&bar_q[t & 1], 2 * ROW_TILE_BYTES);
+          tma_load_3d(smem + (t & 1) * 2 * ROW_TILE_BYTES, &tmap_q, &bar_q[t & 1], h * HD, row0 + (t + 2) * 128, 0);
+          tma_load_3d(smem + (t & 1) * 2 * ROW_TILE_BYTES + ROW_TILE_BYTES, &tmap_q, &bar_q[t & 1], h * HD, row0 + (t + 2) * 128, 1);
+        }
+        if (t > 0) mbar_wait(bar_ofree, (t - 1) & 1);      // the epilogue of tile t-1 has read O
+        // ---- [O | OX] += P_c V_c, P from tensor memory ----
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(&bar_p[c], t & 1);
+          tc_fence_after();
+          if (tr && t == 0 && (c == 2 || c == 3)) tr[c == 2 ? 28 : 30] = clock64();   // MMA thread: P chunk c visible
+          const int ksteps = min(4, (NP - c * 64) / 16);
+          const uint32_t pa = TM_S + c * 64;
+          const uint32_t vo = (uint32_t)c * 4 * 128;       // 16 keys = 2048 B of an MN-major plane = 128 in the address field
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            if (kk < ksteps) {
+              umma_bf16_ts(TM_O, pa + kk * 16, dv_both + vo + kk * 128, idesc_pv2, (c > 0 || kk > 0) ? 1u : 0u);
+              umma_bf16_ts(TM_OX, pa + kk * 16 + 8, dv_hi + vo + kk * 128, idesc_pv1, 1u);
+            }
+          }
+          if (tr && t == 0 && c == 2) tr[29] = clock64();                                // MMA thread: chunk 2 issued
+        }
+        umma_commit(bar_o);
+      }
+    }
+  } else {
+    // ---- softmax warps: 4 warps per TMEM lane quarter; thread == (query row, 16-key group `part` of every 64-key chunk) ----
+    const int q = warp & 3, part = warp >> 2;
+    const int r = q * 32 + lane;                     // 0..127, TMEM lane
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const float c2 = p.scale * LOG2E;
+    const int nsub = NP / 16;                        // 16-key groups; this thread owns groups part, part+4, ...
+    for (int t = 0; t < ntiles; ++t) {
+      const int qr = t * 128 + r;                    // query index inside the image
+      float* xch = xch_base + (t & 1) * 512;         // alternating sets: no barrier needed between tiles
+      const bool valid = qr < p.N;
+      const bool warp_valid = (t * 128 + q * 32) < p.N;   // any valid row in this warp (uniform per warp)
+      mbar_wait(bar_s, t & 1);
+      tc_fence_after();
+      if (tr && threadIdx.x == 0 && t < 3) tr[2 + 8 * t] = clock64();      // S ready
+      // The softmax warps are instruction-issue bound (16 warps on 4 schedulers, ~35 K elements per tile), so the element
+      // loops carry no per-element predicates: only the last key group can hold padding keys, and rows beyond N compute
+      // garbage that is never stored.
+      float m = -INFINITY;
+      if (warp_valid) {
+        for (int sc = part; sc < nsub; sc += 4) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(TM_S + lane_addr + sc * 16, v);
+          tmem_ld_wait();
+          if (sc * 16 + 16 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (sc * 16 + j < p.N) m = fmaxf(m, __uint_as_float(v[j]));
+          }
+        }
+      }
+      xch[part * 128 + r] = m;
+      ew_sync();
+      m = fmaxf(fmaxf(xch[r], xch[128 + r]), fmaxf(xch[256 + r], xch[384 + r]));
+      ew_sync();                                     // xch is reused for the row sums below
+      if (tr && threadIdx.x == 0 && t < 3) tr[3 + 8 * t] = clock64();      // row max known
+      const float mc = m * c2;
+      float sum = 0.f;
+      for (int c = 0; c < nchunks; ++c) {
+        const int sc = c * 4 + part;
+        if (sc < nsub && warp_valid) {
+          uint32_t v[16], w[16];
+          tmem_ld_32x32b_x16(TM_S + lane_addr + sc * 16, v);
+          tmem_ld_wait();
+          // ex2.approx (<= 2 ulp, flushes to zero below 2^-126): FFMA + MUFU + FADD + 3 for the split per element
+          if (sc * 16 + 16 <= p.N) {
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c2, -mc));
+              const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c2, -mc));
+              s0 += e0;
+              s1 += e1;
+              split2(e0, e1, w[j], w[8 + j]);        // hi pairs -> columns [0, 8), lo pairs -> [8, 16) of the group
+            }
+            sum += s0 + s1;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float e0 = (sc * 16 + 2 * j < p.N) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), c2, -mc)) : 0.f;
+              const float e1 = (sc * 16 + 2 * j + 1 < p.N) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c2, -mc)) : 0.f;
+              sum += e0 + e1;
+              split2(e0, e1, w[j], w[8 + j]);
+            }
+          }
+          tmem_st_32x32b_x16(TM_S + lane_addr + sc * 16, w);
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_p[c]);
+        if (tr && threadIdx.x == 0 && t < 3 && (c == 0 || c == nchunks - 1)) tr[(c == 0 ? 4 : 5) + 8 * t] = clock64();   // first / last P chunk handed over
+        if (tr && threadIdx.x == 0 && t == 0 && c == 2) tr[27] = clock64();                                                  // chunk 2 handed over
+      }
+      xch[part * 128 + r] = sum;
+      ew_sync();
+      sum = (xch[r] + xch[128 + r]) + (xch[256 + r] + xch[384 + r]);
+      // ---- epilogue: this thread writes output columns [16*part, 16*part+16) of its row ----
+      mbar_wait(bar_o, t & 1);
+      tc_fence_after();
+      if (tr && threadIdx.x == 0 && t < 3) tr[6 + 8 * t] = clock64();      // O complete
+      uint32_t a[16], x[16];
+      if (warp_valid) {
+        tmem_ld_32x32b_x16(TM_O + lane_addr + part * 16, a);
+        tmem_ld_32x32b_x16(TM_OX + lane_addr + part * 16, x);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_ofree);
+      if (valid) {
+        const float inv = 1.0f / sum;
+        if (part == 0 && p.lse) p.lse[((int64_t)b * p.H + h) * p.N + qr] = m * p.scale + logf(sum);
+        float o16[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o16[j] = (__uint_as_float(a[j]) + __uint_as_float(x[j])) * inv;
+        store_out16(p.o + (int64_t)(row0 + qr) * p.ld_o + h * HD + part * 16, p.o_ps, o16);
+      }
+      if (tr && threadIdx.x == 0 && t < 3) tr[7 + 8 * t] = clock64();      // tile stored
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
 enum { MODE_DQ = 0, MODE_DKV = 1 };
@@ -338,6 +589,7 @@ struct AttnBwdParams {
   const float* lse;                                  // [B,H,N]
   float* delta;                                      // [B,H,N]  written by MODE_DQ, read by MODE_DKV
   __nv_bfloat16* dqkv; int64_t ld_dqkv, dqkv_ps;
+  unsigned long long* trace;   // debug (srw_attn_set_bwd_trace): per CTA 48 clock64 stamps; NULL in production
 };
 
 constexpr int BWD_THREADS = 512 + 64;   // 16 element-wise warps + TMA warp + MMA warp
@@ -351,7 +603,7 @@ constexpr int BWD_SMEM = BWD_OFF_BAR + 256 + 1024;
 
 template <int MODE>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_constant__ CUtensorMap tm_do_r,
+attn_bwd_smem_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_constant__ CUtensorMap tm_do_r,
                 const __grid_constant__ CUtensorMap tm_qkv_c, const __grid_constant__ CUtensorMap tm_do_c, const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -375,6 +627,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
   const int row0 = b * p.N;
   const int nchunks = (p.NP + 63) / 64;
   const int64_t stat0 = ((int64_t)b * p.H + h) * p.N;
+  unsigned long long* tr = p.trace ? p.trace + (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 48 : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
 
   if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tm_qkv_r); tma_prefetch_desc(&tm_do_r); tma_prefetch_desc(&tm_qkv_c); tma_prefetch_desc(&tm_do_c);
@@ -443,10 +697,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       const uint64_t mc2h0 = umma_smem_desc(c2s0, 1024, 1024), mc2l0 = umma_smem_desc(c2s0 + ROW_TILE_BYTES / 2, 1024, 1024);
       constexpr uint32_t STAGE_STEP = BWD_CSTAGE >> 4;
       mbar_wait(bar_r, 0);
+      if (tr) tr[1] = clock64();                                   // R tiles landed
       auto issue_t = [&](int j) {
         const int s = j & 1;
         mbar_wait(&bar_cfull[s], (j >> 1) & 1);
         tc_fence_after();
+        if (tr && j < 5) tr[2 + 4 * j] = clock64();                // C chunk j landed, T MMAs go out
         const uint32_t t1 = tmem + s * 128, t2 = t1 + 64;
         const uint32_t so = s * STAGE_STEP;
 #pragma unroll
@@ -465,8 +721,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       for (int j = 0; j < nchunks; ++j) {
         const int s = j & 1;
         if (j + 1 < nchunks) issue_t(j + 1);
+        if (tr && j < 5) tr[3 + 4 * j] = clock64();                // T(j+1) issued
         mbar_wait(bar_x, j & 1);
         tc_fence_after();
+        if (tr && j < 5) tr[4 + 4 * j] = clock64();                // X(j) visible to the MMA thread
         const int ksteps = min(4, (p.NP - j * 64) / 16);
 #pragma unroll 4
         for (int kk = 0; kk < ksteps; ++kk) {
@@ -483,6 +741,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
         }
         umma_commit(bar_xfree);
         umma_commit(&bar_cfree[s]);
+        if (tr && j < 5) tr[5 + 4 * j] = clock64();                // Acc(j) issued + committed
       }
       umma_commit(bar_acc);
     }
@@ -525,6 +784,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       const int s = j & 1;
       mbar_wait(&bar_t[s], (j >> 1) & 1);
       tc_fence_after();
+      if (tr && threadIdx.x == 0 && j < 5) tr[22 + 4 * j] = clock64();   // T(j) complete
       uint32_t t1[16], t2[16];
       tmem_ld_32x32b_x16(tmem + lane_addr + s * 128 + part * 16, t1);
       tmem_ld_32x32b_x16(tmem + lane_addr + s * 128 + 64 + part * 16, t2);
@@ -544,17 +804,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
         xs[e] = ds;
         ys[e] = pe;
       }
+      if (tr && threadIdx.x == 0 && j < 5) tr[23 + 4 * j] = clock64();   // X(j) computed
       if (j >= 1) mbar_wait(bar_xfree, (j - 1) & 1);
+      if (tr && threadIdx.x == 0 && j < 5) tr[24 + 4 * j] = clock64();   // X buffer free
       store_row16_planes(x_hi, x_lo, r, part * 16, xs);
       if (MODE == MODE_DKV) store_row16_planes(y_hi, y_lo, r, part * 16, ys);
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_x);
+      if (tr && threadIdx.x == 0 && j < 5) tr[25 + 4 * j] = clock64();   // X(j) handed over
     }
     // ---- write the accumulators: this thread owns head-dim columns [16*part, 16*part+16) of its row ----
     mbar_wait(bar_acc, 0);
     tc_fence_after();
+    if (tr && threadIdx.x == 0) tr[42] = clock64();                      // accumulators complete
     const int nout = MODE == MODE_DQ ? 1 : 2;
     for (int w = 0; w < nout; ++w) {
       // DQ: dQ -> columns [0, D);  DKV: dK -> [D, 2D), dV -> [2D, 3D)
@@ -570,6 +834,280 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
         store_out16(p.dqkv + (int64_t)(row0 + rr) * p.ld_dqkv + col0, p.dqkv_ps, o16);
       }
     }
+    if (tr && threadIdx.x == 0) tr[43] = clock64();                      // stored
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, X / Y through tensor memory
+// ------------------------------------------------------------------------------------------------
+// Same skeleton as attn_bwd_smem_kernel, with the element-wise results handed to the accumulating MMAs through TMEM:
+// the threads overwrite the 64 fp32 columns of T1 (T2) with dS (P^T) as split bf16 — per 16-column group, 8 columns of
+// packed hi pairs then 8 of packed lo pairs — and the MMA takes A from there (umma_bf16_ts).  Per 16 chunk columns:
+//   [Acc | AccCross] += X_hi [C_hi | C_lo]   (N = 128: the lo plane of the C stage is the second 64-wide MN chunk)
+//        AccCross    += X_lo  C_hi
+// This removes the single X/Y shared-memory buffer and its hand-back barrier (the chunk loop was a chain
+// T -> threads -> st.shared -> fence.proxy -> MMA -> buffer free: 1.6 / 2.0 us per chunk in the dQ / dK,dV kernels for
+// 0.95 / 1.25 us of tensor time, scripts/attn_trace.py), a third of the accumulating MMAs, and runs the remaining ones
+// at the 35 / 69 clk of the TMEM-A forms instead of 50 clk (scripts/mma_probe.cu).  The freed 64 KB hold two more C
+// stages, so the column chunks are in flight long before the MMA thread asks for them.
+constexpr int BW2_NSTAGE = 4;
+constexpr int BW2_OFF_R1 = 0, BW2_OFF_R2 = 2 * ROW_TILE_BYTES, BW2_OFF_C = 4 * ROW_TILE_BYTES;
+constexpr int BW2_OFF_VEC = BW2_OFF_C + BW2_NSTAGE * BWD_CSTAGE;           // 2 x 320 floats (lse*log2e, delta*scale per column) + [4][128] exchange
+constexpr int BW2_OFF_BAR = BW2_OFF_VEC + 2 * 320 * 4 + 4 * 128 * 4;
+constexpr int BW2_SMEM = BW2_OFF_BAR + 256 + 1024;
+
+template <int MODE>
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_constant__ CUtensorMap tm_do_r,
+                const __grid_constant__ CUtensorMap tm_qkv_c, const __grid_constant__ CUtensorMap tm_do_c, const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BW2_OFF_BAR);
+  uint64_t* bar_r = bars + 0;
+  uint64_t* bar_acc = bars + 1;
+  uint64_t* bar_t = bars + 2;       // [2]
+  uint64_t* bar_x = bars + 4;       // [2] (count 16)
+  uint64_t* bar_cfull = bars + 6;   // [BW2_NSTAGE]
+  uint64_t* bar_cfree = bars + 10;  // [BW2_NSTAGE]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  float* vec_lse = reinterpret_cast<float*>(smem + BW2_OFF_VEC);
+  float* vec_delta = vec_lse + 320;
+  float* xch = vec_delta + 320;     // [4][128]
+
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int D = p.H * HD;
+  const int row0 = b * p.N;
+  const int nchunks = (p.NP + 63) / 64;
+  const int64_t stat0 = ((int64_t)b * p.H + h) * p.N;
+  unsigned long long* tr = p.trace ? p.trace + (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 48 : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
+
+  if (warp == 16 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv_r); tma_prefetch_desc(&tm_do_r); tma_prefetch_desc(&tm_qkv_c); tma_prefetch_desc(&tm_do_c);
+    mbar_init(bar_r, 1); mbar_init(bar_acc, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_t[s], 1); mbar_init(&bar_x[s], 16); }
+    for (int s = 0; s < BW2_NSTAGE; ++s) { mbar_init(&bar_cfull[s], 1); mbar_init(&bar_cfree[s], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  pdl_wait();   // barrier init / TMEM allocation above are CTA-local; everything below reads the previous kernels' outputs
+  if (MODE == MODE_DKV) {
+    // per-column (query) statistics, pre-scaled for the FFMA forms below
+    for (int i = threadIdx.x; i < p.NP; i += blockDim.x) {
+      vec_lse[i] = i < p.N ? p.lse[stat0 + i] * LOG2E : 0.f;
+      vec_delta[i] = i < p.N ? p.delta[stat0 + i] * p.scale : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM columns: T1[s] = s*128, T2[s] = s*128 + 64 (overwritten in place by X / Y); [AccX | cross] = 256, [AccY | cross] = 384
+  const int r1_col = (MODE == MODE_DQ ? 0 : D) + h * HD;       // R1: Q (DQ) / K (DKV)
+  const int r2_col = (MODE == MODE_DQ ? 0 : 2 * D) + h * HD;   // R2: dO (DQ, own matrix) / V (DKV)
+  const int c1_col = (MODE == MODE_DQ ? D : 0) + h * HD;       // C1: K (DQ) / Q (DKV)
+  const int c2_col = (MODE == MODE_DQ ? 2 * D : 0) + h * HD;   // C2: V (DQ) / dO (DKV, own matrix)
+
+  if (warp == 16) {
+    if (elect_one()) {
+      // ===== TMA producer =====
+      mbar_arrive_expect_tx(bar_r, 4 * ROW_TILE_BYTES);
+      tma_load_3d(smem + BW2_OFF_R1, &tm_qkv_r, bar_r, r1_col, row0 + rt * 128, 0);  // box planes = 2: hi, lo
+      if (MODE == MODE_DQ) tma_load_3d(smem + BW2_OFF_R2, &tm_do_r, bar_r, h * HD, row0 + rt * 128, 0);
+      else tma_load_3d(smem + BW2_OFF_R2, &tm_qkv_r, bar_r, r2_col, row0 + rt * 128, 0);
+      for (int j = 0; j < nchunks; ++j) {
+        const int st_i = j % BW2_NSTAGE;
+        mbar_wait(&bar_cfree[st_i], ((j / BW2_NSTAGE) & 1) ^ 1);
+        uint8_t* st = smem + BW2_OFF_C + st_i * BWD_CSTAGE;
+        mbar_arrive_expect_tx(&bar_cfull[st_i], BWD_CSTAGE);
+        tma_load_3d(st, &tm_qkv_c, &bar_cfull[st_i], c1_col, row0 + j * 64, 0);
+        if (MODE == MODE_DQ) tma_load_3d(st + ROW_TILE_BYTES, &tm_qkv_c, &bar_cfull[st_i], c2_col, row0 + j * 64, 0);
+        else tma_load_3d(st + ROW_TILE_BYTES, &tm_do_c, &bar_cfull[st_i], h * HD, row0 + j * 64, 0);
+      }
+    }
+  } else if (warp == 17) {
+    if (elect_one()) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc_t = umma_idesc_bf16(64, 0, 0);        // T = R C^T   (both K-major, K = head dim)
+      constexpr uint32_t idesc_a2 = umma_idesc_bf16(128, 0, 1);      // [Acc | cross] += X_hi [C_hi | C_lo]   (C MN-major, K = chunk columns)
+      constexpr uint32_t idesc_a1 = umma_idesc_bf16(64, 0, 1);       //        cross  += X_lo  C_hi
+      const uint32_t r1 = smem_u32(smem + BW2_OFF_R1), r2 = smem_u32(smem + BW2_OFF_R2);
+      const uint64_t dr1h = umma_smem_desc(r1, 16, 1024), dr1l = umma_smem_desc(r1 + ROW_TILE_BYTES, 16, 1024);
+      const uint64_t dr2h = umma_smem_desc(r2, 16, 1024), dr2l = umma_smem_desc(r2 + ROW_TILE_BYTES, 16, 1024);
+      // C stage 0 views: K-major (T MMAs), MN-major hi plane alone and hi|lo as one 128-wide operand (LBO = plane distance);
+      // stage s = + s * (BWD_CSTAGE >> 4) in the address field
+      const uint32_t c1s0 = smem_u32(smem + BW2_OFF_C), c2s0 = c1s0 + ROW_TILE_BYTES;
+      constexpr uint32_t PLANE = ROW_TILE_BYTES / 2;                  // 64 rows x 128 B
+      const uint64_t dc1h0 = umma_smem_desc(c1s0, 16, 1024), dc1l0 = umma_smem_desc(c1s0 + PLANE, 16, 1024);
+      const uint64_t dc2h0 = umma_smem_desc(c2s0, 16, 1024), dc2l0 = umma_smem_desc(c2s0 + PLANE, 16, 1024);
+      const uint64_t mc1h0 = umma_smem_desc(c1s0, 1024, 1024), mc1b0 = umma_smem_desc(c1s0, PLANE, 1024);
+      const uint64_t mc2h0 = umma_smem_desc(c2s0, 1024, 1024), mc2b0 = umma_smem_desc(c2s0, PLANE, 1024);
+      constexpr uint32_t STAGE_STEP = BWD_CSTAGE >> 4;
+      mbar_wait(bar_r, 0);
+      if (tr) tr[1] = clock64();                                   // R tiles landed
+      auto issue_t = [&](int j) {
+        const int s = j & 1, st_i = j % BW2_NSTAGE;
+        mbar_wait(&bar_cfull[st_i], (j / BW2_NSTAGE) & 1);
+        tc_fence_after();
+        if (tr && j < 5) tr[2 + 4 * j] = clock64();                // C chunk j landed, T MMAs go out
+        const uint32_t t1 = tmem + s * 128, t2 = t1 + 64;
+        const uint32_t so = st_i * STAGE_STEP;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t ko = kk * 2;
+          umma_bf16(t1, dr1l + ko, dc1h0 + so + ko, idesc_t, kk > 0 ? 1u : 0u);
+          umma_bf16(t1, dr1h + ko, dc1l0 + so + ko, idesc_t, 1u);
+          umma_bf16(t1, dr1h + ko, dc1h0 + so + ko, idesc_t, 1u);
+          umma_bf16(t2, dr2l + ko, dc2h0 + so + ko, idesc_t, kk > 0 ? 1u : 0u);
+          umma_bf16(t2, dr2h + ko, dc2l0 + so + ko, idesc_t, 1u);
+          umma_bf16(t2, dr2h + ko, dc2h0 + so + ko, idesc_t, 1u);
+        }
+        umma_commit(&bar_t[s]);
+      };
+      issue_t(0);
+      for (int j = 0; j < nchunks; ++j) {
+        const int s = j & 1, st_i = j % BW2_NSTAGE;
+        // T(j+1) overwrites the columns that held X(j-1): the tensor pipe runs it after Acc(j-1), issued last iteration
+        if (j + 1 < nchunks) issue_t(j + 1);
+        if (tr && j < 5) tr[3 + 4 * j] = clock64();                // T(j+1) issued
+        mbar_wait(&bar_x[s], (j >> 1) & 1);
+        tc_fence_after();
+        if (tr && j < 5) tr[4 + 4 * j] = clock64();                // X(j) visible to the MMA thread
+        const int ksteps = min(4, (p.NP - j * 64) / 16);
+        const uint32_t xa = tmem + s * 128, ya = xa + 64;
+        const uint32_t so = st_i * STAGE_STEP;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (kk < ksteps) {
+            const uint32_t acc = (j > 0 || kk > 0) ? 1u : 0u;
+            const uint32_t bo = kk * 128 + so;                     // 16 chunk rows = 2048 B of an MN-major plane
+            umma_bf16_ts(tmem + 256, xa + kk * 16, mc1b0 + bo, idesc_a2, acc);
+            umma_bf16_ts(tmem + 320, xa + kk * 16 + 8, mc1h0 + bo, idesc_a1, 1u);
+            if (MODE == MODE_DKV) {
+              umma_bf16_ts(tmem + 384, ya + kk * 16, mc2b0 + bo, idesc_a2, acc);
+              umma_bf16_ts(tmem + 448, ya + kk * 16 + 8, mc2h0 + bo, idesc_a1, 1u);
+            }
+          }
+        }
+        umma_commit(&bar_cfree[st_i]);
+        if (tr && j < 5) tr[5 + 4 * j] = clock64();                // Acc(j) issued + committed
+      }
+      umma_commit(bar_acc);
+    }
+  } else {
+    // ===== element-wise warps: 4 per TMEM lane quarter; thread == (tile row, 16-column group `part` of each 64-column chunk) =====
+    const int q = warp & 3, part = warp >> 2;
+    const int r = q * 32 + lane;
+    const int rr = rt * 128 + r;            // row index inside the image (query for DQ, key for DKV)
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const float c2s = p.scale * LOG2E;
+    float row_lse = 0.f, row_dsc = 0.f;     // lse * log2e, delta * scale of this thread's row (DQ)
+    if (MODE == MODE_DQ) {
+      // delta = sum_d dO * O over this head's 64 columns; each of the row's 4 threads sums 16 of them
+      float acc = 0.f;
+      if (rr < p.N) {
+        row_lse = p.lse[stat0 + rr] * LOG2E;
+        const __nv_bfloat16* orow = p.o + (int64_t)(row0 + rr) * p.ld_o + h * HD + part * 16;
+        const __nv_bfloat16* drow = p.d_o + (int64_t)(row0 + rr) * p.ld_do + h * HD + part * 16;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const uint4 oh = *reinterpret_cast<const uint4*>(orow + g * 8), ol = *reinterpret_cast<const uint4*>(orow + p.o_ps + g * 8);
+          const uint4 dh = *reinterpret_cast<const uint4*>(drow + g * 8), dl = *reinterpret_cast<const uint4*>(drow + p.do_ps + g * 8);
+          const uint32_t ohh[4] = {oh.x, oh.y, oh.z, oh.w}, oll[4] = {ol.x, ol.y, ol.z, ol.w};
+          const uint32_t dhh[4] = {dh.x, dh.y, dh.z, dh.w}, dll[4] = {dl.x, dl.y, dl.z, dl.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc = fmaf(bf16_lo_f(ohh[j]) + bf16_lo_f(oll[j]), bf16_lo_f(dhh[j]) + bf16_lo_f(dll[j]), acc);
+            acc = fmaf(bf16_hi_f(ohh[j]) + bf16_hi_f(oll[j]), bf16_hi_f(dhh[j]) + bf16_hi_f(dll[j]), acc);
+          }
+        }
+      }
+      xch[part * 128 + r] = acc;
+      ew_sync();
+      const float row_delta = (xch[r] + xch[128 + r]) + (xch[256 + r] + xch[384 + r]);
+      if (part == 0 && rr < p.N) p.delta[stat0 + rr] = row_delta;
+      row_dsc = row_delta * p.scale;
+    }
+    for (int j = 0; j < nchunks; ++j) {
+      const int s = j & 1;
+      const int col0 = j * 64 + part * 16;          // first key (DQ) / query (DKV) column of this thread's group
+      mbar_wait(&bar_t[s], (j >> 1) & 1);
+      tc_fence_after();
+      if (tr && threadIdx.x == 0 && j < 5) tr[22 + 4 * j] = clock64();   // T(j) complete
+      if (col0 < p.NP) {
+        uint32_t t1[16], t2[16], xw[16], yw[16];
+        const uint32_t ta = tmem + lane_addr + s * 128 + part * 16;
+        tmem_ld_32x32b_x16(ta, t1);
+        tmem_ld_32x32b_x16(ta + 64, t2);
+        tmem_ld_wait();
+        // P = exp2(S * scale*log2e - lse*log2e), dS = P * (dP - delta) * scale.  Issue-bound warps: no per-element predicates
+        // (only the last group of the image can hold padding columns), ex2.approx, everything folded into FFMAs.
+        const bool full = col0 + 16 <= p.N;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float pe0, pe1, ds0, ds1;
+          if (MODE == MODE_DQ) {
+            pe0 = ex2_approx(fmaf(__uint_as_float(t1[2 * e]), c2s, -row_lse));
+            pe1 = ex2_approx(fmaf(__uint_as_float(t1[2 * e + 1]), c2s, -row_lse));
+            ds0 = pe0 * fmaf(__uint_as_float(t2[2 * e]), p.scale, -row_dsc);
+            ds1 = pe1 * fmaf(__uint_as_float(t2[2 * e + 1]), p.scale, -row_dsc);
+          } else {
+            const float2 l2 = *reinterpret_cast<const float2*>(vec_lse + col0 + 2 * e);
+            const float2 d2 = *reinterpret_cast<const float2*>(vec_delta + col0 + 2 * e);
+            pe0 = ex2_approx(fmaf(__uint_as_float(t1[2 * e]), c2s, -l2.x));
+            pe1 = ex2_approx(fmaf(__uint_as_float(t1[2 * e + 1]), c2s, -l2.y));
+            ds0 = pe0 * fmaf(__uint_as_float(t2[2 * e]), p.scale, -d2.x);
+            ds1 = pe1 * fmaf(__uint_as_float(t2[2 * e + 1]), p.scale, -d2.y);
+          }
+          if (!full) {
+            if (col0 + 2 * e >= p.N) pe0 = 0.f, ds0 = 0.f;
+            if (col0 + 2 * e + 1 >= p.N) pe1 = 0.f, ds1 = 0.f;
+          }
+          split2(ds0, ds1, xw[e], xw[8 + e]);          // hi pairs -> columns [0, 8), lo pairs -> [8, 16) of the group
+          if (MODE == MODE_DKV) split2(pe0, pe1, yw[e], yw[8 + e]);
+        }
+        if (tr && threadIdx.x == 0 && j < 5) tr[23 + 4 * j] = clock64();   // X(j) computed
+        tmem_st_32x32b_x16(ta, xw);
+        if (MODE == MODE_DKV) tmem_st_32x32b_x16(ta + 64, yw);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_x[s]);
+      if (tr && threadIdx.x == 0 && j < 5) tr[25 + 4 * j] = clock64();   // X(j) handed over
+    }
+    // ---- write the accumulators: this thread owns head-dim columns [16*part, 16*part+16) of its row ----
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    if (tr && threadIdx.x == 0) tr[42] = clock64();                      // accumulators complete
+    const int nout = MODE == MODE_DQ ? 1 : 2;
+    for (int w = 0; w < nout; ++w) {
+      // DQ: dQ -> columns [0, D);  DKV: dK -> [D, 2D), dV -> [2D, 3D)
+      const int ocol = (MODE == MODE_DQ ? 0 : (w == 0 ? D : 2 * D)) + h * HD + part * 16;
+      uint32_t a[16], x[16];
+      tmem_ld_32x32b_x16(tmem + lane_addr + 256 + w * 128 + part * 16, a);
+      tmem_ld_32x32b_x16(tmem + lane_addr + 320 + w * 128 + part * 16, x);
+      tmem_ld_wait();
+      if (rr < p.N) {
+        float o16[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o16[e] = __uint_as_float(a[e]) + __uint_as_float(x[e]);
+        store_out16(p.dqkv + (int64_t)(row0 + rr) * p.ld_dqkv + ocol, p.dqkv_ps, o16);
+      }
+    }
+    if (tr && threadIdx.x == 0) tr[43] = clock64();                      // stored
   }
   tc_fence_before();
   __syncthreads();
@@ -613,7 +1151,13 @@ extern "C" int srw_attn_fwd(const srw_attn_fwd_args* a, void* stream_) {
   const int smem_bytes = (int)(4 * ROW_TILE_BYTES + 4 * kv_plane + 128 + 2 * 4 * 128 * 4 + 1024);   // regions A, B | K | V | barriers | 2 exchange sets | align
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  static bool smem_p = false;   // SRW_ATTN_FWD=smem: the previous kernel (P through shared memory), kept for A/B measurements
+  std::call_once(once, [] {
+    const char* e = getenv("SRW_ATTN_FWD");
+    smem_p = e && e[0] == 's';
+    attr_err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(attn_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
   SRW_CUDA(attr_err);
   AttnFwdParams p;
   p.B = a->B; p.N = a->N; p.H = a->H; p.NP = NP; p.scale = a->scale;
@@ -622,7 +1166,7 @@ extern "C" int srw_attn_fwd(const srw_attn_fwd_args* a, void* stream_) {
   dim3 grid(a->H, a->B);
   const double pair_flops = 2.0 * a->B * a->H * (double)a->N * a->N * HD;   // one N x N x 64 product per (image, head)
   void* prof = prof_begin(SRW_PROF_ATTN_FWD, 2.0 * pair_flops, 4.0 * 4.0 * a->B * a->N * a->H * HD, stream);
-  SRW_CUDA(launch_pdl(attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), smem_bytes, stream, tq, tkv, p));
+  SRW_CUDA(launch_pdl(smem_p ? attn_fwd_smem_kernel : attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), smem_bytes, stream, tq, tkv, p));
   prof_end(prof, stream);
   g_launches++;
   SRW_LAUNCH_CHECK();
@@ -647,10 +1191,14 @@ extern "C" int srw_attn_bwd(const srw_attn_bwd_args* a, void* stream_) {
               "srw_attn_bwd: planes must be 16-byte aligned");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
+  static bool smem_x = false;   // SRW_ATTN_BWD=smem: the previous kernels (X / Y through shared memory), kept for A/B measurements
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(attn_bwd_kernel<MODE_DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(attn_bwd_kernel<MODE_DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    const char* e = getenv("SRW_ATTN_BWD");
+    smem_x = e && e[0] == 's';
+    attr_err = cudaFuncSetAttribute(attn_bwd_kernel<MODE_DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW2_SMEM);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(attn_bwd_kernel<MODE_DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW2_SMEM);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(attn_bwd_smem_kernel<MODE_DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(attn_bwd_smem_kernel<MODE_DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
   });
   SRW_CUDA(attr_err);
   AttnBwdParams p;
@@ -659,14 +1207,18 @@ extern "C" int srw_attn_bwd(const srw_attn_bwd_args* a, void* stream_) {
   p.d_o = reinterpret_cast<const __nv_bfloat16*>(a->d_o); p.ld_do = a->ld_do; p.do_ps = a->do_plane_stride;
   p.lse = a->lse; p.delta = a->delta;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(a->dqkv); p.ld_dqkv = a->ld_dqkv; p.dqkv_ps = a->dqkv_plane_stride;
+  p.trace = g_attn_bwd_trace;
   dim3 grid(cdiv(a->N, 128), a->H, a->B);
   // algorithmic backward = 4 products (dP, dV, dQ, dK); the S recomputations are overhead, not counted
   const double pair_flops = 2.0 * a->B * a->H * (double)a->N * a->N * HD;
   void* prof = prof_begin(SRW_PROF_ATTN_BWD, 4.0 * pair_flops, 4.0 * 9.0 * a->B * a->N * a->H * HD, stream);
-  SRW_CUDA(launch_pdl(attn_bwd_kernel<MODE_DQ>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p));
+  SRW_CUDA(smem_x ? launch_pdl(attn_bwd_smem_kernel<MODE_DQ>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p)
+                  : launch_pdl(attn_bwd_kernel<MODE_DQ>, dim3(grid), dim3(BWD_THREADS), BW2_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p));
   g_launches++;
   SRW_LAUNCH_CHECK();
-  SRW_CUDA(launch_pdl(attn_bwd_kernel<MODE_DKV>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p));
+  if (p.trace) p.trace += (size_t)grid.x * grid.y * grid.z * 48;
+  SRW_CUDA(smem_x ? launch_pdl(attn_bwd_smem_kernel<MODE_DKV>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p)
+                  : launch_pdl(attn_bwd_kernel<MODE_DKV>, dim3(grid), dim3(BWD_THREADS), BW2_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p));
   prof_end(prof, stream);
   g_launches++;
   SRW_LAUNCH_CHECK();
@@ -676,5 +1228,9 @@ extern "C" int srw_attn_bwd(const srw_attn_bwd_args* a, void* stream_) {
 // debug: per-CTA clock64 timeline of attn_fwd_kernel into buf[B * H][32] (NULL turns it off).  Not part of include/srw.h.
 extern "C" int srw_attn_set_trace(unsigned long long* buf) {
   srw::g_attn_trace = buf;
+  return SRW_OK;
+}
+extern "C" int srw_attn_set_bwd_trace(unsigned long long* buf) {
+  srw::g_attn_bwd_trace = buf;
   return SRW_OK;
 }

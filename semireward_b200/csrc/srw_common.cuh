@@ -242,6 +242,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]: A is read from tensor memory (lane == row, 32-bit column j holds K elements 2j
+// (low half) and 2j+1, so a K = 16 step is 8 columns).  scripts/mma_probe.cu: an M128 N64 K16 MMA costs 35 clk this way
+// against 50 clk with A from shared memory (the 4 KB A read is what bounds the small-N shapes).
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrives once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -270,6 +281,16 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 lanes x 16 consecutive 32-bit columns, registers -> tensor memory (thread t writes row lane base + t)
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory matrix descriptor (sm_100 format, version=1), SWIZZLE_128B.
 //   start address >>4 in [0,14), LBO>>4 in [16,30), SBO>>4 in [32,46), version(=1) in [46,48), layout type in [61,64).

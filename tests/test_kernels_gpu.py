@@ -130,7 +130,7 @@ def _attn_ref(qkv, B, N, H):
     return o, torch.logsumexp(s, -1)
 
 
-@pytest.mark.parametrize("B,N,H", [(3, 257, 6), (2, 197, 2), (1, 64, 1), (2, 272, 1)])
+@pytest.mark.parametrize("B,N,H", [(3, 257, 6), (2, 197, 2), (1, 64, 1), (2, 272, 1), (1, 16, 1), (2, 129, 2), (1, 256, 1), (2, 65, 1), (1, 144, 2)])
 def test_attention_fwd_bwd(ops, B, N, H):
     D = H * 64
     qkv = _rand(B * N, 3 * D, seed=20, scale=1.5)
