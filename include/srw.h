@@ -108,7 +108,23 @@ typedef struct {
   float* out; int accumulate;
   float* workspace;  /* >= 256 * cols floats */
 } srw_colsum_args;
-int srw_colsum(const srw_colsum_args* a, void* stream);
+int srw_colsum(const srw_colsum_args* a, void* stream);   /* out == NULL: leave the partial sums in `workspace` ([srw_colsum_nparts(rows)][cols]) for srw_grad_fold */
+int srw_colsum_nparts(int rows);
+int srw_layernorm_bwd_nparts(int rows);                    /* partial sets srw_layernorm_bwd leaves in its workspace ([nparts][3][cols]: dgamma, dbeta, column sums) */
+
+/* One launch that folds everything a transformer block's backward leaves behind: up to 4 split-K workspaces (the weight
+ * gradients) and up to 8 sets of partial column sums (bias / LayerNorm parameter gradients; srw_colsum with out == NULL,
+ * srw_layernorm_bwd with dgamma == NULL).  Replaces 8 launches of 3-6 us each per block; results are bit-identical to the
+ * separate srw_splitk_reduce / reduce launches (same summation order). */
+typedef struct {
+  const float* partial; int nparts; int64_t stride_p;   /* partial[p * stride_p + c] */
+  int cols; float* out; int accumulate;
+} srw_fold_colsum;
+typedef struct {
+  int n_splitk; srw_splitk_reduce_args splitk[4];
+  int n_colsum; srw_fold_colsum colsum[8];
+} srw_grad_fold_args;
+int srw_grad_fold(const srw_grad_fold_args* a, void* stream);
 
 /* ---- LayerNorm (vit.py:164-165, 282: nn.LayerNorm eps 1e-6) -------------------------------------------------- */
 typedef struct {

@@ -43,6 +43,14 @@ class ColsumArgs(C.Structure):
                 ("rows_per_scale", i32), ("rows", i32), ("cols", i32), ("out", vp), ("accumulate", i32), ("workspace", vp)]
 
 
+class FoldColsum(C.Structure):
+    _fields_ = [("partial", vp), ("nparts", i32), ("stride_p", i64), ("cols", i32), ("out", vp), ("accumulate", i32)]
+
+
+class GradFoldArgs(C.Structure):
+    _fields_ = [("n_splitk", i32), ("splitk", SplitKReduceArgs * 4), ("n_colsum", i32), ("colsum", FoldColsum * 8)]
+
+
 class LayerNormFwdArgs(C.Structure):
     _fields_ = [("x", vp), ("ldx", i64), ("rows", i32), ("cols", i32), ("eps", f32), ("gamma", vp), ("beta", vp),
                 ("mean", vp), ("rstd", vp), ("y_planes", vp), ("ldp", i64), ("plane_stride", i64), ("y_f32", vp), ("ldy", i64)]
@@ -170,6 +178,9 @@ SYMBOLS = [
     ("srw_gemm", i32, [C.POINTER(GemmArgs), vp]),
     ("srw_splitk_reduce", i32, [C.POINTER(SplitKReduceArgs), vp]),
     ("srw_colsum", i32, [C.POINTER(ColsumArgs), vp]),
+    ("srw_colsum_nparts", i32, [i32]),
+    ("srw_layernorm_bwd_nparts", i32, [i32]),
+    ("srw_grad_fold", i32, [C.POINTER(GradFoldArgs), vp]),
     ("srw_layernorm_fwd", i32, [C.POINTER(LayerNormFwdArgs), vp]),
     ("srw_layernorm_bwd", i32, [C.POINTER(LayerNormBwdArgs), vp]),
     ("srw_attn_fwd", i32, [C.POINTER(AttnFwdArgs), vp]),

@@ -203,6 +203,62 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// grad fold: every deferred reduction of one transformer block's backward in one launch
+// ------------------------------------------------------------------------------------------------
+struct FoldParams {
+  int n_splitk, n_colsum;
+  int first_block[13];   // blocks [first_block[i], first_block[i+1]) work on problem i (split-K problems first)
+  srw_splitk_reduce_args sk[4];
+  srw_fold_colsum cs[8];
+};
+
+__global__ void __launch_bounds__(256) grad_fold_kernel(const __grid_constant__ FoldParams fp) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float red[8][33];
+  const int nprob = fp.n_splitk + fp.n_colsum;
+  int prob = 0;
+  while (prob + 1 < nprob && (int)blockIdx.x >= fp.first_block[prob + 1]) ++prob;
+  const int local = blockIdx.x - fp.first_block[prob], nblk = fp.first_block[prob + 1] - fp.first_block[prob];
+  if (prob < fp.n_splitk) {
+    // same order as splitk_reduce_kernel: slices 0 .. split-1, then the previous value
+    const srw_splitk_reduce_args& a = fp.sk[prob];
+    const int64_t MN = (int64_t)a.M * a.N, total4 = MN / 4;
+    for (int64_t i = local * 256 + threadIdx.x; i < total4; i += (int64_t)nblk * 256) {
+      const int64_t e = i * 4;
+      const int m = (int)(e / a.N), n = (int)(e % a.N);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < a.split_k; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(a.workspace + (int64_t)s * MN + e);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      float4* dst = reinterpret_cast<float4*>(a.out + (int64_t)m * a.ldo + n);
+      if (a.accumulate) {
+        const float4 o = *dst;
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+      }
+      *dst = acc;
+    }
+  } else {
+    // same order as reduce_partials_kernel: 8 warps split the partials, then a fixed-order fold
+    const srw_fold_colsum& a = fp.cs[prob - fp.n_splitk];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = local * 32 + tx;
+    float acc = 0.f;
+    if (c < a.cols)
+      for (int p = ty; p < a.nparts; p += 8) acc += a.partial[(int64_t)p * a.stride_p + c];
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && c < a.cols) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += red[i][tx];
+      a.out[c] = a.accumulate ? a.out[c] + s : s;
+    }
+  }
+}
+
 __global__ void colsum_stage2_kernel(const float* __restrict__ partial, int nparts, int cols, float* __restrict__ out, int accumulate) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
@@ -539,13 +595,14 @@ extern "C" int srw_splitk_reduce(const srw_splitk_reduce_args* a, void* stream_)
 
 extern "C" int srw_colsum(const srw_colsum_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  SRW_REQUIRE(a && (a->x || a->planes) && a->out && a->workspace && a->rows > 0 && a->cols > 0, "srw_colsum: bad args");
-  const int nparts = std::min(64, cdiv(a->rows, 32));
+  SRW_REQUIRE(a && (a->x || a->planes) && a->workspace && a->rows > 0 && a->cols > 0, "srw_colsum: bad args");
+  const int nparts = srw_colsum_nparts(a->rows);
   if (a->planes && !a->row_scale && a->cols % 8 == 0 && a->ldp % 8 == 0 && a->plane_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(a->planes) & 15) == 0) {
     SRW_CUDA(launch_pdl(colsum_planes_kernel, dim3(dim3(cdiv(a->cols, 256), nparts)), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(a->planes), a->ldp, a->plane_stride,
                                                                               a->rows, a->cols, a->workspace));
     g_launches++;
     SRW_LAUNCH_CHECK();
+    if (!a->out) return SRW_OK;   // the caller folds the partials (srw_grad_fold)
     SRW_CUDA(launch_pdl(reduce_partials_kernel, dim3(dim3(cdiv(a->cols, 32), 1)), dim3(256), 0, stream, a->workspace, nparts, a->cols, 0, a->cols, a->out, nullptr, a->accumulate, nullptr, 0));
     g_launches++;
     SRW_LAUNCH_CHECK();
@@ -556,7 +613,38 @@ extern "C" int srw_colsum(const srw_colsum_args* a, void* stream_) {
                                                 a->row_scale, a->rows_per_scale > 0 ? a->rows_per_scale : 1, a->rows, a->cols, a->workspace);
   g_launches++;
   SRW_LAUNCH_CHECK();
+  if (!a->out) return SRW_OK;
   SRW_CUDA(launch_pdl(reduce_partials_kernel, dim3(dim3(cdiv(a->cols, 32), 1)), dim3(256), 0, stream, a->workspace, nparts, a->cols, 0, a->cols, a->out, nullptr, a->accumulate, nullptr, 0));
+  g_launches++;
+  SRW_LAUNCH_CHECK();
+  return SRW_OK;
+}
+
+extern "C" int srw_colsum_nparts(int rows) { return std::min(64, cdiv(rows, 32)); }
+extern "C" int srw_layernorm_bwd_nparts(int rows) { return std::min(256, cdiv(rows, 8)); }
+
+extern "C" int srw_grad_fold(const srw_grad_fold_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SRW_REQUIRE(a && a->n_splitk >= 0 && a->n_splitk <= 4 && a->n_colsum >= 0 && a->n_colsum <= 8 && a->n_splitk + a->n_colsum > 0, "srw_grad_fold: bad counts");
+  FoldParams fp = {};
+  fp.n_splitk = a->n_splitk; fp.n_colsum = a->n_colsum;
+  int nb = 0, k = 0;
+  for (int i = 0; i < a->n_splitk; ++i, ++k) {
+    const srw_splitk_reduce_args& r = a->splitk[i];
+    SRW_REQUIRE(r.workspace && r.out && r.split_k >= 1 && r.N % 4 == 0 && r.ldo % 4 == 0, "srw_grad_fold: bad split-K problem %d", i);
+    fp.sk[i] = r;
+    fp.first_block[k] = nb;
+    nb += (int)std::min<int64_t>(cdiv64((int64_t)r.M * r.N / 4, 256), 148 * 2);
+  }
+  for (int i = 0; i < a->n_colsum; ++i, ++k) {
+    const srw_fold_colsum& r = a->colsum[i];
+    SRW_REQUIRE(r.partial && r.out && r.nparts >= 1 && r.cols > 0, "srw_grad_fold: bad column-sum problem %d", i);
+    fp.cs[i] = r;
+    fp.first_block[k] = nb;
+    nb += cdiv(r.cols, 32);
+  }
+  fp.first_block[k] = nb;
+  SRW_CUDA(launch_pdl(grad_fold_kernel, dim3(nb), dim3(256), 0, stream, fp));
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;
@@ -590,7 +678,7 @@ extern "C" int srw_layernorm_bwd(const srw_layernorm_bwd_args* a, void* stream_)
   SRW_REQUIRE(a && a->dy && a->x && a->gamma && a->mean && a->rstd && a->dx && a->workspace && a->rows > 0, "srw_layernorm_bwd: bad args");
   SRW_REQUIRE(!a->dx_planes || (a->ldp > 0 && a->plane_stride > 0), "srw_layernorm_bwd: dx_planes needs ldp / plane_stride");
   SRW_REQUIRE(a->cols % 32 == 0 && a->cols <= 1024, "srw_layernorm_bwd: cols must be a multiple of 32 and <= 1024 (cols=%d)", a->cols);
-  const int nblocks = std::min(256, cdiv(a->rows, 8));
+  const int nblocks = srw_layernorm_bwd_nparts(a->rows);
 #define SRW_LN_BWD(J)                                                                                                             \
   case J:                                                                                                                         \
     SRW_CUDA(launch_pdl(layernorm_bwd_kernel<J>, dim3(nblocks), dim3(256), 0, stream, a->dy, a->lddy, a->x, a->ldx, a->rows, a->gamma, a->mean, a->rstd, a->dx, \

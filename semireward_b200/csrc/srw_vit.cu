@@ -263,6 +263,9 @@ struct Layout {
   // backward scratch
   int64_t dt, g, dz, dy, d_o, dqkv, delta, dfeat, dtmp, dwpe, splitk, colsum_ws, ln_ws;
   int64_t splitk_floats;
+  // deferred folds (srw_grad_fold, one launch per block): every reduction of a block keeps its own workspace until then
+  int64_t sk4[4];   // split-K workspaces of the fc2 / fc1 / proj / qkv weight gradients
+  int64_t colsum_ws2, ln_ws2;
   int64_t total;
 };
 
@@ -320,6 +323,12 @@ static Layout make_layout(const Dims& d) {
   L.splitk = c.take(sk * 4);
   L.colsum_ws = c.take((int64_t)256 * std::max(3 * d.D, d.hidden) * 4);
   L.ln_ws = c.take((int64_t)3 * 256 * D * 4);
+  L.sk4[0] = c.take(splitk_for(d.D, d.hidden, Tg, nullptr) * 4);
+  L.sk4[1] = c.take(splitk_for(d.hidden, d.D, Tg, nullptr) * 4);
+  L.sk4[2] = c.take(splitk_for(d.D, d.D, Tg, nullptr) * 4);
+  L.sk4[3] = c.take(splitk_for(3 * d.D, d.D, Tg, nullptr) * 4);
+  L.colsum_ws2 = c.take((int64_t)256 * std::max(3 * d.D, d.hidden) * 4);
+  L.ln_ws2 = c.take((int64_t)3 * 256 * D * 4);
   L.total = c.off;
   return L;
 }
@@ -370,7 +379,7 @@ struct Gemm {
   } while (0)
 
 static int wgrad(int M, int N, int64_t K, const void* a_planes, int64_t lda, int64_t a_rows, const void* b_planes, int64_t ldb, int64_t b_rows,
-                 float* ws, float* out, int64_t ldo, int accumulate, int impl, cudaStream_t s) {
+                 float* ws, float* out, int64_t ldo, int accumulate, int impl, cudaStream_t s, srw_grad_fold_args* fold = nullptr) {
   // out[M,N] (+)= A^T B with A stored [K, M] and B stored [K, N] (token-major activations / gradients)
   int split = 1;
   splitk_for(M, N, K, &split);
@@ -380,15 +389,32 @@ static int wgrad(int M, int N, int64_t K, const void* a_planes, int64_t lda, int
   SRW_TRY(g.run(s));
   srw_splitk_reduce_args r = {};
   r.workspace = ws; r.split_k = split; r.M = M; r.N = N; r.out = out; r.ldo = ldo; r.accumulate = accumulate;
+  if (fold) {   // folded with the rest of the block's reductions (srw_grad_fold)
+    fold->splitk[fold->n_splitk++] = r;
+    return SRW_OK;
+  }
   return srw_splitk_reduce(&r, s);
 }
 
+static void fold_colsum(srw_grad_fold_args* fold, const float* partial, int nparts, int64_t stride_p, int cols, float* out, int accumulate) {
+  srw_fold_colsum& c = fold->colsum[fold->n_colsum++];
+  c.partial = partial; c.nparts = nparts; c.stride_p = stride_p; c.cols = cols; c.out = out; c.accumulate = accumulate;
+}
+
 static int colsum_planes(const void* planes, int64_t ld, int64_t rows_total, int rows, int cols, float* out, int accumulate, float* ws,
-                         cudaStream_t s) {
+                         cudaStream_t s, srw_grad_fold_args* fold = nullptr) {
   srw_colsum_args a = {};
-  a.planes = planes; a.ldp = ld; a.plane_stride = rows_total * ld; a.rows = rows; a.cols = cols; a.out = out; a.accumulate = accumulate;
+  a.planes = planes; a.ldp = ld; a.plane_stride = rows_total * ld; a.rows = rows; a.cols = cols; a.out = fold ? nullptr : out; a.accumulate = accumulate;
   a.workspace = ws;
-  return srw_colsum(&a, s);
+  SRW_TRY(srw_colsum(&a, s));
+  if (fold) fold_colsum(fold, ws, srw_colsum_nparts(rows), cols, cols, out, accumulate);
+  return SRW_OK;
+}
+
+// SRW_FOLD=0: every reduction as its own launch right behind its producer (the previous behaviour; for A/B measurements)
+static bool fold_enabled() {
+  static const bool on = [] { const char* e = getenv("SRW_FOLD"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 }  // namespace srw
@@ -591,23 +617,28 @@ static int vit_backward_body(const srw_vit_bwd_args* a, cudaStream_t s) {
   }
   }
   // ---- blocks ----
+  const int ln_parts = srw_layernorm_bwd_nparts(Tg);
   for (int l = blk_hi; l >= blk_lo; --l) {
     const BlockBufs& b = L.blk[l];
+    // the block's four weight-gradient split-K folds, two bias column sums and two LayerNorm parameter reductions are
+    // deferred into ONE launch at the end of the block (8 launches of 3-6 us otherwise); each keeps its own workspace
+    srw_grad_fold_args fold_args = {};
+    srw_grad_fold_args* fold = fold_enabled() ? &fold_args : nullptr;
     const float* ds_attn = a->drop_scale ? a->drop_scale + ((int64_t)l * 2 + 0) * d.B : nullptr;
     const float* ds_mlp = a->drop_scale ? a->drop_scale + ((int64_t)l * 2 + 1) * d.B : nullptr;
     // MLP branch:  t_out = t_mid + s * (gelu(LN2(t_mid) W1^T + b1) W2^T + b2)
     // g = planes of ds_mlp * dt (+ fc2 bias gradient = its column sums): produced by the previous block's LN1 backward
     // (fused hand-over), except for the first block processed, whose dt comes from the head
     if (l == d.L - 1) SRW_TRY(split_to(dt, D, Tg, D, ws + L.g, D, ds_mlp, d.N, s, G[pblk(l, B_FC2B)], acc, cws));
-    SRW_TRY(wgrad(D, Fh, Tg, ws + L.g, D, Tg, ws + b.h, Fh, T, sk, G[pblk(l, B_FC2W)], Fh, acc, impl, s));
+    SRW_TRY(wgrad(D, Fh, Tg, ws + L.g, D, Tg, ws + b.h, Fh, T, fold ? F32(L.sk4[0]) : sk, G[pblk(l, B_FC2W)], Fh, acc, impl, s, fold));
     {
       Gemm g(Tg, Fh, D, impl);  // dz = (g W2) * gelu'(z)
       g.A(ws + L.g, D, Tg, 0).Bm(wp + w[l].fc2, Fh, D, 1);
       g.g.epilogue = SRW_EPI_DGELU; g.g.aux = F32(b.z); g.g.ldaux = Fh; g.g.out_planes = ws + L.dz; g.g.ldp = Fh; g.g.out_plane_stride = (int64_t)Tg * Fh;
       SRW_TRY(g.run(s));
     }
-    SRW_TRY(colsum_planes(ws + L.dz, Fh, Tg, Tg, Fh, G[pblk(l, B_FC1B)], acc, cws, s));
-    SRW_TRY(wgrad(Fh, D, Tg, ws + L.dz, Fh, Tg, ws + b.y2, D, T, sk, G[pblk(l, B_FC1W)], D, acc, impl, s));
+    SRW_TRY(colsum_planes(ws + L.dz, Fh, Tg, Tg, Fh, G[pblk(l, B_FC1B)], acc, cws, s, fold));
+    SRW_TRY(wgrad(Fh, D, Tg, ws + L.dz, Fh, Tg, ws + b.y2, D, T, fold ? F32(L.sk4[1]) : sk, G[pblk(l, B_FC1W)], D, acc, impl, s, fold));
     {
       Gemm g(Tg, D, Fh, impl);  // dy2 = dz W1
       g.A(ws + L.dz, Fh, Tg, 0).Bm(wp + w[l].fc1, D, Fh, 1);
@@ -622,8 +653,14 @@ static int vit_backward_body(const srw_vit_bwd_args* a, cudaStream_t s) {
     // ds_attn * dt and the proj bias gradient
     lb.dx_planes = ws + L.g; lb.ldp = D; lb.plane_stride = (int64_t)Tg * D; lb.row_scale = ds_attn; lb.rows_per_scale = d.N;
     lb.colsum_out = G[pblk(l, B_PROJB)]; lb.colsum_accumulate = acc;
+    if (fold) {
+      fold_colsum(fold, lb.workspace, ln_parts, 3 * (int64_t)D, D, lb.dgamma, acc);
+      fold_colsum(fold, lb.workspace + D, ln_parts, 3 * (int64_t)D, D, lb.dbeta, acc);
+      fold_colsum(fold, lb.workspace + 2 * D, ln_parts, 3 * (int64_t)D, D, lb.colsum_out, acc);
+      lb.dgamma = lb.dbeta = lb.colsum_out = nullptr;   // partials stay in the workspace
+    }
     SRW_TRY(srw_layernorm_bwd(&lb, s));
-    SRW_TRY(wgrad(D, D, Tg, ws + L.g, D, Tg, ws + b.o, D, T, sk, G[pblk(l, B_PROJW)], D, acc, impl, s));
+    SRW_TRY(wgrad(D, D, Tg, ws + L.g, D, Tg, ws + b.o, D, T, fold ? F32(L.sk4[2]) : sk, G[pblk(l, B_PROJW)], D, acc, impl, s, fold));
     {
       Gemm g(Tg, D, D, impl);  // d_o = g Wp
       g.A(ws + L.g, D, Tg, 0).Bm(wp + w[l].proj, D, D, 1);
@@ -640,8 +677,8 @@ static int vit_backward_body(const srw_vit_bwd_args* a, cudaStream_t s) {
       at.dqkv = ws + L.dqkv; at.ld_dqkv = 3 * D; at.dqkv_plane_stride = (int64_t)Tg * 3 * D;
       SRW_TRY(srw_attn_bwd(&at, s));
     }
-    SRW_TRY(colsum_planes(ws + L.dqkv, 3 * D, Tg, Tg, 3 * D, G[pblk(l, B_QKVB)], acc, cws, s));
-    SRW_TRY(wgrad(3 * D, D, Tg, ws + L.dqkv, 3 * D, Tg, ws + b.y1, D, T, sk, G[pblk(l, B_QKVW)], D, acc, impl, s));
+    SRW_TRY(colsum_planes(ws + L.dqkv, 3 * D, Tg, Tg, 3 * D, G[pblk(l, B_QKVB)], acc, fold ? F32(L.colsum_ws2) : cws, s, fold));
+    SRW_TRY(wgrad(3 * D, D, Tg, ws + L.dqkv, 3 * D, Tg, ws + b.y1, D, T, fold ? F32(L.sk4[3]) : sk, G[pblk(l, B_QKVW)], D, acc, impl, s, fold));
     {
       Gemm g(Tg, D, 3 * D, impl);  // dy1 = dqkv Wqkv
       g.A(ws + L.dqkv, 3 * D, Tg, 0).Bm(wp + w[l].qkv, D, 3 * D, 1);
@@ -656,7 +693,15 @@ static int vit_backward_body(const srw_vit_bwd_args* a, cudaStream_t s) {
     } else {
       lb.dx_planes = nullptr; lb.colsum_out = nullptr; lb.row_scale = nullptr;
     }
+    if (fold) {
+      lb.workspace = F32(L.ln_ws2);
+      fold_colsum(fold, lb.workspace, ln_parts, 3 * (int64_t)D, D, lb.dgamma, acc);
+      fold_colsum(fold, lb.workspace + D, ln_parts, 3 * (int64_t)D, D, lb.dbeta, acc);
+      if (lb.colsum_out) fold_colsum(fold, lb.workspace + 2 * D, ln_parts, 3 * (int64_t)D, D, lb.colsum_out, acc);
+      lb.dgamma = lb.dbeta = lb.colsum_out = nullptr;
+    }
     SRW_TRY(srw_layernorm_bwd(&lb, s));
+    if (fold) SRW_TRY(srw_grad_fold(fold, s));
   }
   // ---- embedding ----
   if (blk_lo == 0) {

@@ -151,3 +151,43 @@ def test_attention_fwd_bwd(ops, B, N, H):
     err_g = (dqkv.to_f32().double() - qd.grad).abs().max().item()
     scale_g = qd.grad.abs().max().item()
     assert err_g < 1e-4 * max(1.0, scale_g), f"dqkv err {err_g} (max |grad| {scale_g})"
+
+
+def test_grad_fold_matches_separate_reductions(ops):
+    """srw_grad_fold (one launch per block) against float64 sums and, bit for bit, against srw_splitk_reduce."""
+    import ctypes as C
+    from semireward_b200 import _lib as L
+    lib = L.load()
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    a = L.GradFoldArgs()
+    keep, checks = [], []
+    shapes = [(384, 1536, 5, 1536, 0), (1152, 384, 8, 384, 1), (384, 384, 3, 392, 1)]   # (M, N, split, ldo, accumulate)
+    for i, (M, N, split, ldo, acc) in enumerate(shapes):
+        ws = _rand(split, M, N, seed=30 + i)
+        out = _rand(M, ldo, seed=40 + i)
+        ref = (ws.double().sum(0) + (out[:, :N].double() if acc else 0))
+        out_sep = out.clone()
+        r = L.SplitKReduceArgs(workspace=ws.data_ptr(), split_k=split, M=M, N=N, out=out_sep.data_ptr(), ldo=ldo, accumulate=acc)
+        L.check(lib.srw_splitk_reduce(C.byref(r), s), "srw_splitk_reduce")
+        a.splitk[i] = L.SplitKReduceArgs(workspace=ws.data_ptr(), split_k=split, M=M, N=N, out=out.data_ptr(), ldo=ldo, accumulate=acc)
+        keep += [ws, out]
+        checks.append((out, ref, out_sep, N))
+    a.n_splitk = len(shapes)
+    csum = [(64, 1536, 1536, 0), (129, 384, 3 * 384, 1), (7, 100, 100, 0)]   # (nparts, cols, stride_p, accumulate)
+    cchecks = []
+    for i, (nparts, cols, stride, acc) in enumerate(csum):
+        part = _rand(nparts, stride, seed=50 + i)
+        out = _rand(cols, seed=60 + i)
+        ref = part[:, :cols].double().sum(0) + (out.double() if acc else 0)
+        a.colsum[i] = L.FoldColsum(partial=part.data_ptr(), nparts=nparts, stride_p=stride, cols=cols, out=out.data_ptr(), accumulate=acc)
+        keep += [part, out]
+        cchecks.append((out, ref))
+    a.n_colsum = len(csum)
+    L.check(lib.srw_grad_fold(C.byref(a), s), "srw_grad_fold")
+    torch.cuda.synchronize()
+    for out, ref, out_sep, N in checks:
+        assert torch.equal(out, out_sep), "fold differs from srw_splitk_reduce"
+        assert (out[:, :N].double() - ref).abs().max().item() < 1e-5
+    for out, ref in cchecks:
+        assert (out.double() - ref).abs().max().item() < 1e-4
+    assert lib.srw_colsum_nparts(4112) == 64 and lib.srw_layernorm_bwd_nparts(4112) == 256 and lib.srw_layernorm_bwd_nparts(100) == 13
