@@ -5,12 +5,14 @@
 // Operands are split-bf16 planes (srw_common.cuh); every product runs as hi*hi + hi*lo + lo*hi on tcgen05 tensor cores
 // with fp32 accumulation in TMEM.  head_dim is 64 (ViT-S/B, BERT-base and HuBERT-base all use 64).
 //
-// Forward (one CTA per (128-query tile, head, image); N <= 272 keys so a whole score row lives in TMEM):
-//   TMA: Q tile, all K, all V -> smem.   MMA: S[128, NP] = Q K^T into TMEM.   4 softmax warps (thread == query row):
-//   row max, p = exp2((s - max) * scale*log2e), split p into bf16 hi/lo and write 64-key chunks of P into swizzled
-//   smem; the MMA warp consumes each chunk as soon as it lands: O += P_chunk V_chunk.  O / rowsum -> global planes.
+// Forward (one CTA per (head, image), looping over 128-query tiles; N <= 272 keys so a whole score row lives in TMEM):
+//   TMA: all K, all V once, Q tiles double-buffered -> smem.   MMA: S[128, NP] = Q K^T into TMEM.   16 softmax warps
+//   (thread == query row x 16-key group): row max, p = exp2((s - max) * scale*log2e), split p into bf16 hi/lo and write
+//   it back over S in TMEM; the MMA warp consumes each 64-key chunk as soon as it lands, taking P as the A operand from
+//   TMEM: [O | OX] += P_chunk [V_hi | V_lo].  (O + OX) / rowsum -> global planes.
 // Backward = two kernels sharing one skeleton (attn_bwd_kernel<MODE>): a 128-row tile R against 64-wide column
-//   chunks C_j:   T1_j = R1 C1_j^T, T2_j = R2 C2_j^T (TMEM) -> threads form X_j (and Y_j) -> Acc += X_j C1_j (Y_j C2_j).
+//   chunks C_j:   T1_j = R1 C1_j^T, T2_j = R2 C2_j^T (TMEM) -> threads overwrite them with X_j (and Y_j) -> Acc += X_j C1_j
+//   (Y_j C2_j), again with A from TMEM.
 //   MODE_DQ : R = query tile (Q, dO), C = key chunks (K, V):  X = dS           -> dQ = sum_j dS_j K_j
 //   MODE_DKV: R = key tile (K, V),  C = query chunks (Q, dO): X = dS^T, Y = P^T -> dK = sum_j dS^T_j Q_j, dV = sum_j P^T_j dO_j
 //   (dS = P o (dP - delta) * scale, P = exp(S*scale - lse), delta = rowsum(dO o O)).  No atomics: deterministic.
@@ -29,24 +31,6 @@ extern std::atomic<int64_t> g_launches;
 constexpr int HD = 64;                    // head dim
 constexpr int ROW_TILE_BYTES = 128 * 128; // 128 rows x 64 bf16 (one plane)
 constexpr float LOG2E = 1.4426950408889634f;
-
-// byte offset of the 16-byte group `g` (0..7) of row `r` inside a K-major SWIZZLE_128B tile (128 B rows, 8-row atoms)
-__device__ __forceinline__ uint32_t sw128_off(int r, int g) {
-  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((g ^ (r & 7)) << 4));
-}
-
-// write 16 consecutive fp32 values of row r (columns [c0, c0+16) of a 64-wide chunk, c0 % 16 == 0) as split planes
-__device__ __forceinline__ void store_row16_planes(uint8_t* hi_tile, uint8_t* lo_tile, int r, int c0, const float (&v)[16]) {
-#pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) split2(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1], h[j], l[j]);
-    const uint32_t off = sw128_off(r, (c0 >> 3) + g);
-    *reinterpret_cast<uint4*>(hi_tile + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(lo_tile + off) = make_uint4(l[0], l[1], l[2], l[3]);
-  }
-}
 
 // sync the 512 element-wise threads only (named barrier 1); the TMA / MMA warps never take part
 __device__ __forceinline__ void ew_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
@@ -90,255 +74,18 @@ struct AttnFwdParams {
 
 constexpr int FWD_THREADS = 512 + 32;   // 16 softmax warps (4 per TMEM lane quarter, 16 columns each) + 1 TMA/MMA warp
 
-// One CTA per (head, image).  K and V of the head are staged ONCE and stay in shared memory while the CTA walks the
-// ceil(N / 128) query tiles: per tile  TMA Q -> S = Q K^T (TMEM) -> softmax warps -> P chunks -> O += P V -> store.
-// The next tile's Q load overlaps this tile's epilogue, its S MMAs start as soon as the softmax warps have drained S.
-// Shared memory: [A: Q tile, re-used as P buffer 1 once S is done | B: P buffer 0 | K hi,lo | V hi,lo | barriers | exchange].
-// Rows beyond N (the third tile of N = 257 holds ONE valid row) skip all softmax work: MMA rows are independent, so their
-// stale P rows only produce discarded O rows.
-__global__ void __launch_bounds__(FWD_THREADS, 1)
-attn_fwd_smem_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const AttnFwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  pdl_trigger();
-  const int NP = p.NP;
-  const uint32_t kv_plane = (uint32_t)NP * 128;           // bytes of one K (or V) plane
-  const uint32_t off_k = 4 * ROW_TILE_BYTES;              // after region A (Q / P1) and region B (P0), 32 KiB each
-  const uint32_t off_v = off_k + 2 * kv_plane;
-  const uint32_t off_bar = off_v + 2 * kv_plane;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bar);
-  uint64_t* bar_kv = bars + 0; uint64_t* bar_q = bars + 1; uint64_t* bar_s = bars + 2; uint64_t* bar_o = bars + 3;
-  uint64_t* bar_p = bars + 4;      // [2]
-  uint64_t* bar_pfree = bars + 6;  // [2]
-  uint64_t* bar_sfree = bars + 8;  // softmax warps have read S for the last time (count 16)
-  uint64_t* bar_ofree = bars + 9;  // softmax warps have read O (count 16)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-  float* xch_base = reinterpret_cast<float*>(smem + off_bar + 128);   // [2][4][128] partial row max / row sum exchange, one set per tile parity
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x, b = blockIdx.y;
-  const int D = p.H * HD;
-  const int row0 = b * p.N;           // first token row of this image in the [B*N, 3D] qkv matrix
-  const int nchunks = (NP + 63) / 64;
-  const int ntiles = (p.N + 127) / 128;
-  unsigned long long* tr = p.trace ? p.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 32 : nullptr;
-  if (tr && threadIdx.x == 0) tr[0] = clock64();
-
-  if (warp == 16 && lane == 0) {
-    tma_prefetch_desc(&tmap_q);
-    tma_prefetch_desc(&tmap_kv);
-    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
-    mbar_init(&bar_p[0], 16); mbar_init(&bar_p[1], 16);
-    mbar_init(&bar_pfree[0], 1); mbar_init(&bar_pfree[1], 1);
-    mbar_init(bar_sfree, 16); mbar_init(bar_ofree, 16);
-    fence_barrier_init();
-  }
-  if (warp == 0) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t TM_S = tmem, TM_O = tmem + 384, TM_OX = tmem + 448;
-  pdl_wait();   // CTA-local setup above; q/k/v come from the previous kernel
-
-  if (warp == 16) {
-    if (elect_one()) {   // one elected lane: the compiler keeps descriptors / addresses in uniform registers (no per-MMA R2UR waterfall)
-      // ---- K, V once; Q of tile 0 ----
-      const int half = NP / 2;
-      mbar_arrive_expect_tx(bar_kv, 4 * kv_plane);
-      for (int pl = 0; pl < 2; ++pl)
-        for (int hf = 0; hf < 2; ++hf) {
-          tma_load_3d(smem + off_k + pl * kv_plane + hf * half * 128, &tmap_kv, bar_kv, D + h * HD, row0 + hf * half, pl);
-          tma_load_3d(smem + off_v + pl * kv_plane + hf * half * 128, &tmap_kv, bar_kv, 2 * D + h * HD, row0 + hf * half, pl);
-        }
-      mbar_arrive_expect_tx(bar_q, 2 * ROW_TILE_BYTES);
-      tma_load_3d(smem, &tmap_q, bar_q, h * HD, row0, 0);
-      tma_load_3d(smem + ROW_TILE_BYTES, &tmap_q, bar_q, h * HD, row0, 1);
-      mbar_wait(bar_kv, 0);
-      if (tr) tr[1] = clock64();                       // K, V landed
-      // The single issuing thread is the bottleneck of the small (N = 64) PV MMAs if it rebuilds four 64-bit descriptors per
-      // MMA triple: build each base descriptor once; a step along K (or to the next chunk) only adds (bytes >> 4) to the
-      // 14-bit start-address field (no carry: everything lives below 227 KB).
-      const uint64_t dq_hi = umma_smem_desc(smem_u32(smem), 16, 1024), dq_lo = umma_smem_desc(smem_u32(smem) + ROW_TILE_BYTES, 16, 1024);
-      const uint64_t dk_hi = umma_smem_desc(smem_u32(smem + off_k), 16, 1024), dk_lo = umma_smem_desc(smem_u32(smem + off_k) + kv_plane, 16, 1024);
-      const uint64_t dv_hi = umma_smem_desc(smem_u32(smem + off_v), 1024, 1024), dv_lo = umma_smem_desc(smem_u32(smem + off_v) + kv_plane, 1024, 1024);
-      // P buffer 0 = region B (offset 32 KiB), buffer 1 = region A (offset 0)
-      const uint64_t dp_hi0 = umma_smem_desc(smem_u32(smem) + 2 * ROW_TILE_BYTES, 16, 1024), dp_hi1 = umma_smem_desc(smem_u32(smem), 16, 1024);
-      const uint64_t dp_lo0 = umma_smem_desc(smem_u32(smem) + 3 * ROW_TILE_BYTES, 16, 1024), dp_lo1 = umma_smem_desc(smem_u32(smem) + ROW_TILE_BYTES, 16, 1024);
-      const uint32_t idesc_pv = umma_idesc_bf16(HD, 0, 1);
-      const int n1 = NP <= 256 ? NP : 256, n2 = NP - n1;
-      uint32_t g = 0;   // running P-chunk counter across tiles -> buffer / phase
-      for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(bar_q, t & 1);
-        if (t > 0) mbar_wait(bar_sfree, (t - 1) & 1);      // the softmax warps have drained S of tile t-1
-        tc_fence_after();
-        // ---- S = Q K^T ----
-        for (int part = 0; part < 2; ++part) {
-          const int n = part == 0 ? n1 : n2;
-          if (n == 0) break;
-          const uint32_t idesc = umma_idesc_bf16(n, 0, 0);
-          const uint32_t boff = part * ((256 * 128) >> 4), tcol = part * 256;
-#pragma unroll
-          for (int kk = 0; kk < HD / 16; ++kk) {
-            const uint64_t aq_hi = dq_hi + kk * 2, aq_lo = dq_lo + kk * 2;             // + 32 B per K step
-            const uint64_t bk_hi = dk_hi + boff + kk * 2, bk_lo = dk_lo + boff + kk * 2;
-            umma_bf16(TM_S + tcol, aq_lo, bk_hi, idesc, kk > 0 ? 1u : 0u);
-            umma_bf16(TM_S + tcol, aq_hi, bk_lo, idesc, 1u);
-            umma_bf16(TM_S + tcol, aq_hi, bk_hi, idesc, 1u);
-          }
-        }
-        umma_commit(bar_s);
-        if (t > 0) mbar_wait(bar_ofree, (t - 1) & 1);      // the epilogue of tile t-1 has read O
-        tc_fence_after();
-        // ---- O += P_c V_c ----
-        for (int c = 0; c < nchunks; ++c, ++g) {
-          const int buf = g & 1;
-          mbar_wait(&bar_p[buf], (g >> 1) & 1);
-          tc_fence_after();
-          if (tr && t == 0 && (c == 2 || c == 3)) tr[c == 2 ? 28 : 30] = clock64();   // MMA thread: P chunk c visible
-          const int ksteps = min(4, (NP - c * 64) / 16);
-          const uint64_t pb_hi = buf ? dp_hi1 : dp_hi0, pb_lo = buf ? dp_lo1 : dp_lo0;
-#pragma unroll 4
-          for (int kk = 0; kk < ksteps; ++kk) {
-            const uint32_t voff = (uint32_t)(c * 64 + kk * 16) * (128 >> 4);
-            const uint64_t ap_hi = pb_hi + kk * 2, ap_lo = pb_lo + kk * 2;
-            const uint64_t bv_hi = dv_hi + voff, bv_lo = dv_lo + voff;
-            const uint32_t acc = (c > 0 || kk > 0) ? 1u : 0u;
-            umma_bf16(TM_OX, ap_lo, bv_hi, idesc_pv, acc);
-            umma_bf16(TM_OX, ap_hi, bv_lo, idesc_pv, 1u);
-            umma_bf16(TM_O, ap_hi, bv_hi, idesc_pv, acc);
-          }
-          umma_commit(&bar_pfree[buf]);
-          if (tr && t == 0 && c == 2) tr[29] = clock64();                                // MMA thread: chunk 2 issued + committed
-        }
-        umma_commit(bar_o);
-        if (t + 1 < ntiles) {
-          // region A held P buffer 1 of this tile: reload it with the next Q tile once every MMA that read it is complete
-          mbar_wait(bar_o, t & 1);
-          mbar_arrive_expect_tx(bar_q, 2 * ROW_TILE_BYTES);
-          tma_load_3d(smem, &tmap_q, bar_q, h * HD, row0 + (t + 1) * 128, 0);
-          tma_load_3d(smem + ROW_TILE_BYTES, &tmap_q, bar_q, h * HD, row0 + (t + 1) * 128, 1);
-        }
-      }
-    }
-  } else {
-    // ---- softmax warps: 4 warps per TMEM lane quarter; thread == (query row, 16-column interleave `part`) ----
-    const int q = warp & 3, part = warp >> 2;
-    const int r = q * 32 + lane;                     // 0..127, TMEM lane
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const float c2 = p.scale * LOG2E;
-    const int nsub = NP / 16;                        // 16-column sub-chunks; this thread owns sub-chunks part, part+4, ...
-    // P buffer 0 is region B (offset 32 KiB), buffer 1 is region A (offset 0): buffer index -> byte offset
-    uint32_t g = 0;
-    for (int t = 0; t < ntiles; ++t) {
-      const int qr = t * 128 + r;                    // query index inside the image
-      float* xch = xch_base + (t & 1) * 512;         // alternating sets: no barrier needed between tiles
-      const bool valid = qr < p.N;
-      const bool warp_valid = (t * 128 + q * 32) < p.N;   // any valid row in this warp (uniform per warp)
-      mbar_wait(bar_s, t & 1);
-      tc_fence_after();
-      if (tr && threadIdx.x == 0 && t < 3) tr[2 + 8 * t] = clock64();      // S ready
-      float m = -INFINITY;
-      if (warp_valid) {
-        for (int sc = part; sc < nsub; sc += 4) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(TM_S + lane_addr + sc * 16, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (sc * 16 + j < p.N) m = fmaxf(m, __uint_as_float(v[j]));
-        }
-      }
-      xch[part * 128 + r] = m;
-      ew_sync();
-      m = fmaxf(fmaxf(xch[r], xch[128 + r]), fmaxf(xch[256 + r], xch[384 + r]));
-      ew_sync();                                     // xch is reused for the row sums below
-      if (tr && threadIdx.x == 0 && t < 3) tr[3 + 8 * t] = clock64();      // row max known
-      const float mc = m * c2;
-      float sum = 0.f;
-      for (int c = 0; c < nchunks; ++c, ++g) {
-        const int buf = g & 1;
-        const int sc = c * 4 + part;
-        float pv[16];
-        const bool have = sc < nsub && warp_valid;
-        if (have) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(TM_S + lane_addr + sc * 16, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float e = (valid && sc * 16 + j < p.N) ? exp2f(fmaf(__uint_as_float(v[j]), c2, -mc)) : 0.f;
-            pv[j] = e;
-            sum += e;
-          }
-        }
-        if (c == nchunks - 1) {                      // last read of S by this warp: the next tile's S MMAs may overwrite it
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_sfree);
-        }
-        if (g >= 2) mbar_wait(&bar_pfree[buf], ((g >> 1) - 1) & 1);
-        if (tr && threadIdx.x == 0 && t == 0 && (c == 2 || c == 4)) tr[c == 2 ? 26 : 31] = clock64();   // softmax: buffer free again
-        if (have) {
-          uint8_t* hi_tile = smem + (buf ^ 1) * 2 * ROW_TILE_BYTES;   // buffer 0 -> region B (32 KiB), buffer 1 -> region A (0)
-          store_row16_planes(hi_tile, hi_tile + ROW_TILE_BYTES, r, part * 16, pv);
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_p[buf]);
-        if (tr && threadIdx.x == 0 && t < 3 && (c == 0 || c == nchunks - 1)) tr[(c == 0 ? 4 : 5) + 8 * t] = clock64();   // first / last P chunk handed over
-        if (tr && threadIdx.x == 0 && t == 0 && c == 2) tr[27] = clock64();                                                  // chunk 2 handed over
-      }
-      xch[part * 128 + r] = sum;
-      ew_sync();
-      sum = (xch[r] + xch[128 + r]) + (xch[256 + r] + xch[384 + r]);
-      // ---- epilogue: this thread writes output columns [16*part, 16*part+16) of its row ----
-      mbar_wait(bar_o, t & 1);
-      tc_fence_after();
-      if (tr && threadIdx.x == 0 && t < 3) tr[6 + 8 * t] = clock64();      // O complete
-      uint32_t a[16], x[16];
-      if (warp_valid) {
-        tmem_ld_32x32b_x16(TM_O + lane_addr + part * 16, a);
-        tmem_ld_32x32b_x16(TM_OX + lane_addr + part * 16, x);
-        tmem_ld_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_ofree);
-      if (valid) {
-        const float inv = 1.0f / sum;
-        if (part == 0 && p.lse) p.lse[((int64_t)b * p.H + h) * p.N + qr] = m * p.scale + logf(sum);
-        float o16[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) o16[j] = (__uint_as_float(a[j]) + __uint_as_float(x[j])) * inv;
-        store_out16(p.o + (int64_t)(row0 + qr) * p.ld_o + h * HD + part * 16, p.o_ps, o16);
-      }
-      if (tr && threadIdx.x == 0 && t < 3) tr[7 + 8 * t] = clock64();      // tile stored
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-// forward, P through tensor memory
+// forward: one CTA per (head, image), K/V staged once, loop over query tiles, P through tensor memory
 // ------------------------------------------------------------------------------------------------
-// Same decomposition as above (one CTA per (head, image), K/V staged once, loop over query tiles) but the probabilities
-// never touch shared memory: a softmax thread reads 16 fp32 scores of its row from TMEM, and writes the 16 probabilities
-// back IN PLACE as split bf16 — columns [16g, 16g+8) = packed hi pairs, [16g+8, 16g+16) = packed lo pairs of key group g —
+// The probabilities never touch shared memory: a softmax thread reads 16 fp32 scores of its row from TMEM, and writes the
+// 16 probabilities back IN PLACE as split bf16 — columns [16g, 16g+8) = packed hi pairs, [16g+8, 16g+16) = packed lo pairs of key group g —
 // and the PV product takes its A operand from TMEM (umma_bf16_ts).  Per key group that is two MMAs instead of three:
 //   [O | OX] += P_hi [V_hi | V_lo]   (one N = 128 MN-major operand: the lo plane is the second 64-wide chunk, LBO = plane)
 //        OX  += P_lo  V_hi
-// What this removes (scripts/attn_trace.py on the kernel above): the two 32 KB P buffers and their hand-back barrier —
-// a 1.8 us round trip per pair of 64-key chunks that made a tile cost 7.6 us whatever the softmax work — the
-// st.shared + fence.proxy.async of every P element, and a third of the PV instructions.  The freed shared memory double-
+// What this removed (scripts/attn_trace.py on the previous kernel, which staged P in two 32 KB shared-memory buffers): the
+// buffers' hand-back barrier — a 1.8 us round trip per pair of 64-key chunks that made a tile cost 7.6 us whatever the
+// softmax work — the st.shared + fence.proxy.async of every P element, and a third of the PV instructions (30 -> 20 us
+// per launch at 24 images x 6 heads x 257 tokens).  The freed shared memory double-
 // buffers Q, and the tensor pipe orders S(t+1) after PV(t) by itself (tcgen05.mma executes in issue order), so the next
 // tile's scores are computed while the softmax warps write the current tile's output.
 __global__ void __launch_bounds__(FWD_THREADS, 1)
@@ -593,275 +340,53 @@ struct AttnBwdParams {
 };
 
 constexpr int BWD_THREADS = 512 + 64;   // 16 element-wise warps + TMA warp + MMA warp
-constexpr int BWD_OFF_R1 = 0, BWD_OFF_R2 = 2 * ROW_TILE_BYTES, BWD_OFF_C = 4 * ROW_TILE_BYTES;
 constexpr int BWD_CSTAGE = 2 * ROW_TILE_BYTES;  // C1 (hi 8K, lo 8K) + C2 (hi 8K, lo 8K)
-constexpr int BWD_OFF_X = BWD_OFF_C + 2 * BWD_CSTAGE;
-constexpr int BWD_OFF_Y = BWD_OFF_X + 2 * ROW_TILE_BYTES;
-constexpr int BWD_OFF_VEC = BWD_OFF_Y + 2 * ROW_TILE_BYTES;       // 2 x 320 floats (lse*log2e, delta per column) + [4][128] exchange
-constexpr int BWD_OFF_BAR = BWD_OFF_VEC + 2 * 320 * 4 + 4 * 128 * 4;
-constexpr int BWD_SMEM = BWD_OFF_BAR + 256 + 1024;
-
-template <int MODE>
-__global__ void __launch_bounds__(BWD_THREADS, 1)
-attn_bwd_smem_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_constant__ CUtensorMap tm_do_r,
-                const __grid_constant__ CUtensorMap tm_qkv_c, const __grid_constant__ CUtensorMap tm_do_c, const AttnBwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BWD_OFF_BAR);
-  uint64_t* bar_r = bars + 0;
-  uint64_t* bar_cfull = bars + 1;   // [2]
-  uint64_t* bar_cfree = bars + 3;   // [2]
-  uint64_t* bar_t = bars + 5;       // [2]
-  uint64_t* bar_x = bars + 7;
-  uint64_t* bar_xfree = bars + 8;
-  uint64_t* bar_acc = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-  float* vec_lse = reinterpret_cast<float*>(smem + BWD_OFF_VEC);
-  float* vec_delta = vec_lse + 320;
-  float* xch = vec_delta + 320;     // [4][128]
-
-  pdl_trigger();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int D = p.H * HD;
-  const int row0 = b * p.N;
-  const int nchunks = (p.NP + 63) / 64;
-  const int64_t stat0 = ((int64_t)b * p.H + h) * p.N;
-  unsigned long long* tr = p.trace ? p.trace + (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 48 : nullptr;
-  if (tr && threadIdx.x == 0) tr[0] = clock64();
-
-  if (warp == 16 && lane == 0) {
-    tma_prefetch_desc(&tm_qkv_r); tma_prefetch_desc(&tm_do_r); tma_prefetch_desc(&tm_qkv_c); tma_prefetch_desc(&tm_do_c);
-    mbar_init(bar_r, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&bar_cfull[s], 1); mbar_init(&bar_cfree[s], 1); mbar_init(&bar_t[s], 1); }
-    mbar_init(bar_x, 16); mbar_init(bar_xfree, 1); mbar_init(bar_acc, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  pdl_wait();   // barrier init / TMEM allocation above are CTA-local; everything below reads the previous kernels' outputs
-  if (MODE == MODE_DKV) {
-    // per-column (query) statistics
-    for (int i = threadIdx.x; i < p.NP; i += blockDim.x) {
-      vec_lse[i] = i < p.N ? p.lse[stat0 + i] * LOG2E : 0.f;
-      vec_delta[i] = i < p.N ? p.delta[stat0 + i] : 0.f;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  // TMEM columns: T1[s] = s*128, T2[s] = s*128 + 64; AccX main 256, cross 320; AccY main 384, cross 448
-  const int r1_col = (MODE == MODE_DQ ? 0 : D) + h * HD;       // R1: Q (DQ) / K (DKV)
-  const int r2_col = (MODE == MODE_DQ ? 0 : 2 * D) + h * HD;   // R2: dO (DQ, own matrix) / V (DKV)
-  const int c1_col = (MODE == MODE_DQ ? D : 0) + h * HD;       // C1: K (DQ) / Q (DKV)
-  const int c2_col = (MODE == MODE_DQ ? 2 * D : 0) + h * HD;   // C2: V (DQ) / dO (DKV, own matrix)
-
-  if (warp == 16) {
-    if (elect_one()) {   // one elected lane: the compiler keeps descriptors / addresses in uniform registers (no per-MMA R2UR waterfall)
-      // ===== TMA producer =====
-      mbar_arrive_expect_tx(bar_r, 4 * ROW_TILE_BYTES);
-      tma_load_3d(smem + BWD_OFF_R1, &tm_qkv_r, bar_r, r1_col, row0 + rt * 128, 0);  // box planes = 2: hi, lo
-      if (MODE == MODE_DQ) tma_load_3d(smem + BWD_OFF_R2, &tm_do_r, bar_r, h * HD, row0 + rt * 128, 0);
-      else tma_load_3d(smem + BWD_OFF_R2, &tm_qkv_r, bar_r, r2_col, row0 + rt * 128, 0);
-      for (int j = 0; j < nchunks; ++j) {
-        const int s = j & 1;
-        mbar_wait(&bar_cfree[s], ((j >> 1) & 1) ^ 1);
-        uint8_t* st = smem + BWD_OFF_C + s * BWD_CSTAGE;
-        mbar_arrive_expect_tx(&bar_cfull[s], BWD_CSTAGE);
-        tma_load_3d(st, &tm_qkv_c, &bar_cfull[s], c1_col, row0 + j * 64, 0);
-        if (MODE == MODE_DQ) tma_load_3d(st + ROW_TILE_BYTES, &tm_qkv_c, &bar_cfull[s], c2_col, row0 + j * 64, 0);
-        else tma_load_3d(st + ROW_TILE_BYTES, &tm_do_c, &bar_cfull[s], h * HD, row0 + j * 64, 0);
-      }
-    }
-  } else if (warp == 17) {
-    if (elect_one()) {   // one elected lane: the compiler keeps descriptors / addresses in uniform registers (no per-MMA R2UR waterfall)
-      // ===== MMA issuer =====
-      const uint32_t idesc_t = umma_idesc_bf16(64, 0, 0);     // T = R C^T   (both K-major, K = head dim)
-      const uint32_t idesc_a = umma_idesc_bf16(64, 0, 1);     // Acc = X C   (X K-major, C MN-major, K = chunk columns)
-      // base descriptors once (the single issuing thread is on the critical path of these N = 64 MMAs); a K step adds
-      // (bytes >> 4) to the start-address field: 32 B -> 2 for K-major tiles, 2048 B -> 128 for MN-major tiles
-      const uint32_t r1 = smem_u32(smem + BWD_OFF_R1), r2 = smem_u32(smem + BWD_OFF_R2);
-      const uint32_t xb = smem_u32(smem + BWD_OFF_X), yb = smem_u32(smem + BWD_OFF_Y);
-      const uint64_t dr1h = umma_smem_desc(r1, 16, 1024), dr1l = umma_smem_desc(r1 + ROW_TILE_BYTES, 16, 1024);
-      const uint64_t dr2h = umma_smem_desc(r2, 16, 1024), dr2l = umma_smem_desc(r2 + ROW_TILE_BYTES, 16, 1024);
-      const uint64_t dxh = umma_smem_desc(xb, 16, 1024), dxl = umma_smem_desc(xb + ROW_TILE_BYTES, 16, 1024);
-      const uint64_t dyh = umma_smem_desc(yb, 16, 1024), dyl = umma_smem_desc(yb + ROW_TILE_BYTES, 16, 1024);
-      // C stage 0 views, K-major (T MMAs) and MN-major (Acc MMAs); stage 1 = + (BWD_CSTAGE >> 4) in the address field
-      const uint32_t c1s0 = smem_u32(smem + BWD_OFF_C), c2s0 = c1s0 + ROW_TILE_BYTES;
-      const uint64_t dc1h0 = umma_smem_desc(c1s0, 16, 1024), dc1l0 = umma_smem_desc(c1s0 + ROW_TILE_BYTES / 2, 16, 1024);
-      const uint64_t dc2h0 = umma_smem_desc(c2s0, 16, 1024), dc2l0 = umma_smem_desc(c2s0 + ROW_TILE_BYTES / 2, 16, 1024);
-      const uint64_t mc1h0 = umma_smem_desc(c1s0, 1024, 1024), mc1l0 = umma_smem_desc(c1s0 + ROW_TILE_BYTES / 2, 1024, 1024);
-      const uint64_t mc2h0 = umma_smem_desc(c2s0, 1024, 1024), mc2l0 = umma_smem_desc(c2s0 + ROW_TILE_BYTES / 2, 1024, 1024);
-      constexpr uint32_t STAGE_STEP = BWD_CSTAGE >> 4;
-      mbar_wait(bar_r, 0);
-      if (tr) tr[1] = clock64();                                   // R tiles landed
-      auto issue_t = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(&bar_cfull[s], (j >> 1) & 1);
-        tc_fence_after();
-        if (tr && j < 5) tr[2 + 4 * j] = clock64();                // C chunk j landed, T MMAs go out
-        const uint32_t t1 = tmem + s * 128, t2 = t1 + 64;
-        const uint32_t so = s * STAGE_STEP;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint32_t ko = kk * 2;
-          umma_bf16(t1, dr1l + ko, dc1h0 + so + ko, idesc_t, kk > 0 ? 1u : 0u);
-          umma_bf16(t1, dr1h + ko, dc1l0 + so + ko, idesc_t, 1u);
-          umma_bf16(t1, dr1h + ko, dc1h0 + so + ko, idesc_t, 1u);
-          umma_bf16(t2, dr2l + ko, dc2h0 + so + ko, idesc_t, kk > 0 ? 1u : 0u);
-          umma_bf16(t2, dr2h + ko, dc2l0 + so + ko, idesc_t, 1u);
-          umma_bf16(t2, dr2h + ko, dc2h0 + so + ko, idesc_t, 1u);
-        }
-        umma_commit(&bar_t[s]);
-      };
-      issue_t(0);
-      for (int j = 0; j < nchunks; ++j) {
-        const int s = j & 1;
-        if (j + 1 < nchunks) issue_t(j + 1);
-        if (tr && j < 5) tr[3 + 4 * j] = clock64();                // T(j+1) issued
-        mbar_wait(bar_x, j & 1);
-        tc_fence_after();
-        if (tr && j < 5) tr[4 + 4 * j] = clock64();                // X(j) visible to the MMA thread
-        const int ksteps = min(4, (p.NP - j * 64) / 16);
-#pragma unroll 4
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint32_t acc = (j > 0 || kk > 0) ? 1u : 0u;
-          const uint32_t ko = kk * 2, bo = kk * 128 + s * STAGE_STEP;
-          umma_bf16(tmem + 320, dxl + ko, mc1h0 + bo, idesc_a, acc);
-          umma_bf16(tmem + 320, dxh + ko, mc1l0 + bo, idesc_a, 1u);
-          umma_bf16(tmem + 256, dxh + ko, mc1h0 + bo, idesc_a, acc);
-          if (MODE == MODE_DKV) {
-            umma_bf16(tmem + 448, dyl + ko, mc2h0 + bo, idesc_a, acc);
-            umma_bf16(tmem + 448, dyh + ko, mc2l0 + bo, idesc_a, 1u);
-            umma_bf16(tmem + 384, dyh + ko, mc2h0 + bo, idesc_a, acc);
-          }
-        }
-        umma_commit(bar_xfree);
-        umma_commit(&bar_cfree[s]);
-        if (tr && j < 5) tr[5 + 4 * j] = clock64();                // Acc(j) issued + committed
-      }
-      umma_commit(bar_acc);
-    }
-  } else {
-    // ===== element-wise warps: 4 per TMEM lane quarter; thread == (tile row, 16-column slice `part` of each 64-column chunk) =====
-    const int q = warp & 3, part = warp >> 2;
-    const int r = q * 32 + lane;
-    const int rr = rt * 128 + r;            // row index inside the image (query for DQ, key for DKV)
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const float c2s = p.scale * LOG2E;
-    float row_lse = 0.f, row_delta = 0.f;
-    if (MODE == MODE_DQ) {
-      // delta = sum_d dO * O over this head's 64 columns; each of the row's 4 threads sums 16 of them
-      float acc = 0.f;
-      if (rr < p.N) {
-        row_lse = p.lse[stat0 + rr] * LOG2E;
-        const __nv_bfloat16* orow = p.o + (int64_t)(row0 + rr) * p.ld_o + h * HD + part * 16;
-        const __nv_bfloat16* drow = p.d_o + (int64_t)(row0 + rr) * p.ld_do + h * HD + part * 16;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const uint4 oh = *reinterpret_cast<const uint4*>(orow + g * 8), ol = *reinterpret_cast<const uint4*>(orow + p.o_ps + g * 8);
-          const uint4 dh = *reinterpret_cast<const uint4*>(drow + g * 8), dl = *reinterpret_cast<const uint4*>(drow + p.do_ps + g * 8);
-          const uint32_t ohh[4] = {oh.x, oh.y, oh.z, oh.w}, oll[4] = {ol.x, ol.y, ol.z, ol.w};
-          const uint32_t dhh[4] = {dh.x, dh.y, dh.z, dh.w}, dll[4] = {dl.x, dl.y, dl.z, dl.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            acc = fmaf(bf16_lo_f(ohh[j]) + bf16_lo_f(oll[j]), bf16_lo_f(dhh[j]) + bf16_lo_f(dll[j]), acc);
-            acc = fmaf(bf16_hi_f(ohh[j]) + bf16_hi_f(oll[j]), bf16_hi_f(dhh[j]) + bf16_hi_f(dll[j]), acc);
-          }
-        }
-      }
-      xch[part * 128 + r] = acc;
-      ew_sync();
-      row_delta = (xch[r] + xch[128 + r]) + (xch[256 + r] + xch[384 + r]);
-      if (part == 0 && rr < p.N) p.delta[stat0 + rr] = row_delta;
-    }
-    uint8_t* x_hi = smem + BWD_OFF_X; uint8_t* x_lo = x_hi + ROW_TILE_BYTES;
-    uint8_t* y_hi = smem + BWD_OFF_Y; uint8_t* y_lo = y_hi + ROW_TILE_BYTES;
-    for (int j = 0; j < nchunks; ++j) {
-      const int s = j & 1;
-      mbar_wait(&bar_t[s], (j >> 1) & 1);
-      tc_fence_after();
-      if (tr && threadIdx.x == 0 && j < 5) tr[22 + 4 * j] = clock64();   // T(j) complete
-      uint32_t t1[16], t2[16];
-      tmem_ld_32x32b_x16(tmem + lane_addr + s * 128 + part * 16, t1);
-      tmem_ld_32x32b_x16(tmem + lane_addr + s * 128 + 64 + part * 16, t2);
-      tmem_ld_wait();
-      float xs[16], ys[16];
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int col = j * 64 + part * 16 + e;     // key index (DQ) / query index (DKV)
-        float pe, ds;
-        if (MODE == MODE_DQ) {
-          pe = (col < p.N) ? exp2f(fmaf(__uint_as_float(t1[e]), c2s, -row_lse)) : 0.f;
-          ds = pe * (__uint_as_float(t2[e]) - row_delta) * p.scale;
-        } else {
-          pe = (col < p.N) ? exp2f(fmaf(__uint_as_float(t1[e]), c2s, -vec_lse[col])) : 0.f;
-          ds = pe * (__uint_as_float(t2[e]) - vec_delta[col]) * p.scale;
-        }
-        xs[e] = ds;
-        ys[e] = pe;
-      }
-      if (tr && threadIdx.x == 0 && j < 5) tr[23 + 4 * j] = clock64();   // X(j) computed
-      if (j >= 1) mbar_wait(bar_xfree, (j - 1) & 1);
-      if (tr && threadIdx.x == 0 && j < 5) tr[24 + 4 * j] = clock64();   // X buffer free
-      store_row16_planes(x_hi, x_lo, r, part * 16, xs);
-      if (MODE == MODE_DKV) store_row16_planes(y_hi, y_lo, r, part * 16, ys);
-      tc_fence_before();
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_x);
-      if (tr && threadIdx.x == 0 && j < 5) tr[25 + 4 * j] = clock64();   // X(j) handed over
-    }
-    // ---- write the accumulators: this thread owns head-dim columns [16*part, 16*part+16) of its row ----
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-    if (tr && threadIdx.x == 0) tr[42] = clock64();                      // accumulators complete
-    const int nout = MODE == MODE_DQ ? 1 : 2;
-    for (int w = 0; w < nout; ++w) {
-      // DQ: dQ -> columns [0, D);  DKV: dK -> [D, 2D), dV -> [2D, 3D)
-      const int col0 = (MODE == MODE_DQ ? 0 : (w == 0 ? D : 2 * D)) + h * HD + part * 16;
-      uint32_t a[16], x[16];
-      tmem_ld_32x32b_x16(tmem + lane_addr + 256 + w * 128 + part * 16, a);
-      tmem_ld_32x32b_x16(tmem + lane_addr + 320 + w * 128 + part * 16, x);
-      tmem_ld_wait();
-      if (rr < p.N) {
-        float o16[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) o16[e] = __uint_as_float(a[e]) + __uint_as_float(x[e]);
-        store_out16(p.dqkv + (int64_t)(row0 + rr) * p.ld_dqkv + col0, p.dqkv_ps, o16);
-      }
-    }
-    if (tr && threadIdx.x == 0) tr[43] = clock64();                      // stored
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // backward, X / Y through tensor memory
 // ------------------------------------------------------------------------------------------------
-// Same skeleton as attn_bwd_smem_kernel, with the element-wise results handed to the accumulating MMAs through TMEM:
-// the threads overwrite the 64 fp32 columns of T1 (T2) with dS (P^T) as split bf16 — per 16-column group, 8 columns of
+// The element-wise results are handed to the accumulating MMAs through TMEM: the threads overwrite the 64 fp32 columns of T1 (T2) with dS (P^T) as split bf16 — per 16-column group, 8 columns of
 // packed hi pairs then 8 of packed lo pairs — and the MMA takes A from there (umma_bf16_ts).  Per 16 chunk columns:
 //   [Acc | AccCross] += X_hi [C_hi | C_lo]   (N = 128: the lo plane of the C stage is the second 64-wide MN chunk)
 //        AccCross    += X_lo  C_hi
-// This removes the single X/Y shared-memory buffer and its hand-back barrier (the chunk loop was a chain
+// This removed the X/Y shared-memory buffer of the previous kernels and its hand-back barrier (the chunk loop was a chain
 // T -> threads -> st.shared -> fence.proxy -> MMA -> buffer free: 1.6 / 2.0 us per chunk in the dQ / dK,dV kernels for
 // 0.95 / 1.25 us of tensor time, scripts/attn_trace.py), a third of the accumulating MMAs, and runs the remaining ones
-// at the 35 / 69 clk of the TMEM-A forms instead of 50 clk (scripts/mma_probe.cu).  The freed 64 KB hold two more C
-// stages, so the column chunks are in flight long before the MMA thread asks for them.
-constexpr int BW2_NSTAGE = 4;
-constexpr int BW2_OFF_R1 = 0, BW2_OFF_R2 = 2 * ROW_TILE_BYTES, BW2_OFF_C = 4 * ROW_TILE_BYTES;
-constexpr int BW2_OFF_VEC = BW2_OFF_C + BW2_NSTAGE * BWD_CSTAGE;           // 2 x 320 floats (lse*log2e, delta*scale per column) + [4][128] exchange
-constexpr int BW2_OFF_BAR = BW2_OFF_VEC + 2 * 320 * 4 + 4 * 128 * 4;
-constexpr int BW2_SMEM = BW2_OFF_BAR + 256 + 1024;
+// at the 35 / 69 clk of the TMEM-A forms instead of 50 clk (scripts/mma_probe.cu): 1.2 / 1.3 us per chunk, 97 -> 77 us
+// per dQ + dK,dV pair at 24 images.  The freed 64 KB hold two more C stages, so the column chunks are in flight long
+// before the MMA thread asks for them.
+constexpr int BWD_NSTAGE = 4;
+constexpr int BWD_OFF_R1 = 0, BWD_OFF_R2 = 2 * ROW_TILE_BYTES, BWD_OFF_C = 4 * ROW_TILE_BYTES;
+constexpr int BWD_OFF_VEC = BWD_OFF_C + BWD_NSTAGE * BWD_CSTAGE;           // 2 x 320 floats (lse*log2e, delta*scale per column) + [4][128] exchange
+constexpr int BWD_OFF_BAR = BWD_OFF_VEC + 2 * 320 * 4 + 4 * 128 * 4;
+constexpr int BWD_SMEM = BWD_OFF_BAR + 256 + 1024;
+
+// one 16-column group of a chunk: t1 = S, t2 = dP (fp32 from TMEM) -> xw = split(dS), yw = split(P) as 8 packed hi pairs
+// followed by 8 packed lo pairs.  DQ: the statistics belong to the thread's row; DKV: to the columns (shared memory).
+template <int MODE, bool FULL>
+__device__ __forceinline__ void bwd_group(const uint32_t (&t1)[16], const uint32_t (&t2)[16], uint32_t (&xw)[16], uint32_t (&yw)[16], float c2s,
+                                          float scale, float row_lse, float row_dsc, const float* __restrict__ col_lse,
+                                          const float* __restrict__ col_dsc, int nvalid) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float l0 = row_lse, l1 = row_lse, d0 = row_dsc, d1 = row_dsc;
+    if (MODE == MODE_DKV) {
+      const float2 l2 = *reinterpret_cast<const float2*>(col_lse + 2 * e);
+      const float2 d2 = *reinterpret_cast<const float2*>(col_dsc + 2 * e);
+      l0 = l2.x; l1 = l2.y; d0 = d2.x; d1 = d2.y;
+    }
+    float pe0 = ex2_approx(fmaf(__uint_as_float(t1[2 * e]), c2s, -l0));
+    float pe1 = ex2_approx(fmaf(__uint_as_float(t1[2 * e + 1]), c2s, -l1));
+    float ds0 = pe0 * fmaf(__uint_as_float(t2[2 * e]), scale, -d0);
+    float ds1 = pe1 * fmaf(__uint_as_float(t2[2 * e + 1]), scale, -d1);
+    if (!FULL) {
+      if (2 * e >= nvalid) pe0 = 0.f, ds0 = 0.f;
+      if (2 * e + 1 >= nvalid) pe1 = 0.f, ds1 = 0.f;
+    }
+    split2(ds0, ds1, xw[e], xw[8 + e]);
+    if (MODE == MODE_DKV) split2(pe0, pe1, yw[e], yw[8 + e]);
+  }
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
@@ -869,15 +394,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
                 const __grid_constant__ CUtensorMap tm_qkv_c, const __grid_constant__ CUtensorMap tm_do_c, const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BW2_OFF_BAR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BWD_OFF_BAR);
   uint64_t* bar_r = bars + 0;
   uint64_t* bar_acc = bars + 1;
   uint64_t* bar_t = bars + 2;       // [2]
   uint64_t* bar_x = bars + 4;       // [2] (count 16)
-  uint64_t* bar_cfull = bars + 6;   // [BW2_NSTAGE]
-  uint64_t* bar_cfree = bars + 10;  // [BW2_NSTAGE]
+  uint64_t* bar_cfull = bars + 6;   // [BWD_NSTAGE]
+  uint64_t* bar_cfree = bars + 10;  // [BWD_NSTAGE]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-  float* vec_lse = reinterpret_cast<float*>(smem + BW2_OFF_VEC);
+  float* vec_lse = reinterpret_cast<float*>(smem + BWD_OFF_VEC);
   float* vec_delta = vec_lse + 320;
   float* xch = vec_delta + 320;     // [4][128]
 
@@ -895,7 +420,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
     tma_prefetch_desc(&tm_qkv_r); tma_prefetch_desc(&tm_do_r); tma_prefetch_desc(&tm_qkv_c); tma_prefetch_desc(&tm_do_c);
     mbar_init(bar_r, 1); mbar_init(bar_acc, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&bar_t[s], 1); mbar_init(&bar_x[s], 16); }
-    for (int s = 0; s < BW2_NSTAGE; ++s) { mbar_init(&bar_cfull[s], 1); mbar_init(&bar_cfree[s], 1); }
+    for (int s = 0; s < BWD_NSTAGE; ++s) { mbar_init(&bar_cfull[s], 1); mbar_init(&bar_cfree[s], 1); }
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -924,13 +449,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
     if (elect_one()) {
       // ===== TMA producer =====
       mbar_arrive_expect_tx(bar_r, 4 * ROW_TILE_BYTES);
-      tma_load_3d(smem + BW2_OFF_R1, &tm_qkv_r, bar_r, r1_col, row0 + rt * 128, 0);  // box planes = 2: hi, lo
-      if (MODE == MODE_DQ) tma_load_3d(smem + BW2_OFF_R2, &tm_do_r, bar_r, h * HD, row0 + rt * 128, 0);
-      else tma_load_3d(smem + BW2_OFF_R2, &tm_qkv_r, bar_r, r2_col, row0 + rt * 128, 0);
+      tma_load_3d(smem + BWD_OFF_R1, &tm_qkv_r, bar_r, r1_col, row0 + rt * 128, 0);  // box planes = 2: hi, lo
+      if (MODE == MODE_DQ) tma_load_3d(smem + BWD_OFF_R2, &tm_do_r, bar_r, h * HD, row0 + rt * 128, 0);
+      else tma_load_3d(smem + BWD_OFF_R2, &tm_qkv_r, bar_r, r2_col, row0 + rt * 128, 0);
       for (int j = 0; j < nchunks; ++j) {
-        const int st_i = j % BW2_NSTAGE;
-        mbar_wait(&bar_cfree[st_i], ((j / BW2_NSTAGE) & 1) ^ 1);
-        uint8_t* st = smem + BW2_OFF_C + st_i * BWD_CSTAGE;
+        const int st_i = j % BWD_NSTAGE;
+        mbar_wait(&bar_cfree[st_i], ((j / BWD_NSTAGE) & 1) ^ 1);
+        uint8_t* st = smem + BWD_OFF_C + st_i * BWD_CSTAGE;
         mbar_arrive_expect_tx(&bar_cfull[st_i], BWD_CSTAGE);
         tma_load_3d(st, &tm_qkv_c, &bar_cfull[st_i], c1_col, row0 + j * 64, 0);
         if (MODE == MODE_DQ) tma_load_3d(st + ROW_TILE_BYTES, &tm_qkv_c, &bar_cfull[st_i], c2_col, row0 + j * 64, 0);
@@ -943,12 +468,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       constexpr uint32_t idesc_t = umma_idesc_bf16(64, 0, 0);        // T = R C^T   (both K-major, K = head dim)
       constexpr uint32_t idesc_a2 = umma_idesc_bf16(128, 0, 1);      // [Acc | cross] += X_hi [C_hi | C_lo]   (C MN-major, K = chunk columns)
       constexpr uint32_t idesc_a1 = umma_idesc_bf16(64, 0, 1);       //        cross  += X_lo  C_hi
-      const uint32_t r1 = smem_u32(smem + BW2_OFF_R1), r2 = smem_u32(smem + BW2_OFF_R2);
+      const uint32_t r1 = smem_u32(smem + BWD_OFF_R1), r2 = smem_u32(smem + BWD_OFF_R2);
       const uint64_t dr1h = umma_smem_desc(r1, 16, 1024), dr1l = umma_smem_desc(r1 + ROW_TILE_BYTES, 16, 1024);
       const uint64_t dr2h = umma_smem_desc(r2, 16, 1024), dr2l = umma_smem_desc(r2 + ROW_TILE_BYTES, 16, 1024);
       // C stage 0 views: K-major (T MMAs), MN-major hi plane alone and hi|lo as one 128-wide operand (LBO = plane distance);
       // stage s = + s * (BWD_CSTAGE >> 4) in the address field
-      const uint32_t c1s0 = smem_u32(smem + BW2_OFF_C), c2s0 = c1s0 + ROW_TILE_BYTES;
+      const uint32_t c1s0 = smem_u32(smem + BWD_OFF_C), c2s0 = c1s0 + ROW_TILE_BYTES;
       constexpr uint32_t PLANE = ROW_TILE_BYTES / 2;                  // 64 rows x 128 B
       const uint64_t dc1h0 = umma_smem_desc(c1s0, 16, 1024), dc1l0 = umma_smem_desc(c1s0 + PLANE, 16, 1024);
       const uint64_t dc2h0 = umma_smem_desc(c2s0, 16, 1024), dc2l0 = umma_smem_desc(c2s0 + PLANE, 16, 1024);
@@ -958,8 +483,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       mbar_wait(bar_r, 0);
       if (tr) tr[1] = clock64();                                   // R tiles landed
       auto issue_t = [&](int j) {
-        const int s = j & 1, st_i = j % BW2_NSTAGE;
-        mbar_wait(&bar_cfull[st_i], (j / BW2_NSTAGE) & 1);
+        const int s = j & 1, st_i = j % BWD_NSTAGE;
+        mbar_wait(&bar_cfull[st_i], (j / BWD_NSTAGE) & 1);
         tc_fence_after();
         if (tr && j < 5) tr[2 + 4 * j] = clock64();                // C chunk j landed, T MMAs go out
         const uint32_t t1 = tmem + s * 128, t2 = t1 + 64;
@@ -978,7 +503,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       };
       issue_t(0);
       for (int j = 0; j < nchunks; ++j) {
-        const int s = j & 1, st_i = j % BW2_NSTAGE;
+        const int s = j & 1, st_i = j % BWD_NSTAGE;
         // T(j+1) overwrites the columns that held X(j-1): the tensor pipe runs it after Acc(j-1), issued last iteration
         if (j + 1 < nchunks) issue_t(j + 1);
         if (tr && j < 5) tr[3 + 4 * j] = clock64();                // T(j+1) issued
@@ -1052,32 +577,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
         tmem_ld_32x32b_x16(ta, t1);
         tmem_ld_32x32b_x16(ta + 64, t2);
         tmem_ld_wait();
-        // P = exp2(S * scale*log2e - lse*log2e), dS = P * (dP - delta) * scale.  Issue-bound warps: no per-element predicates
-        // (only the last group of the image can hold padding columns), ex2.approx, everything folded into FFMAs.
-        const bool full = col0 + 16 <= p.N;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float pe0, pe1, ds0, ds1;
-          if (MODE == MODE_DQ) {
-            pe0 = ex2_approx(fmaf(__uint_as_float(t1[2 * e]), c2s, -row_lse));
-            pe1 = ex2_approx(fmaf(__uint_as_float(t1[2 * e + 1]), c2s, -row_lse));
-            ds0 = pe0 * fmaf(__uint_as_float(t2[2 * e]), p.scale, -row_dsc);
-            ds1 = pe1 * fmaf(__uint_as_float(t2[2 * e + 1]), p.scale, -row_dsc);
-          } else {
-            const float2 l2 = *reinterpret_cast<const float2*>(vec_lse + col0 + 2 * e);
-            const float2 d2 = *reinterpret_cast<const float2*>(vec_delta + col0 + 2 * e);
-            pe0 = ex2_approx(fmaf(__uint_as_float(t1[2 * e]), c2s, -l2.x));
-            pe1 = ex2_approx(fmaf(__uint_as_float(t1[2 * e + 1]), c2s, -l2.y));
-            ds0 = pe0 * fmaf(__uint_as_float(t2[2 * e]), p.scale, -d2.x);
-            ds1 = pe1 * fmaf(__uint_as_float(t2[2 * e + 1]), p.scale, -d2.y);
-          }
-          if (!full) {
-            if (col0 + 2 * e >= p.N) pe0 = 0.f, ds0 = 0.f;
-            if (col0 + 2 * e + 1 >= p.N) pe1 = 0.f, ds1 = 0.f;
-          }
-          split2(ds0, ds1, xw[e], xw[8 + e]);          // hi pairs -> columns [0, 8), lo pairs -> [8, 16) of the group
-          if (MODE == MODE_DKV) split2(pe0, pe1, yw[e], yw[8 + e]);
-        }
+        // P = exp2(S * scale*log2e - lse*log2e), dS = P * (dP - delta) * scale.  Issue-bound warps: ex2.approx, everything
+        // folded into FFMAs, and no per-element predicates — only the last group of the image can hold padding columns, and
+        // that case is a separate (warp-uniform) branch, because predicated-off instructions still take issue slots.
+        if (col0 + 16 <= p.N) bwd_group<MODE, true>(t1, t2, xw, yw, c2s, p.scale, row_lse, row_dsc, vec_lse + col0, vec_delta + col0, 16);
+        else bwd_group<MODE, false>(t1, t2, xw, yw, c2s, p.scale, row_lse, row_dsc, vec_lse + col0, vec_delta + col0, p.N - col0);
         if (tr && threadIdx.x == 0 && j < 5) tr[23 + 4 * j] = clock64();   // X(j) computed
         tmem_st_32x32b_x16(ta, xw);
         if (MODE == MODE_DKV) tmem_st_32x32b_x16(ta + 64, yw);
@@ -1151,13 +655,7 @@ extern "C" int srw_attn_fwd(const srw_attn_fwd_args* a, void* stream_) {
   const int smem_bytes = (int)(4 * ROW_TILE_BYTES + 4 * kv_plane + 128 + 2 * 4 * 128 * 4 + 1024);   // regions A, B | K | V | barriers | 2 exchange sets | align
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  static bool smem_p = false;   // SRW_ATTN_FWD=smem: the previous kernel (P through shared memory), kept for A/B measurements
-  std::call_once(once, [] {
-    const char* e = getenv("SRW_ATTN_FWD");
-    smem_p = e && e[0] == 's';
-    attr_err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(attn_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   SRW_CUDA(attr_err);
   AttnFwdParams p;
   p.B = a->B; p.N = a->N; p.H = a->H; p.NP = NP; p.scale = a->scale;
@@ -1166,7 +664,7 @@ extern "C" int srw_attn_fwd(const srw_attn_fwd_args* a, void* stream_) {
   dim3 grid(a->H, a->B);
   const double pair_flops = 2.0 * a->B * a->H * (double)a->N * a->N * HD;   // one N x N x 64 product per (image, head)
   void* prof = prof_begin(SRW_PROF_ATTN_FWD, 2.0 * pair_flops, 4.0 * 4.0 * a->B * a->N * a->H * HD, stream);
-  SRW_CUDA(launch_pdl(smem_p ? attn_fwd_smem_kernel : attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), smem_bytes, stream, tq, tkv, p));
+  SRW_CUDA(launch_pdl(attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), smem_bytes, stream, tq, tkv, p));
   prof_end(prof, stream);
   g_launches++;
   SRW_LAUNCH_CHECK();
@@ -1191,14 +689,9 @@ extern "C" int srw_attn_bwd(const srw_attn_bwd_args* a, void* stream_) {
               "srw_attn_bwd: planes must be 16-byte aligned");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  static bool smem_x = false;   // SRW_ATTN_BWD=smem: the previous kernels (X / Y through shared memory), kept for A/B measurements
   std::call_once(once, [] {
-    const char* e = getenv("SRW_ATTN_BWD");
-    smem_x = e && e[0] == 's';
-    attr_err = cudaFuncSetAttribute(attn_bwd_kernel<MODE_DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW2_SMEM);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(attn_bwd_kernel<MODE_DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW2_SMEM);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(attn_bwd_smem_kernel<MODE_DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(attn_bwd_smem_kernel<MODE_DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    attr_err = cudaFuncSetAttribute(attn_bwd_kernel<MODE_DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(attn_bwd_kernel<MODE_DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
   });
   SRW_CUDA(attr_err);
   AttnBwdParams p;
@@ -1212,13 +705,11 @@ extern "C" int srw_attn_bwd(const srw_attn_bwd_args* a, void* stream_) {
   // algorithmic backward = 4 products (dP, dV, dQ, dK); the S recomputations are overhead, not counted
   const double pair_flops = 2.0 * a->B * a->H * (double)a->N * a->N * HD;
   void* prof = prof_begin(SRW_PROF_ATTN_BWD, 4.0 * pair_flops, 4.0 * 9.0 * a->B * a->N * a->H * HD, stream);
-  SRW_CUDA(smem_x ? launch_pdl(attn_bwd_smem_kernel<MODE_DQ>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p)
-                  : launch_pdl(attn_bwd_kernel<MODE_DQ>, dim3(grid), dim3(BWD_THREADS), BW2_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p));
+  SRW_CUDA(launch_pdl(attn_bwd_kernel<MODE_DQ>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p));
   g_launches++;
   SRW_LAUNCH_CHECK();
   if (p.trace) p.trace += (size_t)grid.x * grid.y * grid.z * 48;
-  SRW_CUDA(smem_x ? launch_pdl(attn_bwd_smem_kernel<MODE_DKV>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p)
-                  : launch_pdl(attn_bwd_kernel<MODE_DKV>, dim3(grid), dim3(BWD_THREADS), BW2_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p));
+  SRW_CUDA(launch_pdl(attn_bwd_kernel<MODE_DKV>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p));
   prof_end(prof, stream);
   g_launches++;
   SRW_LAUNCH_CHECK();
