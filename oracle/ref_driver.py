@@ -110,11 +110,26 @@ def build_reference_algorithm(cfg: dict, net_kwargs: dict | None = None):
     args.ulb_dest_len = ulb_dest_len
     builder = semilearn.get_net_builder(args.net, False)
     nk = dict(net_kwargs or {})
-    if not drop_path:
+    if not drop_path and not args.net.startswith("bert"):
         nk["drop_path_rate"] = 0.0
 
     def net_builder(num_classes, pretrained=False, pretrained_path=None, **kw):
         kw = dict(kw)
+        if args.net.startswith("bert"):
+            # bert.py:13 calls BertModel.from_pretrained(name): no hub access here, so hand it a randomly initialised BertModel of
+            # the requested (small) configuration instead; `bert` = BertConfig overrides, `dropout` = the wrapper's own p
+            import semilearn.nets.bert.bert as ref_bert
+            from transformers import BertConfig, BertModel
+            hf = dict(nk.get("bert", {}))
+            orig = ref_bert.BertModel.from_pretrained
+            ref_bert.BertModel.from_pretrained = classmethod(lambda cls, name, **k: BertModel(BertConfig(**hf)))
+            try:
+                m = builder(num_classes=num_classes, pretrained=False, pretrained_path=None)
+            finally:
+                ref_bert.BertModel.from_pretrained = orig
+            if "dropout" in nk:
+                m.dropout.p = nk["dropout"]
+            return m
         for k, v in nk.items():
             kw[k] = v
         if "drop_path_rate" in kw:
@@ -143,7 +158,7 @@ def load_det_weights(alg, seed: int = 0, head_gain: float = 1.0):
         for prefix, mod in (("", alg.model), ("rewarder.", alg.rewarder), ("generator.", alg.generator)):
             for n, p in mod.named_parameters():
                 p.copy_(torch.from_numpy(detgen.fill_param(prefix + n, p.shape, seed)))
-                if prefix == "" and n == "head.weight":
+                if prefix == "" and n in ("head.weight", "classifier.2.weight"):
                     p.mul_(head_gain)
         alg.ema_model.load_state_dict(alg.model.state_dict())
     # optimizers hold references to the same Parameter objects -> nothing to rebuild

@@ -436,8 +436,8 @@ class SSLOracle:
     """Holds backbone/Rewarder/Generator parameters, optimizer and hook state; `train_step` + `param_update`
     follow srflexmatch.py:107-217 / srfreematch.py:116-228 / srsoftmatch.py:107-221 and param_update.py:21-40."""
 
-    def __init__(self, vit_cfg: ViTConfig, cfg: StepConfig, params: Dict[str, Tensor], rewarder: Dict[str, Tensor],
-                 generator: Dict[str, Tensor]):
+    def __init__(self, vit_cfg: Optional[ViTConfig], cfg: StepConfig, params: Dict[str, Tensor], rewarder: Dict[str, Tensor],
+                 generator: Dict[str, Tensor], hparams: Optional[Dict[str, Tuple[float, float]]] = None):
         self.vit_cfg, self.cfg = vit_cfg, cfg
         self.p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
         self.rp = {k: v.clone().requires_grad_(True) for k, v in rewarder.items()}
@@ -445,7 +445,8 @@ class SSLOracle:
         self.opt = AdamState(self.p, decoupled=True)
         self.ropt = AdamState(self.rp, decoupled=False)
         self.gopt = AdamState(self.gp, decoupled=False)
-        self.hp = vit_param_hparams(vit_cfg.param_shapes(), vit_cfg.depth, cfg.lr, cfg.weight_decay, cfg.layer_decay)
+        # per-parameter (lr, weight decay); other backbones (oracle/bert_oracle.py) pass their own table
+        self.hp = hparams if hparams is not None else vit_param_hparams(vit_cfg.param_shapes(), vit_cfg.depth, cfg.lr, cfg.weight_decay, cfg.layer_decay)
         self.sched_step = 0  # number of scheduler.step() calls so far (LambdaLR.last_epoch)
         self.max_reward = -float("inf")
         C = cfg.num_classes

@@ -84,7 +84,7 @@ def fill_param(name: str, shape, seed: int = 0) -> np.ndarray:
     shape = tuple(int(s) for s in shape)
     if name.endswith("cls_token") or name.endswith("pos_embed"):
         return normal(name, shape, seed, std=0.02)
-    if "norm" in name and name.endswith(".weight") and len(shape) == 1:
+    if ("norm" in name or "LayerNorm" in name) and name.endswith(".weight") and len(shape) == 1:   # "LayerNorm": the HF BERT names (bert.py:13)
         return normal(name, shape, seed, std=0.1, mean=1.0)
     if name.endswith(".bias") or len(shape) == 1:
         return normal(name, shape, seed, std=0.05)
@@ -113,4 +113,29 @@ def ssl_batch(batch_size: int, uratio: int, num_classes: int, ulb_dest_len: int,
         idx_ulb=distinct_integers("idx_ulb", bu, ulb_dest_len, s),
         x_ulb_w=normal("x_ulb_w", (bu, in_chans, img_size, img_size), s),
         x_ulb_s=normal("x_ulb_s", (bu, in_chans, img_size, img_size), s),
+    )
+
+
+def nlp_batch(batch_size: int, uratio: int, num_classes: int, ulb_dest_len: int, max_length: int = 512, vocab_size: int = 30522,
+              min_length: int = 0, seed: int = 1, step: int = 0):
+    """One synthetic text SSL batch with the reference's batch-dict keys (semilearn/datasets/nlp_datasets/datasetbase.py,
+    collators: x_* = {'input_ids', 'attention_mask'} int64 [B, L]): token ids uniform in [1000, vocab) (or [1, vocab) for a
+    small test vocabulary), lengths uniform in [min_length or L/4, L], a zero tail of padding (pad id 0) under a zero
+    attention mask — BASELINE configs[3] as SURVEY.md §8d describes it."""
+    bu = batch_size * uratio
+    s = seed * 1000003 + step
+    lo = 1000 if vocab_size > 2000 else 1
+    min_len = min_length if min_length > 0 else max(1, max_length // 4)
+
+    def text(tag, n):
+        ids = integers(tag + "_ids", (n, max_length), lo, vocab_size, s)
+        lens = integers(tag + "_len", (n,), min_len, max_length + 1, s)
+        am = (np.arange(max_length, dtype=np.int64)[None, :] < lens[:, None]).astype(np.int64)
+        return dict(input_ids=ids * am, attention_mask=am)
+    return dict(
+        x_lb=text("x_lb", batch_size),
+        y_lb=integers("y_lb", (batch_size,), 0, num_classes, s),
+        idx_ulb=distinct_integers("idx_ulb", bu, ulb_dest_len, s),
+        x_ulb_w=text("x_ulb_w", bu),
+        x_ulb_s=text("x_ulb_s", bu),
     )

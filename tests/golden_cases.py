@@ -9,3 +9,21 @@ CASES = {
     "srpseudolabel_d2": dict(cfg=dict(algorithm="srpseudolabel", p_cutoff=0.5, unsup_warm_up=0.05), depth=2, head_gain=2.0),
     "srfixmatch_d2": dict(cfg=dict(algorithm="srfixmatch", p_cutoff=0.5), depth=2, head_gain=2.0),   # mixed masks in every stage
 }
+
+# Text path (BASELINE configs[3]): ClassificationBert with a 2-layer random-init BertModel, use_cat False,
+# dropout 0 (deterministic parity mode).  oracle/bert_oracle.py is pinned by tests/golden/bert_*.npz (make_golden_bert.py).
+BERT_SMALL = dict(vocab_size=512, layers=2, max_position=64, max_length=32)
+BERT_CASES = {
+    # the BASELINE configs[3] algorithm: SoftMatch weights + uniform DistAlign, 2 classes (IMDb)
+    "bert_srsoftmatch_l2": dict(cfg=dict(algorithm="srsoftmatch", num_classes=2), head_gain=4.0),
+    # fixed threshold between the weak-view confidences (4 classes, ag_news) -> mixed masks in every stage
+    "bert_srfixmatch_l2": dict(cfg=dict(algorithm="srfixmatch", num_classes=4, p_cutoff=0.85), head_gain=3.0),
+}
+
+
+def bert_small_cfg(**over):
+    c = dict(algorithm="srsoftmatch", net="bert_base_uncased", optim="AdamW", lr=5e-5, layer_decay=0.75, weight_decay=5e-4,
+             num_train_iter=64, num_warmup_iter=0, start_timing=3, N_k=2, batch_size=4, uratio=1, num_classes=2, ulb_dest_len=64,
+             feature_dim=768, sr_lr=5e-4, sr_ema=False, use_cat=False, amp=False, ema_m=0.0, thresh_warmup=True, p_cutoff=0.95)
+    c.update(over)
+    return c
