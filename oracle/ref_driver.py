@@ -110,11 +110,15 @@ def build_reference_algorithm(cfg: dict, net_kwargs: dict | None = None):
     args.ulb_dest_len = ulb_dest_len
     builder = semilearn.get_net_builder(args.net, False)
     nk = dict(net_kwargs or {})
-    if not drop_path and not args.net.startswith("bert"):
+    if not drop_path and args.net.startswith("vit"):
         nk["drop_path_rate"] = 0.0
 
     def net_builder(num_classes, pretrained=False, pretrained_path=None, **kw):
         kw = dict(kw)
+        if args.net.startswith("wrn") and "depth" in nk:
+            # the named builders fix depth 28 (wrn.py:160-171): a shallower fixture goes through the class directly
+            from semilearn.nets.wrn.wrn import WideResNet
+            return WideResNet(first_stride=1, num_classes=num_classes, depth=nk["depth"], widen_factor=dict(wrn_28_2=2, wrn_28_8=8)[args.net])
         if args.net.startswith("bert"):
             # bert.py:13 calls BertModel.from_pretrained(name): no hub access here, so hand it a randomly initialised BertModel of
             # the requested (small) configuration instead; `bert` = BertConfig overrides, `dropout` = the wrapper's own p
@@ -158,7 +162,7 @@ def load_det_weights(alg, seed: int = 0, head_gain: float = 1.0):
         for prefix, mod in (("", alg.model), ("rewarder.", alg.rewarder), ("generator.", alg.generator)):
             for n, p in mod.named_parameters():
                 p.copy_(torch.from_numpy(detgen.fill_param(prefix + n, p.shape, seed)))
-                if prefix == "" and n in ("head.weight", "classifier.2.weight"):
+                if prefix == "" and n in ("head.weight", "classifier.2.weight", "classifier.weight"):
                     p.mul_(head_gain)
         alg.ema_model.load_state_dict(alg.model.state_dict())
     # optimizers hold references to the same Parameter objects -> nothing to rebuild

@@ -84,7 +84,8 @@ def fill_param(name: str, shape, seed: int = 0) -> np.ndarray:
     shape = tuple(int(s) for s in shape)
     if name.endswith("cls_token") or name.endswith("pos_embed"):
         return normal(name, shape, seed, std=0.02)
-    if ("norm" in name or "LayerNorm" in name) and name.endswith(".weight") and len(shape) == 1:   # "LayerNorm": the HF BERT names (bert.py:13)
+    is_bn = name.endswith((".bn1.weight", ".bn2.weight")) or name == "bn1.weight"   # WideResNet's BatchNorm scales (wrn.py:33,37,97)
+    if ("norm" in name or "LayerNorm" in name or is_bn) and name.endswith(".weight") and len(shape) == 1:   # "LayerNorm": the HF BERT names (bert.py:13)
         return normal(name, shape, seed, std=0.1, mean=1.0)
     if name.endswith(".bias") or len(shape) == 1:
         return normal(name, shape, seed, std=0.05)

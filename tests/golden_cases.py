@@ -27,3 +27,18 @@ def bert_small_cfg(**over):
              feature_dim=768, sr_lr=5e-4, sr_ema=False, use_cat=False, amp=False, ema_m=0.0, thresh_warmup=True, p_cutoff=0.95)
     c.update(over)
     return c
+
+# Convolutional path (BASELINE configs[0]): WideResNet (depth 10 for the fixtures, widen 2), use_cat True,
+# SGD + nesterov.  oracle/wrn_oracle.py is pinned by tests/golden/wrn_*.npz (make_golden_wrn.py).
+WRN_CASES = {
+    "wrn_srflexmatch_d10": dict(cfg=dict(algorithm="srflexmatch"), depth=10, head_gain=4.0),
+    "wrn_srfixmatch_d10": dict(cfg=dict(algorithm="srfixmatch", p_cutoff=0.2), depth=10, head_gain=4.0),   # mixed masks in every stage
+}
+
+
+def wrn_small_cfg(**over):
+    c = dict(algorithm="srflexmatch", net="wrn_28_2", optim="SGD", lr=0.03, momentum=0.9, layer_decay=1.0, weight_decay=1e-3,
+             num_train_iter=64, num_warmup_iter=0, start_timing=3, N_k=2, batch_size=4, uratio=2, num_classes=100, ulb_dest_len=64,
+             feature_dim=128, sr_lr=5e-4, sr_ema=False, use_cat=True, amp=False, ema_m=0.999, thresh_warmup=True, p_cutoff=0.95)
+    c.update(over)
+    return c
