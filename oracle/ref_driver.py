@@ -119,6 +119,20 @@ def build_reference_algorithm(cfg: dict, net_kwargs: dict | None = None):
             # the named builders fix depth 28 (wrn.py:160-171): a shallower fixture goes through the class directly
             from semilearn.nets.wrn.wrn import WideResNet
             return WideResNet(first_stride=1, num_classes=num_classes, depth=nk["depth"], widen_factor=dict(wrn_28_2=2, wrn_28_8=8)[args.net])
+        if args.net.startswith("hubert"):
+            # hubert.py:13 calls HubertModel.from_pretrained(name): hand it a randomly initialised HubertModel(HubertConfig(**hubert))
+            import semilearn.nets.hubert.hubert as ref_hubert
+            from transformers import HubertConfig, HubertModel
+            hf = dict(nk.get("hubert", {}))
+            orig = ref_hubert.HubertModel.from_pretrained
+            ref_hubert.HubertModel.from_pretrained = classmethod(lambda cls, name, **k: HubertModel(HubertConfig(**hf)))
+            try:
+                m = builder(num_classes=num_classes, pretrained=False, pretrained_path=None)
+            finally:
+                ref_hubert.HubertModel.from_pretrained = orig
+            if "dropout" in nk:
+                m.dropout.p = nk["dropout"]
+            return m
         if args.net.startswith("bert"):
             # bert.py:13 calls BertModel.from_pretrained(name): no hub access here, so hand it a randomly initialised BertModel of
             # the requested (small) configuration instead; `bert` = BertConfig overrides, `dropout` = the wrapper's own p

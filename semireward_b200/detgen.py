@@ -140,3 +140,17 @@ def nlp_batch(batch_size: int, uratio: int, num_classes: int, ulb_dest_len: int,
         x_ulb_w=text("x_ulb_w", bu),
         x_ulb_s=text("x_ulb_s", bu),
     )
+
+
+def audio_batch(batch_size: int, uratio: int, num_classes: int, ulb_dest_len: int, samples: int = 64000, seed: int = 1, step: int = 0):
+    """One synthetic audio SSL batch with the reference's batch-dict keys (semilearn/datasets/audio_datasets/datasetbase.py:
+    x_* = fp32 waveforms [B, samples], 16 kHz): unit-variance noise, the normalised case of BASELINE configs[4]."""
+    bu = batch_size * uratio
+    s = seed * 1000003 + step
+    return dict(
+        x_lb=normal("x_lb", (batch_size, samples), s),
+        y_lb=integers("y_lb", (batch_size,), 0, num_classes, s),
+        idx_ulb=distinct_integers("idx_ulb", bu, ulb_dest_len, s),
+        x_ulb_w=normal("x_ulb_w", (bu, samples), s),
+        x_ulb_s=normal("x_ulb_s", (bu, samples), s),
+    )

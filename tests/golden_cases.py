@@ -42,3 +42,19 @@ def wrn_small_cfg(**over):
              feature_dim=128, sr_lr=5e-4, sr_ema=False, use_cat=True, amp=False, ema_m=0.999, thresh_warmup=True, p_cutoff=0.95)
     c.update(over)
     return c
+
+# Audio path (BASELINE configs[4]): ClassificationHubert with a 2-layer random-init HubertModel (full conv
+# stem), use_cat False, 4000-sample clips (12 frames), every source of randomness off (dropout, LayerDrop, SpecAugment).
+HUBERT_SMALL = dict(layers=2, samples=4000)
+HUBERT_CASES = {
+    "hubert_srflexmatch_l2": dict(cfg=dict(algorithm="srflexmatch"), head_gain=4.0),                   # the configs[4] algorithm
+    "hubert_srfixmatch_l2": dict(cfg=dict(algorithm="srfixmatch", p_cutoff=0.5), head_gain=4.0),       # mixed masks
+}
+
+
+def hubert_small_cfg(**over):
+    c = dict(algorithm="srflexmatch", net="hubert_base", optim="AdamW", lr=2e-5, layer_decay=0.75, weight_decay=5e-4, num_train_iter=64,
+             num_warmup_iter=0, start_timing=3, N_k=2, batch_size=2, uratio=2, num_classes=10, ulb_dest_len=64, feature_dim=768, sr_lr=5e-4,
+             sr_ema=False, use_cat=False, amp=False, ema_m=0.0, thresh_warmup=True, p_cutoff=0.95)
+    c.update(over)
+    return c
