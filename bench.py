@@ -236,6 +236,12 @@ def main_native(a):
     # the ParamUpdateHook's own event timing syncs every step; the bench brackets the whole region instead
     del alg.start_run, alg.end_run
     W, K = max(3, a.warmup), a.steps
+    # one-time engine set-up outside the measurement (reported as config.setup_steps): the first call of a backbone pass runs
+    # eagerly, the second is captured into a CUDA graph, kernels are lazily loaded on first use and stage 2 alternates between
+    # step variants (SR update every N_k steps) — with a short --warmup those one-offs would land in the timed region
+    SETUP_STEPS = 12
+    for i in range(SETUP_STEPS):
+        step_device(i)
     for i in range(W):
         step_device(i)
     launches0 = lib.srw_kernel_launches()
@@ -296,7 +302,7 @@ def main_native(a):
                     config=dict(workload=(f"srflexmatch vit_small_patch2_32 cifar100 batch_size {B} uratio {args.uratio} stage {a.stage} (BASELINE configs[1])"
                                           if a.config == 2 else
                                           f"srfreematch vit_base_patch16_224 synthetic 224x224 1000 classes batch_size {B} per GPU stage {a.stage} (BASELINE configs[2])"),
-                                samples_per_step_per_gpu=samples_per_step, parallelism=f"dp{world}", drop_path=0.2,
+                                samples_per_step_per_gpu=samples_per_step, parallelism=f"dp{world}", drop_path=0.2, setup_steps=SETUP_STEPS,
                                 arithmetic="fp32 semantics: bf16x3 split-precision tcgen05 MMA, fp32 accumulate",
                                 l2="step working set (~1.8 GB of activations at batch 8) >> 126 MB L2; 4 rotating input batches",
                                 launch="CUDA-graph replay of the backbone forward/backward (SRW_GRAPHS) + programmatic dependent launch (SRW_PDL); "
