@@ -48,7 +48,9 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch-size", type=int, default=8, help="per-GPU labelled batch (config-faithful: 8)")
     ap.add_argument("--stage", type=int, default=1, choices=[1, 2])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3], help="BASELINE.json configs index + 1: 2 = headline ViT-S CIFAR-100, 3 = ViT-B/16 224 FreeMatch")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE.json configs index + 1: 2 = headline ViT-S CIFAR-100, 3 = ViT-B/16 224 FreeMatch; 1 (WRN-28-2), 4 (BERT-base) and "
+                         "5 (HuBERT-base) have no CUDA path yet and exist for --impl reference only (CPU oracle timing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     return ap.parse_args()
@@ -140,9 +142,65 @@ def cpu_reference_run(cfg, steps, warmup, stage):
     return samples / per_step, per_step, cores
 
 
+def cpu_reference_run_other(config, steps, warmup):
+    """CPU timing of the oracles of the BASELINE configs that have no CUDA path yet: configs[0] WRN-28-2
+    (oracle/wrn_oracle.py), configs[3] BERT-base (oracle/bert_oracle.py), configs[4] HuBERT-base (oracle/hubert_oracle.py), all
+    pinned against the live reference.  Bounded samples of the named workloads (stated in the returned description)."""
+    import torch
+    from oracle import ssl_oracle as O
+    from semireward_b200 import detgen
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    common = dict(ulb_dest_len=50000, start_timing=20000, N_k=10, num_train_iter=204800, num_warmup_iter=0, sr_lr=5e-4)
+    if config == 1:     # config/classic_cv/flexmatch/flexmatch_cifar100_400_0.yaml + SR keys (SURVEY.md §8d): B 64, uratio 7, SGD
+        from oracle import wrn_oracle as WO
+        B, u, C = 64, 7, 100
+        sc = O.StepConfig(algorithm="srflexmatch", num_classes=C, lr=0.03, weight_decay=1e-3, layer_decay=1.0, feature_dim=128, **common)
+        orc = WO.build_det_wrn_oracle(WO.WRNCfg(num_classes=C), sc, seed=0)
+        batch = lambda i: O.to_torch_batch(detgen.ssl_batch(B, u, C, 50000, seed=1, step=i))
+        name, what = "WRN-28-2 CIFAR-100", f"srflexmatch wrn_28_2 cifar100 batch_size {B} uratio {u} SGD stage 1 (BASELINE configs[0])"
+    elif config == 4:   # config/usb_nlp/softmatch/softmatch_aclImdb_20_0.yaml + SR keys: max_length 512, 2 classes; sample: batch 2 of 8
+        from oracle import bert_oracle as BO
+        B, u, C = 2, 1, 2
+        sc = O.StepConfig(algorithm="srsoftmatch", num_classes=C, lr=5e-5, weight_decay=5e-4, layer_decay=0.75, feature_dim=768, **common)
+        orc = BO.build_det_bert_oracle(BO.BertCfg(num_classes=C, hidden_dropout=0.0, attn_dropout=0.0, pooled_dropout=0.0), sc, seed=0)
+
+        def batch(i):
+            b = detgen.nlp_batch(B, u, C, 50000, max_length=512, seed=1, step=i)
+            return {k: ({kk: torch.from_numpy(vv) for kk, vv in v.items()} if isinstance(v, dict) else torch.from_numpy(v)) for k, v in b.items()}
+        name, what = "BERT-base IMDb", f"srsoftmatch bert_base_uncased max_length 512 batch_size {B} (of 8) uratio {u} stage 1, dropout off (BASELINE configs[3])"
+    else:               # config/SemiReward/usb_audio/flexmatch/flexmatch_urbansound8k_100_0.yaml: 4 s clips, 10 classes; sample: batch 2 of 8
+        from oracle import hubert_oracle as HO
+        B, u, C = 2, 1, 10
+        sc = O.StepConfig(algorithm="srflexmatch", num_classes=C, lr=2e-5, weight_decay=5e-4, layer_decay=0.75, feature_dim=768, **common)
+        orc = HO.build_det_hubert_oracle(HO.HubertCfg(num_classes=C), sc, seed=0)
+        batch = lambda i: O.to_torch_batch(detgen.audio_batch(B, u, C, 50000, samples=64000, seed=1, step=i))
+        name, what = "HuBERT-base UrbanSound8k", f"srflexmatch hubert_base 64000-sample clips batch_size {B} (of 8) uratio {u} stage 1, dropout / LayerDrop / SpecAugment off (BASELINE configs[4])"
+    times = []
+    for i in range(warmup + steps):
+        b = batch(i)
+        t0 = time.perf_counter()
+        orc.train_step(b, 1 + i)
+        orc.param_update()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    per_step = sum(times) / len(times)
+    return B * (1 + 2 * u) / per_step, per_step, cores, name, what, B * (1 + 2 * u)
+
+
 def main_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if a.config in (1, 4, 5):
+        steps, warmup = max(1, min(a.steps, 2)), max(0, min(a.warmup, 1))     # tens of seconds per CPU step
+        sps, per_step, cores, name, what, samples = cpu_reference_run_other(a.config, steps, warmup)
+        print(json.dumps(dict(impl="reference", metric=f"SSL train-step samples/sec ({name})", value=sps, unit="samples/s", n_gpus=a.gpus, steps=steps,
+                              warmup=warmup, ms_per_step=per_step * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                              data="synthetic", config=dict(workload=what, samples_per_step=samples),
+                              cpu_baseline=dict(value=sps, unit="samples/s", cores=cores, kind="port",
+                                                sample=f"{steps} step(s) of the oracle restatement (pinned against the live reference), {warmup} warm-up"),
+                              e2e=dict(value=sps, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
         return
     cfg = dict(YAML_CFG, batch_size=a.batch_size)
     steps, warmup = max(1, min(a.steps, 8)), max(0, min(a.warmup, 2))   # bounded sample: ~1 s per CPU step, at most 8 + 2 steps
@@ -162,6 +220,8 @@ def main_reference(a):
 # native arm
 # ------------------------------------------------------------------------------------------------
 def main_native(a):
+    if a.config not in (2, 3):
+        raise SystemExit(f"bench.py: BASELINE configs[{a.config - 1}] has no CUDA path yet (DESIGN.md §9); only --impl reference can time it")
     import torch
     import torch.distributed as dist
     import semireward_b200 as S
