@@ -78,19 +78,47 @@ class BertCfg:
         return self.layers * per_layer + 2.0 * (H * H + H * self.num_classes)
 
 
+def counter_keep_mask(numel: int, keep: float, seed: int, site: int) -> Tensor:
+    """Counter-based Bernoulli(keep) mask that a CUDA epilogue can reproduce element for element (no RNG stream to share):
+    element i of dropout site `site` is kept iff the top 24 bits of splitmix64(seed * 2^32 + site * 2^40-ish mix + i) are
+    below keep * 2^24.  Pure 64-bit integer arithmetic (wrap-around multiply), identical on every device."""
+    M = (1 << 64) - 1
+
+    def to_i64(v):
+        v &= M
+        return v - (1 << 64) if v >= (1 << 63) else v
+    base = to_i64(((seed & 0xFFFFFFFF) << 32) ^ ((site & 0xFFFFF) * 0x9E3779B97F4A7C15))
+    x = torch.arange(numel, dtype=torch.int64) + base                     # int64 add / mul wrap modulo 2^64 like uint64
+    x = x + to_i64(0x9E3779B97F4A7C15)
+
+    def shr(v, n):                                                        # logical right shift on int64 storage
+        return (v >> n) & ((1 << (64 - n)) - 1)
+    z = (x ^ shr(x, 30)) * to_i64(0xBF58476D1CE4E5B9)
+    z = (z ^ shr(z, 27)) * to_i64(0x94D049BB133111EB)
+    z = z ^ shr(z, 31)
+    return shr(z, 40) < int(keep * (1 << 24))
+
+
 class BertDropout:
     """Order in which a stochastic pass draws its Bernoulli(1-p)/(1-p) masks: embeddings; per layer attention probabilities
     [B, heads, L, L], attention output [B, L, H], FFN output [B, L, H]; last the pooled-feature dropout [B, L, H].
-    p = 0 everywhere (deterministic parity mode) draws nothing."""
+    p = 0 everywhere (deterministic parity mode) draws nothing.  `generator` is either a torch.Generator (masks from torch's
+    CPU stream, like the reference's nn.Dropout but not reproducible elsewhere) or an int seed: then site k of the pass uses
+    counter_keep_mask(numel, keep, seed, k), which a native kernel can regenerate bit for bit."""
 
-    def __init__(self, cfg: BertCfg, generator: Optional[torch.Generator], enabled: bool):
+    def __init__(self, cfg: BertCfg, generator, enabled: bool):
         self.cfg, self.gen, self.enabled = cfg, generator, enabled
+        self.site = 0
 
     def __call__(self, x: Tensor, p: float) -> Tensor:
         if not self.enabled or p == 0.0:
             return x
         keep = 1.0 - p
-        m = torch.empty_like(x).bernoulli_(keep, generator=self.gen).div_(keep)
+        if isinstance(self.gen, int):
+            m = counter_keep_mask(x.numel(), keep, self.gen, self.site).view(x.shape).to(x.dtype).div_(keep)
+            self.site += 1
+        else:
+            m = torch.empty_like(x).bernoulli_(keep, generator=self.gen).div_(keep)
         return x * m
 
 

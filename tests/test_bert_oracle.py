@@ -157,3 +157,32 @@ def test_bert_oracle_matches_live_reference_default_attention():
             assert abs(g["lr"] - lr) < 1e-15 and g["weight_decay"] == wd, names[id(p)]
             seen += 1
     assert seen == len(hp)
+
+
+def test_counter_dropout_masks_are_reproducible_and_unbiased():
+    """The counter-based masks (what a native epilogue will regenerate): keep rate, independence across sites, and a stochastic
+    forward that is a pure function of (inputs, seed)."""
+    from oracle import bert_oracle as BO
+    m3 = BO.counter_keep_mask(1 << 18, 0.9, 7, 3)
+    assert abs(float(m3.float().mean()) - 0.9) < 3e-3
+    assert 0.15 < float((BO.counter_keep_mask(1 << 18, 0.9, 7, 4) != m3).float().mean()) < 0.21     # 2 * 0.9 * 0.1 for independent sites
+    assert torch.equal(BO.counter_keep_mask(1000, 0.9, 7, 3), m3[:1000])                            # element i does not depend on the extent
+    # numpy uint64 restatement of the same hash
+    keep, seed, site, n = 0.9, 7, 3, 4096
+    base = np.uint64((((seed & 0xFFFFFFFF) << 32) ^ (((site & 0xFFFFF) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF)
+    with np.errstate(over="ignore"):
+        x = np.arange(n, dtype=np.uint64) + base + np.uint64(0x9E3779B97F4A7C15)
+        z = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    assert np.array_equal((z >> np.uint64(40)) < np.uint64(int(keep * (1 << 24))), m3[:n].numpy())
+    cfg = bert_small_cfg()
+    bc = _bert_cfg(cfg, hidden_dropout=0.1, attn_dropout=0.1, pooled_dropout=0.1)
+    from semireward_b200 import detgen
+    p = {n_: torch.from_numpy(detgen.fill_param(n_, s, 0)) for n_, s in bc.param_shapes()}
+    x = _text_batch(cfg, 0)["x_lb"]
+    a, _ = BO.bert_forward(p, x, bc, BO.BertDropout(bc, 11, True))
+    b, _ = BO.bert_forward(p, x, bc, BO.BertDropout(bc, 11, True))
+    c, _ = BO.bert_forward(p, x, bc, BO.BertDropout(bc, 12, True))
+    d, _ = BO.bert_forward(p, x, bc)
+    assert torch.equal(a, b) and not torch.equal(a, c) and not torch.equal(a, d)
