@@ -364,7 +364,9 @@ class VisionTransformer(nn.Module):
         """grad_batch (extension): only the first `grad_batch` rows are back-propagated (rows after it must only feed
         detached consumers, like the weak-augmentation rows of the SSL batch)."""
         if only_fc:
-            raise NotImplementedError("only_fc (classifier on external features) is an eval.py path, not on the train-step hot path")
+            # vit.py:293-294 / eval.py:82-83: the classifier alone on externally pooled features [B, D].  Off the train-step hot
+            # path (a [B, D] x [D, C] product), so it is the plain library linear on the module's own parameters.
+            return torch.nn.functional.linear(x, self.head.weight, self.head.bias)
         logits, feat = self._run(x, grad_batch, drop_scale)
         if only_feat:
             return feat

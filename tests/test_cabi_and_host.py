@@ -58,6 +58,8 @@ def test_net_builder_state_dict_contract():
     assert [k for k in sd] == [n for n, _ in ref] and len(sd) == 152
     assert all(tuple(sd[n].shape) == tuple(s) for n, s in ref)
     assert m.num_features == 384 and m.no_weight_decay() == {"pos_embed", "cls_token"}
+    feat = torch.randn(5, 384)
+    assert torch.equal(m(feat, only_fc=True), torch.nn.functional.linear(feat, m.head.weight, m.head.bias))   # vit.py:293-294
     assert set(m.group_matcher()) == {"stem", "blocks"}
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(1, 3, 32, 32))   # no CPU fallback
