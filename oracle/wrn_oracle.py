@@ -95,10 +95,32 @@ def new_bn_buffers(cfg: WRNCfg) -> Dict[str, Tensor]:
     return buf
 
 
-def wrn_forward(p: Dict[str, Tensor], buf: Dict[str, Tensor], x: Tensor, cfg: WRNCfg, training: bool = True):
+def _sync_batch_norm(t: Tensor, rm: Tensor, rv: Tensor, w: Tensor, b: Tensor, momentum: float, eps: float, group) -> Tensor:
+    """nn.SyncBatchNorm in train mode (what send_model_cuda turns every BatchNorm2d into under DDP, core/utils/misc.py:54):
+    mean / biased variance over the rows of ALL ranks, running statistics advanced with the global mean and the unbiased
+    global variance.  Differentiable all-reduces, so the backward exchanges the gradient statistics as SyncBatchNorm does."""
+    import torch.distributed.nn.functional as dfn
+    C = t.shape[1]
+    cnt = torch.tensor([float(t.numel() // C)])
+    s = dfn.all_reduce(t.sum((0, 2, 3)), group=group)
+    ss = dfn.all_reduce((t * t).sum((0, 2, 3)), group=group)
+    n = dfn.all_reduce(cnt, group=group)
+    mean = s / n
+    var = ss / n - mean * mean
+    with torch.no_grad():
+        rm.mul_(1 - momentum).add_(mean.detach(), alpha=momentum)
+        rv.mul_(1 - momentum).add_(var.detach() * (n / (n - 1)), alpha=momentum)
+    return (t - mean[None, :, None, None]) * torch.rsqrt(var + eps)[None, :, None, None] * w[None, :, None, None] + b[None, :, None, None]
+
+
+def wrn_forward(p: Dict[str, Tensor], buf: Dict[str, Tensor], x: Tensor, cfg: WRNCfg, training: bool = True, sync_group=None):
     """-> (logits [B, C], feat [B, 64*widen]).  In training mode the batch statistics of ALL rows of x normalise every row
-    and `buf` (running mean / unbiased running var) is advanced in place, exactly like nn.BatchNorm2d."""
+    and `buf` (running mean / unbiased running var) is advanced in place, exactly like nn.BatchNorm2d.  `sync_group`: a
+    torch.distributed group -> SyncBatchNorm semantics (statistics over the rows of every rank), the data-parallel form."""
     def bn(name, t, eps=1e-5):
+        if sync_group is not None and training:
+            return _sync_batch_norm(t, buf[name + ".running_mean"], buf[name + ".running_var"], p[name + ".weight"], p[name + ".bias"],
+                                    cfg.bn_momentum, eps, sync_group)
         return F.batch_norm(t, buf[name + ".running_mean"], buf[name + ".running_var"], p[name + ".weight"], p[name + ".bias"], training,
                             cfg.bn_momentum, eps)
 

@@ -53,3 +53,55 @@ def test_two_rank_gradient_average_and_sharding():
     assert res[0][3] == res[1][3] == 11.0
     assert res[0][4] != res[1][4]
     assert res[0][5] == [[9, 6, 3], [3, 2, 1], [1], []]   # dp_overlap_split = 4 block ranges
+
+
+def _wrn_sync_worker(rank, world, port, q):
+    """Data-parallel WRN: under DDP the reference's BatchNorms are SyncBatchNorms (misc.py:54), so the N
+    ranks are NOT independent — every rank normalises with the statistics of all ranks' rows.  The oracle's sync form on
+    `world` ranks must equal one process running BatchNorm over the union of the ranks' batches, with the mean of the
+    per-rank losses as the loss (DDP averages gradients)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    import torch.nn.functional as F
+    from oracle import wrn_oracle as WO
+    from semireward_b200 import detgen
+    cfg = WO.WRNCfg(depth=10, num_classes=10)
+    p = {n: torch.from_numpy(detgen.fill_param(n, s, 0)).requires_grad_(True) for n, s in cfg.param_shapes()}
+    xs = [torch.from_numpy(detgen.normal("x", (6, 3, 16, 16), 100 + r)) for r in range(world)]
+    ys = [torch.from_numpy(detgen.integers("y", (6,), 0, 10, 100 + r)) for r in range(world)]
+    names = list(p)
+    # this rank, synchronised statistics
+    buf = WO.new_bn_buffers(cfg)
+    logits, _ = WO.wrn_forward(p, buf, xs[rank], cfg, training=True, sync_group=dist.group.WORLD)
+    loss = F.cross_entropy(logits, ys[rank])
+    grads = torch.autograd.grad(loss, [p[n] for n in names], allow_unused=True)
+    flat = torch.cat([(g if g is not None else torch.zeros_like(p[n])).reshape(-1) for n, g in zip(names, grads)])
+    dist.all_reduce(flat)
+    flat /= world                                   # DDP: average of the ranks' gradients
+    # one process, BatchNorm over the union
+    buf1 = WO.new_bn_buffers(cfg)
+    lu, _ = WO.wrn_forward(p, buf1, torch.cat(xs), cfg, training=True)
+    loss_u = sum(F.cross_entropy(lu[6 * r:6 * (r + 1)], ys[r]) for r in range(world)) / world
+    gu = torch.autograd.grad(loss_u, [p[n] for n in names], allow_unused=True)
+    flat_u = torch.cat([(g if g is not None else torch.zeros_like(p[n])).reshape(-1) for n, g in zip(names, gu)])
+    err_l = (logits - lu[6 * rank:6 * (rank + 1)]).abs().max().item()
+    err_g = (flat - flat_u).abs().max().item() / flat_u.abs().max().item()
+    err_b = max((buf[k] - buf1[k]).abs().max().item() for k in buf)
+    q.put((rank, err_l, err_g, err_b))
+    dist.destroy_process_group()
+
+
+def test_wrn_sync_batchnorm_equals_union_batch():
+    world, port = 2, 29741
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_wrn_sync_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err_l, err_g, err_b in res:
+        assert err_l < 2e-4 and err_g < 2e-4 and err_b < 1e-5, (rank, err_l, err_g, err_b)
