@@ -34,6 +34,41 @@ def test_struct_sizes_match_header_layout():
     assert C.sizeof(L.VitConfig) == 9 * 4
 
 
+def test_every_struct_matches_the_header_field_by_field(tmp_path):
+    """include/srw.h compiled as plain C11 by gcc: sizeof and every offsetof against the ctypes mirrors in _lib.py (a field
+    added, renamed or retyped on one side only fails here, on CPU, instead of corrupting arguments on the GPU box)."""
+    import ctypes as C
+    import subprocess
+    from semireward_b200 import _lib as L
+    pairs = dict(srw_profile_stats="ProfileStats", srw_split_args="SplitArgs", srw_gemm_args="GemmArgs", srw_splitk_reduce_args="SplitKReduceArgs",
+                 srw_colsum_args="ColsumArgs", srw_fold_colsum="FoldColsum", srw_grad_fold_args="GradFoldArgs", srw_layernorm_fwd_args="LayerNormFwdArgs",
+                 srw_layernorm_bwd_args="LayerNormBwdArgs", srw_attn_fwd_args="AttnFwdArgs", srw_attn_bwd_args="AttnBwdArgs", srw_vit_config="VitConfig",
+                 srw_vit_fwd_args="VitFwdArgs", srw_vit_bwd_args="VitBwdArgs", srw_rewarder_fwd_args="RewarderFwdArgs",
+                 srw_generator_fwd_args="GeneratorFwdArgs", srw_rewarder_train_args="RewarderTrainArgs", srw_flexmatch_mask_args="FlexMatchMaskArgs",
+                 srw_ssl_loss_args="SslLossArgs", srw_freematch_mask_args="FreeMatchMaskArgs", srw_freematch_entropy_args="FreeMatchEntropyArgs",
+                 srw_softmatch_mask_args="SoftMatchMaskArgs", srw_adamw_row="AdamWRow", srw_adamw_args="AdamWArgs", srw_ema_row="EmaRow",
+                 srw_ema_args="EmaArgs")
+    hdr = open(os.path.join(ROOT, "include", "srw.h")).read()
+    assert set(re.findall(r"}\s*(srw_[a-z0-9_]+);", hdr)) == set(pairs), "a struct of include/srw.h has no ctypes mirror in this table"
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "srw.h"', "int main(void) {"]
+    for cname, pyname in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for f in getattr(L, pyname)._fields_:
+            lines.append(f'  printf("{cname} {f[0]} %zu\\n", offsetof({cname}, {f[0]}));')
+    lines += ["  return 0;", "}"]
+    src, exe = tmp_path / "abi.c", tmp_path / "abi"
+    src.write_text("\n".join(lines))
+    r = subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[:2000]
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout.strip().split("\n")
+    assert len(out) > 300
+    for ln in out:
+        cname, field, val = ln.split()
+        cls = getattr(L, pairs[cname])
+        exp = C.sizeof(cls) if field == "size" else getattr(cls, field).offset
+        assert int(val) == exp, f"{cname}.{field}: header {val}, ctypes {exp}"
+
+
 def test_registry_and_config_surface():
     import semireward_b200 as S
     assert "srflexmatch" in S.ALGORITHMS and "srflexmatch" in S.name2alg.keys()
