@@ -23,6 +23,13 @@ def test_library_exports_every_declared_symbol():
     bound = {n for n, _, _ in L.SYMBOLS}
     assert declared <= bound, f"not bound in _lib.py: {sorted(declared - bound)}"
     assert lib.srw_version() >= 1
+    # same number of parameters in every prototype and in its ctypes argtypes
+    hdr_nc = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    arity = {m.group(1): (0 if m.group(2).strip() in ("", "void") else m.group(2).count(",") + 1)
+             for m in re.finditer(r"\b(srw_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", hdr_nc)}
+    assert len(arity) >= 30
+    for name, _, args in L.SYMBOLS:
+        assert arity[name] == len(args), f"{name}: {arity[name]} parameters in include/srw.h, {len(args)} in _lib.py"
 
 
 def test_struct_sizes_match_header_layout():
