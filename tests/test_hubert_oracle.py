@@ -136,3 +136,21 @@ def test_hubert_oracle_bit_exact_against_live_reference():
         assert abs(alg.log_dict["train/total_loss"] - float(rec["total_loss"])) < 1e-6
         worst = max((p.detach() - orc.p[n].detach()).abs().max().item() for n, p in alg.model.named_parameters())
         assert worst < 1e-4, (it, worst)
+
+
+def test_strided_conv_is_a_gemm_over_an_overlapping_view():
+    """The layout plan for a native conv stem: with the signal stored time-major [T, C_in], row t of the im2col
+    matrix is the k * C_in CONTIGUOUS elements starting at row s * t, so a strided Conv1d is one GEMM over an overlapping
+    strided view (what a TMA tensor map with row stride s * C_in describes) against the weight reordered to [C_out, k, C_in]."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    for cin, cout, k, s, T in ((512, 512, 3, 2, 200), (1, 512, 10, 5, 4000), (512, 512, 2, 2, 99)):
+        x = torch.randn(2, cin, T, generator=g)
+        w = torch.randn(cout, cin, k, generator=g) / (cin * k) ** 0.5
+        ref = F.conv1d(x, w, None, stride=s)                                   # [B, C_out, F]
+        Fr = (T - k) // s + 1
+        xt = x.transpose(1, 2).contiguous()                                    # time-major [B, T, C_in]
+        a = torch.as_strided(xt, (2, Fr, k * cin), (T * cin, s * cin, 1))      # overlapping rows, no copy
+        w2 = w.permute(0, 2, 1).reshape(cout, k * cin)                         # [C_out, (tap, channel)]
+        out = (a @ w2.t()).transpose(1, 2)
+        assert out.shape == ref.shape and (out - ref).abs().max().item() < 1e-4
