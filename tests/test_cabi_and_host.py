@@ -160,3 +160,23 @@ def test_detgen_is_platform_independent():
     if not os.path.isfile(golden):
         open(golden, "w").write("\n".join(lines) + "\n")
     assert open(golden).read().split("\n")[:3] == lines
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the arm the driver runs next to ours) on the host cores: one JSON line with the contract keys.
+    Also the cheapest guard against a syntax / import error in bench.py before it reaches the GPU box."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"], capture_output=True,
+                       text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.strip().split("\n") if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["metric"] == "SSL train-step samples/sec (ViT-S CIFAR-100)" and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
+    # the native arm refuses the configs that have no CUDA path instead of falling back to anything
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", "4"], capture_output=True, text=True, timeout=120, cwd=ROOT)
+    assert r.returncode != 0 and "no CUDA path" in (r.stderr + r.stdout)
