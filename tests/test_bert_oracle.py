@@ -186,3 +186,40 @@ def test_counter_dropout_masks_are_reproducible_and_unbiased():
     c, _ = BO.bert_forward(p, x, bc, BO.BertDropout(bc, 12, True))
     d, _ = BO.bert_forward(p, x, bc)
     assert torch.equal(a, b) and not torch.equal(a, c) and not torch.equal(a, d)
+
+
+def test_two_sweep_chunked_attention_plan_is_exact():
+    """The plan for L = 512: sweep 1 walks the 256-key chunks only for the row max and the row sum (a scalar
+    rescale when the max moves), sweep 2 recomputes the scores, forms P = exp(S - max) as split bf16 and accumulates P V with
+    no rescale of O.  Emulated here with the split-plane products (hi*hi + hi*lo + lo*hi) and an additive key-padding mask,
+    against plain fp32 softmax attention."""
+    def split(x):
+        hi = x.to(torch.bfloat16).float()
+        return hi, (x - hi).to(torch.bfloat16).float()
+
+    def mm3(a, b):
+        ah, al = split(a)
+        bh, bl = split(b)
+        return ah @ bh + (ah @ bl + al @ bh)
+    g = torch.Generator().manual_seed(0)
+    L, dh, chunk = 512, 64, 256
+    q, k, v = (torch.randn(3, L, dh, generator=g) * s for s in (1.5, 1.5, 1.0))
+    lens = torch.tensor([512, 300, 129])
+    keymask = torch.zeros(3, 1, L).masked_fill(torch.arange(L)[None, None, :] >= lens[:, None, None], torch.finfo(torch.float32).min)
+    ref = torch.softmax(q @ k.transpose(1, 2) * dh ** -0.5 + keymask, -1) @ v
+    scale = dh ** -0.5
+    m = torch.full((3, L), -float("inf"))
+    ssum = torch.zeros(3, L)
+    for c in range(0, L, chunk):                                   # sweep 1: statistics only
+        s = mm3(q, k[:, c:c + chunk].transpose(1, 2)) * scale + keymask[:, :, c:c + chunk]
+        m_new = torch.maximum(m, s.max(-1)[0])
+        ssum = ssum * torch.exp(m - m_new) + torch.exp(s - m_new[..., None]).sum(-1)
+        m = m_new
+    o = torch.zeros(3, L, dh)
+    for c in range(0, L, chunk):                                   # sweep 2: P in place, PV accumulate, no rescale
+        s = mm3(q, k[:, c:c + chunk].transpose(1, 2)) * scale + keymask[:, :, c:c + chunk]
+        o = o + mm3(torch.exp(s - m[..., None]), v[:, c:c + chunk])
+    out = o / ssum[..., None]
+    assert (out - ref).abs().max().item() < 2e-5
+    lse = m + torch.log(ssum)
+    assert (lse - torch.logsumexp(q @ k.transpose(1, 2) * scale + keymask, -1)).abs().max().item() < 2e-5
