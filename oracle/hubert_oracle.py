@@ -99,8 +99,11 @@ class HubertCfg:
         return fl + 2.0 * (H * H + H * self.num_classes)
 
 
-def hubert_forward(p: Dict[str, Tensor], x: Tensor, cfg: HubertCfg):
-    """-> (logits [B, C], feat [B, 768]) in deterministic parity mode (no dropout / LayerDrop / SpecAugment).  x: fp32 [B, T]."""
+def hubert_forward(p: Dict[str, Tensor], x: Tensor, cfg: HubertCfg, mask_time_indices: Optional[Tensor] = None, skip_layers=()):
+    """-> (logits [B, C], feat [B, 768]).  x: fp32 [B, T].  Default = deterministic parity mode (no dropout / LayerDrop /
+    SpecAugment).  The two structural sources of randomness of a train-mode pass can be injected explicitly:
+    `mask_time_indices` bool [B, F] (SpecAugment: those frames are replaced by `masked_spec_embed` after the feature
+    projection, modeling_hubert.py `_mask_hidden_states`) and `skip_layers` (LayerDrop: encoder layers left out)."""
     H, nh = cfg.hidden, cfg.heads
     dh = H // nh
     h = x[:, None]
@@ -114,6 +117,8 @@ def hubert_forward(p: Dict[str, Tensor], x: Tensor, cfg: HubertCfg):
     h = F.layer_norm(h, (cfg.conv_dim[-1],), p["model.feature_projection.layer_norm.weight"], p["model.feature_projection.layer_norm.bias"], cfg.eps)
     h = F.linear(h, p["model.feature_projection.projection.weight"], p["model.feature_projection.projection.bias"])
     B, Fr, _ = h.shape
+    if mask_time_indices is not None:
+        h = torch.where(mask_time_indices[..., None], p["model.masked_spec_embed"].to(h.dtype), h)
     # positional convolution, weight-normalised over (out, in) for every tap: w = g * v / ||v||  (weight_norm(dim=2))
     g = p["model.encoder.pos_conv_embed.conv.parametrizations.weight.original0"]
     v = p["model.encoder.pos_conv_embed.conv.parametrizations.weight.original1"]
@@ -124,6 +129,8 @@ def hubert_forward(p: Dict[str, Tensor], x: Tensor, cfg: HubertCfg):
     pos = F.gelu(pos).transpose(1, 2)
     h = F.layer_norm(h + pos, (H,), p["model.encoder.layer_norm.weight"], p["model.encoder.layer_norm.bias"], cfg.eps)
     for i in range(cfg.layers):
+        if i in skip_layers:
+            continue
         pre = f"model.encoder.layers.{i}."
         q = F.linear(h, p[pre + "attention.q_proj.weight"], p[pre + "attention.q_proj.bias"]).view(B, Fr, nh, dh).transpose(1, 2)
         k = F.linear(h, p[pre + "attention.k_proj.weight"], p[pre + "attention.k_proj.bias"]).view(B, Fr, nh, dh).transpose(1, 2)

@@ -106,6 +106,38 @@ def test_hubert_forward_matches_huggingface_eager_and_sdpa():
         assert err <= tol, (impl, err)
 
 
+@pytest.mark.skipif(not LIVE, reason="transformers pin only exists in the build container")
+def test_hubert_specaugment_and_layerdrop_injection_match_huggingface():
+    """The structural randomness of a train-mode pass, injected explicitly on both sides: SpecAugment frames through
+    `mask_time_indices` (HubertModel.forward takes them) and LayerDrop by pinning torch.rand([]) for the layer loop."""
+    from transformers import HubertConfig, HubertModel
+    from oracle import hubert_oracle as HO
+    from semireward_b200 import detgen
+    hc = HO.HubertCfg(layers=3)
+    x = torch.from_numpy(detgen.normal("clip", (2, 4000), 9))
+    conf = HubertConfig(num_hidden_layers=3, hidden_dropout=0.0, activation_dropout=0.0, attention_dropout=0.0, feat_proj_dropout=0.0, final_dropout=0.0,
+                        layerdrop=0.5, apply_spec_augment=True, attn_implementation="eager")   # explicit mask_time_indices: no random spans are drawn
+    torch.manual_seed(0)
+    m = HubertModel(conf).train()
+    p = {"model." + n: v.detach().clone() for n, v in m.named_parameters()}
+    p.update({"classifier.0.weight": torch.zeros(768, 768), "classifier.0.bias": torch.zeros(768), "classifier.2.weight": torch.zeros(10, 768),
+              "classifier.2.bias": torch.zeros(10)})
+    mask = torch.zeros(2, hc.frames(4000), dtype=torch.bool)
+    mask[0, 2:5] = True
+    mask[1, 7] = True
+    draws = iter([0.9, 0.1, 0.7])                      # layer 1 is dropped (0.1 < layerdrop 0.5)
+    orig = torch.rand
+    torch.rand = lambda *a, **k: torch.tensor(next(draws)) if (len(a) == 1 and list(a[0]) == []) else orig(*a, **k)
+    try:
+        ref = m(x, mask_time_indices=mask, return_dict=True)["last_hidden_state"].mean(1)
+    finally:
+        torch.rand = orig
+    _, feat = HO.hubert_forward(p, x, hc, mask_time_indices=mask, skip_layers=(1,))
+    assert torch.equal(feat, ref), (feat - ref).abs().max().item()
+    _, plain = HO.hubert_forward(p, x, hc)
+    assert not torch.equal(plain, ref)
+
+
 @pytest.mark.skipif(not LIVE, reason="live reference only exists in the build container")
 def test_hubert_oracle_bit_exact_against_live_reference():
     import inspect
