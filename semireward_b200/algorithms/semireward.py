@@ -98,6 +98,26 @@ class Rewarder(nn.Module):
         L.check(L.load().srw_rewarder_fwd(C.byref(a), L.stream_ptr()), "srw_rewarder_fwd")
         return reward
 
+    # -- checkpoint of the online-update optimizer (the reference's checkpoints drop the whole SemiReward state) --
+    def optimizer_state(self):
+        """Adam moments and step count of the fused online update on the CPU, None before the first update."""
+        if self._adam is None:
+            return None
+        return dict(m=[t.detach().cpu() for t in self._adam["m"]], v=[t.detach().cpu() for t in self._adam["v"]], step=int(self._adam["step"]))
+
+    def load_optimizer_state(self, state):
+        if state is None:
+            self._adam = None
+            return
+        ps = self._params()
+        dev = ps[0].device
+        gflat = torch.empty(sum(p.numel() for p in ps), dtype=torch.float32, device=dev)
+        gs, off = [], 0
+        for p in ps:
+            gs.append(gflat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        self._adam = dict(m=[t.to(dev).clone() for t in state["m"]], v=[t.to(dev).clone() for t in state["v"]], g=gs, gflat=gflat, step=int(state["step"]))
+
     @torch.no_grad()
     def train_step(self, features, gen_labels, true_labels, lr, num_classes):
         """One online update (srflexmatch.py:173-208): reward = R(features, gen_labels); generator_loss = MSE(reward, 1);

@@ -37,10 +37,14 @@ class SRFixMatch(SRFlexMatch):
         return self._train_step_eager(x_lb, y_lb, None, x_ulb_w, x_ulb_s)
 
     def get_save_dict(self):
-        return super(SRFlexMatch, self).get_save_dict()
+        d = super(SRFlexMatch, self).get_save_dict()
+        d["semireward"] = self._sr_save_dict()
+        return d
 
     def load_model(self, load_path):
-        return super(SRFlexMatch, self).load_model(load_path)
+        ck = super(SRFlexMatch, self).load_model(load_path)
+        self._sr_load(ck)
+        return ck
 
     @staticmethod
     def get_argument():

@@ -413,10 +413,27 @@ class SRFlexMatch(AlgorithmBase):
         self._last_mask, self._last_mask2, self._last_pseudo_label = mask, side["mask2"], pseudo_label
         return out_dict, log_dict
 
+    # The reference's checkpoints keep only the backbone and the masking-hook state: a resumed run restarts the Rewarder and the
+    # Generator from scratch.  Here the SemiReward state travels under one extra key, "semireward";
+    # checkpoints written by the reference (no such key) still load.
+    def _sr_save_dict(self):
+        self._sr_wait()   # the side-stream online update must have landed before the parameters are read
+        return dict(rewarder=self.rewarder.state_dict(), generator=self.generator.state_dict(), rewarder_adam=self.rewarder.optimizer_state())
+
+    def _sr_load(self, ck):
+        sr = ck.get("semireward")
+        if sr is None:
+            return
+        self._sr_wait()
+        self.rewarder.load_state_dict(sr["rewarder"])
+        self.generator.load_state_dict(sr["generator"])
+        self.rewarder.load_optimizer_state(sr.get("rewarder_adam"))
+
     def get_save_dict(self):
         d = super().get_save_dict()
         d["classwise_acc"] = self.hooks_dict["MaskingHook"].classwise_acc.cpu()
         d["selected_label"] = self.hooks_dict["MaskingHook"].selected_label.cpu()
+        d["semireward"] = self._sr_save_dict()
         return d
 
     def load_model(self, load_path):
@@ -425,6 +442,7 @@ class SRFlexMatch(AlgorithmBase):
         h.classwise_acc = ck["classwise_acc"].cuda(self.gpu)
         h.selected_label = ck["selected_label"].cuda(self.gpu)
         h._rebuild_hist()
+        self._sr_load(ck)
         return ck
 
     @staticmethod

@@ -56,12 +56,14 @@ class SRFreeMatch(SRFlexMatch):
         d = super(SRFlexMatch, self).get_save_dict()
         h = self.hooks_dict["MaskingHook"]
         d["p_model"], d["time_p"], d["label_hist"] = h.p_model.cpu(), h.time_p.reshape(()).cpu(), h.label_hist.cpu()   # 0-dim like the reference
+        d["semireward"] = self._sr_save_dict()
         return d
 
     def load_model(self, load_path):
         ck = super(SRFlexMatch, self).load_model(load_path)
         h = self.hooks_dict["MaskingHook"]
         h.p_model, h.time_p, h.label_hist = ck["p_model"].cuda(self.gpu), ck["time_p"].cuda(self.gpu), ck["label_hist"].cuda(self.gpu)
+        self._sr_load(ck)
         return ck
 
     @staticmethod

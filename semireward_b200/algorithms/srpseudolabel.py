@@ -93,10 +93,14 @@ class SRPseudoLabel(SRFlexMatch):
         return out_dict, log_dict
 
     def get_save_dict(self):
-        return super(SRFlexMatch, self).get_save_dict()
+        d = super(SRFlexMatch, self).get_save_dict()
+        d["semireward"] = self._sr_save_dict()
+        return d
 
     def load_model(self, load_path):
-        return super(SRFlexMatch, self).load_model(load_path)
+        ck = super(SRFlexMatch, self).load_model(load_path)
+        self._sr_load(ck)
+        return ck
 
     @staticmethod
     def get_argument():

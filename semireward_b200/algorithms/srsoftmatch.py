@@ -51,6 +51,7 @@ class SRSoftMatch(SRFlexMatch):
         da, h = self.hooks_dict["DistAlignHook"], self.hooks_dict["MaskingHook"]
         d["p_model"], d["p_target"] = da.p_model.cpu(), da.p_target.cpu()
         d["prob_max_mu_t"], d["prob_max_var_t"] = h.prob_max_mu_t.reshape(()).cpu(), h.prob_max_var_t.reshape(()).cpu()   # 0-dim like the reference
+        d["semireward"] = self._sr_save_dict()
         return d
 
     def load_model(self, load_path):
@@ -58,6 +59,7 @@ class SRSoftMatch(SRFlexMatch):
         da, h = self.hooks_dict["DistAlignHook"], self.hooks_dict["MaskingHook"]
         da.p_model, da.p_target = ck["p_model"].cuda(self.gpu), ck["p_target"].cuda(self.gpu)
         h.prob_max_mu_t, h.prob_max_var_t = ck["prob_max_mu_t"].cuda(self.gpu), ck["prob_max_var_t"].cuda(self.gpu)
+        self._sr_load(ck)
         return ck
 
     @staticmethod

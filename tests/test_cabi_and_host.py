@@ -141,6 +141,25 @@ def test_algorithm_construction_and_process_batch_filter():
     sd = alg.get_save_dict()
     assert {"model", "ema_model", "optimizer", "scheduler", "it", "epoch", "best_it", "best_eval_acc", "classwise_acc", "selected_label"} <= set(sd)
     assert sd["selected_label"].shape == (64,) and int(sd["selected_label"][0]) == -1
+    # the SemiReward state travels under one extra key (the reference's checkpoints drop it); a round trip restores it,
+    # and a reference-style checkpoint without the key still loads
+    sr = sd["semireward"]
+    assert set(sr) == {"rewarder", "generator", "rewarder_adam"} and sr["rewarder_adam"] is None and len(sr["rewarder"]) == 17
+    saved = {k: v.clone() for k, v in sr["rewarder"].items()}
+    with torch.no_grad():
+        for p_ in alg.rewarder.parameters():
+            p_.add_(1.0)
+    ps = alg.rewarder._params()
+    adam = dict(m=[torch.full_like(t, 0.5) for t in ps], v=[torch.full_like(t, 0.25) for t in ps], step=7)
+    alg._sr_load(dict(semireward=dict(rewarder=saved, generator=sr["generator"], rewarder_adam=adam)))
+    assert all(torch.equal(v, saved[k]) for k, v in alg.rewarder.state_dict().items())
+    st = alg.rewarder.optimizer_state()
+    assert st["step"] == 7 and float(st["m"][0].flatten()[0]) == 0.5 and float(st["v"][-1].flatten()[0]) == 0.25
+    alg._sr_load({})
+    for name in ("srfreematch", "srsoftmatch", "srfixmatch", "srpseudolabel"):
+        a2 = S.get_algorithm(S.get_config(dict(algorithm=name, optim="AdamW", lr=5e-4, layer_decay=0.5, ulb_dest_len=64, sr_ema=False, num_train_iter=64)),
+                             functools.partial(S.get_net_builder(args.net), depth=1), None, None)
+        assert "semireward" in a2.get_save_dict(), name
 
 
 def test_detgen_is_platform_independent():
