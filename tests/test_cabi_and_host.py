@@ -199,3 +199,30 @@ def test_bench_reference_arm_prints_the_contract_line():
     # the native arm refuses the configs that have no CUDA path instead of falling back to anything
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", "4"], capture_output=True, text=True, timeout=120, cwd=ROOT)
     assert r.returncode != 0 and "no CUDA path" in (r.stderr + r.stdout)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/semilearn"), reason="live reference only exists in the build container")
+def test_integration_recipe_combined_class_constructs_on_the_reference_base():
+    """`class SRFlexMatch(Native, RefBase)` — native step and hooks, the reference's loop / dataset methods."""
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only construction test")
+    from oracle import ref_driver as R
+    R.load_reference()
+    from semilearn.core import AlgorithmBase as RefBase
+    from semilearn.lighting.config import get_config
+    import semireward_b200 as S
+    from semireward_b200.algorithms.srflexmatch import SRFlexMatch as Native
+
+    class Combined(Native, RefBase):
+        pass
+    cfg = dict(R.DEFAULT_CFG)
+    ulb = cfg.pop("ulb_dest_len")
+    cfg.pop("drop_path")
+    args = get_config(cfg)
+    args.ulb_dest_len = ulb
+    alg = Combined(args, S.get_net_builder("vit_small_patch2_32"), None, None)
+    assert type(alg.model).__module__ == "semireward_b200.nets.vit"
+    assert Combined.train_step is Native.train_step and Combined.set_hooks is Native.set_hooks
+    for name in ("train", "set_dataset", "set_data_loader", "evaluate"):
+        assert getattr(Combined, name) is getattr(RefBase, name), name
+    assert list(alg.hooks_dict)[:2] == ["ParamUpdateHook", "EMAHook"]
