@@ -205,6 +205,7 @@ typedef struct {
   float* logits; float* feat;                 /* [batch, num_classes], [batch, embed_dim] */
   void* workspace; int64_t workspace_bytes;
   int gemm_impl;
+  float* tokens_out;                          /* optional [batch, N, embed_dim]: the final LayerNorm of ALL tokens = VisionTransformer.extract (vit.py:277-283) */
 } srw_vit_fwd_args;
 int srw_vit_forward(const srw_vit_fwd_args* a, void* stream);
 

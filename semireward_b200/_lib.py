@@ -82,7 +82,7 @@ class VitConfig(C.Structure):
 class VitFwdArgs(C.Structure):
     _fields_ = [("cfg", C.POINTER(VitConfig)), ("params", C.POINTER(vp)), ("weight_planes", vp), ("x", vp), ("batch", i32),
                 ("grad_batch", i32), ("drop_scale", vp), ("logits", vp), ("feat", vp), ("workspace", vp),
-                ("workspace_bytes", i64), ("gemm_impl", i32)]
+                ("workspace_bytes", i64), ("gemm_impl", i32), ("tokens_out", vp)]
 
 
 class VitBwdArgs(C.Structure):

@@ -1,5 +1,5 @@
 """SemiReward modules behind the reference's class names (semilearn/algorithms/semireward/semireward.py):
-Rewarder (:27-72), Generator (:6-24), cosine_similarity_n (:130-139), label_dim (:147-148).
+Rewarder (:27-72), EMARewarder (:75-127), Generator (:6-24), cosine_similarity_n (:130-139), label_dim (:147-148).
 
 The nn.Modules are parameter holders with the reference's state_dict keys and default initialisation; forward() and the
 online training step run as single fused kernels (srw_rewarder_fwd / srw_generator_fwd / srw_rewarder_train)."""
@@ -158,3 +158,48 @@ class Rewarder(nn.Module):
             a.phase = 2
             L.check(L.load().srw_rewarder_train(C.byref(a), L.stream_ptr()), "srw_rewarder_train")
         return losses
+
+
+class EMARewarder(Rewarder):
+    """semireward.py:75-127 (`sr_ema: True`, the argparse default; every shipped YAML sets it to False): the same forward as
+    Rewarder on the LIVE parameters, followed by `ema = decay * ema + (1 - decay) * param` over all 17 tensors.  The averaged
+    copies (`ema_params`, keyed by parameter name like the reference's dict) are never read by any algorithm there either;
+    they are kept so that code written against the reference finds them.  One srw_ema_step launch per forward."""
+
+    def __init__(self, label_dim, label_embedding_dim, feature_dim=384, ema_decay=0.9):
+        super().__init__(label_dim, label_embedding_dim, feature_dim)
+        self.ema_decay = float(ema_decay)
+        self.ema_params = {}
+        self.initialize_ema()
+        self._ema_table = self._ema_key = None
+
+    def initialize_ema(self):
+        for name, param in self.named_parameters():
+            if param.requires_grad:
+                self.ema_params[name] = nn.Parameter(param.data.clone())
+
+    @torch.no_grad()
+    def update_ema(self):
+        named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
+        key = tuple(p.data_ptr() for _, p in named)
+        if self._ema_key != key:
+            rows = (L.EmaRow * len(named))()
+            blk = 0
+            for i, (n, p) in enumerate(named):
+                e = self.ema_params[n]
+                if e.device != p.device:   # semireward.py:100-101: first use after .cuda() restarts the average from the parameter
+                    e.data = p.data.clone()
+                rows[i].param, rows[i].shadow, rows[i].numel, rows[i].first_block = p.data_ptr(), e.data_ptr(), p.numel(), blk
+                blk += (p.numel() + L.ADAMW_BLOCK_ELEMS - 1) // L.ADAMW_BLOCK_ELEMS
+            host = torch.empty(C.sizeof(rows), dtype=torch.uint8)
+            C.memmove(host.data_ptr(), C.addressof(rows), C.sizeof(rows))
+            self._ema_table, self._ema_key, self._ema_n, self._ema_blocks = host.to(named[0][1].device), key, len(named), blk
+            return
+        a = L.EmaArgs(num_tensors=self._ema_n, total_blocks=self._ema_blocks, table=self._ema_table.data_ptr(), decay=self.ema_decay)
+        L.check(L.load().srw_ema_step(C.byref(a), L.stream_ptr()), "srw_ema_step")
+
+    @torch.no_grad()
+    def forward(self, features, label_indices):
+        reward = super().forward(features, label_indices)
+        self.update_ema()
+        return reward

@@ -23,7 +23,7 @@ from .. import _lib as L
 from ..core.algorithmbase import AlgorithmBase
 from ..core.hooks import FlexMatchThresholdingHook, PseudoLabelingHook
 from ..core.registry import ALGORITHMS
-from .semireward import Generator, Rewarder, label_dim
+from .semireward import EMARewarder, Generator, Rewarder, label_dim
 from .utils import SSL_Argument, str2bool
 
 
@@ -103,9 +103,10 @@ class SRFlexMatch(AlgorithmBase):
         super().__init__(args, net_builder, tb_log, logger)
         self._init_algorithm(args)
         self.N_k = args.N_k
-        if args.sr_ema != 0:
-            raise NotImplementedError("sr_ema: every shipped SemiReward config sets sr_ema: False (EMARewarder is unused, SURVEY.md §8a a6)")
-        self.rewarder = Rewarder(label_dim(self.num_classes), 128, args.feature_dim)
+        if args.sr_ema != 0:   # srflexmatch.py:49-50
+            self.rewarder = EMARewarder(label_dim(self.num_classes), 128, feature_dim=args.feature_dim, ema_decay=args.sr_ema_m)
+        else:
+            self.rewarder = Rewarder(label_dim(self.num_classes), 128, args.feature_dim)
         self.generator = Generator(args.feature_dim)
         if torch.cuda.is_available():   # reference: send_model_cuda(args, Rewarder(...)) in the ctor (srflexmatch.py:49-51)
             self.rewarder, self.generator = self.rewarder.cuda(self.gpu), self.generator.cuda(self.gpu)
@@ -218,7 +219,18 @@ class SRFlexMatch(AlgorithmBase):
             self._sr_done = None
 
     def _net(self):
-        return self.model.module if hasattr(self.model, "module") else self.model
+        m = self.model
+        if hasattr(m, "module"):
+            inner = m.module
+            # the reference's train.py wraps alg.model with torch DDP (send_model_cuda, misc.py:56-64).  The native step never
+            # calls the wrapper's forward, so DDP's reducer hooks never fire: take its process group and average the flat
+            # gradient buffer ourselves (same all-reduce(avg), one message)
+            if getattr(inner, "_dp_group", None) is None and hasattr(m, "process_group"):
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size(m.process_group) > 1:
+                    inner._dp_group = m.process_group
+            return inner
+        return m
 
     def _host_scalars(self, n):
         """Two alternating pinned staging buffers for the per-step D2H read of the loss vector."""

@@ -40,6 +40,8 @@ class AlgorithmBase:
         self.print_fn = print if logger is None else logger.info
         self.ngpus_per_node = torch.cuda.device_count()
         self.amp_cm = contextlib.nullcontext
+        self.loss_scaler = torch.amp.GradScaler("cuda")   # algorithmbase.py:94; unused while amp is off, but its state is a checkpoint key
+        self.task_type = "cls"
         self.gpu = args.gpu
         self.rank = getattr(args, "rank", 0)
         self.distributed = getattr(args, "distributed", False)
@@ -84,7 +86,7 @@ class AlgorithmBase:
     _PRIORITY = dict(HIGHEST=0, VERY_HIGH=10, HIGH=30, ABOVE_NORMAL=40, NORMAL=50, BELOW_NORMAL=60, LOW=70, VERY_LOW=90, LOWEST=100)
 
     def register_hook(self, hook, name=None, priority="NORMAL"):
-        assert isinstance(hook, Hook)
+        assert isinstance(hook, Hook) or all(hasattr(hook, st) for st in Hook.stages), "a hook implements the six stage methods"
         if hasattr(hook, "priority"):
             raise ValueError('"priority" is a reserved attribute for hooks')
         hook.priority = self._PRIORITY[priority] if isinstance(priority, str) else int(priority)
@@ -153,18 +155,47 @@ class AlgorithmBase:
         self.it += 1
         return self.out_dict, self.log_dict
 
-    # -- checkpoint (keys of algorithmbase.py:459-496) ----------------------------------------------
+    # -- checkpoint (keys of algorithmbase.py:459-525) ----------------------------------------------
     def get_save_dict(self):
-        return dict(model=self.model.state_dict(), ema_model=self.ema_model.state_dict(), optimizer=self.optimizer.state_dict(),
-                    scheduler=self.scheduler.state_dict() if self.scheduler is not None else None, it=self.it + 1, epoch=self.epoch + 1,
-                    best_it=self.best_it, best_eval_acc=self.best_eval_metric)
+        """Same keys as the reference writes (algorithmbase.py:459-485), so either side loads the other's file.  `loss_scaler`
+        is the state of a disabled-in-effect GradScaler: every SemiReward config runs `amp: False`, the reference still writes
+        and reads the key unconditionally (:472, :505)."""
+        d = dict(model=self.model.state_dict(), ema_model=self.ema_model.state_dict(), optimizer=self.optimizer.state_dict(),
+                 loss_scaler=self._loss_scaler_state(), it=self.it + 1, epoch=self.epoch + 1, best_it=self.best_it,
+                 best_eval_acc=self.best_eval_metric)
+        if self.scheduler is not None:
+            d["scheduler"] = self.scheduler.state_dict()
+        return d
+
+    def _loss_scaler_state(self):
+        """State of the GradScaler as the reference would write it.  Without CUDA (CPU tests) torch disables the scaler and
+        its state is {}, which an enabled scaler refuses to load (the reference's load_model, :505): write the initial state."""
+        sd = self.loss_scaler.state_dict()
+        return sd if sd else {"scale": 65536.0, "growth_factor": 2.0, "backoff_factor": 0.5, "growth_interval": 2000, "_growth_tracker": 0}
+
+    def save_model(self, save_name, save_path):
+        import os
+        os.makedirs(save_path, exist_ok=True)
+        fn = os.path.join(save_path, save_name)
+        torch.save(self.get_save_dict(), fn)
+        self.print_fn(f"model saved: {fn}")
 
     def load_model(self, load_path):
+        """algorithmbase.py:498-525: model, EMA model, loss scaler, counters, optimizer (AdamW moments + step) and scheduler
+        are all restored, so a resumed run continues the learning-rate schedule and the moments instead of restarting them."""
         ck = torch.load(load_path, map_location="cpu")
         self.model.load_state_dict(ck["model"])
         self.ema_model.load_state_dict(ck["ema_model"])
+        if ck.get("loss_scaler") and self.loss_scaler.is_enabled():   # files written before the key existed here simply lack it
+            self.loss_scaler.load_state_dict(ck["loss_scaler"])
         self.it, self.start_epoch, self.epoch = ck["it"], ck["epoch"], ck["epoch"]
         self.best_it, self.best_eval_metric = ck["best_it"], ck["best_eval_acc"]
+        self.optimizer.load_state_dict(ck["optimizer"])
+        if self.scheduler is not None and ck.get("scheduler") is not None:
+            self.scheduler.load_state_dict(ck["scheduler"])
+        if hasattr(self.model, "mark_weights_updated"):
+            self.model.mark_weights_updated()
+        self.print_fn("Model loaded")
         return ck
 
     @staticmethod

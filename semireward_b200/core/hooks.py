@@ -25,6 +25,12 @@ class Hook:
     def before_run(self, algorithm): pass
     def after_run(self, algorithm): pass
 
+    # schedule helpers of the reference's Hook base (core/hooks/hook.py:28-42)
+    def every_n_epochs(self, algorithm, n): return (algorithm.epoch + 1) % n == 0 if n > 0 else False
+    def every_n_iters(self, algorithm, n): return (algorithm.it + 1) % n == 0 if n > 0 else False
+    def is_last_epoch(self, algorithm): return algorithm.epoch + 1 == algorithm.epochs
+    def is_last_iter(self, algorithm): return algorithm.it + 1 == algorithm.num_train_iter
+
 
 class ParamUpdateHook(Hook):
     """backward + (clip) + optimizer.step + scheduler.step + zero_grad; CUDA-event run_time like the reference."""
@@ -65,14 +71,16 @@ class EMA:
         m = self.model.module if hasattr(self.model, "module") else self.model
         return list(m.named_parameters())
 
-    def register(self):
+    def register(self, keep_ema_values=False):
+        """keep_ema_values: the EMA model already holds the shadow (a resumed run: ema.py:17-18 `ema.load(ema_model)`)."""
         named = self._named()
         if self.ema_model is not None:
             em = dict(self.ema_model.named_parameters())
             for n, p in named:
                 if em[n].device != p.device:
                     em[n].data = em[n].data.to(p.device)
-                em[n].data.copy_(p.data)
+                if not keep_ema_values:
+                    em[n].data.copy_(p.data)
                 self.shadow[n] = em[n].data
         else:
             for n, p in named:
@@ -123,7 +131,7 @@ class EMAHook(Hook):
 
     def before_run(self, algorithm):
         algorithm.ema = EMA(algorithm.model, algorithm.ema_m, ema_model=algorithm.ema_model)
-        algorithm.ema.register()
+        algorithm.ema.register(keep_ema_values=bool(getattr(algorithm, "resume", False)) and getattr(algorithm, "it", 0) > 0)
 
     def after_train_step(self, algorithm):
         if getattr(algorithm, "ema", None) is None:

@@ -76,7 +76,18 @@ class FusedAdamW(torch.optim.Optimizer):
         self._flip = 0
         self._step = 0
 
+    def load_state_dict(self, state_dict):
+        """torch's loader replaces the per-parameter state tensors; the flat moment buffers and the row table are rebuilt
+        from them on the next step() (`_build` copies a restored exp_avg / exp_avg_sq into the flat buffers)."""
+        super().load_state_dict(state_dict)
+        self._rows = None
+        self._step = 0
+
     def _build(self):
+        g0 = self.param_groups[0]
+        for g in self.param_groups:   # one launch = one (betas, eps) pair; the reference's groups only differ in lr / weight decay
+            if tuple(g["betas"]) != tuple(g0["betas"]) or g["eps"] != g0["eps"]:
+                raise ValueError("FusedAdamW: all param groups must share betas and eps")
         ps = [p for g in self.param_groups for p in g["params"]]
         dev = ps[0].device
         total = sum(p.numel() for p in ps)

@@ -1,7 +1,7 @@
 """Algorithm registry with the reference's surface (semilearn/core/utils/registry.py:25-36):
 `@ALGORITHMS.register('name')`, `ALGORITHMS['name']`, `'name' in ALGORITHMS`, `.keys()`.
-When the real `semilearn` package is importable, classes registered here are mirrored into ITS registry too
-(INTEGRATION.md), so `semilearn.get_algorithm(args, ...)` with an unchanged YAML picks up the B200 implementation."""
+This registry is the package's own.  `semireward_b200.integration.register_into_reference()` is the
+explicit call that puts these classes, combined with the reference's AlgorithmBase loop, into `semilearn`'s registry."""
 from __future__ import annotations
 
 

@@ -572,6 +572,14 @@ static int vit_forward_body(const srw_vit_fwd_args* a, cudaStream_t s) {
   g_launches++;
   SRW_LAUNCH_CHECK();
   SRW_CUDA(cudaMemcpyAsync(F32(L.feat), a->feat, (size_t)d.B * D * 4, cudaMemcpyDeviceToDevice, s));
+  if (a->tokens_out) {   // extract(): the final norm over every token, not just the CLS rows
+    srw_layernorm_fwd_args ln = {};
+    ln.x = F32(L.t[d.L]); ln.ldx = D; ln.rows = T; ln.cols = D; ln.eps = eps; ln.gamma = P[ptail(d.L, 0)]; ln.beta = P[ptail(d.L, 1)];
+    ln.mean = F32(L.blk[0].mean1); ln.rstd = F32(L.blk[0].rstd1);   // scratch: extract() is an inference call, nothing is kept for a backward
+    ln.y_f32 = a->tokens_out; ln.ldy = D;
+    SRW_REQUIRE(a->grad_batch == 0, "srw_vit_forward: tokens_out is an inference output (grad_batch must be 0)");
+    SRW_TRY(srw_layernorm_fwd(&ln, s));
+  }
   return SRW_OK;
 }
 
@@ -845,7 +853,7 @@ extern "C" int srw_vit_forward(const srw_vit_fwd_args* a, void* stream_) {
   kb.add((int)1); kb.add(*a->cfg); kb.add(s);
   for (int i = 0; i < vit_num_params(a->cfg); ++i) kb.add(a->params[i]);
   kb.add(a->weight_planes); kb.add(a->x); kb.add(a->batch); kb.add(a->grad_batch); kb.add(a->drop_scale); kb.add(a->logits); kb.add(a->feat);
-  kb.add(a->workspace); kb.add(a->workspace_bytes); kb.add(a->gemm_impl);
+  kb.add(a->workspace); kb.add(a->workspace_bytes); kb.add(a->gemm_impl); kb.add(a->tokens_out);
   return run_graphed(std::move(kb.k), s, [a](cudaStream_t st) { return vit_forward_body(a, st); });
 }
 

@@ -357,8 +357,27 @@ class VisionTransformer(nn.Module):
         return _VitFunction.apply(self, x, drop_scale, gb, *params)
 
     # -- reference interface --------------------------------------------------------------------
+    @torch.no_grad()
     def extract(self, x):
-        raise NotImplementedError("extract() (all token features) is not produced by the fused engine; use forward(only_feat=True)")
+        """vit.py:277-283: every token after the final LayerNorm, [B, N, D].  Inference output of the fused engine (the engine's
+        backward starts from logits / feat, so no gradient flows through this tensor)."""
+        if not x.is_cuda:
+            raise RuntimeError("semireward_b200 ViT runs on CUDA (sm_100a) only; there is no CPU path")
+        lib, cfg, dev, B = L.load(), self._cfg, x.device, x.shape[0]
+        x = x.contiguous().float()
+        params, pa = self._native_params()
+        wbytes = lib.srw_vit_workspace_bytes(C.byref(cfg), B, 0)
+        ws = self._acquire_ws(wbytes, dev)
+        ntok = self.patch_embed.num_patches + 1
+        tokens = torch.empty(B, ntok, cfg.embed_dim, dtype=torch.float32, device=dev)
+        lo, fe = torch.empty(B, cfg.num_classes, device=dev), torch.empty(B, cfg.embed_dim, device=dev)
+        ds = self._draw_drop_scale(B, dev)
+        a = L.VitFwdArgs(cfg=C.pointer(cfg), params=pa, weight_planes=self._weight_planes().data_ptr(), x=x.data_ptr(), batch=B,
+                         grad_batch=0, drop_scale=L.ptr(ds), logits=lo.data_ptr(), feat=fe.data_ptr(), workspace=ws.data_ptr(),
+                         workspace_bytes=wbytes, gemm_impl=self.gemm_impl, tokens_out=tokens.data_ptr())
+        L.check(lib.srw_vit_forward(C.byref(a), L.stream_ptr()), "srw_vit_forward")
+        self._release_ws(ws)
+        return tokens
 
     def forward(self, x, only_fc=False, only_feat=False, grad_batch=None, drop_scale=None, **kwargs):
         """grad_batch (extension): only the first `grad_batch` rows are back-propagated (rows after it must only feed
@@ -384,10 +403,9 @@ def _build(defaults, pretrained, pretrained_path, kwargs):
     kw = dict(defaults)
     kw.update(kwargs)
     model = VisionTransformer(**kw)
-    if pretrained:
-        sd = torch.load(pretrained_path, map_location="cpu")
-        sd = sd.get("model", sd.get("state_dict", sd))
-        model.load_state_dict({k: v for k, v in sd.items() if not k.startswith("head.")}, strict=False)
+    if pretrained:   # vit.py:352-354 and twins
+        from .utils import load_checkpoint
+        model = load_checkpoint(model, pretrained_path)
     return model
 
 

@@ -226,3 +226,85 @@ def test_integration_recipe_combined_class_constructs_on_the_reference_base():
     for name in ("train", "set_dataset", "set_data_loader", "evaluate"):
         assert getattr(Combined, name) is getattr(RefBase, name), name
     assert list(alg.hooks_dict)[:2] == ["ParamUpdateHook", "EMAHook"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/semilearn"), reason="live reference only exists in the build container")
+def test_combined_class_steps_through_the_reference_train_loop(tmp_path, monkeypatch):
+    """INTEGRATION.md §1 end to end on the host side: `reference_algorithm(Native)` runs under the reference's own
+    `AlgorithmBase.train()` (algorithmbase.py:346-375) with its Evaluation / Checkpoint / Timer / Logging hooks for two
+    iterations, `evaluate()` works, the checkpoint it writes is loaded by the native class AND by the unmodified reference
+    class.  No GPU here, so only the device work is stubbed (train_step's arithmetic, optimizer / EMA launches, the model
+    forward inside evaluate, CUDA events); every call of the loop protocol is the real one."""
+    if torch.cuda.is_available():
+        pytest.skip("host-protocol test for the CPU container")
+    from oracle import ref_driver as R
+    R.load_reference()
+    from semilearn.core import AlgorithmBase as RefBase
+    from semilearn.lighting.config import get_config
+    import semireward_b200 as S
+    from semireward_b200.core import hooks as H
+    from semireward_b200.integration import reference_algorithm, register_into_reference
+    from semireward_b200.algorithms.srflexmatch import SRFlexMatch as Native
+
+    class FakeEvent:
+        def __init__(self, enable_timing=False): pass
+        def record(self): pass
+        def elapsed_time(self, other): return 0.0
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(H.EMA, "update", lambda self: None)
+    Combined = reference_algorithm(Native)
+    assert Combined.train is RefBase.train and Combined.evaluate is RefBase.evaluate and Combined.train_step is Native.train_step
+    cfg = dict(R.DEFAULT_CFG, num_train_iter=2, epoch=1, num_eval_iter=2, num_log_iter=1, save_dir=str(tmp_path), save_name="run",
+               resume=False, num_warmup_iter=0, start_timing=100)
+    ulb = cfg.pop("ulb_dest_len")
+    cfg.pop("drop_path")
+    args = get_config(cfg)
+    args.ulb_dest_len = ulb
+    import functools
+    builder = functools.partial(S.get_net_builder("vit_small_patch2_32"), depth=1)
+    alg = Combined(args, builder, None, None)
+    names = list(alg.hooks_dict)
+    for h in ("ParamUpdateHook", "EMAHook", "EvaluationHook", "CheckpointHook", "DistSamplerSeedHook", "TimerHook", "LoggingHook",
+              "PseudoLabelingHook", "MaskingHook"):
+        assert h in names, (h, names)
+    assert names.index("ParamUpdateHook") < names.index("EMAHook") < names.index("EvaluationHook") < names.index("CheckpointHook") < names.index("LoggingHook")
+    calls = []
+
+    def train_step(x_lb, y_lb, idx_ulb, x_ulb_w, x_ulb_s):   # same parameter names: process_batch filters the batch by them
+        calls.append(x_lb.shape[0])
+        loss = sum((p * 0).sum() for p in alg.model.parameters()) + 1.0
+        return dict(loss=loss, feat={}), {"train/sup_loss": 1.0, "train/unsup_loss": 0.0, "train/total_loss": 1.0, "train/util_ratio": 1.0}
+    alg.train_step = train_step
+    alg.optimizer.step = lambda *a, **k: None
+    alg.model.forward = lambda x, **k: {"logits": torch.zeros(x.shape[0], 100), "feat": torch.zeros(x.shape[0], 384)}
+    g = torch.Generator().manual_seed(0)
+    lb = [dict(idx_lb=torch.arange(8), x_lb=torch.randn(8, 3, 32, 32, generator=g), y_lb=torch.randint(0, 100, (8,), generator=g)) for _ in range(2)]
+    ulb_l = [dict(idx_ulb=torch.arange(8), x_ulb_w=torch.randn(8, 3, 32, 32, generator=g), x_ulb_s=torch.randn(8, 3, 32, 32, generator=g)) for _ in range(2)]
+    alg.loader_dict = {"train_lb": lb, "train_ulb": ulb_l, "eval": [dict(x_lb=lb[0]["x_lb"], y_lb=lb[0]["y_lb"])]}
+    alg.train()                                          # the reference's loop
+    assert calls == [8, 8] and alg.it == 2
+    assert "eval/top-1-acc" in alg.log_dict and "train/prefetch_time" in alg.log_dict and "lr" in alg.log_dict
+    assert alg.results_dict["eval/best_it"] == alg.best_it
+    ck_path = os.path.join(str(tmp_path), "run", "latest_model.pth")
+    ck = torch.load(ck_path, map_location="cpu")
+    for k in ("model", "ema_model", "optimizer", "loss_scaler", "scheduler", "it", "epoch", "best_it", "best_eval_acc", "classwise_acc",
+              "selected_label", "semireward"):
+        assert k in ck, k
+    assert ck["loss_scaler"]          # non-empty: the reference's enabled GradScaler refuses an empty state (algorithmbase.py:505)
+    # native resume: counters, scheduler position and (here empty) optimizer state come back
+    alg2 = Combined(args, builder, None, None)
+    alg2.load_model(ck_path)
+    assert alg2.it == ck["it"] and alg2.scheduler.last_epoch == alg.scheduler.last_epoch == 2
+    # the unmodified reference loads the native checkpoint (same keys; 28 AdamW groups; FlexMatch hook state)
+    ref = R.build_reference_algorithm(dict(num_train_iter=2, epoch=1, num_warmup_iter=0), net_kwargs=dict(depth=1))
+    ref.load_model(ck_path)
+    assert ref.it == ck["it"] and ref.scheduler.last_epoch == 2
+    for (n1, p1), (n2, p2) in zip(ref.model.state_dict().items(), alg.model.state_dict().items()):
+        assert n1 == n2 and torch.equal(p1, p2)
+    # and the registry route of INTEGRATION.md: the reference's get_algorithm now builds the combined native class
+    import semilearn
+    reg = register_into_reference()
+    a3 = semilearn.get_algorithm(args, semilearn.get_net_builder("vit_small_patch2_32", False), None, None)
+    assert isinstance(a3, Native) and isinstance(a3, RefBase) and type(a3) is reg["srflexmatch"]
+    assert type(a3.model).__module__ == "semireward_b200.nets.vit"

@@ -1,0 +1,223 @@
+"""-m gpu: the parity cases round 1 left open (VERDICT r01 "What's weak").
+
+  * the BENCHMARKED mode: DropPath on, the same multipliers injected into the oracle and the native step, stage 1, the gap step
+    and the stochastic stage 2 (batched route AND sequential passes) — compared with the ORACLE, not with another native route;
+  * BASELINE configs[2] at its real per-GPU shape (128 + 128 + 128 images of 224 x 224, 1000 classes, SRFreeMatch): the Rewarder's
+    batch softmax over 256 rows, the 0.8-quantile over 128 max-probabilities, 75 648 tokens per GEMM;
+  * mask2 ties are counted and printed, and every mask2 bit that is NOT within the tie band must match;
+  * checkpoint round trip: save -> load -> step continues the AdamW moments and the schedule;
+  * extract() and EMARewarder."""
+import functools
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import SharedDropPath, batch_tensors, build_native, build_oracle, small_cfg
+from test_train_step_gpu import _grad_tap, _resync
+
+pytestmark = pytest.mark.gpu
+
+
+def mask2_report(rec, native_mask2, tag):
+    """mask2 = reward >= reward.mean() (srflexmatch.py:100-101).  Samples whose reward sits within 4e-7 relative of the mean are
+    rounding coin-flips (identical rewards for identical pseudo-labels; the mean's summation order decides) — they are COUNTED
+    and printed; every other bit must match the oracle exactly.  Returns the number of tied samples."""
+    if "dg_reward" not in rec:
+        return 0
+    r = rec["dg_reward"].flatten().double()
+    tied = (r - r.mean()).abs() <= 4e-7 * r.mean().abs()
+    ref, nat = rec["dg_mask2"].flatten(), native_mask2.detach().cpu().flatten()
+    assert torch.equal(ref[~tied], nat[~tied]), f"{tag}: mask2 differs outside the tie band: {ref.tolist()} vs {nat.tolist()}"
+    n = int(tied.sum())
+    if n:
+        print(f"{tag}: {n} of {r.numel()} rewards tie with their mean (|r - mean| <= 4e-7 |mean|); "
+              f"{int((ref[tied] != nat[tied]).sum())} of those bits differ")
+    return n
+
+
+@pytest.mark.parametrize("algorithm,depth,batched", [("srflexmatch", 12, True), ("srflexmatch", 2, False), ("srfreematch", 2, True)])
+def test_droppath_on_steps_vs_oracle(algorithm, depth, batched):
+    """drop_path_rate 0.2 (the shipped builders' value, the mode bench.py times).  it 0-1 stage 1 (SR trained on labelled data),
+    it 2 the gap step, it 3-5 stage 2 with K = 8 fresh draws per step and two graphs carrying gradient."""
+    from oracle import ssl_oracle as O
+    cfg = small_cfg(algorithm=algorithm, num_train_iter=16, start_timing=2, N_k=2, ent_loss_ratio=0.05, ema_p=0.9)
+    orc = build_oracle(cfg, depth, drop_path_rate=0.2)
+    alg = build_native(cfg, depth, drop_path_rate=0.2)
+    alg.batch_stochastic_passes = batched
+    nl = nu = cfg["batch_size"]
+    sdp = SharedDropPath(orc.vit_cfg, nl, nu)
+    sdp.install(orc, alg)
+    tap = _grad_tap(alg)
+    ties = 0
+    try:
+        for it in range(6):
+            sdp.new_step()
+            batch = batch_tensors(cfg, it)
+            rec = orc.train_step(dict(batch), it)
+            ref_grads = orc.param_update()
+            assert len(sdp.step_draws) == (1 if it <= cfg["start_timing"] else 1 + rec["K"])
+            alg.it = it
+            alg.out_dict, alg.log_dict = alg.train_step(**alg.process_batch(**batch))
+            alg.call_hook("after_train_step")
+            torch.cuda.synchronize()
+            ld = alg.log_dict
+            assert torch.equal(alg._last_pseudo_label.cpu(), rec["pseudo"]), f"it {it}: pseudo labels differ"
+            if algorithm == "srflexmatch":
+                assert torch.equal(alg._last_mask.cpu(), rec["mask"]), f"it {it}: mask differs"
+                hook = alg.hooks_dict["MaskingHook"]
+                assert torch.equal(hook.selected_label.cpu(), orc.hook.selected_label) and torch.equal(hook.classwise_acc.cpu(), orc.hook.classwise_acc)
+            else:
+                assert torch.equal(alg._last_mask.cpu(), rec["mask"]), f"it {it}: mask differs"
+            assert abs(ld["train/sup_loss"] - float(rec["sup_loss"])) < 1e-3
+            assert abs(ld["train/util_ratio"] - float(rec["util_ratio"])) < 1e-6
+            tied = mask2_report(rec, alg._last_mask2, f"{algorithm} d{depth} it {it}")
+            ties += tied
+            if not tied:
+                for kn, ko in (("train/unsup_loss", "unsup_loss"), ("train/total_loss", "total_loss")):
+                    assert abs(ld[kn] - float(rec[ko])) < 1e-3, f"it {it} {ko}: {ld[kn]} vs {float(rec[ko])}"
+                worst = 0.0
+                for n, p in alg.model.named_parameters():
+                    gr = ref_grads[n]
+                    worst = max(worst, (tap[n].cpu() - gr).abs().max().item() / max(gr.abs().max().item(), 1e-20))
+                print(f"{algorithm} depth {depth} it {it} (DropPath on, K={rec.get('K', 0)}): total {ld['train/total_loss']:.5f} "
+                      f"(oracle {float(rec['total_loss']):.5f}) grad rel err {worst:.2e}")
+                assert worst < 1e-3, f"it {it}: gradient error {worst}"
+            _resync(alg, orc)
+    finally:
+        sdp.uninstall()
+    print(f"{algorithm} depth {depth}: {ties} tied mask2 samples over 6 steps")
+
+
+def test_config3_real_per_gpu_shape_step():
+    """BASELINE configs[2] per-GPU shape: vit_base_patch16_224, 1000 classes, batch 128 + 128 + 128 (global 1024 over 8 ranks),
+    SRFreeMatch with use_quantile — 2 blocks, three steps (stage 1, the gap step, stage 2 with an SR update)."""
+    import semireward_b200 as S
+    from oracle import ssl_oracle as O
+    from semireward_b200 import detgen
+    torch.set_num_threads(os.cpu_count() or 8)
+    B = 128
+    cfg = small_cfg(algorithm="srfreematch", net="vit_base_patch16_224", num_classes=1000, batch_size=B, feature_dim=768, img_size=224,
+                    use_quantile=True, clip_thresh=False, ent_loss_ratio=0.05, ema_p=0.9, start_timing=1, N_k=2, num_train_iter=16, ulb_dest_len=4096)
+    depth = 2
+    vc = O.ViTConfig(img_size=224, patch_size=16, embed_dim=768, depth=depth, num_heads=12, num_classes=1000)
+    sc = O.StepConfig(algorithm="srfreematch", num_classes=1000, ulb_dest_len=cfg["ulb_dest_len"], start_timing=1, N_k=2,
+                      num_train_iter=16, num_warmup_iter=0, lr=cfg["lr"], weight_decay=cfg["weight_decay"], layer_decay=cfg["layer_decay"],
+                      sr_lr=cfg["sr_lr"], feature_dim=768, ema_p=0.9, use_quantile=True, clip_thresh=False, lambda_e=0.05)
+    orc = O.build_det_oracle(vc, sc, seed=0, head_gain=4.0)
+    orc.reuse_deterministic_passes = True   # DropPath off: stage 2's K passes are identical; 384 images of 224 x 224 once, not 9 times
+    args = S.get_config(cfg)
+    alg = S.get_algorithm(args, functools.partial(S.get_net_builder(args.net, False), depth=depth, drop_path_rate=0.0), None, None)
+    with torch.no_grad():
+        for prefix, mod in (("", alg.model), ("rewarder.", alg.rewarder), ("generator.", alg.generator)):
+            for n, p in mod.named_parameters():
+                p.copy_(torch.from_numpy(detgen.fill_param(prefix + n, p.shape, 0)))
+                if prefix == "" and n == "head.weight":
+                    p.mul_(4.0)
+    alg.model = alg.model.cuda(args.gpu).train()
+    alg.rewarder, alg.generator = alg.rewarder.cuda(args.gpu), alg.generator.cuda(args.gpu)
+    tap = _grad_tap(alg)
+    hook = alg.hooks_dict["MaskingHook"]
+    for it in (0, 1, 2):
+        b = detgen.ssl_batch(B, 1, 1000, cfg["ulb_dest_len"], img_size=224, seed=1, step=it)
+        batch = {k: torch.from_numpy(v) for k, v in b.items()}
+        rec = orc.train_step(dict(batch), it)
+        ref_grads = orc.param_update()
+        alg.it = it
+        alg.out_dict, alg.log_dict = alg.train_step(**alg.process_batch(**batch))
+        alg.call_hook("after_train_step")
+        torch.cuda.synchronize()
+        ld = alg.log_dict
+        # with 128 rows and 1000 classes a top-2 logit gap below the 1e-3 gate is possible: report such rows, compare the rest exactly
+        lw = rec["logits_w"]
+        top2 = lw.topk(2, dim=-1).values
+        close = (top2[:, 0] - top2[:, 1]) < 2e-3
+        assert torch.equal(alg._last_pseudo_label.cpu()[~close], rec["pseudo"][~close]), f"it {it}: pseudo labels differ"
+        mp = rec["probs_w"].max(dim=-1).values
+        thr_gap = (alg._last_mask.cpu() != rec["mask"])
+        if thr_gap.any():   # only rows whose max-prob sits within 1e-4 of the threshold may flip
+            thr = float(orc.hook.time_p) * (orc.hook.p_model / orc.hook.p_model.max())[rec["pseudo"]]
+            assert ((mp - thr).abs()[thr_gap] < 1e-4).all(), f"it {it}: mask differs away from the threshold"
+        print(f"config-3 shape it {it}: {int(close.sum())} near-tie argmax rows, {int(thr_gap.sum())} threshold-band mask flips")
+        assert abs(ld["train/sup_loss"] - float(rec["sup_loss"])) < 1e-3
+        assert abs(hook.time_p.item() - float(orc.hook.time_p)) < 1e-4
+        tied = mask2_report(rec, alg._last_mask2, f"config-3 shape it {it}")
+        if not tied and not thr_gap.any() and not close.any():
+            for kn, ko in (("train/unsup_loss", "unsup_loss"), ("train/total_loss", "total_loss")):
+                assert abs(ld[kn] - float(rec[ko])) < 1e-3, f"it {it} {ko}: {ld[kn]} vs {float(rec[ko])}"
+            worst = 0.0
+            for n, p in alg.model.named_parameters():
+                gr = ref_grads[n]
+                worst = max(worst, (tap[n].cpu() - gr).abs().max().item() / max(gr.abs().max().item(), 1e-20))
+            print(f"config-3 shape it {it}: total {ld['train/total_loss']:.5f} (oracle {float(rec['total_loss']):.5f}) grad rel err {worst:.2e}")
+            assert worst < 1e-3
+        _resync(alg, orc)
+
+
+def test_checkpoint_round_trip_continues_moments_and_schedule(tmp_path):
+    """a resumed run must continue AdamW's moments, its step count and the LR schedule.  Run A: 4 steps.  Run B: 2
+    steps, save, fresh object, load, 2 more steps.  Parameters, moments and learning rates must be bit-identical."""
+    cfg = small_cfg(num_warmup_iter=3, num_train_iter=64)
+
+    def steps(alg, its):
+        for it in its:
+            alg.it = it
+            alg.out_dict, alg.log_dict = alg.train_step(**alg.process_batch(**batch_tensors(cfg, it)))
+            alg.call_hook("after_train_step")
+        torch.cuda.synchronize()
+    a = build_native(cfg, 2)
+    steps(a, range(4))
+    b = build_native(cfg, 2)
+    steps(b, range(2))
+    b.it = 1
+    b.save_model("ck.pth", str(tmp_path))
+    c = build_native(cfg, 2, seed=5)        # different initial weights: everything must come from the file
+    c.load_model(os.path.join(str(tmp_path), "ck.pth"))
+    assert c.it == 2 and c.scheduler.last_epoch == 2
+    steps(c, range(2, 4))
+    assert [g["lr"] for g in c.optimizer.param_groups] == [g["lr"] for g in a.optimizer.param_groups]
+    for (n, pa), (_, pc) in zip(a.model.named_parameters(), c.model.named_parameters()):
+        assert torch.equal(pa, pc), n
+        sa, scc = a.optimizer.state[pa], c.optimizer.state[pc]
+        assert torch.equal(sa["exp_avg"], scc["exp_avg"]) and torch.equal(sa["exp_avg_sq"], scc["exp_avg_sq"]), n
+    for pa, pc in zip(a.rewarder.parameters(), c.rewarder.parameters()):
+        assert torch.equal(pa, pc)
+    ha, hc = a.hooks_dict["MaskingHook"], c.hooks_dict["MaskingHook"]
+    assert torch.equal(ha.selected_label, hc.selected_label) and torch.equal(ha.classwise_acc, hc.classwise_acc)
+
+
+def test_extract_matches_oracle_tokens():
+    from oracle import ssl_oracle as O
+    cfg = small_cfg()
+    orc = build_oracle(cfg, 2)
+    alg = build_native(cfg, 2)
+    x = batch_tensors(cfg, 0)["x_lb"]
+    with torch.no_grad():
+        _, feat, tok = O.vit_forward(orc.p, x, orc.vit_cfg, return_tokens=True)
+    alg.model.eval()
+    got = alg.model.extract(x.cuda())
+    assert got.shape == tok.shape
+    assert (got.cpu() - tok).abs().max().item() < 1e-3
+    assert (alg.model(x.cuda(), only_feat=True).cpu() - feat).abs().max().item() < 1e-3
+
+
+def test_ema_rewarder_matches_reference_expression():
+    """EMARewarder (semireward.py:75-127): forward == Rewarder.forward on the live parameters; every forward then moves
+    ema_params by ema = decay * ema + (1 - decay) * param."""
+    from semireward_b200.algorithms.semireward import EMARewarder, Rewarder
+    torch.manual_seed(0)
+    r = EMARewarder(100, 128, feature_dim=384, ema_decay=0.9).cuda()
+    plain = Rewarder(100, 128, feature_dim=384).cuda()
+    plain.load_state_dict(r.state_dict())
+    feats, labels = torch.randn(8, 384, device="cuda"), torch.randint(0, 100, (8,), device="cuda")
+    before = {n: e.detach().clone().cuda() for n, e in r.ema_params.items()}
+    out = r(feats, labels)          # first forward on the device re-seats the average on the parameters (semireward.py:100-101)
+    assert torch.equal(out, plain(feats, labels))
+    with torch.no_grad():
+        for p in r.parameters():
+            p.add_(0.25)
+    r(feats, labels)
+    for n, p in r.named_parameters():
+        want = before[n] * 0.9 + (1 - 0.9) * p.detach()
+        assert (r.ema_params[n].detach() - want).abs().max().item() < 1e-6, n
