@@ -281,6 +281,12 @@ typedef struct {
                                                   2: Adam only from g (lets the caller all-reduce g between 1 and 2: DDP, C3) */
   float* losses;                               /* [2] generator_loss, rewarder_loss */
   float* workspace;                            /* >= srw_rewarder_workspace_floats(B, feature_dim) */
+  /* Data parallel, matching torch DDP on the reference's sequence `generator_loss.backward(); rewarder_loss.backward()` after ONE
+   * forward of the DDP-wrapped Rewarder (srflexmatch.py:204-205): DDP's reducer synchronises only the FIRST backward, so the
+   * optimizer sees mean_ranks(g_generator_loss) + LOCAL g_rewarder_loss (measured with the reference's own module under gloo DDP,
+   * scripts/c3_ddp_probe.py).  loss_select: 0 = both losses (single process), 1 = gradient of generator_loss only, 2 = of
+   * rewarder_loss only (phases 0/1).  g_add (phase 2, may be NULL): a second gradient set added to g before the Adam step. */
+  int loss_select; float* const* g_add;
 } srw_rewarder_train_args;
 int srw_rewarder_train(const srw_rewarder_train_args* a, void* stream);
 

@@ -470,6 +470,11 @@ class SSLOracle:
         # With DropPath off the K passes are numerically identical, so a big-shape test may evaluate the backbone once per
         # data_generator call and replay only the hook-state updates — bit-equivalent in that deterministic mode ONLY.
         self.reuse_deterministic_passes = False
+        # Data parallel: a torch.distributed group (gloo on CPU).  Every rank holds its own oracle on its own
+        # shard; backbone gradients are averaged over the ranks (DDP, misc.py:56-64); of the SR update's two backward passes
+        # only the first (generator_loss) is synchronised by DDP's reducer, the second (rewarder_loss) stays local
+        # (srflexmatch.py:204-205; measured on the reference's own module by scripts/c3_ddp_probe.py).
+        self.dp_group = None
 
     # -- pieces ---------------------------------------------------------------------------------
     def _backbone(self, x_lb, x_ulb_w, x_ulb_s):
@@ -524,6 +529,8 @@ class SSLOracle:
         g1 = torch.autograd.grad(gen_loss, [self.rp[k] for k in names], retain_graph=True, allow_unused=True)
         g2 = torch.autograd.grad(rew_loss, [self.rp[k] for k in names], retain_graph=True, allow_unused=True)
         grads = {}
+        if self.dp_group is not None:
+            g1 = [self._dp_mean(torch.zeros_like(self.rp[k]) if a is None else a) for k, a in zip(names, g1)]
         for k, a, b in zip(names, g1, g2):
             grads[k] = None if (a is None and b is None) else ((0 if a is None else a) + (0 if b is None else b))
         lr_wd = {k: (self.cfg.sr_lr, 0.0) for k in names}
@@ -626,12 +633,20 @@ class SSLOracle:
                    util_ratio=mask.float().mean())
         return rec
 
+    def _dp_mean(self, t: Tensor) -> Tensor:
+        import torch.distributed as dist
+        t = t.detach().clone()
+        dist.all_reduce(t, group=self.dp_group)
+        return t / dist.get_world_size(self.dp_group)
+
     def param_update(self) -> Dict[str, Tensor]:
         """ParamUpdateHook.after_train_step (param_update.py:21-40): backward, AdamW step, scheduler step, zero_grad.
         Returns the gradients (for parity checks)."""
         names = list(self.p.keys())
         gs = torch.autograd.grad(self.loss, [self.p[k] for k in names], allow_unused=True)
         grads = {k: g for k, g in zip(names, gs)}
+        if self.dp_group is not None:
+            grads = {k: self._dp_mean(torch.zeros_like(self.p[k]) if g is None else g) for k, g in grads.items()}
         f = cosine_lr_factor(self.sched_step, self.cfg.num_train_iter, self.cfg.num_warmup_iter)
         lr_wd = {k: (self.hp[k][0] * f, self.hp[k][1]) for k in names}
         self.opt.step(self.p, grads, lr_wd)

@@ -104,7 +104,8 @@ class GeneratorFwdArgs(C.Structure):
 class RewarderTrainArgs(C.Structure):
     _fields_ = [("B", i32), ("feature_dim", i32), ("label_rows", i32), ("num_classes", i32), ("rp", C.POINTER(vp)),
                 ("g", C.POINTER(vp)), ("m", C.POINTER(vp)), ("v", C.POINTER(vp)), ("feats", vp), ("ld_feats", i64),
-                ("gen_labels", vp), ("true_labels", vp), ("lr", f32), ("step", i32), ("phase", i32), ("losses", vp), ("workspace", vp)]
+                ("gen_labels", vp), ("true_labels", vp), ("lr", f32), ("step", i32), ("phase", i32), ("losses", vp), ("workspace", vp),
+                ("loss_select", i32), ("g_add", C.POINTER(vp))]
 
 
 class FlexMatchMaskArgs(C.Structure):

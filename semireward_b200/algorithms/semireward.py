@@ -149,13 +149,25 @@ class Rewarder(nn.Module):
         if group is None:
             L.check(L.load().srw_rewarder_train(C.byref(a), L.stream_ptr()), "srw_rewarder_train")
         else:
-            # data-parallel (reference: Rewarder wrapped in DDP, srflexmatch.py:49-51): gradients are averaged over the
-            # ranks between the backward and the Adam step
+            # Data parallel.  The reference wraps the Rewarder in torch DDP (srflexmatch.py:49-51) and calls backward twice after one
+            # forward (:204-205); DDP's reducer only synchronises the first of them, so its optimizer steps with
+            # mean_ranks(grad generator_loss) + LOCAL grad rewarder_loss and the ranks' Rewarders drift apart
+            # (scripts/c3_ddp_probe.py runs the reference's module under gloo DDP).  Same here: the generator-loss gradient
+            # is averaged, the rewarder-loss gradient stays local, one Adam step on their sum.
             from ..parallel import allreduce_mean_
-            a.phase = 1
+            if "g2" not in st:
+                g2flat = torch.empty_like(st["gflat"])
+                st["g2"], off = [], 0
+                for p in ps:
+                    st["g2"].append(g2flat[off:off + p.numel()].view_as(p))
+                    off += p.numel()
+            losses2 = torch.empty(2, dtype=torch.float32, device=dev)
+            a.phase, a.loss_select = 1, 1
             L.check(L.load().srw_rewarder_train(C.byref(a), L.stream_ptr()), "srw_rewarder_train")
             allreduce_mean_(st["gflat"], group)
-            a.phase = 2
+            a.loss_select, a.g, a.losses = 2, L.ptr_array(st["g2"]), losses2.data_ptr()
+            L.check(L.load().srw_rewarder_train(C.byref(a), L.stream_ptr()), "srw_rewarder_train")
+            a.phase, a.loss_select, a.g, a.g_add = 2, 0, L.ptr_array(st["g"]), L.ptr_array(st["g2"])
             L.check(L.load().srw_rewarder_train(C.byref(a), L.stream_ptr()), "srw_rewarder_train")
         return losses
 

@@ -401,7 +401,8 @@ struct AdamScalars { float lr; double bc1, bc2_sqrt; };
 
 __global__ void __launch_bounds__(SSL_THREADS) rewarder_train_kernel(RewPtrs P, RewPtrs G, RewPtrs M, RewPtrs V, RewSizes N, const float* feats,
                                                                     int64_t ld_feats, const int64_t* gen_labels, const int64_t* true_labels,
-                                                                    int B, int D, int label_rows, AdamScalars ad, int phase, float* losses, float* ws) {
+                                                                    int B, int D, int label_rows, AdamScalars ad, int phase, float* losses, float* ws, int loss_select, RewPtrs GA,
+                                                                    int has_g_add) {
   __shared__ float red[32];
   const RewWs s = rew_carve(ws, B);
   if (phase != 2) {
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(SSL_THREADS) rewarder_train_kernel(RewPtrs P, 
     const float tgt = (gen_labels[b] == true_labels[b]) ? 1.0f : 0.5f;
     gl += (r - 1.0f) * (r - 1.0f);
     rl += (r - tgt) * (r - tgt);
-    const float dr = (2.0f * (r - 1.0f) + 2.0f * (r - tgt)) / (float)B;
+    const float dr = ((loss_select == 2 ? 0.f : 2.0f * (r - 1.0f)) + (loss_select == 1 ? 0.f : 2.0f * (r - tgt))) / (float)B;
     s.dz4[b] = dr * r * (1.0f - r);
   }
   gl = block_reduce_sum(gl, red);
@@ -497,8 +498,9 @@ __global__ void __launch_bounds__(SSL_THREADS) rewarder_train_kernel(RewPtrs P, 
   const float bc2s = (float)ad.bc2_sqrt;
   for (int t = 0; t < R_NUM; ++t) {
     float* p = P.p[t]; const float* g = G.p[t]; float* m = M.p[t]; float* v = V.p[t];
+    const float* ga = has_g_add ? GA.p[t] : nullptr;
     for (int64_t i = threadIdx.x; i < N.n[t]; i += blockDim.x) {
-      const float gi = g[i];
+      const float gi = ga ? g[i] + ga[i] : g[i];
       const float mi = m[i] + 0.1f * (gi - m[i]);
       const float vi = v[i] * 0.999f + (0.001f * gi) * gi;
       m[i] = mi;
@@ -572,8 +574,10 @@ extern "C" int srw_rewarder_train(const srw_rewarder_train_args* a, void* stream
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SRW_REQUIRE(a && a->rp && a->g && a->m && a->v && a->feats && a->gen_labels && a->true_labels && a->losses && a->workspace, "srw_rewarder_train: null pointer");
   SRW_REQUIRE(a->B > 0 && a->B <= MAX_ROWS && a->feature_dim > 0 && a->label_rows > 0 && a->step >= 1, "srw_rewarder_train: bad shape / step");
-  RewPtrs P, G, M, V;
+  SRW_REQUIRE(a->loss_select >= 0 && a->loss_select <= 2, "srw_rewarder_train: loss_select must be 0, 1 or 2");
+  RewPtrs P, G, M, V, GA = {};
   fill_ptrs(P, a->rp); fill_ptrs(G, a->g); fill_ptrs(M, a->m); fill_ptrs(V, a->v);
+  if (a->g_add) fill_ptrs(GA, a->g_add);
   RewSizes N;
   const int64_t D = a->feature_dim, Lr = a->label_rows;
   const int64_t sizes[R_NUM] = {128 * D, 128, 128, 128, Lr * 128, 128, 128, 128, 1, 256 * 128, 256, 128 * 256, 128, 64 * 128, 64, 64, 1};
@@ -583,7 +587,7 @@ extern "C" int srw_rewarder_train(const srw_rewarder_train_args* a, void* stream
   ad.bc1 = 1.0 - pow(0.9, (double)a->step);
   ad.bc2_sqrt = sqrt(1.0 - pow(0.999, (double)a->step));
   rewarder_train_kernel<<<1, SSL_THREADS, 0, stream>>>(P, G, M, V, N, a->feats, a->ld_feats, a->gen_labels, a->true_labels, a->B, a->feature_dim,
-                                                      a->label_rows, ad, a->phase, a->losses, a->workspace);
+                                                      a->label_rows, ad, a->phase, a->losses, a->workspace, a->loss_select, GA, a->g_add ? 1 : 0);
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;

@@ -308,3 +308,34 @@ def test_combined_class_steps_through_the_reference_train_loop(tmp_path, monkeyp
     a3 = semilearn.get_algorithm(args, semilearn.get_net_builder("vit_small_patch2_32", False), None, None)
     assert isinstance(a3, Native) and isinstance(a3, RefBase) and type(a3) is reg["srflexmatch"]
     assert type(a3.model).__module__ == "semireward_b200.nets.vit"
+
+
+def test_pretrained_loading_follows_the_reference_load_checkpoint(tmp_path):
+    """nets/utils.py:18-73 semantics: weights under 'model', `module.` prefix stripped, classifier tensors skipped,
+    pos_embed resampled bicubically to the model's grid, non-strict.  Against the live reference function when it is mounted."""
+    import functools
+    import semireward_b200 as S
+    from semireward_b200.nets.utils import load_checkpoint, resize_pos_embed_vit
+    torch.manual_seed(0)
+    src = S.get_net_builder("vit_small_patch2_32")(num_classes=10, depth=1, img_size=16)       # 8 x 8 grid + cls
+    sd = {("module." + k): v.clone() for k, v in src.state_dict().items()}
+    sd["module.fc.weight"] = torch.zeros(3, 3)                                                   # foreign classifier tensors are dropped
+    path = os.path.join(str(tmp_path), "pre.pth")
+    torch.save({"model": sd}, path)
+    dst = S.get_net_builder("vit_small_patch2_32")(num_classes=100, pretrained=True, pretrained_path=path, depth=1)   # 16 x 16 grid
+    assert dst.pos_embed.shape == (1, 257, 384)
+    want = resize_pos_embed_vit(src.pos_embed.data, dst.pos_embed.data)
+    assert torch.equal(dst.pos_embed.data, want)
+    assert torch.equal(dst.pos_embed.data[:, 0], src.pos_embed.data[:, 0])                       # the cls slot is copied, the grid resampled
+    assert torch.equal(dst.blocks[0].attn.qkv.weight, src.blocks[0].attn.qkv.weight)
+    assert dst.head.weight.shape == (100, 384) and not torch.equal(dst.head.bias, torch.full((100,), 7.0))
+    if os.path.isdir("/root/reference/semilearn"):
+        from oracle import ref_driver as R
+        R.load_reference()
+        from semilearn.nets.utils import load_checkpoint as ref_load, resize_pos_embed_vit as ref_resize
+        assert torch.equal(ref_resize(src.pos_embed.data, dst.pos_embed.data), want)
+        ref_dst = S.get_net_builder("vit_small_patch2_32")(num_classes=100, depth=1)
+        ref_load(ref_dst, path)
+        for (n, a), (_, b) in zip(ref_dst.state_dict().items(), dst.state_dict().items()):
+            if not n.startswith("head"):
+                assert torch.equal(a, b), n

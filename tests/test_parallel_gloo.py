@@ -1,9 +1,12 @@
 """CPU, world_size 2, gloo: the host logic of the data-parallel path — gradient averaging of the flat
 buffer, rank sharding, and that rank-local state (FlexMatch hook) is NOT synchronised."""
 import os
+import sys
 
 import torch
 import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import torch.multiprocessing as mp
 
 
@@ -105,3 +108,43 @@ def test_wrn_sync_batchnorm_equals_union_batch():
         assert p.exitcode == 0
     for rank, err_l, err_g, err_b in res:
         assert err_l < 2e-4 and err_g < 2e-4 and err_b < 1e-5, (rank, err_l, err_g, err_b)
+
+
+def _oracle_dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import batch_tensors, build_oracle, small_cfg
+    cfg = small_cfg(start_timing=2, N_k=2, num_train_iter=16)
+    orc = build_oracle(cfg, 1)
+    orc.dp_group = dist.group.WORLD
+    for it in range(3):
+        orc.train_step(dict(batch_tensors(cfg, it, seed=1 + rank)), it)
+        orc.param_update()
+    q.put((rank, {k: v.detach().numpy().copy() for k, v in orc.p.items()}, {k: v.detach().numpy().copy() for k, v in orc.rp.items()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_oracle_data_parallel_semantics_two_ranks():
+    """The oracle's N-rank form (the checker of the 2-GPU NCCL parity test): backbone gradients averaged -> the ranks' backbones stay
+    bit-identical; of the SR update only the generator-loss gradient is averaged (DDP synchronises the first backward only,
+    scripts/c3_ddp_probe.py) -> the ranks' Rewarders differ, as they do in the reference."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_oracle_dp_worker, args=(r, 2, 29641, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict()
+    for _ in range(2):
+        r, p, rp = q.get(timeout=600)
+        got[r] = (p, rp)
+    for p in procs:
+        p.join(60)
+    import numpy as np
+    for k in got[0][0]:
+        assert np.array_equal(got[0][0][k], got[1][0][k]), k
+    assert any(not np.array_equal(got[0][1][k], got[1][1][k]) for k in got[0][1])
