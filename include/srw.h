@@ -43,6 +43,22 @@ typedef struct { int64_t launches; double total_ms; double flops; double bytes; 
 int srw_profile_enable(int on);
 int srw_profile_collect(srw_profile_stats* out /* [SRW_PROF_NUM] */);
 
+/* ---- counter-based dropout ----------------------------------------------------------------------------------- */
+/* nn.Dropout of the text / audio encoders (HF BertModel: embeddings, attention probabilities, attention output, FFN output;
+ * bert.py:14 pooled features).  torch draws its masks from a Philox stream no other implementation can reproduce, so the
+ * native path (and the oracle) define the mask as a pure function: element idx of site `site` of a sequence is kept iff
+ *   (lowbias32(idx + lowbias32(seq_key + site * 0x9E3779B9)) >> 8) < (1 - p) * 2^24        (csrc/srw_common.cuh)
+ * kept values are scaled by 1 / (1 - p).  seq_key[s] identifies the sequence's stream (one key per backbone call of the
+ * reference: the three calls of `use_cat: False`, the K sampling passes), seq_row[s] is the sequence's row inside that call
+ * (element indices are those of the call's own tensor, e.g. ((row * H + h) * L + q) * L + k for attention probabilities,
+ * (row * L + l) * D + d for hidden states).  p == 0 or seq_key == NULL: no dropout. */
+typedef struct {
+  const uint32_t* seq_key;   /* device [num sequences] */
+  const int32_t* seq_row;    /* device [num sequences] */
+  uint32_t site;
+  double p;
+} srw_dropout;
+
 /* ---- split-plane conversion -------------------------------------------------------------------------------- */
 /* planes[r, c] = split(x[r, c] * (row_scale ? row_scale[r / rows_per_scale] : 1)).  Used for weights once per optimizer
  * step and for gradient tensors entering a GEMM.  transposed != 0 additionally writes planes_t[c, r] (ld = rows). */
@@ -89,6 +105,10 @@ typedef struct {
   int impl;                                   /* srw_gemm_impl; SIMT is the on-device verification twin */
   int max_ctas;                               /* 0 = the whole GPU; > 0: persistent grid of at most this many CTAs (the GEMM
                                                  shares the GPU with kernels on other streams, e.g. the four wgrads of a block) */
+  /* SRW_EPI_RESID only: out = resid + dropout(acc + bias) (BertSelfOutput / BertOutput: dropout between the dense layer and the
+   * residual add, HF modeling_bert.py:287-298, 330-356).  Rows are tokens: sequence = row / drop_rows_per_seq, element index
+   * (seq_row * drop_rows_per_seq + row % drop_rows_per_seq) * N + col. */
+  srw_dropout drop; int drop_rows_per_seq;
 } srw_gemm_args;
 int srw_gemm(const srw_gemm_args* a, void* stream);
 
@@ -149,6 +169,9 @@ typedef struct {
   void* dx_planes; int64_t ldp; int64_t plane_stride;
   const float* row_scale; int rows_per_scale;
   float* colsum_out; int colsum_accumulate;
+  /* post-LN encoders: the handed-over operand is the gradient entering the dropout that precedes the residual add,
+   * dx_planes = split(dropout_mask * dx_new / keep) (same mask as the forward's SRW_EPI_RESID dropout); rows per sequence as there */
+  srw_dropout drop; int drop_rows_per_seq;
 } srw_layernorm_bwd_args;
 int srw_layernorm_bwd(const srw_layernorm_bwd_args* a, void* stream);
 
@@ -160,6 +183,14 @@ typedef struct {
   const void* qkv; int64_t ld_qkv; int64_t qkv_plane_stride;
   void* o; int64_t ld_o; int64_t o_plane_stride;
   float* lse;
+  /* Extensions for the text / audio encoders (NULL / 0 = plain ViT attention).  With any of them set, or N > 272, the
+   * key-streaming kernels run (N <= 512):
+   *   key_bias [B, ld_bias] fp32: additive key-padding bias, 0 for real tokens and -inf for padding (HF create_bidirectional_mask
+   *     adds finfo.min, whose exp is exactly 0 as well); kv_len[b] = number of leading keys that can be non-masked (key chunks past
+   *     it are skipped).  Build both from an attention_mask with srw_attn_mask_prepare.
+   *   drop: dropout on the attention probabilities (BertSelfAttention, p = attention_probs_dropout_prob). */
+  const float* key_bias; int64_t ld_bias; const int32_t* kv_len;
+  srw_dropout drop;
 } srw_attn_fwd_args;
 int srw_attn_fwd(const srw_attn_fwd_args* a, void* stream);
 
@@ -171,8 +202,14 @@ typedef struct {
   const float* lse;
   float* delta;                               /* scratch [B, H, N] */
   void* dqkv; int64_t ld_dqkv; int64_t dqkv_plane_stride;
+  const float* key_bias; int64_t ld_bias; const int32_t* kv_len;   /* as in srw_attn_fwd_args */
+  srw_dropout drop;
 } srw_attn_bwd_args;
 int srw_attn_bwd(const srw_attn_bwd_args* a, void* stream);
+
+/* attention_mask int64 [B, L] (1 = token, 0 = padding; NULL = all ones) -> key_bias fp32 [B, ld_bias] (0 / -inf; columns in
+ * [L, ld_bias) are -inf) and kv_len int32 [B] = 1 + index of the last non-zero mask entry (>= 1).  ld_bias >= L rounded up to 64. */
+int srw_attn_mask_prepare(const int64_t* attention_mask, int B, int L, float* key_bias, int64_t ld_bias, int32_t* kv_len, void* stream);
 
 /* ---- ViT engine: the whole backbone forward / backward as one native call ------------------------------------ */
 /* Mirrors VisionTransformer.forward (vit.py:277-306).  Parameters stay PyTorch-owned fp32 tensors in nn.Linear layout;

@@ -78,45 +78,54 @@ class BertCfg:
         return self.layers * per_layer + 2.0 * (H * H + H * self.num_classes)
 
 
-def counter_keep_mask(numel: int, keep: float, seed: int, site: int) -> Tensor:
-    """Counter-based Bernoulli(keep) mask that a CUDA epilogue can reproduce element for element (no RNG stream to share):
-    element i of dropout site `site` is kept iff the top 24 bits of splitmix64(seed * 2^32 + site * 2^40-ish mix + i) are
-    below keep * 2^24.  Pure 64-bit integer arithmetic (wrap-around multiply), identical on every device."""
-    M = (1 << 64) - 1
+def lowbias32(x):
+    """32-bit integer mixer (two multiply-xorshift rounds) on numpy uint32 arrays / ints; wraps modulo 2^32."""
+    import numpy as np
+    x = np.asarray(x, dtype=np.uint64) & 0xFFFFFFFF
+    x ^= x >> 16
+    x = (x * 0x7FEB352D) & 0xFFFFFFFF
+    x ^= x >> 15
+    x = (x * 0x846CA68B) & 0xFFFFFFFF
+    x ^= x >> 16
+    return x
 
-    def to_i64(v):
-        v &= M
-        return v - (1 << 64) if v >= (1 << 63) else v
-    base = to_i64(((seed & 0xFFFFFFFF) << 32) ^ ((site & 0xFFFFF) * 0x9E3779B97F4A7C15))
-    x = torch.arange(numel, dtype=torch.int64) + base                     # int64 add / mul wrap modulo 2^64 like uint64
-    x = x + to_i64(0x9E3779B97F4A7C15)
 
-    def shr(v, n):                                                        # logical right shift on int64 storage
-        return (v >> n) & ((1 << (64 - n)) - 1)
-    z = (x ^ shr(x, 30)) * to_i64(0xBF58476D1CE4E5B9)
-    z = (z ^ shr(z, 27)) * to_i64(0x94D049BB133111EB)
-    z = z ^ shr(z, 31)
-    return shr(z, 40) < int(keep * (1 << 24))
+def call_key(seed: int, call: int) -> int:
+    """Stream key of one backbone call (the reference makes three per step with `use_cat: False`, and three more per sampling
+    pass): every call draws from its own stream, like successive nn.Dropout invocations do."""
+    return int(lowbias32((seed * 0x9E3779B9 + call * 0x85EBCA6B + 0x165667B1) & 0xFFFFFFFF))
+
+
+def counter_keep_mask(numel: int, keep: float, key: int, site: int, offset: int = 0) -> Tensor:
+    """Counter-based Bernoulli(keep) mask that a CUDA epilogue regenerates element for element (no RNG stream to share; the
+    definition is restated from include/srw.h `srw_dropout`): element i of dropout site `site` of the stream `key` is kept iff
+    the top 24 bits of lowbias32(i + lowbias32(key + site * 0x9E3779B9)) are below keep * 2^24.  Pure 32-bit integer arithmetic."""
+    import numpy as np
+    site_key = int(lowbias32((key + site * 0x9E3779B9) & 0xFFFFFFFF))
+    idx = (np.arange(offset, offset + numel, dtype=np.uint64) + site_key) & 0xFFFFFFFF
+    return torch.from_numpy((lowbias32(idx) >> 8) < int(keep * (1 << 24)))
 
 
 class BertDropout:
     """Order in which a stochastic pass draws its Bernoulli(1-p)/(1-p) masks: embeddings; per layer attention probabilities
     [B, heads, L, L], attention output [B, L, H], FFN output [B, L, H]; last the pooled-feature dropout [B, L, H].
     p = 0 everywhere (deterministic parity mode) draws nothing.  `generator` is either a torch.Generator (masks from torch's
-    CPU stream, like the reference's nn.Dropout but not reproducible elsewhere) or an int seed: then site k of the pass uses
-    counter_keep_mask(numel, keep, seed, k), which a native kernel can regenerate bit for bit."""
+    CPU stream, like the reference's nn.Dropout but not reproducible elsewhere) or an int stream key (`call_key(seed, call)`):
+    then site k of the call uses counter_keep_mask(numel, keep, key, k) over the call's own tensor (row-major element index),
+    which a native kernel regenerates bit for bit."""
 
     def __init__(self, cfg: BertCfg, generator, enabled: bool):
         self.cfg, self.gen, self.enabled = cfg, generator, enabled
         self.site = 0
 
     def __call__(self, x: Tensor, p: float) -> Tensor:
+        site = self.site
+        self.site += 1            # site numbers are positions in the forward, whether or not that dropout is active
         if not self.enabled or p == 0.0:
             return x
         keep = 1.0 - p
         if isinstance(self.gen, int):
-            m = counter_keep_mask(x.numel(), keep, self.gen, self.site).view(x.shape).to(x.dtype).div_(keep)
-            self.site += 1
+            m = counter_keep_mask(x.numel(), keep, self.gen, site).view(x.shape).to(x.dtype).div_(keep)
         else:
             m = torch.empty_like(x).bernoulli_(keep, generator=self.gen).div_(keep)
         return x * m
@@ -188,13 +197,24 @@ class BertSSLOracle(O.SSLOracle):
         super().__init__(None, cfg, params, rewarder, generator, hparams=hp)
         self.bert_cfg = bert_cfg
         self.stochastic = stochastic
+        self.calls = 0          # backbone calls made so far (counter-dropout stream index)
+
+    def _drop(self):
+        """Dropout source of the next backbone call: `drop_gen` a torch.Generator -> torch's stream; an int seed -> the counter
+        masks with one stream key per call (`call_key(seed, number of calls so far)`)."""
+        if isinstance(self.drop_gen, int):
+            d = BertDropout(self.bert_cfg, call_key(self.drop_gen, self.calls), self.stochastic)
+        else:
+            d = BertDropout(self.bert_cfg, self.drop_gen, self.stochastic)
+        self.calls += 1
+        return d
 
     def _backbone(self, x_lb, x_ulb_w, x_ulb_s):
-        drop = BertDropout(self.bert_cfg, self.drop_gen, self.stochastic)
-        llb, flb = bert_forward(self.p, x_lb, self.bert_cfg, drop)
-        ls, fs = bert_forward(self.p, x_ulb_s, self.bert_cfg, drop)
+        # srsoftmatch.py:119-130 order: labelled, strong (both with autograd), then weak under no_grad
+        llb, flb = bert_forward(self.p, x_lb, self.bert_cfg, self._drop())
+        ls, fs = bert_forward(self.p, x_ulb_s, self.bert_cfg, self._drop())
         with torch.no_grad():
-            lw, fw = bert_forward(self.p, x_ulb_w, self.bert_cfg, drop)
+            lw, fw = bert_forward(self.p, x_ulb_w, self.bert_cfg, self._drop())
         return llb, lw, ls, flb, fw, fs
 
 

@@ -267,6 +267,7 @@ class FlexMatchState:
     def masking(self, probs: Tensor, idx_ulb: Tensor, p_cutoff: float) -> Tensor:
         max_probs, max_idx = torch.max(probs, dim=-1)
         acc = self.classwise_acc[max_idx]
+        self.last_gap = max_probs - p_cutoff * (acc / (2.0 - acc))   # diagnostic for the parity tests: distance to the threshold
         mask = max_probs.ge(p_cutoff * (acc / (2.0 - acc))).to(max_probs.dtype)  # utils.py:52
         select = max_probs.ge(p_cutoff)
         if int(select.sum()) != 0:
@@ -300,6 +301,7 @@ class FreeMatchState:
         self.update(probs, use_quantile, clip_thresh)
         max_probs, max_idx = probs.max(dim=-1)
         mod = self.p_model / torch.max(self.p_model, dim=-1)[0]
+        self.last_gap = max_probs - self.time_p * mod[max_idx]   # diagnostic for the parity tests: distance to the threshold
         return max_probs.ge(self.time_p * mod[max_idx]).to(max_probs.dtype)
 
 
@@ -513,7 +515,8 @@ class SSLOracle:
             reward = rewarder_forward(self.rp, fw, pseudo)  # rewarder.eval(): no dropout/BN inside -> same math
             mask2 = torch.where(reward >= reward.mean(), 1, 0).squeeze().float()
             unsup = consistency_loss(ls, pseudo, mask, mask2)
-            rec.update(dg_mask=mask, dg_mask2=mask2, dg_reward=reward.detach(), dg_pseudo=pseudo)
+            rec.update(dg_mask=mask, dg_mask2=mask2, dg_reward=reward.detach(), dg_pseudo=pseudo, dg_logits_w=lw.detach(),
+                       dg_gap=getattr(self.hook, "last_gap", None))
         return unsup
 
     def _sr_update(self, feats: Tensor, true_labels: Tensor, rec: dict):
@@ -604,6 +607,7 @@ class SSLOracle:
         else:
             probs_for_mask = probs_w
         mask = self._mask_from_probs(probs_for_mask, idx_ulb)
+        rec["gap"] = getattr(self.hook, "last_gap", None)
         pseudo = lw.detach().argmax(dim=-1)  # argmax(probs) == argmax(logits) up to fp ties; reference uses probs for
         if c.algorithm in ("srflexmatch", "srfixmatch"):     # FlexMatch / FixMatch (srflexmatch.py:142-146, fixmatch.py:135-139) and logits for the others
             pseudo = probs_w.argmax(dim=-1)

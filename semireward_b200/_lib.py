@@ -19,6 +19,10 @@ EPI_F32, EPI_PLANES, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_SPLITK = range(6)
 GEMM_TCGEN05, GEMM_SIMT, GEMM_TCGEN05_1CTA = 0, 1, 2
 
 
+class Dropout(C.Structure):
+    _fields_ = [("seq_key", vp), ("seq_row", vp), ("site", C.c_uint32), ("p", C.c_double)]
+
+
 class SplitArgs(C.Structure):
     _fields_ = [("x", vp), ("ldx", i64), ("rows", i32), ("cols", i32), ("row_scale", vp), ("rows_per_scale", i32),
                 ("planes", vp), ("ldp", i64), ("plane_stride", i64), ("planes_t", vp), ("ldpt", i64), ("plane_stride_t", i64),
@@ -31,7 +35,8 @@ class GemmArgs(C.Structure):
                 ("b", vp), ("ldb", i64), ("b_plane_stride", i64), ("b_mn_major", i32),
                 ("epilogue", i32), ("bias", vp), ("resid", vp), ("ldr", i64), ("row_scale", vp), ("rows_per_scale", i32),
                 ("aux", vp), ("ldaux", i64), ("out_f32", vp), ("ldo", i64), ("out_planes", vp), ("ldp", i64),
-                ("out_plane_stride", i64), ("split_k", i32), ("workspace", vp), ("impl", i32), ("max_ctas", i32)]
+                ("out_plane_stride", i64), ("split_k", i32), ("workspace", vp), ("impl", i32), ("max_ctas", i32),
+                ("drop", Dropout), ("drop_rows_per_seq", i32)]
 
 
 class SplitKReduceArgs(C.Structure):
@@ -60,18 +65,21 @@ class LayerNormBwdArgs(C.Structure):
     _fields_ = [("dy", vp), ("lddy", i64), ("x", vp), ("ldx", i64), ("rows", i32), ("cols", i32), ("gamma", vp), ("mean", vp),
                 ("rstd", vp), ("dx", vp), ("lddx", i64), ("accumulate_dx", i32), ("dgamma", vp), ("dbeta", vp),
                 ("accumulate_dparams", i32), ("workspace", vp), ("dx_planes", vp), ("ldp", i64), ("plane_stride", i64),
-                ("row_scale", vp), ("rows_per_scale", i32), ("colsum_out", vp), ("colsum_accumulate", i32)]
+                ("row_scale", vp), ("rows_per_scale", i32), ("colsum_out", vp), ("colsum_accumulate", i32),
+                ("drop", Dropout), ("drop_rows_per_seq", i32)]
 
 
 class AttnFwdArgs(C.Structure):
     _fields_ = [("B", i32), ("N", i32), ("H", i32), ("head_dim", i32), ("scale", f32), ("qkv", vp), ("ld_qkv", i64),
-                ("qkv_plane_stride", i64), ("o", vp), ("ld_o", i64), ("o_plane_stride", i64), ("lse", vp)]
+                ("qkv_plane_stride", i64), ("o", vp), ("ld_o", i64), ("o_plane_stride", i64), ("lse", vp),
+                ("key_bias", vp), ("ld_bias", i64), ("kv_len", vp), ("drop", Dropout)]
 
 
 class AttnBwdArgs(C.Structure):
     _fields_ = [("B", i32), ("N", i32), ("H", i32), ("head_dim", i32), ("scale", f32), ("qkv", vp), ("ld_qkv", i64),
                 ("qkv_plane_stride", i64), ("o", vp), ("ld_o", i64), ("o_plane_stride", i64), ("d_o", vp), ("ld_do", i64),
-                ("do_plane_stride", i64), ("lse", vp), ("delta", vp), ("dqkv", vp), ("ld_dqkv", i64), ("dqkv_plane_stride", i64)]
+                ("do_plane_stride", i64), ("lse", vp), ("delta", vp), ("dqkv", vp), ("ld_dqkv", i64), ("dqkv_plane_stride", i64),
+                ("key_bias", vp), ("ld_bias", i64), ("kv_len", vp), ("drop", Dropout)]
 
 
 class VitConfig(C.Structure):
@@ -186,6 +194,7 @@ SYMBOLS = [
     ("srw_layernorm_bwd", i32, [C.POINTER(LayerNormBwdArgs), vp]),
     ("srw_attn_fwd", i32, [C.POINTER(AttnFwdArgs), vp]),
     ("srw_attn_bwd", i32, [C.POINTER(AttnBwdArgs), vp]),
+    ("srw_attn_mask_prepare", i32, [vp, i32, i32, vp, i64, vp, vp]),
     ("srw_vit_weight_planes_bytes", i64, [C.POINTER(VitConfig)]),
     ("srw_vit_workspace_bytes", i64, [C.POINTER(VitConfig), i32, i32]),
     ("srw_vit_weight_plane_slot", i32, [C.POINTER(VitConfig), i32, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]),

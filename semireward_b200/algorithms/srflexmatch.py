@@ -307,6 +307,7 @@ class SRFlexMatch(AlgorithmBase):
         out_dict = self.process_out_dict(loss=total_loss, feat=feat_dict)
         log_dict = self.process_log_dict(sup_loss=sup, unsup_loss=unsup, total_loss=total, util_ratio=float(host[5:].mean()))
         self._last_mask, self._last_mask2, self._last_pseudo_label = mask, mask2, pseudo_label
+        self._last_mask_dg, self._last_pseudo_dg = mask_dg, pseudo_dg   # the last sampling pass (what the unsupervised loss used)
         return out_dict, log_dict
 
     def _train_step_eager(self, x_lb, y_lb, idx_ulb, x_ulb_w, x_ulb_s):
@@ -386,6 +387,7 @@ class SRFlexMatch(AlgorithmBase):
         out_dict = self.process_out_dict(loss=total_loss, feat=feat_dict)
         log_dict = self.process_log_dict(sup_loss=sup, unsup_loss=unsup, total_loss=total, util_ratio=float(util))
         self._last_mask, self._last_mask2, self._last_pseudo_label = mask, mask2, pseudo_label
+        self._last_mask_dg, self._last_pseudo_dg = (mask_dg, pseudo_dg) if self.it > self.start_timing else (None, None)
         return out_dict, log_dict
 
     def _extra_loss(self, losses, mask, logits_s, dl_s):

@@ -323,6 +323,286 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
+struct AttnExt {              // key-padding bias + probability dropout (text / audio encoders); all off for the ViT
+  const float* key_bias; int64_t ld_bias; const int32_t* kv_len;
+  DropParams drop;
+};
+
+// ------------------------------------------------------------------------------------------------
+// forward, key-streaming form (text / audio encoders: up to 512 tokens, key-padding mask, dropout on the probabilities)
+// ------------------------------------------------------------------------------------------------
+// HF BertSelfAttention / HubertAttention (modeling_bert.py, modeling_hubert.py; called from bert.py:34, hubert.py:45):
+//   A = dropout(softmax(Q K^T / 8 + key_bias)),  O = A V.
+// A 128 x 512 fp32 score tile is all of tensor memory, so the keys are streamed in 64-key chunks through a 4-stage TMA ring (the
+// backward kernels' skeleton) and the softmax is made exact with TWO sweeps instead of an online rescale of O:
+//   sweep 1  S' = Q_hi K_hi^T (one MMA per K step instead of three): the threads only take the row maximum m' of S' c + bias.
+//            Any m' close to the true maximum serves: softmax is shift-invariant, m' only keeps exp2 in range (|S' - S| <= 2^-8 |q||k|).
+//   sweep 2  S = full bf16x3 product again; P = exp2(S c + bias - m') written over S in place as split bf16 (dropped entries as 0);
+//            [O | OX] += P_hi [V_hi | V_lo], OX += P_lo V_hi with A from tensor memory; row sums taken before the dropout.
+//   O = (O + OX) / (keep_prob * sum),  lse = m' ln 2 + ln(sum).
+// Key chunks at or beyond kv_len (trailing padding) are never loaded.  One CTA per (query tile, head, sequence).
+constexpr int FS_NSTAGE = 4;
+constexpr int FS_OFF_Q = 0, FS_OFF_C = 2 * ROW_TILE_BYTES;
+constexpr int FS_CSTAGE = 2 * ROW_TILE_BYTES;                        // K (hi 8K, lo 8K) + V (hi 8K, lo 8K)
+constexpr int FS_VEC = 576;
+constexpr int FS_OFF_VEC = FS_OFF_C + FS_NSTAGE * FS_CSTAGE;         // key bias * log2e per key column, then [4][128] exchange
+constexpr int FS_OFF_BAR = FS_OFF_VEC + FS_VEC * 4 + 4 * 128 * 4;
+constexpr int FS_SMEM = FS_OFF_BAR + 256 + 1024;
+constexpr int FS_THREADS = 512 + 64;
+
+struct AttnFwdStreamParams {
+  int B, N, H, NP;
+  float scale;
+  __nv_bfloat16* o; int64_t ld_o, o_ps;
+  float* lse;
+  AttnExt ext;
+};
+
+__global__ void __launch_bounds__(FS_THREADS, 1)
+attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const AttnFwdStreamParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FS_OFF_BAR);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_acc = bars + 1;
+  uint64_t* bar_t = bars + 2;       // [2] scores of a chunk complete
+  uint64_t* bar_x = bars + 4;       // [2] (count 16) the 16 element-wise warps are done with the chunk (sweep 1: read; sweep 2: P written)
+  uint64_t* bar_cfull = bars + 6;   // [FS_NSTAGE]
+  uint64_t* bar_cfree = bars + 10;  // [FS_NSTAGE]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  float* vec_bias = reinterpret_cast<float*>(smem + FS_OFF_VEC);
+  float* xch = vec_bias + FS_VEC;   // [4][128]
+
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int D = p.H * HD;
+  const int row0 = b * p.N;
+  const int kv_len = p.ext.kv_len ? min(max(p.ext.kv_len[b], 1), p.N) : p.N;
+  const int NPk = (kv_len + 15) / 16 * 16;
+  const int nch = (NPk + 63) / 64;
+
+  if (warp == 16 && lane == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv);
+    mbar_init(bar_q, 1); mbar_init(bar_acc, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_t[s], 1); mbar_init(&bar_x[s], 16); }
+    for (int s = 0; s < FS_NSTAGE; ++s) { mbar_init(&bar_cfull[s], 1); mbar_init(&bar_cfree[s], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  pdl_wait();
+  for (int i = threadIdx.x; i < nch * 64; i += blockDim.x)
+    vec_bias[i] = i < p.N ? (p.ext.key_bias ? p.ext.key_bias[(int64_t)b * p.ext.ld_bias + i] * LOG2E : 0.f) : -INFINITY;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t TM_O = tmem + 256, TM_OX = tmem + 320;     // adjacent: one N = 128 MMA writes both
+
+  if (warp == 16) {
+    if (elect_one()) {
+      // ===== TMA producer: Q tile once; sweep 1 streams K, sweep 2 streams K and V =====
+      mbar_arrive_expect_tx(bar_q, 2 * ROW_TILE_BYTES);
+      tma_load_3d(smem + FS_OFF_Q, &tm_q, bar_q, h * HD, row0 + rt * 128, 0);   // box planes = 2: hi, lo
+      for (int g = 0; g < 2 * nch; ++g) {
+        const int j = g < nch ? g : g - nch, st_i = g % FS_NSTAGE;
+        mbar_wait(&bar_cfree[st_i], ((g / FS_NSTAGE) & 1) ^ 1);
+        uint8_t* st = smem + FS_OFF_C + st_i * FS_CSTAGE;
+        mbar_arrive_expect_tx(&bar_cfull[st_i], g < nch ? ROW_TILE_BYTES : FS_CSTAGE);
+        tma_load_3d(st, &tm_kv, &bar_cfull[st_i], D + h * HD, row0 + j * 64, 0);
+        if (g >= nch) tma_load_3d(st + ROW_TILE_BYTES, &tm_kv, &bar_cfull[st_i], 2 * D + h * HD, row0 + j * 64, 0);
+      }
+    }
+  } else if (warp == 17) {
+    if (elect_one()) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc_t = umma_idesc_bf16(64, 0, 0);        // S = Q K^T   (both K-major, K = head dim)
+      constexpr uint32_t idesc_a2 = umma_idesc_bf16(128, 0, 1);      // [O | OX] += P_hi [V_hi | V_lo]   (V MN-major, K = chunk keys)
+      constexpr uint32_t idesc_a1 = umma_idesc_bf16(64, 0, 1);       //       OX  += P_lo  V_hi
+      const uint32_t q0 = smem_u32(smem + FS_OFF_Q);
+      const uint64_t dqh = umma_smem_desc(q0, 16, 1024), dql = umma_smem_desc(q0 + ROW_TILE_BYTES, 16, 1024);
+      const uint32_t c1s0 = smem_u32(smem + FS_OFF_C), c2s0 = c1s0 + ROW_TILE_BYTES;
+      constexpr uint32_t PLANE = ROW_TILE_BYTES / 2;                  // 64 rows x 128 B
+      const uint64_t dkh0 = umma_smem_desc(c1s0, 16, 1024), dkl0 = umma_smem_desc(c1s0 + PLANE, 16, 1024);
+      const uint64_t mvh0 = umma_smem_desc(c2s0, 1024, 1024), mvb0 = umma_smem_desc(c2s0, PLANE, 1024);
+      constexpr uint32_t STAGE_STEP = FS_CSTAGE >> 4;
+      uint32_t xwaited = 0;   // chunks whose bar_x this thread has observed
+      auto ensure_x = [&](int upto) {
+        while ((int)xwaited <= upto) {
+          mbar_wait(&bar_x[xwaited & 1], (xwaited >> 1) & 1);
+          ++xwaited;
+        }
+        tc_fence_after();
+      };
+      auto issue_s = [&](int g, bool full) {
+        if (g >= 2) ensure_x(g - 2);               // the threads are done with the chunk that used this score buffer before
+        const int st_i = g % FS_NSTAGE;
+        mbar_wait(&bar_cfull[st_i], (g / FS_NSTAGE) & 1);
+        tc_fence_after();
+        const uint32_t t = tmem + (uint32_t)(g & 1) * 64;
+        const uint32_t so = st_i * STAGE_STEP;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t ko = kk * 2;
+          if (full) {
+            umma_bf16(t, dql + ko, dkh0 + so + ko, idesc_t, kk > 0 ? 1u : 0u);
+            umma_bf16(t, dqh + ko, dkl0 + so + ko, idesc_t, 1u);
+            umma_bf16(t, dqh + ko, dkh0 + so + ko, idesc_t, 1u);
+          } else {
+            umma_bf16(t, dqh + ko, dkh0 + so + ko, idesc_t, kk > 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&bar_t[g & 1]);
+      };
+      mbar_wait(bar_q, 0);
+      tc_fence_after();
+      for (int g = 0; g < nch; ++g) {              // sweep 1
+        issue_s(g, false);
+        umma_commit(&bar_cfree[g % FS_NSTAGE]);
+      }
+      issue_s(nch, true);                           // sweep 2
+      for (int j = 0; j < nch; ++j) {
+        const int g = nch + j, st_i = g % FS_NSTAGE;
+        if (j + 1 < nch) issue_s(g + 1, true);      // overwrites P(g-1): the tensor pipe runs it after PV(g-1), issued last iteration
+        ensure_x(g);                                // P(g) is in tensor memory
+        const int ksteps = min(4, (NPk - j * 64) / 16);
+        const uint32_t pa = tmem + (uint32_t)(g & 1) * 64;
+        const uint32_t so = st_i * STAGE_STEP;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (kk < ksteps) {
+            const uint32_t bo = kk * 128 + so;      // 16 keys = 2048 B of an MN-major plane
+            umma_bf16_ts(TM_O, pa + kk * 16, mvb0 + bo, idesc_a2, (j > 0 || kk > 0) ? 1u : 0u);
+            umma_bf16_ts(TM_OX, pa + kk * 16 + 8, mvh0 + bo, idesc_a1, 1u);
+          }
+        }
+        umma_commit(&bar_cfree[st_i]);
+      }
+      umma_commit(bar_acc);
+    }
+  } else {
+    // ===== element-wise warps: 4 per TMEM lane quarter; thread == (query row, 16-key group `part` of each 64-key chunk) =====
+    const int q = warp & 3, part = warp >> 2;
+    const int r = q * 32 + lane;
+    const int qr = rt * 128 + r;            // query index inside the sequence
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const float c2 = p.scale * LOG2E;
+    const DropParams& dr = p.ext.drop;
+    uint32_t site_key = 0, idx_row = 0;
+    if (dr.on) {
+      site_key = drop_site_key(dr.seq_key[b], dr.site);
+      idx_row = (((uint32_t)dr.seq_row[b] * (uint32_t)p.H + (uint32_t)h) * (uint32_t)p.N + (uint32_t)qr) * (uint32_t)p.N;
+    }
+    // ---- sweep 1: row maximum of the (approximate) biased scores, in log2 units ----
+    float m = -INFINITY;
+    for (int g = 0; g < nch; ++g) {
+      const int s = g & 1, col0 = g * 64 + part * 16;
+      mbar_wait(&bar_t[s], (g >> 1) & 1);
+      tc_fence_after();
+      if (col0 < NPk) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(tmem + lane_addr + s * 64 + part * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(vec_bias + col0 + e);
+          m = fmaxf(m, fmaf(__uint_as_float(v[e]), c2, b4.x));
+          m = fmaxf(m, fmaf(__uint_as_float(v[e + 1]), c2, b4.y));
+          m = fmaxf(m, fmaf(__uint_as_float(v[e + 2]), c2, b4.z));
+          m = fmaxf(m, fmaf(__uint_as_float(v[e + 3]), c2, b4.w));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_x[s]);
+    }
+    xch[part * 128 + r] = m;
+    ew_sync();
+    m = fmaxf(fmaxf(xch[r], xch[128 + r]), fmaxf(xch[256 + r], xch[384 + r]));
+    if (!(m > -INFINITY)) m = 0.f;          // a row beyond the sequence (never stored) or fully masked keys: keep exp2 finite
+    ew_sync();                              // xch is reused for the row sums
+    // ---- sweep 2: P = exp2(S c + bias - m), dropout, hand-over through tensor memory ----
+    float sum = 0.f;
+    for (int j = 0; j < nch; ++j) {
+      const int g = nch + j, s = g & 1, col0 = j * 64 + part * 16;
+      mbar_wait(&bar_t[s], (g >> 1) & 1);
+      tc_fence_after();
+      if (col0 < NPk) {
+        uint32_t v[16], w[16];
+        const uint32_t ta = tmem + lane_addr + s * 64 + part * 16;
+        tmem_ld_32x32b_x16(ta, v);
+        tmem_ld_wait();
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float2 b2 = *reinterpret_cast<const float2*>(vec_bias + col0 + 2 * e);
+          float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * e]), c2, b2.x - m));
+          float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c2, b2.y - m));
+          s0 += e0;
+          s1 += e1;
+          if (dr.on) {
+            const uint32_t i0 = idx_row + (uint32_t)(col0 + 2 * e);
+            e0 = drop_kept(site_key, i0, dr.thr24) ? e0 : 0.f;
+            e1 = drop_kept(site_key, i0 + 1, dr.thr24) ? e1 : 0.f;
+          }
+          split2(e0, e1, w[e], w[8 + e]);
+        }
+        sum += s0 + s1;
+        tmem_st_32x32b_x16(ta, w);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_x[s]);
+    }
+    xch[part * 128 + r] = sum;
+    ew_sync();
+    sum = (xch[r] + xch[128 + r]) + (xch[256 + r] + xch[384 + r]);
+    // ---- epilogue: this thread writes output columns [16 * part, 16 * part + 16) of its row ----
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    uint32_t a[16], x[16];
+    tmem_ld_32x32b_x16(TM_O + lane_addr + part * 16, a);
+    tmem_ld_32x32b_x16(TM_OX + lane_addr + part * 16, x);
+    tmem_ld_wait();
+    if (qr < p.N) {
+      const float inv = dr.inv_keep / sum;
+      if (part == 0 && p.lse) p.lse[((int64_t)b * p.H + h) * p.N + qr] = m * (1.0f / LOG2E) + logf(sum);
+      float o16[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) o16[e] = (__uint_as_float(a[e]) + __uint_as_float(x[e])) * inv;
+      store_out16(p.o + (int64_t)(row0 + qr) * p.ld_o + h * HD + part * 16, p.o_ps, o16);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// attention_mask int64 [B, L] -> additive key bias (0 / -inf) and the number of leading keys that can be real tokens
+__global__ void attn_mask_prepare_kernel(const int64_t* __restrict__ mask, int B, int L, float* __restrict__ bias, int64_t ld_bias,
+                                         int32_t* __restrict__ kv_len) {
+  const int b = blockIdx.x;
+  __shared__ int last;
+  if (threadIdx.x == 0) last = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int i = threadIdx.x; i < (int)ld_bias; i += blockDim.x) {
+    const bool real = i < L && (mask == nullptr || mask[(int64_t)b * L + i] != 0);
+    bias[(int64_t)b * ld_bias + i] = real ? 0.f : -INFINITY;
+    if (real) mine = i + 1;
+  }
+  atomicMax(&last, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) kv_len[b] = max(last, 1);
+}
+
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
@@ -337,6 +617,7 @@ struct AttnBwdParams {
   float* delta;                                      // [B,H,N]  written by MODE_DQ, read by MODE_DKV
   __nv_bfloat16* dqkv; int64_t ld_dqkv, dqkv_ps;
   unsigned long long* trace;   // debug (srw_attn_set_bwd_trace): per CTA 48 clock64 stamps; NULL in production
+  AttnExt ext;
 };
 
 constexpr int BWD_THREADS = 512 + 64;   // 16 element-wise warps + TMA warp + MMA warp
@@ -357,16 +638,21 @@ constexpr int BWD_CSTAGE = 2 * ROW_TILE_BYTES;  // C1 (hi 8K, lo 8K) + C2 (hi 8K
 // before the MMA thread asks for them.
 constexpr int BWD_NSTAGE = 4;
 constexpr int BWD_OFF_R1 = 0, BWD_OFF_R2 = 2 * ROW_TILE_BYTES, BWD_OFF_C = 4 * ROW_TILE_BYTES;
-constexpr int BWD_OFF_VEC = BWD_OFF_C + BWD_NSTAGE * BWD_CSTAGE;           // 2 x 320 floats (lse*log2e, delta*scale per column) + [4][128] exchange
-constexpr int BWD_OFF_BAR = BWD_OFF_VEC + 2 * 320 * 4 + 4 * 128 * 4;
+constexpr int BWD_VEC = 576;                                                 // per-column vectors: up to 512 tokens + one chunk of slack
+constexpr int BWD_OFF_VEC = BWD_OFF_C + BWD_NSTAGE * BWD_CSTAGE;           // 3 x BWD_VEC floats (lse*log2e, delta*scale, key bias*log2e per column) + [4][128] exchange
+constexpr int BWD_OFF_BAR = BWD_OFF_VEC + 3 * BWD_VEC * 4 + 4 * 128 * 4;
 constexpr int BWD_SMEM = BWD_OFF_BAR + 256 + 1024;
 
 // one 16-column group of a chunk: t1 = S, t2 = dP (fp32 from TMEM) -> xw = split(dS), yw = split(P) as 8 packed hi pairs
 // followed by 8 packed lo pairs.  DQ: the statistics belong to the thread's row; DKV: to the columns (shared memory).
-template <int MODE, bool FULL>
+// EXT (text / audio encoders): `row_bias` / `col_bias` = key-padding bias * log2e of the key (the row in DKV mode, the column in DQ
+// mode); dropout on the probabilities: A = keep ? P / keep_prob : 0, dA = dO V^T, dP = keep ? dA / keep_prob : 0,
+// dS = P (dP - delta) scale, and the dV operand is A.  Element index of (query q, key k): idx_base + q_or_k term, see the caller.
+template <int MODE, bool FULL, bool EXT>
 __device__ __forceinline__ void bwd_group(const uint32_t (&t1)[16], const uint32_t (&t2)[16], uint32_t (&xw)[16], uint32_t (&yw)[16], float c2s,
                                           float scale, float row_lse, float row_dsc, const float* __restrict__ col_lse,
-                                          const float* __restrict__ col_dsc, int nvalid) {
+                                          const float* __restrict__ col_dsc, int nvalid, float row_bias, const float* __restrict__ col_bias,
+                                          const DropParams& dr, uint32_t site_key, uint32_t idx0, uint32_t idx_step) {
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     float l0 = row_lse, l1 = row_lse, d0 = row_dsc, d1 = row_dsc;
@@ -375,20 +661,36 @@ __device__ __forceinline__ void bwd_group(const uint32_t (&t1)[16], const uint32
       const float2 d2 = *reinterpret_cast<const float2*>(col_dsc + 2 * e);
       l0 = l2.x; l1 = l2.y; d0 = d2.x; d1 = d2.y;
     }
+    if (EXT) {   // masked keys: bias = -inf -> P = 0 exactly
+      if (MODE == MODE_DQ) {
+        const float2 b2 = *reinterpret_cast<const float2*>(col_bias + 2 * e);
+        l0 -= b2.x; l1 -= b2.y;
+      } else {
+        l0 -= row_bias; l1 -= row_bias;
+      }
+    }
     float pe0 = ex2_approx(fmaf(__uint_as_float(t1[2 * e]), c2s, -l0));
     float pe1 = ex2_approx(fmaf(__uint_as_float(t1[2 * e + 1]), c2s, -l1));
-    float ds0 = pe0 * fmaf(__uint_as_float(t2[2 * e]), scale, -d0);
-    float ds1 = pe1 * fmaf(__uint_as_float(t2[2 * e + 1]), scale, -d1);
+    float dp0 = __uint_as_float(t2[2 * e]), dp1 = __uint_as_float(t2[2 * e + 1]);
+    float a0 = pe0, a1 = pe1;
+    if (EXT && dr.on) {
+      const bool k0 = drop_kept(site_key, idx0 + (uint32_t)(2 * e) * idx_step, dr.thr24);
+      const bool k1 = drop_kept(site_key, idx0 + (uint32_t)(2 * e + 1) * idx_step, dr.thr24);
+      dp0 = k0 ? dp0 * dr.inv_keep : 0.f; dp1 = k1 ? dp1 * dr.inv_keep : 0.f;
+      a0 = k0 ? pe0 * dr.inv_keep : 0.f; a1 = k1 ? pe1 * dr.inv_keep : 0.f;
+    }
+    float ds0 = pe0 * fmaf(dp0, scale, -d0);
+    float ds1 = pe1 * fmaf(dp1, scale, -d1);
     if (!FULL) {
-      if (2 * e >= nvalid) pe0 = 0.f, ds0 = 0.f;
-      if (2 * e + 1 >= nvalid) pe1 = 0.f, ds1 = 0.f;
+      if (2 * e >= nvalid) a0 = 0.f, ds0 = 0.f;
+      if (2 * e + 1 >= nvalid) a1 = 0.f, ds1 = 0.f;
     }
     split2(ds0, ds1, xw[e], xw[8 + e]);
-    if (MODE == MODE_DKV) split2(pe0, pe1, yw[e], yw[8 + e]);
+    if (MODE == MODE_DKV) split2(a0, a1, yw[e], yw[8 + e]);
   }
 }
 
-template <int MODE>
+template <int MODE, bool EXT>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_constant__ CUtensorMap tm_do_r,
                 const __grid_constant__ CUtensorMap tm_qkv_c, const __grid_constant__ CUtensorMap tm_do_c, const AttnBwdParams p) {
@@ -403,15 +705,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
   uint64_t* bar_cfree = bars + 10;  // [BWD_NSTAGE]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   float* vec_lse = reinterpret_cast<float*>(smem + BWD_OFF_VEC);
-  float* vec_delta = vec_lse + 320;
-  float* xch = vec_delta + 320;     // [4][128]
+  float* vec_delta = vec_lse + BWD_VEC;
+  float* vec_bias = vec_delta + BWD_VEC;   // EXT: key bias * log2e per key column (DQ mode)
+  float* xch = vec_bias + BWD_VEC;  // [4][128]
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int D = p.H * HD;
   const int row0 = b * p.N;
-  const int nchunks = (p.NP + 63) / 64;
+  // EXT: keys at or beyond kv_len are padding.  DQ walks key chunks (only the first ceil(kv_len / 64)); DKV walks query chunks
+  // (all of them: padded positions are still queries, bert.py:36-37 pools over them) and a key tile past kv_len has zero gradients.
+  const int kv_len = (EXT && p.ext.kv_len) ? min(max(p.ext.kv_len[b], 1), p.N) : p.N;
+  const int NPk = (kv_len + 15) / 16 * 16;                      // key columns that take part (DQ)
+  const int ncols = MODE == MODE_DQ ? NPk : p.NP;               // chunk columns: keys (DQ) / queries (DKV)
+  const int nchunks = (ncols + 63) / 64;
+  const bool dead = EXT && MODE == MODE_DKV && rt * 128 >= kv_len;   // every key of this tile is padding
   const int64_t stat0 = ((int64_t)b * p.H + h) * p.N;
   unsigned long long* tr = p.trace ? p.trace + (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 48 : nullptr;
   if (tr && threadIdx.x == 0) tr[0] = clock64();
@@ -434,6 +743,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       vec_lse[i] = i < p.N ? p.lse[stat0 + i] * LOG2E : 0.f;
       vec_delta[i] = i < p.N ? p.delta[stat0 + i] * p.scale : 0.f;
     }
+  } else if (EXT) {
+    for (int i = threadIdx.x; i < nchunks * 64; i += blockDim.x)
+      vec_bias[i] = (i < p.N && p.ext.key_bias) ? p.ext.key_bias[(int64_t)b * p.ext.ld_bias + i] * LOG2E : (i < p.N ? 0.f : -INFINITY);
   }
   tc_fence_before();
   __syncthreads();
@@ -446,7 +758,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
   const int c2_col = (MODE == MODE_DQ ? 2 * D : 0) + h * HD;   // C2: V (DQ) / dO (DKV, own matrix)
 
   if (warp == 16) {
-    if (elect_one()) {
+    if (!dead && elect_one()) {
       // ===== TMA producer =====
       mbar_arrive_expect_tx(bar_r, 4 * ROW_TILE_BYTES);
       tma_load_3d(smem + BWD_OFF_R1, &tm_qkv_r, bar_r, r1_col, row0 + rt * 128, 0);  // box planes = 2: hi, lo
@@ -463,7 +775,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       }
     }
   } else if (warp == 17) {
-    if (elect_one()) {
+    if (!dead && elect_one()) {
       // ===== MMA issuer =====
       constexpr uint32_t idesc_t = umma_idesc_bf16(64, 0, 0);        // T = R C^T   (both K-major, K = head dim)
       constexpr uint32_t idesc_a2 = umma_idesc_bf16(128, 0, 1);      // [Acc | cross] += X_hi [C_hi | C_lo]   (C MN-major, K = chunk columns)
@@ -510,7 +822,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
         mbar_wait(&bar_x[s], (j >> 1) & 1);
         tc_fence_after();
         if (tr && j < 5) tr[4 + 4 * j] = clock64();                // X(j) visible to the MMA thread
-        const int ksteps = min(4, (p.NP - j * 64) / 16);
+        const int ksteps = min(4, (ncols - j * 64) / 16);
         const uint32_t xa = tmem + s * 128, ya = xa + 64;
         const uint32_t so = st_i * STAGE_STEP;
 #pragma unroll
@@ -539,6 +851,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float c2s = p.scale * LOG2E;
     float row_lse = 0.f, row_dsc = 0.f;     // lse * log2e, delta * scale of this thread's row (DQ)
+    float row_bias = 0.f;                   // EXT, DKV: key bias * log2e of this thread's key
+    uint32_t site_key = 0, idx_row = 0;     // EXT dropout: element (q, k) of this (sequence, head) has index ((seq_row * H + h) * N + q) * N + k
+    if (EXT) {
+      if (MODE == MODE_DKV && p.ext.key_bias) row_bias = rr < p.N ? p.ext.key_bias[(int64_t)b * p.ext.ld_bias + rr] * LOG2E : -INFINITY;
+      if (p.ext.drop.on) {
+        site_key = drop_site_key(p.ext.drop.seq_key[b], p.ext.drop.site);
+        const uint32_t head0 = ((uint32_t)p.ext.drop.seq_row[b] * (uint32_t)p.H + (uint32_t)h) * (uint32_t)p.N;
+        // DQ: row = query -> base (head0 + q) * N, columns step by 1;  DKV: row = key -> base head0 * N + k, columns (queries) step by N
+        idx_row = MODE == MODE_DQ ? (head0 + (uint32_t)rr) * (uint32_t)p.N : head0 * (uint32_t)p.N + (uint32_t)rr;
+      }
+    }
+    if (dead) {
+      // all keys of this tile are padding: dK = dV = 0
+      if (rr < p.N) {
+        float z16[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) z16[e] = 0.f;
+        store_out16(p.dqkv + (int64_t)(row0 + rr) * p.ld_dqkv + D + h * HD + part * 16, p.dqkv_ps, z16);
+        store_out16(p.dqkv + (int64_t)(row0 + rr) * p.ld_dqkv + 2 * D + h * HD + part * 16, p.dqkv_ps, z16);
+      }
+    } else {
     if (MODE == MODE_DQ) {
       // delta = sum_d dO * O over this head's 64 columns; each of the row's 4 threads sums 16 of them
       float acc = 0.f;
@@ -571,7 +904,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       mbar_wait(&bar_t[s], (j >> 1) & 1);
       tc_fence_after();
       if (tr && threadIdx.x == 0 && j < 5) tr[22 + 4 * j] = clock64();   // T(j) complete
-      if (col0 < p.NP) {
+      if (col0 < ncols) {
         uint32_t t1[16], t2[16], xw[16], yw[16];
         const uint32_t ta = tmem + lane_addr + s * 128 + part * 16;
         tmem_ld_32x32b_x16(ta, t1);
@@ -580,8 +913,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
         // P = exp2(S * scale*log2e - lse*log2e), dS = P * (dP - delta) * scale.  Issue-bound warps: ex2.approx, everything
         // folded into FFMAs, and no per-element predicates — only the last group of the image can hold padding columns, and
         // that case is a separate (warp-uniform) branch, because predicated-off instructions still take issue slots.
-        if (col0 + 16 <= p.N) bwd_group<MODE, true>(t1, t2, xw, yw, c2s, p.scale, row_lse, row_dsc, vec_lse + col0, vec_delta + col0, 16);
-        else bwd_group<MODE, false>(t1, t2, xw, yw, c2s, p.scale, row_lse, row_dsc, vec_lse + col0, vec_delta + col0, p.N - col0);
+        const uint32_t idx0 = MODE == MODE_DQ ? idx_row + (uint32_t)col0 : idx_row + (uint32_t)col0 * (uint32_t)p.N;
+        const uint32_t istep = MODE == MODE_DQ ? 1u : (uint32_t)p.N;
+        if (col0 + 16 <= p.N) bwd_group<MODE, true, EXT>(t1, t2, xw, yw, c2s, p.scale, row_lse, row_dsc, vec_lse + col0, vec_delta + col0, 16, row_bias,
+                                                          vec_bias + col0, p.ext.drop, site_key, idx0, istep);
+        else bwd_group<MODE, false, EXT>(t1, t2, xw, yw, c2s, p.scale, row_lse, row_dsc, vec_lse + col0, vec_delta + col0, p.N - col0, row_bias,
+                                         vec_bias + col0, p.ext.drop, site_key, idx0, istep);
         if (tr && threadIdx.x == 0 && j < 5) tr[23 + 4 * j] = clock64();   // X(j) computed
         tmem_st_32x32b_x16(ta, xw);
         if (MODE == MODE_DKV) tmem_st_32x32b_x16(ta + 64, yw);
@@ -612,6 +949,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_r, const __grid_const
       }
     }
     if (tr && threadIdx.x == 0) tr[43] = clock64();                      // stored
+    }   // !dead
   }
   tc_fence_before();
   __syncthreads();
@@ -627,10 +965,18 @@ static int check_attn_shape(int B, int N, int H, int head_dim, const char* who) 
     set_last_error("%s: head_dim must be 64 (got %d)", who, head_dim);
     return SRW_ERR_UNSUPPORTED;
   }
-  if (N > 272 || N < 16) {
-    set_last_error("%s: 16 <= tokens per image <= 272 supported by the single-pass kernels (got %d)", who, N);
+  if (N > 512 || N < 16) {
+    set_last_error("%s: 16 <= tokens per sequence <= 512 supported (got %d)", who, N);
     return SRW_ERR_UNSUPPORTED;
   }
+  return SRW_OK;
+}
+
+static int fill_ext(AttnExt& e, const float* key_bias, int64_t ld_bias, const int32_t* kv_len, const srw_dropout& drop, int N, const char* who) {
+  e.key_bias = key_bias; e.ld_bias = ld_bias; e.kv_len = kv_len;
+  e.drop = make_drop(drop);
+  SRW_REQUIRE(!kv_len || key_bias, "%s: kv_len needs key_bias (keys past kv_len are only skipped, the bias masks them)", who);
+  SRW_REQUIRE(!key_bias || ld_bias >= N, "%s: ld_bias must be >= N", who);
   return SRW_OK;
 }
 
@@ -646,6 +992,29 @@ extern "C" int srw_attn_fwd(const srw_attn_fwd_args* a, void* stream_) {
   const int NP = (a->N + 15) / 16 * 16;
   const int64_t T = (int64_t)a->B * a->N;
   CUtensorMap tq, tkv;
+  AttnExt ext;
+  if ((rc = fill_ext(ext, a->key_bias, a->ld_bias, a->kv_len, a->drop, a->N, "srw_attn_fwd"))) return rc;
+  if (a->N > 272 || ext.key_bias || ext.drop.on) {
+    // key-streaming kernel (text / audio encoders)
+    if ((rc = make_plane_tmap(&tq, a->qkv, 3 * a->H * HD, T, a->ld_qkv, a->qkv_plane_stride, 128, 2))) return rc;
+    if ((rc = make_plane_tmap(&tkv, a->qkv, 3 * a->H * HD, T, a->ld_qkv, a->qkv_plane_stride, 64, 2))) return rc;
+    SRW_REQUIRE(a->ld_o % 8 == 0 && a->o_plane_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(a->o) & 15) == 0, "srw_attn_fwd: o planes must be 16-byte aligned");
+    static std::once_flag once_s;
+    static cudaError_t attr_err_s = cudaSuccess;
+    std::call_once(once_s, [] { attr_err_s = cudaFuncSetAttribute(attn_fwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM); });
+    SRW_CUDA(attr_err_s);
+    AttnFwdStreamParams sp;
+    sp.B = a->B; sp.N = a->N; sp.H = a->H; sp.NP = NP; sp.scale = a->scale;
+    sp.o = reinterpret_cast<__nv_bfloat16*>(a->o); sp.ld_o = a->ld_o; sp.o_ps = a->o_plane_stride; sp.lse = a->lse; sp.ext = ext;
+    dim3 grid(cdiv(a->N, 128), a->H, a->B);
+    const double pf = 2.0 * a->B * a->H * (double)a->N * a->N * HD;
+    void* prof = prof_begin(SRW_PROF_ATTN_FWD, 2.0 * pf, 4.0 * 4.0 * a->B * a->N * a->H * HD, stream);
+    SRW_CUDA(launch_pdl(attn_fwd_stream_kernel, dim3(grid), dim3(FS_THREADS), FS_SMEM, stream, tq, tkv, sp));
+    prof_end(prof, stream);
+    g_launches++;
+    SRW_LAUNCH_CHECK();
+    return SRW_OK;
+  }
   rc = make_plane_tmap(&tq, a->qkv, 3 * a->H * HD, T, a->ld_qkv, a->qkv_plane_stride, 128, 1);
   if (rc) return rc;
   rc = make_plane_tmap(&tkv, a->qkv, 3 * a->H * HD, T, a->ld_qkv, a->qkv_plane_stride, NP / 2, 1);
@@ -690,8 +1059,10 @@ extern "C" int srw_attn_bwd(const srw_attn_bwd_args* a, void* stream_) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(attn_bwd_kernel<MODE_DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(attn_bwd_kernel<MODE_DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    attr_err = cudaFuncSetAttribute(attn_bwd_kernel<MODE_DQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(attn_bwd_kernel<MODE_DKV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(attn_bwd_kernel<MODE_DQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(attn_bwd_kernel<MODE_DKV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
   });
   SRW_CUDA(attr_err);
   AttnBwdParams p;
@@ -701,16 +1072,29 @@ extern "C" int srw_attn_bwd(const srw_attn_bwd_args* a, void* stream_) {
   p.lse = a->lse; p.delta = a->delta;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(a->dqkv); p.ld_dqkv = a->ld_dqkv; p.dqkv_ps = a->dqkv_plane_stride;
   p.trace = g_attn_bwd_trace;
+  if ((rc = fill_ext(p.ext, a->key_bias, a->ld_bias, a->kv_len, a->drop, a->N, "srw_attn_bwd"))) return rc;
+  const bool ext = p.ext.key_bias || p.ext.drop.on;
   dim3 grid(cdiv(a->N, 128), a->H, a->B);
   // algorithmic backward = 4 products (dP, dV, dQ, dK); the S recomputations are overhead, not counted
   const double pair_flops = 2.0 * a->B * a->H * (double)a->N * a->N * HD;
   void* prof = prof_begin(SRW_PROF_ATTN_BWD, 4.0 * pair_flops, 4.0 * 9.0 * a->B * a->N * a->H * HD, stream);
-  SRW_CUDA(launch_pdl(attn_bwd_kernel<MODE_DQ>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p));
+  if (ext) SRW_CUDA(launch_pdl(attn_bwd_kernel<MODE_DQ, true>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p));
+  else SRW_CUDA(launch_pdl(attn_bwd_kernel<MODE_DQ, false>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p));
   g_launches++;
   SRW_LAUNCH_CHECK();
   if (p.trace) p.trace += (size_t)grid.x * grid.y * grid.z * 48;
-  SRW_CUDA(launch_pdl(attn_bwd_kernel<MODE_DKV>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p));
+  if (ext) SRW_CUDA(launch_pdl(attn_bwd_kernel<MODE_DKV, true>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p));
+  else SRW_CUDA(launch_pdl(attn_bwd_kernel<MODE_DKV, false>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM, stream, qkv_r, do_r, qkv_c, do_c, p));
   prof_end(prof, stream);
+  g_launches++;
+  SRW_LAUNCH_CHECK();
+  return SRW_OK;
+}
+
+extern "C" int srw_attn_mask_prepare(const int64_t* attention_mask, int B, int L, float* key_bias, int64_t ld_bias, int32_t* kv_len, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SRW_REQUIRE(B > 0 && L > 0 && key_bias && kv_len && ld_bias >= L, "srw_attn_mask_prepare: bad args");
+  attn_mask_prepare_kernel<<<B, 256, 0, stream>>>(attention_mask, B, L, key_bias, ld_bias, kv_len);
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;

@@ -135,6 +135,31 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// counter-based dropout (srw_dropout, include/srw.h): element `idx` of dropout site `site` of the sequence with stream key
+// `seq_key` is KEPT iff the top 24 bits of lowbias32(idx + site_key) are below keep * 2^24.  No RNG state: the forward
+// epilogues and every backward kernel regenerate the same bits, and the CPU oracle (oracle/bert_oracle.py) restates it.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t drop_site_key(uint32_t seq_key, uint32_t site) { return lowbias32(seq_key + site * 0x9E3779B9U); }
+__device__ __forceinline__ bool drop_kept(uint32_t site_key, uint32_t idx, uint32_t thr24) { return (lowbias32(idx + site_key) >> 8) < thr24; }
+struct DropParams {          // kernel-side view of srw_dropout
+  const uint32_t* seq_key; const int32_t* seq_row;
+  uint32_t site, thr24; float inv_keep; int on;
+};
+static inline DropParams make_drop(const srw_dropout& d) {
+  DropParams p;
+  p.seq_key = d.seq_key; p.seq_row = d.seq_row; p.site = d.site;
+  p.on = (d.p > 0.0 && d.seq_key != nullptr) ? 1 : 0;
+  const double keep = 1.0 - d.p;
+  p.thr24 = (uint32_t)(keep * 16777216.0);
+  p.inv_keep = p.on ? 1.0f / (float)keep : 1.0f;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------
 // warp / block reductions
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -450,7 +450,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const float* __r
                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                 float* __restrict__ dx, int64_t lddx, int accumulate_dx,
                                                                 float* __restrict__ partial, __nv_bfloat16* __restrict__ dxp, int64_t ldp,
-                                                                int64_t ps, const float* __restrict__ row_scale, int rows_per_scale) {
+                                                                int64_t ps, const float* __restrict__ row_scale, int rows_per_scale,
+                                                                const DropParams dr, int drop_rows_per_seq) {
   pdl_trigger();
   pdl_wait();
   constexpr int COLS = J4 * 128;
@@ -493,7 +494,17 @@ __global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const float* __r
       }
       *dst = v;
       if (dxp) {   // the next GEMM's operand: planes of scale(row) * dx, and its column sums (that layer's bias gradient)
-        const float4 u = make_float4(v.x * sc, v.y * sc, v.z * sc, v.w * sc);
+        float4 u = make_float4(v.x * sc, v.y * sc, v.z * sc, v.w * sc);
+        if (dr.on) {   // post-LN encoders: the gradient entering the dropout in front of the residual add (same bits as the forward)
+          const int sq = row / drop_rows_per_seq;
+          const uint32_t key = drop_site_key(dr.seq_key[sq], dr.site);
+          const uint32_t base = ((uint32_t)dr.seq_row[sq] * (uint32_t)drop_rows_per_seq + (uint32_t)(row - sq * drop_rows_per_seq)) * (uint32_t)COLS +
+                                (uint32_t)(j * 128 + lane * 4);
+          u.x = drop_kept(key, base, dr.thr24) ? u.x * dr.inv_keep : 0.f;
+          u.y = drop_kept(key, base + 1, dr.thr24) ? u.y * dr.inv_keep : 0.f;
+          u.z = drop_kept(key, base + 2, dr.thr24) ? u.z * dr.inv_keep : 0.f;
+          u.w = drop_kept(key, base + 3, dr.thr24) ? u.w * dr.inv_keep : 0.f;
+        }
         uint32_t h0, l0, h1, l1;
         split2(u.x, u.y, h0, l0);
         split2(u.z, u.w, h1, l1);
@@ -679,6 +690,7 @@ extern "C" int srw_layernorm_bwd(const srw_layernorm_bwd_args* a, void* stream_)
   SRW_REQUIRE(!a->dx_planes || (a->ldp > 0 && a->plane_stride > 0), "srw_layernorm_bwd: dx_planes needs ldp / plane_stride");
   SRW_REQUIRE(a->cols % 32 == 0 && a->cols <= 1024, "srw_layernorm_bwd: cols must be a multiple of 32 and <= 1024 (cols=%d)", a->cols);
   const int nblocks = srw_layernorm_bwd_nparts(a->rows);
+  const DropParams dr = make_drop(a->drop);
 #define SRW_LN_BWD(J)                                                                                                             \
   case J:                                                                                                                         \
     SRW_CUDA(launch_pdl(layernorm_bwd_kernel<J>, dim3(nblocks), dim3(256), 0, stream, a->dy, a->lddy, a->x, a->ldx, a->rows, a->gamma, a->mean, a->rstd, a->dx, \
@@ -688,10 +700,12 @@ extern "C" int srw_layernorm_bwd(const srw_layernorm_bwd_args* a, void* stream_)
 #define SRW_LN_BWD_VEC(J4)                                                                                                          \
   SRW_CUDA(launch_pdl(layernorm_bwd_vec_kernel<J4>, dim3(nblocks), dim3(256), 0, stream, a->dy, a->lddy, a->x, a->ldx, a->rows, a->gamma,   \
                       a->mean, a->rstd, a->dx, a->lddx, a->accumulate_dx, a->workspace, reinterpret_cast<__nv_bfloat16*>(a->dx_planes), a->ldp, \
-                      a->plane_stride, a->row_scale, a->rows_per_scale > 0 ? a->rows_per_scale : 1))
+                      a->plane_stride, a->row_scale, a->rows_per_scale > 0 ? a->rows_per_scale : 1, dr, a->drop_rows_per_seq > 0 ? a->drop_rows_per_seq : 1))
   const bool vec_ok = a->lddy % 4 == 0 && a->ldx % 4 == 0 && a->lddx % 4 == 0 && (!a->dx_planes || (a->ldp % 4 == 0 && a->plane_stride % 4 == 0)) &&
                       ((reinterpret_cast<uintptr_t>(a->dy) | reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->dx) |
                         reinterpret_cast<uintptr_t>(a->gamma)) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->dx_planes) & 7) == 0;
+  SRW_REQUIRE(!dr.on || (vec_ok && a->dx_planes && (a->cols == 384 || a->cols == 768 || a->cols == 1024)),
+              "srw_layernorm_bwd: the dropout hand-over needs dx_planes and the vectorised path (cols 384 / 768 / 1024, 16-byte aligned)");
   if (vec_ok && a->cols == 384) { SRW_LN_BWD_VEC(3); }
   else if (vec_ok && a->cols == 768) { SRW_LN_BWD_VEC(6); }
   else if (vec_ok && a->cols == 1024) { SRW_LN_BWD_VEC(8); }

@@ -56,6 +56,7 @@ struct EpiParams {
   float* out_f32; int64_t ldo;
   __nv_bfloat16* out_planes; int64_t ldp; int64_t out_plane_stride;
   float* workspace;  // split-K partials [split, M, N]
+  DropParams drop; int drop_rows_per_seq;   // SRW_EPI_RESID: dropout between the dense layer and the residual add
 };
 
 // Apply the fused epilogue to NV consecutive accumulator columns of one row.  NV is 32 (tcgen05 path: one tcgen05.ld
@@ -83,6 +84,13 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
     const float s = p.row_scale ? p.row_scale[row / p.rows_per_scale] : 1.0f;
     const float* r = p.resid + (int64_t)row * p.ldr + col0;
     float* dst = p.out_f32 + (int64_t)row * p.ldo + col0;
+    if (p.drop.on) {
+      const int sq = row / p.drop_rows_per_seq;
+      const uint32_t key = drop_site_key(p.drop.seq_key[sq], p.drop.site);
+      const uint32_t base = ((uint32_t)p.drop.seq_row[sq] * (uint32_t)p.drop_rows_per_seq + (uint32_t)(row - sq * p.drop_rows_per_seq)) * (uint32_t)p.N + (uint32_t)col0;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[j] = drop_kept(key, base + j, p.drop.thr24) ? v[j] * p.drop.inv_keep : 0.f;
+    }
 #pragma unroll
     for (int j = 0; j < NV; j += 4)
       if (col0 + j < p.N) {
@@ -140,9 +148,19 @@ __device__ __forceinline__ void drain_full(const EpiParams& ep, uint32_t acc_add
   const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
   const int row_first = m0 + q * 32 + sub_r;       // this lane's rows: row_first + 4 i
   float scale[8];
+  uint32_t dkey[8], dbase[8];
+  const bool dropping = EPI == SRW_EPI_RESID && ep.drop.on;
   if (EPI == SRW_EPI_RESID) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) scale[i] = ep.row_scale ? ep.row_scale[(row_first + 4 * i) / ep.rows_per_scale] : 1.0f;
+    if (dropping) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = row_first + 4 * i, sq = row / ep.drop_rows_per_seq;
+        dkey[i] = drop_site_key(ep.drop.seq_key[sq], ep.drop.site);
+        dbase[i] = ((uint32_t)ep.drop.seq_row[sq] * (uint32_t)ep.drop_rows_per_seq + (uint32_t)(row - sq * ep.drop_rows_per_seq)) * (uint32_t)ep.N;
+      }
+    }
   }
 #pragma unroll 1
   for (int c = part; c < BN / 32; c += EPI_WARPS / 4) {
@@ -176,6 +194,13 @@ __device__ __forceinline__ void drain_full(const EpiParams& ep, uint32_t acc_add
       }
       if (EPI == SRW_EPI_RESID) {
         const float sc = scale[i];
+        if (dropping) {
+          const uint32_t b0 = dbase[i] + (uint32_t)col;
+          x.x = drop_kept(dkey[i], b0, ep.drop.thr24) ? x.x * ep.drop.inv_keep : 0.f;
+          x.y = drop_kept(dkey[i], b0 + 1, ep.drop.thr24) ? x.y * ep.drop.inv_keep : 0.f;
+          x.z = drop_kept(dkey[i], b0 + 2, ep.drop.thr24) ? x.z * ep.drop.inv_keep : 0.f;
+          x.w = drop_kept(dkey[i], b0 + 3, ep.drop.thr24) ? x.w * ep.drop.inv_keep : 0.f;
+        }
         *reinterpret_cast<float4*>(ep.out_f32 + (int64_t)row * ep.ldo + col) =
             make_float4(fmaf(sc, x.x, pre[i].x), fmaf(sc, x.y, pre[i].y), fmaf(sc, x.z, pre[i].z), fmaf(sc, x.w, pre[i].w));
         continue;
@@ -782,6 +807,8 @@ static int fill_epi(const srw_gemm_args* a, EpiParams& ep) {
   ep.out_f32 = a->out_f32; ep.ldo = a->ldo;
   ep.out_planes = reinterpret_cast<__nv_bfloat16*>(a->out_planes); ep.ldp = a->ldp; ep.out_plane_stride = a->out_plane_stride;
   ep.workspace = a->workspace;
+  ep.drop = make_drop(a->drop); ep.drop_rows_per_seq = a->drop_rows_per_seq > 0 ? a->drop_rows_per_seq : 1;
+  SRW_REQUIRE(!ep.drop.on || a->epilogue == SRW_EPI_RESID, "srw_gemm: dropout is part of SRW_EPI_RESID only");
   SRW_REQUIRE(a->N % 4 == 0, "srw_gemm: N must be a multiple of 4 (N=%d)", a->N);
   switch (a->epilogue) {
     case SRW_EPI_F32: SRW_REQUIRE(a->out_f32 && a->ldo % 4 == 0, "srw_gemm: EPI_F32 needs out_f32, ldo%%4==0"); break;

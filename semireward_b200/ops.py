@@ -59,7 +59,7 @@ def split_planes(x: torch.Tensor, transposed: bool = False, row_scale: torch.Ten
 
 def gemm(a: Planes, b: Planes, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False, epilogue: int = L.EPI_F32,
          bias=None, resid=None, row_scale=None, rows_per_scale: int = 1, aux=None, out_f32=None, out_planes: Planes | None = None,
-         split_k: int = 1, workspace=None, impl: int = L.GEMM_TCGEN05):
+         split_k: int = 1, workspace=None, impl: int = L.GEMM_TCGEN05, drop: L.Dropout | None = None, drop_rows_per_seq: int = 1):
     """D[M,N] = A[M,K] * B[N,K]^T (+ epilogue).  Returns (out_f32, out_planes) as applicable."""
     dev = a.t.device
     if epilogue in (L.EPI_F32, L.EPI_GELU, L.EPI_RESID) and out_f32 is None:
@@ -76,7 +76,8 @@ def gemm(a: Planes, b: Planes, M: int, N: int, K: int, a_mn: bool = False, b_mn:
                    ldo=out_f32.stride(0) if out_f32 is not None else 0,
                    out_planes=out_planes.ptr() if out_planes else None, ldp=out_planes.ld if out_planes else 0,
                    out_plane_stride=out_planes.plane_stride if out_planes else 0, split_k=split_k,
-                   workspace=L.ptr(workspace), impl=impl)
+                   workspace=L.ptr(workspace), impl=impl, drop=drop if drop is not None else dropout_spec(),
+                   drop_rows_per_seq=drop_rows_per_seq)
     L.check(_lib().srw_gemm(C.byref(g), _s()), "srw_gemm")
     if epilogue == L.EPI_SPLITK:
         return workspace
@@ -120,7 +121,8 @@ def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float, want_f32: bool = Tru
     return y, yp, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx=None, accumulate_dx=False, dgamma=None, dbeta=None, accumulate_dparams=False):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx=None, accumulate_dx=False, dgamma=None, dbeta=None, accumulate_dparams=False,
+                  dx_planes: Planes | None = None, colsum_out=None, drop: L.Dropout | None = None, drop_rows_per_seq: int = 1):
     rows, cols = x.shape
     if dx is None:
         dx = torch.empty_like(x)
@@ -131,24 +133,49 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx=None, accumulate_dx=False, dgamma
     a = L.LayerNormBwdArgs(dy=dy.data_ptr(), lddy=dy.stride(0), x=x.data_ptr(), ldx=x.stride(0), rows=rows, cols=cols,
                            gamma=gamma.data_ptr(), mean=mean.data_ptr(), rstd=rstd.data_ptr(), dx=dx.data_ptr(), lddx=dx.stride(0),
                            accumulate_dx=int(accumulate_dx), dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(),
-                           accumulate_dparams=int(accumulate_dparams), workspace=ws.data_ptr())
+                           accumulate_dparams=int(accumulate_dparams), workspace=ws.data_ptr(),
+                           dx_planes=dx_planes.ptr() if dx_planes else None, ldp=dx_planes.ld if dx_planes else 0,
+                           plane_stride=dx_planes.plane_stride if dx_planes else 0, row_scale=None, rows_per_scale=1,
+                           colsum_out=L.ptr(colsum_out), colsum_accumulate=0, drop=drop if drop is not None else dropout_spec(),
+                           drop_rows_per_seq=drop_rows_per_seq)
     L.check(_lib().srw_layernorm_bwd(C.byref(a), _s()), "srw_layernorm_bwd")
     return dx, dgamma, dbeta
 
 
-def attn_fwd(qkv: Planes, B: int, N: int, H: int, head_dim: int = 64):
+def dropout_spec(seq_key=None, seq_row=None, site: int = 0, p: float = 0.0) -> L.Dropout:
+    """srw_dropout: seq_key uint32 (stored as int32/int64 tensors are NOT accepted: pass torch.int32 views of uint32 bits) [S],
+    seq_row int32 [S]; None / p = 0 -> off."""
+    if seq_key is None or p == 0.0:
+        return L.Dropout(seq_key=None, seq_row=None, site=0, p=0.0)
+    assert seq_key.dtype == torch.int32 and seq_row.dtype == torch.int32 and seq_key.is_contiguous() and seq_row.is_contiguous()
+    return L.Dropout(seq_key=seq_key.data_ptr(), seq_row=seq_row.data_ptr(), site=int(site), p=float(p))
+
+
+def attn_mask_prepare(attention_mask, B: int, Lq: int, device="cuda"):
+    """attention_mask int64 [B, L] or None -> (key_bias fp32 [B, ld], kv_len int32 [B])."""
+    ld = (Lq + 63) // 64 * 64
+    bias = torch.empty(B, ld, dtype=torch.float32, device=device)
+    kv = torch.empty(B, dtype=torch.int32, device=device)
+    L.check(_lib().srw_attn_mask_prepare(L.ptr(attention_mask), B, Lq, bias.data_ptr(), ld, kv.data_ptr(), _s()), "srw_attn_mask_prepare")
+    return bias, kv
+
+
+def attn_fwd(qkv: Planes, B: int, N: int, H: int, head_dim: int = 64, key_bias=None, kv_len=None, drop: L.Dropout | None = None):
     """qkv planes [B*N, 3*H*head_dim] -> (o planes [B*N, H*head_dim], lse [B,H,N])."""
     dev = qkv.t.device
     D = H * head_dim
     o = empty_planes(B * N, D, dev)
     lse = torch.empty(B, H, N, dtype=torch.float32, device=dev)
     a = L.AttnFwdArgs(B=B, N=N, H=H, head_dim=head_dim, scale=head_dim ** -0.5, qkv=qkv.ptr(), ld_qkv=qkv.ld,
-                      qkv_plane_stride=qkv.plane_stride, o=o.ptr(), ld_o=o.ld, o_plane_stride=o.plane_stride, lse=lse.data_ptr())
+                      qkv_plane_stride=qkv.plane_stride, o=o.ptr(), ld_o=o.ld, o_plane_stride=o.plane_stride, lse=lse.data_ptr(),
+                      key_bias=L.ptr(key_bias), ld_bias=key_bias.stride(0) if key_bias is not None else 0, kv_len=L.ptr(kv_len),
+                      drop=drop if drop is not None else dropout_spec())
     L.check(_lib().srw_attn_fwd(C.byref(a), _s()), "srw_attn_fwd")
     return o, lse
 
 
-def attn_bwd(qkv: Planes, o: Planes, d_o: Planes, lse: torch.Tensor, B: int, N: int, H: int, head_dim: int = 64):
+def attn_bwd(qkv: Planes, o: Planes, d_o: Planes, lse: torch.Tensor, B: int, N: int, H: int, head_dim: int = 64, key_bias=None, kv_len=None,
+             drop: L.Dropout | None = None):
     dev = qkv.t.device
     D = H * head_dim
     dqkv = empty_planes(B * N, 3 * D, dev)
@@ -156,6 +183,8 @@ def attn_bwd(qkv: Planes, o: Planes, d_o: Planes, lse: torch.Tensor, B: int, N: 
     a = L.AttnBwdArgs(B=B, N=N, H=H, head_dim=head_dim, scale=head_dim ** -0.5, qkv=qkv.ptr(), ld_qkv=qkv.ld,
                       qkv_plane_stride=qkv.plane_stride, o=o.ptr(), ld_o=o.ld, o_plane_stride=o.plane_stride,
                       d_o=d_o.ptr(), ld_do=d_o.ld, do_plane_stride=d_o.plane_stride, lse=lse.data_ptr(), delta=delta.data_ptr(),
-                      dqkv=dqkv.ptr(), ld_dqkv=dqkv.ld, dqkv_plane_stride=dqkv.plane_stride)
+                      dqkv=dqkv.ptr(), ld_dqkv=dqkv.ld, dqkv_plane_stride=dqkv.plane_stride,
+                      key_bias=L.ptr(key_bias), ld_bias=key_bias.stride(0) if key_bias is not None else 0, kv_len=L.ptr(kv_len),
+                      drop=drop if drop is not None else dropout_spec())
     L.check(_lib().srw_attn_bwd(C.byref(a), _s()), "srw_attn_bwd")
     return dqkv

@@ -167,15 +167,20 @@ def test_counter_dropout_masks_are_reproducible_and_unbiased():
     assert abs(float(m3.float().mean()) - 0.9) < 3e-3
     assert 0.15 < float((BO.counter_keep_mask(1 << 18, 0.9, 7, 4) != m3).float().mean()) < 0.21     # 2 * 0.9 * 0.1 for independent sites
     assert torch.equal(BO.counter_keep_mask(1000, 0.9, 7, 3), m3[:1000])                            # element i does not depend on the extent
-    # numpy uint64 restatement of the same hash
-    keep, seed, site, n = 0.9, 7, 3, 4096
-    base = np.uint64((((seed & 0xFFFFFFFF) << 32) ^ (((site & 0xFFFFF) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF)
-    with np.errstate(over="ignore"):
-        x = np.arange(n, dtype=np.uint64) + base + np.uint64(0x9E3779B97F4A7C15)
-        z = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        z = z ^ (z >> np.uint64(31))
-    assert np.array_equal((z >> np.uint64(40)) < np.uint64(int(keep * (1 << 24))), m3[:n].numpy())
+    # scalar restatement of the same 32-bit hash (include/srw.h: srw_dropout; csrc/srw_common.cuh: lowbias32 / drop_kept)
+    def mix(x):
+        x &= 0xFFFFFFFF
+        x ^= x >> 16
+        x = (x * 0x7FEB352D) & 0xFFFFFFFF
+        x ^= x >> 15
+        x = (x * 0x846CA68B) & 0xFFFFFFFF
+        return x ^ (x >> 16)
+    keep, key, site = 0.9, 7, 3
+    sk = mix(key + site * 0x9E3779B9)
+    want = [(mix(i + sk) >> 8) < int(keep * (1 << 24)) for i in range(512)]
+    assert want == m3[:512].tolist()
+    assert torch.equal(BO.counter_keep_mask(100, 0.9, 7, 3, offset=400), m3[400:500])
+    assert BO.call_key(5, 0) != BO.call_key(5, 1) != BO.call_key(6, 1)
     cfg = bert_small_cfg()
     bc = _bert_cfg(cfg, hidden_dropout=0.1, attn_dropout=0.1, pooled_dropout=0.1)
     from semireward_b200 import detgen

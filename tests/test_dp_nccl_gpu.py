@@ -19,7 +19,7 @@ def _worker(rank, world, port, q):
     try:
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
         torch.cuda.set_device(rank)
-        dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         sys.path.insert(0, ROOT)
         from helpers import batch_tensors, build_native, build_oracle, small_cfg

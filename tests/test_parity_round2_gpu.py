@@ -37,6 +37,26 @@ def mask2_report(rec, native_mask2, tag):
     return n
 
 
+def band_report(rec, alg, tag, band=2e-3):
+    """The LAST sampling pass's mask and pseudo-labels (what the unsupervised loss uses).  The native weak logits agree with the
+    oracle's to ~4e-4 (bf16x3 vs fp32), so a sample whose max-probability sits within `band` of its threshold, or whose top-2
+    logits are closer than `band`, may legitimately land on the other side: such samples are counted and printed, every other
+    sample must match bit for bit.  Returns the number of in-band samples that actually differ."""
+    if "dg_mask" not in rec or getattr(alg, "_last_mask_dg", None) is None:
+        return 0
+    nm, npz = alg._last_mask_dg.cpu(), alg._last_pseudo_dg.cpu()
+    top2 = rec["dg_logits_w"].topk(2, dim=-1).values
+    near = (top2[:, 0] - top2[:, 1]) < band
+    if rec.get("dg_gap") is not None:
+        near = near | (rec["dg_gap"].abs() < band)
+    assert torch.equal(npz[~near], rec["dg_pseudo"][~near]), f"{tag}: last-pass pseudo-labels differ away from a top-2 tie"
+    assert torch.equal(nm[~near], rec["dg_mask"][~near]), f"{tag}: last-pass mask differs away from the threshold"
+    flips = int((nm != rec["dg_mask"]).sum() + (npz != rec["dg_pseudo"]).sum())
+    if near.any():
+        print(f"{tag}: {int(near.sum())} samples within {band} of a threshold / top-2 tie in the last pass, {flips} differ")
+    return flips
+
+
 @pytest.mark.parametrize("algorithm,depth,batched", [("srflexmatch", 12, True), ("srflexmatch", 2, False), ("srfreematch", 2, True)])
 def test_droppath_on_steps_vs_oracle(algorithm, depth, batched):
     """drop_path_rate 0.2 (the shipped builders' value, the mode bench.py times).  it 0-1 stage 1 (SR trained on labelled data),
@@ -74,6 +94,7 @@ def test_droppath_on_steps_vs_oracle(algorithm, depth, batched):
             assert abs(ld["train/util_ratio"] - float(rec["util_ratio"])) < 1e-6
             tied = mask2_report(rec, alg._last_mask2, f"{algorithm} d{depth} it {it}")
             ties += tied
+            tied += band_report(rec, alg, f"{algorithm} d{depth} it {it}")
             if not tied:
                 for kn, ko in (("train/unsup_loss", "unsup_loss"), ("train/total_loss", "total_loss")):
                     assert abs(ld[kn] - float(rec[ko])) < 1e-3, f"it {it} {ko}: {ld[kn]} vs {float(rec[ko])}"
@@ -143,6 +164,7 @@ def test_config3_real_per_gpu_shape_step():
         assert abs(ld["train/sup_loss"] - float(rec["sup_loss"])) < 1e-3
         assert abs(hook.time_p.item() - float(orc.hook.time_p)) < 1e-4
         tied = mask2_report(rec, alg._last_mask2, f"config-3 shape it {it}")
+        tied += band_report(rec, alg, f"config-3 shape it {it}")
         if not tied and not thr_gap.any() and not close.any():
             for kn, ko in (("train/unsup_loss", "unsup_loss"), ("train/total_loss", "total_loss")):
                 assert abs(ld[kn] - float(rec[ko])) < 1e-3, f"it {it} {ko}: {ld[kn]} vs {float(rec[ko])}"
