@@ -276,6 +276,66 @@ int srw_set_graph_mode(int on);
  * Changing the mode does not affect CUDA graphs that were already captured. */
 int srw_set_pdl_mode(int on);
 
+/* ---- BERT engine: ClassificationBert.forward (bert.py:22-48) around HF BertModel, as one native call ------------------------ */
+/* Arithmetic restated from transformers 5.5.0 modeling_bert.py (not under /root/reference):
+ *   e = word[ids] + type[0] + pos[:L] -> LayerNorm(eps) -> dropout(p_hidden)                                  (:72-112)
+ *   12 post-LN layers: a = dropout_attn(softmax(q k^T / 8 + key_bias)) v ;  x = LN(dropout(a Wo + bo) + x)     (:287-298)
+ *                      x = LN(dropout(gelu(x W1 + b1) W2 + b2) + x)                                           (:330-356)
+ *   feat = mean over ALL L positions of dropout(x) (padding included, bert.py:36-37); logits = gelu(feat Wc1 + bc1) Wc2 + bc2.
+ * `params` / `grads`: device pointers in ClassificationBert.state_dict() order = embeddings {word, position, token_type,
+ * LayerNorm.w, LayerNorm.b}, per layer {query.w, query.b, key.w, key.b, value.w, value.b, attention.output.dense.w, .b,
+ * attention.output.LayerNorm.w, .b, intermediate.dense.w, .b, output.dense.w, .b, output.LayerNorm.w, .b}, pooler.dense.w, .b
+ * (built by BertModel, executed by the reference but unused by bert.py:35: never read here, no gradient, may be NULL),
+ * classifier.0.w, .b, classifier.2.w, .b  = 5 + 16 * layers + 6 pointers.
+ * Gradient layout requirement: the gradients of query / key / value weights must be contiguous in that order (one [3 hidden,
+ * hidden] matrix), and so must their biases: the three projections run as one GEMM.  The host's flat gradient buffer is laid out
+ * accordingly.  Dropout: counter-based (srw_dropout); sites 0 = embeddings, 1 + 3 l = attention probabilities of layer l,
+ * 2 + 3 l = attention output, 3 + 3 l = FFN output, 1 + 3 layers = pooled features. */
+typedef struct {
+  int vocab_size, max_position, type_vocab, hidden, layers, heads, intermediate, num_classes;
+  float ln_eps;
+  double p_hidden, p_attn, p_pooled;
+} srw_bert_config;
+
+int64_t srw_bert_weight_planes_bytes(const srw_bert_config* c);
+int64_t srw_bert_workspace_bytes(const srw_bert_config* c, int batch, int seq_len, int grad_batch);
+int srw_bert_weight_plane_slot(const srw_bert_config* c, int param_index, int64_t* byte_offset, int* cols, int* ldp, int64_t* plane_stride);
+int srw_bert_prepare_weights(const srw_bert_config* c, const float* const* params, void* weight_planes, void* stream);
+
+typedef struct {
+  const srw_bert_config* cfg;
+  const float* const* params;
+  const void* weight_planes;
+  const int64_t* input_ids; const int64_t* attention_mask;   /* [batch, seq_len] int64; attention_mask may be NULL (all ones) */
+  int batch, seq_len;
+  int grad_batch;                             /* the first grad_batch sequences will be back-propagated */
+  const uint32_t* drop_seq_key; const int32_t* drop_seq_row;   /* [batch] each, or NULL: no dropout (eval mode / deterministic parity mode) */
+  const int32_t* pool_len;                    /* [batch] or NULL (= seq_len): positions the mean pool runs over.  The reference pools over the
+                                                 padded length of EACH of its three calls (bert.py:36-37); when the host pads calls of different
+                                                 length to one seq_len for the concatenated launch, pool_len keeps each call's own length */
+  float* logits; float* feat;                 /* [batch, num_classes], [batch, hidden] */
+  void* workspace; int64_t workspace_bytes;
+  int gemm_impl;
+} srw_bert_fwd_args;
+int srw_bert_forward(const srw_bert_fwd_args* a, void* stream);
+
+typedef struct {
+  const srw_bert_config* cfg;
+  const float* const* params;
+  const void* weight_planes;
+  const int64_t* input_ids; const int64_t* attention_mask;
+  int batch, seq_len, grad_batch;
+  const uint32_t* drop_seq_key; const int32_t* drop_seq_row;
+  const int32_t* pool_len;
+  const float* dlogits; const float* dfeat;   /* [grad_batch, C] and [grad_batch, hidden] (dfeat may be NULL) */
+  float* const* grads;                        /* same order as params; pooler entries are ignored */
+  int accumulate_grads;
+  void* workspace; int64_t workspace_bytes;
+  int gemm_impl;
+  int layer_lo, layer_hi;                     /* layer range, like block_lo / block_hi of the ViT backward; layer_hi < 0 = everything */
+} srw_bert_bwd_args;
+int srw_bert_backward(const srw_bert_bwd_args* a, void* stream);
+
 /* x[i] *= *scale for i < n, where scale is a DEVICE scalar; returns without touching memory when *scale == 1.  Used to
  * apply autograd's upstream gradient of the loss (normally exactly 1, param_update.py:33) to gradients that were
  * computed ahead of loss.backward(). */

@@ -99,6 +99,25 @@ class VitBwdArgs(C.Structure):
                 ("accumulate_grads", i32), ("workspace", vp), ("workspace_bytes", i64), ("gemm_impl", i32), ("block_lo", i32), ("block_hi", i32)]
 
 
+class BertConfig(C.Structure):
+    _fields_ = [("vocab_size", i32), ("max_position", i32), ("type_vocab", i32), ("hidden", i32), ("layers", i32), ("heads", i32),
+                ("intermediate", i32), ("num_classes", i32), ("ln_eps", f32), ("p_hidden", C.c_double), ("p_attn", C.c_double),
+                ("p_pooled", C.c_double)]
+
+
+class BertFwdArgs(C.Structure):
+    _fields_ = [("cfg", C.POINTER(BertConfig)), ("params", C.POINTER(vp)), ("weight_planes", vp), ("input_ids", vp), ("attention_mask", vp),
+                ("batch", i32), ("seq_len", i32), ("grad_batch", i32), ("drop_seq_key", vp), ("drop_seq_row", vp), ("pool_len", vp),
+                ("logits", vp), ("feat", vp), ("workspace", vp), ("workspace_bytes", i64), ("gemm_impl", i32)]
+
+
+class BertBwdArgs(C.Structure):
+    _fields_ = [("cfg", C.POINTER(BertConfig)), ("params", C.POINTER(vp)), ("weight_planes", vp), ("input_ids", vp), ("attention_mask", vp),
+                ("batch", i32), ("seq_len", i32), ("grad_batch", i32), ("drop_seq_key", vp), ("drop_seq_row", vp), ("pool_len", vp),
+                ("dlogits", vp), ("dfeat", vp), ("grads", C.POINTER(vp)), ("accumulate_grads", i32), ("workspace", vp), ("workspace_bytes", i64),
+                ("gemm_impl", i32), ("layer_lo", i32), ("layer_hi", i32)]
+
+
 class RewarderFwdArgs(C.Structure):
     _fields_ = [("B", i32), ("feature_dim", i32), ("label_rows", i32), ("rp", C.POINTER(vp)), ("feats", vp), ("ld_feats", i64),
                 ("labels", vp), ("reward", vp), ("workspace", vp)]
@@ -201,6 +220,12 @@ SYMBOLS = [
     ("srw_vit_prepare_weights", i32, [C.POINTER(VitConfig), C.POINTER(vp), vp, vp]),
     ("srw_vit_forward", i32, [C.POINTER(VitFwdArgs), vp]),
     ("srw_vit_backward", i32, [C.POINTER(VitBwdArgs), vp]),
+    ("srw_bert_weight_planes_bytes", i64, [C.POINTER(BertConfig)]),
+    ("srw_bert_workspace_bytes", i64, [C.POINTER(BertConfig), i32, i32, i32]),
+    ("srw_bert_weight_plane_slot", i32, [C.POINTER(BertConfig), i32, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]),
+    ("srw_bert_prepare_weights", i32, [C.POINTER(BertConfig), C.POINTER(vp), vp, vp]),
+    ("srw_bert_forward", i32, [C.POINTER(BertFwdArgs), vp]),
+    ("srw_bert_backward", i32, [C.POINTER(BertBwdArgs), vp]),
     ("srw_set_graph_mode", i32, [i32]),
     ("srw_set_pdl_mode", i32, [i32]),
     ("srw_scale_inplace", i32, [vp, i64, vp, vp]),

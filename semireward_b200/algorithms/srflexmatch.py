@@ -27,6 +27,15 @@ from .semireward import EMARewarder, Generator, Rewarder, label_dim
 from .utils import SSL_Argument, str2bool
 
 
+def _nrows(x):
+    """Batch rows of an input: image tensor [B, ...] or a text dict {'input_ids': [B, L], ...}."""
+    return (x["input_ids"] if isinstance(x, dict) else x).shape[0]
+
+
+def _device_of(x):
+    return (x["input_ids"] if isinstance(x, dict) else x).device
+
+
 class _SSLLoss(torch.autograd.Function):
     """total_loss with a grad_fn: forward evaluates srw_ssl_loss (which also writes d total / d logits), backward hands
     those gradients to the two logit tensors (they may come from two different backbone passes in stage 2)."""
@@ -89,7 +98,7 @@ class _PrecomputedGrads(torch.autograd.Function):
         flat, views = net._flat_grads, net._grad_views
         g = g.to(torch.float32).contiguous()
         L.check(L.load().srw_scale_inplace(flat.data_ptr(), flat.numel(), g.data_ptr(), L.stream_ptr()), "srw_scale_inplace")
-        for p, v in zip(net._ordered_params(), views):
+        for p, v in zip(net._grad_params(), views):
             if p.grad is None:
                 p.grad = v
             else:
@@ -172,6 +181,8 @@ class SRFlexMatch(AlgorithmBase):
 
     def _stochastic_backbone(self):
         m = self.model.module if hasattr(self.model, "module") else self.model
+        if hasattr(m, "stochastic"):
+            return m.stochastic()
         return m.training and max(getattr(m, "drop_path_rates", [0.0])) > 0.0
 
     def _mask_and_pseudo(self, logits_w, idx_ulb, first_pass=True):
@@ -243,15 +254,17 @@ class SRFlexMatch(AlgorithmBase):
 
     def _backbone_native(self, x_lb, x_ulb_w, x_ulb_s, need_grad=True, drop_scale=None):
         """Autograd-free pass on the net's persistent buffers -> (logits, feats, handle), split as (lb, weak, strong).
-        drop_scale: DropPath multipliers [depth, 2, nl + 2 nu] in engine row order (lb, strong, weak), or None to draw."""
+        drop_scale: the launch's stochastic-regularisation streams in engine row order (lb, strong, weak) from net.streams_for()
+        (DropPath multipliers for a ViT, dropout stream keys for BERT), or None to draw one fresh pass."""
         # use_cat: False makes the reference call the model three times (lb, strong with grad; weak under no_grad,
-        # srflexmatch.py:119-130).  For a LayerNorm backbone rows do not interact, so the one batched call below computes the
-        # same numbers; the weak rows carry no gradient either way.  (The BERT / HuBERT wrappers that need use_cat: False for
-        # their dict / ragged inputs are not built: get_net_builder raises for them.)
+        # srflexmatch.py:119-130).  For a LayerNorm backbone rows do not interact, so the one batched launch below computes the
+        # same numbers; the weak rows carry no gradient either way.  Text batches are dicts {'input_ids', 'attention_mask'}.
         net = self._net()
-        nl, nu = x_lb.shape[0], x_ulb_s.shape[0]
-        xb = net.input_buffer((nl + 2 * nu,) + tuple(x_lb.shape[1:]), x_lb.device)
-        torch.cat((x_lb, x_ulb_s, x_ulb_w), out=xb)
+        nl, nu = _nrows(x_lb), _nrows(x_ulb_s)
+        dev = _device_of(x_lb)
+        if drop_scale is None and net.stochastic():
+            drop_scale = net.streams_for(net.draw_streams(1, nl, nu, dev), [(0, "lb"), (0, "s"), (0, "w")], nl, nu, dev)
+        xb = net.concat_inputs([x_lb, x_ulb_s, x_ulb_w], dev)
         lg, ft, handle = net.forward_native(xb, grad_batch=(nl + nu) if need_grad else 0, drop_scale=drop_scale)
         return (lg[:nl], lg[nl + nu:], lg[nl:nl + nu]), (ft[:nl], ft[nl + nu:], ft[nl:nl + nu]), handle
 
@@ -263,16 +276,12 @@ class SRFlexMatch(AlgorithmBase):
         batch_stochastic_passes in the ctor).  Engine rows: [lb (pass 0) | strong (pass K) | strong (pass 0) | weak (pass 0..K)];
         the first two groups (three when the algorithm adds a loss term on pass 0's strong logits) carry gradient."""
         self._sr_wait()
-        net, dev = self._net(), x_lb.device
-        nl, nu, K = x_lb.shape[0], x_ulb_s.shape[0], self.sr_decay()
-        per = nl + 2 * nu
-        # DropPath multipliers for every (pass, row) the reference would draw, passes in order, rows in engine order (lb, s, w)
-        full = net._draw_drop_scale((K + 1) * per, dev).view(-1, 2, K + 1, per)
-        cols = [full[:, :, 0, :nl], full[:, :, K, nl:nl + nu], full[:, :, 0, nl:nl + nu]] + [full[:, :, k, nl + nu:] for k in range(K + 1)]
-        ds = torch.cat(cols, dim=2)
-        rows = nl + 2 * nu + (K + 1) * nu
-        xb = net.input_buffer((rows,) + tuple(x_lb.shape[1:]), dev)
-        torch.cat([x_lb, x_ulb_s, x_ulb_s] + [x_ulb_w] * (K + 1), out=xb)
+        net, dev = self._net(), _device_of(x_lb)
+        nl, nu, K = _nrows(x_lb), _nrows(x_ulb_s), self.sr_decay()
+        # the streams (DropPath multipliers / dropout keys) of every (pass, row) the reference would draw, passes in order
+        draws = net.draw_streams(K + 1, nl, nu, dev)
+        ds = net.streams_for(draws, [(0, "lb"), (K, "s"), (0, "s")] + [(k, "w") for k in range(K + 1)], nl, nu, dev)
+        xb = net.concat_inputs([x_lb, x_ulb_s, x_ulb_s] + [x_ulb_w] * (K + 1), dev)
         extra = self._has_extra_loss()
         gb = nl + (2 * nu if extra else nu)
         lg, ft, h = net.forward_native(xb, grad_batch=gb, drop_scale=ds)
@@ -301,7 +310,7 @@ class SRFlexMatch(AlgorithmBase):
             self._sr_update_async(f_w[0], pseudo_label)
         net.backward_native(h, dl)
         net.allreduce_grads_()
-        total_loss = _PrecomputedGrads.apply(losses[2], net, net.cls_token)
+        total_loss = _PrecomputedGrads.apply(losses[2], net, net._grad_params()[0])
         copied.synchronize()
         sup, unsup, total, _ = host[:4].tolist()
         out_dict = self.process_out_dict(loss=total_loss, feat=feat_dict)
@@ -317,13 +326,14 @@ class SRFlexMatch(AlgorithmBase):
             return self._train_step_stage2_batched(x_lb, y_lb, idx_ulb, x_ulb_w, x_ulb_s)
         self._sr_wait()
         net = self._net()
-        dev = x_lb.device
-        nl, nu = x_lb.shape[0], x_ulb_s.shape[0]
+        dev = _device_of(x_lb)
+        nl, nu = _nrows(x_lb), _nrows(x_ulb_s)
         full = None
-        if stochastic2 and self._stochastic_backbone():   # same draw layout as the batched route: [depth, 2, pass, (lb, s, w) rows]
-            full = net._draw_drop_scale((self.sr_decay() + 1) * (nl + 2 * nu), dev).view(-1, 2, self.sr_decay() + 1, nl + 2 * nu)
+        one_pass = [(0, "lb"), (0, "s"), (0, "w")]
+        if stochastic2 and self._stochastic_backbone():   # same draws as the batched route: every pass of the step up front
+            full = net.draw_streams(self.sr_decay() + 1, nl, nu, dev)
         (logits_lb, logits_w, logits_s), (feats_lb, feats_w, feats_s), h0 = self._backbone_native(
-            x_lb, x_ulb_w, x_ulb_s, drop_scale=None if full is None else full[:, :, 0].contiguous())
+            x_lb, x_ulb_w, x_ulb_s, drop_scale=None if full is None else net.streams_for(full, one_pass, nl, nu, dev))
         feat_dict = {"x_lb": feats_lb, "x_ulb_w": feats_w, "x_ulb_s": feats_s}
         y_lb = y_lb.to(torch.long)
         mask, pseudo_label = self._mask_and_pseudo(logits_w, idx_ulb, first_pass=True)
@@ -337,7 +347,8 @@ class SRFlexMatch(AlgorithmBase):
             for k in range(K):
                 if stochastic:   # the reference re-runs the backbone every pass; only the last pass's graph survives
                     (_, l_w, l_s), (_, f_w, _), h = self._backbone_native(
-                        x_lb, x_ulb_w, x_ulb_s, need_grad=(k == K - 1), drop_scale=None if full is None else full[:, :, k + 1].contiguous())
+                        x_lb, x_ulb_w, x_ulb_s, need_grad=(k == K - 1),
+                        drop_scale=None if full is None else net.streams_for(full, [(k + 1, pt) for _, pt in one_pass], nl, nu, dev))
                     h_last = h if k == K - 1 else None
                 else:
                     l_w, f_w = logits_w, feats_w
@@ -379,7 +390,7 @@ class SRFlexMatch(AlgorithmBase):
             net.backward_native(h0, dl0, final=False)
             net.backward_native(h_last, dl1, accumulate=True)
         net.allreduce_grads_()
-        total_loss = _PrecomputedGrads.apply(losses[2], net, net.cls_token)   # one parameter anchors the node in the graph
+        total_loss = _PrecomputedGrads.apply(losses[2], net, net._grad_params()[0])   # one parameter anchors the node in the graph
         copied.synchronize()                        # the device is busy with the backward while the host reads these
         sup, unsup, total, util = host[:4].tolist()
         if self.it > self.start_timing:

@@ -21,7 +21,11 @@ def _layer_id(name: str, matcher: dict) -> int | None:
     patterns tagged (99999,) (the final norm) join the last block group, everything unmatched (head) -> last+1."""
     if re.match(matcher["stem"], name):
         return 0
-    for pat, tag in matcher["blocks"]:
+    blocks = matcher["blocks"]
+    if isinstance(blocks, str):   # bert.py:58-60 / hubert.py:51-53: one pattern whose group is the layer index
+        m = re.match(blocks, name)
+        return int(m.group(1)) + 1 if m else None
+    for pat, tag in blocks:
         m = re.match(pat, name)
         if m:
             return ("tail" if tag is not None else int(m.group(1)) + 1)
@@ -88,7 +92,10 @@ class FusedAdamW(torch.optim.Optimizer):
         for g in self.param_groups:   # one launch = one (betas, eps) pair; the reference's groups only differ in lr / weight decay
             if tuple(g["betas"]) != tuple(g0["betas"]) or g["eps"] != g0["eps"]:
                 raise ValueError("FusedAdamW: all param groups must share betas and eps")
-        ps = [p for g in self.param_groups for p in g["params"]]
+        # torch.optim.AdamW skips parameters whose .grad is None (no weight decay, no moments): BERT's pooler, whose output the
+        # wrapper never uses (bert.py:35).  The table is built at the first step, over the parameters that have a gradient then.
+        ps = [p for g in self.param_groups for p in g["params"] if p.grad is not None]
+        self._skipped = sum(1 for g in self.param_groups for p in g["params"] if p.grad is None)
         dev = ps[0].device
         total = sum(p.numel() for p in ps)
         self._m_flat = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -98,6 +105,11 @@ class FusedAdamW(torch.optim.Optimizer):
             planes = self._net._weight_planes()  # allocates + fills the cache once
             lib = L.load()
             for idx, p in enumerate(self._net._ordered_params()):
+                if hasattr(self._net, "weight_plane_slot"):
+                    sl = self._net.weight_plane_slot(idx)
+                    if sl is not None:
+                        slot[id(p)] = (planes.data_ptr() + sl[0],) + tuple(sl[1:])
+                    continue
                 off, cols, ldp, ps_ = L.i64(), L.i32(), L.i32(), L.i64()
                 if lib.srw_vit_weight_plane_slot(C.byref(self._net._cfg), idx, C.byref(off), C.byref(cols), C.byref(ldp), C.byref(ps_)) == 0:
                     slot[id(p)] = (planes.data_ptr() + off.value, cols.value, ldp.value, ps_.value)
@@ -106,6 +118,8 @@ class FusedAdamW(torch.optim.Optimizer):
         self._group_of = []
         for gi, g in enumerate(self.param_groups):
             for p in g["params"]:
+                if p.grad is None:
+                    continue
                 r = rows[len(self._group_of)]
                 n = p.numel()
                 m, v = self._m_flat[off:off + n].view_as(p), self._v_flat[off:off + n].view_as(p)
@@ -136,13 +150,13 @@ class FusedAdamW(torch.optim.Optimizer):
     def step(self, closure=None):
         if closure is not None:
             raise NotImplementedError("FusedAdamW.step does not take a closure")
-        if self._rows is None:
+        if self._rows is None or sum(1 for g in self.param_groups for p in g["params"] if p.grad is None) != self._skipped:
             self._build()
         rows = self._rows
         for i, p in enumerate(self._params):
             g = p.grad
             if g is None:
-                raise RuntimeError("FusedAdamW: every parameter must have a gradient (the native backward produces all of them)")
+                raise RuntimeError("FusedAdamW: a parameter lost its gradient between steps")
             if not g.is_contiguous():
                 g = p.grad = g.contiguous()
             grp = self.param_groups[self._group_of[i]]

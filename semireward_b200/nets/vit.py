@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib as L
+from ._native import NativeBackbone
 
 
 class _Attention(nn.Module):  # holder for vit.py:78-107 parameters
@@ -113,7 +114,7 @@ class _VitFunction(torch.autograd.Function):
         return (None, None, None, None) + tuple(grads)
 
 
-class VisionTransformer(nn.Module):
+class VisionTransformer(NativeBackbone, nn.Module):
     def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=1000, global_pool="token", embed_dim=768, depth=12,
                  num_heads=12, mlp_ratio=4.0, qkv_bias=True, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.0,
                  init_values=None, embed_layer=None, norm_layer=None, act_layer=None, block_fn=None):
@@ -141,10 +142,7 @@ class VisionTransformer(nn.Module):
                                 num_heads=num_heads, hidden_dim=int(embed_dim * mlp_ratio), num_classes=num_classes, ln_eps=1e-6)
         self._planes = None
         self._planes_key = None
-        self._keep_cache, self._ws_pool, self._bufs = {}, {}, {}
-        self.dp_overlap_split = 4   # data parallel: number of block ranges of the backward whose gradients are all-reduced while the next range runs (<= 1: off)
-        self._pending_reduce = []
-        self._pa = self._pa_key = self._flat_grads = self._grad_views = self._ga = None
+        self._init_native()
 
     # -- native plumbing ------------------------------------------------------------------------
     def _ordered_params(self):
@@ -200,32 +198,36 @@ class VisionTransformer(nn.Module):
         torch.bernoulli(keep, out=out)
         return out.div_(keep)
 
-    # -- workspace pool / persistent buffers: stable device pointers let the engine replay CUDA graphs (include/srw.h) ----
-    def _acquire_ws(self, wbytes, device):
-        pool = self._ws_pool.setdefault((wbytes, str(device)), [])
-        return pool.pop() if pool else torch.empty(wbytes, dtype=torch.uint8, device=device)
+    # -- uniform surface the SSL step drives every native backbone through (nets/bert.py has the same four methods) ----
+    def stochastic(self):
+        return self.training and max(self.drop_path_rates) > 0.0
 
-    def _release_ws(self, ws):
-        if ws is not None:
-            self._ws_pool.setdefault((ws.numel(), str(ws.device)), []).append(ws)
+    def draw_streams(self, num_passes, nl, nu, device):
+        """DropPath multipliers of `num_passes` backbone passes over (nl labelled, nu strong, nu weak) rows, drawn in the reference's
+        order (one draw per pass over the whole concatenated batch) -> [depth, 2, pass, nl + 2 nu] in engine row order, or None."""
+        if not self.stochastic():
+            return None
+        per = nl + 2 * nu
+        return self._draw_drop_scale(num_passes * per, device).view(-1, 2, num_passes, per)
 
-    def _buf(self, name, shape, device, dtype=torch.float32):
-        key = (name, tuple(shape), str(device), dtype)
-        t = self._bufs.get(key)
-        if t is None:
-            t = self._bufs[key] = torch.empty(shape, dtype=dtype, device=device)
-        return t
+    def streams_for(self, draws, pieces, nl, nu, device):
+        """pieces: [(pass, 'lb' | 's' | 'w'), ...] in launch row order -> [depth, 2, rows] multipliers for that launch."""
+        if draws is None:
+            return None
+        sl = {"lb": slice(0, nl), "s": slice(nl, nl + nu), "w": slice(nl + nu, nl + 2 * nu)}
+        cols = [draws[:, :, ps_, sl[part]] for ps_, part in pieces]
+        return (cols[0] if len(cols) == 1 else torch.cat(cols, dim=2)).contiguous()
 
+    def concat_inputs(self, parts, device):
+        rows = sum(p.shape[0] for p in parts)
+        xb = self.input_buffer((rows,) + tuple(parts[0].shape[1:]), device)
+        torch.cat(list(parts), out=xb)
+        return xb
+
+    # -- persistent I/O buffers: stable device pointers let the engine replay CUDA graphs (include/srw.h) ----
     def input_buffer(self, shape, device):
         """Persistent staging buffer for the batch: `torch.cat(parts, out=net.input_buffer(...))` then forward_native()."""
         return self._buf("x", shape, device)
-
-    def _native_params(self):
-        ps = self._ordered_params()
-        key = tuple(p.data_ptr() for p in ps)
-        if self._pa_key != key:
-            self._pa, self._pa_key = L.ptr_array(ps), key
-        return ps, self._pa
 
     @torch.no_grad()
     def forward_native(self, x, grad_batch=0, drop_scale=None):
@@ -263,9 +265,6 @@ class VisionTransformer(nn.Module):
             self.release_pass(handle)
         return lo.clone(), fe.clone(), handle
 
-    def release_pass(self, handle):
-        self._release_ws(handle.pop("ws", None))
-
     def dlogits_buffer(self, grad_batch, device):
         return self._buf("dlogits", (grad_batch, self._cfg.num_classes), device)
 
@@ -276,14 +275,7 @@ class VisionTransformer(nn.Module):
         lib, cfg = L.load(), self._cfg
         Bg, dev = handle["grad_batch"], dlogits.device
         params, pa = self._native_params()
-        if self._flat_grads is None or self._flat_grads.device != dev:
-            numels = [p.numel() for p in params]
-            self._flat_grads = torch.empty(sum(numels), dtype=torch.float32, device=dev)
-            self._grad_views, off = [], 0
-            for p, n in zip(params, numels):
-                self._grad_views.append(self._flat_grads[off:off + n].view_as(p))
-                off += n
-            self._ga = L.ptr_array(self._grad_views)
+        self._ensure_flat_grads(dev)
         dl = self.dlogits_buffer(Bg, dev)
         if dlogits.data_ptr() != dl.data_ptr():
             dl.copy_(dlogits)
@@ -313,37 +305,6 @@ class VisionTransformer(nn.Module):
             L.check(lib.srw_vit_backward(C.byref(a), L.stream_ptr()), "srw_vit_backward")
         self.release_pass(handle)
         return self._flat_grads, self._grad_views
-
-    def _dp_bounds(self, depth):
-        """Descending lower block bounds of all but the last range: dp_overlap_split = k -> k ranges of ~depth/k blocks."""
-        k = int(self.dp_overlap_split)
-        if k <= 1 or depth < 2:
-            return []
-        k = min(k, depth)
-        return sorted({(depth * i) // k for i in range(1, k)} - {0}, reverse=True)
-
-    @staticmethod
-    def _allreduce_async(t, group):
-        import torch.distributed as dist
-        if dist.get_backend(group) == "nccl":
-            return (dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group, async_op=True), None)
-        return (dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True), (t, dist.get_world_size(group)))   # gloo: no AVG
-
-    def allreduce_grads_(self):
-        """Average the flat gradient over the data-parallel group (C1 in SURVEY.md §2.1); completes the overlapped
-        all-reduces backward_native() already started, or runs one all-reduce of the whole buffer."""
-        group = getattr(self, "_dp_group", None)
-        if group is None or self._flat_grads is None:
-            return
-        pending, self._pending_reduce = getattr(self, "_pending_reduce", []), []
-        if pending:
-            for work, post in pending:
-                work.wait()            # the current stream waits for NCCL's stream
-                if post is not None:
-                    post[0].div_(post[1])
-            return
-        from ..parallel import allreduce_mean_
-        allreduce_mean_(self._flat_grads, group)
 
     def _run(self, x, grad_batch=None, drop_scale=None):
         if not x.is_cuda:

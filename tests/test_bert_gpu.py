@@ -1,0 +1,209 @@
+"""-m gpu: the text path (BASELINE configs[3]) — native ClassificationBert (srw_bert_forward / srw_bert_backward)
+and the SSL step with `use_cat: False` against oracle/bert_oracle.py, which is pinned to the live reference + Hugging Face BertModel
+(tests/test_bert_oracle.py).  Gates: logits / feat / losses 1e-3, pseudo-labels and 0/1 masks bit-exact, gradients 1e-3 relative;
+stochastic passes are compared with the SAME counter-based dropout bits on both sides."""
+import functools
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from golden_cases import BERT_SMALL, bert_small_cfg
+
+pytestmark = pytest.mark.gpu
+
+
+def _bert_cfg(cfg, **over):
+    from oracle import bert_oracle as BO
+    kw = dict(vocab_size=BERT_SMALL["vocab_size"], layers=BERT_SMALL["layers"], max_position=BERT_SMALL["max_position"], hidden_dropout=0.0,
+              attn_dropout=0.0, pooled_dropout=0.0, num_classes=cfg["num_classes"])
+    kw.update(over)
+    return BO.BertCfg(**kw)
+
+
+def _step_cfg(cfg):
+    from oracle import ssl_oracle as O
+    return O.StepConfig(algorithm=cfg["algorithm"], num_classes=cfg["num_classes"], ulb_dest_len=cfg["ulb_dest_len"], p_cutoff=cfg["p_cutoff"],
+                        thresh_warmup=cfg["thresh_warmup"], start_timing=cfg["start_timing"], N_k=cfg["N_k"], num_train_iter=cfg["num_train_iter"],
+                        num_warmup_iter=cfg["num_warmup_iter"], lr=cfg["lr"], weight_decay=cfg["weight_decay"], layer_decay=cfg["layer_decay"],
+                        sr_lr=cfg["sr_lr"], feature_dim=cfg["feature_dim"], ema_p=cfg.get("ema_p", 0.999), n_sigma=cfg.get("n_sigma", 2))
+
+
+def _text_batch(cfg, it, max_length, vocab, seed=1):
+    from semireward_b200 import detgen
+    b = detgen.nlp_batch(cfg["batch_size"], cfg["uratio"], cfg["num_classes"], cfg["ulb_dest_len"], max_length=max_length, vocab_size=vocab, seed=seed, step=it)
+    return {k: ({kk: torch.from_numpy(vv) for kk, vv in v.items()} if isinstance(v, dict) else torch.from_numpy(v)) for k, v in b.items()}
+
+
+def _build_native(cfg, bc, head_gain, seed=0):
+    import semireward_b200 as S
+    from semireward_b200 import detgen
+    args = S.get_config(dict(cfg, gpu=0))
+    builder = functools.partial(S.get_net_builder("bert_base_uncased"), vocab_size=bc.vocab_size, num_hidden_layers=bc.layers,
+                                max_position_embeddings=bc.max_position, hidden_dropout_prob=bc.hidden_dropout,
+                                attention_probs_dropout_prob=bc.attn_dropout, pooled_dropout=bc.pooled_dropout)
+    alg = S.get_algorithm(args, builder, None, None)
+    with torch.no_grad():
+        for prefix, mod in (("", alg.model), ("rewarder.", alg.rewarder), ("generator.", alg.generator)):
+            for n, p in mod.named_parameters():
+                p.copy_(torch.from_numpy(detgen.fill_param(prefix + n, p.shape, seed)))
+                if prefix == "" and n == "classifier.2.weight":
+                    p.mul_(head_gain)
+    alg.model = alg.model.cuda(0).train()
+    alg.rewarder, alg.generator = alg.rewarder.cuda(0), alg.generator.cuda(0)
+    return alg
+
+
+def _cuda_text(x):
+    return {k: v.cuda() for k, v in x.items()}
+
+
+@pytest.mark.parametrize("layers,Lq,S,drop", [(2, 32, 4, 0.0), (2, 64, 3, 0.1), (3, 512, 2, 0.0), (2, 200, 2, 0.1)])
+def test_bert_backbone_forward_backward_vs_oracle(layers, Lq, S, drop):
+    """ClassificationBert forward + backward on one batch with padding tails (and a masked hole); with dropout on, both sides use
+    the counter masks of stream key call_key(seed, 0)."""
+    from oracle import bert_oracle as BO
+    from semireward_b200 import detgen
+    from semireward_b200.nets.bert import call_key
+    cfg = bert_small_cfg(num_classes=3)
+    bc = _bert_cfg(cfg, layers=layers, max_position=max(64, Lq), hidden_dropout=drop, attn_dropout=drop, pooled_dropout=drop)
+    alg = _build_native(cfg, bc, 1.0)
+    net = alg.model
+    p = {n: torch.from_numpy(detgen.fill_param(n, s, 0)).requires_grad_(True) for n, s in bc.param_shapes()}
+    x = _text_batch(dict(cfg, batch_size=S), 0, Lq, bc.vocab_size)["x_lb"]
+    x["attention_mask"][0, 3] = 0          # a hole: general masks, not only trailing padding
+    assert BO.call_key(7, 0) == call_key(7, 0)
+    logits_ref, feat_ref = BO.bert_forward(p, x, bc, BO.BertDropout(bc, BO.call_key(7, 0), drop > 0))
+    g = torch.Generator().manual_seed(3)
+    dlog = torch.randn(S, 3, generator=g)
+    dft = torch.randn(S, 768, generator=g) * 0.01
+    (logits_ref * dlog).sum().add((feat_ref * dft).sum()).backward()
+    net.dropout_seed = 7
+    dev = torch.device("cuda")
+    inp = net.concat_inputs([_cuda_text(x)], dev)
+    spec = net.streams_for(net.draw_streams(1, S, 0, dev), [(0, "lb")], S, 0, dev)
+    assert (spec is None) == (drop == 0.0)
+    lg, ft, h = net.forward_native(inp, grad_batch=S, drop_scale=spec)
+    torch.cuda.synchronize()
+    e_l, e_f = (lg.cpu() - logits_ref.detach()).abs().max().item(), (ft.cpu() - feat_ref.detach()).abs().max().item()
+    print(f"layers {layers} L {Lq} drop {drop}: logits err {e_l:.2e} feat err {e_f:.2e}")
+    assert e_l < 1e-3 and e_f < 1e-3
+    flat, views = net.backward_native(h, dlog.cuda(), dfeat=dft.cuda())
+    torch.cuda.synchronize()
+    names = {id(q): n for n, q in net.named_parameters()}
+    worst, worst_n = 0.0, ""
+    for q, v in zip(net._grad_params(), views):
+        n = names[id(q)]
+        gr = p[n].grad
+        sc = gr.abs().max().item()
+        err = (v.cpu() - gr).abs().max().item() / max(sc, 1e-12)
+        if sc < 1e-9:      # mathematically zero gradients (the key bias): absolute check
+            assert v.abs().max().item() < 1e-6, n
+            continue
+        if err > worst:
+            worst, worst_n = err, n
+    print(f"   worst gradient rel err {worst:.2e} ({worst_n})")
+    assert worst < 1e-3, (worst, worst_n)
+    assert p["bert.pooler.dense.weight"].grad is None                       # and the native flat buffer has no slot for it
+    assert views[0][0].abs().max().item() == 0.0                            # padding row of the word embeddings: no gradient
+
+
+@pytest.mark.parametrize("algorithm,over,hg,drop", [("srsoftmatch", dict(num_classes=2), 4.0, 0.0), ("srfixmatch", dict(num_classes=4, p_cutoff=0.85), 3.0, 0.0),
+                                                    ("srsoftmatch", dict(num_classes=2), 4.0, 0.1)])
+def test_bert_ssl_steps_vs_oracle(algorithm, over, hg, drop):
+    """SRSoftMatch / SRFixMatch steps with `use_cat: False` on the text backbone: stage 1, the gap step, stage 2 with and without an SR
+    update.  drop = 0.1: every dropout site on, the same counter streams on both sides (three calls per pass, K passes in stage 2:
+    the native batched route against the oracle's sequential passes)."""
+    from oracle import bert_oracle as BO
+    from test_train_step_gpu import _grad_tap, _mask2_tie
+    cfg = bert_small_cfg(algorithm=algorithm, ema_p=0.9, num_train_iter=16, start_timing=2, **over)
+    bc = _bert_cfg(cfg, hidden_dropout=drop, attn_dropout=drop, pooled_dropout=drop)
+    orc = BO.build_det_bert_oracle(bc, _step_cfg(cfg), seed=0, head_gain=hg, stochastic=drop > 0)
+    alg = _build_native(cfg, bc, hg)
+    if drop > 0:
+        orc.drop_gen = 5
+        alg.model.dropout_seed = 5
+    tap = _grad_tap(alg)
+    for it in range(6):
+        batch = _text_batch(cfg, it, BERT_SMALL["max_length"], bc.vocab_size)
+        rec = orc.train_step({k: (dict(v) if isinstance(v, dict) else v) for k, v in batch.items()}, it)
+        ref_grads = orc.param_update()
+        alg.it = it
+        alg.out_dict, alg.log_dict = alg.train_step(**alg.process_batch(**batch))
+        alg.call_hook("after_train_step")
+        torch.cuda.synchronize()
+        ld = alg.log_dict
+        assert abs(ld["train/sup_loss"] - float(rec["sup_loss"])) < 1e-3, (it, ld, float(rec["sup_loss"]))
+        assert torch.equal(alg._last_pseudo_label.cpu(), rec["pseudo"]), f"it {it}: pseudo labels differ"
+        if algorithm == "srfixmatch":
+            assert torch.equal(alg._last_mask.cpu(), rec["mask"]), f"it {it}: mask differs"
+        else:
+            assert (alg._last_mask.cpu() - rec["mask"]).abs().max().item() < 1e-4, f"it {it}: weights differ"
+        tie = _mask2_tie(rec)
+        if not tie:
+            if "dg_mask2" in rec:
+                assert torch.equal(alg._last_mask2.cpu(), rec["dg_mask2"]), f"it {it}: mask2 differs"
+            for kn, ko in (("train/unsup_loss", "unsup_loss"), ("train/total_loss", "total_loss")):
+                assert abs(ld[kn] - float(rec[ko])) < 1e-3, f"it {it} {ko}: {ld[kn]} vs {float(rec[ko])}"
+            worst = 0.0
+            for n, q in alg.model.named_parameters():
+                gr = ref_grads[n]
+                if gr is None:
+                    assert n not in tap or tap[n] is None or n.startswith("bert.pooler")
+                    continue
+                sc = gr.abs().max().item()
+                if sc < 1e-9:
+                    continue
+                worst = max(worst, (tap[n].cpu() - gr).abs().max().item() / sc)
+            print(f"bert {algorithm} drop {drop} it {it}: total {ld['train/total_loss']:.5f} (oracle {float(rec['total_loss']):.5f}) K {rec.get('K', 0)} grad rel err {worst:.2e}")
+            assert worst < 1e-3, f"it {it}: gradient error {worst}"
+        else:
+            print(f"bert {algorithm} it {it}: rewards tie with their mean (mask2-dependent checks skipped)")
+        with torch.no_grad():   # resync from the oracle
+            for n, q in alg.model.named_parameters():
+                q.copy_(orc.p[n].detach())
+            for n, q in alg.rewarder.named_parameters():
+                q.copy_(orc.rp[n].detach())
+        assert alg.model.bert.pooler.dense.weight.grad is None
+
+
+def test_bert_base_full_size_step():
+    """BASELINE configs[3] at full size: bert-base (12 layers, hidden 768, 12 heads), L = 512, batch 8 + 8 + 8 with padding tails,
+    SRSoftMatch, one stage-1 step (dropout off) against the oracle."""
+    from oracle import bert_oracle as BO
+    from test_train_step_gpu import _grad_tap
+    torch.set_num_threads(os.cpu_count() or 8)
+    cfg = bert_small_cfg(algorithm="srsoftmatch", batch_size=8, ema_p=0.9, num_train_iter=16, start_timing=5)
+    bc = BO.BertCfg(hidden_dropout=0.0, attn_dropout=0.0, pooled_dropout=0.0, num_classes=2)
+    orc = BO.build_det_bert_oracle(bc, _step_cfg(cfg), seed=0, head_gain=4.0)
+    alg = _build_native(cfg, bc, 4.0)
+    tap = _grad_tap(alg)
+    for it in range(2):
+        batch = _text_batch(cfg, it, 512, bc.vocab_size)
+        rec = orc.train_step({k: (dict(v) if isinstance(v, dict) else v) for k, v in batch.items()}, it)
+        ref_grads = orc.param_update()
+        alg.it = it
+        alg.out_dict, alg.log_dict = alg.train_step(**alg.process_batch(**batch))
+        alg.call_hook("after_train_step")
+        torch.cuda.synchronize()
+        ld = alg.log_dict
+        for kn, ko in (("train/sup_loss", "sup_loss"), ("train/unsup_loss", "unsup_loss"), ("train/total_loss", "total_loss")):
+            assert abs(ld[kn] - float(rec[ko])) < 1e-3, f"it {it} {ko}: {ld[kn]} vs {float(rec[ko])}"
+        assert torch.equal(alg._last_pseudo_label.cpu(), rec["pseudo"])
+        assert (alg._last_mask.cpu() - rec["mask"]).abs().max().item() < 1e-4
+        worst, wn = 0.0, ""
+        for n, q in alg.model.named_parameters():
+            gr = ref_grads[n]
+            if gr is None or gr.abs().max().item() < 1e-9:
+                continue
+            e = (tap[n].cpu() - gr).abs().max().item() / gr.abs().max().item()
+            if e > worst:
+                worst, wn = e, n
+        print(f"bert-base L=512 B=8 it {it}: total {ld['train/total_loss']:.5f} (oracle {float(rec['total_loss']):.5f}) grad rel err {worst:.2e} ({wn})")
+        assert worst < 1e-3, (worst, wn)
+        with torch.no_grad():
+            for n, q in alg.model.named_parameters():
+                q.copy_(orc.p[n].detach())
+            for n, q in alg.rewarder.named_parameters():
+                q.copy_(orc.rp[n].detach())

@@ -54,7 +54,8 @@ def test_every_struct_matches_the_header_field_by_field(tmp_path):
                  srw_generator_fwd_args="GeneratorFwdArgs", srw_rewarder_train_args="RewarderTrainArgs", srw_flexmatch_mask_args="FlexMatchMaskArgs",
                  srw_ssl_loss_args="SslLossArgs", srw_freematch_mask_args="FreeMatchMaskArgs", srw_freematch_entropy_args="FreeMatchEntropyArgs",
                  srw_softmatch_mask_args="SoftMatchMaskArgs", srw_adamw_row="AdamWRow", srw_adamw_args="AdamWArgs", srw_ema_row="EmaRow",
-                 srw_ema_args="EmaArgs")
+                 srw_ema_args="EmaArgs", srw_dropout="Dropout", srw_bert_config="BertConfig", srw_bert_fwd_args="BertFwdArgs",
+                 srw_bert_bwd_args="BertBwdArgs")
     hdr = open(os.path.join(ROOT, "include", "srw.h")).read()
     assert set(re.findall(r"}\s*(srw_[a-z0-9_]+);", hdr)) == set(pairs), "a struct of include/srw.h has no ctypes mirror in this table"
     lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "srw.h"', "int main(void) {"]

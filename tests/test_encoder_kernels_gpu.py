@@ -45,7 +45,8 @@ def test_streaming_attention_mask_dropout_fwd_bwd(ops, B, N, H, masked, p):
         am = am.cuda()
     bias, kv = (ops.attn_mask_prepare(am, B, N) if masked else (None, None))
     keys, rows = [0x9E3779B1 * (i + 3) & 0xFFFFFFFF for i in range(B)], [(5 * i + 2) % 7 for i in range(B)]
-    drop = ops.dropout_spec(_i32(keys), torch.tensor(rows, dtype=torch.int32).cuda(), site=4, p=p) if p else None
+    tk, trw = _i32(keys), torch.tensor(rows, dtype=torch.int32).cuda()   # the spec only borrows their device pointers: keep them alive
+    drop = ops.dropout_spec(tk, trw, site=4, p=p) if p else None
     o, lse = ops.attn_fwd(pq, B, N, H, key_bias=bias, kv_len=kv, drop=drop)
     torch.cuda.synchronize()
     if masked:
@@ -88,7 +89,8 @@ def test_resid_epilogue_dropout(ops):
     A, B, bias, resid = _rand(M, K, seed=5), _rand(N, K, seed=6, scale=0.05), _rand(N, seed=7), _rand(M, N, seed=8)
     pa, pb = ops.split_planes(A), ops.split_planes(B)
     keys, rows = [11, 11, 11, 977, 977], [0, 1, 2, 0, 1]       # two "calls": rows 0..2 of stream 11, rows 0..1 of stream 977
-    drop = ops.dropout_spec(_i32(keys), torch.tensor(rows, dtype=torch.int32).cuda(), site=2, p=0.1)
+    tk, trw = _i32(keys), torch.tensor(rows, dtype=torch.int32).cuda()
+    drop = ops.dropout_spec(tk, trw, site=2, p=0.1)
     out, _ = ops.gemm(pa, pb, M, N, K, epilogue=L.EPI_RESID, bias=bias, resid=resid, drop=drop, drop_rows_per_seq=Lq)
     torch.cuda.synchronize()
     z = A.double() @ B.double().t() + bias.double()
@@ -106,7 +108,8 @@ def test_layernorm_bwd_dropout_handover(ops):
     y, _, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-12, want_f32=True)
     dy = _rand(rows, cols, seed=14)
     keys, srows = [123456789, 123456789, 42], [4, 5, 0]
-    drop = ops.dropout_spec(_i32(keys), torch.tensor(srows, dtype=torch.int32).cuda(), site=9, p=0.1)
+    tk, trw = _i32(keys), torch.tensor(srows, dtype=torch.int32).cuda()
+    drop = ops.dropout_spec(tk, trw, site=9, p=0.1)
     dxp = ops.empty_planes(rows, cols)
     cs = torch.empty(cols, device="cuda")
     dx, dg, db = ops.layernorm_bwd(dy, x, g, mean, rstd, dx_planes=dxp, colsum_out=cs, drop=drop, drop_rows_per_seq=Lq)

@@ -49,8 +49,13 @@ def band_report(rec, alg, tag, band=2e-3):
     near = (top2[:, 0] - top2[:, 1]) < band
     if rec.get("dg_gap") is not None:
         near = near | (rec["dg_gap"].abs() < band)
-    assert torch.equal(npz[~near], rec["dg_pseudo"][~near]), f"{tag}: last-pass pseudo-labels differ away from a top-2 tie"
-    assert torch.equal(nm[~near], rec["dg_mask"][~near]), f"{tag}: last-pass mask differs away from the threshold"
+    info = (f"native mask {nm.tolist()} oracle mask {rec['dg_mask'].tolist()} gap {None if rec.get('dg_gap') is None else rec['dg_gap'].tolist()} "
+            f"native pseudo {npz.tolist()} oracle pseudo {rec['dg_pseudo'].tolist()}")
+    hook = alg.hooks_dict.get("MaskingHook")
+    if hasattr(hook, "time_p"):
+        info += f" native time_p {hook.time_p.item():.6f} p_model[:4] {hook.p_model[:4].tolist()}"
+    assert torch.equal(npz[~near], rec["dg_pseudo"][~near]), f"{tag}: last-pass pseudo-labels differ away from a top-2 tie: {info}"
+    assert torch.equal(nm[~near], rec["dg_mask"][~near]), f"{tag}: last-pass mask differs away from the threshold: {info}"
     flips = int((nm != rec["dg_mask"]).sum() + (npz != rec["dg_pseudo"]).sum())
     if near.any():
         print(f"{tag}: {int(near.sum())} samples within {band} of a threshold / top-2 tie in the last pass, {flips} differ")
@@ -94,6 +99,8 @@ def test_droppath_on_steps_vs_oracle(algorithm, depth, batched):
             assert abs(ld["train/util_ratio"] - float(rec["util_ratio"])) < 1e-6
             tied = mask2_report(rec, alg._last_mask2, f"{algorithm} d{depth} it {it}")
             ties += tied
+            if algorithm == "srfreematch":
+                print(f"   oracle time_p {float(orc.hook.time_p):.6f} p_model[:4] {orc.hook.p_model[:4].tolist()}")
             tied += band_report(rec, alg, f"{algorithm} d{depth} it {it}")
             if not tied:
                 for kn, ko in (("train/unsup_loss", "unsup_loss"), ("train/total_loss", "total_loss")):
