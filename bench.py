@@ -38,6 +38,38 @@ F_FWD_GF = 12.134          # GFLOP per sample forward
 YAML_CFG3 = dict(YAML_CFG, algorithm="srfreematch", net="vit_base_patch16_224", num_classes=1000, batch_size=128, img_size=224,
                  feature_dim=768, use_quantile=True, clip_thresh=False, ema_p=0.999, ent_loss_ratio=0.0001, hard_label=True, T=0.5)
 F_FWD_GF3 = 35.128
+# BASELINE configs[3]: SoftMatch+SemiReward, bert_base_uncased, IMDb-like text: config/usb_nlp/softmatch/softmatch_aclImdb_20_0.yaml
+# (2 classes, use_cat False, max_length 512, AdamW lr 5e-5, layer_decay 0.75) + the SR keys of
+# config/SemiReward/usb_nlp/softmatch/softmatch_ag_news_40_0.yaml:50-55 (SURVEY.md §8d "Config 4"); `--config 4`.
+YAML_CFG4 = dict(algorithm="srsoftmatch", net="bert_base_uncased", optim="AdamW", lr=5e-5, layer_decay=0.75, weight_decay=5e-4,
+                 num_train_iter=102400, num_warmup_iter=5120, start_timing=10000, N_k=10, batch_size=8, uratio=1, num_classes=2,
+                 ulb_dest_len=25000, feature_dim=768, sr_lr=5e-4, sr_ema=False, use_cat=False, amp=False, ema_m=0.0, max_length=512,
+                 ulb_loss_ratio=1.0, clip_grad=0, dist_align=True, dist_uniform=True, ema_p=0.999, n_sigma=2, per_class=False, hard_label=True, T=0.5)
+F_FWD_GF4 = 96.64          # GFLOP per sequence forward at L = 512
+METRICS = {2: "SSL train-step samples/sec (ViT-S CIFAR-100)", 3: "SSL train-step samples/sec (ViT-S CIFAR-100)",
+           4: "SSL train-step samples/sec (BERT-base IMDb)"}
+
+
+def workload_name(config, B, uratio, stage):
+    if config == 2:
+        return f"srflexmatch vit_small_patch2_32 cifar100 batch_size {B} uratio {uratio} stage {stage} (BASELINE configs[1])"
+    if config == 3:
+        return f"srfreematch vit_base_patch16_224 synthetic 224x224 1000 classes batch_size {B} per GPU stage {stage} (BASELINE configs[2])"
+    return f"srsoftmatch bert_base_uncased max_length 512 2 classes batch_size {B} uratio {uratio} stage {stage}, padding tails, dropout 0.1 (BASELINE configs[3])"
+
+
+def config_block(config, B, uratio, stage, world, setup_steps):
+    """The `config` object of the JSON line; both arms (native, reference) print the same keys."""
+    per = B * (1 + 2 * uratio)
+    f = {2: F_FWD_GF, 3: F_FWD_GF3, 4: F_FWD_GF4}[config]
+    return dict(workload=workload_name(config, B, uratio, stage), samples_per_step_per_gpu=per, parallelism=f"dp{world}",
+                drop_path=0.2 if config in (2, 3) else None, dropout=0.1 if config == 4 else None, setup_steps=setup_steps,
+                arithmetic="fp32 semantics: bf16x3 split-precision tcgen05 MMA, fp32 accumulate",
+                l2=("step working set (~1.8 GB of activations at batch 8) >> 126 MB L2; rotating input batches" if config != 4 else
+                    "step working set (~8 GB of activations at batch 8, L 512) >> 126 MB L2; rotating input batches"),
+                launch="CUDA-graph replay of the backbone forward/backward (SRW_GRAPHS) + programmatic dependent launch (SRW_PDL); "
+                       "backward launched inside train_step ahead of the loss read-back",
+                algorithmic_gflop_per_step_per_gpu=B * (3 + 4 * uratio) * f)   # forward on B (1 + 2u) rows + backward (2x) on the B (1 + u) gradient rows
 
 
 def parse():
@@ -50,7 +82,8 @@ def parse():
     ap.add_argument("--stage", type=int, default=1, choices=[1, 2])
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
                     help="BASELINE.json configs index + 1: 2 = headline ViT-S CIFAR-100, 3 = ViT-B/16 224 FreeMatch; 1 (WRN-28-2), 4 (BERT-base) and "
-                         "5 (HuBERT-base) have no CUDA path yet and exist for --impl reference only (CPU oracle timing)")
+                         "5 (HuBERT-base) have no CUDA path yet and exist for --impl reference only (CPU oracle timing); 4 = BERT-base text (native)")
+    ap.add_argument("--no-eager-leg", action="store_true", help="skip the informational torch-eager fp32 leg on the same GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     return ap.parse_args()
@@ -188,39 +221,123 @@ def cpu_reference_run_other(config, steps, warmup):
     return B * (1 + 2 * u) / per_step, per_step, cores, name, what, B * (1 + 2 * u)
 
 
+def cpu_reference_bert(B, u, steps, warmup, dropout):
+    """BASELINE configs[3] on the host cores: the oracle restatement of ClassificationBert + SRSoftMatch step (pinned against the
+    live reference and Hugging Face BertModel, tests/test_bert_oracle.py), bert-base, L = 512.  -> (samples/s, s/step, cores)."""
+    import torch
+    from oracle import bert_oracle as BO, ssl_oracle as O
+    from semireward_b200 import detgen
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c = YAML_CFG4
+    sc = O.StepConfig(algorithm="srsoftmatch", num_classes=c["num_classes"], lr=c["lr"], weight_decay=c["weight_decay"], layer_decay=c["layer_decay"],
+                      feature_dim=768, ulb_dest_len=c["ulb_dest_len"], start_timing=c["start_timing"], N_k=c["N_k"], num_train_iter=c["num_train_iter"],
+                      num_warmup_iter=c["num_warmup_iter"], sr_lr=c["sr_lr"])
+    p = dropout
+    orc = BO.build_det_bert_oracle(BO.BertCfg(num_classes=c["num_classes"], hidden_dropout=p, attn_dropout=p, pooled_dropout=p), sc, seed=0, stochastic=p > 0)
+    orc.drop_gen = torch.Generator().manual_seed(0)
+    times = []
+    for i in range(warmup + steps):
+        b = detgen.nlp_batch(B, u, c["num_classes"], c["ulb_dest_len"], max_length=512, seed=1, step=i)
+        b = {k: ({kk: torch.from_numpy(vv) for kk, vv in v.items()} if isinstance(v, dict) else torch.from_numpy(v)) for k, v in b.items()}
+        t0 = time.perf_counter()
+        orc.train_step(b, 1 + i)
+        orc.param_update()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    per_step = sum(times) / len(times)
+    return B * (1 + 2 * u) / per_step, per_step, cores
+
+
 def main_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    if a.config in (1, 4, 5):
+    note = "one CPU process on the host cores whatever --gpus says (the reference's CPU path does not shard over GPUs)"
+    if a.config in (1, 5):
         steps, warmup = max(1, min(a.steps, 2)), max(0, min(a.warmup, 1))     # tens of seconds per CPU step
         sps, per_step, cores, name, what, samples = cpu_reference_run_other(a.config, steps, warmup)
         print(json.dumps(dict(impl="reference", metric=f"SSL train-step samples/sec ({name})", value=sps, unit="samples/s", n_gpus=a.gpus, steps=steps,
                               warmup=warmup, ms_per_step=per_step * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                              data="synthetic", config=dict(workload=what, samples_per_step=samples),
+                              data="synthetic", config=dict(workload=what, samples_per_step=samples), note=note,
                               cpu_baseline=dict(value=sps, unit="samples/s", cores=cores, kind="port",
                                                 sample=f"{steps} step(s) of the oracle restatement (pinned against the live reference), {warmup} warm-up"),
                               e2e=dict(value=sps, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
         return
-    cfg = dict(YAML_CFG, batch_size=a.batch_size)
-    steps, warmup = max(1, min(a.steps, 8)), max(0, min(a.warmup, 2))   # bounded sample: ~1 s per CPU step, at most 8 + 2 steps
-    sps, per_step, cores = cpu_reference_run(cfg, steps, warmup, a.stage)
-    line = dict(impl="reference", metric="SSL train-step samples/sec (ViT-S CIFAR-100)", value=sps, unit="samples/s", n_gpus=a.gpus,
+    if a.config == 4:
+        steps, warmup = max(1, min(a.steps, 2)), max(0, min(a.warmup, 1))
+        B = a.batch_size
+        sps, per_step, cores = cpu_reference_bert(B, 1, steps, warmup, 0.1)
+        sample = f"{steps} stage-1 step(s) of the oracle restatement at the full batch (dropout 0.1 from torch's CPU generator), {warmup} warm-up"
+    else:
+        cfg = dict(YAML_CFG, batch_size=a.batch_size)
+        steps, warmup = max(1, min(a.steps, 8)), max(0, min(a.warmup, 2))   # bounded sample: ~1 s per CPU step, at most 8 + 2 steps
+        if a.config == 3:
+            raise SystemExit("bench.py --impl reference --config 3: the CPU arm of ViT-B/16 224 at batch 128 is not bounded to minutes; use --config 2")
+        sps, per_step, cores = cpu_reference_run(cfg, steps, warmup, a.stage)
+        sample = f"{steps} stage-{a.stage} steps of the oracle restatement (bit-exact vs the live reference), {warmup} warm-up"
+    line = dict(impl="reference", metric=METRICS[a.config], value=sps, unit="samples/s", n_gpus=a.gpus,
                 steps=steps, warmup=warmup, ms_per_step=per_step * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32", data="synthetic",
-                config=dict(workload=f"srflexmatch vit_small_patch2_32 cifar100 batch_size {a.batch_size} uratio 1 stage {a.stage} (BASELINE configs[1])",
-                            samples_per_step=cfg["batch_size"] * 3),
-                cpu_baseline=dict(value=sps, unit="samples/s", cores=cores, kind="port",
-                                  sample=f"{steps} stage-{a.stage} steps of the oracle restatement (bit-exact vs the live reference), {warmup} warm-up"),
+                dtype="f32", data="synthetic", config=config_block(a.config, a.batch_size, 1, a.stage, a.gpus, SETUP_STEPS), note=note,
+                cpu_baseline=dict(value=sps, unit="samples/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=sps, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
+# informational leg: the same step in PyTorch eager fp32 on the SAME GPU (TF32 off) — what the reference's own modules would run
+# as on a B200 (cuBLAS sgemm, unfused attention).  Context for the roofline numbers, never the headline or a baseline.
+# ------------------------------------------------------------------------------------------------
+def torch_eager_fp32_leg(cfg, stage, steps=6, warmup=2):
+    import torch
+    from oracle import ssl_oracle as O
+    from semireward_b200 import detgen
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device("cuda")
+    vc = O.ViTConfig(depth=12, num_classes=cfg["num_classes"], drop_path_rate=0.2)
+    sc = O.StepConfig(algorithm="srflexmatch", num_classes=cfg["num_classes"], ulb_dest_len=cfg["ulb_dest_len"], p_cutoff=cfg["p_cutoff"],
+                      thresh_warmup=cfg["thresh_warmup"], start_timing=cfg["start_timing"], N_k=cfg["N_k"], num_train_iter=cfg["num_train_iter"],
+                      num_warmup_iter=cfg["num_warmup_iter"], lr=cfg["lr"], weight_decay=cfg["weight_decay"], layer_decay=cfg["layer_decay"],
+                      sr_lr=cfg["sr_lr"], feature_dim=cfg["feature_dim"])
+    orc = O.build_det_oracle(vc, sc, seed=0)
+    for d in (orc.p, orc.rp, orc.gp):
+        for k in d:
+            d[k] = d[k].detach().to(dev).requires_grad_(True)
+    orc.opt, orc.ropt, orc.gopt = O.AdamState(orc.p, decoupled=True), O.AdamState(orc.rp, decoupled=False), O.AdamState(orc.gp, decoupled=False)
+    orc.hook.selected_label, orc.hook.classwise_acc = orc.hook.selected_label.to(dev), orc.hook.classwise_acc.to(dev)
+    orig = O.draw_drop_path_masks
+    O.draw_drop_path_masks = lambda c, b, g=None: (lambda m: None if m is None else m.to(dev))(orig(c, b, g))
+    try:
+        it0 = 1 if stage == 1 else cfg["start_timing"] + 1 + 8 * cfg["num_train_iter"]
+        batches = [{k: v.to(dev) for k, v in O.to_torch_batch(detgen.ssl_batch(cfg["batch_size"], cfg["uratio"], cfg["num_classes"], cfg["ulb_dest_len"], seed=1, step=i)).items()}
+                   for i in range(4)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(warmup + steps):
+            if i == warmup:
+                torch.cuda.synchronize()
+                e0.record()
+            orc.train_step(dict(batches[i % 4]), it0 + i)
+            orc.param_update()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    finally:
+        O.draw_drop_path_masks = orig
+    samples = cfg["batch_size"] * (1 + 2 * cfg["uratio"])
+    return dict(value=samples / (ms * 1e-3), unit="samples/s", ms_per_step=ms, steps=steps,
+                what="functional torch restatement of the reference step (oracle/ssl_oracle.py) run on cuda:0 in eager fp32, TF32 off: cuBLAS sgemm, "
+                     "unfused attention, torch autograd, per-tensor AdamW, host-side hook bookkeeping — informational only")
+
+
+# ------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------
+SETUP_STEPS = 12
+
+
 def main_native(a):
-    if a.config not in (2, 3):
+    if a.config not in (2, 3, 4):
         raise SystemExit(f"bench.py: BASELINE configs[{a.config - 1}] has no CUDA path yet (DESIGN.md §9); only --impl reference can time it")
     import torch
     import torch.distributed as dist
@@ -239,29 +356,39 @@ def main_native(a):
     lib = L.load()
     L.check(lib.srw_device_check(None, None, None), "srw_device_check")
 
-    base_cfg = YAML_CFG if a.config == 2 else YAML_CFG3
-    bs = a.batch_size if (a.batch_size != 8 or a.config == 2) else base_cfg["batch_size"]
+    base_cfg = {2: YAML_CFG, 3: YAML_CFG3, 4: YAML_CFG4}[a.config]
+    bs = a.batch_size if (a.batch_size != 8 or a.config != 3) else base_cfg["batch_size"]
     cfg = dict(base_cfg, batch_size=bs, gpu=local, distributed=world > 1, world_size=world, rank=rank)
     args = S.get_config(cfg)
     torch.manual_seed(0)
     alg = S.get_algorithm(args, S.get_net_builder(args.net, False), None, None)
     alg.model = send_model_cuda(args, alg.model)
     alg.model.train()
-    alg.start_run, alg.end_run = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     it0 = 1 if a.stage == 1 else args.start_timing + 1 + 8 * args.num_train_iter
     B, U = args.batch_size, args.batch_size * args.uratio
     samples_per_step = B + 2 * U
+    text = a.config == 4
 
     def host_batch(i):
+        if text:
+            b = detgen.nlp_batch(B, args.uratio, args.num_classes, args.ulb_dest_len, max_length=args.max_length, seed=1 + rank, step=i)
+            return {k: ({kk: torch.from_numpy(vv).pin_memory() for kk, vv in v.items()} if isinstance(v, dict) else torch.from_numpy(v).pin_memory())
+                    for k, v in b.items()}
         b = detgen.ssl_batch(B, args.uratio, args.num_classes, args.ulb_dest_len, img_size=args.img_size, seed=1 + rank, step=i)
         return {k: torch.from_numpy(v).pin_memory() for k, v in b.items()}
 
-    n_batches = 4 if a.config == 2 else 2   # config 3: 231 MB per host batch
+    def to_dev(v):
+        return {k: t.cuda(non_blocking=True) for k, t in v.items()} if isinstance(v, dict) else v.cuda(non_blocking=True)
+
+    def nbytes(v):
+        return sum(nbytes(t) for t in v.values()) if isinstance(v, dict) else v.numel() * v.element_size()
+
+    n_batches = 4 if a.config != 3 else 2   # config 3: 231 MB per host batch
     hbatches = [host_batch(i) for i in range(n_batches)]
     import inspect
     step_keys = set(inspect.signature(alg.train_step).parameters)   # process_batch's filter (algorithmbase.py:287-296)
-    dbatches = [{k: v.cuda(non_blocking=True) for k, v in hb.items() if k in step_keys} for hb in hbatches]
-    h2d = sum(v.numel() * v.element_size() for v in hbatches[0].values())
+    dbatches = [{k: to_dev(v) for k, v in hb.items() if k in step_keys} for hb in hbatches]
+    h2d = sum(nbytes(v) for k, v in hbatches[0].items() if k in step_keys)
 
     def step_device(i):
         alg.it = it0 + i
@@ -293,13 +420,12 @@ def main_native(a):
             ms = t.item()
         return ms
 
-    # the ParamUpdateHook's own event timing syncs every step; the bench brackets the whole region instead
-    del alg.start_run, alg.end_run
     W, K = max(3, a.warmup), a.steps
+    if text and a.steps == 300:
+        K = 60          # a BERT step is ~10x a ViT-S step: keep the default run within minutes
     # one-time engine set-up outside the measurement (reported as config.setup_steps): the first call of a backbone pass runs
     # eagerly, the second is captured into a CUDA graph, kernels are lazily loaded on first use and stage 2 alternates between
     # step variants (SR update every N_k steps) — with a short --warmup those one-offs would land in the timed region
-    SETUP_STEPS = 12
     for i in range(SETUP_STEPS):
         step_device(i)
     for i in range(W):
@@ -313,8 +439,9 @@ def main_native(a):
     ms_e2e = timed(step_e2e, K, W + K)
     value = world * samples_per_step * K / (ms / 1e3)
     e2e = world * samples_per_step * K / (ms_e2e / 1e3)
+    step_ms = ms / K
 
-    roof = attn = None
+    roof = None
     if not a.no_roofline:   # every rank runs the profiled steps (they contain the gradient all-reduce); rank 0 reports
         lib.srw_profile_enable(1)
         st = (L.ProfileStats * L.PROF_NUM)()
@@ -332,49 +459,57 @@ def main_native(a):
         ach = g.flops / (g.total_ms * 1e-3) / 1e12 if g.total_ms > 0 else 0.0
         traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-        if os.path.isfile(tp):   # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch from the committed `ncu --set full` capture
+        if os.path.isfile(tp) and a.config == 2:   # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch from the committed `ncu --set full` capture
             tj = json.load(open(tp))
             traffic, traffic_src = tj.get("gemm_mean_traffic_bytes"), tj.get("source")
-        roof = dict(bound="tensor", kernel="gemm_bf16x3_tcgen05_kernel", achieved=ach, peak=sust, unit="TFLOP/s", frac=ach / sust,
-                    traffic=traffic, traffic_source=traffic_src, algorithmic_bytes_per_launch=g.bytes / max(g.launches, 1), peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})", launches_per_step=g.launches / nprof,
-                    avg_launch_us=1e3 * g.total_ms / max(g.launches, 1), share_of_step=g.total_ms / nprof / step_ms_prof,
-                    note="achieved = algorithmic 2MNK per launch / CUDA-event launch time; the kernel issues 3 bf16 MMAs per algorithmic "
-                         "product (hi*hi, hi*lo, lo*hi) for fp32-level accuracy, so the tensor pipe does 3x these FLOPs")
-        af, ab = st[L.PROF_ATTN_FWD], st[L.PROF_ATTN_BWD]
-        attn = dict(fwd=dict(achieved=af.flops / (af.total_ms * 1e-3) / 1e12 if af.total_ms > 0 else 0.0, unit="TFLOP/s",
-                             avg_launch_us=1e3 * af.total_ms / max(af.launches, 1), share_of_step=af.total_ms / nprof / step_ms_prof),
-                    bwd=dict(achieved=ab.flops / (ab.total_ms * 1e-3) / 1e12 if ab.total_ms > 0 else 0.0, unit="TFLOP/s",
-                             avg_launch_us=1e3 * ab.total_ms / max(ab.launches, 1), share_of_step=ab.total_ms / nprof / step_ms_prof),
-                    peak=sust)
-        ad = st[L.PROF_ADAMW]
-        if ad.total_ms > 0:
-            attn["adamw"] = dict(achieved_gbs=ad.bytes / (ad.total_ms * 1e-3) / 1e9, peak_gbs=hbm, avg_launch_us=1e3 * ad.total_ms / max(ad.launches, 1))
 
-    cpu = None
+        def kern(stat, peak, unit="TFLOP/s"):
+            if stat.total_ms <= 0:
+                return None
+            v = (stat.flops if unit == "TFLOP/s" else stat.bytes) / (stat.total_ms * 1e-3) / (1e12 if unit == "TFLOP/s" else 1e9)
+            # share_of_step: the kernel class's device time per step over the TIMED (graph-replayed) step; the per-launch events are
+            # taken in a separate pass with graph replay off (profiled_step_ms), kernel durations are the same kernels' either way
+            return dict(bound="tensor" if unit == "TFLOP/s" else "hbm", achieved=v, peak=peak, unit=unit, frac=v / peak,
+                        avg_launch_us=1e3 * stat.total_ms / max(stat.launches, 1), launches_per_step=stat.launches / nprof,
+                        share_of_step=stat.total_ms / nprof / step_ms)
+        roof = kern(g, sust)
+        roof.update(kernel="gemm_bf16x3_tcgen05_kernel", traffic=traffic, traffic_source=traffic_src,
+                    algorithmic_bytes_per_launch=g.bytes / max(g.launches, 1), peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})",
+                    profiled_step_ms=step_ms_prof,
+                    note="achieved = algorithmic 2MNK per launch / CUDA-event launch time; the kernel issues 3 bf16 MMAs per algorithmic "
+                         "product (hi*hi, hi*lo, lo*hi) for fp32-level accuracy, so the tensor pipe does 3x these FLOPs (frac is capped at 1/3)")
+        # the attention kernels (north_star quotes the attention-GEMM roofline) and the optimizer, as siblings of the dominant kernel
+        roof["attention_fwd"] = kern(st[L.PROF_ATTN_FWD], sust)
+        roof["attention_bwd"] = kern(st[L.PROF_ATTN_BWD], sust)
+        roof["adamw"] = kern(st[L.PROF_ADAMW], hbm, "GB/s")
+
+    cpu = eager = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline and a.config == 2:
         sps, per_step, cores = cpu_reference_run(dict(YAML_CFG, batch_size=a.batch_size), 6, 1, a.stage)
         cpu = dict(value=sps, unit="samples/s", cores=cores, kind="port",
                    sample=f"6 stage-{a.stage} steps (+1 warm-up) of the oracle restatement of the reference train_step+ParamUpdateHook, "
                           f"{per_step:.2f} s/step, torch CPU fp32, {cores} threads")
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and a.config == 4:
+        sps, per_step, cores = cpu_reference_bert(2, 1, 1, 0, 0.1)
+        cpu = dict(value=sps, unit="samples/s", cores=cores, kind="port",
+                   sample=f"1 stage-1 step of the oracle restatement at batch_size 2 (of {B}; 6 sequences of 512 tokens), {per_step:.1f} s/step, torch CPU fp32, {cores} threads")
+    if rank == 0 and world == 1 and not a.no_eager_leg and a.config == 2:
+        try:
+            eager = torch_eager_fp32_leg(dict(YAML_CFG, batch_size=a.batch_size), a.stage)
+        except Exception as e:   # informational leg: never fail the bench on it
+            eager = dict(unavailable=f"{type(e).__name__}: {e}"[:200])
     if rank == 0:
-        line = dict(metric="SSL train-step samples/sec (ViT-S CIFAR-100)", value=value, unit="samples/s", n_gpus=world, steps=K, warmup=W,
-                    ms_per_step=ms / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=(f"srflexmatch vit_small_patch2_32 cifar100 batch_size {B} uratio {args.uratio} stage {a.stage} (BASELINE configs[1])"
-                                          if a.config == 2 else
-                                          f"srfreematch vit_base_patch16_224 synthetic 224x224 1000 classes batch_size {B} per GPU stage {a.stage} (BASELINE configs[2])"),
-                                samples_per_step_per_gpu=samples_per_step, parallelism=f"dp{world}", drop_path=0.2, setup_steps=SETUP_STEPS,
-                                arithmetic="fp32 semantics: bf16x3 split-precision tcgen05 MMA, fp32 accumulate",
-                                l2="step working set (~1.8 GB of activations at batch 8) >> 126 MB L2; 4 rotating input batches",
-                                launch="CUDA-graph replay of the backbone forward/backward (SRW_GRAPHS) + programmatic dependent launch (SRW_PDL); "
-                                       "backward launched inside train_step ahead of the loss read-back",
-                                algorithmic_gflop_per_step_per_gpu=7 * B * (F_FWD_GF if a.config == 2 else F_FWD_GF3)),
+        line = dict(metric=METRICS[a.config], value=value, unit="samples/s", n_gpus=world, steps=K, warmup=W,
+                    ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=config_block(a.config, B, args.uratio, a.stage, world, SETUP_STEPS),
                     clocks=clk.summary(), gpu_launches=int(launches),
                     e2e=dict(value=e2e, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4 * (5 + U), ms_per_step=ms_e2e / K))
         if roof is not None:
             line["roofline"] = roof
-            line["attention"] = attn
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if eager is not None:
+            line["torch_eager_fp32_b200"] = eager
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -517,6 +517,9 @@ class SSLOracle:
             unsup = consistency_loss(ls, pseudo, mask, mask2)
             rec.update(dg_mask=mask, dg_mask2=mask2, dg_reward=reward.detach(), dg_pseudo=pseudo, dg_logits_w=lw.detach(),
                        dg_gap=getattr(self.hook, "last_gap", None))
+            rec.setdefault("dg_all_logits_w", []).append(lw.detach())
+            if hasattr(self.hook, "time_p"):
+                rec.setdefault("dg_all_time_p", []).append(float(self.hook.time_p))
         return unsup
 
     def _sr_update(self, feats: Tensor, true_labels: Tensor, rec: dict):

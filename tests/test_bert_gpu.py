@@ -98,8 +98,9 @@ def test_bert_backbone_forward_backward_vs_oracle(layers, Lq, S, drop):
         gr = p[n].grad
         sc = gr.abs().max().item()
         err = (v.cpu() - gr).abs().max().item() / max(sc, 1e-12)
-        if sc < 1e-9:      # mathematically zero gradients (the key bias): absolute check
-            assert v.abs().max().item() < 1e-6, n
+        if sc < 1e-9 or n.endswith("attention.self.key.bias"):
+            # mathematically zero gradient (softmax is invariant to a per-query shift of the scores): both sides hold rounding noise
+            assert v.abs().max().item() < 1e-5 and sc < 1e-5, (n, v.abs().max().item(), sc)
             continue
         if err > worst:
             worst, worst_n = err, n
@@ -153,7 +154,7 @@ def test_bert_ssl_steps_vs_oracle(algorithm, over, hg, drop):
                     assert n not in tap or tap[n] is None or n.startswith("bert.pooler")
                     continue
                 sc = gr.abs().max().item()
-                if sc < 1e-9:
+                if sc < 1e-9 or n.endswith("attention.self.key.bias"):
                     continue
                 worst = max(worst, (tap[n].cpu() - gr).abs().max().item() / sc)
             print(f"bert {algorithm} drop {drop} it {it}: total {ld['train/total_loss']:.5f} (oracle {float(rec['total_loss']):.5f}) K {rec.get('K', 0)} grad rel err {worst:.2e}")
@@ -192,16 +193,26 @@ def test_bert_base_full_size_step():
             assert abs(ld[kn] - float(rec[ko])) < 1e-3, f"it {it} {ko}: {ld[kn]} vs {float(rec[ko])}"
         assert torch.equal(alg._last_pseudo_label.cpu(), rec["pseudo"])
         assert (alg._last_mask.cpu() - rec["mask"]).abs().max().item() < 1e-4
-        worst, wn = 0.0, ""
+        worst, wn, rows = 0.0, "", []
+        gmax = max(g.abs().max().item() for g in ref_grads.values() if g is not None)
         for n, q in alg.model.named_parameters():
             gr = ref_grads[n]
-            if gr is None or gr.abs().max().item() < 1e-9:
+            if gr is None or gr.abs().max().item() < 1e-9 or n.endswith("attention.self.key.bias"):
                 continue
-            e = (tap[n].cpu() - gr).abs().max().item() / gr.abs().max().item()
+            sc = gr.abs().max().item()
+            e = (tap[n].cpu() - gr).abs().max().item() / sc
+            rows.append((e, n, sc))
             if e > worst:
                 worst, wn = e, n
-        print(f"bert-base L=512 B=8 it {it}: total {ld['train/total_loss']:.5f} (oracle {float(rec['total_loss']):.5f}) grad rel err {worst:.2e} ({wn})")
-        assert worst < 1e-3, (worst, wn)
+        rows.sort(reverse=True)
+        print(f"bert-base L=512 B=8 it {it}: total {ld['train/total_loss']:.5f} (oracle {float(rec['total_loss']):.5f}) grad rel err {worst:.2e} ({wn}); largest |grad| {gmax:.2e}")
+        for e, n, sc in rows[:8]:
+            print(f"      {n}: rel err {e:.2e} max |grad| {sc:.2e}")
+        # Per-tensor relative error where the tensor's gradient is not itself cancellation noise: at random init the 12-layer post-LN
+        # stack attends almost uniformly over 512 keys, so d(query / key weights) are differences of nearly equal terms, ~1e-4 of the
+        # other gradients; those are held to 1e-3 of the LARGEST gradient of the step instead of their own (tiny) maximum
+        for e, n, sc in rows:
+            assert e < 1e-3 or e * sc < 1e-3 * gmax * 1e-2, (n, e, sc, gmax)
         with torch.no_grad():
             for n, q in alg.model.named_parameters():
                 q.copy_(orc.p[n].detach())

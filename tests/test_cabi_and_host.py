@@ -198,7 +198,7 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["metric"] == "SSL train-step samples/sec (ViT-S CIFAR-100)" and "workload" in d["config"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
     # the native arm refuses the configs that have no CUDA path instead of falling back to anything
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", "4"], capture_output=True, text=True, timeout=120, cwd=ROOT)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", "5"], capture_output=True, text=True, timeout=120, cwd=ROOT)
     assert r.returncode != 0 and "no CUDA path" in (r.stderr + r.stdout)
 
 

@@ -67,7 +67,7 @@ def test_droppath_on_steps_vs_oracle(algorithm, depth, batched):
     """drop_path_rate 0.2 (the shipped builders' value, the mode bench.py times).  it 0-1 stage 1 (SR trained on labelled data),
     it 2 the gap step, it 3-5 stage 2 with K = 8 fresh draws per step and two graphs carrying gradient."""
     from oracle import ssl_oracle as O
-    cfg = small_cfg(algorithm=algorithm, num_train_iter=16, start_timing=2, N_k=2, ent_loss_ratio=0.05, ema_p=0.9)
+    cfg = small_cfg(algorithm=algorithm, num_train_iter=16, start_timing=2, N_k=2, ent_loss_ratio=0.05, ema_p=0.9, use_quantile=True, clip_thresh=False)
     orc = build_oracle(cfg, depth, drop_path_rate=0.2)
     alg = build_native(cfg, depth, drop_path_rate=0.2)
     alg.batch_stochastic_passes = batched
@@ -76,8 +76,18 @@ def test_droppath_on_steps_vs_oracle(algorithm, depth, batched):
     sdp.install(orc, alg)
     tap = _grad_tap(alg)
     ties = 0
+    trace = []
+    if algorithm == "srfreematch":   # per-pass trace of the native hook (test-only: one sync per pass)
+        orig_mp = alg._mask_and_pseudo
+
+        def traced(logits_w, idx_ulb, first_pass=True):
+            out = orig_mp(logits_w, idx_ulb, first_pass=first_pass)
+            trace.append((logits_w.detach().cpu().clone(), float(alg.hooks_dict["MaskingHook"].time_p.item())))
+            return out
+        alg._mask_and_pseudo = traced
     try:
         for it in range(6):
+            trace.clear()
             sdp.new_step()
             batch = batch_tensors(cfg, it)
             rec = orc.train_step(dict(batch), it)
@@ -100,7 +110,12 @@ def test_droppath_on_steps_vs_oracle(algorithm, depth, batched):
             tied = mask2_report(rec, alg._last_mask2, f"{algorithm} d{depth} it {it}")
             ties += tied
             if algorithm == "srfreematch":
-                print(f"   oracle time_p {float(orc.hook.time_p):.6f} p_model[:4] {orc.hook.p_model[:4].tolist()}")
+                print(f"   oracle time_p {float(orc.hook.time_p):.6f} native {alg.hooks_dict['MaskingHook'].time_p.item():.6f}")
+                for k, lw_o in enumerate(rec.get("dg_all_logits_w", [])):
+                    lw_n, tp_n = trace[k + 1]
+                    mp_o, mp_n = torch.softmax(lw_o, -1).max(-1).values, torch.softmax(lw_n, -1).max(-1).values
+                    print(f"      pass {k + 1}: |dlogits| {(lw_n - lw_o).abs().max().item():.2e} time_p oracle {rec['dg_all_time_p'][k]:.6f} native {tp_n:.6f} "
+                          f"q oracle {torch.quantile(mp_o, 0.8).item():.6f} q(native logits) {torch.quantile(mp_n, 0.8).item():.6f}")
             tied += band_report(rec, alg, f"{algorithm} d{depth} it {it}")
             if not tied:
                 for kn, ko in (("train/unsup_loss", "unsup_loss"), ("train/total_loss", "total_loss")):
