@@ -19,7 +19,7 @@ def _grad_tap(alg):
 
     def step(*a, **k):
         tap.clear()
-        tap.update({n: p.grad.detach().clone() for n, p in alg.model.named_parameters() if p.grad is not None})   # BERT's pooler has none
+        tap.update({(n[7:] if n.startswith('module.') else n): p.grad.detach().clone() for n, p in alg.model.named_parameters() if p.grad is not None})   # BERT's pooler has none; a data-parallel wrapper prefixes 'module.'
         return orig(*a, **k)
 
     alg.optimizer.step = step
