@@ -420,6 +420,13 @@ typedef struct {
   float* mask2;             /* [B_ulb] out (ones when reward == NULL; may be NULL) */
   float* losses;            /* [>= 4] out: sup, unsup, total, util_ratio ([4] = FreeMatch entropy term, written by srw_freematch_entropy) */
   float* dlogits_lb; float* dlogits_s; int64_t ld_dlogits;   /* d total / d logits (may be NULL) */
+  /* Fused stage-2 epilogue (north_star: "Rewarder MLP forward, reward score, mean-threshold mask and masked cross-entropy consistency
+   * loss collapse into one fused epilogue kernel"): when rp != NULL the kernel first evaluates Rewarder.forward(feats, pseudo)
+   * (semireward.py:52-72, srflexmatch.py:99) itself — `reward` is then ignored — and continues with mask2 / losses / dlogits in the
+   * same launch.  rp = 17 device pointers in Rewarder.state_dict order; rew_workspace >= srw_rewarder_workspace_floats(B_ulb, .)
+   * floats (only touched when the intermediates do not fit in shared memory); reward_out [B_ulb] optional. */
+  const float* const* rp; const float* feats; int64_t ld_feats; int feature_dim, label_rows;
+  float* rew_workspace; float* reward_out;
 } srw_ssl_loss_args;
 int srw_ssl_loss(const srw_ssl_loss_args* a, void* stream);
 

@@ -144,7 +144,8 @@ class FlexMatchMaskArgs(C.Structure):
 class SslLossArgs(C.Structure):
     _fields_ = [("B_lb", i32), ("B_ulb", i32), ("num_classes", i32), ("logits_lb", vp), ("logits_s", vp), ("ld_logits", i64),
                 ("y_lb", vp), ("pseudo", vp), ("mask", vp), ("reward", vp), ("lambda_u", f32), ("mask2", vp), ("losses", vp),
-                ("dlogits_lb", vp), ("dlogits_s", vp), ("ld_dlogits", i64)]
+                ("dlogits_lb", vp), ("dlogits_s", vp), ("ld_dlogits", i64),
+                ("rp", C.POINTER(vp)), ("feats", vp), ("ld_feats", i64), ("feature_dim", i32), ("label_rows", i32), ("rew_workspace", vp), ("reward_out", vp)]
 
 
 f64 = C.c_double

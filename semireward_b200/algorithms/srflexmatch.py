@@ -64,8 +64,10 @@ class _SSLLoss(torch.autograd.Function):
         return ctx.dl_lb * g, ctx.dl_s * g, None, None, None, None, None, None
 
 
-def _ssl_loss_native(logits_lb, logits_s, y_lb, pseudo, mask, reward, lambda_u, dl_lb, dl_s):
-    """srw_ssl_loss -> (losses[4] = sup, unsup, total, util ; mask2).  d total / d logits goes into dl_lb / dl_s (row stride C)."""
+def _ssl_loss_native(logits_lb, logits_s, y_lb, pseudo, mask, reward, lambda_u, dl_lb, dl_s, rewarder=None, feats=None):
+    """srw_ssl_loss -> (losses[4] = sup, unsup, total, util ; mask2).  d total / d logits goes into dl_lb / dl_s (row stride C).
+    rewarder + feats: the fused stage-2 epilogue — Rewarder.forward(feats, pseudo), the mean-threshold mask2, the masked
+    consistency loss and d loss / d logits in ONE launch (`reward` is ignored then)."""
     B_lb, Cn = logits_lb.shape
     B_u = logits_s.shape[0]
     dev = logits_lb.device
@@ -76,7 +78,18 @@ def _ssl_loss_native(logits_lb, logits_s, y_lb, pseudo, mask, reward, lambda_u, 
                       ld_logits=logits_lb.stride(0), y_lb=y_lb.data_ptr(), pseudo=pseudo.data_ptr(), mask=mask.data_ptr(),
                       reward=L.ptr(reward), lambda_u=float(lambda_u), mask2=mask2.data_ptr(), losses=losses.data_ptr(),
                       dlogits_lb=dl_lb.data_ptr(), dlogits_s=dl_s.data_ptr(), ld_dlogits=Cn)
+    keep = None
+    if rewarder is not None:
+        f = feats.detach()
+        if f.stride(-1) != 1:
+            f = f.contiguous()
+        ws = torch.empty(max(L.load().srw_rewarder_workspace_floats(B_u, rewarder.feature_dim), 16), dtype=torch.float32, device=dev)
+        keep = (f, ws, L.ptr_array(rewarder._params()))
+        a.rp, a.feats, a.ld_feats, a.feature_dim, a.label_rows, a.rew_workspace = keep[2], f.data_ptr(), f.stride(0), rewarder.feature_dim, rewarder.label_rows, ws.data_ptr()
+        a.reward = None
     L.check(L.load().srw_ssl_loss(C.byref(a), L.stream_ptr()), "srw_ssl_loss")
+    if rewarder is not None and hasattr(rewarder, "update_ema"):
+        rewarder.update_ema()
     return losses, mask2
 
 
@@ -294,9 +307,10 @@ class SRFlexMatch(AlgorithmBase):
         mask, pseudo_label = self._mask_and_pseudo(l_w[0], idx_ulb, first_pass=True)
         for k in range(1, K + 1):
             mask_dg, pseudo_dg = self._mask_and_pseudo(l_w[k], idx_ulb, first_pass=False)
-        reward_dg = self.rewarder(f_w[K], pseudo_dg)
         dl = net.dlogits_buffer(gb, dev)
-        losses, mask2 = _ssl_loss_native(logits_lb, l_sK, y_lb, pseudo_dg, mask_dg, reward_dg.view(-1), self.lambda_u, dl[:nl], dl[nl:nl + nu])
+        # fused stage-2 epilogue: Rewarder(f_w of the last pass, its pseudo-labels) -> mask2 -> masked consistency loss -> dlogits, one launch
+        losses, mask2 = _ssl_loss_native(logits_lb, l_sK, y_lb, pseudo_dg, mask_dg, None, self.lambda_u, dl[:nl], dl[nl:nl + nu],
+                                         rewarder=self.rewarder, feats=f_w[K])
         if extra:
             dl[nl + nu:].zero_()
             self._extra_loss(losses, mask, logits_s0, dl[nl + nu:])
@@ -353,9 +367,9 @@ class SRFlexMatch(AlgorithmBase):
                 else:
                     l_w, f_w = logits_w, feats_w
                 mask_dg, pseudo_dg = self._mask_and_pseudo(l_w, idx_ulb, first_pass=False)
-                if stochastic or k == K - 1:
-                    reward_dg = self.rewarder(f_w, pseudo_dg)
-            losses, mask2 = _ssl_loss_native(logits_lb, l_s, y_lb, pseudo_dg, mask_dg, reward_dg.view(-1), self.lambda_u, dl_lb, dl_s)
+            # the reward of pass k only feeds pass k's loss and only the last loss survives: one fused launch for the last pass
+            losses, mask2 = _ssl_loss_native(logits_lb, l_s, y_lb, pseudo_dg, mask_dg, None, self.lambda_u, dl_lb, dl_s,
+                                             rewarder=self.rewarder, feats=f_w)
         else:
             losses, mask2 = _ssl_loss_native(logits_lb, logits_s, y_lb, pseudo_label, mask, None, self.lambda_u, dl_lb, dl_s)
         # gradient buffers of the pass(es) that carry gradient; algorithm-specific extra terms (FreeMatch's entropy loss on

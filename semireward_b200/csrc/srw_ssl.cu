@@ -10,6 +10,7 @@
 // All math is plain fp32 in a fixed, documented order (deterministic: no atomics, reductions in index order), which is
 // what the bit-exact mask requirement needs.  HBM traffic is a few KB..MB; these kernels are latency-bound by design.
 #include <atomic>
+#include <mutex>
 
 #include "../../include/srw.h"
 #include "srw_common.cuh"
@@ -127,73 +128,6 @@ __global__ void __launch_bounds__(SSL_THREADS) flexmatch_mask_kernel(const srw_f
 }
 
 // ------------------------------------------------------------------------------------------------
-// losses + dlogits
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SSL_THREADS) ssl_loss_kernel(const srw_ssl_loss_args a) {
-  __shared__ float s_ce[2 * MAX_ROWS];   // [0,B_lb) supervised CE, [MAX_ROWS, +B_ulb) unsupervised CE
-  __shared__ float s_w[MAX_ROWS];        // mask * mask2
-  __shared__ float s_scalar[4];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int C = a.num_classes;
-  const int rows = a.B_lb + a.B_ulb;
-  // mask2 = reward >= mean(reward)   (srflexmatch.py:100-101).  The sum is a fixed-order pairwise tree: samples that share
-  // a pseudo-label have bit-identical rewards (the Rewarder sees features only through the batch context), and a batch
-  // of identical rewards must compare equal to its own mean, which a pairwise sum guarantees for power-of-two batches
-  // (a running sum r+r+r... rounds at 3r) and which is what torch's vectorised reduction does as well.
-  if (a.reward) {
-    float* tree = s_ce;   // scratch: the CE values are written later
-    for (int b = threadIdx.x; b < a.B_ulb; b += blockDim.x) tree[b] = a.reward[b];
-    __syncthreads();
-    for (int stride = 1; stride < a.B_ulb; stride <<= 1) {
-      for (int i = threadIdx.x * 2 * stride; i + stride < a.B_ulb; i += blockDim.x * 2 * stride) tree[i] += tree[i + stride];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) s_scalar[0] = tree[0] / (float)a.B_ulb;
-  } else if (threadIdx.x == 0) {
-    s_scalar[0] = 0.f;
-  }
-  __syncthreads();
-  for (int b = threadIdx.x; b < a.B_ulb; b += blockDim.x) {
-    const float m2 = a.reward ? (a.reward[b] >= s_scalar[0] ? 1.0f : 0.0f) : 1.0f;
-    if (a.mask2) a.mask2[b] = m2;
-    s_w[b] = a.mask[b] * m2;
-  }
-  __syncthreads();
-  for (int r = warp; r < rows; r += nw) {
-    const bool lb = r < a.B_lb;
-    const int b = lb ? r : r - a.B_lb;
-    const float* row = (lb ? a.logits_lb : a.logits_s) + (int64_t)b * a.ld_logits;
-    const int64_t tgt = lb ? a.y_lb[b] : a.pseudo[b];
-    float m, sum;
-    warp_row_max_sum(row, C, lane, m, sum);
-    const float lse = m + logf(sum);
-    if (lane == 0) s_ce[lb ? b : MAX_ROWS + b] = lse - row[tgt];   // -log_softmax[target]
-    float* drow = lb ? a.dlogits_lb : a.dlogits_s;
-    if (drow) {
-      drow += (int64_t)b * a.ld_dlogits;
-      const float w = lb ? 1.0f / (float)a.B_lb : a.lambda_u * s_w[b] / (float)a.B_ulb;
-      for (int c = lane; c < C; c += 32) {
-        const float pr = expf(row[c] - m) / sum;
-        drow[c] = w * (pr - (c == tgt ? 1.0f : 0.0f));
-      }
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float sup = 0.f, unsup = 0.f, util = 0.f;
-    for (int b = 0; b < a.B_lb; ++b) sup += s_ce[b];
-    sup /= (float)a.B_lb;
-    for (int b = 0; b < a.B_ulb; ++b) {
-      unsup += s_ce[MAX_ROWS + b] * s_w[b];
-      util += a.mask[b];
-    }
-    unsup /= (float)a.B_ulb;
-    util /= (float)a.B_ulb;
-    a.losses[0] = sup; a.losses[1] = unsup; a.losses[2] = sup + a.lambda_u * unsup; a.losses[3] = util;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // CTA-wide dense helpers for the Rewarder / Generator (tiny matrices, fp32 FMA)
 // ------------------------------------------------------------------------------------------------
 enum { ACT_NONE = 0, ACT_RELU = 1 };
@@ -307,7 +241,7 @@ struct RewWs {
 __host__ __device__ inline int64_t rew_ws_floats(int B) {
   return (int64_t)B * (128 + 128 + 1 + 256 + 128 + 128 + 1 + 2 + 2 + 128 + 256 + 128 + 64 + 1 + 1 + 64 + 128 + 256 + 128 + 256 + 128 + 128 + 2 + 2) + 128 + 128 + 64;
 }
-__device__ inline RewWs rew_carve(float* w, int B) {
+__host__ __device__ inline RewWs rew_carve(float* w, int B) {
   RewWs s;
   auto take = [&](int64_t n) { float* p = w; w += n; return p; };
   s.u = take(B * 128); s.fxh = take(B * 128); s.frs = take(B); s.X = take(2 * B * 128); s.eraw = take(B * 128); s.exh = take(B * 128);
@@ -374,10 +308,88 @@ __device__ void rewarder_forward_cta(const RewPtrs& P, const RewWs& s, const flo
   __syncthreads();
 }
 
+// ------------------------------------------------------------------------------------------------
+// losses + dlogits
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SSL_THREADS) ssl_loss_kernel(const srw_ssl_loss_args a, RewPtrs RP, int fused_rewarder, int use_smem) {
+  extern __shared__ float dyn[];
+  __shared__ float s_ce[2 * MAX_ROWS];   // [0,B_lb) supervised CE, [MAX_ROWS, +B_ulb) unsupervised CE
+  __shared__ float s_w[MAX_ROWS];        // mask * mask2
+  __shared__ float s_scalar[4];
+  __shared__ float red_r[32];
+  const float* rew = a.reward;
+  if (fused_rewarder) {   // Rewarder.forward on (weak features, pseudo-labels) of the last sampling pass, intermediates on chip when they fit
+    const RewWs rs = rew_carve(use_smem ? dyn : a.rew_workspace, a.B_ulb);
+    rewarder_forward_cta(RP, rs, a.feats, a.ld_feats, a.pseudo, a.B_ulb, a.feature_dim, a.label_rows, red_r);
+    rew = rs.r;
+    if (a.reward_out)
+      for (int b = threadIdx.x; b < a.B_ulb; b += blockDim.x) a.reward_out[b] = rs.r[b];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int C = a.num_classes;
+  const int rows = a.B_lb + a.B_ulb;
+  // mask2 = reward >= mean(reward)   (srflexmatch.py:100-101).  The sum is a fixed-order pairwise tree: samples that share
+  // a pseudo-label have bit-identical rewards (the Rewarder sees features only through the batch context), and a batch
+  // of identical rewards must compare equal to its own mean, which a pairwise sum guarantees for power-of-two batches
+  // (a running sum r+r+r... rounds at 3r) and which is what torch's vectorised reduction does as well.
+  if (rew) {
+    float* tree = s_ce;   // scratch: the CE values are written later
+    for (int b = threadIdx.x; b < a.B_ulb; b += blockDim.x) tree[b] = rew[b];
+    __syncthreads();
+    for (int stride = 1; stride < a.B_ulb; stride <<= 1) {
+      for (int i = threadIdx.x * 2 * stride; i + stride < a.B_ulb; i += blockDim.x * 2 * stride) tree[i] += tree[i + stride];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) s_scalar[0] = tree[0] / (float)a.B_ulb;
+  } else if (threadIdx.x == 0) {
+    s_scalar[0] = 0.f;
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < a.B_ulb; b += blockDim.x) {
+    const float m2 = rew ? (rew[b] >= s_scalar[0] ? 1.0f : 0.0f) : 1.0f;
+    if (a.mask2) a.mask2[b] = m2;
+    s_w[b] = a.mask[b] * m2;
+  }
+  __syncthreads();
+  for (int r = warp; r < rows; r += nw) {
+    const bool lb = r < a.B_lb;
+    const int b = lb ? r : r - a.B_lb;
+    const float* row = (lb ? a.logits_lb : a.logits_s) + (int64_t)b * a.ld_logits;
+    const int64_t tgt = lb ? a.y_lb[b] : a.pseudo[b];
+    float m, sum;
+    warp_row_max_sum(row, C, lane, m, sum);
+    const float lse = m + logf(sum);
+    if (lane == 0) s_ce[lb ? b : MAX_ROWS + b] = lse - row[tgt];   // -log_softmax[target]
+    float* drow = lb ? a.dlogits_lb : a.dlogits_s;
+    if (drow) {
+      drow += (int64_t)b * a.ld_dlogits;
+      const float w = lb ? 1.0f / (float)a.B_lb : a.lambda_u * s_w[b] / (float)a.B_ulb;
+      for (int c = lane; c < C; c += 32) {
+        const float pr = expf(row[c] - m) / sum;
+        drow[c] = w * (pr - (c == tgt ? 1.0f : 0.0f));
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sup = 0.f, unsup = 0.f, util = 0.f;
+    for (int b = 0; b < a.B_lb; ++b) sup += s_ce[b];
+    sup /= (float)a.B_lb;
+    for (int b = 0; b < a.B_ulb; ++b) {
+      unsup += s_ce[MAX_ROWS + b] * s_w[b];
+      util += a.mask[b];
+    }
+    unsup /= (float)a.B_ulb;
+    util /= (float)a.B_ulb;
+    a.losses[0] = sup; a.losses[1] = unsup; a.losses[2] = sup + a.lambda_u * unsup; a.losses[3] = util;
+  }
+}
+
 __global__ void __launch_bounds__(SSL_THREADS) rewarder_fwd_kernel(RewPtrs P, const float* feats, int64_t ld_feats, const int64_t* labels, int B,
-                                                                  int D, int label_rows, float* reward, float* ws) {
+                                                                  int D, int label_rows, float* reward, float* ws, int use_smem) {
+  extern __shared__ float dyn[];
   __shared__ float red[32];
-  const RewWs s = rew_carve(ws, B);
+  const RewWs s = rew_carve(use_smem ? dyn : ws, B);
   rewarder_forward_cta(P, s, feats, ld_feats, labels, B, D, label_rows, red);
   for (int b = threadIdx.x; b < B; b += blockDim.x) reward[b] = s.r[b];
 }
@@ -399,16 +411,22 @@ __global__ void __launch_bounds__(SSL_THREADS) generator_fwd_kernel(GenPtrs P, c
 
 struct AdamScalars { float lr; double bc1, bc2_sqrt; };
 
-__global__ void __launch_bounds__(SSL_THREADS) rewarder_train_kernel(RewPtrs P, RewPtrs G, RewPtrs M, RewPtrs V, RewSizes N, const float* feats,
-                                                                    int64_t ld_feats, const int64_t* gen_labels, const int64_t* true_labels,
-                                                                    int B, int D, int label_rows, AdamScalars ad, int phase, float* losses, float* ws, int loss_select, RewPtrs GA,
-                                                                    int has_g_add) {
+// The online update runs as TWO launches:
+//   rewarder_actgrad_kernel   one CTA: forward, both MSE losses and the backward down to every ACTIVATION gradient.  For the
+//                             configs' batch sizes (B <= 22) all intermediates live in shared memory (the chain of ~25 dependent
+//                             phases was bound by L2 round trips when they lived in the global workspace: 330-480 us); the
+//                             intermediates the second launch needs are copied to the workspace at the end.
+//   rewarder_wgrad_adam_kernel  many CTAs: one thread per PARAMETER element forms its gradient from those activations
+//                             (sum over the <= 2B rows, same order as before) and applies torch.optim.Adam right away.
+// Phase 1 stops after storing the gradients, phase 2 applies Adam to stored gradients (data-parallel exchange in between).
+__global__ void __launch_bounds__(SSL_THREADS) rewarder_actgrad_kernel(RewPtrs P, const float* feats, int64_t ld_feats, const int64_t* gen_labels,
+                                                                      const int64_t* true_labels, int B, int D, int label_rows, float* losses, float* ws,
+                                                                      int loss_select, int use_smem) {
+  extern __shared__ float dyn[];
   __shared__ float red[32];
-  const RewWs s = rew_carve(ws, B);
-  if (phase != 2) {
+  float* base = use_smem ? dyn : ws;
+  const RewWs s = rew_carve(base, B);
   rewarder_forward_cta(P, s, feats, ld_feats, gen_labels, B, D, label_rows, red);
-  float* f = s.X;
-  (void)f;
   // losses: generator_loss = MSE(r, 1), rewarder_loss = MSE(r, target), target = cos-sim of the two one-hots mapped to
   // (cos+1)/2 = 1 if equal else 0.5  (semireward.py:130-139, srflexmatch.py:195-199)
   float gl = 0.f, rl = 0.f;
@@ -424,33 +442,23 @@ __global__ void __launch_bounds__(SSL_THREADS) rewarder_train_kernel(RewPtrs P, 
   rl = block_reduce_sum(rl, red);
   if (threadIdx.x == 0) { losses[0] = gl / (float)B; losses[1] = rl / (float)B; }
   __syncthreads();
-  // ffn_fc2
-  cta_linear_dw(s.dz4, B, 1, s.h3, 64, 64, G.p[R_F2W], G.p[R_F2B]);
-  for (int o = threadIdx.x; o < B * 64; o += blockDim.x) s.dh3[o] = s.h3[o] > 0.f ? s.dz4[o / 64] * P.p[R_F2W][o % 64] : 0.f;
+  for (int o = threadIdx.x; o < B * 64; o += blockDim.x) s.dh3[o] = s.h3[o] > 0.f ? s.dz4[o / 64] * P.p[R_F2W][o % 64] : 0.f;   // ffn_fc2, relu
   __syncthreads();
-  // ffn_fc1
-  cta_linear_dw(s.dh3, B, 64, s.h2, 128, 128, G.p[R_F1W], G.p[R_F1B]);
-  cta_linear_dx(s.dh3, B, 64, P.p[R_F1W], 128, s.dh2);
+  cta_linear_dx(s.dh3, B, 64, P.p[R_F1W], 128, s.dh2);    // ffn_fc1
   __syncthreads();
-  // mlp_fc2
-  cta_linear_dw(s.dh2, B, 128, s.h1, 256, 256, G.p[R_M2W], G.p[R_M2B]);
-  cta_linear_dx(s.dh2, B, 128, P.p[R_M2W], 256, s.dh1);
+  cta_linear_dx(s.dh2, B, 128, P.p[R_M2W], 256, s.dh1);   // mlp_fc2
   __syncthreads();
   for (int o = threadIdx.x; o < B * 256; o += blockDim.x) s.dh1[o] = s.h1[o] > 0.f ? s.dh1[o] : 0.f;
   __syncthreads();
-  // mlp_fc1
-  cta_linear_dw(s.dh1, B, 256, s.h, 128, 128, G.p[R_M1W], G.p[R_M1B]);
-  cta_linear_dx(s.dh1, B, 256, P.p[R_M1W], 128, s.dh);
+  cta_linear_dx(s.dh1, B, 256, P.p[R_M1W], 128, s.dh);    // mlp_fc1
   __syncthreads();
-  // h = ctx + e
-  for (int c = threadIdx.x; c < 128; c += blockDim.x) {
+  for (int c = threadIdx.x; c < 128; c += blockDim.x) {   // h = ctx + e
     float acc = 0.f;
     for (int b = 0; b < B; ++b) acc += s.dh[b * 128 + c];
     s.dctx[c] = acc;
   }
   __syncthreads();
-  // ctx = sum_r w_r X_r ; w = softmax(att) over rows
-  {
+  {   // ctx = sum_r w_r X_r ; w = softmax(att) over rows
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int r = warp; r < 2 * B; r += nw) {
       float acc = 0.f;
@@ -465,7 +473,6 @@ __global__ void __launch_bounds__(SSL_THREADS) rewarder_train_kernel(RewPtrs P, 
   dot = block_reduce_sum(dot, red);
   for (int r = threadIdx.x; r < 2 * B; r += blockDim.x) s.da[r] = s.wsm[r] * (s.dwv[r] - dot);
   __syncthreads();
-  cta_linear_dw(s.da, 2 * B, 1, s.X, 128, 128, G.p[R_CAW], G.p[R_CAB]);
   for (int o = threadIdx.x; o < 2 * B * 128; o += blockDim.x) {
     const int r = o / 128, c = o % 128;
     float v = s.wsm[r] * s.dctx[c] + s.da[r] * P.p[R_CAW][c];
@@ -473,42 +480,69 @@ __global__ void __launch_bounds__(SSL_THREADS) rewarder_train_kernel(RewPtrs P, 
     s.dX[o] = v;
   }
   __syncthreads();
-  // feature branch: f = LN(u), u = feats Wf^T + bf
-  cta_ln_param_grads(s.dX, s.fxh, B, G.p[R_FNW], G.p[R_FNB]);
-  cta_layernorm128_bwd(s.dX, B, P.p[R_FNW], s.fxh, s.frs, s.du);
-  // label branch: e = LN(Emb[label])
-  cta_ln_param_grads(s.dX + B * 128, s.exh, B, G.p[R_LNW], G.p[R_LNB]);
-  cta_layernorm128_bwd(s.dX + B * 128, B, P.p[R_LNW], s.exh, s.ers, s.demb);
+  cta_layernorm128_bwd(s.dX, B, P.p[R_FNW], s.fxh, s.frs, s.du);                    // feature branch: f = LN(u), u = feats Wf^T + bf
+  cta_layernorm128_bwd(s.dX + B * 128, B, P.p[R_LNW], s.exh, s.ers, s.demb);        // label branch: e = LN(Emb[label])
   __syncthreads();
-  cta_linear_dw(s.du, B, 128, feats, ld_feats, D, G.p[R_FCW], G.p[R_FCB]);
-  // embedding gradient: dense, rows of repeated labels summed in batch order
-  for (int o = threadIdx.x; o < label_rows * 128; o += blockDim.x) G.p[R_EMB][o] = 0.f;
-  __syncthreads();
-  for (int c = threadIdx.x; c < 128; c += blockDim.x)
-    for (int b = 0; b < B; ++b) {
-      int64_t l = gen_labels[b];
-      l = l < 0 ? 0 : (l >= label_rows ? label_rows - 1 : l);
-      G.p[R_EMB][l * 128 + c] += s.demb[b * 128 + c];
+  if (use_smem) {
+    const int64_t n = rew_ws_floats(B);
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) ws[i] = dyn[i];
+  }
+}
+
+// one row per Rewarder tensor: how its gradient is formed from the activations rewarder_actgrad_kernel left in the workspace
+enum { RG_LINEAR = 0, RG_BIAS = 1, RG_LN_GAMMA = 2, RG_EMB = 3 };
+struct RewGradRow {
+  int kind; int rows; int N, K;           // LINEAR: dW[n, k] = sum_r dY[r, n] X[r, k];  BIAS: db[n] = sum_r dY[r, n]
+  const float* dY; const float* X; int64_t ldx;   // LN_GAMMA: dg[c] = sum_r dY[r, c] X[r, c] (K = 128);  EMB: dE[l, c] = sum_b [label_b == l] dY[b, c]
+  int64_t first;                          // exclusive prefix sum of the element counts
+};
+struct RewGradTable { RewGradRow t[R_NUM]; int64_t total; };
+
+__global__ void __launch_bounds__(256) rewarder_wgrad_adam_kernel(RewPtrs P, RewPtrs G, RewPtrs M, RewPtrs V, RewPtrs GA, int has_g_add,
+                                                                  const __grid_constant__ RewGradTable tab, const int64_t* __restrict__ labels, int label_rows,
+                                                                  AdamScalars ad, int phase) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= tab.total) return;
+  int t = 0;
+#pragma unroll 1
+  while (t + 1 < R_NUM && i >= tab.t[t + 1].first) ++t;
+  const RewGradRow& r = tab.t[t];
+  const int64_t e = i - r.first;
+  float gi;
+  if (phase != 2) {
+    float acc = 0.f;
+    if (r.kind == RG_LINEAR) {
+      const int n = (int)(e / r.K), k = (int)(e % r.K);
+      for (int q = 0; q < r.rows; ++q) acc = fmaf(r.dY[q * r.N + n], r.X[(int64_t)q * r.ldx + k], acc);
+    } else if (r.kind == RG_BIAS) {
+      for (int q = 0; q < r.rows; ++q) acc += r.dY[q * r.N + (int)e];
+    } else if (r.kind == RG_LN_GAMMA) {
+      for (int q = 0; q < r.rows; ++q) acc = fmaf(r.dY[q * 128 + (int)e], r.X[q * 128 + (int)e], acc);
+    } else {   // embedding rows: repeated labels summed in batch order
+      const int l = (int)(e / 128), c = (int)(e % 128);
+      for (int q = 0; q < r.rows; ++q) {
+        int64_t lb = labels[q];
+        lb = lb < 0 ? 0 : (lb >= label_rows ? label_rows - 1 : lb);
+        if (lb == l) acc += r.dY[q * 128 + c];
+      }
     }
-  __syncthreads();
-  }  // phase != 2
-  if (phase == 1) return;
+    G.p[t][e] = acc;
+    gi = acc;
+    if (phase == 1) return;
+  } else {
+    gi = G.p[t][e];
+    if (has_g_add) gi += GA.p[t][e];
+  }
   // torch.optim.Adam (single-tensor math): m.lerp_(g, 1-b1); v = v*b2 + (1-b2) g g; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
   const float step_size = (float)((double)ad.lr / ad.bc1);
   const float bc2s = (float)ad.bc2_sqrt;
-  for (int t = 0; t < R_NUM; ++t) {
-    float* p = P.p[t]; const float* g = G.p[t]; float* m = M.p[t]; float* v = V.p[t];
-    const float* ga = has_g_add ? GA.p[t] : nullptr;
-    for (int64_t i = threadIdx.x; i < N.n[t]; i += blockDim.x) {
-      const float gi = ga ? g[i] + ga[i] : g[i];
-      const float mi = m[i] + 0.1f * (gi - m[i]);
-      const float vi = v[i] * 0.999f + (0.001f * gi) * gi;
-      m[i] = mi;
-      v[i] = vi;
-      const float denom = sqrtf(vi) / bc2s + 1e-8f;
-      p[i] = p[i] - step_size * (mi / denom);
-    }
-  }
+  const float m0 = M.p[t][e], v0 = V.p[t][e];
+  const float mi = m0 + 0.1f * (gi - m0);
+  const float vi = v0 * 0.999f + (0.001f * gi) * gi;
+  M.p[t][e] = mi;
+  V.p[t][e] = vi;
+  const float denom = sqrtf(vi) / bc2s + 1e-8f;
+  P.p[t][e] = P.p[t][e] - step_size * (mi / denom);
 }
 
 static void fill_ptrs(RewPtrs& dst, float* const* src) {
@@ -534,7 +568,21 @@ extern "C" int srw_ssl_loss(const srw_ssl_loss_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SRW_REQUIRE(a && a->logits_lb && a->logits_s && a->y_lb && a->pseudo && a->mask && a->losses, "srw_ssl_loss: null pointer");
   SRW_REQUIRE(a->B_lb > 0 && a->B_lb <= MAX_ROWS && a->B_ulb > 0 && a->B_ulb <= MAX_ROWS && a->num_classes > 0, "srw_ssl_loss: batch sizes must be in (0, %d]", MAX_ROWS);
-  ssl_loss_kernel<<<1, SSL_THREADS, 0, stream>>>(*a);
+  RewPtrs RP = {};
+  int use_smem = 0;
+  size_t dyn = 0;
+  if (a->rp) {
+    SRW_REQUIRE(a->feats && a->feature_dim > 0 && a->label_rows > 0 && a->rew_workspace, "srw_ssl_loss: the fused Rewarder needs feats, feature_dim, label_rows and rew_workspace");
+    for (int i = 0; i < R_NUM; ++i) RP.p[i] = const_cast<float*>(a->rp[i]);
+    const int64_t wsf = rew_ws_floats(a->B_ulb);
+    use_smem = wsf * 4 <= 176 * 1024 ? 1 : 0;    // next to the kernel's 24 KB of static shared memory
+    dyn = use_smem ? (size_t)wsf * 4 : 0;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(ssl_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024); });
+    SRW_CUDA(attr_err);
+  }
+  ssl_loss_kernel<<<1, SSL_THREADS, dyn, stream>>>(*a, RP, a->rp ? 1 : 0, use_smem);
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;
@@ -552,7 +600,14 @@ extern "C" int srw_rewarder_fwd(const srw_rewarder_fwd_args* a, void* stream_) {
   SRW_REQUIRE(a->B > 0 && a->B <= MAX_ROWS && a->feature_dim > 0 && a->label_rows > 0, "srw_rewarder_fwd: bad shape");
   RewPtrs P;
   for (int i = 0; i < R_NUM; ++i) P.p[i] = const_cast<float*>(a->rp[i]);
-  rewarder_fwd_kernel<<<1, SSL_THREADS, 0, stream>>>(P, a->feats, a->ld_feats, a->labels, a->B, a->feature_dim, a->label_rows, a->reward, a->workspace);
+  const int64_t wsf = rew_ws_floats(a->B);
+  const int use_smem = wsf * 4 <= 200 * 1024 ? 1 : 0;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(rewarder_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+  SRW_CUDA(attr_err);
+  rewarder_fwd_kernel<<<1, SSL_THREADS, use_smem ? (size_t)wsf * 4 : 0, stream>>>(P, a->feats, a->ld_feats, a->labels, a->B, a->feature_dim, a->label_rows, a->reward,
+                                                                                a->workspace, use_smem);
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;
@@ -586,8 +641,44 @@ extern "C" int srw_rewarder_train(const srw_rewarder_train_args* a, void* stream
   ad.lr = a->lr;
   ad.bc1 = 1.0 - pow(0.9, (double)a->step);
   ad.bc2_sqrt = sqrt(1.0 - pow(0.999, (double)a->step));
-  rewarder_train_kernel<<<1, SSL_THREADS, 0, stream>>>(P, G, M, V, N, a->feats, a->ld_feats, a->gen_labels, a->true_labels, a->B, a->feature_dim,
-                                                      a->label_rows, ad, a->phase, a->losses, a->workspace, a->loss_select, GA, a->g_add ? 1 : 0);
+  const int B = a->B;
+  if (a->phase != 2) {
+    const int64_t wsf = rew_ws_floats(B);
+    const int use_smem = wsf * 4 <= 200 * 1024 ? 1 : 0;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(rewarder_actgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    SRW_CUDA(attr_err);
+    rewarder_actgrad_kernel<<<1, SSL_THREADS, use_smem ? (size_t)wsf * 4 : 0, stream>>>(P, a->feats, a->ld_feats, a->gen_labels, a->true_labels, B, a->feature_dim,
+                                                                                     a->label_rows, a->losses, a->workspace, a->loss_select, use_smem);
+    g_launches++;
+    SRW_LAUNCH_CHECK();
+  }
+  // gradient recipes (workspace offsets of rew_carve)
+  RewGradTable tab = {};
+  {
+    const RewWs c = rew_carve(a->workspace, B);
+    float *fxh = c.fxh, *X = c.X, *exh = c.exh, *h = c.h, *h1 = c.h1, *h2 = c.h2, *h3 = c.h3, *dz4 = c.dz4, *dh3 = c.dh3, *dh2 = c.dh2, *dh1 = c.dh1,
+          *dX = c.dX, *du = c.du, *demb = c.demb, *da = c.da;
+    auto lin = [&](int t, int rows, int N_, int K_, const float* dY, const float* Xp, int64_t ldx) {
+      tab.t[t].kind = RG_LINEAR; tab.t[t].rows = rows; tab.t[t].N = N_; tab.t[t].K = K_; tab.t[t].dY = dY; tab.t[t].X = Xp; tab.t[t].ldx = ldx;
+    };
+    auto bias = [&](int t, int rows, int N_, const float* dY) { tab.t[t].kind = RG_BIAS; tab.t[t].rows = rows; tab.t[t].N = N_; tab.t[t].K = 1; tab.t[t].dY = dY; };
+    auto lng = [&](int t, int rows, const float* dY, const float* xh) { tab.t[t].kind = RG_LN_GAMMA; tab.t[t].rows = rows; tab.t[t].N = 128; tab.t[t].K = 128; tab.t[t].dY = dY; tab.t[t].X = xh; };
+    lin(R_FCW, B, 128, a->feature_dim, du, a->feats, a->ld_feats); bias(R_FCB, B, 128, du);
+    lng(R_FNW, B, dX, fxh); bias(R_FNB, B, 128, dX);
+    tab.t[R_EMB].kind = RG_EMB; tab.t[R_EMB].rows = B; tab.t[R_EMB].N = 128; tab.t[R_EMB].K = 128; tab.t[R_EMB].dY = demb;
+    lng(R_LNW, B, dX + B * 128, exh); bias(R_LNB, B, 128, dX + B * 128);
+    lin(R_CAW, 2 * B, 1, 128, da, X, 128); bias(R_CAB, 2 * B, 1, da);
+    lin(R_M1W, B, 256, 128, dh1, h, 128); bias(R_M1B, B, 256, dh1);
+    lin(R_M2W, B, 128, 256, dh2, h1, 256); bias(R_M2B, B, 128, dh2);
+    lin(R_F1W, B, 64, 128, dh3, h2, 128); bias(R_F1B, B, 64, dh3);
+    lin(R_F2W, B, 1, 64, dz4, h3, 64); bias(R_F2B, B, 1, dz4);
+    int64_t off = 0;
+    for (int i = 0; i < R_NUM; ++i) { tab.t[i].first = off; off += N.n[i]; }
+    tab.total = off;
+  }
+  rewarder_wgrad_adam_kernel<<<(int)cdiv64(tab.total, 256), 256, 0, stream>>>(P, G, M, V, GA, a->g_add ? 1 : 0, tab, a->gen_labels, a->label_rows, ad, a->phase);
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;

@@ -303,3 +303,40 @@ def test_softmatch_mask_data_parallel_view():
         if align:
             assert (dah.p_model.cpu() - da.p_model).abs().max().item() < 1e-6
         assert (w.cpu() - ref_w).abs().max().item() < 2e-6, f"call {call}"
+
+
+@pytest.mark.parametrize("B,C,D", [(8, 100, 384), (24, 10, 768), (128, 1000, 768)])
+def test_fused_stage2_epilogue_equals_separate_launches(B, C, D):
+    """north_star's "one fused epilogue kernel": srw_ssl_loss with the Rewarder inside (forward -> mean-threshold mask2 -> masked
+    consistency CE -> dlogits, one launch) against srw_rewarder_fwd followed by srw_ssl_loss — bit-identical (same device code),
+    and against the oracle's functions.  B = 8 / 24 keep the Rewarder's intermediates in shared memory, B = 128 in the workspace."""
+    from oracle import ssl_oracle as O
+    from semireward_b200 import detgen
+    from semireward_b200.algorithms.semireward import Rewarder, label_dim
+    from semireward_b200.algorithms.srflexmatch import _ssl_loss_native
+    R = Rewarder(label_dim(C), 128, D)
+    rp = {n: torch.from_numpy(detgen.fill_param("rewarder." + n, s, 0)) for n, s in O.rewarder_param_shapes(D, C)}
+    with torch.no_grad():
+        for n, q in R.named_parameters():
+            q.copy_(rp[n])
+    R = R.cuda()
+    feats = torch.from_numpy(detgen.normal("f", (B, D), 3)).cuda()
+    llb = torch.from_numpy(detgen.normal("llb", (8, C), 4, std=2.0)).cuda()
+    ls = torch.from_numpy(detgen.normal("ls", (B, C), 5, std=2.0)).cuda()
+    y = torch.from_numpy(detgen.integers("y", (8,), 0, C, 6)).cuda()
+    pseudo = torch.from_numpy(detgen.integers("p", (B,), 0, C, 7)).cuda()
+    mask = (torch.from_numpy(detgen.normal("m", (B,), 8)) > -0.3).float().cuda()
+    dl1, ds1, dl2, ds2 = (torch.empty(8, C, device="cuda"), torch.empty(B, C, device="cuda"), torch.empty(8, C, device="cuda"), torch.empty(B, C, device="cuda"))
+    reward = R(feats, pseudo)
+    lo_a, m2_a = _ssl_loss_native(llb, ls, y, pseudo, mask, reward.view(-1), 1.0, dl1, ds1)
+    lo_b, m2_b = _ssl_loss_native(llb, ls, y, pseudo, mask, None, 1.0, dl2, ds2, rewarder=R, feats=feats)
+    torch.cuda.synchronize()
+    assert torch.equal(m2_a, m2_b) and torch.equal(lo_a[:4], lo_b[:4]) and torch.equal(dl1, dl2) and torch.equal(ds1, ds2)
+    r_ref = O.rewarder_forward(rp, feats.cpu(), pseudo.cpu())
+    assert (reward.cpu() - r_ref).abs().max().item() < 2e-6
+    m2_ref = torch.where(r_ref >= r_ref.mean(), 1, 0).squeeze().float()
+    tied = ((r_ref - r_ref.mean()).abs() <= 4e-7 * r_ref.mean().abs()).flatten()
+    assert torch.equal(m2_b.cpu()[~tied], m2_ref[~tied])
+    if not tied.any():
+        unsup_ref = O.consistency_loss(ls.cpu(), pseudo.cpu(), mask.cpu(), m2_ref)
+        assert abs(float(lo_b[1]) - float(unsup_ref)) < 1e-5 * max(1.0, abs(float(unsup_ref)))
