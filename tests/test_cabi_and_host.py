@@ -305,10 +305,20 @@ def test_combined_class_steps_through_the_reference_train_loop(tmp_path, monkeyp
         assert n1 == n2 and torch.equal(p1, p2)
     # and the registry route of INTEGRATION.md: the reference's get_algorithm now builds the combined native class
     import semilearn
-    reg = register_into_reference()
-    a3 = semilearn.get_algorithm(args, semilearn.get_net_builder("vit_small_patch2_32", False), None, None)
-    assert isinstance(a3, Native) and isinstance(a3, RefBase) and type(a3) is reg["srflexmatch"]
-    assert type(a3.model).__module__ == "semireward_b200.nets.vit"
+    import semilearn.nets as ref_nets
+    from semilearn.core.utils import ALGORITHMS as REF
+    saved_algs, saved_nets = dict(REF._dict), dict(vars(ref_nets))
+    try:
+        reg = register_into_reference()
+        a3 = semilearn.get_algorithm(args, semilearn.get_net_builder("vit_small_patch2_32", False), None, None)
+        assert isinstance(a3, Native) and isinstance(a3, RefBase) and type(a3) is reg["srflexmatch"]
+        assert type(a3.model).__module__ == "semireward_b200.nets.vit"
+    finally:   # the swap is process-wide: later live-reference tests must get the reference's own classes back
+        REF._dict.clear()
+        REF._dict.update(saved_algs)
+        for k, v in saved_nets.items():
+            if getattr(ref_nets, k, None) is not v:
+                setattr(ref_nets, k, v)
 
 
 def test_pretrained_loading_follows_the_reference_load_checkpoint(tmp_path):
