@@ -336,6 +336,80 @@ typedef struct {
 } srw_bert_bwd_args;
 int srw_bert_backward(const srw_bert_bwd_args* a, void* stream);
 
+/* ---- HuBERT engine: ClassificationHubert.forward / backward as two native calls -------------------------------- */
+/* Replaces `self.model(x, ...)` + dropout + mean + classifier of semilearn/nets/hubert/hubert.py:24-50 and autograd's backward of it.
+ * Arithmetic restated from transformers 5.5.0 modeling_hubert.py (not under /root/reference), architecture of
+ * facebook/hubert-base-ls960 (`feat_extract_norm='group'`, `do_stable_layer_norm=False`):
+ *   conv stem: 7 Conv1d without bias on the raw waveform, 512 channels, kernels (10,3,3,3,3,2,2), strides (5,2,2,2,2,2,2), GELU after each,
+ *              GroupNorm(512 groups = per channel over time) after the first                    -> F frames (199 for 64 000 samples)
+ *   feature projection: LayerNorm(512) -> Linear(512, hidden) -> dropout(p_feat_proj)
+ *   SpecAugment: frames flagged in `mask_time` are replaced by `masked_spec_embed`  (the host draws the spans like _compute_mask_indices)
+ *   positional conv: Conv1d(hidden, hidden, k = 128, pad 64, groups 16), weight-normalised per tap, last frame dropped, GELU;
+ *              x = dropout(LayerNorm(h + pos), p_hidden)
+ *   `layers` post-LN encoder layers (attention without any mask: hubert.py:45 passes none), each skipped per model call by LayerDrop
+ *   feat = mean over the F frames of dropout(x, p_pooled);  logits = gelu(feat Wc1 + bc1) Wc2 + bc2          (hubert.py:17-21,44-49)
+ * Layout in HBM: every conv-stem activation is time-major [clip, frame, channel] split planes, clips stacked with one padding frame each so
+ * that a strided Conv1d is ONE GEMM over an overlapping row view (row t of the im2col matrix = frames s t .. s t + k - 1, contiguous: lda =
+ * s * 512 < K = k * 512); the grouped positional conv is 16 GEMMs (one per group) over a group-major zero-padded copy of h (row stride 48).
+ * `params` / `grads`: device pointers in ClassificationHubert.state_dict() order = masked_spec_embed, conv0.weight, conv0.layer_norm.w, .b,
+ * conv{1..6}.weight, feature_projection {layer_norm.w, .b, projection.w, .b}, pos_conv_embed {bias, weight_g (original0), weight_v
+ * (original1)}, encoder.layer_norm {w, b}, per layer {k_proj.w, .b, v_proj.w, .b, q_proj.w, .b, out_proj.w, .b, layer_norm.w, .b,
+ * intermediate_dense.w, .b, output_dense.w, .b, final_layer_norm.w, .b}, classifier.0.w, .b, classifier.2.w, .b = 19 + 16 * layers + 4.
+ * Gradient layout requirement: the gradients of q_proj / k_proj / v_proj weights must be contiguous in THAT order (and their biases).
+ * Dropout sites (srw_dropout): 0 feature projection, 1 encoder input, 2 + 4 l attention probabilities, 3 + 4 l attention output,
+ * 4 + 4 l FFN activation, 5 + 4 l FFN output, 2 + 4 layers pooled features. */
+#define SRW_HUBERT_MAX_CONV 8
+typedef struct {
+  int hidden, layers, heads, intermediate, num_classes;
+  int conv_dim;                                    /* 512, all conv layers */
+  int num_conv; int conv_kernel[SRW_HUBERT_MAX_CONV]; int conv_stride[SRW_HUBERT_MAX_CONV];
+  int pos_kernel, pos_groups;                      /* 128, 16 */
+  float ln_eps;                                    /* 1e-5 (GroupNorm / LayerNorms) */
+  double p_feat_proj, p_hidden, p_attn, p_act, p_pooled;
+} srw_hubert_config;
+
+int srw_hubert_frames(const srw_hubert_config* c, int samples);                 /* F for clips of `samples` samples (< 0: invalid) */
+int64_t srw_hubert_weight_planes_bytes(const srw_hubert_config* c);
+int64_t srw_hubert_workspace_bytes(const srw_hubert_config* c, int batch, int samples, int grad_batch);
+/* rebuilds the whole plane cache (re-laid-out conv weights, weight-normalised positional taps, packed q|k|v): once per optimizer step */
+int srw_hubert_prepare_weights(const srw_hubert_config* c, const float* const* params, void* weight_planes, void* stream);
+
+typedef struct {
+  const srw_hubert_config* cfg;
+  const float* const* params;
+  const void* weight_planes;
+  const float* wav; int64_t ld_wav;             /* [batch, samples] fp32 */
+  int batch, samples;
+  int grad_batch;                               /* the first grad_batch clips will be back-propagated */
+  const uint8_t* mask_time;                     /* device [batch, F] (1 = frame replaced by masked_spec_embed) or NULL */
+  const uint32_t* drop_seq_key; const int32_t* drop_seq_row;   /* [batch] each, or NULL: no dropout */
+  /* LayerDrop: the launch is `num_segments` consecutive clip ranges (the model calls it stands for); segment_start is a HOST array
+   * [num_segments + 1] (first clip of each, last = batch), layer_skip a HOST array [num_segments, layers] (1 = that call skips the
+   * layer).  NULL / 0 = nothing skipped.  A boundary must not fall inside the gradient rows' range end: grad_batch is a boundary. */
+  int num_segments; const int32_t* segment_start; const uint8_t* layer_skip;
+  float* logits; float* feat;                   /* [batch, num_classes], [batch, hidden] */
+  void* workspace; int64_t workspace_bytes;
+  int gemm_impl;
+} srw_hubert_fwd_args;
+int srw_hubert_forward(const srw_hubert_fwd_args* a, void* stream);
+
+typedef struct {
+  const srw_hubert_config* cfg;
+  const float* const* params;
+  const void* weight_planes;
+  const float* wav; int64_t ld_wav;
+  int batch, samples, grad_batch;
+  const uint8_t* mask_time;
+  const uint32_t* drop_seq_key; const int32_t* drop_seq_row;
+  int num_segments; const int32_t* segment_start; const uint8_t* layer_skip;
+  const float* dlogits; const float* dfeat;     /* [grad_batch, C] and [grad_batch, hidden] (dfeat may be NULL) */
+  float* const* grads;                          /* same order as params */
+  int accumulate_grads;
+  void* workspace; int64_t workspace_bytes;
+  int gemm_impl;
+} srw_hubert_bwd_args;
+int srw_hubert_backward(const srw_hubert_bwd_args* a, void* stream);
+
 /* x[i] *= *scale for i < n, where scale is a DEVICE scalar; returns without touching memory when *scale == 1.  Used to
  * apply autograd's upstream gradient of the loss (normally exactly 1, param_update.py:33) to gradients that were
  * computed ahead of loss.backward(). */

@@ -53,6 +53,12 @@ class HubertCfg:
     pos_groups: int = 16
     eps: float = 1e-5
     num_classes: int = 10
+    # train-mode dropout probabilities (facebook/hubert-base-ls960: 0.1 each, layerdrop 0.1); 0 = deterministic parity mode
+    feat_proj_dropout: float = 0.0
+    hidden_dropout: float = 0.0
+    attention_dropout: float = 0.0
+    activation_dropout: float = 0.0
+    pooled_dropout: float = 0.0          # hubert.py:15 (the wrapper's own nn.Dropout(0.1))
 
     def frames(self, samples: int) -> int:
         n = samples
@@ -99,13 +105,32 @@ class HubertCfg:
         return fl + 2.0 * (H * H + H * self.num_classes)
 
 
-def hubert_forward(p: Dict[str, Tensor], x: Tensor, cfg: HubertCfg, mask_time_indices: Optional[Tensor] = None, skip_layers=()):
+class HubertDropout:
+    """Counter-based masks of one model call (include/srw.h `srw_dropout`; bert_oracle.counter_keep_mask): site 0 = feature
+    projection output [B, F, H], 1 = encoder input, 2 + 4 l = attention probabilities of layer l [B, heads, F, F], 3 + 4 l =
+    attention output, 4 + 4 l = FFN activation [B, F, I], 5 + 4 l = FFN output, 2 + 4 layers = the wrapper's dropout before the
+    mean pool.  A layer left out by LayerDrop keeps its site numbers.  `key` None = no dropout."""
+
+    def __init__(self, key):
+        self.key = key
+
+    def __call__(self, x: Tensor, p: float, site: int) -> Tensor:
+        if self.key is None or p == 0.0:
+            return x
+        from .bert_oracle import counter_keep_mask
+        keep = 1.0 - p
+        return x * counter_keep_mask(x.numel(), keep, self.key, site).view(x.shape).to(x.dtype).div_(keep)
+
+
+def hubert_forward(p: Dict[str, Tensor], x: Tensor, cfg: HubertCfg, mask_time_indices: Optional[Tensor] = None, skip_layers=(), drop_key=None):
     """-> (logits [B, C], feat [B, 768]).  x: fp32 [B, T].  Default = deterministic parity mode (no dropout / LayerDrop /
-    SpecAugment).  The two structural sources of randomness of a train-mode pass can be injected explicitly:
-    `mask_time_indices` bool [B, F] (SpecAugment: those frames are replaced by `masked_spec_embed` after the feature
-    projection, modeling_hubert.py `_mask_hidden_states`) and `skip_layers` (LayerDrop: encoder layers left out)."""
+    SpecAugment).  The sources of randomness of a train-mode pass are explicit inputs: `mask_time_indices` bool [B, F]
+    (SpecAugment: those frames are replaced by `masked_spec_embed` after the feature projection, modeling_hubert.py
+    `_mask_hidden_states`), `skip_layers` (LayerDrop: encoder layers left out) and `drop_key` (an int stream key: every
+    nn.Dropout of the call becomes the counter mask of HubertDropout with the cfg's probabilities)."""
     H, nh = cfg.hidden, cfg.heads
     dh = H // nh
+    drop = HubertDropout(drop_key)
     h = x[:, None]
     for i in range(len(cfg.conv_dim)):
         pre = f"model.feature_extractor.conv_layers.{i}."
@@ -116,6 +141,7 @@ def hubert_forward(p: Dict[str, Tensor], x: Tensor, cfg: HubertCfg, mask_time_in
     h = h.transpose(1, 2)                                                     # [B, F, 512]
     h = F.layer_norm(h, (cfg.conv_dim[-1],), p["model.feature_projection.layer_norm.weight"], p["model.feature_projection.layer_norm.bias"], cfg.eps)
     h = F.linear(h, p["model.feature_projection.projection.weight"], p["model.feature_projection.projection.bias"])
+    h = drop(h, cfg.feat_proj_dropout, 0)
     B, Fr, _ = h.shape
     if mask_time_indices is not None:
         h = torch.where(mask_time_indices[..., None], p["model.masked_spec_embed"].to(h.dtype), h)
@@ -128,6 +154,7 @@ def hubert_forward(p: Dict[str, Tensor], x: Tensor, cfg: HubertCfg, mask_time_in
         pos = pos[:, :, :-1]
     pos = F.gelu(pos).transpose(1, 2)
     h = F.layer_norm(h + pos, (H,), p["model.encoder.layer_norm.weight"], p["model.encoder.layer_norm.bias"], cfg.eps)
+    h = drop(h, cfg.hidden_dropout, 1)
     for i in range(cfg.layers):
         if i in skip_layers:
             continue
@@ -135,14 +162,15 @@ def hubert_forward(p: Dict[str, Tensor], x: Tensor, cfg: HubertCfg, mask_time_in
         q = F.linear(h, p[pre + "attention.q_proj.weight"], p[pre + "attention.q_proj.bias"]).view(B, Fr, nh, dh).transpose(1, 2)
         k = F.linear(h, p[pre + "attention.k_proj.weight"], p[pre + "attention.k_proj.bias"]).view(B, Fr, nh, dh).transpose(1, 2)
         vv = F.linear(h, p[pre + "attention.v_proj.weight"], p[pre + "attention.v_proj.bias"]).view(B, Fr, nh, dh).transpose(1, 2)
-        a = F.softmax(torch.matmul(q, k.transpose(2, 3)) * (dh ** -0.5), dim=-1)
+        a = drop(F.softmax(torch.matmul(q, k.transpose(2, 3)) * (dh ** -0.5), dim=-1), cfg.attention_dropout, 2 + 4 * i)
         ctx = torch.matmul(a, vv).transpose(1, 2).contiguous().reshape(B, Fr, H)
-        o = F.linear(ctx, p[pre + "attention.out_proj.weight"], p[pre + "attention.out_proj.bias"])
+        o = drop(F.linear(ctx, p[pre + "attention.out_proj.weight"], p[pre + "attention.out_proj.bias"]), cfg.hidden_dropout, 3 + 4 * i)
         h = F.layer_norm(h + o, (H,), p[pre + "layer_norm.weight"], p[pre + "layer_norm.bias"], cfg.eps)
         f = F.gelu(F.linear(h, p[pre + "feed_forward.intermediate_dense.weight"], p[pre + "feed_forward.intermediate_dense.bias"]))
-        f = F.linear(f, p[pre + "feed_forward.output_dense.weight"], p[pre + "feed_forward.output_dense.bias"])
+        f = drop(f, cfg.activation_dropout, 4 + 4 * i)
+        f = drop(F.linear(f, p[pre + "feed_forward.output_dense.weight"], p[pre + "feed_forward.output_dense.bias"]), cfg.hidden_dropout, 5 + 4 * i)
         h = F.layer_norm(h + f, (H,), p[pre + "final_layer_norm.weight"], p[pre + "final_layer_norm.bias"], cfg.eps)
-    feat = torch.mean(h, 1)
+    feat = torch.mean(drop(h, cfg.pooled_dropout, 2 + 4 * cfg.layers), 1)
     z = F.gelu(F.linear(feat, p["classifier.0.weight"], p["classifier.0.bias"]))
     return F.linear(z, p["classifier.2.weight"], p["classifier.2.bias"]), feat
 
@@ -169,18 +197,30 @@ def hubert_param_hparams(names_shapes, layers: int, lr: float, weight_decay: flo
 
 
 class HubertSSLOracle(O.SSLOracle):
-    """ssl_oracle.SSLOracle with the audio backbone and `use_cat: False` (three calls; the weak one under no_grad)."""
+    """ssl_oracle.SSLOracle with the audio backbone and `use_cat: False` (three calls; the weak one under no_grad).
+    `drop_seed` (int) switches the counter-based dropout on: call c of the run uses stream key call_key(drop_seed, c).
+    `stochastic_inputs(call) -> (mask_time_indices, skip_layers)` injects SpecAugment / LayerDrop decisions per call."""
 
     def __init__(self, hubert_cfg: HubertCfg, cfg: O.StepConfig, params, rewarder, generator):
         hp = hubert_param_hparams(hubert_cfg.param_shapes(), hubert_cfg.layers, cfg.lr, cfg.weight_decay, cfg.layer_decay)
         super().__init__(None, cfg, params, rewarder, generator, hparams=hp)
         self.hubert_cfg = hubert_cfg
+        self.drop_seed = None
+        self.calls = 0
+        self.stochastic_inputs = None
+
+    def _call(self, x):
+        from .bert_oracle import call_key
+        key = None if self.drop_seed is None else call_key(self.drop_seed, self.calls)
+        mti, skip = (None, ()) if self.stochastic_inputs is None else self.stochastic_inputs(self.calls)
+        self.calls += 1
+        return hubert_forward(self.p, x, self.hubert_cfg, mask_time_indices=mti, skip_layers=skip, drop_key=key)
 
     def _backbone(self, x_lb, x_ulb_w, x_ulb_s):
-        llb, flb = hubert_forward(self.p, x_lb, self.hubert_cfg)
-        ls, fs = hubert_forward(self.p, x_ulb_s, self.hubert_cfg)
+        llb, flb = self._call(x_lb)
+        ls, fs = self._call(x_ulb_s)
         with torch.no_grad():
-            lw, fw = hubert_forward(self.p, x_ulb_w, self.hubert_cfg)
+            lw, fw = self._call(x_ulb_w)
         return llb, lw, ls, flb, fw, fs
 
 

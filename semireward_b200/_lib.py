@@ -118,6 +118,30 @@ class BertBwdArgs(C.Structure):
                 ("gemm_impl", i32), ("layer_lo", i32), ("layer_hi", i32)]
 
 
+HUBERT_MAX_CONV = 8
+
+
+class HubertConfig(C.Structure):
+    _fields_ = [("hidden", i32), ("layers", i32), ("heads", i32), ("intermediate", i32), ("num_classes", i32), ("conv_dim", i32),
+                ("num_conv", i32), ("conv_kernel", i32 * HUBERT_MAX_CONV), ("conv_stride", i32 * HUBERT_MAX_CONV), ("pos_kernel", i32),
+                ("pos_groups", i32), ("ln_eps", f32), ("p_feat_proj", C.c_double), ("p_hidden", C.c_double), ("p_attn", C.c_double),
+                ("p_act", C.c_double), ("p_pooled", C.c_double)]
+
+
+class HubertFwdArgs(C.Structure):
+    _fields_ = [("cfg", C.POINTER(HubertConfig)), ("params", C.POINTER(vp)), ("weight_planes", vp), ("wav", vp), ("ld_wav", i64),
+                ("batch", i32), ("samples", i32), ("grad_batch", i32), ("mask_time", vp), ("drop_seq_key", vp), ("drop_seq_row", vp),
+                ("num_segments", i32), ("segment_start", vp), ("layer_skip", vp), ("logits", vp), ("feat", vp), ("workspace", vp),
+                ("workspace_bytes", i64), ("gemm_impl", i32)]
+
+
+class HubertBwdArgs(C.Structure):
+    _fields_ = [("cfg", C.POINTER(HubertConfig)), ("params", C.POINTER(vp)), ("weight_planes", vp), ("wav", vp), ("ld_wav", i64),
+                ("batch", i32), ("samples", i32), ("grad_batch", i32), ("mask_time", vp), ("drop_seq_key", vp), ("drop_seq_row", vp),
+                ("num_segments", i32), ("segment_start", vp), ("layer_skip", vp), ("dlogits", vp), ("dfeat", vp), ("grads", C.POINTER(vp)),
+                ("accumulate_grads", i32), ("workspace", vp), ("workspace_bytes", i64), ("gemm_impl", i32)]
+
+
 class RewarderFwdArgs(C.Structure):
     _fields_ = [("B", i32), ("feature_dim", i32), ("label_rows", i32), ("rp", C.POINTER(vp)), ("feats", vp), ("ld_feats", i64),
                 ("labels", vp), ("reward", vp), ("workspace", vp)]
@@ -227,6 +251,12 @@ SYMBOLS = [
     ("srw_bert_prepare_weights", i32, [C.POINTER(BertConfig), C.POINTER(vp), vp, vp]),
     ("srw_bert_forward", i32, [C.POINTER(BertFwdArgs), vp]),
     ("srw_bert_backward", i32, [C.POINTER(BertBwdArgs), vp]),
+    ("srw_hubert_frames", i32, [C.POINTER(HubertConfig), i32]),
+    ("srw_hubert_weight_planes_bytes", i64, [C.POINTER(HubertConfig)]),
+    ("srw_hubert_workspace_bytes", i64, [C.POINTER(HubertConfig), i32, i32, i32]),
+    ("srw_hubert_prepare_weights", i32, [C.POINTER(HubertConfig), C.POINTER(vp), vp, vp]),
+    ("srw_hubert_forward", i32, [C.POINTER(HubertFwdArgs), vp]),
+    ("srw_hubert_backward", i32, [C.POINTER(HubertBwdArgs), vp]),
     ("srw_set_graph_mode", i32, [i32]),
     ("srw_set_pdl_mode", i32, [i32]),
     ("srw_scale_inplace", i32, [vp, i64, vp, vp]),

@@ -118,6 +118,13 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
         v[j] *= gelu_grad_f(zz.x); v[j + 1] *= gelu_grad_f(zz.y); v[j + 2] *= gelu_grad_f(zz.z); v[j + 3] *= gelu_grad_f(zz.w);
       }
   }
+  if (p.drop.on) {   // activation dropout (HubertFeedForward.intermediate_dropout): h = drop(gelu(z)); backward: the same mask on the incoming gradient
+    const int sq = row / p.drop_rows_per_seq;
+    const uint32_t key = drop_site_key(p.drop.seq_key[sq], p.drop.site);
+    const uint32_t base = ((uint32_t)p.drop.seq_row[sq] * (uint32_t)p.drop_rows_per_seq + (uint32_t)(row - sq * p.drop_rows_per_seq)) * (uint32_t)p.N + (uint32_t)col0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = drop_kept(key, base + j, p.drop.thr24) ? v[j] * p.drop.inv_keep : 0.f;
+  }
   // planes out (SRW_EPI_PLANES, SRW_EPI_GELU, SRW_EPI_DGELU)
   __nv_bfloat16* hi = p.out_planes + (int64_t)row * p.ldp + col0;
   __nv_bfloat16* lo = hi + p.out_plane_stride;
@@ -149,17 +156,17 @@ __device__ __forceinline__ void drain_full(const EpiParams& ep, uint32_t acc_add
   const int row_first = m0 + q * 32 + sub_r;       // this lane's rows: row_first + 4 i
   float scale[8];
   uint32_t dkey[8], dbase[8];
-  const bool dropping = EPI == SRW_EPI_RESID && ep.drop.on;
+  const bool dropping = (EPI == SRW_EPI_RESID || EPI == SRW_EPI_GELU || EPI == SRW_EPI_DGELU) && ep.drop.on;
   if (EPI == SRW_EPI_RESID) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) scale[i] = ep.row_scale ? ep.row_scale[(row_first + 4 * i) / ep.rows_per_scale] : 1.0f;
-    if (dropping) {
+  }
+  if (dropping) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = row_first + 4 * i, sq = row / ep.drop_rows_per_seq;
-        dkey[i] = drop_site_key(ep.drop.seq_key[sq], ep.drop.site);
-        dbase[i] = ((uint32_t)ep.drop.seq_row[sq] * (uint32_t)ep.drop_rows_per_seq + (uint32_t)(row - sq * ep.drop_rows_per_seq)) * (uint32_t)ep.N;
-      }
+    for (int i = 0; i < 8; ++i) {
+      const int row = row_first + 4 * i, sq = row / ep.drop_rows_per_seq;
+      dkey[i] = drop_site_key(ep.drop.seq_key[sq], ep.drop.site);
+      dbase[i] = ((uint32_t)ep.drop.seq_row[sq] * (uint32_t)ep.drop_rows_per_seq + (uint32_t)(row - sq * ep.drop_rows_per_seq)) * (uint32_t)ep.N;
     }
   }
 #pragma unroll 1
@@ -212,6 +219,13 @@ __device__ __forceinline__ void drain_full(const EpiParams& ep, uint32_t acc_add
       }
       if (EPI == SRW_EPI_DGELU) {
         x.x *= gelu_grad_f(pre[i].x); x.y *= gelu_grad_f(pre[i].y); x.z *= gelu_grad_f(pre[i].z); x.w *= gelu_grad_f(pre[i].w);
+      }
+      if ((EPI == SRW_EPI_GELU || EPI == SRW_EPI_DGELU) && dropping) {
+        const uint32_t b0 = dbase[i] + (uint32_t)col;
+        x.x = drop_kept(dkey[i], b0, ep.drop.thr24) ? x.x * ep.drop.inv_keep : 0.f;
+        x.y = drop_kept(dkey[i], b0 + 1, ep.drop.thr24) ? x.y * ep.drop.inv_keep : 0.f;
+        x.z = drop_kept(dkey[i], b0 + 2, ep.drop.thr24) ? x.z * ep.drop.inv_keep : 0.f;
+        x.w = drop_kept(dkey[i], b0 + 3, ep.drop.thr24) ? x.w * ep.drop.inv_keep : 0.f;
       }
       uint32_t h0, l0, h1, l1;
       split2(x.x, x.y, h0, l0);
@@ -808,7 +822,8 @@ static int fill_epi(const srw_gemm_args* a, EpiParams& ep) {
   ep.out_planes = reinterpret_cast<__nv_bfloat16*>(a->out_planes); ep.ldp = a->ldp; ep.out_plane_stride = a->out_plane_stride;
   ep.workspace = a->workspace;
   ep.drop = make_drop(a->drop); ep.drop_rows_per_seq = a->drop_rows_per_seq > 0 ? a->drop_rows_per_seq : 1;
-  SRW_REQUIRE(!ep.drop.on || a->epilogue == SRW_EPI_RESID, "srw_gemm: dropout is part of SRW_EPI_RESID only");
+  SRW_REQUIRE(!ep.drop.on || a->epilogue == SRW_EPI_RESID || a->epilogue == SRW_EPI_GELU || a->epilogue == SRW_EPI_DGELU,
+              "srw_gemm: dropout is part of SRW_EPI_RESID / SRW_EPI_GELU / SRW_EPI_DGELU only");
   SRW_REQUIRE(a->N % 4 == 0, "srw_gemm: N must be a multiple of 4 (N=%d)", a->N);
   switch (a->epilogue) {
     case SRW_EPI_F32: SRW_REQUIRE(a->out_f32 && a->ldo % 4 == 0, "srw_gemm: EPI_F32 needs out_f32, ldo%%4==0"); break;

@@ -132,57 +132,30 @@ __global__ void __launch_bounds__(SSL_THREADS) flexmatch_mask_kernel(const srw_f
 // ------------------------------------------------------------------------------------------------
 enum { ACT_NONE = 0, ACT_RELU = 1 };
 
-// out[r, n] = act(bias[n] + sum_k in[r, k] W[n, k]).  One warp per output COLUMN n and chunk of 8 rows, lanes over k: every weight
-// row is read once per 8 batch rows (coalesced) instead of once per output, and a warp runs 8 independent accumulators — the
-// online-update kernels are one CTA deep, so the number of dependent L2 round trips per phase is what they cost.
-// Summation order per output is unchanged (lane-strided partial sums, then the xor-shuffle tree): results are bit-identical.
+// out[r, n] = act(bias[n] + sum_k in[r, k] W[n, k]);  one warp per output, lanes over k (coalesced W rows)
 __device__ void cta_linear(const float* in, int64_t ld_in, int rows, int K, const float* W, const float* bias, int N, float* out, int ld_out,
                            int act) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int rchunks = (rows + 7) / 8;
-  for (int o = warp; o < rchunks * N; o += nw) {
-    const int n = o % N, r0 = (o / N) * 8;
-    const int nr = min(8, rows - r0);
+  for (int o = warp; o < rows * N; o += nw) {
+    const int r = o / N, n = o % N;
+    const float* x = in + (int64_t)r * ld_in;
     const float* w = W + (int64_t)n * K;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-      const float wv = w[k];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < nr) acc[j] = fmaf(in[(int64_t)(r0 + j) * ld_in + k], wv, acc[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (j < nr) {
-        float v = warp_sum(acc[j]);
-        if (lane == 0) {
-          v += bias[n];
-          out[(int64_t)(r0 + j) * ld_out + n] = (act == ACT_RELU) ? fmaxf(v, 0.f) : v;
-        }
-      }
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(x[k], w[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      acc += bias[n];
+      out[(int64_t)r * ld_out + n] = (act == ACT_RELU) ? fmaxf(acc, 0.f) : acc;
     }
   }
 }
-// dX[r, k] = sum_n dY[r, n] W[n, k]: one thread per column k and chunk of 8 rows (W read once per 8 rows, coalesced over k)
+// dX[r, k] = sum_n dY[r, n] W[n, k]
 __device__ void cta_linear_dx(const float* dY, int rows, int N, const float* W, int K, float* dX) {
-  const int rchunks = (rows + 7) / 8;
-  for (int o = threadIdx.x; o < rchunks * K; o += blockDim.x) {
-    const int k = o % K, r0 = (o / K) * 8;
-    const int nr = min(8, rows - r0);
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int n = 0; n < N; ++n) {
-      const float wv = W[(int64_t)n * K + k];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < nr) acc[j] = fmaf(dY[(r0 + j) * N + n], wv, acc[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < nr) dX[(r0 + j) * K + k] = acc[j];
+  for (int o = threadIdx.x; o < rows * K; o += blockDim.x) {
+    const int r = o / K, k = o % K;
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n) acc = fmaf(dY[r * N + n], W[(int64_t)n * K + k], acc);
+    dX[o] = acc;
   }
 }
 // dW[n, k] = sum_r dY[r, n] X[r, k];  db[n] = sum_r dY[r, n]
