@@ -46,8 +46,15 @@ YAML_CFG4 = dict(algorithm="srsoftmatch", net="bert_base_uncased", optim="AdamW"
                  ulb_dest_len=25000, feature_dim=768, sr_lr=5e-4, sr_ema=False, use_cat=False, amp=False, ema_m=0.0, max_length=512,
                  ulb_loss_ratio=1.0, clip_grad=0, dist_align=True, dist_uniform=True, ema_p=0.999, n_sigma=2, per_class=False, hard_label=True, T=0.5)
 F_FWD_GF4 = 96.64          # GFLOP per sequence forward at L = 512
+# BASELINE configs[4]: config/SemiReward/usb_audio/flexmatch/flexmatch_urbansound8k_100_0.yaml unchanged (hubert_base, 10 classes,
+# use_cat False, 4 s @ 16 kHz, AdamW lr 5e-5, layer_decay 0.75), 2 ranks (SURVEY.md §8d "Config 5"); `--config 5`.
+YAML_CFG5 = dict(algorithm="srflexmatch", net="hubert_base", optim="AdamW", lr=5e-5, layer_decay=0.75, weight_decay=2e-5,
+                 num_train_iter=102400, num_warmup_iter=5120, start_timing=10000, N_k=10, batch_size=8, uratio=1, num_classes=10,
+                 ulb_dest_len=7000, feature_dim=768, sr_lr=5e-4, sr_ema=False, use_cat=False, amp=False, ema_m=0.0, max_length_seconds=4.0,
+                 sample_rate=16000, p_cutoff=0.95, thresh_warmup=True, hard_label=True, T=0.5, ulb_loss_ratio=1.0, clip_grad=0)
+F_FWD_GF5 = 56.9           # GFLOP per 4 s clip forward (oracle/hubert_oracle.py HubertCfg.fwd_flops_per_clip)
 METRICS = {2: "SSL train-step samples/sec (ViT-S CIFAR-100)", 3: "SSL train-step samples/sec (ViT-S CIFAR-100)",
-           4: "SSL train-step samples/sec (BERT-base IMDb)"}
+           4: "SSL train-step samples/sec (BERT-base IMDb)", 5: "SSL train-step samples/sec (HuBERT-base UrbanSound8k)"}
 
 
 def workload_name(config, B, uratio, stage):
@@ -55,18 +62,21 @@ def workload_name(config, B, uratio, stage):
         return f"srflexmatch vit_small_patch2_32 cifar100 batch_size {B} uratio {uratio} stage {stage} (BASELINE configs[1])"
     if config == 3:
         return f"srfreematch vit_base_patch16_224 synthetic 224x224 1000 classes batch_size {B} per GPU stage {stage} (BASELINE configs[2])"
+    if config == 5:
+        return (f"srflexmatch hubert_base 64000-sample clips (4 s @ 16 kHz) 10 classes batch_size {B} uratio {uratio} stage {stage}, dropout 0.1 at every site, "
+                f"SpecAugment on, LayerDrop off (BASELINE configs[4])")
     return f"srsoftmatch bert_base_uncased max_length 512 2 classes batch_size {B} uratio {uratio} stage {stage}, padding tails, dropout 0.1 (BASELINE configs[3])"
 
 
 def config_block(config, B, uratio, stage, world, setup_steps):
     """The `config` object of the JSON line; both arms (native, reference) print the same keys."""
     per = B * (1 + 2 * uratio)
-    f = {2: F_FWD_GF, 3: F_FWD_GF3, 4: F_FWD_GF4}[config]
+    f = {2: F_FWD_GF, 3: F_FWD_GF3, 4: F_FWD_GF4, 5: F_FWD_GF5}[config]
     return dict(workload=workload_name(config, B, uratio, stage), samples_per_step_per_gpu=per, parallelism=f"dp{world}",
-                drop_path=0.2 if config in (2, 3) else None, dropout=0.1 if config == 4 else None, setup_steps=setup_steps,
+                drop_path=0.2 if config in (2, 3) else None, dropout=0.1 if config in (4, 5) else None, setup_steps=setup_steps,
                 arithmetic="fp32 semantics: bf16x3 split-precision tcgen05 MMA, fp32 accumulate",
-                l2=("step working set (~1.8 GB of activations at batch 8) >> 126 MB L2; rotating input batches" if config != 4 else
-                    "step working set (~8 GB of activations at batch 8, L 512) >> 126 MB L2; rotating input batches"),
+                l2=("step working set (~1.8 GB of activations at batch 8) >> 126 MB L2; rotating input batches" if config not in (4, 5) else
+                    "step working set (~7-8 GB of activations at batch 8) >> 126 MB L2; rotating input batches"),
                 launch="CUDA-graph replay of the backbone forward/backward (SRW_GRAPHS) + programmatic dependent launch (SRW_PDL); "
                        "backward launched inside train_step ahead of the loss read-back",
                 algorithmic_gflop_per_step_per_gpu=B * (3 + 4 * uratio) * f)   # forward on B (1 + 2u) rows + backward (2x) on the B (1 + u) gradient rows
@@ -81,8 +91,8 @@ def parse():
     ap.add_argument("--batch-size", type=int, default=8, help="per-GPU labelled batch (config-faithful: 8)")
     ap.add_argument("--stage", type=int, default=1, choices=[1, 2])
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
-                    help="BASELINE.json configs index + 1: 2 = headline ViT-S CIFAR-100, 3 = ViT-B/16 224 FreeMatch; 1 (WRN-28-2), 4 (BERT-base) and "
-                         "5 (HuBERT-base) have no CUDA path yet and exist for --impl reference only (CPU oracle timing); 4 = BERT-base text (native)")
+                    help="BASELINE.json configs index + 1: 2 = headline ViT-S CIFAR-100, 3 = ViT-B/16 224 FreeMatch, 4 = BERT-base text, 5 = HuBERT-base "
+                         "audio; 1 (WRN-28-2) has no CUDA path and exists for --impl reference only (CPU oracle timing)")
     ap.add_argument("--no-eager-leg", action="store_true", help="skip the informational torch-eager fp32 leg on the same GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -249,12 +259,40 @@ def cpu_reference_bert(B, u, steps, warmup, dropout):
     return B * (1 + 2 * u) / per_step, per_step, cores
 
 
+def cpu_reference_hubert(B, u, steps, warmup, dropout):
+    """BASELINE configs[4] on the host cores: the oracle restatement of ClassificationHubert + SRFlexMatch step (pinned against the live
+    reference and Hugging Face HubertModel, tests/test_hubert_oracle.py), hubert-base, 4 s clips.  -> (samples/s, s/step, cores)."""
+    import torch
+    from oracle import hubert_oracle as HO, ssl_oracle as O
+    from semireward_b200 import detgen
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c = YAML_CFG5
+    sc = O.StepConfig(algorithm="srflexmatch", num_classes=c["num_classes"], lr=c["lr"], weight_decay=c["weight_decay"], layer_decay=c["layer_decay"],
+                      feature_dim=768, ulb_dest_len=c["ulb_dest_len"], start_timing=c["start_timing"], N_k=c["N_k"], num_train_iter=c["num_train_iter"],
+                      num_warmup_iter=c["num_warmup_iter"], sr_lr=c["sr_lr"], p_cutoff=c["p_cutoff"], thresh_warmup=c["thresh_warmup"])
+    p = dropout
+    orc = HO.build_det_hubert_oracle(HO.HubertCfg(num_classes=c["num_classes"], feat_proj_dropout=p, hidden_dropout=p, attention_dropout=p,
+                                                  activation_dropout=p, pooled_dropout=p), sc, seed=0)
+    orc.drop_seed = 0 if p > 0 else None
+    times = []
+    for i in range(warmup + steps):
+        b = O.to_torch_batch(detgen.audio_batch(B, u, c["num_classes"], c["ulb_dest_len"], samples=64000, seed=1, step=i))
+        t0 = time.perf_counter()
+        orc.train_step(b, 1 + i)
+        orc.param_update()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    per_step = sum(times) / len(times)
+    return B * (1 + 2 * u) / per_step, per_step, cores
+
+
 def main_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     note = "one CPU process on the host cores whatever --gpus says (the reference's CPU path does not shard over GPUs)"
-    if a.config in (1, 5):
+    if a.config == 1:
         steps, warmup = max(1, min(a.steps, 2)), max(0, min(a.warmup, 1))     # tens of seconds per CPU step
         sps, per_step, cores, name, what, samples = cpu_reference_run_other(a.config, steps, warmup)
         print(json.dumps(dict(impl="reference", metric=f"SSL train-step samples/sec ({name})", value=sps, unit="samples/s", n_gpus=a.gpus, steps=steps,
@@ -269,6 +307,11 @@ def main_reference(a):
         B = a.batch_size
         sps, per_step, cores = cpu_reference_bert(B, 1, steps, warmup, 0.1)
         sample = f"{steps} stage-1 step(s) of the oracle restatement at the full batch (dropout 0.1 from torch's CPU generator), {warmup} warm-up"
+    elif a.config == 5:
+        steps, warmup = max(1, min(a.steps, 2)), max(0, min(a.warmup, 1))
+        sps, per_step, cores = cpu_reference_hubert(a.batch_size, 1, steps, warmup, 0.1)
+        sample = (f"{steps} stage-1 step(s) of the oracle restatement at the full batch (counter-based dropout 0.1 at every site; LayerDrop and SpecAugment off), "
+                  f"{warmup} warm-up")
     else:
         cfg = dict(YAML_CFG, batch_size=a.batch_size)
         steps, warmup = max(1, min(a.steps, 8)), max(0, min(a.warmup, 2))   # bounded sample: ~1 s per CPU step, at most 8 + 2 steps
@@ -337,7 +380,7 @@ SETUP_STEPS = 12
 
 
 def main_native(a):
-    if a.config not in (2, 3, 4):
+    if a.config not in (2, 3, 4, 5):
         raise SystemExit(f"bench.py: BASELINE configs[{a.config - 1}] has no CUDA path yet (DESIGN.md §9); only --impl reference can time it")
     import torch
     import torch.distributed as dist
@@ -356,20 +399,28 @@ def main_native(a):
     lib = L.load()
     L.check(lib.srw_device_check(None, None, None), "srw_device_check")
 
-    base_cfg = {2: YAML_CFG, 3: YAML_CFG3, 4: YAML_CFG4}[a.config]
+    base_cfg = {2: YAML_CFG, 3: YAML_CFG3, 4: YAML_CFG4, 5: YAML_CFG5}[a.config]
     bs = a.batch_size if (a.batch_size != 8 or a.config != 3) else base_cfg["batch_size"]
     cfg = dict(base_cfg, batch_size=bs, gpu=local, distributed=world > 1, world_size=world, rank=rank)
     args = S.get_config(cfg)
     torch.manual_seed(0)
-    alg = S.get_algorithm(args, S.get_net_builder(args.net, False), None, None)
+    builder = S.get_net_builder(args.net, False)
+    if a.config == 5:   # LayerDrop off: the timed step runs all 12 layers for every clip (never less work than the reference's expectation)
+        import functools
+        builder = functools.partial(builder, layerdrop=0.0)
+    alg = S.get_algorithm(args, builder, None, None)
     alg.model = send_model_cuda(args, alg.model)
     alg.model.train()
     it0 = 1 if a.stage == 1 else args.start_timing + 1 + 8 * args.num_train_iter
     B, U = args.batch_size, args.batch_size * args.uratio
     samples_per_step = B + 2 * U
     text = a.config == 4
+    audio = a.config == 5
 
     def host_batch(i):
+        if audio:
+            b = detgen.audio_batch(B, args.uratio, args.num_classes, args.ulb_dest_len, samples=int(args.max_length_seconds * args.sample_rate), seed=1 + rank, step=i)
+            return {k: torch.from_numpy(v).pin_memory() for k, v in b.items()}
         if text:
             b = detgen.nlp_batch(B, args.uratio, args.num_classes, args.ulb_dest_len, max_length=args.max_length, seed=1 + rank, step=i)
             return {k: ({kk: torch.from_numpy(vv).pin_memory() for kk, vv in v.items()} if isinstance(v, dict) else torch.from_numpy(v).pin_memory())
@@ -421,8 +472,8 @@ def main_native(a):
         return ms
 
     W, K = max(3, a.warmup), a.steps
-    if text and a.steps == 300:
-        K = 60          # a BERT step is ~10x a ViT-S step: keep the default run within minutes
+    if (text or audio) and a.steps == 300:
+        K = 60          # a BERT / HuBERT step is ~10x a ViT-S step: keep the default run within minutes
     # one-time engine set-up outside the measurement (reported as config.setup_steps): the first call of a backbone pass runs
     # eagerly, the second is captured into a CUDA graph, kernels are lazily loaded on first use and stage 2 alternates between
     # step variants (SR update every N_k steps) — with a short --warmup those one-offs would land in the timed region
@@ -493,6 +544,10 @@ def main_native(a):
         sps, per_step, cores = cpu_reference_bert(2, 1, 1, 0, 0.1)
         cpu = dict(value=sps, unit="samples/s", cores=cores, kind="port",
                    sample=f"1 stage-1 step of the oracle restatement at batch_size 2 (of {B}; 6 sequences of 512 tokens), {per_step:.1f} s/step, torch CPU fp32, {cores} threads")
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and a.config == 5:
+        sps, per_step, cores = cpu_reference_hubert(2, 1, 1, 0, 0.1)
+        cpu = dict(value=sps, unit="samples/s", cores=cores, kind="port",
+                   sample=f"1 stage-1 step of the oracle restatement at batch_size 2 (of {B}; 6 clips of 64000 samples), {per_step:.1f} s/step, torch CPU fp32, {cores} threads")
     if rank == 0 and world == 1 and not a.no_eager_leg and a.config == 2:
         try:
             eager = torch_eager_fp32_leg(dict(YAML_CFG, batch_size=a.batch_size), a.stage)
