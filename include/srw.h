@@ -109,6 +109,12 @@ typedef struct {
    * residual add, HF modeling_bert.py:287-298, 330-356).  Rows are tokens: sequence = row / drop_rows_per_seq, element index
    * (seq_row * drop_rows_per_seq + row % drop_rows_per_seq) * N + col. */
   srw_dropout drop; int drop_rows_per_seq;
+  /* K segments (K-major A only; 0 = off): the reduction dimension is nseg segments of a_seg_k valid elements each, padded to
+   * whole 64-element blocks (K = nseg * ceil(a_seg_k / 64) * 64; B holds zeros in the padding); segment s of output row m reads
+   * A row m + s * a_seg_rows.  With lda < a_seg_k (overlapping rows) this is a 3x3 convolution over a zero-bordered NHWC tensor
+   * as ONE GEMM: row = pixel, segment = kernel row, a_seg_k = 3 * C_in contiguous elements, a_seg_rows = padded image width
+   * (wrn.py:35,39 nn.Conv2d(kernel_size=3, padding=1)). */
+  int a_seg_k; int64_t a_seg_rows;
 } srw_gemm_args;
 int srw_gemm(const srw_gemm_args* a, void* stream);
 
@@ -410,6 +416,61 @@ typedef struct {
 } srw_hubert_bwd_args;
 int srw_hubert_backward(const srw_hubert_bwd_args* a, void* stream);
 
+/* ---- WideResNet engine: WideResNet.forward / backward as two native calls ----------------------------------------- */
+/* Replaces `self.model(inputs)` of the `use_cat: True` step (srflexmatch.py:111-117) for net wrn_28_2 / wrn_28_8
+ * (semilearn/nets/wrn/wrn.py:73-146; BasicBlock :30-54) and autograd's backward of it.  NHWC with a zero border as operand planes,
+ * 3x3 convolutions as ONE srw_gemm with K segments over an overlapping row view (srw_gemm_args.a_seg_k), train-mode BatchNorm
+ * (batch statistics over ALL rows of the launch, running statistics advanced with momentum bn_momentum and the unbiased variance,
+ * wrn.py:33,37,97; final BatchNorm eps 1e-3, others 1e-5) + LeakyReLU(slope) fused into the operand writers.
+ * `params` / `grads`: device pointers in WideResNet.named_parameters() order = conv1.weight, conv1.bias, per BasicBlock {bn1.weight,
+ * bn1.bias, conv1.weight, bn2.weight, bn2.bias, conv2.weight[, convShortcut.weight]}, bn1.weight, bn1.bias, classifier.weight,
+ * classifier.bias (81 tensors for WRN-28-2).  The bn1 of the first layer of block2 / block3 normalises a tensor the block then
+ * drops (wrn.py:46-51): its running statistics advance, its parameters get NO gradient (grads[] entries may be NULL, never written).
+ * BatchNorm buffers: bn_running_mean / bn_running_var / bn_num_batches_tracked [2 * blocks + 1] pointers, per block bn1 then bn2,
+ * last the final bn1 (num_batches_tracked: int64 scalars, may be NULL). */
+typedef struct {
+  int num_classes, depth, widen, img_size;
+  float bn_momentum, slope;                    /* 0.001, 0.1 */
+} srw_wrn_config;
+
+int srw_wrn_num_params(const srw_wrn_config* c);
+int64_t srw_wrn_weight_planes_bytes(const srw_wrn_config* c);
+int64_t srw_wrn_workspace_bytes(const srw_wrn_config* c, int batch);
+int srw_wrn_prepare_weights(const srw_wrn_config* c, const float* const* params, void* weight_planes, void* stream);
+
+typedef struct {
+  const srw_wrn_config* cfg;
+  const float* const* params;
+  float* const* bn_running_mean; float* const* bn_running_var; int64_t* const* bn_num_batches_tracked;
+  const void* weight_planes;
+  const float* x;                              /* [batch, 3, img, img] fp32 NCHW */
+  int batch;
+  int training;                                /* 1: batch statistics + running-statistics update; 0: running statistics (eval) */
+  int stat_repeats;                            /* training: advance the running statistics this many EXTRA times with the same batch
+                                                  statistics — the K sampling passes of stage 2 re-run the identical deterministic
+                                                  forward (srflexmatch.py:72-104), whose only effect is on these buffers */
+  float* logits; float* feat;                  /* [batch, num_classes], [batch, 64 * widen] */
+  void* workspace; int64_t workspace_bytes;
+  int gemm_impl;
+} srw_wrn_fwd_args;
+int srw_wrn_forward(const srw_wrn_fwd_args* a, void* stream);
+
+typedef struct {
+  const srw_wrn_config* cfg;
+  const float* const* params;
+  const void* weight_planes;
+  int batch;
+  int grad_rows;                               /* dlogits / dfeat cover the first grad_rows rows; the others (weak rows) have zero
+                                                  logit gradient but still take part in every BatchNorm backward */
+  const float* dlogits; const float* dfeat;    /* [grad_rows, C], [grad_rows, 64 * widen] (dfeat may be NULL) */
+  float* const* grads;
+  int accumulate_grads;
+  void* workspace; int64_t workspace_bytes;    /* the forward's workspace */
+  int gemm_impl;
+} srw_wrn_bwd_args;
+int srw_wrn_backward(const srw_wrn_bwd_args* a, void* stream);
+
+
 /* x[i] *= *scale for i < n, where scale is a DEVICE scalar; returns without touching memory when *scale == 1.  Used to
  * apply autograd's upstream gradient of the loss (normally exactly 1, param_update.py:33) to gradients that were
  * computed ahead of loss.backward(). */
@@ -591,6 +652,17 @@ typedef struct {
   int decoupled;                /* 1 = AdamW, 0 = Adam with L2 (grad += wd * p) */
 } srw_adamw_args;
 int srw_adamw_step(const srw_adamw_args* a, void* stream);
+
+/* torch.optim.SGD(momentum, nesterov, weight_decay) over all tensors in one launch (core/utils/build.py:219-220: the optimizer of
+ * config/classic_cv).  Rows are srw_adamw_row with exp_avg = momentum buffer (exp_avg_sq / planes unused).
+ *   g' = g + wd p;  buf = first_step ? g' : momentum buf + g';  p -= lr (nesterov ? g' + momentum buf : buf) */
+typedef struct {
+  int num_tensors; int64_t total_blocks;
+  const void* table;                           /* device array of srw_adamw_row */
+  double lr_factor, momentum;
+  int nesterov, first_step;
+} srw_sgd_args;
+int srw_sgd_step(const srw_sgd_args* a, void* stream);
 
 /* ---- EMA of the parameters: EMAHook.after_train_step / EMA.update (core/hooks/ema.py:20-24, core/utils/misc.py:152-155) ---- */
 /* shadow = (1 - decay) * param + decay * shadow over many tensors in one launch (bit-exact with the reference's fp32 tensor

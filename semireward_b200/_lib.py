@@ -36,7 +36,7 @@ class GemmArgs(C.Structure):
                 ("epilogue", i32), ("bias", vp), ("resid", vp), ("ldr", i64), ("row_scale", vp), ("rows_per_scale", i32),
                 ("aux", vp), ("ldaux", i64), ("out_f32", vp), ("ldo", i64), ("out_planes", vp), ("ldp", i64),
                 ("out_plane_stride", i64), ("split_k", i32), ("workspace", vp), ("impl", i32), ("max_ctas", i32),
-                ("drop", Dropout), ("drop_rows_per_seq", i32)]
+                ("drop", Dropout), ("drop_rows_per_seq", i32), ("a_seg_k", i32), ("a_seg_rows", i64)]
 
 
 class SplitKReduceArgs(C.Structure):
@@ -142,6 +142,21 @@ class HubertBwdArgs(C.Structure):
                 ("accumulate_grads", i32), ("workspace", vp), ("workspace_bytes", i64), ("gemm_impl", i32)]
 
 
+class WrnConfig(C.Structure):
+    _fields_ = [("num_classes", i32), ("depth", i32), ("widen", i32), ("img_size", i32), ("bn_momentum", f32), ("slope", f32)]
+
+
+class WrnFwdArgs(C.Structure):
+    _fields_ = [("cfg", C.POINTER(WrnConfig)), ("params", C.POINTER(vp)), ("bn_running_mean", C.POINTER(vp)), ("bn_running_var", C.POINTER(vp)),
+                ("bn_num_batches_tracked", C.POINTER(vp)), ("weight_planes", vp), ("x", vp), ("batch", i32), ("training", i32), ("stat_repeats", i32),
+                ("logits", vp), ("feat", vp), ("workspace", vp), ("workspace_bytes", i64), ("gemm_impl", i32)]
+
+
+class WrnBwdArgs(C.Structure):
+    _fields_ = [("cfg", C.POINTER(WrnConfig)), ("params", C.POINTER(vp)), ("weight_planes", vp), ("batch", i32), ("grad_rows", i32), ("dlogits", vp),
+                ("dfeat", vp), ("grads", C.POINTER(vp)), ("accumulate_grads", i32), ("workspace", vp), ("workspace_bytes", i64), ("gemm_impl", i32)]
+
+
 class RewarderFwdArgs(C.Structure):
     _fields_ = [("B", i32), ("feature_dim", i32), ("label_rows", i32), ("rp", C.POINTER(vp)), ("feats", vp), ("ld_feats", i64),
                 ("labels", vp), ("reward", vp), ("workspace", vp)]
@@ -203,6 +218,10 @@ class AdamWArgs(C.Structure):
                 ("eps", f64), ("step", i32), ("decoupled", i32)]
 
 
+class SgdArgs(C.Structure):
+    _fields_ = [("num_tensors", i32), ("total_blocks", i64), ("table", vp), ("lr_factor", f64), ("momentum", f64), ("nesterov", i32), ("first_step", i32)]
+
+
 class EmaRow(C.Structure):
     _fields_ = [("param", vp), ("shadow", vp), ("numel", i64), ("first_block", i64)]
 
@@ -257,6 +276,13 @@ SYMBOLS = [
     ("srw_hubert_prepare_weights", i32, [C.POINTER(HubertConfig), C.POINTER(vp), vp, vp]),
     ("srw_hubert_forward", i32, [C.POINTER(HubertFwdArgs), vp]),
     ("srw_hubert_backward", i32, [C.POINTER(HubertBwdArgs), vp]),
+    ("srw_wrn_num_params", i32, [C.POINTER(WrnConfig)]),
+    ("srw_wrn_weight_planes_bytes", i64, [C.POINTER(WrnConfig)]),
+    ("srw_wrn_workspace_bytes", i64, [C.POINTER(WrnConfig), i32]),
+    ("srw_wrn_prepare_weights", i32, [C.POINTER(WrnConfig), C.POINTER(vp), vp, vp]),
+    ("srw_wrn_forward", i32, [C.POINTER(WrnFwdArgs), vp]),
+    ("srw_wrn_backward", i32, [C.POINTER(WrnBwdArgs), vp]),
+    ("srw_sgd_step", i32, [C.POINTER(SgdArgs), vp]),
     ("srw_set_graph_mode", i32, [i32]),
     ("srw_set_pdl_mode", i32, [i32]),
     ("srw_scale_inplace", i32, [vp, i64, vp, vp]),

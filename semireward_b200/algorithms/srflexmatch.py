@@ -346,6 +346,10 @@ class SRFlexMatch(AlgorithmBase):
         one_pass = [(0, "lb"), (0, "s"), (0, "w")]
         if stochastic2 and self._stochastic_backbone():   # same draws as the batched route: every pass of the step up front
             full = net.draw_streams(self.sr_decay() + 1, nl, nu, dev)
+        if self.it > self.start_timing and not stochastic2 and hasattr(net, "stat_repeats_next"):
+            # BatchNorm backbone, deterministic passes: the K sampling passes recompute the identical forward and only advance the
+            # running statistics (wrn.py:33,37,97) — the one forward below advances them 1 + K times (srw_wrn_fwd_args.stat_repeats)
+            net.stat_repeats_next = self.sr_decay()
         (logits_lb, logits_w, logits_s), (feats_lb, feats_w, feats_s), h0 = self._backbone_native(
             x_lb, x_ulb_w, x_ulb_s, drop_scale=None if full is None else net.streams_for(full, one_pass, nl, nu, dev))
         feat_dict = {"x_lb": feats_lb, "x_ulb_w": feats_w, "x_ulb_s": feats_s}

@@ -184,6 +184,96 @@ class FusedAdamW(torch.optim.Optimizer):
         return None
 
 
+class FusedSGD(torch.optim.Optimizer):
+    """torch.optim.SGD-compatible (param_groups, state_dict key 'momentum_buffer') stepping all tensors with one srw_sgd_step launch
+    (the optimizer of config/classic_cv: SGD lr 0.03, momentum 0.9, nesterov, core/utils/build.py:219-220).  Parameters whose
+    .grad is None are skipped like torch does (WideResNet's two unused bn1)."""
+
+    def __init__(self, params, lr=0.03, momentum=0.9, weight_decay=0.0, nesterov=True, net=None):
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay, nesterov=nesterov, dampening=0))
+        self._net = net
+        self._rows = None
+        self._first = True
+        self._flip = 0
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._rows = None
+
+    def _build(self):
+        g0 = self.param_groups[0]
+        for g in self.param_groups:
+            if g["momentum"] != g0["momentum"] or g["nesterov"] != g0["nesterov"] or g.get("dampening", 0) != 0:
+                raise ValueError("FusedSGD: all param groups must share momentum / nesterov, dampening must be 0")
+        ps = [p for g in self.param_groups for p in g["params"] if p.grad is not None]
+        self._skipped = sum(1 for g in self.param_groups for p in g["params"] if p.grad is None)
+        dev = ps[0].device
+        self._buf_flat = torch.zeros(sum(p.numel() for p in ps), dtype=torch.float32, device=dev)
+        rows = (L.AdamWRow * len(ps))()
+        off = blk = 0
+        self._group_of = []
+        restored = False
+        for gi, g in enumerate(self.param_groups):
+            for p in g["params"]:
+                if p.grad is None:
+                    continue
+                r = rows[len(self._group_of)]
+                n = p.numel()
+                m = self._buf_flat[off:off + n].view_as(p)
+                st = self.state[p]
+                if st.get("momentum_buffer") is not None:   # restored by load_state_dict
+                    m.copy_(st["momentum_buffer"])
+                    restored = True
+                st["momentum_buffer"] = m
+                r.param, r.exp_avg, r.exp_avg_sq, r.numel = p.data_ptr(), m.data_ptr(), None, n
+                r.planes, r.cols, r.ldp, r.plane_stride = None, 1, 1, 0
+                r.first_block = blk
+                blk += (n + L.ADAMW_BLOCK_ELEMS - 1) // L.ADAMW_BLOCK_ELEMS
+                off += n
+                self._group_of.append(gi)
+        self._rows, self._params, self._total_blocks = rows, ps, blk
+        if restored:
+            self._first = False
+        nbytes = C.sizeof(rows)
+        self._dev_table = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self._host_tables = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self._copy_events = [None, None]
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise NotImplementedError("FusedSGD.step does not take a closure")
+        if self._rows is None or sum(1 for g in self.param_groups for p in g["params"] if p.grad is None) != self._skipped:
+            self._build()
+        rows = self._rows
+        for i, p in enumerate(self._params):
+            g = p.grad
+            if g is None:
+                raise RuntimeError("FusedSGD: a parameter lost its gradient between steps")
+            if not g.is_contiguous():
+                g = p.grad = g.contiguous()
+            grp = self.param_groups[self._group_of[i]]
+            rows[i].grad, rows[i].lr, rows[i].weight_decay = g.data_ptr(), float(grp["lr"]), float(grp["weight_decay"])
+        k = self._flip
+        self._flip ^= 1
+        if self._copy_events[k] is not None:
+            self._copy_events[k].synchronize()
+        host = self._host_tables[k]
+        C.memmove(host.data_ptr(), C.addressof(rows), C.sizeof(rows))
+        self._dev_table.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._copy_events[k] = ev
+        g0 = self.param_groups[0]
+        a = L.SgdArgs(num_tensors=len(self._params), total_blocks=self._total_blocks, table=self._dev_table.data_ptr(), lr_factor=1.0,
+                      momentum=float(g0["momentum"]), nesterov=int(bool(g0["nesterov"])), first_step=int(self._first))
+        L.check(L.load().srw_sgd_step(C.byref(a), L.stream_ptr()), "srw_sgd_step")
+        self._first = False
+        if self._net is not None and hasattr(self._net, "mark_weights_updated"):
+            self._net.mark_weights_updated()      # the kernel wrote the parameters behind torch's version counters
+        return None
+
+
 def get_optimizer(net, optim_name="SGD", lr=0.1, momentum=0.9, weight_decay=0, layer_decay=1.0, nesterov=True, bn_wd_skip=True):
     assert layer_decay <= 1.0
     no_decay = net.no_weight_decay() if (hasattr(net, "no_weight_decay") and bn_wd_skip) else {}
@@ -194,6 +284,8 @@ def get_optimizer(net, optim_name="SGD", lr=0.1, momentum=0.9, weight_decay=0, l
     if optim_name == "AdamW":
         return FusedAdamW(groups, lr=lr, weight_decay=weight_decay, net=net)
     if optim_name == "SGD":
+        if hasattr(net, "forward_native"):     # a native backbone: one fused launch; anything else keeps torch's optimizer
+            return FusedSGD(groups, lr=lr, momentum=momentum, weight_decay=weight_decay, nesterov=nesterov, net=net)
         return torch.optim.SGD(groups, lr=lr, momentum=momentum, weight_decay=weight_decay, nesterov=nesterov)
     raise ValueError(f"unknown optimizer {optim_name}")
 

@@ -286,6 +286,8 @@ struct TcParams {
   int kb_per_split; // k blocks (of 64) handled by one split
   int a_mn, b_mn;   // operand majors
   int m_tiles, n_tiles, splits;
+  int a_seg_kb;     // > 0: K-major A is read in K segments of a_seg_kb blocks; segment s starts a_seg_rows * s rows further down
+  int a_seg_rows;   //      (implicit-GEMM 3x3 convolution over a zero-bordered NHWC tensor, srw_wrn.cu)
 };
 
 template <int BN>
@@ -358,7 +360,12 @@ gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
           if (tr && it == 0) tr[2] = clock64();
           const int k0 = kb * BK;
           if (!tp.a_mn) {
-            tma_load_3d(st, &tmap_a, &full_bar[s], k0, m0, 0);                       // [2][128][64]
+            if (tp.a_seg_kb > 0) {
+              const int seg = kb / tp.a_seg_kb;
+              tma_load_3d(st, &tmap_a, &full_bar[s], (kb - seg * tp.a_seg_kb) * BK, m0 + seg * tp.a_seg_rows, 0);
+            } else {
+              tma_load_3d(st, &tmap_a, &full_bar[s], k0, m0, 0);                     // [2][128][64]
+            }
           } else {
             tma_load_3d(st, &tmap_a, &full_bar[s], m0, k0, 0);                       // [2][64 k][64 mn] chunk 0
             tma_load_3d(st + PLANE_TILE_BYTES, &tmap_a, &full_bar[s], m0 + 64, k0, 0);  // chunk 1
@@ -858,6 +865,7 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
   const int grid_z = (a->epilogue == SRW_EPI_SPLITK) ? a->split_k : 1;
 
   if (a->impl == SRW_GEMM_SIMT) {
+    SRW_REQUIRE(a->a_seg_k == 0, "srw_gemm: K segments are a tcgen05-path feature");
     SimtParams sp;
     sp.K = a->K; sp.kb_per_split = kb_per_split;
     sp.a = reinterpret_cast<const __nv_bfloat16*>(a->a); sp.lda = a->lda; sp.a_ps = a->a_plane_stride; sp.a_mn = a->a_mn_major;
@@ -893,13 +901,26 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
   tp.trace = g_gemm_trace;
   tp.K = a->K; tp.kb_per_split = kb_per_split; tp.a_mn = a->a_mn_major ? 1 : 0; tp.b_mn = a->b_mn_major ? 1 : 0;
   tp.splits = grid_z;
+  tp.a_seg_kb = 0; tp.a_seg_rows = 0;
+  const bool segmented = a->a_seg_k > 0;
+  int64_t a_inner = a->K, a_outer = a->M;
+  if (segmented) {
+    // K = nseg * a_seg_kb * 64 (every segment padded to whole k-blocks; B carries zeros there, TMA zero-fills A past a_seg_k)
+    SRW_REQUIRE(!a->a_mn_major && a->a_seg_rows > 0, "srw_gemm: K segments need a K-major A and a_seg_rows > 0");
+    tp.a_seg_kb = cdiv(a->a_seg_k, BK);
+    SRW_REQUIRE(a->K % (tp.a_seg_kb * BK) == 0, "srw_gemm: K (%d) must be a whole number of padded segments (%d)", a->K, tp.a_seg_kb * BK);
+    SRW_REQUIRE(a->a_seg_rows <= 0x7fffffff, "srw_gemm: a_seg_rows too large");
+    tp.a_seg_rows = (int)a->a_seg_rows;
+    a_inner = a->a_seg_k;
+    a_outer = (int64_t)a->M + (int64_t)(a->K / (tp.a_seg_kb * BK) - 1) * a->a_seg_rows;
+  }
   const double flops = 2.0 * a->M * a->N * a->K, bytes = 4.0 * ((double)a->M * a->K + (double)a->N * a->K + (double)a->M * a->N);
 
   // ---- 2-CTA path: pair tiles of 256 x BN ----
   // max_ctas > 0: this GEMM may only occupy that many SMs (it runs next to other kernels on other streams)
   const int cta_cap = (a->max_ctas > 0 && a->max_ctas < num_sms) ? std::max(2, a->max_ctas) : num_sms;
   const int bn2 = srw::gemm2_pick_bn(a->M, a->N, grid_z, a->b_mn_major != 0, cta_cap);
-  if (a->impl == SRW_GEMM_TCGEN05 && bn2 > 0) {
+  if (a->impl == SRW_GEMM_TCGEN05 && bn2 > 0 && !segmented) {
     CUtensorMap ta, tb;
     if (!a->a_mn_major) rc = make_plane_tmap(&ta, a->a, a->K, a->M, a->lda, a->a_plane_stride, 128, 2);
     else rc = make_plane_tmap(&ta, a->a, a->M, a->K, a->lda, a->a_plane_stride, 64, 2);
@@ -934,7 +955,7 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
   // ---- 1-CTA path ----
   const int bn = srw::gemm_pick_bn(a->M, a->N, grid_z, cta_cap);
   CUtensorMap ta, tb;
-  if (!a->a_mn_major) rc = make_plane_tmap(&ta, a->a, a->K, a->M, a->lda, a->a_plane_stride, 128, 2);
+  if (!a->a_mn_major) rc = make_plane_tmap(&ta, a->a, a_inner, a_outer, a->lda, a->a_plane_stride, 128, 2);
   else rc = make_plane_tmap(&ta, a->a, a->M, a->K, a->lda, a->a_plane_stride, 64, 2);
   if (rc) return rc;
   if (!a->b_mn_major) rc = make_plane_tmap(&tb, a->b, a->K, a->N, a->ldb, a->b_plane_stride, bn, 2);

@@ -94,6 +94,31 @@ __global__ void __launch_bounds__(256) adamw_kernel(const srw_adamw_row* __restr
     }
   }
 }
+// torch.optim.SGD single-tensor math (momentum, dampening 0, nesterov, coupled weight decay), same chunk-per-CTA table walk
+__global__ void __launch_bounds__(256) sgd_kernel(const srw_adamw_row* __restrict__ table, int num_tensors, double lr_factor, float momentum, int nesterov,
+                                                  int first_step) {
+  int lo = 0, hi = num_tensors - 1;
+  const int64_t blk = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].first_block <= blk) lo = mid; else hi = mid - 1;
+  }
+  const srw_adamw_row row = table[lo];
+  const int64_t base = (blk - row.first_block) * SRW_ADAMW_BLOCK_ELEMS;
+  const int64_t end = min(row.numel, base + SRW_ADAMW_BLOCK_ELEMS);
+  const float lr = (float)(row.lr * lr_factor), wd = (float)row.weight_decay;
+  for (int64_t i = base + threadIdx.x; i < end; i += 256) {
+    float p = row.param[i], g = row.grad[i];
+    if (wd != 0.f) g = fmaf(wd, p, g);
+    float upd = g;
+    if (momentum != 0.f) {
+      const float buf = first_step ? g : fmaf(momentum, row.exp_avg[i], g);
+      row.exp_avg[i] = buf;
+      upd = nesterov ? fmaf(momentum, buf, g) : buf;
+    }
+    row.param[i] = p - lr * upd;
+  }
+}
 // EMA of the parameters (EMA.update, semilearn/core/utils/misc.py:152-155): shadow = (1 - d) * p + d * shadow, two rounded
 // products and one rounded sum like the reference's tensor expression (bit-exact).  Same chunk-per-CTA table walk as AdamW.
 __global__ void __launch_bounds__(256) ema_kernel(const srw_ema_row* __restrict__ table, int num_tensors, float d, float omd) {
@@ -127,6 +152,16 @@ extern "C" int srw_ema_step(const srw_ema_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SRW_REQUIRE(a && a->table && a->num_tensors > 0 && a->total_blocks > 0, "srw_ema_step: bad args");
   ema_kernel<<<(unsigned)a->total_blocks, 256, 0, stream>>>(a->table, a->num_tensors, (float)a->decay, (float)(1.0 - a->decay));
+  g_launches++;
+  SRW_LAUNCH_CHECK();
+  return SRW_OK;
+}
+
+extern "C" int srw_sgd_step(const srw_sgd_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SRW_REQUIRE(a && a->table && a->num_tensors > 0 && a->total_blocks > 0, "srw_sgd_step: bad args");
+  sgd_kernel<<<(unsigned)a->total_blocks, 256, 0, stream>>>(reinterpret_cast<const srw_adamw_row*>(a->table), a->num_tensors, a->lr_factor, (float)a->momentum,
+                                                           a->nesterov, a->first_step);
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;

@@ -55,7 +55,9 @@ def test_every_struct_matches_the_header_field_by_field(tmp_path):
                  srw_ssl_loss_args="SslLossArgs", srw_freematch_mask_args="FreeMatchMaskArgs", srw_freematch_entropy_args="FreeMatchEntropyArgs",
                  srw_softmatch_mask_args="SoftMatchMaskArgs", srw_adamw_row="AdamWRow", srw_adamw_args="AdamWArgs", srw_ema_row="EmaRow",
                  srw_ema_args="EmaArgs", srw_dropout="Dropout", srw_bert_config="BertConfig", srw_bert_fwd_args="BertFwdArgs",
-                 srw_bert_bwd_args="BertBwdArgs")
+                 srw_bert_bwd_args="BertBwdArgs", srw_hubert_config="HubertConfig", srw_hubert_fwd_args="HubertFwdArgs",
+                     srw_hubert_bwd_args="HubertBwdArgs", srw_wrn_config="WrnConfig", srw_wrn_fwd_args="WrnFwdArgs", srw_wrn_bwd_args="WrnBwdArgs",
+                     srw_sgd_args="SgdArgs")
     hdr = open(os.path.join(ROOT, "include", "srw.h")).read()
     assert set(re.findall(r"}\s*(srw_[a-z0-9_]+);", hdr)) == set(pairs), "a struct of include/srw.h has no ctypes mirror in this table"
     lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "srw.h"', "int main(void) {"]
