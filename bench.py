@@ -52,12 +52,22 @@ YAML_CFG5 = dict(algorithm="srflexmatch", net="hubert_base", optim="AdamW", lr=5
                  num_train_iter=102400, num_warmup_iter=5120, start_timing=10000, N_k=10, batch_size=8, uratio=1, num_classes=10,
                  ulb_dest_len=7000, feature_dim=768, sr_lr=5e-4, sr_ema=False, use_cat=False, amp=False, ema_m=0.0, max_length_seconds=4.0,
                  sample_rate=16000, p_cutoff=0.95, thresh_warmup=True, hard_label=True, T=0.5, ulb_loss_ratio=1.0, clip_grad=0)
+# BASELINE configs[0]: config/classic_cv/flexmatch/flexmatch_cifar100_400_0.yaml (wrn_28_2, batch_size 64, uratio 7, SGD lr 0.03 momentum 0.9
+# nesterov, weight_decay 1e-3, ema_m 0.999) with `algorithm: srflexmatch` + the SR keys (no SR YAML exists under config/classic_cv; SURVEY.md
+# §8d "Config 1"); `--config 1`.  BatchNorm couples the rows: the backward runs over all 960 images (9 B F of algorithmic FLOPs, not 7 B F).
+YAML_CFG1 = dict(algorithm="srflexmatch", net="wrn_28_2", optim="SGD", lr=0.03, momentum=0.9, layer_decay=1.0, weight_decay=1e-3,
+                 num_train_iter=1048576, num_warmup_iter=0, start_timing=20000, N_k=10, batch_size=64, uratio=7, num_classes=100,
+                 ulb_dest_len=50000, feature_dim=128, sr_lr=5e-4, sr_ema=False, use_cat=True, amp=False, ema_m=0.999, img_size=32,
+                 p_cutoff=0.95, thresh_warmup=True, hard_label=True, T=0.5, ulb_loss_ratio=1.0, clip_grad=0)
+F_FWD_GF1 = 0.429          # GFLOP per 32 x 32 image forward
 F_FWD_GF5 = 56.9           # GFLOP per 4 s clip forward (oracle/hubert_oracle.py HubertCfg.fwd_flops_per_clip)
-METRICS = {2: "SSL train-step samples/sec (ViT-S CIFAR-100)", 3: "SSL train-step samples/sec (ViT-S CIFAR-100)",
+METRICS = {1: "SSL train-step samples/sec (WRN-28-2 CIFAR-100)", 2: "SSL train-step samples/sec (ViT-S CIFAR-100)", 3: "SSL train-step samples/sec (ViT-S CIFAR-100)",
            4: "SSL train-step samples/sec (BERT-base IMDb)", 5: "SSL train-step samples/sec (HuBERT-base UrbanSound8k)"}
 
 
 def workload_name(config, B, uratio, stage):
+    if config == 1:
+        return f"srflexmatch wrn_28_2 cifar100 batch_size {B} uratio {uratio} SGD stage {stage} (BASELINE configs[0])"
     if config == 2:
         return f"srflexmatch vit_small_patch2_32 cifar100 batch_size {B} uratio {uratio} stage {stage} (BASELINE configs[1])"
     if config == 3:
@@ -71,7 +81,9 @@ def workload_name(config, B, uratio, stage):
 def config_block(config, B, uratio, stage, world, setup_steps):
     """The `config` object of the JSON line; both arms (native, reference) print the same keys."""
     per = B * (1 + 2 * uratio)
-    f = {2: F_FWD_GF, 3: F_FWD_GF3, 4: F_FWD_GF4, 5: F_FWD_GF5}[config]
+    f = {1: F_FWD_GF1, 2: F_FWD_GF, 3: F_FWD_GF3, 4: F_FWD_GF4, 5: F_FWD_GF5}[config]
+    rows = B * (1 + 2 * uratio)
+    gflop = rows * 3 * f if config == 1 else B * (3 + 4 * uratio) * f   # WRN: BatchNorm couples the rows, all of them are back-propagated
     return dict(workload=workload_name(config, B, uratio, stage), samples_per_step_per_gpu=per, parallelism=f"dp{world}",
                 drop_path=0.2 if config in (2, 3) else None, dropout=0.1 if config in (4, 5) else None, setup_steps=setup_steps,
                 arithmetic="fp32 semantics: bf16x3 split-precision tcgen05 MMA, fp32 accumulate",
@@ -79,7 +91,7 @@ def config_block(config, B, uratio, stage, world, setup_steps):
                     "step working set (~7-8 GB of activations at batch 8) >> 126 MB L2; rotating input batches"),
                 launch="CUDA-graph replay of the backbone forward/backward (SRW_GRAPHS) + programmatic dependent launch (SRW_PDL); "
                        "backward launched inside train_step ahead of the loss read-back",
-                algorithmic_gflop_per_step_per_gpu=B * (3 + 4 * uratio) * f)   # forward on B (1 + 2u) rows + backward (2x) on the B (1 + u) gradient rows
+                algorithmic_gflop_per_step_per_gpu=gflop)   # forward on B (1 + 2u) rows + backward (2x) on the B (1 + u) gradient rows
 
 
 def parse():
@@ -91,8 +103,8 @@ def parse():
     ap.add_argument("--batch-size", type=int, default=8, help="per-GPU labelled batch (config-faithful: 8)")
     ap.add_argument("--stage", type=int, default=1, choices=[1, 2])
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
-                    help="BASELINE.json configs index + 1: 2 = headline ViT-S CIFAR-100, 3 = ViT-B/16 224 FreeMatch, 4 = BERT-base text, 5 = HuBERT-base "
-                         "audio; 1 (WRN-28-2) has no CUDA path and exists for --impl reference only (CPU oracle timing)")
+                    help="BASELINE.json configs index + 1: 1 = WRN-28-2 CIFAR-100 (SGD), 2 = headline ViT-S CIFAR-100, 3 = ViT-B/16 224 FreeMatch, "
+                         "4 = BERT-base text, 5 = HuBERT-base audio")
     ap.add_argument("--no-eager-leg", action="store_true", help="skip the informational torch-eager fp32 leg on the same GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -295,9 +307,10 @@ def main_reference(a):
     if a.config == 1:
         steps, warmup = max(1, min(a.steps, 2)), max(0, min(a.warmup, 1))     # tens of seconds per CPU step
         sps, per_step, cores, name, what, samples = cpu_reference_run_other(a.config, steps, warmup)
-        print(json.dumps(dict(impl="reference", metric=f"SSL train-step samples/sec ({name})", value=sps, unit="samples/s", n_gpus=a.gpus, steps=steps,
+        B1 = YAML_CFG1["batch_size"]
+        print(json.dumps(dict(impl="reference", metric=METRICS[1], value=sps, unit="samples/s", n_gpus=a.gpus, steps=steps,
                               warmup=warmup, ms_per_step=per_step * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                              data="synthetic", config=dict(workload=what, samples_per_step=samples), note=note,
+                              data="synthetic", config=config_block(1, B1, YAML_CFG1["uratio"], a.stage, a.gpus, SETUP_STEPS), note=note,
                               cpu_baseline=dict(value=sps, unit="samples/s", cores=cores, kind="port",
                                                 sample=f"{steps} step(s) of the oracle restatement (pinned against the live reference), {warmup} warm-up"),
                               e2e=dict(value=sps, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
@@ -380,8 +393,8 @@ SETUP_STEPS = 12
 
 
 def main_native(a):
-    if a.config not in (2, 3, 4, 5):
-        raise SystemExit(f"bench.py: BASELINE configs[{a.config - 1}] has no CUDA path yet (DESIGN.md §9); only --impl reference can time it")
+    if a.config == 1 and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("bench.py --config 1: the WRN path is single-GPU (SyncBatchNorm is not built); BASELINE configs[0] is the single-device case")
     import torch
     import torch.distributed as dist
     import semireward_b200 as S
@@ -399,8 +412,8 @@ def main_native(a):
     lib = L.load()
     L.check(lib.srw_device_check(None, None, None), "srw_device_check")
 
-    base_cfg = {2: YAML_CFG, 3: YAML_CFG3, 4: YAML_CFG4, 5: YAML_CFG5}[a.config]
-    bs = a.batch_size if (a.batch_size != 8 or a.config != 3) else base_cfg["batch_size"]
+    base_cfg = {1: YAML_CFG1, 2: YAML_CFG, 3: YAML_CFG3, 4: YAML_CFG4, 5: YAML_CFG5}[a.config]
+    bs = a.batch_size if (a.batch_size != 8 or a.config not in (1, 3)) else base_cfg["batch_size"]
     cfg = dict(base_cfg, batch_size=bs, gpu=local, distributed=world > 1, world_size=world, rank=rank)
     args = S.get_config(cfg)
     torch.manual_seed(0)
@@ -472,7 +485,7 @@ def main_native(a):
         return ms
 
     W, K = max(3, a.warmup), a.steps
-    if (text or audio) and a.steps == 300:
+    if (text or audio or a.config == 1) and a.steps == 300:
         K = 60          # a BERT / HuBERT step is ~10x a ViT-S step: keep the default run within minutes
     # one-time engine set-up outside the measurement (reported as config.setup_steps): the first call of a backbone pass runs
     # eagerly, the second is captured into a CUDA graph, kernels are lazily loaded on first use and stage 2 alternates between
@@ -544,6 +557,10 @@ def main_native(a):
         sps, per_step, cores = cpu_reference_bert(2, 1, 1, 0, 0.1)
         cpu = dict(value=sps, unit="samples/s", cores=cores, kind="port",
                    sample=f"1 stage-1 step of the oracle restatement at batch_size 2 (of {B}; 6 sequences of 512 tokens), {per_step:.1f} s/step, torch CPU fp32, {cores} threads")
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and a.config == 1:
+        sps, per_step, cores, _, what, _ = cpu_reference_run_other(1, 1, 0)
+        cpu = dict(value=sps, unit="samples/s", cores=cores, kind="port",
+                   sample=f"1 stage-1 step of the oracle restatement at the full batch (960 images), {per_step:.1f} s/step, torch CPU fp32, {cores} threads")
     if rank == 0 and world == 1 and not a.no_cpu_baseline and a.config == 5:
         sps, per_step, cores = cpu_reference_hubert(2, 1, 1, 0, 0.1)
         cpu = dict(value=sps, unit="samples/s", cores=cores, kind="port",

@@ -253,7 +253,8 @@ static __global__ void __launch_bounds__(256) enc_head_fwd_kernel(const float* _
   for (int n = warp; n < D; n += 8) {
     const float* w = W1 + (int64_t)n * D;
     float acc = 0.f;
-    for (int k = lane; k < D; k += 32) acc = fmaf(f[k], w[k], acc);
+#pragma unroll 8
+    for (int k = lane; k < D; k += 32) acc = fmaf(f[k], w[k], acc);   // unrolled: the weight loads of a row are in flight together
     acc = warp_sum(acc);
     if (lane == 0) {
       const float z = acc + b1[n];
@@ -295,8 +296,16 @@ static __global__ void __launch_bounds__(256) enc_head_bwd_rows_kernel(const flo
   __syncthreads();
   for (int k = threadIdx.x; k < D; k += 256) {
     float acc = dfeat_in ? dfeat_in[(int64_t)s * D + k] : 0.f;
-    for (int n = 0; n < D; ++n) acc = fmaf(dz[n], W1[(int64_t)n * D + k], acc);
-    dfeat_out[(int64_t)s * D + k] = acc;
+    float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int n = 0;
+    for (; n + 8 <= D; n += 8) {   // eight independent loads in flight per thread (the loop is a chain of L2 round trips otherwise)
+      const float w0 = W1[(int64_t)n * D + k], w1 = W1[(int64_t)(n + 1) * D + k], w2 = W1[(int64_t)(n + 2) * D + k], w3 = W1[(int64_t)(n + 3) * D + k];
+      const float w4 = W1[(int64_t)(n + 4) * D + k], w5 = W1[(int64_t)(n + 5) * D + k], w6 = W1[(int64_t)(n + 6) * D + k], w7 = W1[(int64_t)(n + 7) * D + k];
+      acc = fmaf(dz[n], w0, acc); a1 = fmaf(dz[n + 1], w1, a1); a2 = fmaf(dz[n + 2], w2, a2); a3 = fmaf(dz[n + 3], w3, a3);
+      acc = fmaf(dz[n + 4], w4, acc); a1 = fmaf(dz[n + 5], w5, a1); a2 = fmaf(dz[n + 6], w6, a2); a3 = fmaf(dz[n + 7], w7, a3);
+    }
+    for (; n < D; ++n) acc = fmaf(dz[n], W1[(int64_t)n * D + k], acc);
+    dfeat_out[(int64_t)s * D + k] = (acc + a1) + (a2 + a3);
   }
 }
 // dW2[c, k] = sum_s dlogits[s, c] a1[s, k]; db2; dW1[n, k] = sum_s dz1[s, n] feat[s, k]; db1

@@ -141,22 +141,27 @@ __global__ void __launch_bounds__(256) hub_conv0_bwd_stats_kernel(const float* _
   dst[1] = make_float2(a1, q1);
 }
 // per (clip, channel): A = sum_t du, Q = sum_t du nhat (fp64 fold) -> ab[(s, c)] = (A / n0, Q / n0);  dbeta[c] (+)= sum_s A, dgamma[c] (+)= sum_s Q
-__global__ void hub_conv0_bwd_finish_kernel(const float2* __restrict__ partial, int Sg, int chunks, int n0, float2* __restrict__ ab, float* __restrict__ dgamma,
-                                            float* __restrict__ dbeta, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) hub_conv0_bwd_finish_kernel(const float2* __restrict__ partial, int Sg, int chunks, int n0, float2* __restrict__ ab,
+                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+  // one warp per channel, lanes over the chunks of a clip (fp64), clips in order
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= HC) return;
   double ga = 0.0, gq = 0.0;
   for (int s = 0; s < Sg; ++s) {
     double a = 0.0, q = 0.0;
-    for (int k = 0; k < chunks; ++k) {
+    for (int k = lane; k < chunks; k += 32) {
       const float2 p = partial[((int64_t)s * chunks + k) * HC + c];
       a += p.x; q += p.y;
     }
-    ab[s * HC + c] = make_float2((float)(a / n0), (float)(q / n0));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (lane == 0) ab[s * HC + c] = make_float2((float)(a / n0), (float)(q / n0));
     ga += a; gq += q;
   }
-  dbeta[c] = accumulate ? dbeta[c] + (float)ga : (float)ga;
-  dgamma[c] = accumulate ? dgamma[c] + (float)gq : (float)gq;
+  if (lane == 0) {
+    dbeta[c] = accumulate ? dbeta[c] + (float)ga : (float)ga;
+    dgamma[c] = accumulate ? dgamma[c] + (float)gq : (float)gq;
+  }
 }
 // backward, pass 2: dz = rstd gamma (du - A/n - nhat Q/n);  wpart[(s, chunk), c, j] = sum_t dz x[5 t + j]
 __global__ void __launch_bounds__(256) hub_conv0_bwd_wgrad_kernel(const float* __restrict__ wav, int64_t ld_wav, int samples, int n0, int tp0,
@@ -1202,7 +1207,7 @@ static int hubert_backward_body(const srw_hubert_bwd_args* a, cudaStream_t s) {
                                                     F32(L.dy0), reinterpret_cast<float2*>(ws + L.bpart0));
     g_launches++;
     SRW_LAUNCH_CHECK();
-    hub_conv0_bwd_finish_kernel<<<cdiv(HC, 128), 128, 0, s>>>(reinterpret_cast<const float2*>(ws + L.bpart0), Sg, grid.x, d.n[0],
+    hub_conv0_bwd_finish_kernel<<<cdiv(HC, 8), 256, 0, s>>>(reinterpret_cast<const float2*>(ws + L.bpart0), Sg, grid.x, d.n[0],
                                                               reinterpret_cast<float2*>(ws + L.ab0), G[HP_GNW], G[HP_GNB], acc);
     g_launches++;
     SRW_LAUNCH_CHECK();

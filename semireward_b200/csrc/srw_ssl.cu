@@ -132,9 +132,45 @@ __global__ void __launch_bounds__(SSL_THREADS) flexmatch_mask_kernel(const srw_f
 // ------------------------------------------------------------------------------------------------
 enum { ACT_NONE = 0, ACT_RELU = 1 };
 
-// out[r, n] = act(bias[n] + sum_k in[r, k] W[n, k]);  one warp per output, lanes over k (coalesced W rows)
+// out[r, n] = act(bias[n] + sum_k in[r, k] W[n, k]).  One warp per output COLUMN: the K / 32 weights of the row W[n, :] a lane needs are
+// loaded once into registers (independent loads, one L2 round trip) and reused for every batch row; per output the products are
+// summed in the same order as before (lane-strided partial sums over ascending k, then the xor-shuffle tree), so results are
+// bit-identical to the one-warp-per-output form — but a warp now waits for memory once per column instead of once per output
+// (these kernels are one CTA deep: the chain of dependent L2 round trips is what they cost).
+template <int KR>
+__device__ __forceinline__ void cta_linear_cols(const float* in, int64_t ld_in, int rows, const float* W, const float* bias, int N, float* out, int ld_out,
+                                                int act) {
+  constexpr int K = KR * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int n = warp; n < N; n += nw) {
+    const float* w = W + (int64_t)n * K + lane;
+    float wr[KR];
+#pragma unroll
+    for (int j = 0; j < KR; ++j) wr[j] = w[32 * j];
+    const float bn = bias[n];
+    for (int r = 0; r < rows; ++r) {
+      const float* x = in + (int64_t)r * ld_in + lane;
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < KR; ++j) acc = fmaf(x[32 * j], wr[j], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        acc += bn;
+        out[(int64_t)r * ld_out + n] = (act == ACT_RELU) ? fmaxf(acc, 0.f) : acc;
+      }
+    }
+  }
+}
 __device__ void cta_linear(const float* in, int64_t ld_in, int rows, int K, const float* W, const float* bias, int N, float* out, int ld_out,
                            int act) {
+  switch (K) {
+    case 64: cta_linear_cols<2>(in, ld_in, rows, W, bias, N, out, ld_out, act); return;
+    case 128: cta_linear_cols<4>(in, ld_in, rows, W, bias, N, out, ld_out, act); return;
+    case 256: cta_linear_cols<8>(in, ld_in, rows, W, bias, N, out, ld_out, act); return;
+    case 384: cta_linear_cols<12>(in, ld_in, rows, W, bias, N, out, ld_out, act); return;
+    case 768: cta_linear_cols<24>(in, ld_in, rows, W, bias, N, out, ld_out, act); return;
+    default: break;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int o = warp; o < rows * N; o += nw) {
     const int r = o / N, n = o % N;
@@ -149,12 +185,23 @@ __device__ void cta_linear(const float* in, int64_t ld_in, int rows, int K, cons
     }
   }
 }
-// dX[r, k] = sum_n dY[r, n] W[n, k]
+// dX[r, k] = sum_n dY[r, n] W[n, k]: one thread per output, n ascending in ONE accumulator (the summation order of the parity tests);
+// the weight loads of eight consecutive n are issued together so that the loop is N / 8 memory round trips, not N
 __device__ void cta_linear_dx(const float* dY, int rows, int N, const float* W, int K, float* dX) {
   for (int o = threadIdx.x; o < rows * K; o += blockDim.x) {
     const int r = o / K, k = o % K;
+    const float* dy = dY + r * N;
+    const float* w = W + k;
     float acc = 0.f;
-    for (int n = 0; n < N; ++n) acc = fmaf(dY[r * N + n], W[(int64_t)n * K + k], acc);
+    int n = 0;
+    for (; n + 8 <= N; n += 8) {
+      float wv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wv[j] = w[(int64_t)(n + j) * K];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(dy[n + j], wv[j], acc);
+    }
+    for (; n < N; ++n) acc = fmaf(dy[n], w[(int64_t)n * K], acc);
     dX[o] = acc;
   }
 }

@@ -55,7 +55,7 @@ __global__ void wrn_input_planes_kernel(const float* __restrict__ x, int N, Geo 
 // ------------------------------------------------------------------------------------------------
 // BatchNorm statistics: column sums over the valid rows, two stages
 // ------------------------------------------------------------------------------------------------
-constexpr int BN_ROWS_PER_CTA = 2048;
+constexpr int BN_ROWS_PER_CTA = 1024;
 // MODE 0: partial = (sum x, sum x^2).  MODE 1 (backward): du = dy * lrelu'(u), u = (x - mean) rstd gamma + beta; partial = (sum du, sum du xhat)
 template <int MODE>
 __global__ void __launch_bounds__(256) wrn_bn_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy, int64_t rows, int C, Geo g,
@@ -74,20 +74,34 @@ __global__ void __launch_bounds__(256) wrn_bn_partial_kernel(const float* __rest
     b4 = *reinterpret_cast<const float4*>(beta + c);
   }
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), t = s;
-  for (int64_t r = r0 + rl; r < r1; r += rpi) {
-    int n, y, xx;
-    if (!geo_valid(g, r, n, y, xx)) continue;
-    const float4 v = *reinterpret_cast<const float4*>(x + r * C + c);
-    if (MODE == 0) {
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      t.x = fmaf(v.x, v.x, t.x); t.y = fmaf(v.y, v.y, t.y); t.z = fmaf(v.z, v.z, t.z); t.w = fmaf(v.w, v.w, t.w);
-    } else {
-      const float4 d = *reinterpret_cast<const float4*>(dy + r * C + c);
-      const float hx = (v.x - m4.x) * a4.x, hy = (v.y - m4.y) * a4.y, hz = (v.z - m4.z) * a4.z, hw = (v.w - m4.w) * a4.w;
-      const float dx_ = fmaf(hx, g4.x, b4.x) > 0.f ? d.x : d.x * slope, dy_ = fmaf(hy, g4.y, b4.y) > 0.f ? d.y : d.y * slope;
-      const float dz_ = fmaf(hz, g4.z, b4.z) > 0.f ? d.z : d.z * slope, dw_ = fmaf(hw, g4.w, b4.w) > 0.f ? d.w : d.w * slope;
-      s.x += dx_; s.y += dy_; s.z += dz_; s.w += dw_;
-      t.x = fmaf(dx_, hx, t.x); t.y = fmaf(dy_, hy, t.y); t.z = fmaf(dz_, hz, t.z); t.w = fmaf(dw_, hw, t.w);
+  constexpr int U = 4;    // rows in flight per thread: the kernel is a pure HBM stream, one 16-byte load per row would leave it latency-bound
+  for (int64_t r = r0 + rl; r < r1; r += (int64_t)U * rpi) {
+    float4 v[U], d[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + (int64_t)u * rpi;
+      int n, y, xx;
+      ok[u] = rr < r1 && geo_valid(g, rr, n, y, xx);
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f); d[u] = v[u];
+      if (ok[u]) {
+        v[u] = *reinterpret_cast<const float4*>(x + rr * C + c);
+        if (MODE == 1) d[u] = *reinterpret_cast<const float4*>(dy + rr * C + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      if (MODE == 0) {
+        s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
+        t.x = fmaf(v[u].x, v[u].x, t.x); t.y = fmaf(v[u].y, v[u].y, t.y); t.z = fmaf(v[u].z, v[u].z, t.z); t.w = fmaf(v[u].w, v[u].w, t.w);
+      } else {
+        const float hx = (v[u].x - m4.x) * a4.x, hy = (v[u].y - m4.y) * a4.y, hz = (v[u].z - m4.z) * a4.z, hw = (v[u].w - m4.w) * a4.w;
+        const float dx_ = fmaf(hx, g4.x, b4.x) > 0.f ? d[u].x : d[u].x * slope, dy_ = fmaf(hy, g4.y, b4.y) > 0.f ? d[u].y : d[u].y * slope;
+        const float dz_ = fmaf(hz, g4.z, b4.z) > 0.f ? d[u].z : d[u].z * slope, dw_ = fmaf(hw, g4.w, b4.w) > 0.f ? d[u].w : d[u].w * slope;
+        s.x += dx_; s.y += dy_; s.z += dz_; s.w += dw_;
+        t.x = fmaf(dx_, hx, t.x); t.y = fmaf(dy_, hy, t.y); t.z = fmaf(dz_, hz, t.z); t.w = fmaf(dw_, hw, t.w);
+      }
     }
   }
   red[0][threadIdx.x] = s; red[1][threadIdx.x] = t;
@@ -106,18 +120,34 @@ __global__ void __launch_bounds__(256) wrn_bn_partial_kernel(const float* __rest
 // forward finish: mean, rstd of the batch (training) or of the running statistics (eval); running statistics advanced `1 + repeats`
 // times in training (F.batch_norm: running = (1 - m) running + m stat, unbiased variance; `repeats` = further identical passes of
 // the same batch, the deterministic sampling passes of stage 2)
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// one warp per channel: lanes stride over the per-CTA partials (fp64), shuffle tree
+__device__ __forceinline__ void bn_fold_partials(const float* __restrict__ partial, int nparts, int C, int c, double& s, double& q) {
+  const int lane = threadIdx.x & 31;
+  double a = 0.0, b = 0.0;
+  for (int p = lane; p < nparts; p += 32) { a += partial[(int64_t)p * 2 * C + c]; b += partial[(int64_t)p * 2 * C + C + c]; }
+  s = warp_sum_f64(a); q = warp_sum_f64(b);
+}
 __global__ void wrn_bn_finish_kernel(const float* __restrict__ partial, int nparts, int C, double n, float eps, float momentum, int training, int repeats,
                                      float* __restrict__ running_mean, float* __restrict__ running_var, int64_t* __restrict__ num_batches_tracked,
                                      float* __restrict__ mean_out, float* __restrict__ rstd_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
+  const bool lead = (threadIdx.x & 31) == 0;
   if (!training) {
-    mean_out[c] = running_mean[c];
-    rstd_out[c] = 1.0f / sqrtf(running_var[c] + eps);
+    if (lead) {
+      mean_out[c] = running_mean[c];
+      rstd_out[c] = 1.0f / sqrtf(running_var[c] + eps);
+    }
     return;
   }
-  double s = 0.0, q = 0.0;
-  for (int p = 0; p < nparts; ++p) { s += partial[(int64_t)p * 2 * C + c]; q += partial[(int64_t)p * 2 * C + C + c]; }
+  double s, q;
+  bn_fold_partials(partial, nparts, C, c, s, q);
+  if (!lead) return;
   const double m = s / n;
   const double var = fmax(q / n - m * m, 0.0);
   const float mf = (float)m, vf = (float)var;
@@ -135,10 +165,11 @@ __global__ void wrn_bn_finish_kernel(const float* __restrict__ partial, int npar
 // backward finish: dgamma (+)= sum du xhat, dbeta (+)= sum du; coef = (sum du / n, sum du xhat / n)
 __global__ void wrn_bn_bwd_finish_kernel(const float* __restrict__ partial, int nparts, int C, double n, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                          int accumulate, float* __restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int p = 0; p < nparts; ++p) { s += partial[(int64_t)p * 2 * C + c]; q += partial[(int64_t)p * 2 * C + C + c]; }
+  double s, q;
+  bn_fold_partials(partial, nparts, C, c, s, q);
+  if ((threadIdx.x & 31) != 0) return;
   if (dgamma) { dgamma[c] = accumulate ? dgamma[c] + (float)q : (float)q; dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s; }
   coef[c] = (float)(s / n); coef[C + c] = (float)(q / n);
 }
@@ -584,7 +615,7 @@ static int bn_stats(const Ctx& k, const float* x, int st, int C, float eps, int 
     SRW_LAUNCH_CHECK();
   }
   const double n = (double)k.d.N * k.d.geo[st].Hs * k.d.geo[st].Hs;
-  wrn_bn_finish_kernel<<<cdiv(C, 128), 128, 0, k.s>>>(partial, nparts, C, n, eps, k.d.momentum, training, repeats, rm, rv, nbt, mean, rstd);
+  wrn_bn_finish_kernel<<<cdiv(C, 8), 256, 0, k.s>>>(partial, nparts, C, n, eps, k.d.momentum, training, repeats, rm, rv, nbt, mean, rstd);
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;
@@ -607,7 +638,7 @@ static int bn_backward(const Ctx& k, const float* dy, const float* x, int st, in
   g_launches++;
   SRW_LAUNCH_CHECK();
   const double n = (double)k.d.N * k.d.geo[st].Hs * k.d.geo[st].Hs;
-  wrn_bn_bwd_finish_kernel<<<cdiv(C, 128), 128, 0, k.s>>>(partial, nparts, C, n, dgamma, dbeta, acc, coef);
+  wrn_bn_bwd_finish_kernel<<<cdiv(C, 8), 256, 0, k.s>>>(partial, nparts, C, n, dgamma, dbeta, acc, coef);
   g_launches++;
   SRW_LAUNCH_CHECK();
   if (planes_off >= 0) SRW_TRY(zero_slack(k, planes_off, st, C));
@@ -860,7 +891,7 @@ static int wrn_backward_body(const srw_wrn_bwd_args* a, cudaStream_t s) {
     wrn_bn_partial_kernel<0><<<nparts, 256, 0, s>>>(dout, nullptr, d.M[0], 16, d.geo[0], nullptr, nullptr, nullptr, nullptr, 0.f, partial);
     g_launches++;
     SRW_LAUNCH_CHECK();
-    wrn_bn_bwd_finish_kernel<<<1, 128, 0, s>>>(partial, nparts, 16, 1.0, nullptr, nullptr, 0, coef);   // coef[0 .. 15] = column sums (n = 1)
+    wrn_bn_bwd_finish_kernel<<<2, 256, 0, s>>>(partial, nparts, 16, 1.0, nullptr, nullptr, 0, coef);   // coef[0 .. 15] = column sums (n = 1)
     g_launches++;
     SRW_LAUNCH_CHECK();
     if (acc) {
