@@ -338,7 +338,7 @@ int make_plane_tmap(::CUtensorMap_st* out, const void* base, int64_t inner, int6
                     int box_outer, int box_planes);
 
 int gemm_pick_bn(int M, int N, int splits, int ctas = 148);
-int gemm2_pick_bn(int M, int N, int splits, bool b_mn, int ctas = 148);
+int gemm2_pick_bn(int M, int N, int splits, bool b_mn, int ctas = 148, int k_per_cta = 0);
 
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |

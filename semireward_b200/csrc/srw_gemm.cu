@@ -17,6 +17,7 @@
 // A SIMT kernel over the same operands and the same epilogue code is kept as the on-device verification twin
 // (srw_gemm_args.impl = SRW_GEMM_SIMT); it is a debugging aid, never the default path.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -795,7 +796,7 @@ int gemm_pick_bn(int M, int N, int splits, int ctas) {
 
 // Pair-tile width for the 2-CTA kernel (0 = use the 1-CTA kernel): 256 x BN tiles, BN/2 rows of B per CTA, which must be
 // a multiple of 64 for MN-major B.  Small problems (fewer pair tiles than half the SMs' worth) stay on the 1-CTA kernel.
-int gemm2_pick_bn(int M, int N, int splits, bool b_mn, int ctas) {
+int gemm2_pick_bn(int M, int N, int splits, bool b_mn, int ctas, int k_per_cta) {
   if (ctas <= 0) ctas = 148;
   const int npairs = std::max(1, ctas / 2);
   const int cands[3] = {256, 192, 128};
@@ -815,7 +816,10 @@ int gemm2_pick_bn(int M, int N, int splits, bool b_mn, int ctas) {
   const int bn1 = gemm_pick_bn(M, N, splits, ctas);
   const int64_t tiles1 = (int64_t)cdiv(M, BM) * cdiv(N, bn1) * std::max(1, splits);
   const double cost1 = (double)((tiles1 + ctas - 1) / ctas) * (bn1 + 40);
-  if (best == 0 || best_cost > 1.15 * cost1) return 0;
+  // deep reductions (>= 16 k-blocks per tile) are load-latency bound on the 1-CTA kernel's 2-stage ring at BN >= 128; the pair kernel's
+  // 3 stages of 48-56 KB hide it (measured, scripts/gemm_sweep.sh: fc2 forward 33.8 -> 28.5 us), so it may quantise worse and still win
+  const double slack = (k_per_cta >= 1024 && best != 256) ? 1.4 : 1.15;
+  if (best == 0 || best_cost > slack * cost1) return 0;
   return best;
 }
 
@@ -919,7 +923,15 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
   // ---- 2-CTA path: pair tiles of 256 x BN ----
   // max_ctas > 0: this GEMM may only occupy that many SMs (it runs next to other kernels on other streams)
   const int cta_cap = (a->max_ctas > 0 && a->max_ctas < num_sms) ? std::max(2, a->max_ctas) : num_sms;
-  const int bn2 = srw::gemm2_pick_bn(a->M, a->N, grid_z, a->b_mn_major != 0, cta_cap);
+  int bn2 = srw::gemm2_pick_bn(a->M, a->N, grid_z, a->b_mn_major != 0, cta_cap, kb_per_split * BK);
+  // tuning aid (scripts/gemm_bench.py --sweep): SRW_GEMM_FORCE = "1:<bn>" forces the 1-CTA kernel with that tile width, "2:<bn>" the 2-CTA kernel
+  static const char* force_env = getenv("SRW_GEMM_FORCE");
+  int force_bn1 = 0;
+  if (force_env && force_env[0] && force_env[1] == ':') {
+    const int fb = atoi(force_env + 2);
+    if (force_env[0] == '1' && (fb == 64 || fb == 128 || (fb == 192 && a->N % 192 == 0))) { bn2 = 0; force_bn1 = fb; }
+    if (force_env[0] == '2' && (fb == 128 || fb == 256 || (fb == 192 && a->N % 192 == 0 && !a->b_mn_major)) && a->N >= fb) bn2 = fb;
+  }
   if (a->impl == SRW_GEMM_TCGEN05 && bn2 > 0 && !segmented) {
     CUtensorMap ta, tb;
     if (!a->a_mn_major) rc = make_plane_tmap(&ta, a->a, a->K, a->M, a->lda, a->a_plane_stride, 128, 2);
@@ -953,7 +965,7 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
   }
 
   // ---- 1-CTA path ----
-  const int bn = srw::gemm_pick_bn(a->M, a->N, grid_z, cta_cap);
+  const int bn = force_bn1 ? force_bn1 : srw::gemm_pick_bn(a->M, a->N, grid_z, cta_cap);
   CUtensorMap ta, tb;
   if (!a->a_mn_major) rc = make_plane_tmap(&ta, a->a, a_inner, a_outer, a->lda, a->a_plane_stride, 128, 2);
   else rc = make_plane_tmap(&ta, a->a, a->M, a->K, a->lda, a->a_plane_stride, 64, 2);
