@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsrw_b200.so")
+LIB_PATH = os.environ.get("SRW_B200_LIB") or os.path.join(_HERE, "lib", "libsrw_b200.so")   # the override is an A/B aid for kernel work
 
 c_f32p = C.c_void_p
 i64 = C.c_int64

@@ -151,13 +151,15 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
 // row-group iterations of a chunk are straight-line code; the residual / aux operands of all eight are requested BEFORE
 // the TMEM load and the transpose, which hides their L2 latency (the epilogues are latency- and issue-bound, not
 // bandwidth-bound: 12 warps, 3 per scheduler).
-template <int BN, int EPI>
+template <int BN, int EPI, bool ACTDROP>
 __device__ __forceinline__ void drain_full(const EpiParams& ep, uint32_t acc_addr, float* st, int q, int part, int lane, int m0, int n0, int split) {
   const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
   const int row_first = m0 + q * 32 + sub_r;       // this lane's rows: row_first + 4 i
   float scale[8];
   uint32_t dkey[8], dbase[8];
-  const bool dropping = (EPI == SRW_EPI_RESID || EPI == SRW_EPI_GELU || EPI == SRW_EPI_DGELU) && ep.drop.on;
+  // RESID: run-time switch (BERT / HuBERT output dropout).  GELU / DGELU (HuBERT's activation dropout): only in the ACTDROP kernels —
+  // the default kernels keep exactly the code of the drop-free epilogues (mask state in registers cost them spills and 2.6 % of a ViT step)
+  const bool dropping = (EPI == SRW_EPI_RESID && ep.drop.on) || (ACTDROP && (EPI == SRW_EPI_GELU || EPI == SRW_EPI_DGELU));
   if (EPI == SRW_EPI_RESID) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) scale[i] = ep.row_scale ? ep.row_scale[(row_first + 4 * i) / ep.rows_per_scale] : 1.0f;
@@ -239,17 +241,17 @@ __device__ __forceinline__ void drain_full(const EpiParams& ep, uint32_t acc_add
   }
 }
 
-template <int BN>
+template <int BN, bool ACTDROP>
 __device__ __forceinline__ void drain_accumulator(const EpiParams& ep, uint32_t acc_addr, float* st, int q, int part, int lane, int m0, int n0,
                                                   int split, bool has_k) {
   if (has_k && m0 + BM <= ep.M && n0 + BN <= ep.N) {
     switch (ep.epilogue) {
-      case SRW_EPI_F32: drain_full<BN, SRW_EPI_F32>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
-      case SRW_EPI_PLANES: drain_full<BN, SRW_EPI_PLANES>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
-      case SRW_EPI_GELU: drain_full<BN, SRW_EPI_GELU>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
-      case SRW_EPI_RESID: drain_full<BN, SRW_EPI_RESID>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
-      case SRW_EPI_DGELU: drain_full<BN, SRW_EPI_DGELU>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
-      default: drain_full<BN, SRW_EPI_SPLITK>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
+      case SRW_EPI_F32: drain_full<BN, SRW_EPI_F32, false>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
+      case SRW_EPI_PLANES: drain_full<BN, SRW_EPI_PLANES, false>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
+      case SRW_EPI_GELU: drain_full<BN, SRW_EPI_GELU, ACTDROP>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
+      case SRW_EPI_RESID: drain_full<BN, SRW_EPI_RESID, false>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
+      case SRW_EPI_DGELU: drain_full<BN, SRW_EPI_DGELU, ACTDROP>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
+      default: drain_full<BN, SRW_EPI_SPLITK, false>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
     }
   }
   // edge tiles (partial in M or N) and empty K ranges: generic bounds-checked path
@@ -291,7 +293,7 @@ struct TcParams {
   int a_seg_rows;   //      (implicit-GEMM 3x3 convolution over a zero-bordered NHWC tensor, srw_wrn.cu)
 };
 
-template <int BN>
+template <int BN, bool ACTDROP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                            const TcParams tp, const EpiParams ep) {
@@ -438,7 +440,7 @@ gemm_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
       mbar_wait(&acc_full[as], (tile_iter >> 1) & 1);
       tc_fence_after();
       if (tr && warp == 4 && lane == 0 && tile_iter < 5) tr[4 + 2 * tile_iter] = clock64();
-      drain_accumulator<BN>(ep, tmem_base + as * 256, epi_stage + (warp - 4) * (32 * EPI_STAGE_LD), q, part, lane, m0, n0, split, has_k);
+      drain_accumulator<BN, ACTDROP>(ep, tmem_base + as * 256, epi_stage + (warp - 4) * (32 * EPI_STAGE_LD), q, part, lane, m0, n0, split, has_k);
       tc_fence_before();
       __syncwarp();
       if (tr && warp == 4 && lane == 0 && tile_iter < 5) tr[5 + 2 * tile_iter] = clock64();
@@ -515,7 +517,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_m256(int n, int a_mn_majo
          ((uint32_t)(256 >> 4) << 24);
 }
 
-template <int BN>
+template <int BN, bool ACTDROP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcParams tp,
                             const EpiParams ep) {
@@ -651,7 +653,7 @@ gemm2_bf16x3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
       const uint32_t as = tile_iter & 1;
       mbar_wait(&acc_full[as], (tile_iter >> 1) & 1);
       tc_fence_after();
-      drain_accumulator<BN>(ep, tmem_base + as * 256, epi_stage + (warp - 4) * (32 * EPI_STAGE_LD), q, part, lane, m0, n0, split, has_k);
+      drain_accumulator<BN, ACTDROP>(ep, tmem_base + as * 256, epi_stage + (warp - 4) * (32 * EPI_STAGE_LD), q, part, lane, m0, n0, split, has_k);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[as]), 0));
@@ -816,9 +818,10 @@ int gemm2_pick_bn(int M, int N, int splits, bool b_mn, int ctas, int k_per_cta) 
   const int bn1 = gemm_pick_bn(M, N, splits, ctas);
   const int64_t tiles1 = (int64_t)cdiv(M, BM) * cdiv(N, bn1) * std::max(1, splits);
   const double cost1 = (double)((tiles1 + ctas - 1) / ctas) * (bn1 + 40);
-  // deep reductions (>= 16 k-blocks per tile) are load-latency bound on the 1-CTA kernel's 2-stage ring at BN >= 128; the pair kernel's
-  // 3 stages of 48-56 KB hide it (measured, scripts/gemm_sweep.sh: fc2 forward 33.8 -> 28.5 us), so it may quantise worse and still win
-  const double slack = (k_per_cta >= 1024 && best != 256) ? 1.4 : 1.15;
+  // (scripts/gemm_sweep.sh: forcing the 3-stage pair kernel on the deep-K shapes wins 5 us on fc2 forward in isolation, 33.8 -> 28.5 us,
+  // but the whole step did not move — 4.68 vs 4.74 ms — so the wave-quantisation rule stays as it was)
+  (void)k_per_cta;
+  const double slack = 1.15;
   if (best == 0 || best_cost > slack * cost1) return 0;
   return best;
 }
@@ -890,12 +893,18 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
     auto set = [&](const void* fn, int bytes) {
       if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     };
-    set((const void*)gemm_bf16x3_tcgen05_kernel<192>, gemm_smem_bytes(192));
-    set((const void*)gemm_bf16x3_tcgen05_kernel<128>, gemm_smem_bytes(128));
-    set((const void*)gemm_bf16x3_tcgen05_kernel<64>, gemm_smem_bytes(64));
-    set((const void*)gemm2_bf16x3_tcgen05_kernel<256>, gemm2_smem_bytes(256));
-    set((const void*)gemm2_bf16x3_tcgen05_kernel<192>, gemm2_smem_bytes(192));
-    set((const void*)gemm2_bf16x3_tcgen05_kernel<128>, gemm2_smem_bytes(128));
+    set((const void*)gemm_bf16x3_tcgen05_kernel<192, false>, gemm_smem_bytes(192));
+    set((const void*)gemm_bf16x3_tcgen05_kernel<128, false>, gemm_smem_bytes(128));
+    set((const void*)gemm_bf16x3_tcgen05_kernel<64, false>, gemm_smem_bytes(64));
+    set((const void*)gemm2_bf16x3_tcgen05_kernel<256, false>, gemm2_smem_bytes(256));
+    set((const void*)gemm2_bf16x3_tcgen05_kernel<192, false>, gemm2_smem_bytes(192));
+    set((const void*)gemm2_bf16x3_tcgen05_kernel<128, false>, gemm2_smem_bytes(128));
+    set((const void*)gemm_bf16x3_tcgen05_kernel<192, true>, gemm_smem_bytes(192));
+    set((const void*)gemm_bf16x3_tcgen05_kernel<128, true>, gemm_smem_bytes(128));
+    set((const void*)gemm_bf16x3_tcgen05_kernel<64, true>, gemm_smem_bytes(64));
+    set((const void*)gemm2_bf16x3_tcgen05_kernel<256, true>, gemm2_smem_bytes(256));
+    set((const void*)gemm2_bf16x3_tcgen05_kernel<192, true>, gemm2_smem_bytes(192));
+    set((const void*)gemm2_bf16x3_tcgen05_kernel<128, true>, gemm2_smem_bytes(128));
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) num_sms = n;
   });
@@ -907,6 +916,7 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
   tp.splits = grid_z;
   tp.a_seg_kb = 0; tp.a_seg_rows = 0;
   const bool segmented = a->a_seg_k > 0;
+  const bool actdrop = ep.drop.on && (a->epilogue == SRW_EPI_GELU || a->epilogue == SRW_EPI_DGELU);   // HuBERT's activation dropout: own kernel instantiations
   int64_t a_inner = a->K, a_outer = a->M;
   if (segmented) {
     // K = nseg * a_seg_kb * 64 (every segment padded to whole k-blocks; B carries zeros there, TMA zero-fills A past a_seg_k)
@@ -954,9 +964,15 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
     cfg.attrs = attr; cfg.numAttrs = 2;
     void* prof = prof_begin(SRW_PROF_GEMM, flops, bytes, stream);
     cudaError_t le;
-    if (bn2 == 256) le = cudaLaunchKernelEx(&cfg, gemm2_bf16x3_tcgen05_kernel<256>, ta, tb, tp, ep);
-    else if (bn2 == 192) le = cudaLaunchKernelEx(&cfg, gemm2_bf16x3_tcgen05_kernel<192>, ta, tb, tp, ep);
-    else le = cudaLaunchKernelEx(&cfg, gemm2_bf16x3_tcgen05_kernel<128>, ta, tb, tp, ep);
+    if (actdrop) {
+      if (bn2 == 256) le = cudaLaunchKernelEx(&cfg, gemm2_bf16x3_tcgen05_kernel<256, true>, ta, tb, tp, ep);
+      else if (bn2 == 192) le = cudaLaunchKernelEx(&cfg, gemm2_bf16x3_tcgen05_kernel<192, true>, ta, tb, tp, ep);
+      else le = cudaLaunchKernelEx(&cfg, gemm2_bf16x3_tcgen05_kernel<128, true>, ta, tb, tp, ep);
+    } else {
+      if (bn2 == 256) le = cudaLaunchKernelEx(&cfg, gemm2_bf16x3_tcgen05_kernel<256, false>, ta, tb, tp, ep);
+      else if (bn2 == 192) le = cudaLaunchKernelEx(&cfg, gemm2_bf16x3_tcgen05_kernel<192, false>, ta, tb, tp, ep);
+      else le = cudaLaunchKernelEx(&cfg, gemm2_bf16x3_tcgen05_kernel<128, false>, ta, tb, tp, ep);
+    }
     prof_end(prof, stream);
     g_launches++;
     SRW_CUDA(le);
@@ -978,9 +994,15 @@ extern "C" int srw_gemm(const srw_gemm_args* a, void* stream_) {
   const int grid = std::min(total_tiles, cta_cap);
   void* prof = prof_begin(SRW_PROF_GEMM, flops, bytes, stream);
   cudaError_t le;
-  if (bn == 192) le = launch_pdl(gemm_bf16x3_tcgen05_kernel<192>, dim3(grid), dim3(GEMM_THREADS), gemm_smem_bytes(192), stream, ta, tb, tp, ep);
-  else if (bn == 128) le = launch_pdl(gemm_bf16x3_tcgen05_kernel<128>, dim3(grid), dim3(GEMM_THREADS), gemm_smem_bytes(128), stream, ta, tb, tp, ep);
-  else le = launch_pdl(gemm_bf16x3_tcgen05_kernel<64>, dim3(grid), dim3(GEMM_THREADS), gemm_smem_bytes(64), stream, ta, tb, tp, ep);
+  if (actdrop) {
+    if (bn == 192) le = launch_pdl(gemm_bf16x3_tcgen05_kernel<192, true>, dim3(grid), dim3(GEMM_THREADS), gemm_smem_bytes(192), stream, ta, tb, tp, ep);
+    else if (bn == 128) le = launch_pdl(gemm_bf16x3_tcgen05_kernel<128, true>, dim3(grid), dim3(GEMM_THREADS), gemm_smem_bytes(128), stream, ta, tb, tp, ep);
+    else le = launch_pdl(gemm_bf16x3_tcgen05_kernel<64, true>, dim3(grid), dim3(GEMM_THREADS), gemm_smem_bytes(64), stream, ta, tb, tp, ep);
+  } else {
+    if (bn == 192) le = launch_pdl(gemm_bf16x3_tcgen05_kernel<192, false>, dim3(grid), dim3(GEMM_THREADS), gemm_smem_bytes(192), stream, ta, tb, tp, ep);
+    else if (bn == 128) le = launch_pdl(gemm_bf16x3_tcgen05_kernel<128, false>, dim3(grid), dim3(GEMM_THREADS), gemm_smem_bytes(128), stream, ta, tb, tp, ep);
+    else le = launch_pdl(gemm_bf16x3_tcgen05_kernel<64, false>, dim3(grid), dim3(GEMM_THREADS), gemm_smem_bytes(64), stream, ta, tb, tp, ep);
+  }
   prof_end(prof, stream);
   g_launches++;
   SRW_CUDA(le);
