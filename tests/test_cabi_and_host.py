@@ -199,9 +199,14 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["metric"] == "SSL train-step samples/sec (ViT-S CIFAR-100)" and "workload" in d["config"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
-    # the native arm refuses the configs that have no CUDA path instead of falling back to anything
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", "5"], capture_output=True, text=True, timeout=120, cwd=ROOT)
-    assert r.returncode != 0 and "no CUDA path" in (r.stderr + r.stdout)
+    # the native arm never falls back to anything: without a GPU it fails loudly (every config has a CUDA path and only a CUDA path) ...
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", "5", "--steps", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+        assert r.returncode != 0 and not [ln for ln in r.stdout.split("\n") if ln.startswith("{")], r.stdout[-500:]
+    # ... and it refuses what is not built (data-parallel WRN needs SyncBatchNorm) instead of running something else
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", "1"], capture_output=True, text=True, timeout=120, cwd=ROOT,
+                       env=dict(os.environ, WORLD_SIZE="2", RANK="0", LOCAL_RANK="0"))
+    assert r.returncode != 0 and "single-GPU" in (r.stderr + r.stdout)
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/semilearn"), reason="live reference only exists in the build container")
