@@ -522,7 +522,7 @@ def main_native(a):
         g = st[L.PROF_GEMM]
         ach = g.flops / (g.total_ms * 1e-3) / 1e12 if g.total_ms > 0 else 0.0
         traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
         if os.path.isfile(tp) and a.config == 2:   # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch from the committed `ncu --set full` capture
             tj = json.load(open(tp))
             traffic, traffic_src = tj.get("gemm_mean_traffic_bytes"), tj.get("source")

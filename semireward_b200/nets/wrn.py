@@ -26,26 +26,32 @@ from .utils import load_checkpoint
 momentum = 0.001
 
 
-class BasicBlock(nn.Module):   # wrn.py:30-44: parameter / buffer holder with the reference's child names and registration order
-    def __init__(self, in_planes, out_planes, stride, dropRate=0.0, activate_before_residual=False):
+def _conv(cin, cout, k, stride, bias=False):
+    return nn.Conv2d(cin, cout, kernel_size=k, stride=stride, padding=k // 2, bias=bias)
+
+
+class BasicBlock(nn.Module):
+    """Parameter / buffer holder of one pre-activation block.  Children carry the reference's names in its registration order
+    (bn1, conv1, bn2, conv2[, convShortcut]; wrn.py:30-44), so `state_dict()` keys and `named_parameters()` order are the reference's;
+    the activation modules have no state and are not materialised."""
+
+    def __init__(self, in_planes, out_planes, stride, activate_before_residual=False):
         super().__init__()
-        self.bn1 = nn.BatchNorm2d(in_planes, momentum=0.001)
-        self.relu1 = nn.LeakyReLU(negative_slope=0.1, inplace=True)
-        self.conv1 = nn.Conv2d(in_planes, out_planes, kernel_size=3, stride=stride, padding=1, bias=False)
-        self.bn2 = nn.BatchNorm2d(out_planes, momentum=0.001)
-        self.relu2 = nn.LeakyReLU(negative_slope=0.1, inplace=True)
-        self.conv2 = nn.Conv2d(out_planes, out_planes, kernel_size=3, stride=1, padding=1, bias=False)
-        self.droprate = dropRate
         self.equalInOut = in_planes == out_planes
-        self.convShortcut = (not self.equalInOut) and nn.Conv2d(in_planes, out_planes, kernel_size=1, stride=stride, padding=0, bias=False) or None
         self.activate_before_residual = activate_before_residual
+        for name, mod in (("bn1", nn.BatchNorm2d(in_planes, momentum=momentum)), ("conv1", _conv(in_planes, out_planes, 3, stride)),
+                          ("bn2", nn.BatchNorm2d(out_planes, momentum=momentum)), ("conv2", _conv(out_planes, out_planes, 3, 1))):
+            self.add_module(name, mod)
+        self.convShortcut = None if self.equalInOut else _conv(in_planes, out_planes, 1, stride)
 
 
 class NetworkBlock(nn.Module):
-    def __init__(self, nb_layers, in_planes, out_planes, block, stride, drop_rate=0.0, activate_before_residual=False):
+    """`nb_layers` blocks under `.layer` (an nn.Sequential, wrn.py:57-66): only the first changes width / resolution."""
+
+    def __init__(self, nb_layers, in_planes, out_planes, stride, activate_before_residual=False):
         super().__init__()
-        self.layer = nn.Sequential(*[block(i == 0 and in_planes or out_planes, out_planes, i == 0 and stride or 1, drop_rate, activate_before_residual)
-                                     for i in range(int(nb_layers))])
+        widths = [in_planes] + [out_planes] * (int(nb_layers) - 1)
+        self.layer = nn.Sequential(*[BasicBlock(w, out_planes, stride if i == 0 else 1, activate_before_residual) for i, w in enumerate(widths)])
 
 
 class WideResNet(NativeBackbone, nn.Module):
@@ -58,12 +64,10 @@ class WideResNet(NativeBackbone, nn.Module):
         channels = [16, 16 * widen_factor, 32 * widen_factor, 64 * widen_factor]
         assert (depth - 4) % 6 == 0
         n = (depth - 4) // 6
-        self.conv1 = nn.Conv2d(3, channels[0], kernel_size=3, stride=1, padding=1, bias=True)
-        self.block1 = NetworkBlock(n, channels[0], channels[1], BasicBlock, first_stride, drop_rate, activate_before_residual=True)
-        self.block2 = NetworkBlock(n, channels[1], channels[2], BasicBlock, 2, drop_rate)
-        self.block3 = NetworkBlock(n, channels[2], channels[3], BasicBlock, 2, drop_rate)
-        self.bn1 = nn.BatchNorm2d(channels[3], momentum=0.001, eps=0.001)
-        self.relu = nn.LeakyReLU(negative_slope=0.1, inplace=False)
+        self.conv1 = _conv(3, channels[0], 3, 1, bias=True)
+        for b, stride in enumerate((first_stride, 2, 2)):
+            self.add_module(f"block{b + 1}", NetworkBlock(n, channels[b], channels[b + 1], stride, activate_before_residual=(b == 0)))
+        self.bn1 = nn.BatchNorm2d(channels[3], momentum=momentum, eps=0.001)      # wrn.py:97: the one BatchNorm with eps 1e-3
         self.classifier = nn.Linear(channels[3], num_classes)
         self.channels = channels[3]
         self.num_features = channels[3]

@@ -200,3 +200,80 @@ def test_hubert_ssl_steps_vs_oracle(algorithm, over, hg, drop):
             for n, q in alg.rewarder.named_parameters():
                 q.copy_(orc.rp[n].detach())
         alg.model.mark_weights_updated()
+
+
+def test_hubert_ssl_steps_with_layerdrop_and_specaugment_vs_oracle():
+    """The two structural sources of randomness of HubertModel's train mode at the level of the SSL step: every model call of the run
+    gets its own LayerDrop pattern and SpecAugment frames (injected identically into the oracle's calls and into the native launch's
+    call segments), dropout 0.1 on top.  Stage 1, the gap step and stage 2 (K + 1 passes = 3 (K + 1) calls in ONE native launch whose
+    segments skip different layers, against the oracle's sequential calls)."""
+    from oracle import hubert_oracle as HO
+    from test_train_step_gpu import _grad_tap, _mask2_tie
+    drop, layers, samples = 0.1, 3, 8000
+    cfg = hubert_small_cfg(algorithm="srflexmatch", num_train_iter=16, start_timing=2)
+    hc = HO.HubertCfg(layers=layers, num_classes=cfg["num_classes"], feat_proj_dropout=drop, hidden_dropout=drop, attention_dropout=drop,
+                      activation_dropout=drop, pooled_dropout=drop)
+    orc = HO.build_det_hubert_oracle(hc, _step_cfg(cfg), seed=0, head_gain=4.0)
+    alg = _build_native(cfg, layers, 4.0, drop=drop)
+    net = alg.model
+    orc.drop_seed = 5
+    net.dropout_seed = 5
+    Fr = hc.frames(samples)
+    nl, nu = cfg["batch_size"], cfg["batch_size"] * cfg["uratio"]
+    rng = np.random.default_rng(7)
+
+    def decisions(call):   # deterministic per call index: ~1 layer in 3 skipped, two short spans per clip
+        r = np.random.default_rng(1000 + call)
+        skip = (r.random(layers) < 0.34).astype(np.uint8)
+        n = nl if call % 3 == 0 else nu
+        mask = np.zeros((n, Fr), dtype=bool)
+        for b in range(n):
+            for s0 in r.choice(Fr - 3, 2, replace=False):
+                mask[b, s0:s0 + 3] = True
+        return skip, mask
+
+    orc.stochastic_inputs = lambda call: (torch.from_numpy(decisions(call)[1]), tuple(int(i) for i in np.nonzero(decisions(call)[0])[0]))
+    tap = _grad_tap(alg)
+    seen_skip = 0
+    for it in range(5):
+        K = 0 if it <= cfg["start_timing"] else int(max(8, 1 + cfg["num_train_iter"] / it))
+        for c in range(net._calls, net._calls + 3 * (K + 1)):
+            sk, mk = decisions(c)
+            net.set_call_draws(c, layer_skip=sk, mask_time=mk)
+            seen_skip += int(sk.sum())
+        batch = _audio_batch(cfg, it, samples)
+        rec = orc.train_step(dict(batch), it)
+        ref_grads = orc.param_update()
+        alg.it = it
+        alg.out_dict, alg.log_dict = alg.train_step(**alg.process_batch(**batch))
+        alg.call_hook("after_train_step")
+        torch.cuda.synchronize()
+        assert net._calls == orc.calls, (it, net._calls, orc.calls)
+        ld = alg.log_dict
+        assert abs(ld["train/sup_loss"] - float(rec["sup_loss"])) < 1e-3, (it, ld, float(rec["sup_loss"]))
+        assert torch.equal(alg._last_pseudo_label.cpu(), rec["pseudo"]) and torch.equal(alg._last_mask.cpu(), rec["mask"]), it
+        if not _mask2_tie(rec):
+            for kn, ko in (("train/unsup_loss", "unsup_loss"), ("train/total_loss", "total_loss")):
+                assert abs(ld[kn] - float(rec[ko])) < 1e-3, f"it {it} {ko}: {ld[kn]} vs {float(rec[ko])}"
+            worst, wn = 0.0, ""
+            gmax = max(g.abs().max().item() for g in ref_grads.values() if g is not None)
+            for n, q in net.named_parameters():
+                gr = ref_grads[n]
+                if gr is None:
+                    continue
+                sc = gr.abs().max().item()
+                if sc < 1e-9 or n.endswith("attention.k_proj.bias"):
+                    continue
+                e = (tap[n].cpu() - gr).abs().max().item() / sc
+                if e > worst and not e * sc < 1e-5 * gmax:
+                    worst, wn = e, n
+            print(f"hubert layerdrop+specaugment it {it}: total {ld['train/total_loss']:.5f} (oracle {float(rec['total_loss']):.5f}) K {rec.get('K', 0)} grad rel err {worst:.2e} ({wn})")
+            assert worst < 1e-3, (it, worst, wn)
+            assert tap["model.masked_spec_embed"].abs().max().item() > 0      # SpecAugment frames feed their gradient to the embedding
+        with torch.no_grad():
+            for n, q in net.named_parameters():
+                q.copy_(orc.p[n].detach())
+            for n, q in alg.rewarder.named_parameters():
+                q.copy_(orc.rp[n].detach())
+        net.mark_weights_updated()
+    assert seen_skip > 0
