@@ -377,8 +377,13 @@ typedef struct {
 int srw_hubert_frames(const srw_hubert_config* c, int samples);                 /* F for clips of `samples` samples (< 0: invalid) */
 int64_t srw_hubert_weight_planes_bytes(const srw_hubert_config* c);
 int64_t srw_hubert_workspace_bytes(const srw_hubert_config* c, int batch, int samples, int grad_batch);
-/* rebuilds the whole plane cache (re-laid-out conv weights, weight-normalised positional taps, packed q|k|v): once per optimizer step */
+/* rebuilds the whole plane cache (re-laid-out conv weights, weight-normalised positional taps, packed q|k|v) */
 int srw_hubert_prepare_weights(const srw_hubert_config* c, const float* const* params, void* weight_planes, void* stream);
+/* The encoder matrices (q | k | v, out_proj, intermediate_dense, output_dense: 85 of the 94 M parameters) have per-parameter plane slots
+ * the fused AdamW kernel rewrites in the same pass as the parameter (like the ViT / BERT caches); after such a step only the front end
+ * (conv relayouts, projection, weight-normalised positional taps, packed biases) needs rebuilding: */
+int srw_hubert_prepare_front(const srw_hubert_config* c, const float* const* params, void* weight_planes, void* stream);
+int srw_hubert_weight_plane_slot(const srw_hubert_config* c, int param_index, int64_t* byte_offset, int* cols, int* ldp, int64_t* plane_stride);
 
 typedef struct {
   const srw_hubert_config* cfg;

@@ -274,6 +274,8 @@ SYMBOLS = [
     ("srw_hubert_weight_planes_bytes", i64, [C.POINTER(HubertConfig)]),
     ("srw_hubert_workspace_bytes", i64, [C.POINTER(HubertConfig), i32, i32, i32]),
     ("srw_hubert_prepare_weights", i32, [C.POINTER(HubertConfig), C.POINTER(vp), vp, vp]),
+    ("srw_hubert_prepare_front", i32, [C.POINTER(HubertConfig), C.POINTER(vp), vp, vp]),
+    ("srw_hubert_weight_plane_slot", i32, [C.POINTER(HubertConfig), i32, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]),
     ("srw_hubert_forward", i32, [C.POINTER(HubertFwdArgs), vp]),
     ("srw_hubert_backward", i32, [C.POINTER(HubertBwdArgs), vp]),
     ("srw_wrn_num_params", i32, [C.POINTER(WrnConfig)]),

@@ -824,8 +824,9 @@ extern "C" int64_t srw_hubert_workspace_bytes(const srw_hubert_config* c, int ba
   return make_hlayout(d).total;
 }
 
-extern "C" int srw_hubert_prepare_weights(const srw_hubert_config* c, const float* const* P, void* weight_planes, void* stream_) {
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+// what: 1 = front end (re-laid-out conv weights, projection, weight-normalised positional taps, packed q|k|v biases), 2 = the encoder
+// matrices (q|k|v, out_proj, FFN), 3 = both
+static int hubert_prepare(const srw_hubert_config* c, const float* const* P, void* weight_planes, int what, cudaStream_t s) {
   SRW_REQUIRE(c && P && weight_planes, "srw_hubert_prepare_weights: null pointer");
   HDims d;
   int samples = 400;
@@ -834,42 +835,82 @@ extern "C" int srw_hubert_prepare_weights(const srw_hubert_config* c, const floa
   const HWOff w = hub_weight_layout(d);
   uint8_t* base = reinterpret_cast<uint8_t*>(weight_planes);
   auto BF = [&](int64_t off) { return reinterpret_cast<__nv_bfloat16*>(base + off); };
-  for (int l = 1; l < d.NC; ++l) {
-    const int k = d.k[l];
-    hub_conv_relayout_kernel<<<148 * 4, 256, 0, s>>>(P[HP_CONV1 + l - 1], k, BF(w.convf[l]), (int64_t)HC * k * HC, k == 3 ? BF(w.conve[l]) : nullptr,
-                                                     (int64_t)HC * 2 * HC);
+  const int D = d.D, F = d.F;
+  if (what & 1) {
+    for (int l = 1; l < d.NC; ++l) {
+      const int k = d.k[l];
+      hub_conv_relayout_kernel<<<148 * 4, 256, 0, s>>>(P[HP_CONV1 + l - 1], k, BF(w.convf[l]), (int64_t)HC * k * HC, k == 3 ? BF(w.conve[l]) : nullptr,
+                                                       (int64_t)HC * 2 * HC);
+      g_launches++;
+      SRW_LAUNCH_CHECK();
+    }
+    SRW_TRY(split_to(P[hp_after_conv(d, FP_W)], HC, d.D, HC, base + w.proj, HC, nullptr, 1, s));
+    float* norm = reinterpret_cast<float*>(base + w.pos_norm);
+    hub_pos_norm_kernel<<<d.PK, 256, 0, s>>>(P[hp_after_conv(d, POS_V)], d.D * d.GC, d.PK, norm);
+    g_launches++;
+    SRW_LAUNCH_CHECK();
+    hub_pos_relayout_kernel<<<148 * 4, 256, 0, s>>>(P[hp_after_conv(d, POS_V)], P[hp_after_conv(d, POS_G)], norm, d.D, d.GC, d.PK, BF(w.posf), BF(w.posd),
+                                                    (int64_t)d.D * d.GC * d.PK);
+    g_launches++;
+    SRW_LAUNCH_CHECK();
+    HubQkvBiasPtrs bp = {};
+    for (int l = 0; l < d.NL; ++l) {
+      bp.p[3 * l] = P[hp_layer(d, l, HY_QB)]; bp.p[3 * l + 1] = P[hp_layer(d, l, HY_KB)]; bp.p[3 * l + 2] = P[hp_layer(d, l, HY_VB)];
+    }
+    const int nb = d.NL * 3 * D;
+    hub_pack_qkv_bias_kernel<<<cdiv(nb, 256), 256, 0, s>>>(bp, d.NL, D, reinterpret_cast<float*>(base + w.qkv_bias));
     g_launches++;
     SRW_LAUNCH_CHECK();
   }
-  SRW_TRY(split_to(P[hp_after_conv(d, FP_W)], HC, d.D, HC, base + w.proj, HC, nullptr, 1, s));
-  float* norm = reinterpret_cast<float*>(base + w.pos_norm);
-  hub_pos_norm_kernel<<<d.PK, 256, 0, s>>>(P[hp_after_conv(d, POS_V)], d.D * d.GC, d.PK, norm);
-  g_launches++;
-  SRW_LAUNCH_CHECK();
-  hub_pos_relayout_kernel<<<148 * 4, 256, 0, s>>>(P[hp_after_conv(d, POS_V)], P[hp_after_conv(d, POS_G)], norm, d.D, d.GC, d.PK, BF(w.posf), BF(w.posd),
-                                                  (int64_t)d.D * d.GC * d.PK);
-  g_launches++;
-  SRW_LAUNCH_CHECK();
-  HubQkvBiasPtrs bp = {};
-  const int D = d.D, F = d.F;
-  for (int l = 0; l < d.NL; ++l) {
-    const int order[3] = {HY_QW, HY_KW, HY_VW};   // packed rows: q | k | v (the attention kernels' column order)
-    for (int i = 0; i < 3; ++i) {
-      srw_split_args a = {};
-      a.x = P[hp_layer(d, l, order[i])]; a.ldx = D; a.rows = D; a.cols = D; a.rows_per_scale = 1;
-      a.planes = base + w.qkv[l] + (int64_t)i * D * D * 2; a.ldp = D; a.plane_stride = (int64_t)3 * D * D;
-      SRW_TRY(srw_split_planes(&a, s));
-      bp.p[3 * l + i] = P[hp_layer(d, l, order[i] + 1)];
+  if (what & 2) {
+    for (int l = 0; l < d.NL; ++l) {
+      const int order[3] = {HY_QW, HY_KW, HY_VW};   // packed rows: q | k | v (the attention kernels' column order)
+      for (int i = 0; i < 3; ++i) {
+        srw_split_args a = {};
+        a.x = P[hp_layer(d, l, order[i])]; a.ldx = D; a.rows = D; a.cols = D; a.rows_per_scale = 1;
+        a.planes = base + w.qkv[l] + (int64_t)i * D * D * 2; a.ldp = D; a.plane_stride = (int64_t)3 * D * D;
+        SRW_TRY(srw_split_planes(&a, s));
+      }
+      SRW_TRY(split_to(P[hp_layer(d, l, HY_OW)], D, D, D, base + w.o[l], D, nullptr, 1, s));
+      SRW_TRY(split_to(P[hp_layer(d, l, HY_F1W)], D, F, D, base + w.f1[l], D, nullptr, 1, s));
+      SRW_TRY(split_to(P[hp_layer(d, l, HY_F2W)], F, D, F, base + w.f2[l], F, nullptr, 1, s));
     }
-    SRW_TRY(split_to(P[hp_layer(d, l, HY_OW)], D, D, D, base + w.o[l], D, nullptr, 1, s));
-    SRW_TRY(split_to(P[hp_layer(d, l, HY_F1W)], D, F, D, base + w.f1[l], D, nullptr, 1, s));
-    SRW_TRY(split_to(P[hp_layer(d, l, HY_F2W)], F, D, F, base + w.f2[l], F, nullptr, 1, s));
   }
-  const int nb = d.NL * 3 * D;
-  hub_pack_qkv_bias_kernel<<<cdiv(nb, 256), 256, 0, s>>>(bp, d.NL, D, reinterpret_cast<float*>(base + w.qkv_bias));
-  g_launches++;
-  SRW_LAUNCH_CHECK();
   return SRW_OK;
+}
+
+extern "C" int srw_hubert_prepare_weights(const srw_hubert_config* c, const float* const* P, void* weight_planes, void* stream_) {
+  return hubert_prepare(c, P, weight_planes, 3, reinterpret_cast<cudaStream_t>(stream_));
+}
+extern "C" int srw_hubert_prepare_front(const srw_hubert_config* c, const float* const* P, void* weight_planes, void* stream_) {
+  return hubert_prepare(c, P, weight_planes, 1, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int srw_hubert_weight_plane_slot(const srw_hubert_config* c, int param_index, int64_t* byte_offset, int* cols, int* ldp, int64_t* plane_stride) {
+  SRW_REQUIRE(c && byte_offset && cols && ldp && plane_stride, "srw_hubert_weight_plane_slot: null pointer");
+  HDims d;
+  int samples = 400;
+  for (int tries = 0; tries < 12 && make_hdims(c, 1, samples, 0, d); ++tries) samples *= 2;
+  SRW_TRY(make_hdims(c, 1, samples, 0, d));
+  const HWOff w = hub_weight_layout(d);
+  const int rel = param_index - hp_layer(d, 0, 0);
+  if (rel >= 0 && rel < 16 * d.NL) {
+    const int l = rel / 16, which = rel % 16;
+    const int64_t D = d.D, F = d.F;
+    int64_t off = -1, cc = 0, ps = 0;
+    if (which == HY_QW) { off = w.qkv[l]; cc = D; ps = 3 * D * D; }
+    else if (which == HY_KW) { off = w.qkv[l] + D * D * 2; cc = D; ps = 3 * D * D; }        // rows [D, 2D) of the packed [3D, D] hi plane (bf16)
+    else if (which == HY_VW) { off = w.qkv[l] + 2 * D * D * 2; cc = D; ps = 3 * D * D; }
+    else if (which == HY_OW) { off = w.o[l]; cc = D; ps = D * D; }
+    else if (which == HY_F1W) { off = w.f1[l]; cc = D; ps = F * D; }
+    else if (which == HY_F2W) { off = w.f2[l]; cc = F; ps = D * F; }
+    if (off >= 0) {
+      *byte_offset = off; *cols = (int)cc; *ldp = (int)cc; *plane_stride = ps;
+      return SRW_OK;
+    }
+  }
+  set_last_error("srw_hubert_weight_plane_slot: parameter %d has no per-parameter planes", param_index);
+  return SRW_ERR_ARG;
 }
 
 static int hubert_forward_body(const srw_hubert_fwd_args* a, cudaStream_t s) {

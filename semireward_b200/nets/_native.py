@@ -4,6 +4,8 @@ gradient exchange (one NCCL all-reduce(avg), or overlapped pieces as the backwar
 core/utils/misc.py:42-64)."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .. import _lib as L
@@ -15,7 +17,8 @@ class NativeBackbone:
 
     def _init_native(self):
         self._keep_cache, self._ws_pool, self._bufs = {}, {}, {}
-        self.dp_overlap_split = 4   # data parallel: block ranges of the backward whose gradients are all-reduced while the next range runs (<= 1: off)
+        # data parallel: block ranges of the backward whose gradients are all-reduced while the next range runs (<= 1: off); SRW_DP_SPLIT overrides
+        self.dp_overlap_split = int(os.environ.get("SRW_DP_SPLIT", "4"))
         self._pending_reduce = []
         self._pa = self._pa_key = self._flat_grads = self._grad_views = self._ga = None
 

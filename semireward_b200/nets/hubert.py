@@ -158,6 +158,7 @@ class ClassificationHubert(NativeBackbone, nn.Module):
         self.layerdrop, self.apply_spec_augment = layerdrop, apply_spec_augment
         self.mask_time_prob, self.mask_time_length, self.mask_time_min_masks = mask_time_prob, mask_time_length, mask_time_min_masks
         self._planes = self._planes_key = None
+        self._front_stale = False
         self._init_native()
         self.dropout_seed = 0          # seed of the counter-based dropout streams (call_key)
         self.stochastic_seed = 0       # seed of the host-side LayerDrop / SpecAugment draws
@@ -217,23 +218,34 @@ class ClassificationHubert(NativeBackbone, nn.Module):
     def _weight_planes(self):
         ps = self._ordered_params()
         key = tuple((p.data_ptr(), p._version) for p in ps)
+        lib = L.load()
         if self._planes is None or key != self._planes_key:
-            lib = L.load()
             dev = ps[0].device
             if self._planes is None or self._planes.device != dev:
                 self._planes = torch.empty(lib.srw_hubert_weight_planes_bytes(C.byref(self._cfg)), dtype=torch.uint8, device=dev)
             L.check(lib.srw_hubert_prepare_weights(C.byref(self._cfg), L.ptr_array([p.detach() for p in ps]), self._planes.data_ptr(), L.stream_ptr()),
                     "srw_hubert_prepare_weights")
-            self._planes_key = key
+            self._planes_key, self._front_stale = key, False
+        elif self._front_stale:   # the fused optimizer refreshed the encoder matrices' planes itself; the re-laid-out operands follow here
+            L.check(lib.srw_hubert_prepare_front(C.byref(self._cfg), L.ptr_array([p.detach() for p in ps]), self._planes.data_ptr(), L.stream_ptr()),
+                    "srw_hubert_prepare_front")
+            self._front_stale = False
         return self._planes
 
     def weight_plane_slot(self, idx):
-        """The plane cache holds re-laid-out / weight-normalised operands, not per-parameter copies: the optimizer does not write
-        into it; it is rebuilt by srw_hubert_prepare_weights after every step (~0.4 GB of traffic against a ~100 GFLOP step)."""
+        """(byte offset, cols, ldp, plane stride) of parameter `idx` (engine order) inside the plane cache for the encoder matrices, None
+        for everything whose operand is a re-layout (conv stem, weight-normalised positional taps) or has no planes."""
+        off, cols, ldp, ps_ = L.i64(), L.i32(), L.i32(), L.i64()
+        if L.load().srw_hubert_weight_plane_slot(C.byref(self._cfg), idx, C.byref(off), C.byref(cols), C.byref(ldp), C.byref(ps_)) == 0:
+            return off.value, cols.value, ldp.value, ps_.value
         return None
 
     def mark_weights_updated(self, planes_fresh: bool = False):
-        self._planes_key = None
+        if planes_fresh and self._planes is not None:   # FusedAdamW: parameters and the slotted planes were written by the same kernel
+            self._planes_key = tuple((p.data_ptr(), p._version) for p in self._ordered_params())
+            self._front_stale = True
+        else:
+            self._planes_key = None
 
     def stochastic(self):
         c = self._cfg

@@ -357,3 +357,57 @@ def test_pretrained_loading_follows_the_reference_load_checkpoint(tmp_path):
         for (n, a), (_, b) in zip(ref_dst.state_dict().items(), dst.state_dict().items()):
             if not n.startswith("head"):
                 assert torch.equal(a, b), n
+
+
+def test_wrn_and_hubert_builders_param_groups_and_host_randomness():
+    """Host logic of the two round-2 backbones without a GPU: state_dict contracts, optimizer groups against the oracles' tables, the
+    per-call LayerDrop / SpecAugment bookkeeping of the HuBERT wrapper (what the engine later receives as explicit inputs)."""
+    import numpy as np
+    import semireward_b200 as S
+    from oracle import hubert_oracle as HO, wrn_oracle as WO
+    from semireward_b200.core.optim import FusedAdamW, FusedSGD, get_optimizer
+    # WRN-28-2: 81 parameters + 75 BatchNorm buffers, SGD groups = (no decay: bn + biases | decay), the two dead bn1 excluded from the gradient list
+    wrn = S.get_net_builder("wrn_28_2")(num_classes=100)
+    wc = WO.WRNCfg(num_classes=100)
+    assert [(n, tuple(p.shape)) for n, p in wrn.named_parameters()] == wc.param_shapes() and len(wrn.state_dict()) == 156
+    opt = get_optimizer(wrn, "SGD", 0.03, 0.9, 1e-3, 1.0)
+    assert isinstance(opt, FusedSGD) and opt.param_groups[0]["nesterov"] is True
+    hp = WO.wrn_param_hparams(wc.param_shapes(), 0.03, 1e-3)
+    names = {id(p): n for n, p in wrn.named_parameters()}
+    for g in opt.param_groups:
+        for p in g["params"]:
+            assert (g["lr"], g["weight_decay"]) == hp[names[id(p)]], names[id(p)]
+    assert len(wrn._grad_params()) == 77 and wrn.num_features == 128 and not wrn.stochastic()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        wrn.eval()(torch.zeros(1, 3, 32, 32))
+    # HuBERT: HF key names, AdamW layer-decay groups, frames, per-call draws
+    hub = S.get_net_builder("hubert_base")(num_classes=10, num_hidden_layers=2)
+    hc = HO.HubertCfg(layers=2, num_classes=10)
+    assert list(hub.state_dict()) == [n for n, _ in hc.param_shapes()]
+    opt = get_optimizer(hub, "AdamW", 5e-5, 0.9, 2e-5, 0.75)
+    assert isinstance(opt, FusedAdamW)
+    hp = HO.hubert_param_hparams(hc.param_shapes(), 2, 5e-5, 2e-5, 0.75)
+    names = {id(p): n for n, p in hub.named_parameters()}
+    for g in opt.param_groups:
+        for p in g["params"]:
+            lr, wd = hp[names[id(p)]]
+            assert abs(g["lr"] - lr) < 1e-18 and g["weight_decay"] == wd, names[id(p)]
+    assert hub.frames(64000) == hc.frames(64000) == 199 and hub.frames(8000) == 24
+    hub.train()
+    assert hub.stochastic()
+    first = hub.draw_streams(2, 3, 4, "cpu")                      # two passes = six model calls
+    assert first == 0 and hub._calls == 6 and sorted(hub._call_draws) == list(range(6))
+    spec = hub.streams_for(first, [(0, "lb"), (1, "s"), (0, "w")], 3, 4, "cpu")
+    assert spec["segments"].tolist() == [0, 3, 7, 11] and spec["skip"].shape == (3, 2) and spec["keys"].shape == (11,)
+    assert spec["rows"].tolist() == [0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3]
+    assert len(set(spec["keys"].tolist())) == 3                   # one dropout stream per model call
+    assert sorted(hub._call_draws) == [1, 3, 5]                   # the draws of the three calls of this launch were consumed
+    m = hub._mask_time(spec, 199)
+    assert m.shape == (11, 199) and m.dtype == torch.uint8
+    per_clip = m.sum(1)
+    assert int(per_clip.min()) >= 10 and int(per_clip.max()) <= 20   # >= 2 spans of 10 frames each (mask_time_min_masks), overlaps merge
+    assert torch.equal(m, hub._mask_time(spec, 199))              # drawn from the call's own seed: reproducible for the backward
+    hub.set_call_draws(7, layer_skip=[1, 0], mask_time=np.zeros((4, 199), dtype=bool))
+    assert hub._call_draws[7][0].tolist() == [1, 0]
+    hub.eval()
+    assert not hub.stochastic()
