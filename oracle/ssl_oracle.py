@@ -24,7 +24,7 @@ What is restated (fp32, torch CPU, functional style — no nn.Module of the refe
 
 Parity pin: the reference ships NO tests or golden vectors, so this oracle is pinned against
 outputs of the live reference itself, run in the build container by tests/golden/make_golden.py (fixtures in
-tests/golden/*.npz) and re-checked live by tests/test_oracle_vs_reference.py whenever /root/reference is mounted.
+tests/golden/*.npz) and re-checked live by tests/test_oracle_golden.py (test_oracle_matches_live_reference) whenever /root/reference is mounted.
 Gradients come from torch autograd over this functional forward (autograd is the CPU differentiation engine of
 the reference as well).
 """
@@ -352,7 +352,7 @@ def cosine_lr_factor(step: int, num_training_steps: int, num_warmup_steps: int =
 def vit_layer_id(name: str, depth: int) -> int:
     """layer id of the reference's group_matcher + param_groups_layer_decay (vit.py:311-320, nets/utils.py:143-204):
     stem (cls_token,pos_embed,patch_embed) -> 0, blocks.i -> i+1, final norm joins the last block's group, head -> depth+1.
-    Verified against the live reference's optimizer.param_groups (tests/test_oracle_vs_reference.py)."""
+    Verified against the live reference's optimizer.param_groups (tests/test_oracle_golden.py (test_oracle_matches_live_reference))."""
     if name.startswith(("cls_token", "pos_embed", "patch_embed")):
         return 0
     if name.startswith("blocks."):
