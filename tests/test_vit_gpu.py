@@ -182,3 +182,55 @@ def test_split_backward_equals_full_backward():
     model._dp_group = None
     assert all(torch.equal(results[0], r) for r in results[1:])
     assert len(calls) == 3 * (2 + 3 + 4) and sum(calls[:2]) == results[0].numel()
+
+
+def test_vit_pretrained_scale_statistics():
+    """the 1e-3 logit gate had only seen hash-filled weights (|logit| <= 24).  Pre-trained ViTs have heavier statistics:
+    LayerNorm gains far from 1, a few outlier channels in the residual stream, wider MLP weights, logits of several tens.  The same
+    engine on weights reshaped that way (12 blocks): the gate stays 1e-3 ABSOLUTE on logits whose magnitude is printed, features 1e-3,
+    gradients 1e-3 relative."""
+    from oracle import ssl_oracle as O
+    from semireward_b200 import detgen
+    from semireward_b200.nets import vit_small_patch2_32
+    vc = O.ViTConfig(depth=12, num_classes=100)
+    g = torch.Generator().manual_seed(17)
+    p = {}
+    for n, s in vc.param_shapes():
+        t = torch.from_numpy(detgen.fill_param(n, s, 0))
+        if n.endswith(("norm1.weight", "norm2.weight")) or n == "norm.weight":
+            t = t * (0.5 + 2.5 * torch.rand(t.shape, generator=g))            # gains in [0.5, 3]
+            t[torch.randint(0, t.numel(), (3,), generator=g)] *= 4.0             # a few outlier channels (x 4)
+        elif n.endswith(("fc1.weight", "fc2.weight", "qkv.weight")):
+            t = t * 1.6
+        elif n == "pos_embed":
+            t = t * 10.0
+        elif n == "head.weight":
+            t = t * 3.5
+        p[n] = t
+    model = vit_small_patch2_32(num_classes=100, depth=12, drop_path_rate=0.0)
+    model.load_state_dict(p)
+    model = model.cuda().train()
+    batch = detgen.ssl_batch(8, 1, 100, 50000, seed=1, step=0)
+    x = torch.from_numpy(np.concatenate([batch["x_lb"], batch["x_ulb_s"], batch["x_ulb_w"]]))
+    B, Bg = x.shape[0], 16
+    out = model(x.cuda(), grad_batch=Bg)
+    po = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    lo, fo = O.vit_forward(po, x, vc, None)
+    err_l = (out["logits"].cpu() - lo.detach()).abs().max().item()
+    err_f = (out["feat"].cpu() - fo.detach()).abs().max().item()
+    print(f"pretrained-scale statistics: max |logit| {lo.abs().max().item():.1f}, max |feat| {fo.abs().max().item():.1f}: logits err {err_l:.3e}, feat err {err_f:.3e}")
+    assert lo.abs().max().item() > 40.0, "the fixture is meant to produce large logits"
+    assert err_l < 1e-3 and err_f < 1e-3
+    gen = torch.Generator().manual_seed(7)
+    cl = torch.randn(B, 100, generator=gen)
+    cl[Bg:] = 0
+    (out["logits"] * cl.cuda()).sum().backward()
+    (lo * cl).sum().backward()
+    worst, wn = 0.0, ""
+    for name, prm in model.named_parameters():
+        ref = po[name].grad
+        rel = (prm.grad.cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-12)
+        if rel > worst:
+            worst, wn = rel, name
+    print(f"   worst relative gradient error {worst:.3e} ({wn})")
+    assert worst < 1e-3, (worst, wn)
