@@ -152,7 +152,8 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
 // the TMEM load and the transpose, which hides their L2 latency (the epilogues are latency- and issue-bound, not
 // bandwidth-bound: 12 warps, 3 per scheduler).
 template <int BN, int EPI, bool ACTDROP>
-__device__ __forceinline__ void drain_full(const EpiParams& ep, uint32_t acc_addr, float* st, int q, int part, int lane, int m0, int n0, int split) {
+__device__ __forceinline__ void drain_full(const EpiParams& ep, uint32_t acc_addr, float* st, int q, int part, int lane, int m0, int n0, int split,
+                                           int nchunks = BN / 32) {
   const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
   const int row_first = m0 + q * 32 + sub_r;       // this lane's rows: row_first + 4 i
   float scale[8];
@@ -173,7 +174,7 @@ __device__ __forceinline__ void drain_full(const EpiParams& ep, uint32_t acc_add
     }
   }
 #pragma unroll 1
-  for (int c = part; c < BN / 32; c += EPI_WARPS / 4) {
+  for (int c = part; c < nchunks; c += EPI_WARPS / 4) {
     const int col = n0 + c * 32 + sub_c;
     float4 pre[8];
     if (EPI == SRW_EPI_RESID) {
@@ -244,14 +245,18 @@ __device__ __forceinline__ void drain_full(const EpiParams& ep, uint32_t acc_add
 template <int BN, bool ACTDROP>
 __device__ __forceinline__ void drain_accumulator(const EpiParams& ep, uint32_t acc_addr, float* st, int q, int part, int lane, int m0, int n0,
                                                   int split, bool has_k) {
-  if (has_k && m0 + BM <= ep.M && n0 + BN <= ep.N) {
+  // full rows and a whole number of 32-column chunks (the last N tile of a narrow output, e.g. the 32- and 128-channel convolutions
+  // of srw_wrn.cu under a 64- / 192-wide tile, takes the straight-line path over the chunks it has)
+  const int ncols = min(BN, ep.N - n0);
+  if (has_k && m0 + BM <= ep.M && (ncols & 31) == 0) {
+    const int nch = ncols >> 5;
     switch (ep.epilogue) {
-      case SRW_EPI_F32: drain_full<BN, SRW_EPI_F32, false>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
-      case SRW_EPI_PLANES: drain_full<BN, SRW_EPI_PLANES, false>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
-      case SRW_EPI_GELU: drain_full<BN, SRW_EPI_GELU, ACTDROP>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
-      case SRW_EPI_RESID: drain_full<BN, SRW_EPI_RESID, false>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
-      case SRW_EPI_DGELU: drain_full<BN, SRW_EPI_DGELU, ACTDROP>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
-      default: drain_full<BN, SRW_EPI_SPLITK, false>(ep, acc_addr, st, q, part, lane, m0, n0, split); return;
+      case SRW_EPI_F32: drain_full<BN, SRW_EPI_F32, false>(ep, acc_addr, st, q, part, lane, m0, n0, split, nch); return;
+      case SRW_EPI_PLANES: drain_full<BN, SRW_EPI_PLANES, false>(ep, acc_addr, st, q, part, lane, m0, n0, split, nch); return;
+      case SRW_EPI_GELU: drain_full<BN, SRW_EPI_GELU, ACTDROP>(ep, acc_addr, st, q, part, lane, m0, n0, split, nch); return;
+      case SRW_EPI_RESID: drain_full<BN, SRW_EPI_RESID, false>(ep, acc_addr, st, q, part, lane, m0, n0, split, nch); return;
+      case SRW_EPI_DGELU: drain_full<BN, SRW_EPI_DGELU, ACTDROP>(ep, acc_addr, st, q, part, lane, m0, n0, split, nch); return;
+      default: drain_full<BN, SRW_EPI_SPLITK, false>(ep, acc_addr, st, q, part, lane, m0, n0, split, nch); return;
     }
   }
   // edge tiles (partial in M or N) and empty K ranges: generic bounds-checked path

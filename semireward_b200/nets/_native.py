@@ -25,7 +25,13 @@ class NativeBackbone:
     # -- workspace pool / persistent buffers ------------------------------------------------------
     def _acquire_ws(self, wbytes, device):
         pool = self._ws_pool.setdefault((wbytes, str(device)), [])
-        return pool.pop() if pool else torch.empty(wbytes, dtype=torch.uint8, device=device)
+        if pool:
+            return pool.pop()
+        # the engines want 1024-byte alignment (SWIZZLE_128B operand tiles inside the workspace); torch's caching allocator only
+        # promises 512 for small blocks, so over-allocate and hand out an aligned view (the view keeps the storage alive)
+        raw = torch.empty(wbytes + 1024, dtype=torch.uint8, device=device)
+        off = (-raw.data_ptr()) % 1024
+        return raw[off:off + wbytes]
 
     def _release_ws(self, ws):
         if ws is not None:
