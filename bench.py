@@ -393,8 +393,6 @@ SETUP_STEPS = 12
 
 
 def main_native(a):
-    if a.config == 1 and int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        raise SystemExit("bench.py --config 1: the WRN path is single-GPU (SyncBatchNorm is not built); BASELINE configs[0] is the single-device case")
     import torch
     import torch.distributed as dist
     import semireward_b200 as S

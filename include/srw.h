@@ -443,6 +443,14 @@ int64_t srw_wrn_weight_planes_bytes(const srw_wrn_config* c);
 int64_t srw_wrn_workspace_bytes(const srw_wrn_config* c, int batch);
 int srw_wrn_prepare_weights(const srw_wrn_config* c, const float* const* params, void* weight_planes, void* stream);
 
+/* Data parallel = SyncBatchNorm (core/utils/misc.py:54 converts every BatchNorm2d under DDP): the batch statistics of a layer are sums over
+ * the rows of ALL ranks.  The engine folds its per-CTA partials into `sync_buf` (device, >= 2 * 64 * widen floats: per-channel sum and sum of
+ * squares; in the backward sum(du) and sum(du * xhat)), calls `sync_fn(sync_ctx, pointer into sync_buf, count)` on the host thread — the
+ * caller all-reduces (SUM) that range on the same stream (torch.distributed / NCCL) — and continues with the global sums and
+ * world_size * rows as the count.  dgamma / dbeta stay LOCAL sums (averaged later with the other gradients, as DDP does).  With
+ * sync_fn == NULL nothing changes.  Calls with a sync_fn run eagerly (no CUDA-graph replay: the collective is host-enqueued). */
+typedef int (*srw_allreduce_sum_fn)(void* ctx, float* device_buf, int count);
+
 typedef struct {
   const srw_wrn_config* cfg;
   const float* const* params;
@@ -457,6 +465,7 @@ typedef struct {
   float* logits; float* feat;                  /* [batch, num_classes], [batch, 64 * widen] */
   void* workspace; int64_t workspace_bytes;
   int gemm_impl;
+  srw_allreduce_sum_fn sync_fn; void* sync_ctx; float* sync_buf; int world_size;   /* SyncBatchNorm (see above); NULL / 0 = single rank */
 } srw_wrn_fwd_args;
 int srw_wrn_forward(const srw_wrn_fwd_args* a, void* stream);
 
@@ -472,6 +481,7 @@ typedef struct {
   int accumulate_grads;
   void* workspace; int64_t workspace_bytes;    /* the forward's workspace */
   int gemm_impl;
+  srw_allreduce_sum_fn sync_fn; void* sync_ctx; float* sync_buf; int world_size;
 } srw_wrn_bwd_args;
 int srw_wrn_backward(const srw_wrn_bwd_args* a, void* stream);
 

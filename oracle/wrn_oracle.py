@@ -191,7 +191,9 @@ class WRNSSLOracle(O.SSLOracle):
 
     def _backbone(self, x_lb, x_ulb_w, x_ulb_s):
         nb = x_lb.shape[0]
-        logits, feat = wrn_forward(self.p, self.buf, torch.cat((x_lb, x_ulb_w, x_ulb_s)), self.wrn_cfg, training=True)
+        # data parallel: send_model_cuda converts the BatchNorms to SyncBatchNorm (misc.py:54) -> statistics over every rank's rows
+        logits, feat = wrn_forward(self.p, self.buf, torch.cat((x_lb, x_ulb_w, x_ulb_s)), self.wrn_cfg, training=True,
+                                   sync_group=getattr(self, "dp_group", None))
         lw, ls = logits[nb:].chunk(2)
         fw, fs = feat[nb:].chunk(2)
         return logits[:nb], lw, ls, feat[:nb], fw, fs
@@ -200,6 +202,8 @@ class WRNSSLOracle(O.SSLOracle):
         names = list(self.p.keys())
         gs = torch.autograd.grad(self.loss, [self.p[k] for k in names], allow_unused=True)
         grads = {k: g for k, g in zip(names, gs)}
+        if getattr(self, "dp_group", None) is not None:   # DDP: average over the ranks (unused parameters stay without a gradient)
+            grads = {k: (None if g is None else self._dp_mean(g)) for k, g in grads.items()}
         f = O.cosine_lr_factor(self.sched_step, self.cfg.num_train_iter, self.cfg.num_warmup_iter)
         self.sgd.step(self.p, grads, {k: (self.hp[k][0] * f, self.hp[k][1]) for k in names})
         self.sched_step += 1

@@ -149,12 +149,17 @@ class WrnConfig(C.Structure):
 class WrnFwdArgs(C.Structure):
     _fields_ = [("cfg", C.POINTER(WrnConfig)), ("params", C.POINTER(vp)), ("bn_running_mean", C.POINTER(vp)), ("bn_running_var", C.POINTER(vp)),
                 ("bn_num_batches_tracked", C.POINTER(vp)), ("weight_planes", vp), ("x", vp), ("batch", i32), ("training", i32), ("stat_repeats", i32),
-                ("logits", vp), ("feat", vp), ("workspace", vp), ("workspace_bytes", i64), ("gemm_impl", i32)]
+                ("logits", vp), ("feat", vp), ("workspace", vp), ("workspace_bytes", i64), ("gemm_impl", i32),
+                ("sync_fn", vp), ("sync_ctx", vp), ("sync_buf", vp), ("world_size", i32)]
 
 
 class WrnBwdArgs(C.Structure):
     _fields_ = [("cfg", C.POINTER(WrnConfig)), ("params", C.POINTER(vp)), ("weight_planes", vp), ("batch", i32), ("grad_rows", i32), ("dlogits", vp),
-                ("dfeat", vp), ("grads", C.POINTER(vp)), ("accumulate_grads", i32), ("workspace", vp), ("workspace_bytes", i64), ("gemm_impl", i32)]
+                ("dfeat", vp), ("grads", C.POINTER(vp)), ("accumulate_grads", i32), ("workspace", vp), ("workspace_bytes", i64), ("gemm_impl", i32),
+                ("sync_fn", vp), ("sync_ctx", vp), ("sync_buf", vp), ("world_size", i32)]
+
+
+ALLREDUCE_SUM_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)   # srw_allreduce_sum_fn
 
 
 class RewarderFwdArgs(C.Structure):

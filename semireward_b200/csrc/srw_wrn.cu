@@ -132,9 +132,21 @@ __device__ __forceinline__ void bn_fold_partials(const float* __restrict__ parti
   for (int p = lane; p < nparts; p += 32) { a += partial[(int64_t)p * 2 * C + c]; b += partial[(int64_t)p * 2 * C + C + c]; }
   s = warp_sum_f64(a); q = warp_sum_f64(b);
 }
+// SyncBatchNorm: sums[c] = sum, sums[C + c] = sum of squares of THIS rank (all-reduced by the host before the finish kernel reads them);
+// backward form: also the LOCAL dgamma / dbeta
+__global__ void wrn_bn_fold_kernel(const float* __restrict__ partial, int nparts, int C, float* __restrict__ sums, float* __restrict__ dgamma,
+                                   float* __restrict__ dbeta, int accumulate) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double s, q;
+  bn_fold_partials(partial, nparts, C, c, s, q);
+  if ((threadIdx.x & 31) != 0) return;
+  sums[c] = (float)s; sums[C + c] = (float)q;
+  if (dgamma) { dgamma[c] = accumulate ? dgamma[c] + (float)q : (float)q; dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s; }
+}
 __global__ void wrn_bn_finish_kernel(const float* __restrict__ partial, int nparts, int C, double n, float eps, float momentum, int training, int repeats,
                                      float* __restrict__ running_mean, float* __restrict__ running_var, int64_t* __restrict__ num_batches_tracked,
-                                     float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                                     float* __restrict__ mean_out, float* __restrict__ rstd_out, const float* __restrict__ sums) {
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   const bool lead = (threadIdx.x & 31) == 0;
@@ -146,7 +158,8 @@ __global__ void wrn_bn_finish_kernel(const float* __restrict__ partial, int npar
     return;
   }
   double s, q;
-  bn_fold_partials(partial, nparts, C, c, s, q);
+  if (sums) { s = sums[c]; q = sums[C + c]; }        // global sums (SyncBatchNorm)
+  else bn_fold_partials(partial, nparts, C, c, s, q);
   if (!lead) return;
   const double m = s / n;
   const double var = fmax(q / n - m * m, 0.0);
@@ -164,11 +177,12 @@ __global__ void wrn_bn_finish_kernel(const float* __restrict__ partial, int npar
 }
 // backward finish: dgamma (+)= sum du xhat, dbeta (+)= sum du; coef = (sum du / n, sum du xhat / n)
 __global__ void wrn_bn_bwd_finish_kernel(const float* __restrict__ partial, int nparts, int C, double n, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                         int accumulate, float* __restrict__ coef) {
+                                         int accumulate, float* __restrict__ coef, const float* __restrict__ sums) {
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   double s, q;
-  bn_fold_partials(partial, nparts, C, c, s, q);
+  if (sums) { s = sums[c]; q = sums[C + c]; }
+  else bn_fold_partials(partial, nparts, C, c, s, q);
   if ((threadIdx.x & 31) != 0) return;
   if (dgamma) { dgamma[c] = accumulate ? dgamma[c] + (float)q : (float)q; dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s; }
   coef[c] = (float)(s / n); coef[C + c] = (float)(q / n);
@@ -560,6 +574,7 @@ static WLayout make_wlayout(const WDims& d) {
 // ---- host helpers -------------------------------------------------------------------------------
 struct Ctx {
   const WDims& d; uint8_t* ws; const uint8_t* wp; int impl; cudaStream_t s;
+  srw_allreduce_sum_fn sync_fn; void* sync_ctx; float* sync_buf; int world;
   float* F32(int64_t off) const { return reinterpret_cast<float*>(ws + off); }
   __nv_bfloat16* BF(int64_t off) const { return reinterpret_cast<__nv_bfloat16*>(ws + off); }
 };
@@ -614,8 +629,17 @@ static int bn_stats(const Ctx& k, const float* x, int st, int C, float eps, int 
     g_launches++;
     SRW_LAUNCH_CHECK();
   }
-  const double n = (double)k.d.N * k.d.geo[st].Hs * k.d.geo[st].Hs;
-  wrn_bn_finish_kernel<<<cdiv(C, 8), 256, 0, k.s>>>(partial, nparts, C, n, eps, k.d.momentum, training, repeats, rm, rv, nbt, mean, rstd);
+  double n = (double)k.d.N * k.d.geo[st].Hs * k.d.geo[st].Hs;
+  const float* sums = nullptr;
+  if (training && k.sync_fn) {   // SyncBatchNorm: local sums -> all-reduce over the ranks (host-enqueued on this stream) -> global statistics
+    wrn_bn_fold_kernel<<<cdiv(C, 8), 256, 0, k.s>>>(partial, nparts, C, k.sync_buf, nullptr, nullptr, 0);
+    g_launches++;
+    SRW_LAUNCH_CHECK();
+    SRW_REQUIRE(k.sync_fn(k.sync_ctx, k.sync_buf, 2 * C) == 0, "srw_wrn: the SyncBatchNorm all-reduce callback failed");
+    sums = k.sync_buf;
+    n *= k.world;
+  }
+  wrn_bn_finish_kernel<<<cdiv(C, 8), 256, 0, k.s>>>(partial, nparts, C, n, eps, k.d.momentum, training, repeats, rm, rv, nbt, mean, rstd, sums);
   g_launches++;
   SRW_LAUNCH_CHECK();
   return SRW_OK;
@@ -637,8 +661,17 @@ static int bn_backward(const Ctx& k, const float* dy, const float* x, int st, in
   wrn_bn_partial_kernel<1><<<nparts, 256, 0, k.s>>>(x, dy, M, C, k.d.geo[st], mean, rstd, gamma, beta, k.d.slope, partial);
   g_launches++;
   SRW_LAUNCH_CHECK();
-  const double n = (double)k.d.N * k.d.geo[st].Hs * k.d.geo[st].Hs;
-  wrn_bn_bwd_finish_kernel<<<cdiv(C, 8), 256, 0, k.s>>>(partial, nparts, C, n, dgamma, dbeta, acc, coef);
+  double n = (double)k.d.N * k.d.geo[st].Hs * k.d.geo[st].Hs;
+  if (k.sync_fn) {   // dgamma / dbeta from the LOCAL sums (DDP averages them with the other gradients), dx from the global ones
+    wrn_bn_fold_kernel<<<cdiv(C, 8), 256, 0, k.s>>>(partial, nparts, C, k.sync_buf, dgamma, dbeta, acc);
+    g_launches++;
+    SRW_LAUNCH_CHECK();
+    SRW_REQUIRE(k.sync_fn(k.sync_ctx, k.sync_buf, 2 * C) == 0, "srw_wrn: the SyncBatchNorm all-reduce callback failed");
+    n *= k.world;
+    wrn_bn_bwd_finish_kernel<<<cdiv(C, 8), 256, 0, k.s>>>(partial, nparts, C, n, nullptr, nullptr, 0, coef, k.sync_buf);
+  } else {
+    wrn_bn_bwd_finish_kernel<<<cdiv(C, 8), 256, 0, k.s>>>(partial, nparts, C, n, dgamma, dbeta, acc, coef, nullptr);
+  }
   g_launches++;
   SRW_LAUNCH_CHECK();
   if (planes_off >= 0) SRW_TRY(zero_slack(k, planes_off, st, C));
@@ -717,7 +750,9 @@ static int wrn_forward_body(const srw_wrn_fwd_args* a, cudaStream_t s) {
   SRW_REQUIRE(a->stat_repeats >= 0, "srw_wrn_forward: stat_repeats < 0");
   const WWOff w = wrn_weight_layout(d);
   const WIdx ix = make_widx(d);
-  const Ctx k = {d, reinterpret_cast<uint8_t*>(a->workspace), reinterpret_cast<const uint8_t*>(a->weight_planes), a->gemm_impl, s};
+  SRW_REQUIRE(!a->sync_fn || (a->sync_buf && a->world_size >= 1), "srw_wrn_forward: sync_fn needs sync_buf and world_size");
+  const Ctx k = {d, reinterpret_cast<uint8_t*>(a->workspace), reinterpret_cast<const uint8_t*>(a->weight_planes), a->gemm_impl, s,
+                 a->sync_fn, a->sync_ctx, a->sync_buf, a->world_size};
   const float* const* P = a->params;
   const int tr = a->training ? 1 : 0, rep = a->stat_repeats;
   auto NBT = [&](int i) { return a->bn_num_batches_tracked ? a->bn_num_batches_tracked[i] : nullptr; };
@@ -800,7 +835,9 @@ static int wrn_backward_body(const srw_wrn_bwd_args* a, cudaStream_t s) {
   SRW_REQUIRE(a->workspace_bytes >= L.total, "srw_wrn_backward: workspace too small");
   const WWOff w = wrn_weight_layout(d);
   const WIdx ix = make_widx(d);
-  const Ctx k = {d, reinterpret_cast<uint8_t*>(a->workspace), reinterpret_cast<const uint8_t*>(a->weight_planes), a->gemm_impl, s};
+  SRW_REQUIRE(!a->sync_fn || (a->sync_buf && a->world_size >= 1), "srw_wrn_backward: sync_fn needs sync_buf and world_size");
+  const Ctx k = {d, reinterpret_cast<uint8_t*>(a->workspace), reinterpret_cast<const uint8_t*>(a->weight_planes), a->gemm_impl, s,
+                 a->sync_fn, a->sync_ctx, a->sync_buf, a->world_size};
   const float* const* P = a->params;
   float* const* G = a->grads;
   const int acc = a->accumulate_grads ? 1 : 0;
@@ -891,7 +928,7 @@ static int wrn_backward_body(const srw_wrn_bwd_args* a, cudaStream_t s) {
     wrn_bn_partial_kernel<0><<<nparts, 256, 0, s>>>(dout, nullptr, d.M[0], 16, d.geo[0], nullptr, nullptr, nullptr, nullptr, 0.f, partial);
     g_launches++;
     SRW_LAUNCH_CHECK();
-    wrn_bn_bwd_finish_kernel<<<2, 256, 0, s>>>(partial, nparts, 16, 1.0, nullptr, nullptr, 0, coef);   // coef[0 .. 15] = column sums (n = 1)
+    wrn_bn_bwd_finish_kernel<<<2, 256, 0, s>>>(partial, nparts, 16, 1.0, nullptr, nullptr, 0, coef, nullptr);   // coef[0 .. 15] = column sums (n = 1)
     g_launches++;
     SRW_LAUNCH_CHECK();
     if (acc) {
@@ -908,7 +945,7 @@ static int wrn_backward_body(const srw_wrn_bwd_args* a, cudaStream_t s) {
 extern "C" int srw_wrn_forward(const srw_wrn_fwd_args* a, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   SRW_REQUIRE(a && a->cfg && a->params, "srw_wrn_forward: null pointer");
-  if (!graphs_enabled(s)) return wrn_forward_body(a, s);
+  if (!graphs_enabled(s) || a->sync_fn) return wrn_forward_body(a, s);
   const int np = srw_wrn_num_params(a->cfg);
   SRW_REQUIRE(np > 0, "srw_wrn_forward: bad config");
   const int nbn = 2 * ((a->cfg->depth - 4) / 6) * 3 + 1;
@@ -924,7 +961,7 @@ extern "C" int srw_wrn_forward(const srw_wrn_fwd_args* a, void* stream_) {
 extern "C" int srw_wrn_backward(const srw_wrn_bwd_args* a, void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   SRW_REQUIRE(a && a->cfg && a->params && a->grads, "srw_wrn_backward: null pointer");
-  if (!graphs_enabled(s)) return wrn_backward_body(a, s);
+  if (!graphs_enabled(s) || a->sync_fn) return wrn_backward_body(a, s);
   const int np = srw_wrn_num_params(a->cfg);
   SRW_REQUIRE(np > 0, "srw_wrn_backward: bad config");
   KeyBuilder kb;

@@ -10,8 +10,10 @@ parameter and buffer holders and are never called.  There is no PyTorch fallback
 
 BatchNorm couples the rows of a launch, so (unlike the LayerNorm backbones) the K sampling passes of stage 2 cannot be merged into one
 forward; but the network has no dropout (dropRate 0 in every config), so those passes recompute the identical tensors and only advance
-the running statistics — `stat_repeats` of srw_wrn_forward does exactly that (include/srw.h).  Data parallel (SyncBatchNorm,
-core/utils/misc.py:54) is not built: BASELINE configs[0] is the single-device configuration."""
+the running statistics — `stat_repeats` of srw_wrn_forward does exactly that (include/srw.h).  Data parallel = SyncBatchNorm
+(core/utils/misc.py:54 converts every BatchNorm2d under DDP): when the module carries a data-parallel group (send_model_cuda), the engine
+hands every layer's per-channel sums to `_sync_sums`, which all-reduces them over the group on the current stream; those calls run
+eagerly (a host-enqueued collective between kernels cannot be replayed from a CUDA graph)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -159,8 +161,6 @@ class WideResNet(NativeBackbone, nn.Module):
         (train: batch statistics of ALL rows of x + running-statistics update)."""
         if not x.is_cuda:
             raise RuntimeError("semireward_b200 WideResNet runs on CUDA (sm_100a) only; there is no CPU path")
-        if getattr(self, "_dp_group", None) is not None:
-            raise NotImplementedError("native WideResNet: data parallel needs SyncBatchNorm (core/utils/misc.py:54), which is not built")
         lib, cfg, dev = L.load(), self._cfg, x.device
         S = x.shape[0]
         if tuple(x.shape[1:]) != (3, cfg.img_size, cfg.img_size):
@@ -174,11 +174,12 @@ class WideResNet(NativeBackbone, nn.Module):
         ws = self._acquire_ws(wbytes, dev)
         lo, fe = self._buf("logits", (S, cfg.num_classes), dev), self._buf("feat", (S, self.channels), dev)
         rep, self.stat_repeats_next = (int(self.stat_repeats_next) if self.training else 0), 0
+        sync = self._sync_args(dev) if self.training else {}
         a = L.WrnFwdArgs(cfg=C.pointer(cfg), params=pa, bn_running_mean=rm, bn_running_var=rv, bn_num_batches_tracked=nbt,
                          weight_planes=self._weight_planes().data_ptr(), x=x.data_ptr(), batch=S, training=int(self.training), stat_repeats=rep,
-                         logits=lo.data_ptr(), feat=fe.data_ptr(), workspace=ws.data_ptr(), workspace_bytes=wbytes, gemm_impl=self.gemm_impl)
+                         logits=lo.data_ptr(), feat=fe.data_ptr(), workspace=ws.data_ptr(), workspace_bytes=wbytes, gemm_impl=self.gemm_impl, **sync)
         L.check(lib.srw_wrn_forward(C.byref(a), L.stream_ptr()), "srw_wrn_forward")
-        handle = dict(ws=ws, wbytes=wbytes, x=x, B=S, grad_batch=grad_batch)
+        handle = dict(ws=ws, wbytes=wbytes, x=x, B=S, grad_batch=grad_batch, sync=sync)
         if grad_batch == 0:
             self.release_pass(handle)
         return lo.clone(), fe.clone(), handle
@@ -186,8 +187,30 @@ class WideResNet(NativeBackbone, nn.Module):
     def dlogits_buffer(self, grad_batch, device):
         return self._buf("dlogits", (grad_batch, self._cfg.num_classes), device)
 
-    def _ensure_flat_grads(self, dev):
-        super()._ensure_flat_grads(dev)
+    # -- SyncBatchNorm ------------------------------------------------------------------------------
+    def _sync_args(self, dev):
+        """Arguments that switch the engine's BatchNorms to statistics over all ranks of the data-parallel group, or {} (single rank)."""
+        group = getattr(self, "_dp_group", None)
+        if group is None:
+            return {}
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        if world == 1:
+            return {}
+        if getattr(self, "_sync_cb", None) is None or self._sync_group is not group:
+            buf = self._buf("syncbn_sums", (2 * self.channels,), dev)
+
+            def _sync_sums(ctx, ptr, count):   # called by the engine on this thread, between two kernels of the current stream
+                try:
+                    off = (int(ptr) - buf.data_ptr()) // 4
+                    dist.all_reduce(buf[off:off + count], op=dist.ReduceOp.SUM, group=group)
+                    return 0
+                except Exception:   # noqa: BLE001 — an exception must not unwind through the C frame
+                    import traceback
+                    traceback.print_exc()
+                    return -1
+            self._sync_cb, self._sync_buf, self._sync_group = L.ALLREDUCE_SUM_FN(_sync_sums), buf, group
+        return dict(sync_fn=C.cast(self._sync_cb, C.c_void_p), sync_ctx=None, sync_buf=self._sync_buf.data_ptr(), world_size=world)
 
     @torch.no_grad()
     def backward_native(self, handle, dlogits, dfeat=None, accumulate=False, final=True):
@@ -204,7 +227,7 @@ class WideResNet(NativeBackbone, nn.Module):
             df.copy_(dfeat)
         a = L.WrnBwdArgs(cfg=C.pointer(cfg), params=pa, weight_planes=self._weight_planes().data_ptr(), batch=handle["B"], grad_rows=Sg, dlogits=dl.data_ptr(),
                          dfeat=L.ptr(df), grads=self._ga, accumulate_grads=int(bool(accumulate)), workspace=handle["ws"].data_ptr(),
-                         workspace_bytes=handle["wbytes"], gemm_impl=self.gemm_impl)
+                         workspace_bytes=handle["wbytes"], gemm_impl=self.gemm_impl, **handle["sync"])
         L.check(lib.srw_wrn_backward(C.byref(a), L.stream_ptr()), "srw_wrn_backward")
         self._pending_reduce = []
         self.release_pass(handle)

@@ -203,10 +203,6 @@ def test_bench_reference_arm_prints_the_contract_line():
     if not torch.cuda.is_available():
         r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", "5", "--steps", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT)
         assert r.returncode != 0 and not [ln for ln in r.stdout.split("\n") if ln.startswith("{")], r.stdout[-500:]
-    # ... and it refuses what is not built (data-parallel WRN needs SyncBatchNorm) instead of running something else
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", "1"], capture_output=True, text=True, timeout=120, cwd=ROOT,
-                       env=dict(os.environ, WORLD_SIZE="2", RANK="0", LOCAL_RANK="0"))
-    assert r.returncode != 0 and "single-GPU" in (r.stderr + r.stdout)
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/semilearn"), reason="live reference only exists in the build container")
