@@ -686,6 +686,46 @@ typedef struct { const float* param; float* shadow; int64_t numel; int64_t first
 typedef struct { int num_tensors; int64_t total_blocks; const srw_ema_row* table; double decay; } srw_ema_args;
 int srw_ema_step(const srw_ema_args* a, void* stream);
 
+/* ---- image input pipeline: transform_weak / transform_strong on the device ------------------------- */
+/* Replaces, per sample, BasicDataset.__getitem__'s PIL pipelines (semilearn/datasets/cv_datasets/datasetbase.py:85-115) built by
+ * get_cifar (semilearn/datasets/cv_datasets/cifar.py:34-49): Resize (identity at the source size) -> RandomCrop(size, padding,
+ * 'reflect') -> RandomHorizontalFlip -> [RandAugment(3, 5): up to 3 ops of augment_list() + Cutout,
+ * semilearn/datasets/augmentation/randaugment.py:16-206] -> ToTensor -> Normalize.  The uint8 dataset stays resident in HBM; the
+ * host sends the random DECISIONS (drawn from the generators the reference draws from, semireward_b200/datasets/gpu_augment.py);
+ * one CTA per sample writes the normalised fp32 CHW image.  Results are bit-identical to Pillow 12.2 / torchvision 0.26.
+ * Op ids are the positions in augment_list() (randaugment.py:157-174). */
+enum srw_aug_op {
+  SRW_AUG_AUTOCONTRAST = 0, SRW_AUG_BRIGHTNESS = 1, SRW_AUG_COLOR = 2, SRW_AUG_CONTRAST = 3, SRW_AUG_EQUALIZE = 4, SRW_AUG_IDENTITY = 5,
+  SRW_AUG_POSTERIZE = 6, SRW_AUG_ROTATE = 7, SRW_AUG_SHARPNESS = 8, SRW_AUG_SHEAR_X = 9, SRW_AUG_SHEAR_Y = 10, SRW_AUG_SOLARIZE = 11,
+  SRW_AUG_TRANSLATE_X = 12, SRW_AUG_TRANSLATE_Y = 13
+};
+typedef struct {
+  int32_t op;         /* enum srw_aug_op */
+  int32_t ival;       /* Posterize: bits kept (1..8); Solarize: first inverted level = ceil(threshold) */
+  float alpha;        /* Brightness / Color / Contrast / Sharpness: Image.blend factor as a C float */
+  int32_t identity;   /* affine ops: 1 = Image.rotate's `angle % 360 == 0` copy, nothing to do */
+  double a[6];        /* Rotate / Shear / Translate: inverse-map coefficients exactly as Pillow's Python layer computes them */
+} srw_aug_op_desc;
+typedef struct {
+  int64_t src_index;               /* image of the resident dataset */
+  int32_t crop_top, crop_left;     /* RandomCrop.get_params inside the padded image: 0 .. 2 * padding */
+  int32_t flip;
+  int32_t n_ops;                   /* 0 = transform_weak */
+  srw_aug_op_desc ops[3];
+  int32_t cut_x0, cut_y0, cut_x1, cut_y1;   /* Cutout rectangle after ImageDraw's int truncation, corners inclusive; x1 < x0 = none */
+} srw_aug_sample;
+typedef struct {
+  const uint8_t* src;              /* device [n_src, img_size, img_size, 3] uint8 HWC */
+  int64_t n_src;
+  int img_size, padding;
+  const srw_aug_sample* samples;   /* device [n] */
+  int n;
+  float mean[3], std[3];           /* Normalize constants rounded to fp32 (torch.as_tensor(mean, dtype=float32)) */
+  float* out;                      /* device [n, 3, img_size, img_size] fp32 */
+  uint8_t* out_u8;                 /* optional device [n, img_size, img_size, 3]: the image handed to ToTensor */
+} srw_augment_args;
+int srw_augment_batch(const srw_augment_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -239,6 +239,20 @@ ADAMW_BLOCK_ELEMS = 4096
 PROF_GEMM, PROF_ATTN_FWD, PROF_ATTN_BWD, PROF_ADAMW, PROF_NUM = 0, 1, 2, 3, 4
 
 
+class AugOpDesc(C.Structure):
+    _fields_ = [("op", C.c_int32), ("ival", C.c_int32), ("alpha", f32), ("identity", C.c_int32), ("a", C.c_double * 6)]
+
+
+class AugSample(C.Structure):
+    _fields_ = [("src_index", i64), ("crop_top", C.c_int32), ("crop_left", C.c_int32), ("flip", C.c_int32), ("n_ops", C.c_int32),
+                ("ops", AugOpDesc * 3), ("cut_x0", C.c_int32), ("cut_y0", C.c_int32), ("cut_x1", C.c_int32), ("cut_y1", C.c_int32)]
+
+
+class AugmentArgs(C.Structure):
+    _fields_ = [("src", vp), ("n_src", i64), ("img_size", i32), ("padding", i32), ("samples", vp), ("n", i32), ("mean", f32 * 3),
+                ("std", f32 * 3), ("out", vp), ("out_u8", vp)]
+
+
 class ProfileStats(C.Structure):
     _fields_ = [("launches", i64), ("total_ms", f64), ("flops", f64), ("bytes", f64)]
 
@@ -304,6 +318,7 @@ SYMBOLS = [
     ("srw_softmatch_mask", i32, [C.POINTER(SoftMatchMaskArgs), vp]),
     ("srw_adamw_step", i32, [C.POINTER(AdamWArgs), vp]),
     ("srw_ema_step", i32, [C.POINTER(EmaArgs), vp]),
+    ("srw_augment_batch", i32, [C.POINTER(AugmentArgs), vp]),
 ]
 
 _lib = None

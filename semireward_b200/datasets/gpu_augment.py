@@ -1,0 +1,237 @@
+"""`transform_weak` / `transform_strong` of the reference's image datasets on the device.
+
+Reference: get_cifar builds the two torchvision pipelines (semilearn/datasets/cv_datasets/cifar.py:34-49) and
+BasicDataset.__getitem__ applies them per sample in DataLoader workers (semilearn/datasets/cv_datasets/datasetbase.py:74-115):
+weak = Resize -> RandomCrop(reflect padding) -> RandomHorizontalFlip -> ToTensor -> Normalize; strong adds RandAugment(3, 5) + Cutout
+(semilearn/datasets/augmentation/randaugment.py:157-206).  Here the uint8 array stays resident in HBM, the host only DRAWS the
+random decisions — from the same generators, in the same order as the reference's objects (torch's global generator for crop /
+flip, Python's `random` for ops and magnitudes, numpy's global generator for the Cutout position) — and `srw_augment_batch`
+(csrc/srw_augment.cu) does all pixel work: one CTA per sample, bit-identical to Pillow / torchvision.
+
+There is no CPU fallback: without the CUDA library the pipeline raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import random
+from dataclasses import dataclass, field
+from typing import Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+
+# positions in the reference's augment_list() (randaugment.py:157-174) = enum srw_aug_op
+(AUTOCONTRAST, BRIGHTNESS, COLOR, CONTRAST, EQUALIZE, IDENTITY, POSTERIZE, ROTATE, SHARPNESS, SHEAR_X, SHEAR_Y, SOLARIZE,
+ TRANSLATE_X, TRANSLATE_Y) = range(14)
+_RANGE = [(0, 1), (0.05, 0.95), (0.05, 0.95), (0.05, 0.95), (0, 1), (0, 1), (4, 8), (-30, 30), (0.05, 0.95), (-0.3, 0.3), (-0.3, 0.3),
+          (0, 256), (-0.3, 0.3), (-0.3, 0.3)]
+_NO_COLOR = [BRIGHTNESS, EQUALIZE, IDENTITY, ROTATE, SHARPNESS, SHEAR_X, SHEAR_Y, TRANSLATE_X, TRANSLATE_Y]   # augment_list_no_color()
+
+
+@dataclass
+class AugDecision:
+    """Everything random about one transformed sample."""
+    crop_top: int = 0
+    crop_left: int = 0
+    flip: bool = False
+    ops: List[Tuple[int, float]] = field(default_factory=list)       # (op id, val), application order; empty = weak transform
+    cutout: Optional[Tuple[float, float, float, float]] = None       # the xy CutoutAbs hands to ImageDraw.rectangle
+
+
+def _draw_geometry(size: int, padding: int) -> Tuple[int, int, bool]:
+    # RandomCrop.get_params: no draw when the padded image equals the crop; RandomHorizontalFlip: torch.rand(1) < p
+    top = left = 0
+    if padding > 0:
+        top = int(torch.randint(0, 2 * padding + 1, size=(1,)).item())
+        left = int(torch.randint(0, 2 * padding + 1, size=(1,)).item())
+    return top, left, bool(torch.rand(1) < 0.5)
+
+
+def draw_weak(size: int, padding: int) -> AugDecision:
+    return AugDecision(*_draw_geometry(size, padding))
+
+
+def draw_strong(size: int, padding: int, n: int = 3, exclude_color_aug: bool = False) -> AugDecision:
+    """RandAugment.__call__ (randaugment.py:196-203) after the geometric front: random.choices, one random.random() per op, one for
+    the Cutout size, CutoutAbs' two np.random.uniform draws (randaugment.py:136-146)."""
+    top, left, flip = _draw_geometry(size, padding)
+    table = _NO_COLOR if exclude_color_aug else list(range(14))
+    ops = []
+    for i in random.choices(table, k=n):
+        lo, hi = _RANGE[i]
+        ops.append((i, lo + float(hi - lo) * random.random()))
+    v = random.random() * 0.5
+    cut = None
+    if v > 0.0:
+        v = v * size
+        x0 = np.random.uniform(size)
+        y0 = np.random.uniform(size)
+        x0 = int(max(0, x0 - v / 2.0))
+        y0 = int(max(0, y0 - v / 2.0))
+        cut = (x0, y0, min(size, x0 + v), min(size, y0 + v))
+    return AugDecision(top, left, flip, ops, cut)
+
+
+def _affine_coefficients(op: int, v: float, size: int) -> Optional[List[float]]:
+    """Inverse-map coefficients as Pillow's Python layer forms them (Image.rotate rounds cos / sin to 15 decimals and moves the
+    centre (w/2, h/2); the shears / translations pass the tuples of randaugment.py:66-110 through unchanged)."""
+    if op == ROTATE:
+        angle = v % 360.0
+        if angle == 0:
+            return None
+        if angle in (90, 180, 270):
+            raise NotImplementedError("Image.rotate's transpose fast paths (val is a continuous draw)")
+        c = size / 2.0
+        a = -math.radians(angle)
+        m = [round(math.cos(a), 15), round(math.sin(a), 15), 0.0, round(-math.sin(a), 15), round(math.cos(a), 15), 0.0]
+        m[2] = m[0] * (-c) + m[1] * (-c) + m[2]
+        m[5] = m[3] * (-c) + m[4] * (-c) + m[5]
+        m[2] += c
+        m[5] += c
+        return m
+    if op == SHEAR_X:
+        return [1.0, v, 0.0, 0.0, 1.0, 0.0]
+    if op == SHEAR_Y:
+        return [1.0, 0.0, 0.0, v, 1.0, 0.0]
+    if op == TRANSLATE_X:
+        return [1.0, 0.0, v * size, 0.0, 1.0, 0.0]
+    return [1.0, 0.0, 0.0, 0.0, 1.0, v * size]
+
+
+def pack_samples(indices: Sequence[int], decisions: Sequence[AugDecision], size: int):
+    """-> ctypes array of srw_aug_sample (include/srw.h)."""
+    n = len(decisions)
+    assert len(indices) == n
+    arr = (L.AugSample * n)()
+    for s, idx, d in zip(arr, indices, decisions):
+        s.src_index = int(idx)
+        s.crop_top, s.crop_left, s.flip = d.crop_top, d.crop_left, int(d.flip)
+        if len(d.ops) > 3:
+            raise ValueError("srw_aug_sample holds at most 3 ops (RandAugment(3, 5))")
+        s.n_ops = len(d.ops)
+        for k, (op, v) in enumerate(d.ops):
+            o = s.ops[k]
+            o.op = op
+            if op in (BRIGHTNESS, COLOR, CONTRAST, SHARPNESS):
+                if v < 0.0:
+                    raise ValueError("enhancement factor must be >= 0 (randaugment.py:21,26,31,59)")
+                o.alpha = v
+            elif op == POSTERIZE:
+                o.ival = max(1, int(v))                               # randaugment.py:46-49
+                if o.ival > 8:
+                    raise ValueError("posterize bits > 8")
+            elif op == SOLARIZE:
+                if not 0 <= v <= 256:
+                    raise ValueError("solarize threshold outside [0, 256] (randaugment.py:114)")
+                o.ival = int(math.ceil(v))                            # integer level i is kept iff i < v  <=>  i < ceil(v)
+            elif op in (ROTATE, SHEAR_X, SHEAR_Y, TRANSLATE_X, TRANSLATE_Y):
+                m = _affine_coefficients(op, v, size)
+                if m is None:
+                    o.identity = 1
+                else:
+                    # libImaging takes the 16.16 fixed-point path only while every corner maps inside +-32768
+                    for x, y in ((0, 0), (size, size), (0, size), (size, 0)):
+                        if not (abs(x * m[0] + y * m[1] + m[2]) < 32768.0 and abs(x * m[3] + y * m[4] + m[5]) < 32768.0):
+                            raise ValueError("affine coefficients outside the fixed-point range of Image.transform")
+                    for j in range(6):
+                        o.a[j] = m[j]
+        if d.cutout is None:
+            s.cut_x0, s.cut_y0, s.cut_x1, s.cut_y1 = 0, 0, -1, -1
+        else:
+            s.cut_x0, s.cut_y0, s.cut_x1, s.cut_y1 = (int(v) for v in d.cutout)   # ImageDraw truncates the float corners
+    return arr
+
+
+class DeviceImagePipeline:
+    """The dataset's uint8 HWC array resident on the device + the two transforms of get_cifar as one kernel launch per batch."""
+
+    def __init__(self, data, mean: Sequence[float], std: Sequence[float], img_size: Optional[int] = None, crop_ratio: float = 0.875,
+                 device: str = "cuda"):
+        data = torch.as_tensor(np.ascontiguousarray(data)) if not torch.is_tensor(data) else data
+        if data.dtype != torch.uint8 or data.ndim != 4 or data.shape[3] != 3 or data.shape[1] != data.shape[2]:
+            raise ValueError("expected a uint8 [N, S, S, 3] array (torchvision's CIFAR `.data` layout)")
+        self.size = int(data.shape[1])
+        if img_size is not None and int(img_size) != self.size:
+            raise NotImplementedError("transforms.Resize to a different size (PIL antialiased bilinear) is not built; "
+                                      f"source {self.size} px, img_size {img_size}")
+        self.padding = int(self.size * (1 - crop_ratio))             # cifar.py:36
+        self.lib = L.load()
+        self.data = data.contiguous().to(device)
+        self.mean = [float(np.float32(m)) for m in mean]
+        self.std = [float(np.float32(s)) for s in std]
+        self._stage = None                                            # pinned staging buffer of the decision records
+
+    def _upload(self, arr) -> torch.Tensor:
+        nbytes = C.sizeof(arr)
+        if self._stage is None or self._stage.numel() < nbytes:
+            self._stage = torch.empty(max(nbytes, 64 * C.sizeof(L.AugSample)), dtype=torch.uint8).pin_memory()
+        host = self._stage[:nbytes]
+        host.copy_(torch.frombuffer(memoryview(arr).cast("B"), dtype=torch.uint8))
+        dev = torch.empty(nbytes, dtype=torch.uint8, device=self.data.device)
+        dev.copy_(host, non_blocking=True)
+        self._stage_event = torch.cuda.Event()
+        self._stage_event.record()
+        return dev
+
+    def transform(self, indices: Sequence[int], decisions: Sequence[AugDecision], out: Optional[torch.Tensor] = None,
+                  return_u8: bool = False):
+        idx = [int(i) for i in indices]
+        if not idx:
+            raise ValueError("empty batch")
+        if min(idx) < 0 or max(idx) >= self.data.shape[0]:
+            raise IndexError("sample index outside the dataset")
+        for d in decisions:
+            if not (0 <= d.crop_top <= 2 * self.padding and 0 <= d.crop_left <= 2 * self.padding):
+                raise ValueError("crop offset outside the padded image")
+        n, S = len(idx), self.size
+        if getattr(self, "_stage_event", None) is not None:
+            self._stage_event.synchronize()                           # the previous batch's records have left the staging buffer
+        recs = self._upload(pack_samples(idx, decisions, S))
+        if out is None:
+            out = torch.empty(n, 3, S, S, dtype=torch.float32, device=self.data.device)
+        assert out.is_contiguous() and out.shape == (n, 3, S, S) and out.dtype == torch.float32
+        u8 = torch.empty(n, S, S, 3, dtype=torch.uint8, device=self.data.device) if return_u8 else None
+        a = L.AugmentArgs(src=L.ptr(self.data), n_src=self.data.shape[0], img_size=S, padding=self.padding, samples=L.ptr(recs), n=n,
+                          mean=(L.f32 * 3)(*self.mean), std=(L.f32 * 3)(*self.std), out=L.ptr(out), out_u8=L.ptr(u8))
+        L.check(self.lib.srw_augment_batch(C.byref(a), L.stream_ptr()), "srw_augment_batch")
+        recs.record_stream(torch.cuda.current_stream())
+        return (out, u8) if return_u8 else out
+
+    # the reference draws per sample, in __getitem__ order
+    def weak(self, indices: Sequence[int]) -> torch.Tensor:
+        return self.transform(indices, [draw_weak(self.size, self.padding) for _ in indices])
+
+    def weak_and_strong(self, indices: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:
+        """datasetbase.py:90,115: per sample, transform(img) then strong_transform(img); both views in ONE launch."""
+        dec_w, dec_s = [], []
+        for _ in indices:
+            dec_w.append(draw_weak(self.size, self.padding))
+            dec_s.append(draw_strong(self.size, self.padding))
+        n = len(dec_w)
+        both = self.transform(list(indices) + list(indices), dec_w + dec_s)
+        return both[:n], both[n:]
+
+
+class DeviceSSLLoader:
+    """What `zip(loader_dict['train_lb'], loader_dict['train_ulb'])` yields in AlgorithmBase.train() (core/algorithmbase.py:357-370),
+    with the batches already on the device: ({'idx_lb', 'x_lb', 'y_lb'}, {'idx_ulb', 'x_ulb_w', 'x_ulb_s'}).  Index streams come from
+    the caller's samplers (any iterable of index lists, e.g. torch BatchSampler over the reference's DistributedSampler)."""
+
+    def __init__(self, lb: DeviceImagePipeline, lb_targets, ulb: DeviceImagePipeline, lb_batches: Iterable[Sequence[int]],
+                 ulb_batches: Iterable[Sequence[int]]):
+        self.lb, self.ulb = lb, ulb
+        self.targets = torch.as_tensor(np.asarray(lb_targets), dtype=torch.int64).to(lb.data.device)
+        self.lb_batches, self.ulb_batches = lb_batches, ulb_batches
+
+    def __iter__(self) -> Iterator[Tuple[dict, dict]]:
+        for ib, iu in zip(self.lb_batches, self.ulb_batches):
+            ib_t = torch.as_tensor(list(ib), dtype=torch.int64)
+            iu_t = torch.as_tensor(list(iu), dtype=torch.int64)
+            x_lb = self.lb.weak(ib)                                   # the labelled loader's batch is collated first
+            x_w, x_s = self.ulb.weak_and_strong(iu)
+            dev = self.lb.data.device
+            yield ({"idx_lb": ib_t.to(dev), "x_lb": x_lb, "y_lb": self.targets[ib_t.to(dev)]},
+                   {"idx_ulb": iu_t.to(dev), "x_ulb_w": x_w, "x_ulb_s": x_s})

@@ -58,3 +58,33 @@ def hubert_small_cfg(**over):
              sr_ema=False, use_cat=False, amp=False, ema_m=0.0, thresh_warmup=True, p_cutoff=0.95)
     c.update(over)
     return c
+
+
+# Image input pipeline: the reference's transform_weak / transform_strong on 32 x 32 CIFAR-shaped images.
+# tests/golden/augment_cifar.npz (make_golden_augment.py) stores the source images, the decisions the reference's generators
+# produced, and the tensors the imported reference returned.
+def augment_decisions_to_arrays(decs):
+    import numpy as np
+    n = len(decs)
+    geo = np.zeros((n, 3), dtype=np.int64)
+    op_id = np.full((n, 3), -1, dtype=np.int64)
+    op_val = np.zeros((n, 3), dtype=np.float64)
+    cut = np.full((n, 4), np.nan, dtype=np.float64)
+    for i, d in enumerate(decs):
+        geo[i] = (d.crop_top, d.crop_left, int(d.flip))
+        for k, (o, v) in enumerate(d.ops):
+            op_id[i, k], op_val[i, k] = o, v
+        if d.cutout is not None:
+            cut[i] = d.cutout
+    return dict(geo=geo, op_id=op_id, op_val=op_val, cut=cut)
+
+
+def augment_decisions_from_arrays(z):
+    import numpy as np
+    from oracle.augment_oracle import Decision
+    out = []
+    for i in range(len(z["geo"])):
+        ops = [(int(o), float(v)) for o, v in zip(z["op_id"][i], z["op_val"][i]) if o >= 0]
+        cut = None if np.isnan(z["cut"][i][0]) else tuple(float(v) for v in z["cut"][i])
+        out.append(Decision(int(z["geo"][i][0]), int(z["geo"][i][1]), bool(z["geo"][i][2]), ops, cut))
+    return out

@@ -1,0 +1,164 @@
+"""Pins oracle/augment_oracle.py (numpy restatement of the reference's image pipeline) to the live libraries the reference
+calls — Pillow and torchvision, both installed on the build container AND on the GPU box — and, where /root/reference is
+mounted, to the reference's own RandAugment / transform objects under seeded generators.  CPU only."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import augment_oracle as A
+
+PIL = pytest.importorskip("PIL")
+from PIL import Image, ImageDraw, ImageEnhance, ImageFilter, ImageOps  # noqa: E402
+
+HAVE_REF = os.path.isdir("/root/reference/semilearn")
+
+
+def _images(rng, n, size=32):
+    """random images plus the degenerate ones the histogram ops branch on."""
+    out = []
+    for k in range(n):
+        kind = k % 6
+        if kind == 0:
+            a = rng.integers(0, 256, (size, size, 3))
+        elif kind == 1:                                   # narrow range (autocontrast stretches, equalize has few levels)
+            lo = int(rng.integers(0, 200))
+            a = rng.integers(lo, lo + int(rng.integers(2, 56)), (size, size, 3))
+        elif kind == 2:                                   # smooth gradient + noise
+            y, x = np.mgrid[0:size, 0:size]
+            a = (y[..., None] * rng.integers(1, 8, 3) + x[..., None] * rng.integers(1, 8, 3) + rng.integers(0, 16, (size, size, 3))) % 256
+        elif kind == 3:                                   # one constant channel, one two-level channel
+            a = rng.integers(0, 256, (size, size, 3))
+            a[..., 0] = int(rng.integers(0, 256))
+            a[..., 1] = np.where(rng.random((size, size)) < 0.5, 3, 250)
+        elif kind == 4:                                   # constant image
+            a = np.zeros((size, size, 3), dtype=np.int64) + rng.integers(0, 256, 3)
+        else:                                             # a few levels, very unequal counts (equalize step == 0 / small)
+            a = rng.choice([0, 1, 128, 255], size=(size, size, 3), p=[0.9, 0.05, 0.03, 0.02])
+        out.append(a.astype(np.uint8))
+    return out
+
+
+def _pil_op(op, img, v):
+    w, h = img.size
+    if op == A.AUTOCONTRAST:
+        return ImageOps.autocontrast(img)
+    if op == A.BRIGHTNESS:
+        return ImageEnhance.Brightness(img).enhance(v)
+    if op == A.COLOR:
+        return ImageEnhance.Color(img).enhance(v)
+    if op == A.CONTRAST:
+        return ImageEnhance.Contrast(img).enhance(v)
+    if op == A.EQUALIZE:
+        return ImageOps.equalize(img)
+    if op == A.IDENTITY:
+        return img
+    if op == A.POSTERIZE:
+        return ImageOps.posterize(img, max(1, int(v)))
+    if op == A.ROTATE:
+        return img.rotate(v)
+    if op == A.SHARPNESS:
+        return ImageEnhance.Sharpness(img).enhance(v)
+    if op == A.SHEAR_X:
+        return img.transform(img.size, Image.AFFINE, (1, v, 0, 0, 1, 0))
+    if op == A.SHEAR_Y:
+        return img.transform(img.size, Image.AFFINE, (1, 0, 0, v, 1, 0))
+    if op == A.SOLARIZE:
+        return ImageOps.solarize(img, v)
+    if op == A.TRANSLATE_X:
+        return img.transform(img.size, Image.AFFINE, (1, 0, v * w, 0, 1, 0))
+    if op == A.TRANSLATE_Y:
+        return img.transform(img.size, Image.AFFINE, (1, 0, 0, 0, 1, v * h))
+    raise ValueError(op)
+
+
+@pytest.mark.parametrize("op", range(14))
+def test_every_op_matches_pillow_bit_for_bit(op):
+    rng = np.random.default_rng(100 + op)
+    lo, hi = A.OP_RANGE[op]
+    n = 0
+    for size in (32, 96):
+        for a in _images(rng, 36 if size == 32 else 6, size):
+            for v in [lo, lo + (hi - lo) * 0.5] + [lo + (hi - lo) * float(rng.random()) for _ in range(4)]:
+                want = np.asarray(_pil_op(op, Image.fromarray(a), v))
+                got = A.apply_op(a, op, v)
+                assert np.array_equal(got, want), (A.OP_NAMES[op], v, int((got != want).sum()))
+                n += 1
+    assert n >= 200
+
+
+def test_blend_extrapolating_branch_and_smooth_filter():
+    rng = np.random.default_rng(7)
+    for a in _images(rng, 12):
+        img = Image.fromarray(a)
+        assert np.array_equal(A.smooth(a), np.asarray(img.filter(ImageFilter.SMOOTH)))
+        for v in (1.3, 1.9, 0.0, 1.0):
+            assert np.array_equal(A.sharpness(a, v), np.asarray(ImageEnhance.Sharpness(img).enhance(v)))
+            assert np.array_equal(A.contrast(a, v), np.asarray(ImageEnhance.Contrast(img).enhance(v)))
+
+
+def test_rectangle_is_inclusive_and_truncates():
+    rng = np.random.default_rng(3)
+    for a in _images(rng, 6):
+        for _ in range(20):
+            v = float(rng.random()) * 16
+            x0 = int(max(0, float(rng.random()) * 32 - v / 2))
+            y0 = int(max(0, float(rng.random()) * 32 - v / 2))
+            xy = (x0, y0, min(32, x0 + v), min(32, y0 + v))
+            img = Image.fromarray(a).copy()
+            ImageDraw.Draw(img).rectangle(xy, A.CUTOUT_COLOR)
+            assert np.array_equal(A.cutout_abs(a, xy), np.asarray(img)), xy
+
+
+def test_crop_flip_and_normalise_match_torchvision():
+    from torchvision import transforms
+    rng = np.random.default_rng(5)
+    norm = transforms.Compose([transforms.ToTensor(), transforms.Normalize(A.CIFAR100_MEAN, A.CIFAR100_STD)])
+    for k, a in enumerate(_images(rng, 12)):
+        weak = transforms.Compose([transforms.Resize(32), transforms.RandomCrop(32, padding=4, padding_mode="reflect"),
+                                   transforms.RandomHorizontalFlip()])
+        torch.manual_seed(k)
+        want = weak(Image.fromarray(a))
+        torch.manual_seed(k)
+        d = A.draw_weak(32, 4)
+        got = A.transform_u8(a, d, 4)
+        assert np.array_equal(got, np.asarray(want))
+        assert np.array_equal(A.to_tensor_normalize(got, A.CIFAR100_MEAN, A.CIFAR100_STD), norm(want).numpy())   # bit-exact floats
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="live reference only exists in the build container")
+def test_strong_transform_matches_the_live_reference_under_seeded_generators():
+    """The reference's own transform_strong (cifar.py:42-49) with its RandAugment, seeded; the oracle draws the same decisions
+    from the same generators and must reproduce the tensor bit for bit."""
+    from oracle import ref_driver as R
+    R.load_reference()
+    from torchvision import transforms
+    from semilearn.datasets.augmentation import RandAugment
+    strong = transforms.Compose([transforms.Resize(32), transforms.RandomCrop(32, padding=4, padding_mode="reflect"),
+                                 transforms.RandomHorizontalFlip(), RandAugment(3, 5), transforms.ToTensor(),
+                                 transforms.Normalize(A.CIFAR100_MEAN, A.CIFAR100_STD)])
+    rng = np.random.default_rng(11)
+    seen = set()
+    for k, a in enumerate(_images(rng, 240)):
+        torch.manual_seed(k); random.seed(k); np.random.seed(k)
+        want = strong(Image.fromarray(a)).numpy()
+        torch.manual_seed(k); random.seed(k); np.random.seed(k)
+        d = A.draw_strong(32, 4)
+        seen.update(op for op, _ in d.ops)
+        got = A.transform(a, d, 4, A.CIFAR100_MEAN, A.CIFAR100_STD)
+        assert np.array_equal(got, want), (k, d)
+    assert len(seen) == 14
+
+
+def test_golden_fixture():
+    """tests/golden/augment_cifar.npz: outputs of the imported reference (make_golden_augment.py), decisions included."""
+    path = os.path.join(os.path.dirname(__file__), "golden", "augment_cifar.npz")
+    z = np.load(path)
+    from golden_cases import augment_decisions_from_arrays
+    imgs, want = z["images"], z["strong"]
+    decs = augment_decisions_from_arrays(z)
+    for i in range(len(imgs)):
+        got = A.transform(imgs[i], decs[i], 4, A.CIFAR100_MEAN, A.CIFAR100_STD)
+        assert np.array_equal(got, want[i]), i

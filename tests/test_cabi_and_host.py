@@ -57,7 +57,7 @@ def test_every_struct_matches_the_header_field_by_field(tmp_path):
                  srw_ema_args="EmaArgs", srw_dropout="Dropout", srw_bert_config="BertConfig", srw_bert_fwd_args="BertFwdArgs",
                  srw_bert_bwd_args="BertBwdArgs", srw_hubert_config="HubertConfig", srw_hubert_fwd_args="HubertFwdArgs",
                      srw_hubert_bwd_args="HubertBwdArgs", srw_wrn_config="WrnConfig", srw_wrn_fwd_args="WrnFwdArgs", srw_wrn_bwd_args="WrnBwdArgs",
-                     srw_sgd_args="SgdArgs")
+                     srw_sgd_args="SgdArgs", srw_aug_op_desc="AugOpDesc", srw_aug_sample="AugSample", srw_augment_args="AugmentArgs")
     hdr = open(os.path.join(ROOT, "include", "srw.h")).read()
     assert set(re.findall(r"}\s*(srw_[a-z0-9_]+);", hdr)) == set(pairs), "a struct of include/srw.h has no ctypes mirror in this table"
     lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "srw.h"', "int main(void) {"]
