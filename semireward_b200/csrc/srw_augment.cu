@@ -114,16 +114,24 @@ __device__ void op_equalize(unsigned char* img, int nbytes, AugScratch* sc) {
 // Image.transform(AFFINE, NEAREST), fill 0 (libImaging Geometry.c).  a[1] == a[3] == 0: the axis-aligned path (source column and
 // row from coordinates ACCUMULATED in doubles, negative = outside); otherwise 16.16 fixed point with the pixel centre folded
 // into the offsets.
-__device__ void op_affine(const unsigned char* src, unsigned char* dst, int S, const double* a) {
+__device__ void op_affine(const unsigned char* src, unsigned char* dst, int S, const double* a, AugScratch* sc) {
   const int npix = S * S;
   if (a[1] == 0.0 && a[3] == 0.0) {
+    // libImaging walks xo += a[0] / yo += a[4] once per column / row: the same running sums, one thread per column and per row
+    int* xin = sc->hist[0];                // [S] source column of every output column (S <= 128)
+    int* yin = sc->hist[1];
+    if (threadIdx.x < 2 * S) {
+      const bool is_y = threadIdx.x >= S;
+      const int k = is_y ? threadIdx.x - S : threadIdx.x;
+      const double step = is_y ? a[4] : a[0];
+      double o = __dadd_rn(is_y ? a[5] : a[2], __dmul_rn(step, 0.5));
+      for (int j = 0; j < k; ++j) o = __dadd_rn(o, step);
+      (is_y ? yin : xin)[k] = o < 0.0 ? -1 : (int)o;
+    }
+    __syncthreads();
     for (int p = threadIdx.x; p < npix; p += AUG_THREADS) {
       const int y = p / S, x = p - y * S;
-      double xo = __dadd_rn(a[2], __dmul_rn(a[0], 0.5));
-      for (int k = 0; k < x; ++k) xo = __dadd_rn(xo, a[0]);
-      double yo = __dadd_rn(a[5], __dmul_rn(a[4], 0.5));
-      for (int k = 0; k < y; ++k) yo = __dadd_rn(yo, a[4]);
-      const int xi = xo < 0.0 ? -1 : (int)xo, yi = yo < 0.0 ? -1 : (int)yo;
+      const int xi = xin[x], yi = yin[y];
       const bool ok = xi >= 0 && xi < S && yi >= 0 && yi < S;
       const int q = ok ? (yi * S + xi) * 3 : 0;
       dst[p * 3 + 0] = ok ? src[q + 0] : 0;
@@ -236,7 +244,7 @@ augment_kernel(const srw_augment_args A) {
       } break;
       case SRW_AUG_ROTATE: case SRW_AUG_SHEAR_X: case SRW_AUG_SHEAR_Y: case SRW_AUG_TRANSLATE_X: case SRW_AUG_TRANSLATE_Y: {
         if (!op.identity) {
-          op_affine(cur, alt, S, op.a);
+          op_affine(cur, alt, S, op.a, sc);
           unsigned char* t = cur; cur = alt; alt = t;
         }
       } break;
