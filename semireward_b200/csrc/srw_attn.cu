@@ -64,15 +64,127 @@ __device__ __forceinline__ void store_out16(__nv_bfloat16* hi_ptr, int64_t plane
 unsigned long long* g_attn_trace = nullptr;
 unsigned long long* g_attn_bwd_trace = nullptr;   // [2 kernels][B * H * row tiles][48]
 
+// ------------------------------------------------------------------------------------------------
+// tail row on CUDA cores
+// ------------------------------------------------------------------------------------------------
+// N = 257 (ViT-S/2 at 32 px, the headline config: 256 patches + the class token) leaves ONE row for a third 128-row tile, and a
+// tile costs its whole latency chain whatever it holds (3.4 us of a 16.6 us forward CTA).  When N % 128 == 1 the forward takes the
+// last row out of the tensor-core path: two extra warps per CTA compute it in fp32 from the K / V tiles that are in shared memory
+// anyway, next to the two full tiles (24.0 -> 21.9 us per launch at 24 images; `SRW_ATTN_TAIL=0` keeps the row in a tile).
+// The backward keeps its third wave of one-row CTAs.  Measured alternatives (profiles/r2_history.md): the row inside the backward
+// kernels as two more warps on the ring's stages (the element-wise warps are issue-bound: the CTA carrying them took twice as
+// long, 58 -> 72 us per dQ + dK,dV pair); as a CUDA-core kernel of its own between the two tile kernels (the tile kernels drop
+// from three waves to two, 43 -> 32 us each under ncu, but the latency-bound 19 us kernel and the broken programmatic edge cost
+// more: 58 -> 77 us); the same kernel forked onto a side stream next to the dQ kernel (event edges inside the captured graph: 153 us).
+constexpr int TAIL_WARPS = 2;
+constexpr int TAIL_SCRATCH_BYTES = 2560;
+
+__device__ __forceinline__ void tail_sync() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
+
+// SWIZZLE_128B plane with a 1024-byte aligned base and 128-byte rows (64 bf16): 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+__device__ __forceinline__ uint4 sw_ld128(const uint8_t* plane, int row, int chunk) {
+  return *reinterpret_cast<const uint4*>(plane + row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ uint32_t sw_ld32(const uint8_t* plane, int row, int pair) {   // elements 2 pair, 2 pair + 1 of the row
+  return *reinterpret_cast<const uint32_t*>(plane + row * 128 + ((((pair >> 2) ^ (row & 7)) << 4) | ((pair & 3) << 2)));
+}
+#define SRW_TAIL_FMA2(vv0, vv1, hw, lw)                                    \
+  acc0 = fmaf(vv0, bf16_lo_f(hw) + bf16_lo_f(lw), acc0);                   \
+  acc1 = fmaf(vv1, bf16_hi_f(hw) + bf16_hi_f(lw), acc1);
+// dot of a 64-float vector in shared memory with row `row` of a split operand tile (hi plane, lo plane) in shared memory
+__device__ __forceinline__ float sw_dot64(const float* __restrict__ vec, const uint8_t* hi, const uint8_t* lo, int row) {
+  float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 h = sw_ld128(hi, row, c), l = sw_ld128(lo, row, c);
+    const float4 v0 = *reinterpret_cast<const float4*>(vec + c * 8), v1 = *reinterpret_cast<const float4*>(vec + c * 8 + 4);
+    SRW_TAIL_FMA2(v0.x, v0.y, h.x, l.x)
+    SRW_TAIL_FMA2(v0.z, v0.w, h.y, l.y)
+    SRW_TAIL_FMA2(v1.x, v1.y, h.z, l.z)
+    SRW_TAIL_FMA2(v1.z, v1.w, h.w, l.w)
+  }
+  return acc0 + acc1;
+}
+#undef SRW_TAIL_FMA2
+
 struct AttnFwdParams {
   int B, N, H, NP;        // NP = N rounded up to 16 (<= 272)
   float scale;            // head_dim^-0.5
+  const __nv_bfloat16* qkv; int64_t ld_qkv, qkv_ps;   // raw view of the operand (tail row)
+  int tail;               // 1: row N - 1 on CUDA cores (N % 128 == 1)
   __nv_bfloat16* o; int64_t ld_o, o_ps;
   float* lse;             // [B, H, N] natural-log units: scale*max + log(sum)
   unsigned long long* trace;   // debug (srw_attn_set_trace): per CTA 32 clock64 stamps, see scripts/attn_trace.py; NULL in production
 };
 
 constexpr int FWD_THREADS = 512 + 32;   // 16 softmax warps (4 per TMEM lane quarter, 16 columns each) + 1 TMA/MMA warp
+constexpr int FWD_THREADS_TAIL = FWD_THREADS + 32 * TAIL_WARPS;
+
+// the last query row of a (head, image): scores against the K tile in shared memory, softmax, p V against the V tile
+__device__ __noinline__ void fwd_tail_row(const AttnFwdParams& p, const uint8_t* k_hi, const uint8_t* v_hi, uint32_t kv_plane, uint64_t* bar_kv,
+                                          float* scr, int tw, int lane, int h, int b) {
+  float* tq = scr;               // [64] the query
+  float* tp = scr + 64;          // [272] probabilities
+  float* red = scr + 64 + 272;   // [4] row max, row sum per warp
+  float* op = red + 4;           // [2][64] partial outputs per warp
+  const int N = p.N, qr = N - 1, tl = tw * 32 + lane;
+  const int64_t row = (int64_t)b * N + qr;
+  tq[tl] = plane_value(p.qkv + row * p.ld_qkv + h * HD, p.qkv_ps, tl);
+  tail_sync();
+  mbar_wait(bar_kv, 0);
+  const uint8_t* k_lo = k_hi + kv_plane;
+  const uint8_t* v_lo = v_hi + kv_plane;
+  float s[5];                    // thread tl owns keys tl, tl + 64, ... (N <= 272)
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int j = tl + 64 * i;
+    s[i] = -INFINITY;
+    if (j < N) s[i] = sw_dot64(tq, k_hi, k_lo, j);
+    m = fmaxf(m, s[i]);
+  }
+  m = warp_max(m);
+  if (lane == 0) red[tw] = m;
+  tail_sync();
+  m = fmaxf(red[0], red[1]);
+  const float c2 = p.scale * LOG2E, mc = m * c2;
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int j = tl + 64 * i;
+    if (j < N) {
+      const float e = ex2_approx(fmaf(s[i], c2, -mc));
+      tp[j] = e;
+      sum += e;
+    }
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[2 + tw] = sum;
+  tail_sync();
+  sum = red[2] + red[3];
+  // o = p V: each warp takes half of the keys, a lane owns head-dim elements (2 lane, 2 lane + 1)
+  const int half = (N + 1) / 2, j0 = tw * half, j1 = min(N, j0 + half);
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+  for (int j = j0; j < j1; ++j) {
+    const float pj = tp[j];
+    const uint32_t vh = sw_ld32(v_hi, j, lane), vl = sw_ld32(v_lo, j, lane);
+    a0 = fmaf(pj, bf16_lo_f(vh) + bf16_lo_f(vl), a0);
+    a1 = fmaf(pj, bf16_hi_f(vh) + bf16_hi_f(vl), a1);
+  }
+  op[tw * 64 + 2 * lane] = a0;
+  op[tw * 64 + 2 * lane + 1] = a1;
+  tail_sync();
+  if (tw == 0) {
+    const float inv = 1.0f / sum;
+    uint32_t hh, ll;
+    split2((op[2 * lane] + op[64 + 2 * lane]) * inv, (op[2 * lane + 1] + op[64 + 2 * lane + 1]) * inv, hh, ll);
+    __nv_bfloat16* dst = p.o + row * p.ld_o + h * HD + 2 * lane;
+    *reinterpret_cast<uint32_t*>(dst) = hh;
+    *reinterpret_cast<uint32_t*>(dst + p.o_ps) = ll;
+    if (lane == 0 && p.lse) p.lse[((int64_t)b * p.H + h) * N + qr] = m * p.scale + logf(sum);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // forward: one CTA per (head, image), K/V staged once, loop over query tiles, P through tensor memory
@@ -88,8 +200,8 @@ constexpr int FWD_THREADS = 512 + 32;   // 16 softmax warps (4 per TMEM lane qua
 // per launch at 24 images x 6 heads x 257 tokens).  The freed shared memory double-
 // buffers Q, and the tensor pipe orders S(t+1) after PV(t) by itself (tcgen05.mma executes in issue order), so the next
 // tile's scores are computed while the softmax warps write the current tile's output.
-__global__ void __launch_bounds__(FWD_THREADS, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const AttnFwdParams p) {
+__global__ void __launch_bounds__(FWD_THREADS_TAIL, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const __grid_constant__ AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   pdl_trigger();
@@ -111,7 +223,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int D = p.H * HD;
   const int row0 = b * p.N;           // first token row of this image in the [B*N, 3D] qkv matrix
   const int nchunks = (NP + 63) / 64;
-  const int ntiles = (p.N + 127) / 128;
+  const int ntiles = p.tail ? (p.N - 1) / 128 : (p.N + 127) / 128;
   unsigned long long* tr = p.trace ? p.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 32 : nullptr;
   if (tr && threadIdx.x == 0) tr[0] = clock64();
 
@@ -211,6 +323,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         umma_commit(bar_o);
       }
     }
+  } else if (warp >= 17) {
+    // ---- tail warps (launched only when p.tail): the last query row on CUDA cores ----
+    if (p.tail) fwd_tail_row(p, smem + off_k, smem + off_v, kv_plane, bar_kv, xch_base + 2 * 512, warp - 17, lane, h, b);
   } else {
     // ---- softmax warps: 4 warps per TMEM lane quarter; thread == (query row, 16-key group `part` of every 64-key chunk) ----
     const int q = warp & 3, part = warp >> 2;
@@ -972,6 +1087,16 @@ static int check_attn_shape(int B, int N, int H, int head_dim, const char* who) 
   return SRW_OK;
 }
 
+// N % 128 == 1: the last row leaves the tensor-core tiles (see "tail row on CUDA cores")
+static bool tail_row_mode(int N) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("SRW_ATTN_TAIL");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  return enabled && N > 128 && N <= 272 && N % 128 == 1;
+}
+
 static int fill_ext(AttnExt& e, const float* key_bias, int64_t ld_bias, const int32_t* kv_len, const srw_dropout& drop, int N, const char* who) {
   e.key_bias = key_bias; e.ld_bias = ld_bias; e.kv_len = kv_len;
   e.drop = make_drop(drop);
@@ -1021,7 +1146,7 @@ extern "C" int srw_attn_fwd(const srw_attn_fwd_args* a, void* stream_) {
   if (rc) return rc;
   SRW_REQUIRE(a->ld_o % 8 == 0 && a->o_plane_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(a->o) & 15) == 0, "srw_attn_fwd: o planes must be 16-byte aligned");
   const uint32_t kv_plane = (uint32_t)NP * 128;
-  const int smem_bytes = (int)(4 * ROW_TILE_BYTES + 4 * kv_plane + 128 + 2 * 4 * 128 * 4 + 1024);   // regions A, B | K | V | barriers | 2 exchange sets | align
+  const int smem_bytes = (int)(4 * ROW_TILE_BYTES + 4 * kv_plane + 128 + 2 * 4 * 128 * 4 + TAIL_SCRATCH_BYTES + 1024);   // Q buffers | K | V | barriers | 2 exchange sets | tail scratch | align
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
@@ -1029,11 +1154,13 @@ extern "C" int srw_attn_fwd(const srw_attn_fwd_args* a, void* stream_) {
   AttnFwdParams p;
   p.B = a->B; p.N = a->N; p.H = a->H; p.NP = NP; p.scale = a->scale;
   p.o = reinterpret_cast<__nv_bfloat16*>(a->o); p.ld_o = a->ld_o; p.o_ps = a->o_plane_stride; p.lse = a->lse;
+  p.qkv = reinterpret_cast<const __nv_bfloat16*>(a->qkv); p.ld_qkv = a->ld_qkv; p.qkv_ps = a->qkv_plane_stride;
+  p.tail = tail_row_mode(a->N) ? 1 : 0;
   p.trace = g_attn_trace;
   dim3 grid(a->H, a->B);
   const double pair_flops = 2.0 * a->B * a->H * (double)a->N * a->N * HD;   // one N x N x 64 product per (image, head)
   void* prof = prof_begin(SRW_PROF_ATTN_FWD, 2.0 * pair_flops, 4.0 * 4.0 * a->B * a->N * a->H * HD, stream);
-  SRW_CUDA(launch_pdl(attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), smem_bytes, stream, tq, tkv, p));
+  SRW_CUDA(launch_pdl(attn_fwd_kernel, dim3(grid), dim3(p.tail ? FWD_THREADS_TAIL : FWD_THREADS), smem_bytes, stream, tq, tkv, p));
   prof_end(prof, stream);
   g_launches++;
   SRW_LAUNCH_CHECK();
