@@ -69,17 +69,17 @@ unsigned long long* g_attn_bwd_trace = nullptr;   // [2 kernels][B * H * row til
 // ------------------------------------------------------------------------------------------------
 // N = 257 (ViT-S/2 at 32 px, the headline config: 256 patches + the class token) leaves ONE row for a third 128-row tile, and a
 // tile costs its whole latency chain whatever it holds (3.4 us of a 16.6 us forward CTA).  When N % 128 == 1 the forward takes the
-// last row out of the tensor-core path: two extra warps per CTA compute it in fp32 from the K / V tiles that are in shared memory
+// last row out of the tensor-core path: three extra warps per CTA compute it in fp32 from the K / V tiles that are in shared memory
 // anyway, next to the two full tiles (24.0 -> 21.9 us per launch at 24 images; `SRW_ATTN_TAIL=0` keeps the row in a tile).
 // The backward keeps its third wave of one-row CTAs.  Measured alternatives (profiles/r2_history.md): the row inside the backward
 // kernels as two more warps on the ring's stages (the element-wise warps are issue-bound: the CTA carrying them took twice as
 // long, 58 -> 72 us per dQ + dK,dV pair); as a CUDA-core kernel of its own between the two tile kernels (the tile kernels drop
 // from three waves to two, 43 -> 32 us each under ncu, but the latency-bound 19 us kernel and the broken programmatic edge cost
 // more: 58 -> 77 us); the same kernel forked onto a side stream next to the dQ kernel (event edges inside the captured graph: 153 us).
-constexpr int TAIL_WARPS = 2;
+constexpr int TAIL_WARPS = 3;    // 17 + 3 = 20 warps: five per scheduler partition keeps the 96-register budget of the tile path
 constexpr int TAIL_SCRATCH_BYTES = 2560;
 
-__device__ __forceinline__ void tail_sync() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
+__device__ __forceinline__ void tail_sync() { asm volatile("bar.sync 2, 96;" ::: "memory"); }   // the 32 * TAIL_WARPS tail threads
 
 // SWIZZLE_128B plane with a 1024-byte aligned base and 128-byte rows (64 bf16): 16-byte chunk c of row r sits at chunk c ^ (r & 7)
 __device__ __forceinline__ uint4 sw_ld128(const uint8_t* plane, int row, int chunk) {
@@ -123,22 +123,23 @@ constexpr int FWD_THREADS_TAIL = FWD_THREADS + 32 * TAIL_WARPS;
 // the last query row of a (head, image): scores against the K tile in shared memory, softmax, p V against the V tile
 __device__ __noinline__ void fwd_tail_row(const AttnFwdParams& p, const uint8_t* k_hi, const uint8_t* v_hi, uint32_t kv_plane, uint64_t* bar_kv,
                                           float* scr, int tw, int lane, int h, int b) {
-  float* tq = scr;               // [64] the query
-  float* tp = scr + 64;          // [272] probabilities
-  float* red = scr + 64 + 272;   // [4] row max, row sum per warp
-  float* op = red + 4;           // [2][64] partial outputs per warp
+  constexpr int NT = 32 * TAIL_WARPS;                  // 96 tail threads
+  float* tq = scr;                                     // [64] the query
+  float* tp = scr + 64;                                // [272] probabilities
+  float* red = scr + 64 + 272;                         // [2][TAIL_WARPS] row max, row sum per warp
+  float* op = red + 2 * TAIL_WARPS;                    // [TAIL_WARPS][64] partial outputs per warp
   const int N = p.N, qr = N - 1, tl = tw * 32 + lane;
   const int64_t row = (int64_t)b * N + qr;
-  tq[tl] = plane_value(p.qkv + row * p.ld_qkv + h * HD, p.qkv_ps, tl);
+  if (tl < 64) tq[tl] = plane_value(p.qkv + row * p.ld_qkv + h * HD, p.qkv_ps, tl);
   tail_sync();
   mbar_wait(bar_kv, 0);
   const uint8_t* k_lo = k_hi + kv_plane;
   const uint8_t* v_lo = v_hi + kv_plane;
-  float s[5];                    // thread tl owns keys tl, tl + 64, ... (N <= 272)
+  float s[3];                                          // thread tl owns keys tl, tl + 96, tl + 192 (N <= 272)
   float m = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    const int j = tl + 64 * i;
+  for (int i = 0; i < 3; ++i) {
+    const int j = tl + NT * i;
     s[i] = -INFINITY;
     if (j < N) s[i] = sw_dot64(tq, k_hi, k_lo, j);
     m = fmaxf(m, s[i]);
@@ -146,12 +147,12 @@ __device__ __noinline__ void fwd_tail_row(const AttnFwdParams& p, const uint8_t*
   m = warp_max(m);
   if (lane == 0) red[tw] = m;
   tail_sync();
-  m = fmaxf(red[0], red[1]);
+  m = fmaxf(fmaxf(red[0], red[1]), red[2]);
   const float c2 = p.scale * LOG2E, mc = m * c2;
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    const int j = tl + 64 * i;
+  for (int i = 0; i < 3; ++i) {
+    const int j = tl + NT * i;
     if (j < N) {
       const float e = ex2_approx(fmaf(s[i], c2, -mc));
       tp[j] = e;
@@ -159,11 +160,11 @@ __device__ __noinline__ void fwd_tail_row(const AttnFwdParams& p, const uint8_t*
     }
   }
   sum = warp_sum(sum);
-  if (lane == 0) red[2 + tw] = sum;
+  if (lane == 0) red[TAIL_WARPS + tw] = sum;
   tail_sync();
-  sum = red[2] + red[3];
-  // o = p V: each warp takes half of the keys, a lane owns head-dim elements (2 lane, 2 lane + 1)
-  const int half = (N + 1) / 2, j0 = tw * half, j1 = min(N, j0 + half);
+  sum = (red[TAIL_WARPS] + red[TAIL_WARPS + 1]) + red[TAIL_WARPS + 2];
+  // o = p V: each warp takes a third of the keys, a lane owns head-dim elements (2 lane, 2 lane + 1)
+  const int span = (N + TAIL_WARPS - 1) / TAIL_WARPS, j0 = tw * span, j1 = min(N, j0 + span);
   float a0 = 0.f, a1 = 0.f;
 #pragma unroll 4
   for (int j = j0; j < j1; ++j) {
@@ -177,29 +178,18 @@ __device__ __noinline__ void fwd_tail_row(const AttnFwdParams& p, const uint8_t*
   tail_sync();
   if (tw == 0) {
     const float inv = 1.0f / sum;
+    const float o0 = (op[2 * lane] + op[64 + 2 * lane]) + op[128 + 2 * lane];
+    const float o1 = (op[2 * lane + 1] + op[64 + 2 * lane + 1]) + op[128 + 2 * lane + 1];
     uint32_t hh, ll;
-    split2((op[2 * lane] + op[64 + 2 * lane]) * inv, (op[2 * lane + 1] + op[64 + 2 * lane + 1]) * inv, hh, ll);
+    split2(o0 * inv, o1 * inv, hh, ll);
     __nv_bfloat16* dst = p.o + row * p.ld_o + h * HD + 2 * lane;
     *reinterpret_cast<uint32_t*>(dst) = hh;
     *reinterpret_cast<uint32_t*>(dst + p.o_ps) = ll;
     if (lane == 0 && p.lse) p.lse[((int64_t)b * p.H + h) * N + qr] = m * p.scale + logf(sum);
   }
 }
+static_assert(TAIL_WARPS == 3, "fwd_tail_row folds three warps");
 
-// ------------------------------------------------------------------------------------------------
-// forward: one CTA per (head, image), K/V staged once, loop over query tiles, P through tensor memory
-// ------------------------------------------------------------------------------------------------
-// The probabilities never touch shared memory: a softmax thread reads 16 fp32 scores of its row from TMEM, and writes the
-// 16 probabilities back IN PLACE as split bf16 — columns [16g, 16g+8) = packed hi pairs, [16g+8, 16g+16) = packed lo pairs of key group g —
-// and the PV product takes its A operand from TMEM (umma_bf16_ts).  Per key group that is two MMAs instead of three:
-//   [O | OX] += P_hi [V_hi | V_lo]   (one N = 128 MN-major operand: the lo plane is the second 64-wide chunk, LBO = plane)
-//        OX  += P_lo  V_hi
-// What this removed (scripts/attn_trace.py on the previous kernel, which staged P in two 32 KB shared-memory buffers): the
-// buffers' hand-back barrier — a 1.8 us round trip per pair of 64-key chunks that made a tile cost 7.6 us whatever the
-// softmax work — the st.shared + fence.proxy.async of every P element, and a third of the PV instructions (30 -> 20 us
-// per launch at 24 images x 6 heads x 257 tokens).  The freed shared memory double-
-// buffers Q, and the tensor pipe orders S(t+1) after PV(t) by itself (tcgen05.mma executes in issue order), so the next
-// tile's scores are computed while the softmax warps write the current tile's output.
 __global__ void __launch_bounds__(FWD_THREADS_TAIL, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const __grid_constant__ AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
