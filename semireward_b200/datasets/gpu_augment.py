@@ -200,6 +200,10 @@ class DeviceImagePipeline:
         recs.record_stream(torch.cuda.current_stream())
         return (out, u8) if return_u8 else out
 
+    def val(self, indices: Sequence[int]) -> torch.Tensor:
+        """transform_val (cifar.py:51-55): Resize (identity) -> ToTensor -> Normalize; nothing random."""
+        return self.transform(indices, [AugDecision(self.padding, self.padding, False)] * len(indices))
+
     # the reference draws per sample, in __getitem__ order
     def weak(self, indices: Sequence[int]) -> torch.Tensor:
         return self.transform(indices, [draw_weak(self.size, self.padding) for _ in indices])

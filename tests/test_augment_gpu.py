@@ -118,3 +118,42 @@ def test_loader_draws_the_reference_decision_stream():
         assert np.array_equal(g_lb["x_lb"], x_lb) and np.array_equal(g_lb["y_lb"], targets[ib]) and np.array_equal(g_lb["idx_lb"], ib)
         assert np.array_equal(g_ulb["x_ulb_w"], np.stack(xw)) and np.array_equal(g_ulb["x_ulb_s"], np.stack(xs))
         assert np.array_equal(g_ulb["idx_ulb"], iu)
+
+
+def test_val_transform_and_train_steps_from_the_raw_dataset():
+    """End to end on the device: uint8 dataset -> srw_augment_batch (weak / strong views drawn like the reference's loaders) -> native
+    SRFlexMatch steps, against the oracle stepping on the ORACLE's transforms of the same images under the same seeds."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from helpers import build_native, build_oracle, small_cfg
+    from semireward_b200.datasets import DeviceSSLLoader
+    rng = np.random.default_rng(21)
+    lb_imgs, ulb_imgs = _images(rng, 16, 32), _images(rng, 64, 32)
+    targets = rng.integers(0, 100, 16)
+    pipe_lb, pipe_ulb = _pipe(lb_imgs), _pipe(ulb_imgs)
+    val = pipe_lb.val(range(4)).cpu().numpy()
+    for i in range(4):
+        assert np.array_equal(val[i], A.to_tensor_normalize(lb_imgs[i], A.CIFAR100_MEAN, A.CIFAR100_STD))
+    cfg = small_cfg()
+    orc, alg = build_oracle(cfg, 2), build_native(cfg, 2)
+    lb_batches = [list(rng.integers(0, 16, 8)) for _ in range(3)]
+    ulb_batches = [list(rng.choice(64, 8, replace=False)) for _ in range(3)]
+    torch.manual_seed(5); random.seed(5); np.random.seed(5)
+    native_batches = list(DeviceSSLLoader(pipe_lb, targets, pipe_ulb, lb_batches, ulb_batches))
+    torch.manual_seed(5); random.seed(5); np.random.seed(5)
+    for it, ((d_lb, d_ulb), ib, iu) in enumerate(zip(native_batches, lb_batches, ulb_batches)):
+        x_lb = np.stack([A.transform(lb_imgs[i], A.draw_weak(32, 4), 4, A.CIFAR100_MEAN, A.CIFAR100_STD) for i in ib])
+        xw, xs = [], []
+        for i in iu:
+            xw.append(A.transform(ulb_imgs[i], A.draw_weak(32, 4), 4, A.CIFAR100_MEAN, A.CIFAR100_STD))
+            xs.append(A.transform(ulb_imgs[i], A.draw_strong(32, 4), 4, A.CIFAR100_MEAN, A.CIFAR100_STD))
+        batch = dict(x_lb=torch.from_numpy(x_lb), y_lb=torch.from_numpy(targets[ib]), idx_ulb=torch.tensor([int(i) for i in iu]),
+                     x_ulb_w=torch.from_numpy(np.stack(xw)), x_ulb_s=torch.from_numpy(np.stack(xs)))
+        rec = orc.train_step(dict(batch), it)
+        orc.param_update()
+        alg.it = it
+        alg.out_dict, alg.log_dict = alg.train_step(**alg.process_batch(**d_lb, **d_ulb))
+        alg.call_hook("after_train_step")
+        torch.cuda.synchronize()
+        assert abs(alg.log_dict["train/total_loss"] - float(rec["total_loss"])) < 1e-3
+        assert torch.equal(alg._last_mask.cpu(), rec["mask"]) and torch.equal(alg._last_pseudo_label.cpu(), rec["pseudo"])

@@ -162,3 +162,45 @@ def test_golden_fixture():
     for i in range(len(imgs)):
         got = A.transform(imgs[i], decs[i], 4, A.CIFAR100_MEAN, A.CIFAR100_STD)
         assert np.array_equal(got, want[i]), i
+
+
+def test_host_records_carry_what_pillows_python_layer_computes():
+    """semireward_b200.datasets.gpu_augment (product host code, no GPU needed): the decision stream equals the oracle's under the
+    same seeds, and pack_samples turns a decision into the record fields the kernel consumes — C-float blend factor, posterize
+    bits, ceil of the solarize threshold, Pillow's affine coefficients, ImageDraw's truncated rectangle."""
+    import ctypes as C
+    import math
+    from semireward_b200 import _lib as L
+    from semireward_b200.datasets import gpu_augment as G
+    assert C.sizeof(L.AugSample) == 232 and C.sizeof(L.AugOpDesc) == 64
+    for k in range(100):
+        torch.manual_seed(k); random.seed(k); np.random.seed(k)
+        a = [G.draw_weak(32, 4), G.draw_strong(32, 4)]
+        torch.manual_seed(k); random.seed(k); np.random.seed(k)
+        b = [A.draw_weak(32, 4), A.draw_strong(32, 4)]
+        for x, y in zip(a, b):
+            assert (x.crop_top, x.crop_left, x.flip, x.ops, x.cutout) == (y.crop_top, y.crop_left, y.flip, y.ops, y.cutout)
+        rec = G.pack_samples([7, 9], a, 32)
+        assert rec[0].n_ops == 0 and rec[0].src_index == 7 and rec[0].cut_x1 < rec[0].cut_x0
+        s = rec[1]
+        assert (s.src_index, s.crop_top, s.crop_left, s.flip, s.n_ops) == (9, a[1].crop_top, a[1].crop_left, int(a[1].flip), 3)
+        assert (s.cut_x0, s.cut_y0, s.cut_x1, s.cut_y1) == tuple(int(v) for v in b[1].cutout)
+        for j, (op, v) in enumerate(b[1].ops):
+            o = s.ops[j]
+            assert o.op == op
+            if op in (A.BRIGHTNESS, A.COLOR, A.CONTRAST, A.SHARPNESS):
+                assert o.alpha == float(np.float32(v))
+            elif op == A.POSTERIZE:
+                assert o.ival == max(1, int(v))
+            elif op == A.SOLARIZE:
+                assert o.ival == math.ceil(v) and all((i < v) == (i < o.ival) for i in range(257))
+            elif op in (A.ROTATE, A.SHEAR_X, A.SHEAR_Y, A.TRANSLATE_X, A.TRANSLATE_Y):
+                m = A.op_matrix(op, v, 32, 32)
+                assert (o.identity == 1) if m is None else list(o.a) == [float(t) for t in m]
+    # no-colour list of RandAugment(exclude_color_aug=True) (randaugment.py:176-193)
+    random.seed(3)
+    assert all(op in (1, 4, 5, 7, 8, 9, 10, 12, 13) for _ in range(50) for op, _v in G.draw_strong(32, 4, exclude_color_aug=True).ops)
+    with pytest.raises(ValueError):
+        G.pack_samples([0], [G.AugDecision(0, 0, False, [(A.SOLARIZE, 300.0)])], 32)
+    with pytest.raises(ValueError):
+        G.pack_samples([0], [G.AugDecision(0, 0, False, [(A.IDENTITY, 0.0)] * 4)], 32)
