@@ -493,7 +493,10 @@ int srw_scale_inplace(float* x, int64_t n, const float* scale, void* stream);
 
 /* ---- fused SSL epilogue (the a6-a12 rows of SURVEY.md §8a) ---------------------------------------------------- */
 /* Rewarder.forward (semireward.py:52-72): reward[b] in (0,1), one CTA, softmax over the 2B rows done on chip.
- * rp = 17 device pointers in Rewarder.state_dict order. */
+ * rp = 17 device pointers in Rewarder.state_dict order.
+ * Deliberate divergence: a label outside [0, label_rows) is CLAMPED into range in every Rewarder kernel (forward, training step,
+ * fused SSL loss), where the reference's nn.Embedding / F.one_hot would raise a device-side assert (semireward.py:56,136); the
+ * Generator's relu(...).long() output is unbounded in principle (0 at initialisation, never trained, semireward.py:21-24). */
 typedef struct {
   int B, feature_dim, label_rows;
   const float* const* rp;
