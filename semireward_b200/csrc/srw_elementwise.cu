@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(256) colsum_planes_kernel(const __nv_bfloat16*
   const int r_begin = blockIdx.y * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (c < cols) {
+#pragma unroll 4   // eight 16-byte loads in flight per lane; the sums keep their row order
     for (int r = r_begin + warp; r < r_end; r += 8) {
       const uint4 h = *reinterpret_cast<const uint4*>(planes + (int64_t)r * ldp + c);
       const uint4 l = *reinterpret_cast<const uint4*>(planes + (int64_t)r * ldp + c + ps);
@@ -462,6 +463,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const float* __r
     pg[j] = pb[j] = pc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     gm[j] = *reinterpret_cast<const float4*>(gamma + j * 128 + lane * 4);
   }
+#pragma unroll 2   // a warp walks ~2 rows (4112 rows over 256 x 8 warps): both rows' loads go out together
   for (int row = blockIdx.x * 8 + warp; row < rows; row += 8 * gridDim.x) {
     const float mu = mean[row], rs = rstd[row];
     const float* dyr = dy + (int64_t)row * lddy;
