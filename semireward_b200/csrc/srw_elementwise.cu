@@ -139,6 +139,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int split, in
     const int64_t e = i * 4;
     const int m = (int)(e / N), n = (int)(e % N);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
     for (int s = 0; s < split; ++s) {
       const float4 v = *reinterpret_cast<const float4*>(ws + (int64_t)s * M * N + e);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -190,8 +191,10 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
   const int c = blockIdx.x * 32 + tx;
   const float* src = partial + blockIdx.y * stride_y;
   float acc = 0.f;
-  if (c < cols)
+  if (c < cols) {
+#pragma unroll 4
     for (int p = ty; p < nparts; p += 8) acc += src[(int64_t)p * stride_p + c];
+  }
   red[ty][tx] = acc;
   __syncthreads();
   if (ty == 0 && c < cols) {
@@ -230,6 +233,7 @@ __global__ void __launch_bounds__(256) grad_fold_kernel(const __grid_constant__ 
       const int64_t e = i * 4;
       const int m = (int)(e / a.N), n = (int)(e % a.N);
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4   // four slices' loads in flight, added in slice order
       for (int s = 0; s < a.split_k; ++s) {
         const float4 v = *reinterpret_cast<const float4*>(a.workspace + (int64_t)s * MN + e);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -247,8 +251,10 @@ __global__ void __launch_bounds__(256) grad_fold_kernel(const __grid_constant__ 
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = local * 32 + tx;
     float acc = 0.f;
-    if (c < a.cols)
+    if (c < a.cols) {
+#pragma unroll 4
       for (int p = ty; p < a.nparts; p += 8) acc += a.partial[(int64_t)p * a.stride_p + c];
+    }
     red[ty][tx] = acc;
     __syncthreads();
     if (ty == 0 && c < a.cols) {
