@@ -22,8 +22,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+MEAN = [x / 255 for x in [129.3, 124.1, 112.4]]     # cifar.py:18-21
+STD = [x / 255 for x in [68.2, 65.4, 70.4]]
+
+
 def host_pipeline(size=32):
-    """The reference's transform_strong rebuilt from the same library calls (torchvision transforms + PIL ops in RandAugment order)."""
+    """CPU baseline leg (the only part of this script that touches oracle/ and tests/): the reference's transform_strong rebuilt from
+    the same library calls (torchvision transforms + PIL ops in RandAugment order)."""
     from PIL import Image
     from torchvision import transforms
     from oracle import augment_oracle as A
@@ -52,13 +57,12 @@ def main():
     ap.add_argument("--size", type=int, default=32)
     ap.add_argument("--cpu-images", type=int, default=2000)
     a = ap.parse_args()
-    from oracle import augment_oracle as A
     from semireward_b200 import _lib as L
     from semireward_b200.datasets import gpu_augment as G
     S = a.size
     rng = np.random.default_rng(0)
     data = rng.integers(0, 256, (50000, S, S, 3), dtype=np.uint8)
-    pipe = G.DeviceImagePipeline(data, A.CIFAR100_MEAN, A.CIFAR100_STD)
+    pipe = G.DeviceImagePipeline(data, MEAN, STD)
     torch.manual_seed(0); random.seed(0); np.random.seed(0)
     n = a.batch
     idx = rng.integers(0, 50000, n).tolist()
