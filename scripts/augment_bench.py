@@ -75,6 +75,16 @@ def main():
         pipe.weak_and_strong(idx)
     torch.cuda.synchronize()
     e2e = 5 * 2 * n / (time.perf_counter() - t0)
+    # ---- the same with the decisions drawn in bulk (draw_records: same distributions, one numpy Generator) ----
+    g = np.random.default_rng(0)
+    for _ in range(3):
+        pipe.weak_and_strong_fast(idx, g)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        pipe.weak_and_strong_fast(idx, g)
+    torch.cuda.synchronize()
+    e2e_fast = 5 * 2 * n / (time.perf_counter() - t0)
     # ---- kernel only: records resident ----
     decs = [G.draw_strong(S, pipe.padding) for _ in idx]
     recs = pipe._upload(G.pack_samples(idx, decs, S))
@@ -114,7 +124,7 @@ def main():
                       "device_kernel_images_per_s": n / (ms * 1e-3), "kernel_ms": ms,
                       "roofline": {"bound": "hbm", "achieved": bytes_alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                    "frac": (bytes_alg / (ms * 1e-3) / 1e9 / peak) if peak else None, "bytes_per_pixel": 15},
-                      "device_e2e_images_per_s": e2e, "host_pipeline_images_per_s_1core": cpu, "host_sample_images": 2 * m}))
+                      "device_e2e_images_per_s": e2e, "device_e2e_bulk_draw_images_per_s": e2e_fast, "host_pipeline_images_per_s_1core": cpu, "host_sample_images": 2 * m}))
 
 
 if __name__ == "__main__":

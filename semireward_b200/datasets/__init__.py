@@ -1,2 +1,3 @@
 """Input side of the hot path: the reference's per-sample PIL transforms as one device kernel."""
-from .gpu_augment import AugDecision, DeviceImagePipeline, DeviceSSLLoader, draw_strong, draw_weak  # noqa: F401
+from .gpu_augment import (SAMPLE_DTYPE, AugDecision, DeviceImagePipeline, DeviceSSLLoader, draw_records, draw_strong, draw_weak,  # noqa: F401
+                          pack_arrays, records_from_decisions)

@@ -145,6 +145,96 @@ def pack_samples(indices: Sequence[int], decisions: Sequence[AugDecision], size:
     return arr
 
 
+# numpy mirror of srw_aug_op_desc / srw_aug_sample (include/srw.h): every field naturally aligned, so the packed dtype IS the C layout
+OP_DTYPE = np.dtype([("op", "<i4"), ("ival", "<i4"), ("alpha", "<f4"), ("identity", "<i4"), ("a", "<f8", (6,))])
+SAMPLE_DTYPE = np.dtype([("src_index", "<i8"), ("crop_top", "<i4"), ("crop_left", "<i4"), ("flip", "<i4"), ("n_ops", "<i4"),
+                         ("ops", OP_DTYPE, (3,)), ("cut", "<i4", (4,))])
+assert OP_DTYPE.itemsize == C.sizeof(L.AugOpDesc) and SAMPLE_DTYPE.itemsize == C.sizeof(L.AugSample)
+
+
+def records_from_decisions(indices: Sequence[int], decisions: Sequence[AugDecision], size: int) -> np.ndarray:
+    """pack_samples as a numpy structured array (same bytes)."""
+    return np.frombuffer(bytes(memoryview(pack_samples(indices, decisions, size)).cast("B")), dtype=SAMPLE_DTYPE).copy()
+
+
+def pack_arrays(idx, top, left, flip, ops=None, val=None, cut=None, size: int = 32) -> np.ndarray:
+    """pack_samples over arrays: idx / top / left / flip [n]; ops int [n, k <= 3] and val float64 [n, k] (None = weak); cut float64
+    [n, 4] = CutoutAbs' xy with NaN rows for "no Cutout".  Field for field what pack_samples writes (tests compare the bytes)."""
+    idx = np.asarray(idx, dtype=np.int64)
+    n = idx.shape[0]
+    rec = np.zeros(n, dtype=SAMPLE_DTYPE)
+    rec["src_index"] = idx
+    rec["crop_top"], rec["crop_left"], rec["flip"] = top, left, flip
+    rec["cut"][:, 2:] = -1
+    if ops is None:
+        return rec
+    ops = np.asarray(ops, dtype=np.int64)
+    val = np.asarray(val, dtype=np.float64)
+    k = ops.shape[1]
+    if k > 3:
+        raise ValueError("srw_aug_sample holds at most 3 ops (RandAugment(3, 5))")
+    enh = np.isin(ops, (BRIGHTNESS, COLOR, CONTRAST, SHARPNESS))
+    if (val[enh] < 0).any() or (val[ops == SOLARIZE] < 0).any() or (val[ops == SOLARIZE] > 256).any() or (val[ops == POSTERIZE] >= 9).any():
+        raise ValueError("op magnitude outside the range the reference asserts (randaugment.py:21-59,114)")
+    rec["n_ops"] = k
+    o = rec["ops"][:, :k]
+    o["op"] = ops
+    o["alpha"] = np.where(enh, val, 0.0).astype(np.float32)
+    o["ival"] = np.where(ops == POSTERIZE, np.maximum(1, val.astype(np.int64)), np.where(ops == SOLARIZE, np.ceil(val).astype(np.int64), 0))
+    a = np.zeros((n, k, 6), dtype=np.float64)
+    aff = np.isin(ops, (SHEAR_X, SHEAR_Y, TRANSLATE_X, TRANSLATE_Y))
+    a[aff, 0] = 1.0
+    a[aff, 4] = 1.0
+    a[ops == SHEAR_X, 1] = val[ops == SHEAR_X]
+    a[ops == SHEAR_Y, 3] = val[ops == SHEAR_Y]
+    a[ops == TRANSLATE_X, 2] = val[ops == TRANSLATE_X] * size
+    a[ops == TRANSLATE_Y, 5] = val[ops == TRANSLATE_Y] * size
+    ident = np.zeros((n, k), dtype=np.int32)
+    for i, j in zip(*np.nonzero(ops == ROTATE)):          # Python floats, as Image.rotate computes them (round(cos, 15) ...)
+        m = _affine_coefficients(ROTATE, float(val[i, j]), size)
+        if m is None:
+            ident[i, j] = 1
+        else:
+            a[i, j] = m
+    geo = np.isin(ops, (ROTATE, SHEAR_X, SHEAR_Y, TRANSLATE_X, TRANSLATE_Y)) & (ident == 0)
+    for x, y in ((0, 0), (size, size), (0, size), (size, 0)):   # libImaging's fixed-point range check
+        bad = geo & ~((np.abs(x * a[..., 0] + y * a[..., 1] + a[..., 2]) < 32768.0) & (np.abs(x * a[..., 3] + y * a[..., 4] + a[..., 5]) < 32768.0))
+        if bad.any():
+            raise ValueError("affine coefficients outside the fixed-point range of Image.transform")
+    o["a"] = a
+    o["identity"] = ident
+    if cut is not None:
+        cut = np.asarray(cut, dtype=np.float64)
+        has = ~np.isnan(cut[:, 0])
+        rec["cut"] = np.where(has[:, None], np.nan_to_num(cut).astype(np.int64), np.array([0, 0, -1, -1]))   # ImageDraw truncates the corners
+    return rec
+
+
+def draw_records(indices, size: int, padding: int, strong: bool, rng: np.random.Generator, n_ops: int = 3) -> np.ndarray:
+    """Bulk drawing for throughput: the SAME distributions as draw_weak / draw_strong (RandomCrop.get_params, RandomHorizontalFlip,
+    RandAugment.__call__, CutoutAbs) from one numpy Generator, vectorised over the batch — not the reference's generator streams, so a
+    run is not seed-for-seed the reference's; every record is still transformed exactly as Pillow would transform that decision
+    (pack_arrays forms the per-op parameters like pack_samples; Image.rotate's coefficients go through the same Python floats)."""
+    idx = np.asarray(indices, dtype=np.int64)
+    n = idx.shape[0]
+    top = rng.integers(0, 2 * padding + 1, n) if padding > 0 else np.zeros(n, dtype=np.int64)
+    left = rng.integers(0, 2 * padding + 1, n) if padding > 0 else np.zeros(n, dtype=np.int64)
+    flip = rng.random(n) < 0.5
+    if not strong:
+        return pack_arrays(idx, top, left, flip, size=size)
+    ops = rng.integers(0, 14, (n, n_ops))
+    lo = np.array([r[0] for r in _RANGE], dtype=np.float64)[ops]
+    hi = np.array([r[1] for r in _RANGE], dtype=np.float64)[ops]
+    val = lo + (hi - lo) * rng.random((n, n_ops))
+    # Cutout: v = U[0, 0.5) * size; corner = int(max(0, U[0, size) - v / 2)); far corner = min(size, corner + v)
+    v = rng.random(n) * 0.5 * size
+    x0 = np.maximum(0.0, rng.random(n) * size - v / 2.0).astype(np.int64).astype(np.float64)
+    y0 = np.maximum(0.0, rng.random(n) * size - v / 2.0).astype(np.int64).astype(np.float64)
+    cut = np.stack([x0, y0, np.minimum(float(size), x0 + v), np.minimum(float(size), y0 + v)], axis=1)
+    cut[v <= 0.0] = np.nan
+    return pack_arrays(idx, top, left, flip, ops, val, cut, size)
+
+
 class DeviceImagePipeline:
     """The dataset's uint8 HWC array resident on the device + the two transforms of get_cifar as one kernel launch per batch."""
 
@@ -199,6 +289,42 @@ class DeviceImagePipeline:
         L.check(self.lib.srw_augment_batch(C.byref(a), L.stream_ptr()), "srw_augment_batch")
         recs.record_stream(torch.cuda.current_stream())
         return (out, u8) if return_u8 else out
+
+    def transform_records(self, rec: np.ndarray, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Same launch as transform() from a SAMPLE_DTYPE array (records_from_decisions / draw_records)."""
+        if rec.dtype != SAMPLE_DTYPE or rec.ndim != 1 or rec.shape[0] == 0:
+            raise ValueError("expected a non-empty 1-D SAMPLE_DTYPE array")
+        if rec["src_index"].min() < 0 or rec["src_index"].max() >= self.data.shape[0]:
+            raise IndexError("sample index outside the dataset")
+        if rec["crop_top"].min() < 0 or rec["crop_top"].max() > 2 * self.padding or rec["crop_left"].min() < 0 or rec["crop_left"].max() > 2 * self.padding:
+            raise ValueError("crop offset outside the padded image")
+        n, S = int(rec.shape[0]), self.size
+        raw = torch.from_numpy(np.ascontiguousarray(rec).view(np.uint8))
+        if getattr(self, "_stage_event", None) is not None:
+            self._stage_event.synchronize()
+        if self._stage is None or self._stage.numel() < raw.numel():
+            self._stage = torch.empty(max(raw.numel(), 64 * SAMPLE_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
+        host = self._stage[:raw.numel()]
+        host.copy_(raw)
+        recs = torch.empty(raw.numel(), dtype=torch.uint8, device=self.data.device)
+        recs.copy_(host, non_blocking=True)
+        self._stage_event = torch.cuda.Event()
+        self._stage_event.record()
+        if out is None:
+            out = torch.empty(n, 3, S, S, dtype=torch.float32, device=self.data.device)
+        assert out.is_contiguous() and out.shape == (n, 3, S, S) and out.dtype == torch.float32
+        a = L.AugmentArgs(src=L.ptr(self.data), n_src=self.data.shape[0], img_size=S, padding=self.padding, samples=L.ptr(recs), n=n,
+                          mean=(L.f32 * 3)(*self.mean), std=(L.f32 * 3)(*self.std), out=L.ptr(out), out_u8=None)
+        L.check(self.lib.srw_augment_batch(C.byref(a), L.stream_ptr()), "srw_augment_batch")
+        recs.record_stream(torch.cuda.current_stream())
+        return out
+
+    def weak_and_strong_fast(self, indices: Sequence[int], rng: np.random.Generator) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Both views of every sample in one launch, decisions drawn in bulk (draw_records): the throughput route."""
+        idx = np.asarray(indices, dtype=np.int64)
+        rec = np.concatenate([draw_records(idx, self.size, self.padding, False, rng), draw_records(idx, self.size, self.padding, True, rng)])
+        both = self.transform_records(rec)
+        return both[:idx.shape[0]], both[idx.shape[0]:]
 
     def val(self, indices: Sequence[int]) -> torch.Tensor:
         """transform_val (cifar.py:51-55): Resize (identity) -> ToTensor -> Normalize; nothing random."""

@@ -157,3 +157,28 @@ def test_val_transform_and_train_steps_from_the_raw_dataset():
         torch.cuda.synchronize()
         assert abs(alg.log_dict["train/total_loss"] - float(rec["total_loss"])) < 1e-3
         assert torch.equal(alg._last_mask.cpu(), rec["mask"]) and torch.equal(alg._last_pseudo_label.cpu(), rec["pseudo"])
+
+
+def test_record_array_route_equals_the_per_sample_route():
+    """transform_records (numpy records, the throughput route) launches the same kernel on the same bytes as transform()."""
+    from semireward_b200.datasets import draw_records, records_from_decisions
+    rng = np.random.default_rng(33)
+    imgs = _images(rng, 24, 32)
+    pipe = _pipe(imgs)
+    idx = [int(i) for i in rng.integers(0, 24, 96)]
+    torch.manual_seed(2); random.seed(2); np.random.seed(2)
+    decs = [A.draw_strong(32, 4) for _ in idx]
+    prod = [_to_product(d) for d in decs]
+    a = pipe.transform(idx, prod).cpu().numpy()
+    b = pipe.transform_records(records_from_decisions(idx, prod, 32)).cpu().numpy()
+    assert np.array_equal(a, b)
+    for k, (i, d) in enumerate(zip(idx, decs)):
+        assert np.array_equal(b[k], A.transform(imgs[i], d, 4, A.CIFAR100_MEAN, A.CIFAR100_STD))
+    # bulk-drawn records: a finite, normalised batch of the right shape for both views
+    w, s = pipe.weak_and_strong_fast(idx, np.random.default_rng(5))
+    assert w.shape == s.shape == (96, 3, 32, 32) and torch.isfinite(w).all() and torch.isfinite(s).all()
+    rec = draw_records(idx, 32, 4, False, np.random.default_rng(6))
+    got = pipe.transform_records(rec).cpu().numpy()
+    for k in range(8):
+        d = A.Decision(int(rec["crop_top"][k]), int(rec["crop_left"][k]), bool(rec["flip"][k]))
+        assert np.array_equal(got[k], A.transform(imgs[idx[k]], d, 4, A.CIFAR100_MEAN, A.CIFAR100_STD))

@@ -204,3 +204,53 @@ def test_host_records_carry_what_pillows_python_layer_computes():
         G.pack_samples([0], [G.AugDecision(0, 0, False, [(A.SOLARIZE, 300.0)])], 32)
     with pytest.raises(ValueError):
         G.pack_samples([0], [G.AugDecision(0, 0, False, [(A.IDENTITY, 0.0)] * 4)], 32)
+
+
+def test_vectorised_records_equal_the_per_sample_packing_byte_for_byte():
+    """pack_arrays / draw_records (the throughput route of the input pipeline) against pack_samples, the route the GPU parity tests
+    validate: same bytes for the same decisions, every op, degenerate magnitudes included; layout of the numpy mirror == ctypes."""
+    import ctypes as C
+    from semireward_b200 import _lib as L
+    from semireward_b200.datasets import gpu_augment as G
+    for name in G.SAMPLE_DTYPE.names:
+        assert G.SAMPLE_DTYPE.fields[name][1] == getattr(L.AugSample, {"cut": "cut_x0"}.get(name, name)).offset, name
+    for name in G.OP_DTYPE.names:
+        assert G.OP_DTYPE.fields[name][1] == getattr(L.AugOpDesc, name).offset, name
+    assert G.SAMPLE_DTYPE.itemsize == C.sizeof(L.AugSample) == 232
+    rng = np.random.default_rng(12)
+    for size, pad in ((32, 4), (96, 12)):
+        n = 600
+        idx = rng.integers(0, 1000, n)
+        top, left, flip = rng.integers(0, 2 * pad + 1, n), rng.integers(0, 2 * pad + 1, n), rng.random(n) < 0.5
+        ops = rng.integers(0, 14, (n, 3))
+        lo = np.array([r[0] for r in A.OP_RANGE], dtype=np.float64)[ops]
+        hi = np.array([r[1] for r in A.OP_RANGE], dtype=np.float64)[ops]
+        val = lo + (hi - lo) * rng.random((n, 3))
+        val[:14, 0], ops[:14, 0] = lo[:14, 0] * 0 + np.array([r[0] for r in A.OP_RANGE]), np.arange(14)      # every op at its lower end
+        val[14, :], ops[14, :] = [360.0, -720.0, 0.0], [A.ROTATE] * 3                                        # rotations Image.rotate copies
+        v = rng.random(n) * 0.5 * size
+        x0 = np.maximum(0.0, rng.random(n) * size - v / 2).astype(np.int64).astype(np.float64)
+        y0 = np.maximum(0.0, rng.random(n) * size - v / 2).astype(np.int64).astype(np.float64)
+        cut = np.stack([x0, y0, np.minimum(float(size), x0 + v), np.minimum(float(size), y0 + v)], axis=1)
+        cut[::7] = np.nan
+        decs = [G.AugDecision(int(top[i]), int(left[i]), bool(flip[i]), [(int(o), float(x)) for o, x in zip(ops[i], val[i])],
+                              None if np.isnan(cut[i, 0]) else tuple(float(c) for c in cut[i])) for i in range(n)]
+        want = G.records_from_decisions(idx, decs, size)
+        got = G.pack_arrays(idx, top, left, flip, ops, val, cut, size)
+        assert got.tobytes() == want.tobytes()
+        weak = [G.AugDecision(int(top[i]), int(left[i]), bool(flip[i])) for i in range(n)]
+        assert G.pack_arrays(idx, top, left, flip, size=size).tobytes() == G.records_from_decisions(idx, weak, size).tobytes()
+    # the bulk drawer: distributions of RandAugment(3, 5) / RandomCrop / flip / Cutout
+    rec = G.draw_records(np.arange(20000) % 500, 32, 4, True, np.random.default_rng(1))
+    assert rec["n_ops"].min() == 3 and set(np.unique(rec["ops"]["op"])) == set(range(14))
+    assert abs(rec["flip"].mean() - 0.5) < 0.02 and rec["crop_top"].min() == 0 and rec["crop_top"].max() == 8 and abs(rec["crop_left"].mean() - 4) < 0.1
+    counts = np.bincount(rec["ops"]["op"].ravel(), minlength=14) / rec["ops"]["op"].size
+    assert np.abs(counts - 1 / 14).max() < 0.01
+    w = rec["cut"][:, 2] - rec["cut"][:, 0]
+    assert w.min() >= 0 and w.max() <= 16 and rec["cut"][:, 2].max() <= 32
+    post = rec["ops"]["ival"][rec["ops"]["op"] == A.POSTERIZE]
+    assert set(np.unique(post)) == {4, 5, 6, 7}
+    weak = G.draw_records(np.arange(100), 32, 4, False, np.random.default_rng(2))
+    assert weak["n_ops"].max() == 0 and (weak["cut"][:, 2] < weak["cut"][:, 0]).all()
+    with pytest.raises(ValueError):
+        G.pack_arrays([0], [0], [0], [False], np.array([[A.SOLARIZE]]), np.array([[300.0]]), None, 32)
