@@ -254,3 +254,42 @@ def test_vectorised_records_equal_the_per_sample_packing_byte_for_byte():
     assert weak["n_ops"].max() == 0 and (weak["cut"][:, 2] < weak["cut"][:, 0]).all()
     with pytest.raises(ValueError):
         G.pack_arrays([0], [0], [0], [False], np.array([[A.SOLARIZE]]), np.array([[300.0]]), None, 32)
+
+
+def test_loader_glue_on_a_stub_pipeline():
+    """DeviceSSLLoader's host glue without a device: batch keys, shapes, targets gather and which pipeline entry points each route
+    calls (per-sample reference streams vs bulk records)."""
+    from semireward_b200.datasets import gpu_augment as G
+
+    class Stub:
+        size, padding = 32, 4
+
+        def __init__(self):
+            self.data = torch.zeros(50, 32, 32, 3, dtype=torch.uint8)
+            self.calls = []
+
+        def weak(self, idx):
+            self.calls.append(("weak", len(idx)))
+            return torch.zeros(len(idx), 3, 32, 32)
+
+        def weak_and_strong(self, idx):
+            self.calls.append(("weak_and_strong", len(idx)))
+            return torch.zeros(len(idx), 3, 32, 32), torch.ones(len(idx), 3, 32, 32)
+
+        def transform_records(self, rec):
+            assert rec.dtype == G.SAMPLE_DTYPE and rec["n_ops"].max() == 0
+            self.calls.append(("records", len(rec)))
+            return torch.zeros(len(rec), 3, 32, 32)
+
+        def weak_and_strong_fast(self, idx, rng):
+            self.calls.append(("fast", len(idx)))
+            return torch.zeros(len(idx), 3, 32, 32), torch.ones(len(idx), 3, 32, 32)
+    targets = np.arange(50) % 7
+    for rng, want in ((None, [("weak", 4)], ), (np.random.default_rng(0), [("records", 4)])):
+        lb, ulb = Stub(), Stub()
+        out = list(G.DeviceSSLLoader(lb, targets, ulb, [[3, 9, 1, 1], [4, 5, 6, 7]], [[0, 1, 2, 3, 4, 5, 6, 7], [8, 9, 10, 11, 12, 13, 14, 15]], bulk_rng=rng))
+        assert len(out) == 2 and lb.calls == want * 2 and ulb.calls == [("fast" if rng is not None else "weak_and_strong", 8)] * 2
+        d_lb, d_ulb = out[0]
+        assert set(d_lb) == {"idx_lb", "x_lb", "y_lb"} and set(d_ulb) == {"idx_ulb", "x_ulb_w", "x_ulb_s"}
+        assert d_lb["y_lb"].tolist() == [3, 2, 1, 1] and d_lb["idx_lb"].tolist() == [3, 9, 1, 1] and d_ulb["idx_ulb"].tolist() == list(range(8))
+        assert d_ulb["x_ulb_s"].shape == (8, 3, 32, 32) and d_lb["x_lb"].shape == (4, 3, 32, 32)
